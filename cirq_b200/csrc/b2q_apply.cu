@@ -1,0 +1,712 @@
+// Gate application on a dense state vector: psi <- (M on target bits) psi.
+//
+// Replaces (reference, cirq-core/cirq/): linalg/transformations.py:105-172
+// (targeted_left_multiply, one np.einsum over the whole state), :310-380
+// (apply_matrix_to_slices) and the per-gate slice tricks of ops/*.py, as
+// reached from protocols/apply_unitary_protocol.py:440-466.
+//
+// Design: every gate is ONE in-place streaming pass.
+// A warp owns a "zone" of 512 contiguous bytes (the low 6 bits of the index for
+// complex64, 5 for complex128) times 2^h strided copies of it, one per
+// combination of the h register-resident high bits.  Each lane moves 16 bytes
+// per access, so every global load/store instruction of a warp covers 512
+// contiguous bytes regardless of which qubits the gate acts on:
+//   * target bits above the zone   -> different registers of the same thread
+//     (coalesced strided copies),
+//   * target bit 0 (complex64)     -> the two halves of the 16-byte vector,
+//   * target bits inside the zone  -> exchanged with a spare register bit by a
+//     warp-shuffle butterfly before the multiply and back after it.
+// After the exchange every thread holds complete 2^k-amplitude groups in
+// registers; the matrix sits in the kernel parameter (constant) bank so the
+// FMAs take it as a direct operand: no shared memory, no barriers.
+#include "b2q_common.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace b2q {
+
+constexpr int kMaxRegBits = 6;
+constexpr int kMaxIns = 6;
+constexpr int kFastThreads = 256;
+
+template <typename real, int K>
+struct FastParams {
+  typename Cplx<real>::type* state;
+  uint64_t num_items;               // warp-items (one 512-byte zone x 2^h copies each)
+  int n_ins;                        // number of register-resident high bits
+  int ins_pos[kMaxIns];             // their positions, ascending
+  long long reg_off[kMaxRegBits];   // element offset contributed by each register bit
+  int swap_lane[kMaxRegBits];       // per target slot: lane bit to exchange with, or -1
+  real mat[2 << (2 * K)];           // row-major (re, im), index bit i <-> i-th lowest target
+};
+
+template <typename real, int K>
+struct SmallParams {
+  typename Cplx<real>::type* state;
+  uint64_t num_groups;
+  int tpos[K];  // ascending
+  real mat[2 << (2 * K)];
+};
+
+
+// 16-byte global accesses.  `volatile` keeps the loads of a thread grouped in
+// program order ahead of the arithmetic so all of them are in flight at once.
+__device__ __forceinline__ float4 ldg16(const float2* p) {
+  float4 v;
+  asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double2 ldg16(const double2* p) {
+  double2 v;
+  asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg16(float2* p, const float4& v) {
+  asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void stg16(double2* p, const double2& v) {
+  asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+template <typename C>
+__device__ __forceinline__ C shfl_xor_c(const C& v, int mask);
+template <>
+__device__ __forceinline__ float2 shfl_xor_c<float2>(const float2& v, int mask) {
+  float2 r;
+  r.x = __shfl_xor_sync(0xffffffffu, v.x, mask);
+  r.y = __shfl_xor_sync(0xffffffffu, v.y, mask);
+  return r;
+}
+template <>
+__device__ __forceinline__ double2 shfl_xor_c<double2>(const double2& v, int mask) {
+  double2 r;
+  r.x = __shfl_xor_sync(0xffffffffu, v.x, mask);
+  r.y = __shfl_xor_sync(0xffffffffu, v.y, mask);
+  return r;
+}
+
+// Exchanges register bit RBIT with lane bit `lbit` across the warp: afterwards
+// register bit RBIT of a thread enumerates what used to be lane bit `lbit`.
+template <int RBIT, int NR, typename C>
+__device__ __forceinline__ void swap_bit(C (&x)[NR], int lbit, int lane) {
+  const bool hi = (lane >> lbit) & 1;
+  const int mask = 1 << lbit;
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    if (i & (1 << RBIT)) continue;
+    const int i0 = i, i1 = i | (1 << RBIT);
+    C send = hi ? x[i0] : x[i1];
+    C recv = shfl_xor_c<C>(send, mask);
+    if (hi) {
+      x[i0] = recv;
+    } else {
+      x[i1] = recv;
+    }
+  }
+}
+
+template <int K, int NR, typename C>
+__device__ __forceinline__ void swap_all(C (&x)[NR], const int* swap_lane, int lane) {
+  // Target slots are register bits 0..K-1 in the S=0 layout.
+  if constexpr (K >= 1) {
+    if (swap_lane[0] >= 0) swap_bit<0>(x, swap_lane[0], lane);
+  }
+  if constexpr (K >= 2) {
+    if (swap_lane[1] >= 0) swap_bit<1>(x, swap_lane[1], lane);
+  }
+  if constexpr (K >= 3) {
+    if (swap_lane[2] >= 0) swap_bit<2>(x, swap_lane[2], lane);
+  }
+  if constexpr (K >= 4) {
+    if (swap_lane[3] >= 0) swap_bit<3>(x, swap_lane[3], lane);
+  }
+  if constexpr (K >= 5) {
+    if (swap_lane[4] >= 0) swap_bit<4>(x, swap_lane[4], lane);
+  }
+}
+
+// Register index layout: [GT group bits][K target slots][S low group bit].
+// complex64: register bit 0 is always the 16-byte vector bit (index bit 0).
+template <typename real, int K, int S, int GT, bool SWAPS>
+__global__ void __launch_bounds__(kFastThreads)
+    sv_apply_fast_kernel(const __grid_constant__ FastParams<real, K> p) {
+  using C = typename Cplx<real>::type;
+  constexpr bool kVec = sizeof(real) == 4;
+  constexpr int RB = S + K + GT;
+  constexpr int NR = 1 << RB;
+  constexpr int DIM = 1 << K;
+  constexpr int ZB = kVec ? 6 : 5;
+  static_assert(!(SWAPS && S), "lane exchanges only exist in the S=0 layout");
+  static_assert(kVec || S == 0, "complex128 has no vector bit");
+
+  const int lane = threadIdx.x & 31;
+  const uint64_t item =
+      (uint64_t)blockIdx.x * (kFastThreads / 32) + (uint64_t)(threadIdx.x >> 5);
+  if (item >= p.num_items) return;
+  uint64_t base = insert_zero_bits(item << ZB, p.ins_pos, p.n_ins);
+  base += kVec ? (uint64_t)(lane << 1) : (uint64_t)lane;
+  C* __restrict__ ptr = p.state + base;
+
+  C x[NR];
+  if constexpr (kVec) {
+#pragma unroll
+    for (int i = 0; i < NR / 2; ++i) {
+      long long off = 0;
+#pragma unroll
+      for (int b = 0; b < RB - 1; ++b)
+        if ((i >> b) & 1) off += p.reg_off[b + 1];
+      const float4 v = ldg16(ptr + off);
+      x[2 * i] = make_float2(v.x, v.y);
+      x[2 * i + 1] = make_float2(v.z, v.w);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      long long off = 0;
+#pragma unroll
+      for (int b = 0; b < RB; ++b)
+        if ((i >> b) & 1) off += p.reg_off[b];
+      x[i] = ldg16(ptr + off);
+    }
+  }
+
+  if constexpr (SWAPS) swap_all<K>(x, p.swap_lane, lane);
+
+  if constexpr (SWAPS) {
+    C y[NR];
+#pragma unroll
+    for (int g = 0; g < (1 << GT); ++g) {
+#pragma unroll
+      for (int r = 0; r < DIM; ++r) {
+        C acc = make_c<real>(0, 0);
+#pragma unroll
+        for (int c = 0; c < DIM; ++c)
+          cmac<real>(acc, p.mat[2 * (r * DIM + c)], p.mat[2 * (r * DIM + c) + 1],
+                     x[(g << K) | c]);
+        y[(g << K) | r] = acc;
+      }
+    }
+    swap_all<K>(y, p.swap_lane, lane);
+    if constexpr (kVec) {
+#pragma unroll
+      for (int i = 0; i < NR / 2; ++i) {
+        long long off = 0;
+#pragma unroll
+        for (int b = 0; b < RB - 1; ++b)
+          if ((i >> b) & 1) off += p.reg_off[b + 1];
+        stg16(ptr + off, make_float4(y[2 * i].x, y[2 * i].y, y[2 * i + 1].x, y[2 * i + 1].y));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        long long off = 0;
+#pragma unroll
+        for (int b = 0; b < RB; ++b)
+          if ((i >> b) & 1) off += p.reg_off[b];
+        stg16(ptr + off, y[i]);
+      }
+    }
+  } else if constexpr (kVec && S == 1) {
+    // Vector bit is a group bit: rows r for both halves form one 16-byte store.
+#pragma unroll
+    for (int g = 0; g < (1 << GT); ++g) {
+#pragma unroll
+      for (int r = 0; r < DIM; ++r) {
+        C a0 = make_c<real>(0, 0), a1 = make_c<real>(0, 0);
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) {
+          const real mr = p.mat[2 * (r * DIM + c)], mi = p.mat[2 * (r * DIM + c) + 1];
+          cmac<real>(a0, mr, mi, x[(((g << K) | c) << 1)]);
+          cmac<real>(a1, mr, mi, x[(((g << K) | c) << 1) | 1]);
+        }
+        const int i = (g << K) | r;  // index over register bits 1..RB-1
+        long long off = 0;
+#pragma unroll
+        for (int b = 0; b < RB - 1; ++b)
+          if ((i >> b) & 1) off += p.reg_off[b + 1];
+        stg16(ptr + off, make_float4(a0.x, a0.y, a1.x, a1.y));
+      }
+    }
+  } else if constexpr (kVec) {
+    // S == 0, vector bit is target slot 0: rows (2i, 2i+1) form one store.
+#pragma unroll
+    for (int g = 0; g < (1 << GT); ++g) {
+#pragma unroll
+      for (int r2 = 0; r2 < DIM / 2; ++r2) {
+        C a0 = make_c<real>(0, 0), a1 = make_c<real>(0, 0);
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) {
+          const C xv = x[(g << K) | c];
+          cmac<real>(a0, p.mat[2 * ((2 * r2) * DIM + c)], p.mat[2 * ((2 * r2) * DIM + c) + 1], xv);
+          cmac<real>(a1, p.mat[2 * ((2 * r2 + 1) * DIM + c)],
+                     p.mat[2 * ((2 * r2 + 1) * DIM + c) + 1], xv);
+        }
+        const int i = (g << (K - 1)) | r2;  // index over register bits 1..RB-1
+        long long off = 0;
+#pragma unroll
+        for (int b = 0; b < RB - 1; ++b)
+          if ((i >> b) & 1) off += p.reg_off[b + 1];
+        stg16(ptr + off, make_float4(a0.x, a0.y, a1.x, a1.y));
+      }
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < (1 << GT); ++g) {
+#pragma unroll
+      for (int r = 0; r < DIM; ++r) {
+        C acc = make_c<real>(0, 0);
+#pragma unroll
+        for (int c = 0; c < DIM; ++c)
+          cmac<real>(acc, p.mat[2 * (r * DIM + c)], p.mat[2 * (r * DIM + c) + 1],
+                     x[(g << K) | c]);
+        const int i = (g << K) | r;
+        long long off = 0;
+#pragma unroll
+        for (int b = 0; b < RB; ++b)
+          if ((i >> b) & 1) off += p.reg_off[b];
+        stg16(ptr + off, acc);
+      }
+    }
+  }
+}
+
+// One thread per 2^K-amplitude group; for states too small for the zone layout.
+template <typename real, int K>
+__global__ void __launch_bounds__(128)
+    sv_apply_small_kernel(const __grid_constant__ SmallParams<real, K> p) {
+  using C = typename Cplx<real>::type;
+  constexpr int DIM = 1 << K;
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= p.num_groups) return;
+  const uint64_t base = insert_zero_bits(g, p.tpos, K);
+  C x[DIM];
+#pragma unroll
+  for (int j = 0; j < DIM; ++j) {
+    uint64_t off = 0;
+#pragma unroll
+    for (int b = 0; b < K; ++b)
+      if ((j >> b) & 1) off |= 1ull << p.tpos[b];
+    x[j] = p.state[base | off];
+  }
+#pragma unroll
+  for (int r = 0; r < DIM; ++r) {
+    C acc = make_c<real>(0, 0);
+#pragma unroll
+    for (int c = 0; c < DIM; ++c)
+      cmac<real>(acc, p.mat[2 * (r * DIM + c)], p.mat[2 * (r * DIM + c) + 1], x[c]);
+    uint64_t off = 0;
+#pragma unroll
+    for (int b = 0; b < K; ++b)
+      if ((r >> b) & 1) off |= 1ull << p.tpos[b];
+    p.state[base | off] = acc;
+  }
+}
+
+// Any k <= 10: out[i] = sum_c M[row(i), c] * in[i with target bits := c].
+struct GenericParams {
+  int n;
+  int k;
+  int tpos[16];  // ascending
+};
+
+template <typename real>
+__global__ void __launch_bounds__(256)
+    sv_apply_generic_kernel(const typename Cplx<real>::type* __restrict__ in,
+                            typename Cplx<real>::type* __restrict__ out,
+                            const typename Cplx<real>::type* __restrict__ mat,
+                            const __grid_constant__ GenericParams p) {
+  using C = typename Cplx<real>::type;
+  const uint64_t total = 1ull << p.n;
+  const int dim = 1 << p.k;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t row = 0, mask = 0;
+    for (int b = 0; b < p.k; ++b) {
+      row |= ((i >> p.tpos[b]) & 1ull) << b;
+      mask |= 1ull << p.tpos[b];
+    }
+    const uint64_t base = i & ~mask;
+    C acc = make_c<real>(0, 0);
+    for (int c = 0; c < dim; ++c) {
+      uint64_t off = 0;
+      for (int b = 0; b < p.k; ++b)
+        if ((c >> b) & 1) off |= 1ull << p.tpos[b];
+      const C m = mat[row * dim + c];
+      cmac<real>(acc, m.x, m.y, in[base | off]);
+    }
+    out[i] = acc;
+  }
+}
+
+// psi[i] *= diag[bits of i at targets]
+struct DiagParams {
+  int n;
+  int k;
+  int tpos[16];  // tpos[b] <-> bit b of the table index
+};
+
+template <typename real>
+__global__ void __launch_bounds__(256)
+    sv_apply_diag_kernel(typename Cplx<real>::type* __restrict__ state,
+                         const typename Cplx<real>::type* __restrict__ diag,
+                         const __grid_constant__ DiagParams p) {
+  using C = typename Cplx<real>::type;
+  const uint64_t total = 1ull << p.n;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t v = 0;
+    for (int b = 0; b < p.k; ++b) v |= ((i >> p.tpos[b]) & 1ull) << b;
+    const C d = diag[v];
+    const C a = state[i];
+    state[i] = cmul<real>(d.x, d.y, a);
+  }
+}
+
+// ---- host-side planning -----------------------------------------------------
+
+struct FastPlan {
+  bool feasible = false;
+  int K = 0, S = 0, GT = 0;
+  bool swaps = false;
+  uint64_t num_items = 0;
+  int n_ins = 0;
+  int ins_pos[kMaxIns] = {0};
+  long long reg_off[kMaxRegBits] = {0};
+  int swap_lane[kMaxRegBits] = {-1, -1, -1, -1, -1, -1};
+};
+
+// `sorted` = ascending target bit positions.  Mirrors the layout rules in the
+// header comment; exported through b2q_debug_plan for the host unit tests.
+FastPlan make_fast_plan(int dtype, int n, const int* sorted, int K) {
+  FastPlan pl;
+  pl.K = K;
+  const bool vec = dtype == B2Q_C64;
+  const int ZB = vec ? 6 : 5;
+  const int VB = vec ? 1 : 0;
+  const int max_k = vec ? 5 : 4;
+  if (K < 1 || K > max_k) return pl;
+  const bool vec_is_target = vec && sorted[0] == 0;
+  int n_lane = 0;
+  for (int i = 0; i < K; ++i)
+    if (sorted[i] >= VB && sorted[i] < ZB) ++n_lane;
+  pl.S = (vec && !vec_is_target && n_lane == 0) ? 1 : 0;
+  pl.GT = pl.S ? std::max(0, 2 - K) : std::max(0, 3 - K);
+  pl.swaps = n_lane > 0;
+  auto is_target = [&](int b) {
+    for (int i = 0; i < K; ++i)
+      if (sorted[i] == b) return true;
+    return false;
+  };
+  int next_extra = ZB;
+  auto take_extra = [&]() {
+    while (is_target(next_extra)) ++next_extra;
+    return next_extra++;
+  };
+  std::vector<int> ins;
+  const int RB = pl.S + K + pl.GT;
+  for (int i = 0; i < kMaxRegBits; ++i) {
+    pl.reg_off[i] = 0;
+    pl.swap_lane[i] = -1;
+  }
+  // Target slots.
+  for (int i = 0; i < K; ++i) {
+    const int rbit = pl.S + i;
+    const int t = sorted[i];
+    if (t >= ZB) {
+      pl.reg_off[rbit] = 1ll << t;
+      ins.push_back(t);
+    } else if (vec && t == 0) {
+      // rbit == 0: the vector bit itself.
+    } else {
+      // Lane target: needs a spare register bit to trade places with.
+      pl.swap_lane[i] = t - VB;
+      if (vec && rbit == 0) {
+        // Spare is the vector bit (index bit 0, not a target here).
+      } else {
+        const int e = take_extra();
+        pl.reg_off[rbit] = 1ll << e;
+        ins.push_back(e);
+      }
+    }
+  }
+  // Group bits on top.
+  for (int g = 0; g < pl.GT; ++g) {
+    const int e = take_extra();
+    pl.reg_off[pl.S + K + g] = 1ll << e;
+    ins.push_back(e);
+  }
+  (void)RB;
+  std::sort(ins.begin(), ins.end());
+  if ((int)ins.size() > kMaxIns) return pl;
+  for (int b : ins)
+    if (b >= n) return pl;
+  if (n < ZB + (int)ins.size()) return pl;
+  pl.n_ins = (int)ins.size();
+  for (int i = 0; i < pl.n_ins; ++i) pl.ins_pos[i] = ins[i];
+  pl.num_items = 1ull << (n - ZB - pl.n_ins);
+  pl.feasible = true;
+  return pl;
+}
+
+// Reorders a gate matrix from "first target = MSB" order to "index bit i <->
+// i-th lowest target bit position" and casts it to `real`.
+template <typename real>
+void permute_matrix(const double* m128, const int* targets, const int* sorted, int K, real* out) {
+  const int dim = 1 << K;
+  // rank_of_gate_qubit[q] = index in `sorted` of targets[q]
+  int rank[16];
+  for (int q = 0; q < K; ++q)
+    for (int i = 0; i < K; ++i)
+      if (sorted[i] == targets[q]) rank[q] = i;
+  std::vector<int> orig(dim);
+  for (int j = 0; j < dim; ++j) {
+    int idx = 0;
+    for (int q = 0; q < K; ++q) {
+      const int bit = (j >> rank[q]) & 1;
+      idx |= bit << (K - 1 - q);
+    }
+    orig[j] = idx;
+  }
+  for (int r = 0; r < dim; ++r)
+    for (int c = 0; c < dim; ++c) {
+      const double* src = m128 + 2 * ((size_t)orig[r] * dim + orig[c]);
+      out[2 * ((size_t)r * dim + c)] = (real)src[0];
+      out[2 * ((size_t)r * dim + c) + 1] = (real)src[1];
+    }
+}
+
+template <typename real, int K, int S, int GT, bool SWAPS>
+int launch_fast(void* state, const FastPlan& pl, const real* mat, cudaStream_t stream) {
+  FastParams<real, K> p;
+  p.state = reinterpret_cast<typename Cplx<real>::type*>(state);
+  p.num_items = pl.num_items;
+  p.n_ins = pl.n_ins;
+  for (int i = 0; i < kMaxIns; ++i) p.ins_pos[i] = pl.ins_pos[i];
+  for (int i = 0; i < kMaxRegBits; ++i) {
+    p.reg_off[i] = pl.reg_off[i];
+    p.swap_lane[i] = pl.swap_lane[i];
+  }
+  std::memcpy(p.mat, mat, sizeof(real) * (2u << (2 * K)));
+  const uint64_t warps_per_block = kFastThreads / 32;
+  const uint64_t blocks = (pl.num_items + warps_per_block - 1) / warps_per_block;
+  if (blocks > 0x7fffffffull) return set_error(B2Q_ERR_UNSUPPORTED, "grid too large");
+  sv_apply_fast_kernel<real, K, S, GT, SWAPS>
+      <<<(unsigned)blocks, kFastThreads, 0, stream>>>(p);
+  B2Q_LAUNCH_CHECK("sv_apply_fast_kernel");
+  return B2Q_OK;
+}
+
+template <typename real, int K>
+int dispatch_fast_k(void* state, const FastPlan& pl, const real* mat, cudaStream_t stream) {
+  constexpr bool vec = sizeof(real) == 4;
+  constexpr int GT1 = (2 - K) > 0 ? (2 - K) : 0;
+  constexpr int GT0 = (3 - K) > 0 ? (3 - K) : 0;
+  if constexpr (vec) {
+    if (pl.S == 1) return launch_fast<real, K, 1, GT1, false>(state, pl, mat, stream);
+  }
+  if (pl.swaps) return launch_fast<real, K, 0, GT0, true>(state, pl, mat, stream);
+  return launch_fast<real, K, 0, GT0, false>(state, pl, mat, stream);
+}
+
+template <typename real, int K>
+int launch_small(void* state, int n, const int* sorted, const real* mat, cudaStream_t stream) {
+  SmallParams<real, K> p;
+  p.state = reinterpret_cast<typename Cplx<real>::type*>(state);
+  p.num_groups = 1ull << (n - K);
+  for (int i = 0; i < K; ++i) p.tpos[i] = sorted[i];
+  std::memcpy(p.mat, mat, sizeof(real) * (2u << (2 * K)));
+  const uint64_t blocks = (p.num_groups + 127) / 128;
+  if (blocks > 0x7fffffffull) return set_error(B2Q_ERR_UNSUPPORTED, "grid too large");
+  sv_apply_small_kernel<real, K><<<(unsigned)blocks, 128, 0, stream>>>(p);
+  B2Q_LAUNCH_CHECK("sv_apply_small_kernel");
+  return B2Q_OK;
+}
+
+template <typename real>
+int apply_generic(void* state, int n, const int* sorted, int K, const real* mat, void* scratch,
+                  cudaStream_t stream) {
+  using C = typename Cplx<real>::type;
+  if (scratch == nullptr)
+    return set_error(B2Q_ERR_INVALID,
+                     "a %d-qubit gate needs the out-of-place kernel: pass a scratch buffer", K);
+  const size_t dim = (size_t)1 << K;
+  C* dmat = nullptr;
+  B2Q_CUDA_CHECK(cudaMallocAsync((void**)&dmat, sizeof(C) * dim * dim, stream));
+  B2Q_CUDA_CHECK(
+      cudaMemcpyAsync(dmat, mat, sizeof(C) * dim * dim, cudaMemcpyHostToDevice, stream));
+  // The host matrix buffer is reused by the caller: make the copy complete.
+  B2Q_CUDA_CHECK(cudaStreamSynchronize(stream));
+  GenericParams p;
+  p.n = n;
+  p.k = K;
+  for (int i = 0; i < K; ++i) p.tpos[i] = sorted[i];
+  const uint64_t total = 1ull << n;
+  const uint64_t blocks = std::min<uint64_t>((total + 255) / 256, 148ull * 64);
+  sv_apply_generic_kernel<real><<<(unsigned)blocks, 256, 0, stream>>>(
+      reinterpret_cast<const C*>(state), reinterpret_cast<C*>(scratch), dmat, p);
+  B2Q_LAUNCH_CHECK("sv_apply_generic_kernel");
+  B2Q_CUDA_CHECK(
+      cudaMemcpyAsync(state, scratch, sizeof(C) * total, cudaMemcpyDeviceToDevice, stream));
+  B2Q_CUDA_CHECK(cudaFreeAsync(dmat, stream));
+  return B2Q_OK;
+}
+
+template <typename real>
+int apply_matrix_t(void* state, int dtype, int n, const double* m128, const int* targets, int K,
+                   void* scratch, cudaStream_t stream) {
+  int sorted[16];
+  for (int i = 0; i < K; ++i) sorted[i] = targets[i];
+  std::sort(sorted, sorted + K);
+  for (int i = 0; i < K; ++i) {
+    B2Q_REQUIRE(sorted[i] >= 0 && sorted[i] < n, "target bit %d out of range for %d qubits",
+                sorted[i], n);
+    B2Q_REQUIRE(i == 0 || sorted[i] != sorted[i - 1], "duplicate target bit %d", sorted[i]);
+  }
+  std::vector<real> mat((size_t)2 << (2 * K));
+  permute_matrix<real>(m128, targets, sorted, K, mat.data());
+  const FastPlan pl = make_fast_plan(dtype, n, sorted, K);
+  if (pl.feasible) {
+    switch (K) {
+      case 1: return dispatch_fast_k<real, 1>(state, pl, mat.data(), stream);
+      case 2: return dispatch_fast_k<real, 2>(state, pl, mat.data(), stream);
+      case 3: return dispatch_fast_k<real, 3>(state, pl, mat.data(), stream);
+      case 4: return dispatch_fast_k<real, 4>(state, pl, mat.data(), stream);
+      case 5:
+        if constexpr (sizeof(real) == 4)
+          return dispatch_fast_k<real, 5>(state, pl, mat.data(), stream);
+        break;
+    }
+  }
+  const int max_small = sizeof(real) == 4 ? 5 : 4;
+  if (K <= max_small && n <= 20) {
+    switch (K) {
+      case 1: return launch_small<real, 1>(state, n, sorted, mat.data(), stream);
+      case 2: return launch_small<real, 2>(state, n, sorted, mat.data(), stream);
+      case 3: return launch_small<real, 3>(state, n, sorted, mat.data(), stream);
+      case 4: return launch_small<real, 4>(state, n, sorted, mat.data(), stream);
+      case 5:
+        if constexpr (sizeof(real) == 4)
+          return launch_small<real, 5>(state, n, sorted, mat.data(), stream);
+        break;
+    }
+  }
+  return apply_generic<real>(state, n, sorted, K, mat.data(), scratch, stream);
+}
+
+}  // namespace b2q
+
+using namespace b2q;
+
+extern "C" int b2q_sv_apply_matrix(void* state, int dtype, int n_qubits,
+                                   const double* matrix_c128, const int* targets, int k,
+                                   void* scratch, void* stream) {
+  B2Q_REQUIRE(state != nullptr && matrix_c128 != nullptr && targets != nullptr, "null argument");
+  B2Q_REQUIRE(dtype == B2Q_C64 || dtype == B2Q_C128, "bad dtype %d", dtype);
+  B2Q_REQUIRE(n_qubits >= 1 && n_qubits <= 40, "n_qubits=%d out of range", n_qubits);
+  B2Q_REQUIRE(k >= 1 && k <= 10 && k <= n_qubits, "k=%d out of range (n=%d)", k, n_qubits);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == B2Q_C64)
+    return apply_matrix_t<float>(state, dtype, n_qubits, matrix_c128, targets, k, scratch, s);
+  return apply_matrix_t<double>(state, dtype, n_qubits, matrix_c128, targets, k, scratch, s);
+}
+
+extern "C" int b2q_sv_apply_batch(void* state, int dtype, int n_qubits, int num_gates,
+                                  const int* ks, const int* targets, const double* matrices_c128,
+                                  void* scratch, void* stream) {
+  B2Q_REQUIRE(num_gates >= 0, "num_gates < 0");
+  size_t toff = 0, moff = 0;
+  for (int g = 0; g < num_gates; ++g) {
+    const int k = ks[g];
+    const int rc = b2q_sv_apply_matrix(state, dtype, n_qubits, matrices_c128 + moff,
+                                       targets + toff, k, scratch, stream);
+    if (rc != B2Q_OK) return rc;
+    toff += k;
+    moff += (size_t)2 << (2 * k);
+  }
+  return B2Q_OK;
+}
+
+extern "C" int b2q_sv_apply_diagonal(void* state, int dtype, int n_qubits,
+                                     const double* diag_c128, const int* targets, int k,
+                                     void* stream) {
+  B2Q_REQUIRE(state != nullptr && diag_c128 != nullptr && targets != nullptr, "null argument");
+  B2Q_REQUIRE(dtype == B2Q_C64 || dtype == B2Q_C128, "bad dtype %d", dtype);
+  B2Q_REQUIRE(k >= 1 && k <= 16 && k <= n_qubits, "k=%d out of range", k);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DiagParams p;
+  p.n = n_qubits;
+  p.k = k;
+  // table index: first target = MSB  ->  bit (k-1-q) of the index <-> targets[q]
+  for (int q = 0; q < k; ++q) {
+    B2Q_REQUIRE(targets[q] >= 0 && targets[q] < n_qubits, "target bit out of range");
+    p.tpos[k - 1 - q] = targets[q];
+  }
+  const size_t dim = (size_t)1 << k;
+  const uint64_t total = 1ull << n_qubits;
+  const uint64_t blocks = std::min<uint64_t>((total + 255) / 256, 148ull * 64);
+  void* ddiag = nullptr;
+  if (dtype == B2Q_C64) {
+    std::vector<float> h(2 * dim);
+    for (size_t i = 0; i < 2 * dim; ++i) h[i] = (float)diag_c128[i];
+    B2Q_CUDA_CHECK(cudaMallocAsync(&ddiag, sizeof(float2) * dim, s));
+    B2Q_CUDA_CHECK(cudaMemcpyAsync(ddiag, h.data(), sizeof(float2) * dim, cudaMemcpyHostToDevice, s));
+    B2Q_CUDA_CHECK(cudaStreamSynchronize(s));
+    sv_apply_diag_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(
+        reinterpret_cast<float2*>(state), reinterpret_cast<const float2*>(ddiag), p);
+  } else {
+    B2Q_CUDA_CHECK(cudaMallocAsync(&ddiag, sizeof(double2) * dim, s));
+    B2Q_CUDA_CHECK(
+        cudaMemcpyAsync(ddiag, diag_c128, sizeof(double2) * dim, cudaMemcpyHostToDevice, s));
+    B2Q_CUDA_CHECK(cudaStreamSynchronize(s));
+    sv_apply_diag_kernel<double><<<(unsigned)blocks, 256, 0, s>>>(
+        reinterpret_cast<double2*>(state), reinterpret_cast<const double2*>(ddiag), p);
+  }
+  B2Q_LAUNCH_CHECK("sv_apply_diag_kernel");
+  B2Q_CUDA_CHECK(cudaFreeAsync(ddiag, s));
+  return B2Q_OK;
+}
+
+// Host-only: exposes the fast-path plan for unit tests (no GPU needed).
+// out[0]=feasible, [1]=S, [2]=GT, [3]=swaps, [4]=n_ins, [5..10]=ins_pos,
+// [11..16]=log2(reg_off) or -1, [17..22]=swap_lane, [23]=log2(num_items).
+extern "C" int b2q_debug_plan(int dtype, int n_qubits, const int* targets, int k, int* out) {
+  int sorted[16];
+  for (int i = 0; i < k; ++i) sorted[i] = targets[i];
+  std::sort(sorted, sorted + k);
+  const FastPlan pl = make_fast_plan(dtype, n_qubits, sorted, k);
+  out[0] = pl.feasible;
+  out[1] = pl.S;
+  out[2] = pl.GT;
+  out[3] = pl.swaps;
+  out[4] = pl.n_ins;
+  for (int i = 0; i < 6; ++i) out[5 + i] = pl.ins_pos[i];
+  for (int i = 0; i < 6; ++i) {
+    int lg = -1;
+    if (pl.reg_off[i] > 0) {
+      lg = 0;
+      while ((1ll << lg) < pl.reg_off[i]) ++lg;
+    }
+    out[11 + i] = lg;
+  }
+  for (int i = 0; i < 6; ++i) out[17 + i] = pl.swap_lane[i];
+  int lg = 0;
+  while ((1ull << lg) < pl.num_items) ++lg;
+  out[23] = pl.feasible ? lg : -1;
+  return B2Q_OK;
+}
+
+// Host-only: the matrix permutation used by every kernel, for unit tests.
+extern "C" int b2q_debug_permute_matrix(const double* m128, const int* targets, int k,
+                                        double* out) {
+  int sorted[16];
+  for (int i = 0; i < k; ++i) sorted[i] = targets[i];
+  std::sort(sorted, sorted + k);
+  permute_matrix<double>(m128, targets, sorted, k, out);
+  return B2Q_OK;
+}

@@ -1,0 +1,980 @@
+// Read-out side of the hot path: norms, marginal probabilities, inverse-CDF
+// sampling, collapse, amplitude gather, Pauli expectation values, and the
+// density-matrix diagonal / collapse.
+//
+// Replaces (reference, cirq-core/cirq/): sim/state_vector.py:170-322
+// (sample_state_vector / measure_state_vector), sim/simulation_utils.py:24-65
+// (state_probabilities_by_indices), sim/density_matrix_utils.py:31-192,
+// ops/pauli_string.py:625-655 and the fancy-index gather of
+// sim/state_vector_simulator.py:95-98.
+//
+// Sampling is a three-level inverse CDF: one streaming
+// read of the state produces float64 sums of 128-amplitude chunks, chunks are
+// grouped by 128 into blocks, block sums are prefix-scanned, and each sample is
+// resolved by one warp: binary search over blocks, warp scan over the block's
+// chunk sums, warp scan over the chunk's amplitudes (re-read, ~1.5 KB/sample).
+#include "b2q_common.cuh"
+
+#include <algorithm>
+#include <vector>
+
+namespace b2q {
+
+constexpr int kChunkLog2 = 7;  // amplitudes per chunk (<= 128 = 4 per lane)
+constexpr int kCpbLog2 = 7;    // chunks per block
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ double warp_inclusive_scan(double v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+template <typename real>
+__device__ __forceinline__ double abs2(const typename Cplx<real>::type& a) {
+  // |a|^2 in the state's real type, as (psi * psi.conj()).real of the
+  // reference (sim/state_vector.py:220), then widened for accumulation.
+  return (double)(a.x * a.x + a.y * a.y);
+}
+
+// ---- block-wise norm --------------------------------------------------------
+
+// partial[b] = sum of |psi|^2 over a grid-strided subset; deterministic order.
+template <typename real>
+__global__ void __launch_bounds__(256)
+    sv_norm_partial_kernel(const typename Cplx<real>::type* __restrict__ state, uint64_t total,
+                           double* __restrict__ partial) {
+  using C = typename Cplx<real>::type;
+  double acc = 0.0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const C a = state[i];
+    acc += abs2<real>(a);
+  }
+  __shared__ double sm[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < 8; ++w) t += sm[w];
+    partial[blockIdx.x] = t;
+  }
+}
+
+// Sums `count` doubles (<= a few thousand) with one CTA into out[0..ncomp).
+// in is laid out [count][ncomp].
+__global__ void __launch_bounds__(256)
+    final_sum_kernel(const double* __restrict__ in, uint64_t count, int ncomp,
+                     double* __restrict__ out) {
+  __shared__ double sm[8];
+  for (int comp = 0; comp < ncomp; ++comp) {
+    double acc = 0.0;
+    for (uint64_t i = threadIdx.x; i < count; i += blockDim.x) acc += in[i * ncomp + comp];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0;
+      for (int w = 0; w < 8; ++w) t += sm[w];
+      out[comp] = t;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- init / scale / collapse ------------------------------------------------
+
+template <typename real>
+__global__ void set_one_kernel(typename Cplx<real>::type* state, uint64_t index) {
+  state[index] = make_c<real>(1, 0);
+}
+
+template <typename real>
+__global__ void __launch_bounds__(256)
+    sv_scale_kernel(typename Cplx<real>::type* __restrict__ state, uint64_t total, real re,
+                    real im) {
+  using C = typename Cplx<real>::type;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const C a = state[i];
+    state[i] = cmul<real>(re, im, a);
+  }
+}
+
+// Keeps amplitudes with (i & mask) == want scaled by `scale`, zeroes the rest.
+template <typename real>
+__global__ void __launch_bounds__(256)
+    sv_collapse_kernel(typename Cplx<real>::type* __restrict__ state, uint64_t total,
+                       uint64_t mask, uint64_t want, real scale) {
+  using C = typename Cplx<real>::type;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    if ((i & mask) == want) {
+      C a = state[i];
+      a.x *= scale;
+      a.y *= scale;
+      state[i] = a;
+    } else {
+      state[i] = make_c<real>(0, 0);
+    }
+  }
+}
+
+// ---- gather / diagonal ------------------------------------------------------
+
+template <typename real>
+__global__ void sv_gather_kernel(const typename Cplx<real>::type* __restrict__ state,
+                                 const uint64_t* __restrict__ idx, uint64_t count,
+                                 double2* __restrict__ out) {
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= count) return;
+  const auto a = state[idx[j]];
+  out[j] = make_double2((double)a.x, (double)a.y);
+}
+
+template <typename real>
+__global__ void dm_diag_kernel(const typename Cplx<real>::type* __restrict__ rho, int n,
+                               double* __restrict__ probs) {
+  const uint64_t dim = 1ull << n;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < dim;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    probs[i] = (double)rho[i * dim + i].x;
+}
+
+// ---- marginal probabilities -------------------------------------------------
+
+struct MarginalParams {
+  int n;
+  int zb;             // zone bits (6 for c64, 5 for c128)
+  int m;              // measured bits
+  int bits[24];       // measured bit positions, bits[0] = MSB of the key
+  int n_meas_high;    // measured bits >= zb
+  int meas_high_pos[24];  // ascending positions relative to zb
+  int log2_iters;     // iterations per warp over unmeasured high bits
+  uint64_t num_warps; // total warp tasks
+};
+
+// Each warp owns the 512-byte zone; each lane accumulates the amplitudes it
+// streams into at most two private float64 sums (its key never changes while it
+// iterates over the unmeasured high bits), then lanes that share a key are
+// folded by shuffles and one atomicAdd per surviving lane hits probs[key].
+template <typename real>
+__global__ void __launch_bounds__(256)
+    sv_marginal_kernel(const typename Cplx<real>::type* __restrict__ state,
+                       const __grid_constant__ MarginalParams p, double* __restrict__ probs) {
+  using C = typename Cplx<real>::type;
+  constexpr bool kVec = sizeof(real) == 4;
+  const int lane = threadIdx.x & 31;
+  const uint64_t task = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (task >= p.num_warps) return;
+  // task enumerates all high bits except the lowest `log2_iters` unmeasured ones.
+  const uint64_t iters = 1ull << p.log2_iters;
+  double a0 = 0.0, a1 = 0.0;
+  // High index (bits >= zb) = insert_zero_bits(unmeasured combo, measured positions) | measured value.
+  // task = (meas_value << (unmeasured_high - log2_iters)) | upper part of the unmeasured combo.
+  const int n_high = p.n - p.zb;
+  const int n_unmeas = n_high - p.n_meas_high;
+  const int up_bits = n_unmeas - p.log2_iters;
+  const uint64_t up = task & ((1ull << up_bits) - 1ull);
+  const uint64_t mv = task >> up_bits;
+  uint64_t meas_dep = 0;
+  for (int i = 0; i < p.n_meas_high; ++i) meas_dep |= ((mv >> i) & 1ull) << p.meas_high_pos[i];
+  uint64_t first_index = 0;
+  for (uint64_t it = 0; it < iters; ++it) {
+    const uint64_t combo = (up << p.log2_iters) | it;
+    const uint64_t high = insert_zero_bits(combo, p.meas_high_pos, p.n_meas_high) | meas_dep;
+    const uint64_t idx = (high << p.zb) | (uint64_t)(kVec ? (lane << 1) : lane);
+    if (it == 0) first_index = idx;
+    if constexpr (kVec) {
+      const float4 v = *reinterpret_cast<const float4*>(state + idx);
+      a0 += (double)(v.x * v.x + v.y * v.y);
+      a1 += (double)(v.z * v.z + v.w * v.w);
+    } else {
+      const C v = state[idx];
+      a0 += abs2<real>(v);
+    }
+  }
+  // Fold lanes whose keys coincide.
+  uint64_t meas_mask = 0;
+  for (int q = 0; q < p.m; ++q) meas_mask |= 1ull << p.bits[q];
+  bool alive = true;
+  if constexpr (kVec) {
+    if (!(meas_mask & 1ull)) {
+      a0 += a1;
+      a1 = 0.0;
+    }
+  }
+  const int vb = kVec ? 1 : 0;
+  for (int lb = 0; lb < 5; ++lb) {
+    if (!((meas_mask >> (lb + vb)) & 1ull)) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, 1 << lb);
+      if constexpr (kVec) a1 += __shfl_xor_sync(0xffffffffu, a1, 1 << lb);
+      if ((lane >> lb) & 1) alive = false;
+    }
+  }
+  if (alive) {
+    const uint64_t k0 = extract_bits_msb_first(first_index, p.bits, p.m);
+    atomicAdd(&probs[k0], a0);
+    if constexpr (kVec) {
+      if (meas_mask & 1ull) {
+        const uint64_t k1 = extract_bits_msb_first(first_index | 1ull, p.bits, p.m);
+        atomicAdd(&probs[k1], a1);
+      }
+    }
+  }
+}
+
+// Small-state fallback (n < zone): one thread per amplitude, global atomics.
+template <typename real>
+__global__ void sv_marginal_small_kernel(const typename Cplx<real>::type* __restrict__ state,
+                                         const __grid_constant__ MarginalParams p,
+                                         double* __restrict__ probs) {
+  const uint64_t total = 1ull << p.n;
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  atomicAdd(&probs[extract_bits_msb_first(i, p.bits, p.m)], abs2<real>(state[i]));
+}
+
+// ---- prefix scan (single CTA) -----------------------------------------------
+
+// out[i] = in[0] + ... + in[i]; count arbitrary; 1024 threads, contiguous
+// chunk per thread, block scan of the chunk totals.
+__global__ void __launch_bounds__(1024)
+    scan_inclusive_kernel(const double* __restrict__ in, double* __restrict__ out, uint64_t count) {
+  __shared__ double warp_tot[32];
+  __shared__ double carry_s;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, wid = tid >> 5;
+  const uint64_t per = (count + 1023) / 1024;
+  const uint64_t lo = std::min<uint64_t>(count, per * tid);
+  const uint64_t hi = std::min<uint64_t>(count, lo + per);
+  double t = 0.0;
+  for (uint64_t i = lo; i < hi; ++i) t += in[i];
+  double inc = warp_inclusive_scan(t, lane);
+  if (lane == 31) warp_tot[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    double w = warp_tot[lane];
+    w = warp_inclusive_scan(w, lane);
+    warp_tot[lane] = w;
+  }
+  __syncthreads();
+  double prefix = inc - t + (wid > 0 ? warp_tot[wid - 1] : 0.0);
+  (void)carry_s;
+  for (uint64_t i = lo; i < hi; ++i) {
+    prefix += in[i];
+    out[i] = prefix;
+  }
+}
+
+// ---- hierarchical sampler ---------------------------------------------------
+
+// chunk_sums[c] = sum_{i in chunk c} |psi_i|^2 ; one warp per chunk.
+template <typename real>
+__global__ void __launch_bounds__(256)
+    sv_chunk_sums_kernel(const typename Cplx<real>::type* __restrict__ state, uint64_t total,
+                         int chunk_log2, double* __restrict__ chunk_sums) {
+  using C = typename Cplx<real>::type;
+  const int lane = threadIdx.x & 31;
+  const uint64_t nchunks = total >> chunk_log2;
+  const uint64_t chunk_elems = 1ull << chunk_log2;
+  for (uint64_t c = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < nchunks;
+       c += (uint64_t)gridDim.x * (blockDim.x >> 5)) {
+    const C* base = state + (c << chunk_log2);
+    double acc = 0.0;
+    // lane owns 4 consecutive amplitudes (fewer for tiny chunks)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const uint64_t i = (uint64_t)lane * 4 + e;
+      if (i < chunk_elems) acc += abs2<real>(base[i]);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) chunk_sums[c] = acc;
+  }
+}
+
+// block_sums[b] = sum of the block's chunk sums (warp per block).
+__global__ void __launch_bounds__(256)
+    block_sums_kernel(const double* __restrict__ chunk_sums, uint64_t nblocks, int cpb_log2,
+                      double* __restrict__ block_sums) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t cpb = 1ull << cpb_log2;
+  for (uint64_t b = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < nblocks;
+       b += (uint64_t)gridDim.x * (blockDim.x >> 5)) {
+    const double* base = chunk_sums + (b << cpb_log2);
+    double acc = 0.0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const uint64_t i = (uint64_t)lane * 4 + e;
+      if (i < cpb) acc += base[i];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) block_sums[b] = acc;
+  }
+}
+
+// Finds, within 4-per-lane values v[0..3] (lane-major order), the first global
+// position whose inclusive prefix exceeds `target`.  Returns position or -1, and
+// the exclusive prefix at that position through *before.
+__device__ __forceinline__ int warp_search4(const double (&v)[4], int valid, double target,
+                                            int lane, double* before) {
+  const double lane_tot = v[0] + v[1] + v[2] + v[3];
+  const double inc = warp_inclusive_scan(lane_tot, lane);
+  const double exc = inc - lane_tot;
+  int pos = -1;
+  double bef = 0.0;
+  double run = exc;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int gi = lane * 4 + e;
+    if (pos < 0 && gi < valid && run + v[e] > target) {
+      pos = gi;
+      bef = run;
+    }
+    run += v[e];
+  }
+  // first lane that found something wins
+  const unsigned ball = __ballot_sync(0xffffffffu, pos >= 0);
+  if (ball == 0) return -1;
+  const int src = __ffs(ball) - 1;
+  pos = __shfl_sync(0xffffffffu, pos, src);
+  bef = __shfl_sync(0xffffffffu, bef, src);
+  *before = bef;
+  return pos;
+}
+
+// Last position with a strictly positive value, or -1.
+__device__ __forceinline__ int warp_last_positive4(const double (&v)[4], int valid, int lane) {
+  int pos = -1;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int gi = lane * 4 + e;
+    if (gi < valid && v[e] > 0.0) pos = gi;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) pos = max(pos, __shfl_xor_sync(0xffffffffu, pos, o));
+  return pos;
+}
+
+template <typename real>
+__global__ void __launch_bounds__(256)
+    sv_sample_resolve_kernel(const typename Cplx<real>::type* __restrict__ state, uint64_t total,
+                             int chunk_log2, int cpb_log2, const double* __restrict__ chunk_sums,
+                             const double* __restrict__ block_cum, uint64_t nblocks,
+                             const double* __restrict__ uniforms, uint64_t reps,
+                             uint64_t* __restrict__ out) {
+  using C = typename Cplx<real>::type;
+  const int lane = threadIdx.x & 31;
+  const double grand = block_cum[nblocks - 1];
+  const int chunk_elems = 1 << chunk_log2;
+  const int cpb = 1 << cpb_log2;
+  for (uint64_t j = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < reps;
+       j += (uint64_t)gridDim.x * (blockDim.x >> 5)) {
+    double target = uniforms[j] * grand;
+    // smallest b with block_cum[b] > target
+    uint64_t lo = 0, hi = nblocks;
+    while (lo < hi) {
+      const uint64_t mid = (lo + hi) >> 1;
+      if (block_cum[mid] > target) {
+        hi = mid;
+      } else {
+        lo = mid + 1;
+      }
+    }
+    uint64_t b = lo;
+    if (b >= nblocks) b = nblocks - 1;
+    target -= (b > 0 ? block_cum[b - 1] : 0.0);
+    // chunk level
+    double v[4];
+    const double* cs = chunk_sums + (b << cpb_log2);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int gi = lane * 4 + e;
+      v[e] = gi < cpb ? cs[gi] : 0.0;
+    }
+    double before = 0.0;
+    int c = warp_search4(v, cpb, target, lane, &before);
+    if (c < 0) {
+      c = warp_last_positive4(v, cpb, lane);
+      if (c < 0) c = cpb - 1;
+      before = target;  // forces the in-chunk fallback below
+      // exclusive prefix unknown: make the in-chunk search pick its last positive entry
+      target = 1e300;
+    } else {
+      target -= before;
+    }
+    const uint64_t chunk = (b << cpb_log2) + (uint64_t)c;
+    const C* base = state + (chunk << chunk_log2);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int gi = lane * 4 + e;
+      v[e] = gi < chunk_elems ? abs2<real>(base[gi]) : 0.0;
+    }
+    int pos = warp_search4(v, chunk_elems, target, lane, &before);
+    if (pos < 0) {
+      pos = warp_last_positive4(v, chunk_elems, lane);
+      if (pos < 0) pos = chunk_elems - 1;
+    }
+    if (lane == 0) out[j] = (chunk << chunk_log2) + (uint64_t)pos;
+  }
+}
+
+// Thread per sample: searchsorted(cum, u*total, 'right') over a small table.
+__global__ void cdf_search_kernel(const double* __restrict__ cum, uint64_t count,
+                                  const double* __restrict__ uniforms, uint64_t reps,
+                                  uint64_t* __restrict__ out) {
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= reps) return;
+  const double target = uniforms[j] * cum[count - 1];
+  uint64_t lo = 0, hi = count;
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (cum[mid] > target) {
+      hi = mid;
+    } else {
+      lo = mid + 1;
+    }
+  }
+  if (lo >= count) {
+    // rounding pushed the target to the very end: last entry with positive mass
+    lo = count - 1;
+    while (lo > 0 && !(cum[lo] > cum[lo - 1])) --lo;
+  }
+  out[j] = lo;
+}
+
+struct UnpackParams {
+  int m;
+  int bits[64];
+};
+
+__global__ void unpack_bits_kernel(const uint64_t* __restrict__ idx, uint64_t total_out,
+                                   const __grid_constant__ UnpackParams p,
+                                   uint8_t* __restrict__ out) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total_out) return;
+  const uint64_t j = t / (uint64_t)p.m;
+  const int q = (int)(t - j * (uint64_t)p.m);
+  out[t] = (uint8_t)((idx[j] >> p.bits[q]) & 1ull);
+}
+
+// ---- Pauli expectation ------------------------------------------------------
+
+// partial[b] = sum_i sign(i) * conj(psi[i ^ x]) * psi[i]   (complex, 2 doubles)
+template <typename real>
+__global__ void __launch_bounds__(256)
+    sv_pauli_partial_kernel(const typename Cplx<real>::type* __restrict__ state, uint64_t total,
+                            uint64_t xmask, uint64_t zmask, double* __restrict__ partial) {
+  using C = typename Cplx<real>::type;
+  double ar = 0.0, ai = 0.0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const C a = state[i];
+    const C b = state[i ^ xmask];
+    // conj(b) * a
+    double re = (double)b.x * (double)a.x + (double)b.y * (double)a.y;
+    double im = (double)b.x * (double)a.y - (double)b.y * (double)a.x;
+    if (__popcll(i & zmask) & 1) {
+      re = -re;
+      im = -im;
+    }
+    ar += re;
+    ai += im;
+  }
+  __shared__ double sm[16];
+  ar = warp_sum(ar);
+  ai = warp_sum(ai);
+  if ((threadIdx.x & 31) == 0) {
+    sm[2 * (threadIdx.x >> 5)] = ar;
+    sm[2 * (threadIdx.x >> 5) + 1] = ai;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tr = 0, ti = 0;
+    for (int w = 0; w < 8; ++w) {
+      tr += sm[2 * w];
+      ti += sm[2 * w + 1];
+    }
+    partial[2 * blockIdx.x] = tr;
+    partial[2 * blockIdx.x + 1] = ti;
+  }
+}
+
+// ---- dist pack / unpack -----------------------------------------------------
+
+struct PackParams {
+  int n_local;
+  int g;
+  int pos[8];  // ascending local bit positions being exchanged
+  int rank_of[8];  // pos[i] <-> bit rank_of[i] of the segment index
+};
+
+// One thread per amplitude of the shard.  dir=0: shard -> packed; 1: packed -> shard.
+template <typename real, int DIR>
+__global__ void __launch_bounds__(256)
+    dist_pack_kernel(typename Cplx<real>::type* __restrict__ shard,
+                     typename Cplx<real>::type* __restrict__ packed,
+                     const __grid_constant__ PackParams p) {
+  const uint64_t total = 1ull << p.n_local;
+  const int rest = p.n_local - p.g;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    // t = (segment << rest) | r  indexes `packed`
+    const uint64_t seg = t >> rest;
+    const uint64_t r = t & ((1ull << rest) - 1ull);
+    uint64_t idx = insert_zero_bits(r, p.pos, p.g);
+    for (int i = 0; i < p.g; ++i) idx |= ((seg >> p.rank_of[i]) & 1ull) << p.pos[i];
+    if (DIR == 0) {
+      packed[t] = shard[idx];
+    } else {
+      shard[idx] = packed[t];
+    }
+  }
+}
+
+inline unsigned stride_grid(uint64_t work_items, int threads) {
+  const uint64_t b = (work_items + threads - 1) / threads;
+  return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(b, 148ull * 32));
+}
+
+template <typename real>
+int norm2_t(const void* state, int n, double* out_host, cudaStream_t s) {
+  using C = typename Cplx<real>::type;
+  const uint64_t total = 1ull << n;
+  const unsigned blocks = stride_grid(total, 256);
+  double* partial = nullptr;
+  B2Q_CUDA_CHECK(cudaMallocAsync((void**)&partial, sizeof(double) * (blocks + 1), s));
+  sv_norm_partial_kernel<real><<<blocks, 256, 0, s>>>(reinterpret_cast<const C*>(state), total,
+                                                      partial);
+  B2Q_LAUNCH_CHECK("sv_norm_partial_kernel");
+  final_sum_kernel<<<1, 256, 0, s>>>(partial, blocks, 1, partial + blocks);
+  B2Q_LAUNCH_CHECK("final_sum_kernel");
+  B2Q_CUDA_CHECK(
+      cudaMemcpyAsync(out_host, partial + blocks, sizeof(double), cudaMemcpyDeviceToHost, s));
+  B2Q_CUDA_CHECK(cudaStreamSynchronize(s));
+  B2Q_CUDA_CHECK(cudaFreeAsync(partial, s));
+  return B2Q_OK;
+}
+
+}  // namespace b2q
+
+using namespace b2q;
+
+#define B2Q_CHECK_DTYPE(dtype) \
+  B2Q_REQUIRE((dtype) == B2Q_C64 || (dtype) == B2Q_C128, "bad dtype %d", (dtype))
+
+extern "C" int b2q_sv_init_basis(void* state, int dtype, int n_qubits, uint64_t basis_index,
+                                 void* stream) {
+  B2Q_REQUIRE(state != nullptr, "null state");
+  B2Q_CHECK_DTYPE(dtype);
+  B2Q_REQUIRE(n_qubits >= 0 && n_qubits <= 40, "n_qubits out of range");
+  const uint64_t total = 1ull << n_qubits;
+  B2Q_REQUIRE(basis_index < total, "basis index out of range");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  B2Q_CUDA_CHECK(cudaMemsetAsync(state, 0, total * elem_bytes(dtype), s));
+  if (dtype == B2Q_C64)
+    set_one_kernel<float><<<1, 1, 0, s>>>(reinterpret_cast<float2*>(state), basis_index);
+  else
+    set_one_kernel<double><<<1, 1, 0, s>>>(reinterpret_cast<double2*>(state), basis_index);
+  B2Q_LAUNCH_CHECK("set_one_kernel");
+  return B2Q_OK;
+}
+
+extern "C" int b2q_sv_scale(void* state, int dtype, int n_qubits, double re, double im,
+                            void* stream) {
+  B2Q_REQUIRE(state != nullptr, "null state");
+  B2Q_CHECK_DTYPE(dtype);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const uint64_t total = 1ull << n_qubits;
+  const unsigned blocks = stride_grid(total, 256);
+  if (dtype == B2Q_C64)
+    sv_scale_kernel<float><<<blocks, 256, 0, s>>>(reinterpret_cast<float2*>(state), total,
+                                                  (float)re, (float)im);
+  else
+    sv_scale_kernel<double><<<blocks, 256, 0, s>>>(reinterpret_cast<double2*>(state), total, re,
+                                                   im);
+  B2Q_LAUNCH_CHECK("sv_scale_kernel");
+  return B2Q_OK;
+}
+
+extern "C" int b2q_sv_norm2(const void* state, int dtype, int n_qubits, double* out,
+                            void* stream) {
+  B2Q_REQUIRE(state != nullptr && out != nullptr, "null argument");
+  B2Q_CHECK_DTYPE(dtype);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == B2Q_C64) return norm2_t<float>(state, n_qubits, out, s);
+  return norm2_t<double>(state, n_qubits, out, s);
+}
+
+extern "C" int b2q_sv_gather(const void* state, int dtype, int n_qubits, const uint64_t* indices,
+                             uint64_t count, double* out_c128, void* stream) {
+  B2Q_REQUIRE(state != nullptr && (count == 0 || (indices && out_c128)), "null argument");
+  B2Q_CHECK_DTYPE(dtype);
+  if (count == 0) return B2Q_OK;
+  const uint64_t total = 1ull << n_qubits;
+  for (uint64_t j = 0; j < count; ++j)
+    B2Q_REQUIRE(indices[j] < total, "index %llu out of range", (unsigned long long)indices[j]);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  uint64_t* didx = nullptr;
+  double2* dout = nullptr;
+  B2Q_CUDA_CHECK(cudaMallocAsync((void**)&didx, sizeof(uint64_t) * count, s));
+  B2Q_CUDA_CHECK(cudaMallocAsync((void**)&dout, sizeof(double2) * count, s));
+  B2Q_CUDA_CHECK(
+      cudaMemcpyAsync(didx, indices, sizeof(uint64_t) * count, cudaMemcpyHostToDevice, s));
+  const unsigned blocks = (unsigned)((count + 255) / 256);
+  if (dtype == B2Q_C64)
+    sv_gather_kernel<float><<<blocks, 256, 0, s>>>(reinterpret_cast<const float2*>(state), didx,
+                                                   count, dout);
+  else
+    sv_gather_kernel<double><<<blocks, 256, 0, s>>>(reinterpret_cast<const double2*>(state), didx,
+                                                    count, dout);
+  B2Q_LAUNCH_CHECK("sv_gather_kernel");
+  B2Q_CUDA_CHECK(
+      cudaMemcpyAsync(out_c128, dout, sizeof(double2) * count, cudaMemcpyDeviceToHost, s));
+  B2Q_CUDA_CHECK(cudaStreamSynchronize(s));
+  B2Q_CUDA_CHECK(cudaFreeAsync(didx, s));
+  B2Q_CUDA_CHECK(cudaFreeAsync(dout, s));
+  return B2Q_OK;
+}
+
+extern "C" int b2q_sv_marginal_probs(const void* state, int dtype, int n_qubits, const int* bits,
+                                     int m, double* probs_dev, double* probs_host, void* stream) {
+  B2Q_REQUIRE(state != nullptr && bits != nullptr && probs_dev != nullptr, "null argument");
+  B2Q_CHECK_DTYPE(dtype);
+  B2Q_REQUIRE(m >= 1 && m <= 24 && m <= n_qubits, "m=%d out of range", m);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  MarginalParams p;
+  p.n = n_qubits;
+  p.zb = dtype == B2Q_C64 ? 6 : 5;
+  p.m = m;
+  uint64_t seen = 0;
+  for (int q = 0; q < m; ++q) {
+    B2Q_REQUIRE(bits[q] >= 0 && bits[q] < n_qubits, "bit out of range");
+    B2Q_REQUIRE(!((seen >> bits[q]) & 1ull), "duplicate bit %d", bits[q]);
+    seen |= 1ull << bits[q];
+    p.bits[q] = bits[q];
+  }
+  const size_t dim = (size_t)1 << m;
+  B2Q_CUDA_CHECK(cudaMemsetAsync(probs_dev, 0, sizeof(double) * dim, s));
+  if (n_qubits < p.zb + 1) {
+    const uint64_t total = 1ull << n_qubits;
+    p.n_meas_high = 0;
+    p.log2_iters = 0;
+    p.num_warps = 0;
+    if (dtype == B2Q_C64)
+      sv_marginal_small_kernel<float><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(
+          reinterpret_cast<const float2*>(state), p, probs_dev);
+    else
+      sv_marginal_small_kernel<double><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(
+          reinterpret_cast<const double2*>(state), p, probs_dev);
+    B2Q_LAUNCH_CHECK("sv_marginal_small_kernel");
+  } else {
+    std::vector<int> mh;
+    for (int b = p.zb; b < n_qubits; ++b)
+      if ((seen >> b) & 1ull) mh.push_back(b - p.zb);
+    p.n_meas_high = (int)mh.size();
+    for (int i = 0; i < p.n_meas_high; ++i) p.meas_high_pos[i] = mh[i];
+    const int n_high = n_qubits - p.zb;
+    const int n_unmeas = n_high - p.n_meas_high;
+    // aim for >= 2^15 warp tasks, <= 2^10 iterations each
+    int up_bits = std::max(0, 15 - p.n_meas_high);
+    up_bits = std::min(up_bits, n_unmeas);
+    up_bits = std::max(up_bits, n_unmeas - 10);
+    p.log2_iters = n_unmeas - up_bits;
+    p.num_warps = 1ull << (p.n_meas_high + up_bits);
+    const uint64_t blocks = (p.num_warps + 7) / 8;
+    B2Q_REQUIRE(blocks <= 0x7fffffffull, "grid too large");
+    if (dtype == B2Q_C64)
+      sv_marginal_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(
+          reinterpret_cast<const float2*>(state), p, probs_dev);
+    else
+      sv_marginal_kernel<double><<<(unsigned)blocks, 256, 0, s>>>(
+          reinterpret_cast<const double2*>(state), p, probs_dev);
+    B2Q_LAUNCH_CHECK("sv_marginal_kernel");
+  }
+  if (probs_host != nullptr) {
+    B2Q_CUDA_CHECK(
+        cudaMemcpyAsync(probs_host, probs_dev, sizeof(double) * dim, cudaMemcpyDeviceToHost, s));
+    B2Q_CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+  return B2Q_OK;
+}
+
+static void sample_geometry(int n, int* chunk_log2, int* cpb_log2, uint64_t* nchunks,
+                            uint64_t* nblocks) {
+  *chunk_log2 = std::min(n, kChunkLog2);
+  *nchunks = 1ull << (n - *chunk_log2);
+  *cpb_log2 = std::min(n - *chunk_log2, kCpbLog2);
+  *nblocks = *nchunks >> *cpb_log2;
+}
+
+extern "C" uint64_t b2q_sv_sample_workspace_bytes(int n_qubits, uint64_t reps) {
+  (void)reps;
+  int cl, bl;
+  uint64_t nchunks, nblocks;
+  sample_geometry(n_qubits, &cl, &bl, &nchunks, &nblocks);
+  return sizeof(double) * (nchunks + 2 * nblocks) + 256;
+}
+
+extern "C" int b2q_sv_sample(const void* state, int dtype, int n_qubits,
+                             const double* uniforms_dev, uint64_t reps,
+                             uint64_t* out_indices_dev, void* workspace,
+                             uint64_t workspace_bytes, void* stream) {
+  B2Q_REQUIRE(state != nullptr && workspace != nullptr, "null argument");
+  B2Q_CHECK_DTYPE(dtype);
+  B2Q_REQUIRE(workspace_bytes >= b2q_sv_sample_workspace_bytes(n_qubits, reps),
+              "workspace too small");
+  if (reps == 0) return B2Q_OK;
+  B2Q_REQUIRE(uniforms_dev != nullptr && out_indices_dev != nullptr, "null argument");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int cl, bl;
+  uint64_t nchunks, nblocks;
+  sample_geometry(n_qubits, &cl, &bl, &nchunks, &nblocks);
+  const uint64_t total = 1ull << n_qubits;
+  double* chunk_sums = reinterpret_cast<double*>(workspace);
+  double* block_sums = chunk_sums + nchunks;
+  double* block_cum = block_sums + nblocks;
+  const unsigned g1 = stride_grid(nchunks * 32, 256);
+  if (dtype == B2Q_C64)
+    sv_chunk_sums_kernel<float><<<g1, 256, 0, s>>>(reinterpret_cast<const float2*>(state), total,
+                                                   cl, chunk_sums);
+  else
+    sv_chunk_sums_kernel<double><<<g1, 256, 0, s>>>(reinterpret_cast<const double2*>(state),
+                                                    total, cl, chunk_sums);
+  B2Q_LAUNCH_CHECK("sv_chunk_sums_kernel");
+  block_sums_kernel<<<stride_grid(nblocks * 32, 256), 256, 0, s>>>(chunk_sums, nblocks, bl,
+                                                                   block_sums);
+  B2Q_LAUNCH_CHECK("block_sums_kernel");
+  scan_inclusive_kernel<<<1, 1024, 0, s>>>(block_sums, block_cum, nblocks);
+  B2Q_LAUNCH_CHECK("scan_inclusive_kernel");
+  const unsigned g2 = stride_grid(reps * 32, 256);
+  if (dtype == B2Q_C64)
+    sv_sample_resolve_kernel<float><<<g2, 256, 0, s>>>(reinterpret_cast<const float2*>(state),
+                                                       total, cl, bl, chunk_sums, block_cum,
+                                                       nblocks, uniforms_dev, reps,
+                                                       out_indices_dev);
+  else
+    sv_sample_resolve_kernel<double><<<g2, 256, 0, s>>>(reinterpret_cast<const double2*>(state),
+                                                        total, cl, bl, chunk_sums, block_cum,
+                                                        nblocks, uniforms_dev, reps,
+                                                        out_indices_dev);
+  B2Q_LAUNCH_CHECK("sv_sample_resolve_kernel");
+  return B2Q_OK;
+}
+
+extern "C" int b2q_cdf_sample(const double* probs_dev, uint64_t count, const double* uniforms_dev,
+                              uint64_t reps, uint64_t* out_indices_dev, void* stream) {
+  B2Q_REQUIRE(probs_dev != nullptr && count >= 1, "bad distribution");
+  if (reps == 0) return B2Q_OK;
+  B2Q_REQUIRE(uniforms_dev != nullptr && out_indices_dev != nullptr, "null argument");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  double* cum = nullptr;
+  B2Q_CUDA_CHECK(cudaMallocAsync((void**)&cum, sizeof(double) * count, s));
+  scan_inclusive_kernel<<<1, 1024, 0, s>>>(probs_dev, cum, count);
+  B2Q_LAUNCH_CHECK("scan_inclusive_kernel");
+  cdf_search_kernel<<<(unsigned)((reps + 255) / 256), 256, 0, s>>>(cum, count, uniforms_dev, reps,
+                                                                   out_indices_dev);
+  B2Q_LAUNCH_CHECK("cdf_search_kernel");
+  B2Q_CUDA_CHECK(cudaFreeAsync(cum, s));
+  return B2Q_OK;
+}
+
+extern "C" int b2q_unpack_bits(const uint64_t* indices_dev, uint64_t reps, const int* bits, int m,
+                               uint8_t* out_dev, void* stream) {
+  if (reps == 0 || m == 0) return B2Q_OK;
+  B2Q_REQUIRE(indices_dev != nullptr && bits != nullptr && out_dev != nullptr, "null argument");
+  B2Q_REQUIRE(m <= 64, "m too large");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  UnpackParams p;
+  p.m = m;
+  for (int q = 0; q < m; ++q) {
+    B2Q_REQUIRE(bits[q] >= 0 && bits[q] < 64, "bit out of range");
+    p.bits[q] = bits[q];
+  }
+  const uint64_t total_out = reps * (uint64_t)m;
+  const uint64_t blocks = (total_out + 255) / 256;
+  B2Q_REQUIRE(blocks <= 0x7fffffffull, "grid too large");
+  unpack_bits_kernel<<<(unsigned)blocks, 256, 0, s>>>(indices_dev, total_out, p, out_dev);
+  B2Q_LAUNCH_CHECK("unpack_bits_kernel");
+  return B2Q_OK;
+}
+
+static int collapse_common(void* state, int dtype, uint64_t total, uint64_t mask, uint64_t want,
+                           double scale, cudaStream_t s) {
+  const unsigned blocks = stride_grid(total, 256);
+  if (dtype == B2Q_C64)
+    sv_collapse_kernel<float><<<blocks, 256, 0, s>>>(reinterpret_cast<float2*>(state), total,
+                                                     mask, want, (float)scale);
+  else
+    sv_collapse_kernel<double><<<blocks, 256, 0, s>>>(reinterpret_cast<double2*>(state), total,
+                                                      mask, want, scale);
+  B2Q_LAUNCH_CHECK("sv_collapse_kernel");
+  return B2Q_OK;
+}
+
+extern "C" int b2q_sv_collapse(void* state, int dtype, int n_qubits, const int* bits,
+                               const int* values, int m, double prob, void* stream) {
+  B2Q_REQUIRE(state != nullptr && (m == 0 || (bits && values)), "null argument");
+  B2Q_CHECK_DTYPE(dtype);
+  B2Q_REQUIRE(prob > 0.0, "collapse onto an outcome of probability %g", prob);
+  uint64_t mask = 0, want = 0;
+  for (int q = 0; q < m; ++q) {
+    B2Q_REQUIRE(bits[q] >= 0 && bits[q] < n_qubits, "bit out of range");
+    mask |= 1ull << bits[q];
+    if (values[q]) want |= 1ull << bits[q];
+  }
+  // The reference divides by np.sqrt(probs[result]) computed in the state's
+  // real dtype (sim/state_vector.py:318).
+  const double scale = dtype == B2Q_C64 ? 1.0 / (double)sqrtf((float)prob) : 1.0 / sqrt(prob);
+  return collapse_common(state, dtype, 1ull << n_qubits, mask, want, scale,
+                         reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b2q_dm_collapse(void* rho, int dtype, int n_qubits, const int* bits,
+                               const int* values, int m, double prob, void* stream) {
+  B2Q_REQUIRE(rho != nullptr && (m == 0 || (bits && values)), "null argument");
+  B2Q_CHECK_DTYPE(dtype);
+  B2Q_REQUIRE(prob > 0.0, "collapse onto an outcome of probability %g", prob);
+  B2Q_REQUIRE(2 * n_qubits <= 40, "density matrix too large");
+  uint64_t mask = 0, want = 0;
+  for (int q = 0; q < m; ++q) {
+    B2Q_REQUIRE(bits[q] >= 0 && bits[q] < n_qubits, "bit out of range");
+    mask |= (1ull << bits[q]) | (1ull << (bits[q] + n_qubits));
+    if (values[q]) want |= (1ull << bits[q]) | (1ull << (bits[q] + n_qubits));
+  }
+  return collapse_common(rho, dtype, 1ull << (2 * n_qubits), mask, want, 1.0 / prob,
+                         reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b2q_sv_pauli_expectation(const void* state, int dtype, int n_qubits,
+                                        uint64_t x_mask, uint64_t z_mask, double* out_re_im,
+                                        void* stream) {
+  B2Q_REQUIRE(state != nullptr && out_re_im != nullptr, "null argument");
+  B2Q_CHECK_DTYPE(dtype);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const uint64_t total = 1ull << n_qubits;
+  B2Q_REQUIRE(x_mask < total && z_mask < total, "mask out of range");
+  const unsigned blocks = stride_grid(total, 256);
+  double* partial = nullptr;
+  B2Q_CUDA_CHECK(cudaMallocAsync((void**)&partial, sizeof(double) * 2 * (blocks + 1), s));
+  if (dtype == B2Q_C64)
+    sv_pauli_partial_kernel<float><<<blocks, 256, 0, s>>>(reinterpret_cast<const float2*>(state),
+                                                          total, x_mask, z_mask, partial);
+  else
+    sv_pauli_partial_kernel<double><<<blocks, 256, 0, s>>>(
+        reinterpret_cast<const double2*>(state), total, x_mask, z_mask, partial);
+  B2Q_LAUNCH_CHECK("sv_pauli_partial_kernel");
+  final_sum_kernel<<<1, 256, 0, s>>>(partial, blocks, 2, partial + 2 * blocks);
+  B2Q_LAUNCH_CHECK("final_sum_kernel");
+  double h[2];
+  B2Q_CUDA_CHECK(
+      cudaMemcpyAsync(h, partial + 2 * blocks, sizeof(double) * 2, cudaMemcpyDeviceToHost, s));
+  B2Q_CUDA_CHECK(cudaStreamSynchronize(s));
+  B2Q_CUDA_CHECK(cudaFreeAsync(partial, s));
+  // P|i> = i^{nY} (-1)^{popcount(i & z)} |i ^ x>, nY = popcount(x & z)
+  const int ny = __builtin_popcountll(x_mask & z_mask) & 3;
+  double re = h[0], im = h[1];
+  for (int t = 0; t < ny; ++t) {  // multiply by i
+    const double nr = -im, ni = re;
+    re = nr;
+    im = ni;
+  }
+  out_re_im[0] = re;
+  out_re_im[1] = im;
+  return B2Q_OK;
+}
+
+extern "C" int b2q_dm_diagonal(const void* rho, int dtype, int n_qubits, double* probs_dev,
+                               void* stream) {
+  B2Q_REQUIRE(rho != nullptr && probs_dev != nullptr, "null argument");
+  B2Q_CHECK_DTYPE(dtype);
+  B2Q_REQUIRE(2 * n_qubits <= 40, "density matrix too large");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const uint64_t dim = 1ull << n_qubits;
+  const unsigned blocks = stride_grid(dim, 256);
+  if (dtype == B2Q_C64)
+    dm_diag_kernel<float><<<blocks, 256, 0, s>>>(reinterpret_cast<const float2*>(rho), n_qubits,
+                                                 probs_dev);
+  else
+    dm_diag_kernel<double><<<blocks, 256, 0, s>>>(reinterpret_cast<const double2*>(rho), n_qubits,
+                                                  probs_dev);
+  B2Q_LAUNCH_CHECK("dm_diag_kernel");
+  return B2Q_OK;
+}
+
+extern "C" int b2q_dm_trace(const void* rho, int dtype, int n_qubits, double* out, void* stream) {
+  B2Q_REQUIRE(rho != nullptr && out != nullptr, "null argument");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const uint64_t dim = 1ull << n_qubits;
+  double* probs = nullptr;
+  B2Q_CUDA_CHECK(cudaMallocAsync((void**)&probs, sizeof(double) * (dim + 1), s));
+  int rc = b2q_dm_diagonal(rho, dtype, n_qubits, probs, stream);
+  if (rc != B2Q_OK) return rc;
+  final_sum_kernel<<<1, 256, 0, s>>>(probs, dim, 1, probs + dim);
+  B2Q_LAUNCH_CHECK("final_sum_kernel");
+  B2Q_CUDA_CHECK(cudaMemcpyAsync(out, probs + dim, sizeof(double), cudaMemcpyDeviceToHost, s));
+  B2Q_CUDA_CHECK(cudaStreamSynchronize(s));
+  B2Q_CUDA_CHECK(cudaFreeAsync(probs, s));
+  return B2Q_OK;
+}
+
+static int pack_common(void* shard, int dtype, int n_local, const int* local_bits, int g,
+                       void* packed, int dir, void* stream) {
+  B2Q_REQUIRE(shard != nullptr && packed != nullptr && local_bits != nullptr, "null argument");
+  B2Q_CHECK_DTYPE(dtype);
+  B2Q_REQUIRE(g >= 1 && g <= 8 && g <= n_local, "g=%d out of range", g);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  PackParams p;
+  p.n_local = n_local;
+  p.g = g;
+  // Segment index: local_bits[0] = MSB.
+  std::vector<std::pair<int, int>> pr;
+  for (int i = 0; i < g; ++i) {
+    B2Q_REQUIRE(local_bits[i] >= 0 && local_bits[i] < n_local, "local bit out of range");
+    pr.push_back({local_bits[i], g - 1 - i});
+  }
+  std::sort(pr.begin(), pr.end());
+  for (int i = 0; i < g; ++i) {
+    B2Q_REQUIRE(i == 0 || pr[i].first != pr[i - 1].first, "duplicate local bit");
+    p.pos[i] = pr[i].first;
+    p.rank_of[i] = pr[i].second;
+  }
+  const uint64_t total = 1ull << n_local;
+  const unsigned blocks = stride_grid(total, 256);
+  if (dtype == B2Q_C64) {
+    if (dir == 0)
+      dist_pack_kernel<float, 0><<<blocks, 256, 0, s>>>(reinterpret_cast<float2*>(shard),
+                                                        reinterpret_cast<float2*>(packed), p);
+    else
+      dist_pack_kernel<float, 1><<<blocks, 256, 0, s>>>(reinterpret_cast<float2*>(shard),
+                                                        reinterpret_cast<float2*>(packed), p);
+  } else {
+    if (dir == 0)
+      dist_pack_kernel<double, 0><<<blocks, 256, 0, s>>>(reinterpret_cast<double2*>(shard),
+                                                         reinterpret_cast<double2*>(packed), p);
+    else
+      dist_pack_kernel<double, 1><<<blocks, 256, 0, s>>>(reinterpret_cast<double2*>(shard),
+                                                         reinterpret_cast<double2*>(packed), p);
+  }
+  B2Q_LAUNCH_CHECK("dist_pack_kernel");
+  return B2Q_OK;
+}
+
+extern "C" int b2q_dist_pack(const void* shard, int dtype, int n_local, const int* local_bits,
+                             int g, void* packed, void* stream) {
+  return pack_common(const_cast<void*>(shard), dtype, n_local, local_bits, g, packed, 0, stream);
+}
+
+extern "C" int b2q_dist_unpack(void* shard, int dtype, int n_local, const int* local_bits, int g,
+                               const void* packed, void* stream) {
+  return pack_common(shard, dtype, n_local, local_bits, g, const_cast<void*>(packed), 1, stream);
+}

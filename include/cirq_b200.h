@@ -1,0 +1,185 @@
+/*
+ * cirq_b200 — C-ABI of the B200-native state evolution library for Cirq.
+ *
+ * The reference (quantumlib/Cirq 1.8.0.dev0) is pure Python; it has no FFI for
+ * this path.  The boundary a Cirq maintainer binds is therefore defined here:
+ * every entry point replaces one numpy-backed function of the reference and
+ * cites it (paths relative to cirq-core/cirq/).  INTEGRATION.md shows the
+ * ctypes stub for each.
+ *
+ * Conventions
+ *   - All functions return 0 on success, non-zero on error; the message of the
+ *     last error on the calling thread is returned by b2q_last_error().
+ *   - Device buffers are owned by the caller (torch tensors in the Python
+ *     host layer).  They are passed as raw device pointers.  Host arrays are
+ *     read (or written) during the call only.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *     Kernels are asynchronous on that stream; functions that return scalars
+ *     or fill host arrays synchronise the stream before returning.
+ *   - dtype: B2Q_C64 = interleaved float (re,im), B2Q_C128 = interleaved double.
+ *   - A state vector over n qubits is complex[2^n]; qubit "axis" a of Cirq
+ *     (axis 0 = first qubit = most significant bit of the flat index,
+ *     sim/state_vector_simulation_state.py:33-62) is BIT POSITION p = n-1-a.
+ *     All `targets` / `bits` arguments are bit positions.
+ *   - Gate matrices are row-major complex128[2^k * 2^k] on the host, with the
+ *     FIRST target as the most significant bit of the row/column index — the
+ *     convention of `U.reshape((2,)*2k)` in
+ *     protocols/apply_unitary_protocol.py:440-466.  They are cast to the
+ *     state dtype before use (same file, :450).
+ *   - A density matrix over n qubits is stored as a 2n-qubit vector
+ *     (row bits above column bits), sim/density_matrix_simulation_state.py:33-60.
+ */
+#ifndef CIRQ_B200_H_
+#define CIRQ_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2Q_C64 0
+#define B2Q_C128 1
+
+#define B2Q_OK 0
+#define B2Q_ERR_INVALID 1
+#define B2Q_ERR_CUDA 2
+#define B2Q_ERR_UNSUPPORTED 3
+
+/* ---- library / device ---------------------------------------------------- */
+
+/* ABI version (major*1000 + minor). */
+int b2q_version(void);
+/* Message of the last error raised on this thread ("" if none). */
+const char* b2q_last_error(void);
+/* Fills sm_count, total HBM bytes, compute capability (major*10+minor) of the
+ * current device. */
+int b2q_device_info(int* sm_count, uint64_t* hbm_bytes, int* cc);
+/* Count of kernel launches issued by this library since load (all threads). */
+uint64_t b2q_launch_count(void);
+
+/* ---- state vector: initialise / copy ------------------------------------- */
+
+/* |basis_index> in the computational basis (big-endian int of
+ * qis/states.py:766-832 `to_valid_state_vector(int)` — one_hot on device). */
+int b2q_sv_init_basis(void* state, int dtype, int n_qubits, uint64_t basis_index, void* stream);
+/* state <- state * (re + i*im); replaces in-place scalar multiplies such as
+ * sim/state_vector_simulation_state.py:371 (remove_qubits phase fold). */
+int b2q_sv_scale(void* state, int dtype, int n_qubits, double re, double im, void* stream);
+
+/* ---- state vector: gate application -------------------------------------- */
+
+/* psi <- (M on `targets`) psi, in place, one streaming pass over HBM.
+ * Replaces linalg/transformations.py:105-172 (targeted_left_multiply),
+ * :310-380 (apply_matrix_to_slices) and the per-gate slice fast paths in
+ * ops/*.py::_apply_unitary_.  M need not be unitary (Kraus operators, and the
+ * superoperators of the density-matrix path use the same entry point).
+ * k = number of targets (1 <= k <= 10; k <= 5 (c64) / 4 (c128) take the
+ * register-tiled streaming kernels, larger k a generic out-of-place kernel
+ * that needs `scratch`, a device buffer of the state's size, else NULL). */
+int b2q_sv_apply_matrix(void* state, int dtype, int n_qubits, const double* matrix_c128,
+                        const int* targets, int k, void* scratch, void* stream);
+
+/* Applies `num_gates` gates in order with one call (one pass each).  ks[g]
+ * targets for gate g are consecutive in `targets`; its matrix (complex128,
+ * 4^k entries) is consecutive in `matrices_c128`.  Replaces the op loop of
+ * sim/simulator_base.py:199-212 for runs of unitary ops. */
+int b2q_sv_apply_batch(void* state, int dtype, int n_qubits, int num_gates, const int* ks,
+                       const int* targets, const double* matrices_c128, void* scratch,
+                       void* stream);
+
+/* psi[i] <- diag[bits of i at `targets`] * psi[i]  (diag: complex128[2^k],
+ * first target = MSB).  Replaces the diagonal slice fast paths
+ * ops/common_gates.py:658-669 (Z), :1072-1083 (CZ) and
+ * ops/fourier_transform.py:137-146 (PhaseGradient).  1 <= k <= 16. */
+int b2q_sv_apply_diagonal(void* state, int dtype, int n_qubits, const double* diag_c128,
+                          const int* targets, int k, void* stream);
+
+/* ---- state vector: reductions / read-out --------------------------------- */
+
+/* *out = sum |psi_i|^2 (float64 accumulation). np.linalg.norm()**2 of
+ * sim/state_vector_simulator.py:134 and state_vector_simulation_state.py:231. */
+int b2q_sv_norm2(const void* state, int dtype, int n_qubits, double* out, void* stream);
+
+/* out[j] = psi[indices[j]], out complex128[count].  Replaces the fancy-index
+ * gather of sim/state_vector_simulator.py:95-98 (compute_amplitudes). */
+int b2q_sv_gather(const void* state, int dtype, int n_qubits, const uint64_t* indices,
+                  uint64_t count, double* out_c128, void* stream);
+
+/* probs_out[v] = sum over i with (bits of i at `bits`, first = MSB of v) == v
+ * of |psi_i|^2, float64[2^m], NOT normalised.  Replaces
+ * sim/simulation_utils.py:24-65 (state_probabilities_by_indices) fused with
+ * the |psi|^2 pass of sim/state_vector.py:220.  m <= 24. `probs_dev` is a
+ * caller-owned device buffer of 2^m doubles; `probs_host` (may be NULL)
+ * receives a copy. */
+int b2q_sv_marginal_probs(const void* state, int dtype, int n_qubits, const int* bits, int m,
+                          double* probs_dev, double* probs_host, void* stream);
+
+/* Draws `reps` basis states from |psi|^2 by inverse CDF: sample j is the
+ * smallest index i with cdf(i) > uniforms[j] * total, the rule of
+ * numpy RandomState.choice (cdf.searchsorted(u, side='right')) used at
+ * sim/state_vector.py:226.  `uniforms_dev`: device float64[reps] in [0,1).
+ * `out_indices_dev`: device uint64[reps].  `workspace` from
+ * b2q_sv_sample_workspace_bytes().  Replaces sim/state_vector.py:170-232 for
+ * the all-qubits case; arbitrary subsets/orders go through
+ * b2q_unpack_bits on the sampled indices. */
+int b2q_sv_sample(const void* state, int dtype, int n_qubits, const double* uniforms_dev,
+                  uint64_t reps, uint64_t* out_indices_dev, void* workspace,
+                  uint64_t workspace_bytes, void* stream);
+uint64_t b2q_sv_sample_workspace_bytes(int n_qubits, uint64_t reps);
+
+/* Inverse-CDF draw from a small explicit distribution held on the device
+ * (float64 probs_dev[count], need not be normalised): out_indices_dev[j] =
+ * searchsorted(cumsum(p)/sum(p), uniforms[j], 'right').  One CTA. Used for
+ * marginals (measurement of a few qubits, density-matrix diagonals). */
+int b2q_cdf_sample(const double* probs_dev, uint64_t count, const double* uniforms_dev,
+                   uint64_t reps, uint64_t* out_indices_dev, void* stream);
+
+/* out[j*m + q] = bit `bits[q]` of indices[j] (uint8 0/1): the big-endian digit
+ * loop of sim/state_vector.py:228-232 (value/digits.py:139-200) on device. */
+int b2q_unpack_bits(const uint64_t* indices_dev, uint64_t reps, const int* bits, int m,
+                    uint8_t* out_dev, void* stream);
+
+/* Projects onto bits==values at `bits` and renormalises: amplitudes whose
+ * bits differ are zeroed, the rest scaled by 1/sqrt(prob).  Replaces the mask
+ * write + divide of sim/state_vector.py:300-318. */
+int b2q_sv_collapse(void* state, int dtype, int n_qubits, const int* bits, const int* values,
+                    int m, double prob, void* stream);
+
+/* <psi| P |psi> for a Pauli string given as x_mask/z_mask over bit positions
+ * (Y = both; the (-i)^{#Y} phase is applied inside).  Writes re, im.
+ * Replaces ops/pauli_string.py:625-655. */
+int b2q_sv_pauli_expectation(const void* state, int dtype, int n_qubits, uint64_t x_mask,
+                             uint64_t z_mask, double* out_re_im, void* stream);
+
+/* ---- density matrix (rho as a 2n-qubit vector) ---------------------------- */
+
+/* probs_dev[i] = Re rho[i,i], float64[2^n]: sim/density_matrix_utils.py:185-192. */
+int b2q_dm_diagonal(const void* rho, int dtype, int n_qubits, double* probs_dev, void* stream);
+/* *out = Re trace(rho). */
+int b2q_dm_trace(const void* rho, int dtype, int n_qubits, double* out, void* stream);
+/* Zeroes rows and columns whose measured bits differ from `values`, divides
+ * by prob: sim/density_matrix_utils.py:167-180. */
+int b2q_dm_collapse(void* rho, int dtype, int n_qubits, const int* bits, const int* values, int m,
+                    double prob, void* stream);
+
+/* ---- sharded state vector: global<->local qubit swap ---------------------- */
+
+/* Packs, for each of the 2^g combinations of the `g` local bit positions
+ * `local_bits`, the sub-block of the shard having those bits == combination
+ * into a contiguous segment of `packed` (segment c holds 2^(n_local-g)
+ * amplitudes in index order).  After an all-to-all of the segments,
+ * b2q_dist_unpack writes segment c back to the positions with local_bits ==
+ * c.  Together with the exchange this realises the global<->local qubit
+ * swap of DESIGN.md §multi-GPU (no reference counterpart; closest is the
+ * index-only SWAP of sim/simulation_product_state.py:95-108). */
+int b2q_dist_pack(const void* shard, int dtype, int n_local, const int* local_bits, int g,
+                  void* packed, void* stream);
+int b2q_dist_unpack(void* shard, int dtype, int n_local, const int* local_bits, int g,
+                    const void* packed, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CIRQ_B200_H_ */
