@@ -47,21 +47,55 @@ __device__ __forceinline__ double abs2(const typename Cplx<real>::type& a) {
 
 // ---- block-wise norm --------------------------------------------------------
 
+// 16-byte streaming access helpers: V16<real> is the 16-byte vector type, holding
+// 2 complex64 or 1 complex128 amplitudes.
+template <typename real>
+struct V16;
+template <>
+struct V16<float> {
+  using type = float4;
+  static constexpr int kElems = 2;
+  static __device__ __forceinline__ double abs2sum(const float4& v) {
+    return (double)(v.x * v.x + v.y * v.y) + (double)(v.z * v.z + v.w * v.w);
+  }
+};
+template <>
+struct V16<double> {
+  using type = double2;
+  static constexpr int kElems = 1;
+  static __device__ __forceinline__ double abs2sum(const double2& v) {
+    return v.x * v.x + v.y * v.y;
+  }
+};
+
+constexpr int kStreamUnroll = 4;
+
 // partial[b] = sum of |psi|^2 over a grid-strided subset; deterministic order.
+// Each thread keeps kStreamUnroll independent 16-byte loads in flight.
 template <typename real>
 __global__ void __launch_bounds__(256)
     sv_norm_partial_kernel(const typename Cplx<real>::type* __restrict__ state, uint64_t total,
                            double* __restrict__ partial) {
-  using C = typename Cplx<real>::type;
-  double acc = 0.0;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (uint64_t)gridDim.x * blockDim.x) {
-    const C a = state[i];
-    acc += abs2<real>(a);
+  using V = typename V16<real>::type;
+  const uint64_t nvec = total / V16<real>::kElems;  // total >= 2 for c64 is ensured by the host
+  const V* __restrict__ vp = reinterpret_cast<const V*>(state);
+  double acc[kStreamUnroll];
+#pragma unroll
+  for (int u = 0; u < kStreamUnroll; ++u) acc[u] = 0.0;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + (kStreamUnroll - 1) * stride < nvec; i += kStreamUnroll * stride) {
+    V v[kStreamUnroll];
+#pragma unroll
+    for (int u = 0; u < kStreamUnroll; ++u) v[u] = vp[i + u * stride];
+#pragma unroll
+    for (int u = 0; u < kStreamUnroll; ++u) acc[u] += V16<real>::abs2sum(v[u]);
   }
+  for (; i < nvec; i += stride) acc[0] += V16<real>::abs2sum(vp[i]);
+  double a = (acc[0] + acc[1]) + (acc[2] + acc[3]);
   __shared__ double sm[8];
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  a = warp_sum(a);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = a;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0;
@@ -99,30 +133,60 @@ __global__ void set_one_kernel(typename Cplx<real>::type* state, uint64_t index)
 }
 
 template <typename real>
-__global__ void __launch_bounds__(256)
-    sv_scale_kernel(typename Cplx<real>::type* __restrict__ state, uint64_t total, real re,
-                    real im) {
-  using C = typename Cplx<real>::type;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (uint64_t)gridDim.x * blockDim.x) {
-    const C a = state[i];
-    state[i] = cmul<real>(re, im, a);
-  }
+__device__ __forceinline__ typename V16<real>::type scale_v16(const typename V16<real>::type& v,
+                                                              real re, real im);
+template <>
+__device__ __forceinline__ float4 scale_v16<float>(const float4& v, float re, float im) {
+  return make_float4(re * v.x - im * v.y, re * v.y + im * v.x, re * v.z - im * v.w,
+                     re * v.w + im * v.z);
+}
+template <>
+__device__ __forceinline__ double2 scale_v16<double>(const double2& v, double re, double im) {
+  return make_double2(re * v.x - im * v.y, re * v.y + im * v.x);
 }
 
-// Keeps amplitudes with (i & mask) == want scaled by `scale`, zeroes the rest.
+// state <- (re + i im) * state on the amplitudes with (index & mask) == want,
+// zero elsewhere (mask == 0: plain scaling).  16-byte vectors, 4 in flight.
 template <typename real>
 __global__ void __launch_bounds__(256)
-    sv_collapse_kernel(typename Cplx<real>::type* __restrict__ state, uint64_t total,
-                       uint64_t mask, uint64_t want, real scale) {
-  using C = typename Cplx<real>::type;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (uint64_t)gridDim.x * blockDim.x) {
+    sv_scale_mask_kernel(typename Cplx<real>::type* __restrict__ state, uint64_t total,
+                         uint64_t mask, uint64_t want, real re, real im) {
+  using V = typename V16<real>::type;
+  constexpr int E = V16<real>::kElems;
+  const uint64_t nvec = total / E;
+  V* __restrict__ vp = reinterpret_cast<V*>(state);
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  auto apply = [&](uint64_t vi, V v) {
+    V r = scale_v16<real>(v, re, im);
+    if (mask) {
+      const uint64_t e0 = vi * E;
+      if constexpr (E == 2) {
+        if ((e0 & mask) != want) r.x = r.y = 0;
+        if (((e0 | 1ull) & mask) != want) r.z = r.w = 0;
+      } else {
+        if ((e0 & mask) != want) r.x = r.y = 0;
+      }
+    }
+    return r;
+  };
+  for (; i + (kStreamUnroll - 1) * stride < nvec; i += kStreamUnroll * stride) {
+    V v[kStreamUnroll];
+#pragma unroll
+    for (int u = 0; u < kStreamUnroll; ++u) v[u] = vp[i + u * stride];
+#pragma unroll
+    for (int u = 0; u < kStreamUnroll; ++u) vp[i + u * stride] = apply(i + u * stride, v[u]);
+  }
+  for (; i < nvec; i += stride) vp[i] = apply(i, vp[i]);
+}
+
+// Scalar fallback for the 1-amplitude complex64 state (n = 0).
+template <typename real>
+__global__ void sv_scale_tiny_kernel(typename Cplx<real>::type* state, uint64_t total,
+                                     uint64_t mask, uint64_t want, real re, real im) {
+  for (uint64_t i = threadIdx.x; i < total; i += blockDim.x) {
     if ((i & mask) == want) {
-      C a = state[i];
-      a.x *= scale;
-      a.y *= scale;
-      state[i] = a;
+      state[i] = cmul<real>(re, im, state[i]);
     } else {
       state[i] = make_c<real>(0, 0);
     }
@@ -242,6 +306,16 @@ __global__ void sv_marginal_small_kernel(const typename Cplx<real>::type* __rest
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   atomicAdd(&probs[extract_bits_msb_first(i, p.bits, p.m)], abs2<real>(state[i]));
+}
+
+// Marginal of an explicit probability vector (density-matrix diagonals, n <= 20).
+__global__ void probs_marginal_kernel(const double* __restrict__ probs,
+                                      const __grid_constant__ MarginalParams p,
+                                      double* __restrict__ out) {
+  const uint64_t total = 1ull << p.n;
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  atomicAdd(&out[extract_bits_msb_first(i, p.bits, p.m)], probs[i]);
 }
 
 // ---- prefix scan (single CTA) -----------------------------------------------
@@ -541,16 +615,26 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Grid for grid-stride kernels: enough CTAs to cover the work, capped at 16
+// resident waves of 256 threads on the 148 SMs.
 inline unsigned stride_grid(uint64_t work_items, int threads) {
   const uint64_t b = (work_items + threads - 1) / threads;
-  return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(b, 148ull * 32));
+  return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(b, 148ull * 8 * 16));
 }
 
 template <typename real>
 int norm2_t(const void* state, int n, double* out_host, cudaStream_t s) {
   using C = typename Cplx<real>::type;
   const uint64_t total = 1ull << n;
-  const unsigned blocks = stride_grid(total, 256);
+  if (total < 2) {
+    // single amplitude: read it back directly
+    C h;
+    B2Q_CUDA_CHECK(cudaMemcpyAsync(&h, state, sizeof(C), cudaMemcpyDeviceToHost, s));
+    B2Q_CUDA_CHECK(cudaStreamSynchronize(s));
+    *out_host = (double)h.x * (double)h.x + (double)h.y * (double)h.y;
+    return B2Q_OK;
+  }
+  const unsigned blocks = stride_grid(total / V16<real>::kElems / kStreamUnroll, 256);
   double* partial = nullptr;
   B2Q_CUDA_CHECK(cudaMallocAsync((void**)&partial, sizeof(double) * (blocks + 1), s));
   sv_norm_partial_kernel<real><<<blocks, 256, 0, s>>>(reinterpret_cast<const C*>(state), total,
@@ -589,21 +673,32 @@ extern "C" int b2q_sv_init_basis(void* state, int dtype, int n_qubits, uint64_t 
   return B2Q_OK;
 }
 
+static int scale_mask_common(void* state, int dtype, uint64_t total, uint64_t mask, uint64_t want,
+                             double re, double im, cudaStream_t s) {
+  if (dtype == B2Q_C64) {
+    if (total < 2) {
+      sv_scale_tiny_kernel<float><<<1, 32, 0, s>>>(reinterpret_cast<float2*>(state), total, mask,
+                                                   want, (float)re, (float)im);
+    } else {
+      const unsigned blocks = stride_grid(total / 2 / kStreamUnroll, 256);
+      sv_scale_mask_kernel<float><<<blocks, 256, 0, s>>>(reinterpret_cast<float2*>(state), total,
+                                                         mask, want, (float)re, (float)im);
+    }
+  } else {
+    const unsigned blocks = stride_grid(total / kStreamUnroll, 256);
+    sv_scale_mask_kernel<double><<<blocks, 256, 0, s>>>(reinterpret_cast<double2*>(state), total,
+                                                        mask, want, re, im);
+  }
+  B2Q_LAUNCH_CHECK("sv_scale_mask_kernel");
+  return B2Q_OK;
+}
+
 extern "C" int b2q_sv_scale(void* state, int dtype, int n_qubits, double re, double im,
                             void* stream) {
   B2Q_REQUIRE(state != nullptr, "null state");
   B2Q_CHECK_DTYPE(dtype);
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const uint64_t total = 1ull << n_qubits;
-  const unsigned blocks = stride_grid(total, 256);
-  if (dtype == B2Q_C64)
-    sv_scale_kernel<float><<<blocks, 256, 0, s>>>(reinterpret_cast<float2*>(state), total,
-                                                  (float)re, (float)im);
-  else
-    sv_scale_kernel<double><<<blocks, 256, 0, s>>>(reinterpret_cast<double2*>(state), total, re,
-                                                   im);
-  B2Q_LAUNCH_CHECK("sv_scale_kernel");
-  return B2Q_OK;
+  return scale_mask_common(state, dtype, 1ull << n_qubits, 0, 0, re, im,
+                           reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int b2q_sv_norm2(const void* state, int dtype, int n_qubits, double* out,
@@ -810,15 +905,7 @@ extern "C" int b2q_unpack_bits(const uint64_t* indices_dev, uint64_t reps, const
 
 static int collapse_common(void* state, int dtype, uint64_t total, uint64_t mask, uint64_t want,
                            double scale, cudaStream_t s) {
-  const unsigned blocks = stride_grid(total, 256);
-  if (dtype == B2Q_C64)
-    sv_collapse_kernel<float><<<blocks, 256, 0, s>>>(reinterpret_cast<float2*>(state), total,
-                                                     mask, want, (float)scale);
-  else
-    sv_collapse_kernel<double><<<blocks, 256, 0, s>>>(reinterpret_cast<double2*>(state), total,
-                                                      mask, want, scale);
-  B2Q_LAUNCH_CHECK("sv_collapse_kernel");
-  return B2Q_OK;
+  return scale_mask_common(state, dtype, total, mask, want, scale, 0.0, s);
 }
 
 extern "C" int b2q_sv_collapse(void* state, int dtype, int n_qubits, const int* bits,
@@ -908,6 +995,33 @@ extern "C" int b2q_dm_diagonal(const void* rho, int dtype, int n_qubits, double*
     dm_diag_kernel<double><<<blocks, 256, 0, s>>>(reinterpret_cast<const double2*>(rho), n_qubits,
                                                   probs_dev);
   B2Q_LAUNCH_CHECK("dm_diag_kernel");
+  return B2Q_OK;
+}
+
+extern "C" int b2q_probs_marginal(const double* probs_dev, int n_qubits, const int* bits, int m,
+                                  double* out_dev, void* stream) {
+  B2Q_REQUIRE(probs_dev != nullptr && bits != nullptr && out_dev != nullptr, "null argument");
+  B2Q_REQUIRE(n_qubits >= 0 && n_qubits <= 30, "n_qubits out of range");
+  B2Q_REQUIRE(m >= 1 && m <= 24 && m <= n_qubits, "m=%d out of range", m);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  MarginalParams p;
+  p.n = n_qubits;
+  p.zb = 0;
+  p.m = m;
+  p.n_meas_high = 0;
+  p.log2_iters = 0;
+  p.num_warps = 0;
+  uint64_t seen = 0;
+  for (int q = 0; q < m; ++q) {
+    B2Q_REQUIRE(bits[q] >= 0 && bits[q] < n_qubits, "bit out of range");
+    B2Q_REQUIRE(!((seen >> bits[q]) & 1ull), "duplicate bit %d", bits[q]);
+    seen |= 1ull << bits[q];
+    p.bits[q] = bits[q];
+  }
+  B2Q_CUDA_CHECK(cudaMemsetAsync(out_dev, 0, sizeof(double) << m, s));
+  const uint64_t total = 1ull << n_qubits;
+  probs_marginal_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(probs_dev, p, out_dev);
+  B2Q_LAUNCH_CHECK("probs_marginal_kernel");
   return B2Q_OK;
 }
 

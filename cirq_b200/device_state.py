@@ -1,0 +1,368 @@
+"""Device-resident dense quantum state: the thin host mirror of the C-ABI.
+
+``DeviceState`` owns one torch tensor in HBM (torch is used for allocation,
+streams and copies only) and forwards every numeric operation to the sm_100a
+kernels in ``libcirq_b200.so`` through ctypes.  It knows nothing about Cirq:
+qubits are BIT POSITIONS of the flat index (bit p = n-1-axis).  It replaces
+the numpy buffers of the reference's ``_BufferedStateVector``
+(cirq-core/cirq/sim/state_vector_simulation_state.py:33-307) and
+``_BufferedDensityMatrix`` (sim/density_matrix_simulation_state.py:33-250);
+unlike them it needs no second buffer: every kernel is in place.
+
+There is no CPU fallback: without a CUDA device or the built library every
+method raises ``B200Error``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Sequence
+
+import numpy as np
+
+from cirq_b200 import _lib
+from cirq_b200._lib import B200Error, check
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise B200Error('cirq_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+    return torch
+
+
+def _stream_ptr(torch):
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class DeviceState:
+    """complex[2^n_bits] in HBM (a state vector, or a density matrix with
+    n_bits = 2 * n_qubits, row bits above column bits)."""
+
+    def __init__(self, n_bits: int, dtype, tensor=None):
+        torch = _torch()
+        self.n_bits = int(n_bits)
+        self.dtype = np.dtype(dtype)
+        self.code = _lib.dtype_code(self.dtype)
+        self._real = torch.float32 if self.code == _lib.C64 else torch.float64
+        if tensor is None:
+            tensor = torch.empty((1 << self.n_bits, 2), dtype=self._real, device='cuda')
+        self.tensor = tensor
+        self._lib = _lib.load()
+        self._scratch = None
+
+    # ------------------------------------------------------------------ creation
+
+    @classmethod
+    def basis(cls, n_bits: int, dtype, index: int = 0) -> 'DeviceState':
+        st = cls(n_bits, dtype)
+        torch = _torch()
+        check(
+            st._lib.b2q_sv_init_basis(
+                st.ptr, st.code, st.n_bits, ctypes.c_uint64(int(index)), _stream_ptr(torch)
+            )
+        )
+        return st
+
+    @classmethod
+    def from_numpy(cls, array: np.ndarray, dtype=None) -> 'DeviceState':
+        torch = _torch()
+        flat = np.ascontiguousarray(np.asarray(array).reshape(-1))
+        dtype = np.dtype(dtype or flat.dtype)
+        flat = flat.astype(dtype, copy=False)
+        n_bits = int(flat.size).bit_length() - 1
+        if flat.size != 1 << n_bits:
+            raise ValueError(f'state size {flat.size} is not a power of two')
+        real = np.float32 if dtype == np.complex64 else np.float64
+        host = torch.from_numpy(flat.view(real).reshape(-1, 2).copy())
+        st = cls(n_bits, dtype, tensor=host.to('cuda'))
+        return st
+
+    def copy(self) -> 'DeviceState':
+        return DeviceState(self.n_bits, self.dtype, tensor=self.tensor.clone())
+
+    # ------------------------------------------------------------------ plumbing
+
+    @property
+    def ptr(self):
+        return ctypes.c_void_p(self.tensor.data_ptr())
+
+    @property
+    def nbytes(self) -> int:
+        return self.tensor.numel() * self.tensor.element_size()
+
+    def to_numpy(self) -> np.ndarray:
+        """Flat complex ndarray (device -> host copy of the whole state)."""
+        host = self.tensor.cpu().numpy()
+        return host.view(self.dtype).reshape(-1)
+
+    def synchronize(self):
+        _torch().cuda.current_stream().synchronize()
+
+    # ------------------------------------------------------------------ gates
+
+    def apply_matrix(self, matrix, bits: Sequence[int]) -> None:
+        """psi <- (M on bits) psi.  bits[0] is the MSB of M's index."""
+        torch = _torch()
+        k = len(bits)
+        m = _lib.as_c128_buffer(matrix)
+        if m.size != (1 << k) ** 2:
+            raise ValueError(f'matrix of size {m.size} does not act on {k} qubits')
+        max_fast = 5 if self.code == _lib.C64 else 4
+        scratch = ctypes.c_void_p(0)
+        if k > max_fast:
+            if self._scratch is None:
+                self._scratch = torch.empty_like(self.tensor)
+            scratch = ctypes.c_void_p(self._scratch.data_ptr())
+        check(
+            self._lib.b2q_sv_apply_matrix(
+                self.ptr, self.code, self.n_bits, m.ctypes.data, _lib.int_array(bits), k, scratch,
+                _stream_ptr(torch),
+            )
+        )
+
+    def apply_batch(self, gates: Sequence[tuple]) -> None:
+        """Applies [(matrix, bits), ...] in order with one library call."""
+        torch = _torch()
+        if not gates:
+            return
+        max_fast = 5 if self.code == _lib.C64 else 4
+        if any(len(b) > max_fast for _, b in gates):
+            for m, b in gates:
+                self.apply_matrix(m, b)
+            return
+        ks = [len(b) for _, b in gates]
+        targets = [int(t) for _, b in gates for t in b]
+        mats = np.concatenate([_lib.as_c128_buffer(m).reshape(-1) for m, _ in gates])
+        check(
+            self._lib.b2q_sv_apply_batch(
+                self.ptr, self.code, self.n_bits, len(gates), _lib.int_array(ks),
+                _lib.int_array(targets), mats.ctypes.data, ctypes.c_void_p(0), _stream_ptr(torch),
+            )
+        )
+
+    def apply_diagonal(self, diag, bits: Sequence[int]) -> None:
+        torch = _torch()
+        d = _lib.as_c128_buffer(diag).reshape(-1)
+        check(
+            self._lib.b2q_sv_apply_diagonal(
+                self.ptr, self.code, self.n_bits, d.ctypes.data, _lib.int_array(bits), len(bits),
+                _stream_ptr(torch),
+            )
+        )
+
+    def scale(self, factor: complex) -> None:
+        torch = _torch()
+        factor = complex(factor)
+        check(
+            self._lib.b2q_sv_scale(
+                self.ptr, self.code, self.n_bits, factor.real, factor.imag, _stream_ptr(torch)
+            )
+        )
+
+    # ------------------------------------------------------------------ read-out
+
+    def norm2(self) -> float:
+        torch = _torch()
+        out = ctypes.c_double(0.0)
+        check(self._lib.b2q_sv_norm2(self.ptr, self.code, self.n_bits, ctypes.byref(out), _stream_ptr(torch)))
+        return out.value
+
+    def amplitudes(self, indices: Sequence[int]) -> np.ndarray:
+        torch = _torch()
+        idx = np.ascontiguousarray(np.asarray(indices, dtype=np.uint64).reshape(-1))
+        out = np.empty(idx.size, dtype=np.complex128)
+        check(
+            self._lib.b2q_sv_gather(
+                self.ptr, self.code, self.n_bits, idx.ctypes.data, idx.size, out.ctypes.data,
+                _stream_ptr(torch),
+            )
+        )
+        return out
+
+    def marginal_probs_device(self, bits: Sequence[int]):
+        """Unnormalised float64 marginal over `bits` (bits[0] = MSB), on device."""
+        torch = _torch()
+        m = len(bits)
+        probs = torch.empty(1 << m, dtype=torch.float64, device='cuda')
+        check(
+            self._lib.b2q_sv_marginal_probs(
+                self.ptr, self.code, self.n_bits, _lib.int_array(bits), m,
+                ctypes.c_void_p(probs.data_ptr()), ctypes.c_void_p(0), _stream_ptr(torch),
+            )
+        )
+        return probs
+
+    def marginal_probs(self, bits: Sequence[int]) -> np.ndarray:
+        return self.marginal_probs_device(bits).cpu().numpy()
+
+    def sample_indices_device(self, uniforms: np.ndarray):
+        """Inverse-CDF draw of full basis-state indices; uniforms in [0, 1)."""
+        torch = _torch()
+        u = np.ascontiguousarray(np.asarray(uniforms, dtype=np.float64).reshape(-1))
+        reps = u.size
+        u_dev = torch.from_numpy(u).to('cuda')
+        out = torch.empty(max(reps, 1), dtype=torch.int64, device='cuda')
+        ws_bytes = int(self._lib.b2q_sv_sample_workspace_bytes(self.n_bits, reps))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device='cuda')
+        check(
+            self._lib.b2q_sv_sample(
+                self.ptr, self.code, self.n_bits, ctypes.c_void_p(u_dev.data_ptr()), reps,
+                ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ws.data_ptr()), ws_bytes,
+                _stream_ptr(torch),
+            )
+        )
+        return out[:reps]
+
+    def sample_indices(self, uniforms: np.ndarray) -> np.ndarray:
+        return self.sample_indices_device(uniforms).cpu().numpy().astype(np.uint64)
+
+    @staticmethod
+    def cdf_sample_device(probs_dev, uniforms: np.ndarray):
+        """searchsorted(cumsum(p)/sum(p), u, 'right') on the device."""
+        torch = _torch()
+        lib = _lib.load()
+        u = np.ascontiguousarray(np.asarray(uniforms, dtype=np.float64).reshape(-1))
+        reps = u.size
+        u_dev = torch.from_numpy(u).to('cuda')
+        out = torch.empty(max(reps, 1), dtype=torch.int64, device='cuda')
+        check(
+            lib.b2q_cdf_sample(
+                ctypes.c_void_p(probs_dev.data_ptr()), probs_dev.numel(),
+                ctypes.c_void_p(u_dev.data_ptr()), reps, ctypes.c_void_p(out.data_ptr()),
+                _stream_ptr(torch),
+            )
+        )
+        return out[:reps]
+
+    @staticmethod
+    def unpack_bits_device(indices_dev, bits: Sequence[int]):
+        """uint8[reps, m] on device: column q = bit bits[q] of each index."""
+        torch = _torch()
+        lib = _lib.load()
+        reps = indices_dev.numel()
+        m = len(bits)
+        out = torch.empty((reps, m), dtype=torch.uint8, device='cuda')
+        if reps and m:
+            check(
+                lib.b2q_unpack_bits(
+                    ctypes.c_void_p(indices_dev.data_ptr()), reps, _lib.int_array(bits), m,
+                    ctypes.c_void_p(out.data_ptr()), _stream_ptr(torch),
+                )
+            )
+        return out
+
+    def sample_bits(self, bits: Sequence[int], uniforms: np.ndarray) -> np.ndarray:
+        """uint8[reps, len(bits)] drawn from |psi|^2; mirrors sample_state_vector.
+
+        All bits in natural order -> hierarchical sampler on the full state
+        (same CDF order as the reference); up to 24 bits -> marginal in the
+        requested order (again the reference's CDF order); otherwise full-state
+        draw followed by bit extraction (same distribution).
+        """
+        bits = [int(b) for b in bits]
+        m = len(bits)
+        u = np.asarray(uniforms, dtype=np.float64).reshape(-1)
+        if m == 0 or u.size == 0:
+            return np.zeros((u.size, m), dtype=np.uint8)
+        natural = bits == list(range(self.n_bits - 1, -1, -1))
+        if natural or m > 24:
+            idx = self.sample_indices_device(u)
+            return self.unpack_bits_device(idx, bits).cpu().numpy()
+        probs = self.marginal_probs_device(bits)
+        idx = self.cdf_sample_device(probs, u)
+        return self.unpack_bits_device(idx, [m - 1 - q for q in range(m)]).cpu().numpy()
+
+    def collapse(self, bits: Sequence[int], values: Sequence[int], prob: float) -> None:
+        torch = _torch()
+        check(
+            self._lib.b2q_sv_collapse(
+                self.ptr, self.code, self.n_bits, _lib.int_array(bits), _lib.int_array(values),
+                len(bits), float(prob), _stream_ptr(torch),
+            )
+        )
+
+    def pauli_expectation(self, x_mask: int, z_mask: int) -> complex:
+        torch = _torch()
+        out = (ctypes.c_double * 2)()
+        check(
+            self._lib.b2q_sv_pauli_expectation(
+                self.ptr, self.code, self.n_bits, ctypes.c_uint64(int(x_mask)),
+                ctypes.c_uint64(int(z_mask)), out, _stream_ptr(torch),
+            )
+        )
+        return complex(out[0], out[1])
+
+    # ------------------------------------------------------------------ density matrix view
+
+    def dm_diagonal_device(self):
+        torch = _torch()
+        n = self.n_bits // 2
+        probs = torch.empty(1 << n, dtype=torch.float64, device='cuda')
+        check(
+            self._lib.b2q_dm_diagonal(
+                self.ptr, self.code, n, ctypes.c_void_p(probs.data_ptr()), _stream_ptr(torch)
+            )
+        )
+        return probs
+
+    @staticmethod
+    def probs_marginal_device(probs_dev, n_qubits: int, bits: Sequence[int]):
+        """Marginal of a float64[2^n] device vector over `bits` (bits[0] = MSB)."""
+        torch = _torch()
+        lib = _lib.load()
+        m = len(bits)
+        out = torch.empty(1 << m, dtype=torch.float64, device='cuda')
+        check(
+            lib.b2q_probs_marginal(
+                ctypes.c_void_p(probs_dev.data_ptr()), int(n_qubits), _lib.int_array(bits), m,
+                ctypes.c_void_p(out.data_ptr()), _stream_ptr(torch),
+            )
+        )
+        return out
+
+    def dm_trace(self) -> float:
+        torch = _torch()
+        out = ctypes.c_double(0.0)
+        check(self._lib.b2q_dm_trace(self.ptr, self.code, self.n_bits // 2, ctypes.byref(out), _stream_ptr(torch)))
+        return out.value
+
+    def dm_collapse(self, bits: Sequence[int], values: Sequence[int], prob: float) -> None:
+        torch = _torch()
+        check(
+            self._lib.b2q_dm_collapse(
+                self.ptr, self.code, self.n_bits // 2, _lib.int_array(bits),
+                _lib.int_array(values), len(bits), float(prob), _stream_ptr(torch),
+            )
+        )
+
+    def dm_apply_channel(self, kraus_ops, bits: Sequence[int]) -> None:
+        """rho <- sum_i K_i rho K_i^dagger as ONE pass with the superoperator
+        sum_i K_i (x) conj(K_i) on (row bits, column bits)."""
+        n = self.n_bits // 2
+        sup = None
+        for k in kraus_ops:
+            k = np.asarray(k, dtype=np.complex128)
+            term = np.kron(k, np.conj(k))
+            sup = term if sup is None else sup + term
+        self.apply_matrix(sup, [b + n for b in bits] + list(bits))
+
+    # ------------------------------------------------------------------ sharding
+
+    def dist_pack(self, local_bits: Sequence[int], packed) -> None:
+        torch = _torch()
+        check(
+            self._lib.b2q_dist_pack(
+                self.ptr, self.code, self.n_bits, _lib.int_array(local_bits), len(local_bits),
+                ctypes.c_void_p(packed.data_ptr()), _stream_ptr(torch),
+            )
+        )
+
+    def dist_unpack(self, local_bits: Sequence[int], packed) -> None:
+        torch = _torch()
+        check(
+            self._lib.b2q_dist_unpack(
+                self.ptr, self.code, self.n_bits, _lib.int_array(local_bits), len(local_bits),
+                ctypes.c_void_p(packed.data_ptr()), _stream_ptr(torch),
+            )
+        )

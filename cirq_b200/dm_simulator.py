@@ -1,0 +1,365 @@
+"""B200 density-matrix simulator: a drop-in for ``cirq.DensityMatrixSimulator``.
+
+rho over n qubits is stored as a 2n-"qubit" vector in HBM (flat index = row *
+2^n + column; row bits above column bits — the layout of the reference's
+``(2,)*2n`` tensor, sim/density_matrix_simulation_state.py:33-60).  Every
+operation becomes a gate on that vector, applied by the same streaming
+kernels as the state-vector path:
+
+  * unitary U on qubits Q      ->  U on the row bits of Q, conj(U) on the column bits
+                                   (``_apply_unitary``, protocols/apply_channel_protocol.py:274-294)
+  * channel {K_i} on qubits Q  ->  the superoperator sum_i K_i (x) conj(K_i) on
+                                   (row bits, column bits) of Q  (``_apply_kraus``, :297-356;
+                                   the reference does copy + 2 multiplies + accumulate PER Kraus
+                                   operator, ~16 passes for a 1-qubit depolarising channel; here
+                                   it is one pass, and it fuses with neighbouring gates)
+
+Operations are queued and fused exactly as in the state-vector simulator, so
+e.g. a 2-qubit gate followed by depolarising noise on both qubits is a single
+4-"qubit" pass over rho.
+"""
+from __future__ import annotations
+
+from typing import Any, Sequence
+
+import numpy as np
+
+from cirq_b200._cirq_compat import import_cirq
+from cirq_b200.device_state import DeviceState
+from cirq_b200.fusion import GateFuser
+
+cirq = import_cirq()
+
+from cirq import ops, protocols, qis, study, value  # noqa: E402
+from cirq.sim import density_matrix_simulator as _ref_dm  # noqa: E402
+from cirq.sim import simulator, simulator_base  # noqa: E402
+from cirq.sim.simulation_state import SimulationState, strat_act_on_from_apply_decompose  # noqa: E402
+
+_MAX_DIRECT_QUBITS = 3  # widest op whose Kraus/unitary matrices are requested directly
+
+
+class B200DensityMatrix(qis.QuantumStateRepresentation):
+    """Device-resident replacement of ``_BufferedDensityMatrix`` (no scratch
+    buffers: the reference keeps three)."""
+
+    def __init__(self, dev: DeviceState, num_qubits: int, max_fused_qubits: int = 4):
+        self._dev = dev
+        self._n = int(num_qubits)
+        self._max_fused = int(max_fused_qubits)
+        self._fuser = GateFuser(self._max_fused)
+        self._qid_shape = (2,) * self._n
+        self.passes = 0
+
+    @classmethod
+    def create(cls, *, initial_state: Any = 0, qid_shape, dtype=np.complex64, max_fused_qubits=4):
+        if any(d != 2 for d in qid_shape):
+            raise ValueError(
+                f'cirq_b200 simulates qubits only (dimension 2); got qid_shape={qid_shape}'
+            )
+        n = len(qid_shape)
+        if isinstance(initial_state, (int, np.integer)):
+            index = int(initial_state)
+            if index < 0 or index >= (1 << n):
+                raise ValueError(
+                    f'initial_state={index} was out of range for {n} qubits (qid_shape={qid_shape})'
+                )
+            dev = DeviceState.basis(2 * n, dtype, index * ((1 << n) + 1))
+        else:
+            if isinstance(initial_state, np.ndarray) and dtype and initial_state.dtype != dtype:
+                initial_state = initial_state.astype(dtype)
+            rho = qis.to_valid_density_matrix(initial_state, n, qid_shape=qid_shape, dtype=dtype)
+            dev = DeviceState.from_numpy(np.asarray(rho).reshape(-1), dtype)
+        return cls(dev, n, max_fused_qubits)
+
+    # ---- bit maps ---------------------------------------------------------------------------
+
+    def _col_bits(self, axes: Sequence[int]) -> list[int]:
+        return [self._n - 1 - int(a) for a in axes]
+
+    def _row_bits(self, axes: Sequence[int]) -> list[int]:
+        return [2 * self._n - 1 - int(a) for a in axes]
+
+    # ---- queue ------------------------------------------------------------------------------
+
+    def queue_unitary(self, u: np.ndarray, axes: Sequence[int]) -> None:
+        if len(axes) == 0:
+            return  # |c|^2 = 1 for a unitary scalar: rho is unchanged
+        u = np.asarray(u, dtype=np.complex128)
+        self._fuser.add(u, self._row_bits(axes))
+        self._fuser.add(np.conj(u), self._col_bits(axes))
+
+    def queue_kraus(self, kraus_ops: Sequence[np.ndarray], axes: Sequence[int]) -> None:
+        k = len(axes)
+        if k == 0:
+            scale = sum(abs(complex(np.asarray(op).reshape(-1)[0])) ** 2 for op in kraus_ops)
+            self.flush()
+            self._dev.scale(scale)
+            return
+        sup = None
+        for op in kraus_ops:
+            op = np.asarray(op, dtype=np.complex128).reshape(1 << k, 1 << k)
+            term = np.kron(op, np.conj(op))
+            sup = term if sup is None else sup + term
+        self._fuser.add(sup, self._row_bits(axes) + self._col_bits(axes))
+
+    def flush(self) -> None:
+        if len(self._fuser) == 0:
+            return
+        blocks = self._fuser.blocks()
+        self._fuser.clear()
+        self._dev.apply_batch(blocks)
+        self.passes += len(blocks)
+
+    @property
+    def device_state(self) -> DeviceState:
+        self.flush()
+        return self._dev
+
+    # ---- QuantumStateRepresentation ---------------------------------------------------------
+
+    def copy(self, deep_copy_buffers: bool = True) -> 'B200DensityMatrix':
+        self.flush()
+        return B200DensityMatrix(self._dev.copy(), self._n, self._max_fused)
+
+    def _marginal_device(self, axes: Sequence[int]):
+        """Unnormalised float64 marginal of Re diag(rho) over `axes` (first axis
+        = MSB), on the device: ``_probs`` of sim/density_matrix_utils.py:185-192."""
+        diag = self._dev.dm_diagonal_device()
+        return DeviceState.probs_marginal_device(diag, self._n, self._col_bits(axes))
+
+    def measure(self, axes: Sequence[int], seed=None) -> list[int]:
+        """``measure_density_matrix`` (sim/density_matrix_utils.py:97-182)."""
+        axes = list(axes)
+        if not axes:
+            return []
+        self.flush()
+        prng = value.parse_random_state(seed)
+        m = len(axes)
+        u = float(prng.random_sample())
+        probs = self._marginal_device(axes)
+        pick = int(DeviceState.cdf_sample_device(probs, np.array([u])).cpu()[0])
+        values = [(pick >> (m - 1 - q)) & 1 for q in range(m)]
+        p = np.clip(probs.cpu().numpy(), 0, None)
+        self._dev.dm_collapse(self._col_bits(axes), values, float(p[pick] / p.sum()))
+        return values
+
+    def sample(self, axes: Sequence[int], repetitions: int = 1, seed=None) -> np.ndarray:
+        """``sample_density_matrix`` (sim/density_matrix_utils.py:31-94)."""
+        if repetitions < 0:
+            raise ValueError(f'Number of repetitions cannot be negative. Was {repetitions}')
+        axes = [int(a) for a in axes]
+        for a in axes:
+            if a < 0 or a >= self._n:
+                raise IndexError(f'Out of range indices in {axes}, must be less than {self._n}')
+        m = len(axes)
+        if repetitions == 0 or m == 0:
+            return np.zeros(shape=(repetitions, m), dtype=np.int8)
+        self.flush()
+        prng = value.parse_random_state(seed)
+        uniforms = prng.random_sample(repetitions)
+        probs = self._marginal_device(axes)
+        idx = DeviceState.cdf_sample_device(probs, uniforms)
+        bits = DeviceState.unpack_bits_device(idx, [m - 1 - q for q in range(m)])
+        return bits.cpu().numpy().astype(np.int8)
+
+    @property
+    def supports_factor(self) -> bool:
+        return False
+
+    @property
+    def can_represent_mixed_states(self) -> bool:
+        return True
+
+    def to_numpy_tensor(self) -> np.ndarray:
+        self.flush()
+        return self._dev.to_numpy().reshape(self._qid_shape * 2)
+
+
+class B200DensityMatrixSimulationState(SimulationState[B200DensityMatrix]):
+    """Replaces ``DensityMatrixSimulationState``
+    (sim/density_matrix_simulation_state.py:252-354)."""
+
+    def __init__(
+        self,
+        *,
+        prng=None,
+        qubits=None,
+        initial_state: Any = 0,
+        dtype=np.complex64,
+        classical_data=None,
+        max_fused_qubits: int = 4,
+    ):
+        qubits = tuple(qubits) if qubits is not None else ()
+        state = B200DensityMatrix.create(
+            initial_state=initial_state,
+            qid_shape=tuple(q.dimension for q in qubits),
+            dtype=dtype,
+            max_fused_qubits=max_fused_qubits,
+        )
+        super().__init__(state=state, prng=prng, qubits=qubits, classical_data=classical_data)
+        self._host_cache = None
+
+    def _act_on_fallback_(self, action: Any, qubits, allow_decompose: bool = True) -> bool:
+        self._host_cache = None
+        strats = [_strat_apply_channel]
+        if allow_decompose:
+            strats.append(strat_act_on_from_apply_decompose)
+        for strat in strats:
+            result = strat(action, self, qubits)
+            if result is True:
+                return True
+            assert result is NotImplemented, str(result)
+        raise TypeError(
+            "Can't simulate operations that don't implement "
+            "SupportsUnitary, SupportsConsistentApplyUnitary, "
+            f"SupportsMixture or SupportsKraus or is a measurement: {action!r}"
+        )
+
+    def _perform_measurement(self, qubits) -> list[int]:
+        self._host_cache = None
+        return super()._perform_measurement(qubits)
+
+    def copy(self, deep_copy_buffers: bool = True):
+        out = super().copy(deep_copy_buffers)
+        out._host_cache = None
+        return out
+
+    @property
+    def target_tensor(self) -> np.ndarray:
+        if self._host_cache is None:
+            self._host_cache = self._state.to_numpy_tensor()
+        return self._host_cache
+
+    @property
+    def device_state(self) -> DeviceState:
+        return self._state.device_state
+
+    @property
+    def qid_shape(self) -> tuple[int, ...]:
+        return self._state._qid_shape
+
+    def __repr__(self) -> str:
+        return (
+            'cirq_b200.B200DensityMatrixSimulationState('
+            f'qubits={self.qubits!r}, classical_data={self.classical_data!r})'
+        )
+
+
+def can_decompose(action: Any, qubits) -> bool:
+    if isinstance(action, ops.Gate):
+        return protocols.decompose_once_with_qubits(action, qubits, None) is not None
+    return protocols.decompose_once(action, None) is not None
+
+
+def _strat_apply_channel(action: Any, args: B200DensityMatrixSimulationState, qubits) -> bool:
+    """Strategy order of ``protocols.apply_channel``
+    (protocols/apply_channel_protocol.py:239-262): unitary first, else Kraus
+    operators (``kraus`` also covers mixtures, protocols/kraus_protocol.py:138-227)."""
+    n = len(qubits)
+    axes = args.get_axes(qubits)
+    wide = n > _MAX_DIRECT_QUBITS
+    if protocols.has_unitary(action) and not (wide and not hasattr(action, '_unitary_')):
+        u = protocols.unitary(action, None)
+        if u is not None:
+            args._state.queue_unitary(u, axes)
+            return True
+    if wide and can_decompose(action, qubits):
+        return NotImplemented
+    ks = protocols.kraus(action, default=None)
+    if ks is None:
+        return NotImplemented
+    args._state.queue_kraus(ks, axes)
+    return True
+
+
+class B200DensityMatrixStepResult(_ref_dm.DensityMatrixStepResult):
+    """Step result; ``density_matrix()`` downloads rho on first use."""
+
+
+class B200DensityMatrixTrialResult(_ref_dm.DensityMatrixTrialResult):
+    @property
+    def device_state(self) -> DeviceState:
+        """rho in HBM as complex[4^n] (row-major)."""
+        return self._get_merged_sim_state().device_state
+
+
+class B200DensityMatrixSimulator(
+    simulator_base.SimulatorBase[
+        'B200DensityMatrixStepResult',
+        'B200DensityMatrixTrialResult',
+        'B200DensityMatrixSimulationState',
+    ],
+    simulator.SimulatesExpectationValues,
+):
+    """Drop-in for ``cirq.DensityMatrixSimulator`` (sim/density_matrix_simulator.py:32-262)."""
+
+    def __init__(
+        self,
+        *,
+        dtype=np.complex64,
+        noise: 'cirq.NOISE_MODEL_LIKE' = None,
+        seed: 'cirq.RANDOM_STATE_OR_SEED_LIKE' = None,
+        split_untangled_states: bool = True,
+        max_fused_qubits: int | None = None,
+    ):
+        super().__init__(dtype=dtype, noise=noise, seed=seed, split_untangled_states=False)
+        if dtype not in {np.complex64, np.complex128}:
+            raise ValueError(f'dtype must be complex64 or complex128, was {dtype}')
+        self._max_fused = int(max_fused_qubits if max_fused_qubits is not None else 4)
+
+    def _create_partial_simulation_state(self, initial_state, qubits, classical_data):
+        if isinstance(initial_state, B200DensityMatrixSimulationState):
+            return initial_state
+        return B200DensityMatrixSimulationState(
+            qubits=qubits,
+            prng=self._prng,
+            classical_data=classical_data,
+            initial_state=initial_state,
+            dtype=self._dtype,
+            max_fused_qubits=self._max_fused,
+        )
+
+    def _can_be_in_run_prefix(self, val: Any):
+        return not protocols.measurement_keys_touched(val)
+
+    def _create_step_result(self, sim_state):
+        return B200DensityMatrixStepResult(sim_state=sim_state, dtype=self._dtype)
+
+    def _create_simulator_trial_result(self, params, measurements, final_simulator_state):
+        return B200DensityMatrixTrialResult(
+            params=params, measurements=measurements, final_simulator_state=final_simulator_state
+        )
+
+    def simulate_expectation_values_sweep(
+        self,
+        program,
+        observables,
+        params,
+        qubit_order=ops.QubitOrder.DEFAULT,
+        initial_state=None,
+        permit_terminal_measurements: bool = False,
+    ) -> list[list[float]]:
+        """tr(rho O) — sim/density_matrix_simulator.py:204-235."""
+        if not permit_terminal_measurements and program.are_any_measurements_terminal():
+            raise ValueError(
+                'Provided circuit has terminal measurements, which may '
+                'skew expectation values. If this is intentional, set '
+                'permit_terminal_measurements=True.'
+            )
+        swept_evs = []
+        qubit_order = ops.QubitOrder.as_qubit_order(qubit_order)
+        qmap = {q: i for i, q in enumerate(qubit_order.order_for(program.all_qubits()))}
+        if not isinstance(observables, list):
+            observables = [observables]
+        pslist = [ops.PauliSum.wrap(pslike) for pslike in observables]
+        for param_resolver in study.to_resolvers(params):
+            result = self.simulate(
+                program, param_resolver, qubit_order=qubit_order, initial_state=initial_state
+            )
+            swept_evs.append(
+                [
+                    obs.expectation_from_density_matrix(result.final_density_matrix, qmap)
+                    for obs in pslist
+                ]
+            )
+        return swept_evs

@@ -1,0 +1,194 @@
+"""Host-side gate scheduler: fuses a stream of small matrices into k-qubit blocks.
+
+One GPU pass over the state costs the same HBM traffic whether it applies a
+1-qubit or a 4-qubit matrix, so the scheduler's job is to minimise the number
+of passes.  The reference's fuser (``cirq.merge_k_qubit_unitaries``,
+cirq-core/cirq/transformers/merge_k_qubit_gates.py:70-114, driven by
+``_merge_operations_impl`` transformer_primitives.py:442-546) only merges two
+operations when the qubits of one are a subset of the other's (:452-455), so
+it never grows a block beyond the widest gate.  This scheduler works on
+(matrix, wires) pairs — `wires` are bit positions of the flat index — and
+grows blocks up to ``max_qubits`` wires by a frontier rule:
+
+* a block is *movable* when it is the last block on every one of its wires
+  (nothing scheduled after it touches them), so it can be executed later;
+* a new gate is merged with all the last-blocks on its wires when they are
+  all movable and the union fits; otherwise into the latest of those blocks
+  (always order-safe, see ``add``) plus whatever movable neighbours still
+  fit; otherwise it opens a new block.
+
+Matrix convention everywhere: wires[0] is the most significant bit of the
+row/column index (the ``reshape((2,)*2k)`` convention of
+protocols/apply_unitary_protocol.py:440-466).
+"""
+from __future__ import annotations
+
+from typing import Iterable, Sequence
+
+import numpy as np
+
+
+def expand_matrix(matrix: np.ndarray, wires: Sequence[int], out_wires: Sequence[int]) -> np.ndarray:
+    """Embeds `matrix` on `wires` into the space of `out_wires` (a superset),
+    acting as identity elsewhere."""
+    k = len(wires)
+    u = len(out_wires)
+    m = np.asarray(matrix, dtype=np.complex128).reshape((2,) * (2 * k))
+    if tuple(wires) == tuple(out_wires):
+        return m.reshape(1 << k, 1 << k)
+    pos = [out_wires.index(w) for w in wires]
+    full = np.eye(1 << u, dtype=np.complex128).reshape((2,) * (2 * u))
+    # contract the input legs of m with the row legs `pos` of the identity
+    res = np.tensordot(m, full, axes=(list(range(k, 2 * k)), pos))
+    # res legs: m's k output legs, then the identity's legs minus `pos`, in order
+    rest = [i for i in range(2 * u) if i not in pos]
+    order = [0] * (2 * u)
+    for j, p in enumerate(pos):
+        order[p] = j
+    for j, r in enumerate(rest):
+        order[r] = k + j
+    return np.transpose(res, order).reshape(1 << u, 1 << u)
+
+
+class _Block:
+    __slots__ = ('wires', 'matrix', 'seq', 'alive', 'count')
+
+    def __init__(self, wires, matrix, seq, count=1):
+        self.wires = tuple(wires)
+        self.matrix = matrix
+        self.seq = seq
+        self.alive = True
+        self.count = count
+
+
+class GateFuser:
+    """Accumulates gates and emits fused blocks in a valid execution order."""
+
+    def __init__(self, max_qubits: int = 4):
+        self.max_qubits = int(max_qubits)
+        self._blocks: list[_Block] = []
+        self._last: dict[int, _Block] = {}
+        self._seq = 0
+        self.num_gates = 0
+
+    def __len__(self) -> int:
+        return self.num_gates
+
+    def _movable(self, b: _Block) -> bool:
+        return all(self._last.get(w) is b for w in b.wires)
+
+    def _new_seq(self) -> int:
+        self._seq += 1
+        return self._seq
+
+    @staticmethod
+    def _union(wire_lists: Iterable[Sequence[int]]) -> tuple[int, ...]:
+        seen: dict[int, None] = {}
+        for ws in wire_lists:
+            for w in ws:
+                seen.setdefault(w, None)
+        return tuple(sorted(seen, reverse=True))
+
+    def add(self, matrix: np.ndarray, wires: Sequence[int]) -> None:
+        wires = tuple(int(w) for w in wires)
+        k = len(wires)
+        self.num_gates += 1
+        matrix = np.asarray(matrix, dtype=np.complex128).reshape(1 << k, 1 << k)
+        if k > self.max_qubits:
+            # Too wide to fuse with anything: its own block at the end.
+            self._append(_Block(wires, matrix, self._new_seq()))
+            return
+        cands: list[_Block] = []
+        for w in wires:
+            b = self._last.get(w)
+            if b is not None and b not in cands:
+                cands.append(b)
+        movable = [b for b in cands if self._movable(b)]
+
+        # 1. everything on our wires can be pulled together at the end
+        if cands and len(movable) == len(cands):
+            union = self._union([wires] + [b.wires for b in cands])
+            if len(union) <= self.max_qubits:
+                self._merge_at_end(cands, matrix, wires, union)
+                return
+        # 2. merge into the latest predecessor (order-safe: every other
+        #    predecessor on our wires is earlier, and nothing after the latest
+        #    touches any of our wires), plus movable neighbours that fit
+        if cands:
+            latest = max(cands, key=lambda b: b.seq)
+            if len(latest.wires) <= self.max_qubits:
+                union = self._union([latest.wires, wires])
+                if len(union) <= self.max_qubits:
+                    extra = []
+                    for b in sorted(movable, key=lambda b: len(b.wires)):
+                        if b is latest:
+                            continue
+                        u2 = self._union([union, b.wires])
+                        if len(u2) <= self.max_qubits:
+                            union = u2
+                            extra.append(b)
+                    self._merge_into(latest, extra, matrix, wires, union)
+                    return
+        # 3. new block, pulling in movable predecessors that fit
+        union = tuple(sorted(wires, reverse=True))
+        extra = []
+        for b in sorted(movable, key=lambda b: len(b.wires)):
+            u2 = self._union([union, b.wires])
+            if len(u2) <= self.max_qubits:
+                union = u2
+                extra.append(b)
+        self._merge_at_end(extra, matrix, wires, union)
+
+    def _append(self, block: _Block) -> None:
+        self._blocks.append(block)
+        for w in block.wires:
+            self._last[w] = block
+
+    def _compose(self, blocks: Sequence[_Block], matrix, wires, union) -> tuple[np.ndarray, int]:
+        """G . (product of the given blocks, seq order) on `union`."""
+        total = None
+        count = 1
+        for b in sorted(blocks, key=lambda b: b.seq):
+            e = expand_matrix(b.matrix, b.wires, union)
+            total = e if total is None else e @ total
+            count += b.count
+        g = expand_matrix(matrix, wires, union)
+        return (g if total is None else g @ total), count
+
+    def _merge_at_end(self, blocks, matrix, wires, union) -> None:
+        m, count = self._compose(blocks, matrix, wires, union)
+        for b in blocks:
+            b.alive = False
+        self._append(_Block(union, m, self._new_seq(), count))
+
+    def _merge_into(self, target: _Block, extra, matrix, wires, union) -> None:
+        m, count = self._compose([target] + list(extra), matrix, wires, union)
+        for b in extra:
+            b.alive = False
+        target.wires = union
+        target.matrix = m
+        target.count = count
+        # Only the wires that gained an operation move their frontier here; the
+        # target's other wires may already have later blocks.
+        for w in wires:
+            self._last[w] = target
+        for b in extra:
+            for w in b.wires:
+                self._last[w] = target
+
+    def blocks(self) -> list[tuple[np.ndarray, tuple[int, ...]]]:
+        """Fused (matrix, wires) in execution order."""
+        return [(b.matrix, b.wires) for b in self._blocks if b.alive]
+
+    def clear(self) -> None:
+        self._blocks = []
+        self._last = {}
+        self.num_gates = 0
+
+
+def fuse_gates(gates, max_qubits: int = 4):
+    """Convenience wrapper: [(matrix, wires)] -> fused [(matrix, wires)]."""
+    f = GateFuser(max_qubits)
+    for m, w in gates:
+        f.add(m, w)
+    return f.blocks()

@@ -1,0 +1,528 @@
+"""B200 state-vector simulator: a drop-in for ``cirq.Simulator``.
+
+Boundary (reference paths relative to cirq-core/cirq/): the driver classes
+``SimulatorBase`` (sim/simulator_base.py:46-352), ``SimulationState``
+(sim/simulation_state.py:35-339) and the simulator interfaces
+(sim/simulator.py) are imported from Cirq and reused unchanged; this module
+replaces what sits below them:
+
+  reference (numpy)                                   here (HBM + sm_100a kernels)
+  ------------------------------------------------    ------------------------------------
+  _BufferedStateVector                                B200StateVector
+    sim/state_vector_simulation_state.py:33-307
+  StateVectorSimulationState  (same file :310-447)    B200StateVectorSimulationState
+  Simulator / SparseSimulatorStep                     B200Simulator / B200SimulatorStep
+    sim/sparse_simulator.py:31-290
+  StateVectorTrialResult                              B200StateVectorTrialResult
+    sim/state_vector_simulator.py:107-217
+
+Gate application is LAZY: unitary operations are queued as (matrix, bits) and
+fused by ``cirq_b200.fusion.GateFuser`` into blocks of up to
+``max_fused_qubits`` qubits; the queue is flushed (one GPU pass per block)
+whenever the state is observed — measurement, sampling, copy, read-out, a
+non-unitary operation.  This keeps ``simulate_moment_steps`` semantics while
+still fusing across moments.
+"""
+from __future__ import annotations
+
+from typing import Any, Iterator, Sequence
+
+import numpy as np
+
+from cirq_b200._cirq_compat import import_cirq
+from cirq_b200.device_state import DeviceState
+from cirq_b200.fusion import GateFuser
+
+cirq = import_cirq()
+
+from cirq import ops, protocols, qis, value  # noqa: E402
+from cirq.sim import simulator, state_vector, state_vector_simulator  # noqa: E402
+from cirq.sim.simulation_state import SimulationState, strat_act_on_from_apply_decompose  # noqa: E402
+
+# Widest gate whose full unitary is requested from Cirq before falling back to
+# the decomposition strategy (mirrors the "<= 4 qubits" shortcut of
+# protocols/apply_unitary_protocol.py:375-399, one wider because a 5-qubit
+# matrix is still a single streaming pass here).
+_MAX_DIRECT_UNITARY_QUBITS = 5
+
+
+class B200StateVector(qis.QuantumStateRepresentation):
+    """Device-resident replacement of ``_BufferedStateVector``.
+
+    Holds one complex[2^n] buffer in HBM (no second buffer: kernels are in
+    place) plus the queue of not-yet-applied unitaries.
+    """
+
+    def __init__(self, dev: DeviceState, num_qubits: int, max_fused_qubits: int = 4):
+        self._dev = dev
+        self._n = int(num_qubits)
+        self._max_fused = int(max_fused_qubits)
+        self._fuser = GateFuser(self._max_fused)
+        self._qid_shape = (2,) * self._n
+        self.passes = 0  # GPU gate passes issued so far (for benchmarks)
+
+    # ------------------------------------------------------------------ creation
+
+    @classmethod
+    def create(
+        cls,
+        *,
+        initial_state: Any = 0,
+        qid_shape: tuple[int, ...],
+        dtype=np.complex64,
+        max_fused_qubits: int = 4,
+    ) -> 'B200StateVector':
+        if any(d != 2 for d in qid_shape):
+            raise ValueError(
+                f'cirq_b200 simulates qubits only (dimension 2); got qid_shape={qid_shape}'
+            )
+        n = len(qid_shape)
+        if isinstance(initial_state, (int, np.integer)):
+            # Basis state by big-endian integer, as qis.to_valid_state_vector
+            # (qis/states.py:766-832), but built on the device: at 34 qubits the
+            # reference's host-side one_hot would be a 137 GB array.
+            index = int(initial_state)
+            if index < 0 or index >= (1 << n):
+                raise ValueError(
+                    f'initial_state={index} was out of range for {n} qubits (qid_shape={qid_shape})'
+                )
+            dev = DeviceState.basis(n, dtype, index)
+        else:
+            vec = qis.to_valid_state_vector(initial_state, n, qid_shape=qid_shape, dtype=dtype)
+            dev = DeviceState.from_numpy(np.asarray(vec).reshape(-1), dtype)
+        return cls(dev, n, max_fused_qubits)
+
+    # ------------------------------------------------------------------ queue
+
+    def _bits(self, axes: Sequence[int]) -> list[int]:
+        return [self._n - 1 - int(a) for a in axes]
+
+    def queue_unitary(self, matrix: np.ndarray, axes: Sequence[int]) -> None:
+        if len(axes) == 0:
+            # a global phase / scalar: fold it into the state
+            self.flush()
+            self._dev.scale(complex(np.asarray(matrix).reshape(-1)[0]))
+            return
+        self._fuser.add(matrix, self._bits(axes))
+
+    def flush(self) -> None:
+        if len(self._fuser) == 0:
+            return
+        blocks = self._fuser.blocks()
+        self._fuser.clear()
+        self._dev.apply_batch(blocks)
+        self.passes += len(blocks)
+
+    @property
+    def device_state(self) -> DeviceState:
+        self.flush()
+        return self._dev
+
+    # ------------------------------------------------------------------ QuantumStateRepresentation
+
+    def copy(self, deep_copy_buffers: bool = True) -> 'B200StateVector':
+        self.flush()
+        out = B200StateVector(self._dev.copy(), self._n, self._max_fused)
+        return out
+
+    def measure(self, axes: Sequence[int], seed: 'cirq.RANDOM_STATE_OR_SEED_LIKE' = None) -> list[int]:
+        """Projective measurement with collapse, as ``measure_state_vector``
+        (sim/state_vector.py:235-322): one ``choice`` draw from the marginal."""
+        axes = list(axes)
+        if not axes:
+            return []
+        self.flush()
+        prng = value.parse_random_state(seed)
+        bits = self._bits(axes)
+        m = len(bits)
+        u = float(prng.random_sample())
+        if m <= 24:
+            probs = self._dev.marginal_probs_device(bits)
+            pick = int(DeviceState.cdf_sample_device(probs, np.array([u])).cpu()[0])
+            values = [(pick >> (m - 1 - q)) & 1 for q in range(m)]
+            p = probs.cpu().numpy()
+            prob = float(p[pick] / p.sum())
+            self._dev.collapse(bits, values, prob)
+        else:
+            idx = int(self._dev.sample_indices(np.array([u]))[0])
+            values = [(idx >> b) & 1 for b in bits]
+            before = self._dev.norm2()
+            self._dev.collapse(bits, values, 1.0)
+            prob = self._dev.norm2() / before
+            self._dev.scale(1.0 / np.sqrt(prob))
+        return values
+
+    def sample(
+        self,
+        axes: Sequence[int],
+        repetitions: int = 1,
+        seed: 'cirq.RANDOM_STATE_OR_SEED_LIKE' = None,
+    ) -> np.ndarray:
+        """``sample_state_vector`` (sim/state_vector.py:170-232) on the device."""
+        if repetitions < 0:
+            raise ValueError(f'Number of repetitions cannot be negative. Was {repetitions}')
+        axes = [int(a) for a in axes]
+        for a in axes:
+            if a < 0 or a >= self._n:
+                raise IndexError(f'Out of range indices in {axes}, must be less than {self._n}')
+        if repetitions == 0 or len(axes) == 0:
+            return np.zeros(shape=(repetitions, len(axes)), dtype=np.uint8)
+        self.flush()
+        prng = value.parse_random_state(seed)
+        uniforms = prng.random_sample(repetitions)
+        return self._dev.sample_bits(self._bits(axes), uniforms)
+
+    @property
+    def supports_factor(self) -> bool:
+        # One dense tensor on the device; unentangled qubits are not split off.
+        return False
+
+    # ------------------------------------------------------------------ non-unitary helpers
+
+    def apply_matrix_now(self, matrix: np.ndarray, axes: Sequence[int]) -> None:
+        self.flush()
+        self._dev.apply_matrix(matrix, self._bits(axes))
+        self.passes += 1
+
+    def norm2(self) -> float:
+        self.flush()
+        return self._dev.norm2()
+
+    def to_numpy_tensor(self) -> np.ndarray:
+        self.flush()
+        return self._dev.to_numpy().reshape(self._qid_shape)
+
+
+class B200StateVectorSimulationState(SimulationState[B200StateVector]):
+    """State and context for operations acting on a device state vector
+    (replaces ``StateVectorSimulationState``)."""
+
+    def __init__(
+        self,
+        *,
+        prng: np.random.RandomState | None = None,
+        qubits: Sequence['cirq.Qid'] | None = None,
+        initial_state: Any = 0,
+        dtype=np.complex64,
+        classical_data: 'cirq.ClassicalDataStore' | None = None,
+        max_fused_qubits: int = 4,
+    ):
+        qubits = tuple(qubits) if qubits is not None else ()
+        state = B200StateVector.create(
+            initial_state=initial_state,
+            qid_shape=tuple(q.dimension for q in qubits),
+            dtype=dtype,
+            max_fused_qubits=max_fused_qubits,
+        )
+        super().__init__(state=state, prng=prng, qubits=qubits, classical_data=classical_data)
+        self._host_cache = None
+
+    # ---- act_on entry point (protocols/act_on_protocol.py:90-170) ------------------------
+
+    def _act_on_fallback_(
+        self, action: Any, qubits: Sequence['cirq.Qid'], allow_decompose: bool = True
+    ) -> bool:
+        self._host_cache = None
+        strats = [_strat_unitary, _strat_mixture, _strat_channel]
+        if allow_decompose:
+            if (
+                len(qubits) > _MAX_DIRECT_UNITARY_QUBITS
+                and not hasattr(action, '_unitary_')
+                and _can_decompose(action, qubits)
+            ):
+                # Wide composite operation: apply its parts (each a cheap pass)
+                # instead of materialising a 2^k x 2^k matrix on the host.
+                strats.insert(0, strat_act_on_from_apply_decompose)
+            else:
+                strats.append(strat_act_on_from_apply_decompose)
+        for strat in strats:
+            result = strat(action, self, qubits)
+            if result is True:
+                return True
+            assert result is NotImplemented, str(result)
+        raise TypeError(
+            "Can't simulate operations that don't implement "
+            "SupportsUnitary, SupportsConsistentApplyUnitary, "
+            f"SupportsMixture or is a measurement: {action!r}"
+        )
+
+    def _perform_measurement(self, qubits: Sequence['cirq.Qid']) -> list[int]:
+        self._host_cache = None
+        return super()._perform_measurement(qubits)
+
+    def copy(self, deep_copy_buffers: bool = True):
+        out = super().copy(deep_copy_buffers)
+        out._host_cache = None
+        return out
+
+    # ---- read-out ------------------------------------------------------------------------
+
+    @property
+    def target_tensor(self) -> np.ndarray:
+        """Host copy of the state as a ``(2,)*n`` tensor (downloads 2^n amplitudes)."""
+        if self._host_cache is None:
+            self._host_cache = self._state.to_numpy_tensor()
+        return self._host_cache
+
+    @property
+    def device_state(self) -> DeviceState:
+        return self._state.device_state
+
+    def __repr__(self) -> str:
+        return (
+            'cirq_b200.B200StateVectorSimulationState('
+            f'qubits={self.qubits!r}, classical_data={self.classical_data!r})'
+        )
+
+
+def _can_decompose(action: Any, qubits) -> bool:
+    if isinstance(action, ops.Gate):
+        return protocols.decompose_once_with_qubits(action, qubits, None) is not None
+    return protocols.decompose_once(action, None) is not None
+
+
+def _strat_unitary(action: Any, args: B200StateVectorSimulationState, qubits) -> bool:
+    """Unitary strategy: obtain the matrix from Cirq's query protocols and queue
+    it.  Replaces ``_strat_act_on_state_vector_from_apply_unitary``
+    (state_vector_simulation_state.py:402-407): the per-gate ``_apply_unitary_``
+    numpy fast paths are never called."""
+    if not protocols.has_unitary(action):
+        return NotImplemented
+    u = protocols.unitary(action, None)
+    if u is None:
+        return NotImplemented
+    args._state.queue_unitary(u, args.get_axes(qubits))
+    return True
+
+
+def _strat_mixture(action: Any, args: B200StateVectorSimulationState, qubits) -> bool:
+    """Samples one unitary of a mixture (state_vector_simulation_state.py:183-203)."""
+    mixture = protocols.mixture(action, default=None)
+    if mixture is None:
+        return NotImplemented
+    probabilities, unitaries = zip(*mixture)
+    index = args.prng.choice(range(len(unitaries)), p=probabilities)
+    args._state.queue_unitary(unitaries[index], args.get_axes(qubits))
+    if protocols.is_measurement(action):
+        key = protocols.measurement_key_obj(action)
+        args._classical_data.record_channel_measurement(key, index)
+    return True
+
+
+def _strat_channel(action: Any, args: B200StateVectorSimulationState, qubits) -> bool:
+    """Kraus-trajectory sampling, the algorithm of
+    state_vector_simulation_state.py:205-257: try operators in order, weight =
+    ||K_i psi||^2, stop when the uniform draw is used up, renormalise."""
+    kraus_operators = protocols.kraus(action, default=None)
+    if kraus_operators is None:
+        return NotImplemented
+    state = args._state
+    axes = args.get_axes(qubits)
+    p = args.prng.random()
+    fallback_weight = 0.0
+    fallback_index = 0
+    base = state.copy()
+    chosen = None
+    index = 0
+    weight = None
+    for index, k in enumerate(kraus_operators):
+        trial = base.copy()
+        trial.apply_matrix_now(k, axes)
+        weight = trial.norm2()
+        if weight > fallback_weight:
+            fallback_weight = weight
+            fallback_index = index
+        p -= weight
+        if p < 0:
+            chosen = trial
+            break
+    assert weight is not None, 'No Kraus operators'
+    if chosen is None or weight == 0:
+        chosen = base.copy()
+        chosen.apply_matrix_now(kraus_operators[fallback_index], axes)
+        weight = fallback_weight
+        index = fallback_index
+    chosen._dev.scale(1.0 / np.sqrt(weight))
+    state._dev = chosen._dev
+    if protocols.is_measurement(action):
+        key = protocols.measurement_key_obj(action)
+        args._classical_data.record_channel_measurement(key, index)
+    return True
+
+
+class B200SimulatorStep(state_vector.StateVectorMixin, state_vector_simulator.StateVectorStepResult):
+    """Step result of ``B200Simulator`` (replaces ``SparseSimulatorStep``,
+    sim/sparse_simulator.py:221-290)."""
+
+    def __init__(self, sim_state, dtype=np.complex64):
+        qubit_map = {q: i for i, q in enumerate(sim_state.qubits)}
+        super().__init__(sim_state=sim_state, qubit_map=qubit_map)
+        self._dtype = dtype
+        self._state_vector: np.ndarray | None = None
+
+    def state_vector(self, copy: bool = False) -> np.ndarray:
+        """Host copy of the state vector (big-endian), downloaded on first use."""
+        if self._state_vector is None:
+            self._state_vector = np.array([1])
+            state = self._merged_sim_state
+            if state is not None:
+                vector = state.target_tensor
+                self._state_vector = np.reshape(vector, -1)
+        return self._state_vector.copy() if copy else self._state_vector
+
+    def __repr__(self) -> str:
+        return (
+            f'cirq_b200.B200SimulatorStep(sim_state={self._sim_state!r},'
+            f' dtype=np.{np.dtype(self._dtype)!r})'
+        )
+
+
+class B200StateVectorTrialResult(state_vector_simulator.StateVectorTrialResult):
+    """Trial result whose final state stays on the device until asked for."""
+
+    @property
+    def device_state(self) -> DeviceState:
+        """The final state in HBM (complex[2^n], big-endian)."""
+        return self._get_merged_sim_state().device_state
+
+
+class B200Simulator(
+    state_vector_simulator.SimulatesIntermediateStateVector['B200SimulatorStep'],
+    simulator.SimulatesExpectationValues,
+):
+    """Drop-in for ``cirq.Simulator`` running on one B200.
+
+    Implements SimulatesSamples / SimulatesFinalState /
+    SimulatesIntermediateState / SimulatesAmplitudes /
+    SimulatesExpectationValues: ``run``, ``run_sweep``, ``simulate``,
+    ``simulate_sweep``, ``simulate_moment_steps``, ``compute_amplitudes`` and
+    ``simulate_expectation_values`` work unchanged on ``cirq.Circuit`` objects.
+
+    Args:
+        dtype: ``np.complex64`` or ``np.complex128``.
+        noise, seed: as ``cirq.Simulator``.
+        split_untangled_states: accepted for compatibility; the device state is
+            always one dense tensor.
+        max_fused_qubits: widest fused block (one GPU pass each).
+    """
+
+    def __init__(
+        self,
+        *,
+        dtype=np.complex64,
+        noise: 'cirq.NOISE_MODEL_LIKE' = None,
+        seed: 'cirq.RANDOM_STATE_OR_SEED_LIKE' = None,
+        split_untangled_states: bool = True,
+        max_fused_qubits: int | None = None,
+    ):
+        if np.dtype(dtype).kind != 'c':
+            raise ValueError(f'dtype must be a complex type but was {dtype}')
+        if np.dtype(dtype) not in (np.dtype(np.complex64), np.dtype(np.complex128)):
+            raise ValueError(f'dtype must be complex64 or complex128 but was {dtype}')
+        super().__init__(dtype=dtype, noise=noise, seed=seed, split_untangled_states=False)
+        self._requested_split = split_untangled_states
+        if max_fused_qubits is None:
+            max_fused_qubits = 4
+        self._max_fused = int(max_fused_qubits)
+
+    def _create_partial_simulation_state(self, initial_state, qubits, classical_data):
+        if isinstance(initial_state, B200StateVectorSimulationState):
+            return initial_state
+        return B200StateVectorSimulationState(
+            qubits=qubits,
+            prng=self._prng,
+            classical_data=classical_data,
+            initial_state=initial_state,
+            dtype=self._dtype,
+            max_fused_qubits=self._max_fused,
+        )
+
+    def _create_step_result(self, sim_state):
+        return B200SimulatorStep(sim_state=sim_state, dtype=self._dtype)
+
+    def _create_simulator_trial_result(self, params, measurements, final_simulator_state):
+        return B200StateVectorTrialResult(
+            params=params, measurements=measurements, final_simulator_state=final_simulator_state
+        )
+
+    # ---- device-side result consumers -------------------------------------
+
+    def compute_amplitudes_sweep_iter(
+        self, program, bitstrings, params, qubit_order=ops.QubitOrder.DEFAULT
+    ) -> Iterator[Sequence[complex]]:
+        """Amplitudes gathered on the device instead of indexing a downloaded
+        state (sim/state_vector_simulator.py:74-98)."""
+        if isinstance(bitstrings, np.ndarray) and len(bitstrings.shape) > 1:
+            raise ValueError(
+                'The list of bitstrings must be input as a '
+                '1-dimensional array of ints. Got an array with '
+                f'shape {bitstrings.shape}.'
+            )
+        idx = [int(b) for b in bitstrings]
+        for trial_result in self.simulate_sweep_iter(program, params, qubit_order):
+            dev = trial_result.device_state
+            total = 1 << dev.n_bits
+            wrapped = [i % total if -total <= i < total else i for i in idx]
+            for i in wrapped:
+                if i < 0 or i >= total:
+                    raise IndexError(f'index {i} is out of bounds for axis 0 with size {total}')
+            amps = dev.amplitudes(wrapped).astype(self._dtype)
+            yield amps.tolist()
+
+    def simulate_expectation_values_sweep_iter(
+        self,
+        program,
+        observables,
+        params,
+        qubit_order=ops.QubitOrder.DEFAULT,
+        initial_state=None,
+        permit_terminal_measurements: bool = False,
+    ) -> Iterator[list[float]]:
+        """<psi|O|psi> computed on the device, one reduction pass per Pauli
+        string (replaces sim/sparse_simulator.py:193-218 ->
+        ops/pauli_string.py:625-655)."""
+        if not permit_terminal_measurements and program.are_any_measurements_terminal():
+            raise ValueError(
+                'Provided circuit has terminal measurements, which may '
+                'skew expectation values. If this is intentional, set '
+                'permit_terminal_measurements=True.'
+            )
+        qubit_order = ops.QubitOrder.as_qubit_order(qubit_order)
+        qmap = {q: i for i, q in enumerate(qubit_order.order_for(program.all_qubits()))}
+        if not isinstance(observables, list):
+            observables = [observables]
+        pslist = [ops.PauliSum.wrap(pslike) for pslike in observables]
+        for result in self.simulate_sweep_iter(
+            program, params, qubit_order=qubit_order, initial_state=initial_state
+        ):
+            dev = result.device_state
+            yield [pauli_sum_expectation(dev, obs, qmap) for obs in pslist]
+
+
+def pauli_masks(pauli_string, qubit_map, n_qubits: int) -> tuple[int, int]:
+    """x/z bit masks of a PauliString under axis -> bit p = n-1-axis."""
+    x = z = 0
+    for q, p in pauli_string.items():
+        if q not in qubit_map:
+            raise ValueError(f'Qubit {q} of the observable is not in the circuit')
+        bit = n_qubits - 1 - qubit_map[q]
+        if p == ops.X or p == ops.Y:
+            x |= 1 << bit
+        if p == ops.Z or p == ops.Y:
+            z |= 1 << bit
+    return x, z
+
+
+def pauli_sum_expectation(dev: DeviceState, pauli_sum, qubit_map) -> complex:
+    """sum_k c_k <psi|P_k|psi>, each term one device reduction."""
+    n = dev.n_bits
+    total = 0.0 + 0.0j
+    for ps in pauli_sum:
+        if abs(complex(ps.coefficient).imag) > 0.0001:
+            raise NotImplementedError(
+                'Cannot compute expectation value of a non-Hermitian '
+                f'PauliString <{ps}>. Coefficient must be real.'
+            )
+        x, z = pauli_masks(ps, qubit_map, n)
+        total += ps.coefficient * dev.pauli_expectation(x, z)
+    return total

@@ -157,6 +157,12 @@ int b2q_sv_pauli_expectation(const void* state, int dtype, int n_qubits, uint64_
 
 /* probs_dev[i] = Re rho[i,i], float64[2^n]: sim/density_matrix_utils.py:185-192. */
 int b2q_dm_diagonal(const void* rho, int dtype, int n_qubits, double* probs_dev, void* stream);
+/* out_dev[v] = sum of probs_dev[i] over i whose bits at `bits` (first = MSB of
+ * v) equal v; probs_dev: float64[2^n], out_dev: float64[2^m].  The marginal
+ * step of sim/density_matrix_utils.py:185-192 (`_probs` ->
+ * state_probabilities_by_indices) on a diagonal already extracted. */
+int b2q_probs_marginal(const double* probs_dev, int n_qubits, const int* bits, int m,
+                       double* out_dev, void* stream);
 /* *out = Re trace(rho). */
 int b2q_dm_trace(const void* rho, int dtype, int n_qubits, double* out, void* stream);
 /* Zeroes rows and columns whose measured bits differ from `values`, divides

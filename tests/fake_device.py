@@ -1,0 +1,125 @@
+"""TEST-ONLY stand-in for cirq_b200.device_state.DeviceState backed by the CPU
+oracle.  It lets the host-side simulator logic (queueing, fusion, flush-on-
+observe, measurement/sampling plumbing, strategy order) be exercised on a
+machine without a GPU.  Never imported by the product."""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import sv_oracle as orc
+
+
+class FakeTensor(np.ndarray):
+    def cpu(self):
+        return self
+
+    def numpy(self):
+        return np.asarray(self)
+
+    def numel(self):
+        return self.size
+
+
+def _ft(a):
+    return np.asarray(a).view(FakeTensor)
+
+
+class OracleDeviceState:
+    def __init__(self, n_bits, dtype, array=None):
+        self.n_bits = int(n_bits)
+        self.dtype = np.dtype(dtype)
+        self.array = (
+            np.zeros(1 << self.n_bits, dtype=self.dtype) if array is None else np.array(array, dtype=self.dtype)
+        )
+
+    @classmethod
+    def basis(cls, n_bits, dtype, index=0):
+        st = cls(n_bits, dtype)
+        st.array[int(index)] = 1
+        return st
+
+    @classmethod
+    def from_numpy(cls, array, dtype=None):
+        flat = np.asarray(array).reshape(-1)
+        dtype = np.dtype(dtype or flat.dtype)
+        return cls(int(flat.size).bit_length() - 1, dtype, flat.astype(dtype))
+
+    def copy(self):
+        return OracleDeviceState(self.n_bits, self.dtype, self.array.copy())
+
+    def to_numpy(self):
+        return self.array.copy()
+
+    def synchronize(self):
+        pass
+
+    def apply_matrix(self, matrix, bits):
+        self.array = orc.apply_matrix(self.array, self.n_bits, np.asarray(matrix), list(bits))
+
+    def apply_batch(self, gates):
+        for m, b in gates:
+            self.apply_matrix(m, b)
+
+    def apply_diagonal(self, diag, bits):
+        self.array = orc.apply_diagonal(self.array, self.n_bits, diag, list(bits))
+
+    def scale(self, factor):
+        self.array = (self.array * self.dtype.type(factor)).astype(self.dtype)
+
+    def norm2(self):
+        return orc.norm2(self.array)
+
+    def amplitudes(self, indices):
+        return self.array[np.asarray(indices, dtype=np.int64)].astype(np.complex128)
+
+    def marginal_probs_device(self, bits):
+        return _ft(orc.marginal_probs(self.array, self.n_bits, list(bits)))
+
+    def marginal_probs(self, bits):
+        return orc.marginal_probs(self.array, self.n_bits, list(bits))
+
+    def sample_indices_device(self, uniforms):
+        probs = orc.marginal_probs(self.array, self.n_bits, list(range(self.n_bits - 1, -1, -1)))
+        return _ft(orc.choice_indices(probs, uniforms).astype(np.int64))
+
+    def sample_indices(self, uniforms):
+        return np.asarray(self.sample_indices_device(uniforms)).astype(np.uint64)
+
+    @staticmethod
+    def cdf_sample_device(probs_dev, uniforms):
+        return _ft(orc.choice_indices(np.asarray(probs_dev), uniforms).astype(np.int64))
+
+    @staticmethod
+    def unpack_bits_device(indices_dev, bits):
+        return _ft(orc.unpack_bits(np.asarray(indices_dev), list(bits)))
+
+    @staticmethod
+    def probs_marginal_device(probs_dev, n_qubits, bits):
+        p = np.asarray(probs_dev)
+        i = np.arange(p.size, dtype=np.int64)
+        key = np.zeros_like(i)
+        for b in bits:
+            key = (key << 1) | ((i >> b) & 1)
+        return _ft(np.bincount(key, weights=p, minlength=1 << len(bits)))
+
+    def sample_bits(self, bits, uniforms):
+        bits = [int(b) for b in bits]
+        u = np.asarray(uniforms, dtype=np.float64).reshape(-1)
+        if len(bits) == 0 or u.size == 0:
+            return np.zeros((u.size, len(bits)), dtype=np.uint8)
+        return orc.sample(self.array, self.n_bits, bits, u)
+
+    def collapse(self, bits, values, prob):
+        self.array = orc.collapse(self.array, self.n_bits, list(bits), list(values), prob)
+
+    def pauli_expectation(self, x_mask, z_mask):
+        return orc.pauli_expectation(self.array, self.n_bits, x_mask, z_mask)
+
+    def dm_diagonal_device(self):
+        return _ft(orc.dm_diagonal(self.array, self.n_bits // 2))
+
+    def dm_trace(self):
+        return float(orc.dm_diagonal(self.array, self.n_bits // 2).sum())
+
+    def dm_collapse(self, bits, values, prob):
+        self.array = orc.dm_collapse(self.array, self.n_bits // 2, list(bits), list(values), prob)

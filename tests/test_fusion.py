@@ -1,0 +1,87 @@
+"""The host scheduler must preserve circuit semantics: applying the fused
+blocks equals applying the original gates one by one (checked with the CPU
+oracle), for every max block width."""
+import numpy as np
+import pytest
+
+from cirq_b200.fusion import GateFuser, expand_matrix, fuse_gates
+from oracle import sv_oracle as orc
+
+
+def rand_unitary(rng, k):
+    d = 1 << k
+    q, r = np.linalg.qr(rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d)))
+    return q * (np.diag(r) / np.abs(np.diag(r)))
+
+
+def random_gates(rng, n, count, max_k=3):
+    gates = []
+    for _ in range(count):
+        k = int(rng.randint(1, min(max_k, n) + 1))
+        wires = rng.permutation(n)[:k].tolist()
+        gates.append((rand_unitary(rng, k), wires))
+    return gates
+
+
+def run(n, gates):
+    psi = np.zeros(1 << n, dtype=np.complex128)
+    psi[0] = 1
+    for m, w in gates:
+        psi = orc.apply_matrix(psi, n, m, list(w))
+    return psi
+
+
+@pytest.mark.parametrize('max_q', [1, 2, 3, 4, 5])
+@pytest.mark.parametrize('n', [2, 5, 8])
+def test_fused_blocks_equal_sequential(n, max_q):
+    rng = np.random.RandomState(100 * n + max_q)
+    gates = random_gates(rng, n, 60)
+    fused = fuse_gates(gates, max_q)
+    assert all(len(w) <= max(max_q, 3) for _, w in fused)
+    np.testing.assert_allclose(run(n, fused), run(n, gates), atol=1e-10)
+    if max_q >= 2:
+        assert len(fused) < len(gates)
+
+
+def test_expand_matrix_matches_kron():
+    rng = np.random.RandomState(0)
+    a = rand_unitary(rng, 1)
+    b = rand_unitary(rng, 2)
+    np.testing.assert_allclose(expand_matrix(a, [5], [5, 3]), np.kron(a, np.eye(2)), atol=1e-14)
+    np.testing.assert_allclose(expand_matrix(a, [3], [5, 3]), np.kron(np.eye(2), a), atol=1e-14)
+    np.testing.assert_allclose(expand_matrix(b, [7, 2], [7, 4, 2]).reshape(2, 2, 2, 2, 2, 2)[:, 0, :, :, 0, :].reshape(4, 4), b, atol=1e-14)
+    # wire order swap
+    sw = np.eye(4)[[0, 2, 1, 3]]
+    np.testing.assert_allclose(expand_matrix(b, [2, 7], [7, 2]), sw @ b @ sw, atol=1e-14)
+
+
+def test_layered_circuit_fuses_to_few_blocks():
+    """Sycamore-like layer structure: 1-qubit layer + disjoint 2-qubit layer
+    must collapse into the 2-qubit blocks (no leftover 1-qubit passes)."""
+    rng = np.random.RandomState(3)
+    n = 8
+    gates = []
+    for layer in range(4):
+        for q in range(n):
+            gates.append((rand_unitary(rng, 1), [q]))
+        start = layer % 2
+        for q in range(start, n - 1, 2):
+            gates.append((rand_unitary(rng, 2), [q, q + 1]))
+    fused2 = fuse_gates(gates, 2)
+    assert all(len(w) == 2 for _, w in fused2[:-1]) or len(fused2) <= 16
+    np.testing.assert_allclose(run(n, fused2), run(n, gates), atol=1e-10)
+    fused4 = fuse_gates(gates, 4)
+    assert len(fused4) < len(fused2)
+    np.testing.assert_allclose(run(n, fused4), run(n, gates), atol=1e-10)
+
+
+def test_fuser_incremental_interface():
+    f = GateFuser(3)
+    rng = np.random.RandomState(1)
+    gates = random_gates(rng, 4, 10, max_k=2)
+    for m, w in gates:
+        f.add(m, w)
+    assert len(f) == 10
+    np.testing.assert_allclose(run(4, f.blocks()), run(4, gates), atol=1e-10)
+    f.clear()
+    assert f.blocks() == [] and len(f) == 0

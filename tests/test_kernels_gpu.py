@@ -1,0 +1,352 @@
+"""Parity of the CUDA path (through the C-ABI, via cirq_b200.DeviceState)
+against the CPU oracle and the committed reference goldens.  GPU only.
+
+Tolerances (north star): max-abs amplitude error 1e-5 for complex64 and
+1e-12 for complex128 on normalised states; index/bit work is bit-exact."""
+import itertools
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import sv_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+ATOL = {np.dtype(np.complex64): 1e-5, np.dtype(np.complex128): 1e-12}
+
+
+@pytest.fixture(scope='module')
+def DS():
+    from cirq_b200.device_state import DeviceState
+
+    return DeviceState
+
+
+def rand_state(rng, n, dtype):
+    v = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    v /= np.linalg.norm(v)
+    return v.astype(dtype)
+
+
+def rand_unitary(rng, k):
+    d = 1 << k
+    q, r = np.linalg.qr(rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d)))
+    return q * (np.diag(r) / np.abs(np.diag(r)))
+
+
+def rand_matrix(rng, k):
+    d = 1 << k
+    return (rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d))) / np.sqrt(d)
+
+
+def target_sets(n, k, rng, count):
+    """Mix of hand-picked position classes (vector bit, zone bits, high bits)
+    and random draws, as ordered tuples (gate order matters)."""
+    sets = set()
+    pools = [list(range(min(n, 7))), list(range(max(0, n - 6), n)), list(range(n))]
+    for pool in pools:
+        if len(pool) >= k:
+            for _ in range(count):
+                sets.add(tuple(rng.permutation(pool)[:k].tolist()))
+    low = tuple(range(k))
+    if k <= n:
+        sets.add(low)
+        sets.add(low[::-1])
+        sets.add(tuple(range(n - k, n)))
+    return sorted(sets)
+
+
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
+@pytest.mark.parametrize('n', [1, 2, 3, 5, 8, 11, 12, 13, 16, 21])
+def test_apply_matrix_matches_oracle(DS, dtype, n):
+    rng = np.random.RandomState(1000 + n)
+    max_k = 5 if dtype == np.complex64 else 4
+    for k in range(1, min(n, max_k) + 1):
+        for targets in target_sets(n, k, rng, 3 if n < 20 else 1):
+            state = rand_state(rng, n, dtype)
+            m = rand_matrix(rng, k)
+            dev = DS.from_numpy(state)
+            dev.apply_matrix(m, targets)
+            got = dev.to_numpy()
+            want = orc.apply_matrix(state, n, m, targets)
+            err = np.max(np.abs(got - want))
+            assert err <= ATOL[np.dtype(dtype)], (n, k, targets, err)
+
+
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
+def test_every_single_and_pair_position(DS, dtype):
+    """All 1-qubit positions and all ordered 2-qubit pairs at n=13: covers the
+    vector bit, every lane bit, the zone boundary and high bits."""
+    n = 13
+    rng = np.random.RandomState(7)
+    state = rand_state(rng, n, dtype)
+    for t in range(n):
+        m = rand_matrix(rng, 1)
+        dev = DS.from_numpy(state)
+        dev.apply_matrix(m, [t])
+        assert np.max(np.abs(dev.to_numpy() - orc.apply_matrix(state, n, m, [t]))) <= ATOL[np.dtype(dtype)]
+    for a, b in itertools.permutations(range(n), 2):
+        m = rand_matrix(rng, 2)
+        dev = DS.from_numpy(state)
+        dev.apply_matrix(m, [a, b])
+        err = np.max(np.abs(dev.to_numpy() - orc.apply_matrix(state, n, m, [a, b])))
+        assert err <= ATOL[np.dtype(dtype)], (a, b, err)
+
+
+def test_generic_kernel_large_k(DS):
+    rng = np.random.RandomState(5)
+    for dtype, ks in ((np.complex64, (6, 7)), (np.complex128, (5, 6))):
+        for k in ks:
+            n = 12
+            targets = rng.permutation(n)[:k].tolist()
+            state = rand_state(rng, n, dtype)
+            m = rand_matrix(rng, k)
+            dev = DS.from_numpy(state)
+            dev.apply_matrix(m, targets)
+            err = np.max(np.abs(dev.to_numpy() - orc.apply_matrix(state, n, m, targets)))
+            assert err <= ATOL[np.dtype(dtype)] * 4
+
+
+def test_golden_targeted_left_multiply(DS):
+    g = load_golden('targeted_left_multiply.npz')
+    for c in range(int(g['num_cases'])):
+        n = int(g[f'c{c}_n'])
+        state = g[f'c{c}_state']
+        dev = DS.from_numpy(state)
+        dev.apply_matrix(g[f'c{c}_matrix'], orc.axes_to_bits(n, g[f'c{c}_axes']))
+        # golden matrices are unnormalised gaussians: scale the tolerance by ||M||
+        scale = max(1.0, np.linalg.norm(g[f'c{c}_matrix'], 2))
+        err = np.max(np.abs(dev.to_numpy() - g[f'c{c}_out']))
+        assert err <= ATOL[state.dtype] * scale, (c, err)
+
+
+def test_golden_simulator_final_states(DS):
+    g = load_golden('simulator_final_states.npz')
+    for c in range(int(g['num_cases'])):
+        n = int(g[f'c{c}_n'])
+        final = g[f'c{c}_final']
+        gates = [
+            (g[f'c{c}_g{i}_u'], orc.axes_to_bits(n, g[f'c{c}_g{i}_axes']))
+            for i in range(int(g[f'c{c}_num_gates']))
+        ]
+        for batch in (False, True):
+            dev = DS.basis(n, final.dtype, 0)
+            if batch:
+                dev.apply_batch(gates)
+            else:
+                for m, b in gates:
+                    dev.apply_matrix(m, b)
+            err = np.max(np.abs(dev.to_numpy() - final))
+            assert err <= ATOL[final.dtype], (c, batch, err)
+            assert abs(dev.norm2() - 1.0) < 1e-4
+
+
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
+def test_diagonal_scale_init(DS, dtype):
+    rng = np.random.RandomState(3)
+    for n in (2, 9, 14):
+        state = rand_state(rng, n, dtype)
+        for k in (1, 2, min(n, 5)):
+            targets = rng.permutation(n)[:k].tolist()
+            d = np.exp(1j * rng.standard_normal(1 << k))
+            dev = DS.from_numpy(state)
+            dev.apply_diagonal(d, targets)
+            err = np.max(np.abs(dev.to_numpy() - orc.apply_diagonal(state, n, d, targets)))
+            assert err <= ATOL[np.dtype(dtype)]
+        dev = DS.from_numpy(state)
+        dev.scale(0.3 - 0.4j)
+        assert np.max(np.abs(dev.to_numpy() - state * (0.3 - 0.4j))) <= ATOL[np.dtype(dtype)]
+        idx = int(rng.randint(1 << n))
+        b = DS.basis(n, dtype, idx).to_numpy()
+        assert b[idx] == 1 and np.count_nonzero(b) == 1
+
+
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
+def test_norm_gather_pauli(DS, dtype):
+    rng = np.random.RandomState(11)
+    for n in (1, 4, 10, 17):
+        state = rand_state(rng, n, dtype) * 1.7
+        dev = DS.from_numpy(state)
+        assert abs(dev.norm2() - orc.norm2(state)) <= 1e-5 * orc.norm2(state)
+        idx = rng.randint(0, 1 << n, size=33)
+        np.testing.assert_array_equal(dev.amplitudes(idx), state[idx].astype(np.complex128))
+        for _ in range(4):
+            x = int(rng.randint(1 << n))
+            z = int(rng.randint(1 << n))
+            got = dev.pauli_expectation(x, z)
+            want = orc.pauli_expectation(state, n, x, z)
+            assert abs(got - want) <= (1e-5 if dtype == np.complex64 else 1e-11) * 3
+
+
+def test_golden_pauli_expectation(DS):
+    g = load_golden('pauli_expectation.npz')
+    for c in range(int(g['num_cases'])):
+        n = int(g[f'c{c}_n'])
+        x = z = 0
+        for axis, code in enumerate(g[f'c{c}_codes']):
+            b = n - 1 - axis
+            if code in (1, 2):
+                x |= 1 << b
+            if code in (2, 3):
+                z |= 1 << b
+        dev = DS.from_numpy(g[f'c{c}_state'])
+        assert abs(dev.pauli_expectation(x, z) - complex(g[f'c{c}_value'])) < 1e-11
+
+
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
+def test_marginal_probs(DS, dtype):
+    rng = np.random.RandomState(21)
+    for n in (1, 3, 6, 7, 10, 15):
+        state = rand_state(rng, n, dtype)
+        dev = DS.from_numpy(state)
+        for m in sorted({1, min(2, n), min(5, n), n}):
+            for _ in range(3):
+                bits = rng.permutation(n)[:m].tolist()
+                got = dev.marginal_probs(bits)
+                want = orc.marginal_probs(state, n, bits)
+                np.testing.assert_allclose(got, want, atol=1e-6 if dtype == np.complex64 else 1e-13)
+
+
+def test_golden_sampling_and_measurement(DS):
+    g = load_golden('sampling.npz')
+    for c in range(int(g['num_cases'])):
+        n = int(g[f'c{c}_n'])
+        state = g[f'c{c}_state']
+        bits = orc.axes_to_bits(n, g[f'c{c}_indices'])
+        m = len(bits)
+        dev = DS.from_numpy(state)
+        got = dev.sample_bits(bits, g[f'c{c}_uniforms'])
+        want = g[f'c{c}_bits']
+        assert got.dtype == np.uint8 and got.shape == want.shape
+        assert np.mean(np.any(got != want, axis=1)) <= 1 / 64 + 1e-9, c
+        # measurement: same outcome as the reference for the same uniform draw
+        probs = dev.marginal_probs_device(bits)
+        pick = int(DS.cdf_sample_device(probs, np.array([g[f'c{c}_measure_uniform']])).cpu()[0])
+        values = [(pick >> (m - 1 - q)) & 1 for q in range(m)]
+        assert values == g[f'c{c}_measure_bits'].tolist()
+        p = probs.cpu().numpy()
+        dev.collapse(bits, values, p[pick] / p.sum())
+        err = np.max(np.abs(dev.to_numpy() - g[f'c{c}_measure_state']))
+        assert err <= ATOL[state.dtype] * 4
+
+
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
+def test_full_state_sampler_matches_oracle_and_chi_squared(DS, dtype):
+    rng = np.random.RandomState(31)
+    for n in (1, 5, 7, 8, 13, 16, 18):
+        state = rand_state(rng, n, dtype)
+        dev = DS.from_numpy(state)
+        reps = 20000
+        u = rng.random_sample(reps)
+        got = dev.sample_indices(u)
+        probs = orc.marginal_probs(state, n, list(range(n - 1, -1, -1)))
+        want = orc.choice_indices(probs, u)
+        mismatch = np.mean(got != want.astype(np.uint64))
+        assert mismatch < 2e-3, (n, mismatch)
+        # chi-squared on a coarse marginal (top min(n,6) bits)
+        mbits = min(n, 6)
+        hist = np.bincount((got >> np.uint64(n - mbits)).astype(np.int64), minlength=1 << mbits)
+        expect = probs.reshape(1 << mbits, -1).sum(axis=1) * reps
+        chi2 = np.sum((hist - expect) ** 2 / np.maximum(expect, 1e-12))
+        dof = (1 << mbits) - 1
+        assert chi2 < dof + 6 * np.sqrt(2 * dof) + 10, (n, chi2)
+
+
+def test_sampler_never_returns_zero_probability_states(DS):
+    for n in (3, 9, 15):
+        for idx in (0, (1 << n) - 1, 5):
+            dev = DS.basis(n, np.complex64, idx)
+            u = np.concatenate([[0.0, 1.0 - 2**-53], np.random.RandomState(0).random_sample(100)])
+            assert np.all(dev.sample_indices(u) == idx)
+            got = dev.sample_bits(list(range(n - 1, -1, -1)), u[:5])
+            want = [(idx >> (n - 1 - a)) & 1 for a in range(n)]
+            assert np.all(got == np.array(want, dtype=np.uint8))
+
+
+def test_reference_known_answer_vectors(DS):
+    g = load_golden('reference_test_vectors.npz')
+    for x in range(8):
+        dev = DS.basis(3, np.complex64, x)
+        got = dev.sample_bits(orc.axes_to_bits(3, [2, 1, 0]), np.array([0.5]))
+        np.testing.assert_array_equal(got, g['big_endian_samples'][x])
+    dev = DS.basis(3, np.complex64, 6)
+    for perm, want in zip(g['perms'], g['perm_samples']):
+        got = dev.sample_bits(orc.axes_to_bits(3, perm), np.array([0.3]))
+        np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
+def test_density_matrix_golden_and_helpers(DS, dtype):
+    g = load_golden('density_matrix_final_states.npz')
+    for c in range(int(g['num_cases'])):
+        final = g[f'c{c}_final']
+        if final.dtype != np.dtype(dtype):
+            continue
+        n = int(g[f'c{c}_n'])
+        dev = DS.basis(2 * n, dtype, 0)
+        for i in range(int(g[f'c{c}_num_ops'])):
+            dev.dm_apply_channel(
+                list(g[f'c{c}_g{i}_kraus']), orc.axes_to_bits(n, g[f'c{c}_g{i}_axes'])
+            )
+        rho = dev.to_numpy()
+        err = np.max(np.abs(rho.reshape(final.shape) - final))
+        assert err <= ATOL[np.dtype(dtype)], (c, err)
+        assert abs(dev.dm_trace() - 1.0) < 1e-5
+        diag = dev.dm_diagonal_device().cpu().numpy()
+        np.testing.assert_allclose(diag, orc.dm_diagonal(rho, n), atol=1e-7)
+        p = orc.marginal_probs(np.sqrt(np.maximum(diag, 0)).astype(np.complex128), n, [0])
+        if p[1] > 1e-3:
+            dev.dm_collapse([0], [1], p[1] / p.sum())
+            want = orc.dm_collapse(rho, n, [0], [1], p[1] / p.sum())
+            assert np.max(np.abs(dev.to_numpy() - want)) <= ATOL[np.dtype(dtype)] * 10
+
+
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
+def test_dist_pack_unpack(DS, dtype):
+    import torch
+
+    rng = np.random.RandomState(41)
+    n = 12
+    state = rand_state(rng, n, dtype)
+    dev = DS.from_numpy(state)
+    for bits in ([11], [10, 11], [0, 5], [7, 3, 9]):
+        packed = torch.empty_like(dev.tensor)
+        dev.dist_pack(bits, packed)
+        got = packed.cpu().numpy().view(np.dtype(dtype)).reshape(-1)
+        np.testing.assert_array_equal(got, orc.dist_pack(state, n, bits))
+        dev2 = DS(n, dtype)
+        dev2.dist_unpack(bits, packed)
+        np.testing.assert_array_equal(dev2.to_numpy(), state)
+
+
+def test_full_size_properties_30q(DS):
+    """BASELINE config sizes: size-independent properties at 30 qubits c64
+    (8.6 GB state): unitarity round trip, norm, basis-state sampling."""
+    n = 30
+    rng = np.random.RandomState(2024)
+    dev = DS.basis(n, np.complex64, 0)
+    gates = []
+    for layer in range(3):
+        for k in (1, 2, 3, 4):
+            targets = rng.permutation(n)[:k].tolist()
+            gates.append((rand_unitary(rng, k), targets))
+        gates.append((rand_unitary(rng, 2), [0, 29]))
+        gates.append((rand_unitary(rng, 2), [3, 1]))
+    dev.apply_batch(gates)
+    assert abs(dev.norm2() - 1.0) < 1e-4
+    inv = [(m.conj().T, t) for m, t in reversed(gates)]
+    dev.apply_batch(inv)
+    amp0 = dev.amplitudes([0, 1, 12345])
+    assert abs(amp0[0] - 1.0) < 1e-4 and abs(amp0[1]) < 1e-5 and abs(amp0[2]) < 1e-5
+    assert abs(dev.norm2() - 1.0) < 1e-4
+    # Hadamard on every qubit -> uniform superposition: analytic amplitude 2^-15
+    h = np.array([[1, 1], [1, -1]]) / np.sqrt(2)
+    dev.apply_batch([(h, [q]) for q in range(n)])
+    amps = dev.amplitudes(rng.randint(0, 1 << n, size=64))
+    np.testing.assert_allclose(amps, 2.0**-15, atol=1e-9)
+    idx = dev.sample_indices(rng.random_sample(4096))
+    # uniform distribution: top 4 bits chi-squared
+    hist = np.bincount((idx >> np.uint64(26)).astype(np.int64), minlength=16)
+    chi2 = np.sum((hist - 256.0) ** 2 / 256.0)
+    assert chi2 < 15 + 6 * np.sqrt(30) + 10

@@ -1,0 +1,422 @@
+"""Drop-in parity of B200Simulator / B200DensityMatrixSimulator with the
+reference cirq.Simulator / cirq.DensityMatrixSimulator on identical circuits.
+
+Every test runs twice:
+  * backend 'oracle' (CPU, no GPU needed): the simulators drive a test-only
+    DeviceState backed by the numpy oracle, which checks the host logic;
+  * backend 'cuda' (marked gpu): the real CUDA path through the C-ABI.
+
+Modelled on the reference's cirq-core/cirq/sim/sparse_simulator_test.py and
+density_matrix_simulator_test.py.  Tolerances: 1e-5 (complex64) / 1e-12
+(complex128) max-abs on amplitudes (north star)."""
+import numpy as np
+import pytest
+import sympy
+
+from fake_device import OracleDeviceState
+
+ATOL = {np.complex64: 1e-5, np.complex128: 1e-12}
+
+
+@pytest.fixture(
+    params=['oracle', pytest.param('cuda', marks=pytest.mark.gpu)], scope='module'
+)
+def backend(request, cirq):
+    import cirq_b200.dm_simulator as dmm
+    import cirq_b200.sv_simulator as svm
+    from cirq_b200.device_state import DeviceState
+
+    if request.param == 'oracle':
+        svm.DeviceState = OracleDeviceState
+        dmm.DeviceState = OracleDeviceState
+    else:
+        svm.DeviceState = DeviceState
+        dmm.DeviceState = DeviceState
+    yield request.param
+    svm.DeviceState = DeviceState
+    dmm.DeviceState = DeviceState
+
+
+@pytest.fixture(scope='module')
+def SV(backend):
+    import cirq_b200
+
+    return cirq_b200.B200Simulator
+
+
+@pytest.fixture(scope='module')
+def DM(backend):
+    import cirq_b200
+
+    return cirq_b200.B200DensityMatrixSimulator
+
+
+# --------------------------------------------------------------------------- state vector
+
+
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
+@pytest.mark.parametrize('max_fused', [1, 2, 3, 4, 5])
+def test_random_circuits_match_reference(cirq, SV, dtype, max_fused):
+    if dtype == np.complex128 and max_fused == 5:
+        max_fused = 4
+    for n, depth, seed in ((1, 5, 0), (2, 8, 1), (5, 10, 2), (9, 12, 3), (12, 16, 4)):
+        qubits = cirq.LineQubit.range(n)
+        circuit = cirq.testing.random_circuit(qubits, depth, 0.9, random_state=seed)
+        want = cirq.Simulator(dtype=dtype).simulate(circuit, qubit_order=qubits)
+        got = SV(dtype=dtype, max_fused_qubits=max_fused).simulate(circuit, qubit_order=qubits)
+        np.testing.assert_allclose(
+            got.final_state_vector, want.final_state_vector, atol=ATOL[dtype], rtol=0
+        )
+        assert got.qubit_map == want.qubit_map
+        assert got.final_state_vector.dtype == dtype
+
+
+def test_run_reports_config1_circuit_like_reference(cirq, SV):
+    """BASELINE config 1 generator at a CPU-friendly size."""
+    qubits = cirq.LineQubit.range(14)
+    circuit = cirq.testing.random_circuit(qubits, 20, 0.9, random_state=1234)
+    want = cirq.Simulator(dtype=np.complex64).simulate(circuit, qubit_order=qubits)
+    got = SV(dtype=np.complex64).simulate(circuit, qubit_order=qubits)
+    np.testing.assert_allclose(got.final_state_vector, want.final_state_vector, atol=1e-5, rtol=0)
+
+
+def test_qubit_order_and_initial_states(cirq, SV):
+    a, b, c = cirq.LineQubit.range(3)
+    circuit = cirq.Circuit(cirq.X(a), cirq.H(b), cirq.CNOT(b, c), cirq.T(c))
+    for order in ([a, b, c], [c, a, b], [b, c, a]):
+        want = cirq.Simulator().simulate(circuit, qubit_order=order)
+        got = SV().simulate(circuit, qubit_order=order)
+        np.testing.assert_allclose(got.final_state_vector, want.final_state_vector, atol=1e-6)
+    for init in (5, 0, 7):
+        want = cirq.Simulator().simulate(circuit, initial_state=init)
+        got = SV().simulate(circuit, initial_state=init)
+        np.testing.assert_allclose(got.final_state_vector, want.final_state_vector, atol=1e-6)
+    vec = cirq.testing.random_superposition(8, random_state=3).astype(np.complex64)
+    keep = vec.copy()
+    want = cirq.Simulator().simulate(circuit, initial_state=vec)
+    got = SV().simulate(circuit, initial_state=vec)
+    np.testing.assert_allclose(got.final_state_vector, want.final_state_vector, atol=1e-6)
+    np.testing.assert_array_equal(vec, keep)  # test_does_not_modify_initial_state
+    got = SV().simulate(circuit, initial_state=vec.reshape(2, 2, 2))
+    np.testing.assert_allclose(got.final_state_vector, want.final_state_vector, atol=1e-6)
+    want = cirq.Simulator().simulate(circuit, initial_state=(1, 0, 1))
+    got = SV().simulate(circuit, initial_state=(1, 0, 1))
+    np.testing.assert_allclose(got.final_state_vector, want.final_state_vector, atol=1e-6)
+    with pytest.raises(ValueError):
+        SV().simulate(circuit, initial_state=8)
+
+
+def test_run_terminal_measurements_seeded_like_reference(cirq, SV):
+    qubits = cirq.LineQubit.range(6)
+    circuit = cirq.testing.random_circuit(qubits, 8, 0.9, random_state=7)
+    circuit.append(cirq.measure(*qubits, key='m'))
+    want = cirq.Simulator(seed=11, split_untangled_states=False).run(circuit, repetitions=400)
+    got = SV(seed=11).run(circuit, repetitions=400)
+    w, g = want.measurements['m'], got.measurements['m']
+    assert g.shape == w.shape and g.dtype == w.dtype
+    assert np.mean(np.any(w != g, axis=1)) <= 0.01
+    # subset, permuted order, invert mask, two keys
+    circuit2 = cirq.testing.random_circuit(qubits, 8, 0.9, random_state=8)
+    circuit2.append(
+        [
+            cirq.measure(qubits[4], qubits[1], key='a', invert_mask=(True, False)),
+            cirq.measure(qubits[0], key='b'),
+        ]
+    )
+    want = cirq.Simulator(seed=3, split_untangled_states=False).run(circuit2, repetitions=300)
+    got = SV(seed=3).run(circuit2, repetitions=300)
+    for key in ('a', 'b'):
+        assert got.measurements[key].shape == want.measurements[key].shape
+        assert np.mean(np.any(want.measurements[key] != got.measurements[key], axis=1)) <= 0.01
+
+
+def test_run_histogram_chi_squared(cirq, SV):
+    qubits = cirq.LineQubit.range(5)
+    circuit = cirq.testing.random_circuit(qubits, 10, 0.9, random_state=21)
+    probs = np.abs(cirq.Simulator(dtype=np.complex128).simulate(circuit, qubit_order=qubits).final_state_vector) ** 2
+    circuit.append(cirq.measure(*qubits, key='m'))
+    reps = 20000
+    res = SV(seed=1).run(circuit, repetitions=reps)
+    ints = res.measurements['m'].astype(np.int64) @ (1 << np.arange(4, -1, -1))
+    hist = np.bincount(ints, minlength=32)
+    mask = probs * reps > 5
+    chi2 = np.sum((hist[mask] - probs[mask] * reps) ** 2 / (probs[mask] * reps))
+    dof = mask.sum() - 1
+    assert chi2 < dof + 6 * np.sqrt(2 * dof) + 10
+    assert hist[~mask].sum() <= 6 * max(1.0, (probs[~mask] * reps).sum()) + 5
+
+
+def test_mid_circuit_measurement_classical_control_reset(cirq, SV):
+    a, b = cirq.LineQubit.range(2)
+    circuit = cirq.Circuit(
+        cirq.H(a),
+        cirq.measure(a, key='x'),
+        cirq.X(b).with_classical_controls('x'),
+        cirq.measure(b, key='y'),
+        cirq.reset(a),
+        cirq.measure(a, key='z'),
+    )
+    want = cirq.Simulator(seed=5, split_untangled_states=False).run(circuit, repetitions=60)
+    got = SV(seed=5).run(circuit, repetitions=60)
+    for k in ('x', 'y', 'z'):
+        np.testing.assert_array_equal(got.measurements[k], want.measurements[k])
+        assert got.measurements[k].dtype == want.measurements[k].dtype
+    np.testing.assert_array_equal(got.measurements['x'], got.measurements['y'])
+    assert not got.measurements['z'].any()
+    # phase preserved through measure + control + reset (sparse_simulator_test.py:1453-1465)
+    q = cirq.LineQubit.range(3)
+    c = cirq.Circuit(cirq.Z(q[0]) ** 0.3, cirq.measure(q[1], key='m'), cirq.reset(q[2]))
+    want = cirq.Simulator().simulate(c, initial_state=(1, 1, 1))
+    got = SV().simulate(c, initial_state=(1, 1, 1))
+    np.testing.assert_allclose(got.final_state_vector, want.final_state_vector, atol=1e-6)
+
+
+def test_simulate_moment_steps_matches_reference(cirq, SV):
+    qubits = cirq.LineQubit.range(4)
+    circuit = cirq.testing.random_circuit(qubits, 6, 0.9, random_state=31)
+    circuit.append(cirq.measure(qubits[0], qubits[2], key='m'))
+    ref_steps = cirq.Simulator(seed=2, split_untangled_states=False).simulate_moment_steps(circuit, qubit_order=qubits)
+    steps = SV(seed=2).simulate_moment_steps(circuit, qubit_order=qubits)
+    count = 0
+    for i, (step, ref) in enumerate(zip(steps, ref_steps)):
+        np.testing.assert_allclose(step.state_vector(), ref.state_vector(), atol=1e-6)
+        if i == 2:
+            s1 = step.sample(qubits[:2], repetitions=5, seed=3)
+            s2 = ref.sample(qubits[:2], repetitions=5, seed=3)
+            np.testing.assert_array_equal(s1, s2)
+        count += 1
+    assert count == len(circuit)
+    assert dict(step.measurements) == dict(ref.measurements)
+    assert step.dirac_notation() == ref.dirac_notation()
+
+
+def test_param_sweeps(cirq, SV):
+    q = cirq.LineQubit.range(3)
+    t, s = sympy.Symbol('t'), sympy.Symbol('s')
+    circuit = cirq.Circuit(
+        cirq.H.on_each(*q), cirq.CZ(q[0], q[1]) ** t, cirq.rx(s).on(q[2]), cirq.CNOT(q[2], q[0])
+    )
+    sweep = cirq.Product(cirq.Linspace('t', 0, 1, 3), cirq.Points('s', [0.1, 0.7]))
+    want = cirq.Simulator().simulate_sweep(circuit, sweep)
+    got = SV().simulate_sweep(circuit, sweep)
+    assert len(got) == len(want) == 6
+    for g, w in zip(got, want):
+        assert g.params == w.params
+        np.testing.assert_allclose(g.final_state_vector, w.final_state_vector, atol=1e-6)
+    circuit.append(cirq.measure(*q, key='m'))
+    # seeded parity is with the unsplit reference: with split_untangled_states=True the
+    # reference samples each unentangled factor separately (same distribution, other stream)
+    want = cirq.Simulator(seed=9, split_untangled_states=False).run_sweep(
+        circuit, sweep, repetitions=50
+    )
+    got = SV(seed=9).run_sweep(circuit, sweep, repetitions=50)
+    for g, w in zip(got, want):
+        np.testing.assert_array_equal(g.measurements['m'], w.measurements['m'])
+    with pytest.raises(ValueError, match='symbols'):
+        SV().simulate(circuit)
+
+
+def test_noisy_state_vector_trajectories_seeded(cirq, SV):
+    q = cirq.LineQubit.range(3)
+    circuit = cirq.Circuit(
+        cirq.H(q[0]),
+        cirq.CNOT(q[0], q[1]),
+        cirq.bit_flip(0.3).on(q[1]),
+        cirq.amplitude_damp(0.4).on(q[0]),
+        cirq.depolarize(0.2).on(q[2]),
+        cirq.measure(*q, key='m'),
+    )
+    want = cirq.Simulator(seed=17, split_untangled_states=False).run(circuit, repetitions=80)
+    got = SV(seed=17).run(circuit, repetitions=80)
+    np.testing.assert_array_equal(got.measurements['m'], want.measurements['m'])
+    want = cirq.Simulator(seed=4, noise=cirq.depolarize(0.1), split_untangled_states=False).run(circuit, repetitions=40)
+    got = SV(seed=4, noise=cirq.depolarize(0.1)).run(circuit, repetitions=40)
+    np.testing.assert_array_equal(got.measurements['m'], want.measurements['m'])
+
+
+def test_expectation_values_and_amplitudes(cirq, SV):
+    q = cirq.LineQubit.range(4)
+    circuit = cirq.testing.random_circuit(q, 8, 0.9, random_state=5)
+    circuit.append(cirq.I.on_each(*q))
+    obs = [
+        cirq.Z(q[0]) * cirq.X(q[2]),
+        0.5 * cirq.Y(q[1]) + 2.0 * cirq.Z(q[3]) * cirq.Y(q[0]) - 1.5 * cirq.X(q[1]) * cirq.X(q[2]),
+        cirq.PauliString(),
+    ]
+    want = cirq.Simulator(dtype=np.complex128).simulate_expectation_values(circuit, obs)
+    got = SV(dtype=np.complex128).simulate_expectation_values(circuit, obs)
+    np.testing.assert_allclose(got, want, atol=1e-10)
+    bitstrings = [0, 3, 15, 9]
+    want = cirq.Simulator().compute_amplitudes(circuit, bitstrings)
+    got = SV().compute_amplitudes(circuit, bitstrings)
+    np.testing.assert_allclose(got, want, atol=1e-6)
+    with pytest.raises(ValueError, match='terminal measurements'):
+        SV().simulate_expectation_values(
+            cirq.Circuit(cirq.H(q[0]), cirq.measure(q[0])), [cirq.Z(q[0])]
+        )
+
+
+def test_wide_and_composite_operations(cirq, SV):
+    q = cirq.LineQubit.range(7)
+    circuit = cirq.Circuit(
+        cirq.H.on_each(*q[:3]),
+        cirq.qft(*q, without_reverse=True),
+        cirq.MatrixGate(cirq.testing.random_unitary(8, random_state=1)).on(q[5], q[0], q[3]),
+        cirq.CCX(q[1], q[2], q[6]),
+        cirq.ControlledGate(cirq.ISWAP, num_controls=2).on(q[0], q[4], q[2], q[6]),
+        cirq.MatrixGate(cirq.testing.random_unitary(64, random_state=2)).on(*q[:6]),
+        cirq.CircuitOperation(cirq.FrozenCircuit(cirq.X(q[0]), cirq.CZ(q[0], q[1])), repetitions=3),
+    )
+    want = cirq.Simulator(dtype=np.complex128).simulate(circuit, qubit_order=q)
+    got = SV(dtype=np.complex128).simulate(circuit, qubit_order=q)
+    np.testing.assert_allclose(got.final_state_vector, want.final_state_vector, atol=1e-10)
+
+
+def test_errors_match_reference(cirq, SV):
+    q = cirq.LineQubit.range(2)
+    with pytest.raises(ValueError, match='no measurements'):
+        SV().run(cirq.Circuit(cirq.H(q[0])))
+    with pytest.raises(ValueError, match='complex'):
+        SV(dtype=np.float32)
+
+    class Unsupported(cirq.Gate):
+        def _num_qubits_(self):
+            return 1
+
+    with pytest.raises(TypeError, match="doesn't support"):
+        SV().simulate(cirq.Circuit(Unsupported().on(q[0])))
+    with pytest.raises(ValueError, match='dimension 2|qubits only'):
+        SV().simulate(cirq.Circuit(cirq.IdentityGate(qid_shape=(3,)).on(cirq.LineQid(0, 3))))
+
+
+def test_repeated_keys_and_empty_circuit(cirq, SV):
+    q = cirq.LineQubit.range(2)
+    circuit = cirq.Circuit(cirq.X(q[0]), cirq.measure(q[0], key='k'), cirq.measure(q[1], key='k'))
+    want = cirq.Simulator(seed=1, split_untangled_states=False).run(circuit, repetitions=7)
+    got = SV(seed=1).run(circuit, repetitions=7)
+    np.testing.assert_array_equal(got.records['k'], want.records['k'])
+    assert got.records['k'].shape == (7, 2, 1)
+    res = SV().simulate(cirq.Circuit(), qubit_order=q)
+    np.testing.assert_allclose(res.final_state_vector, [1, 0, 0, 0])
+    assert str(res).startswith('measurements:')
+
+
+def test_same_seed_same_result_and_global_state_untouched(cirq, SV):
+    q = cirq.LineQubit.range(3)
+    circuit = cirq.Circuit(cirq.H.on_each(*q), cirq.measure(*q, key='m'))
+    a = SV(seed=123).run(circuit, repetitions=30).measurements['m']
+    b = SV(seed=123).run(circuit, repetitions=30).measurements['m']
+    np.testing.assert_array_equal(a, b)
+    np.random.seed(10)
+    before = np.random.get_state()[1].copy()
+    SV(seed=1).run(circuit, repetitions=5)
+    np.testing.assert_array_equal(before, np.random.get_state()[1])
+
+
+# --------------------------------------------------------------------------- density matrix
+
+
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
+def test_density_matrix_matches_reference(cirq, DM, dtype):
+    for n, depth, seed in ((1, 4, 0), (3, 6, 1), (5, 8, 2)):
+        qubits = cirq.LineQubit.range(n)
+        circuit = cirq.testing.random_circuit(qubits, depth, 0.9, random_state=seed)
+        circuit.append(cirq.I.on_each(*qubits))
+        circuit.append(cirq.amplitude_damp(0.2).on(qubits[0]))
+        circuit.append(cirq.phase_damp(0.3).on(qubits[-1]))
+        circuit.append(cirq.bit_flip(0.1).on(qubits[0]))
+        if n >= 2:
+            circuit.append(cirq.depolarize(0.1, n_qubits=2).on(qubits[0], qubits[1]))
+        for noise in (None, cirq.depolarize(0.02)):
+            want = cirq.DensityMatrixSimulator(dtype=dtype, noise=noise).simulate(
+                circuit, qubit_order=qubits
+            )
+            for max_fused in (2, 4):
+                got = DM(dtype=dtype, noise=noise, max_fused_qubits=max_fused).simulate(
+                    circuit, qubit_order=qubits
+                )
+                np.testing.assert_allclose(
+                    got.final_density_matrix, want.final_density_matrix, atol=ATOL[dtype], rtol=0
+                )
+
+
+def test_density_matrix_equals_state_vector_outer_product(cirq, DM):
+    q = cirq.LineQubit.range(4)
+    circuit = cirq.testing.random_circuit(q, 8, 0.9, random_state=12)
+    circuit.append(cirq.I.on_each(*q))
+    psi = cirq.Simulator(dtype=np.complex128).simulate(circuit, qubit_order=q).final_state_vector
+    rho = DM(dtype=np.complex128).simulate(circuit, qubit_order=q).final_density_matrix
+    np.testing.assert_allclose(rho, np.outer(psi, psi.conj()), atol=1e-10)
+
+
+def test_density_matrix_run_and_measurement_seeded(cirq, DM):
+    q = cirq.LineQubit.range(3)
+    circuit = cirq.Circuit(
+        cirq.H(q[0]),
+        cirq.CNOT(q[0], q[1]),
+        cirq.depolarize(0.2).on(q[1]),
+        cirq.ry(0.7).on(q[2]),
+        cirq.measure(q[2], q[0], key='a'),
+        cirq.measure(q[1], key='b', invert_mask=(True,)),
+    )
+    want = cirq.DensityMatrixSimulator(
+        seed=6, noise=cirq.depolarize(0.05), split_untangled_states=False
+    ).run(circuit, repetitions=200)
+    got = DM(seed=6, noise=cirq.depolarize(0.05)).run(circuit, repetitions=200)
+    for k in ('a', 'b'):
+        assert got.measurements[k].dtype == want.measurements[k].dtype
+        assert np.mean(np.any(got.measurements[k] != want.measurements[k], axis=1)) <= 0.01
+    # mid-circuit measurement collapses rho (simulate path)
+    c2 = cirq.Circuit(
+        cirq.H(q[0]), cirq.CNOT(q[0], q[1]), cirq.measure(q[0], key='m'), cirq.H(q[2]),
+        cirq.X(q[2]).with_classical_controls('m'),
+    )
+    want = cirq.DensityMatrixSimulator(seed=8, split_untangled_states=False).simulate(c2, qubit_order=q)
+    got = DM(seed=8).simulate(c2, qubit_order=q)
+    assert dict(got.measurements) == dict(want.measurements) or np.array_equal(
+        got.measurements['m'], want.measurements['m']
+    )
+    np.testing.assert_allclose(got.final_density_matrix, want.final_density_matrix, atol=1e-6)
+
+
+def test_density_matrix_sweep_qaoa_style(cirq, DM):
+    """BASELINE config 5 shape at a CPU-friendly size: noisy QAOA, run_sweep."""
+    q = cirq.LineQubit.range(4)
+    beta, gamma = sympy.Symbol('beta0'), sympy.Symbol('gamma0')
+    edges = [(0, 1), (1, 2), (2, 3), (0, 3)]
+    circuit = cirq.Circuit(cirq.H.on_each(*q))
+    circuit.append(cirq.ZZ(q[i], q[j]) ** gamma for i, j in edges)
+    circuit.append(cirq.X.on_each(*q) ** beta if False else [cirq.X(x) ** beta for x in q])
+    circuit.append(cirq.measure(*q, key='m'))
+    sweep = cirq.Zip(cirq.Linspace('beta0', 0.1, 0.9, 4), cirq.Linspace('gamma0', 0.2, 0.8, 4))
+    want = cirq.DensityMatrixSimulator(
+        noise=cirq.depolarize(0.01), seed=0, split_untangled_states=False
+    ).run_sweep(
+        circuit, sweep, repetitions=100
+    )
+    got = DM(noise=cirq.depolarize(0.01), seed=0).run_sweep(circuit, sweep, repetitions=100)
+    assert len(got) == 4
+    for g, w in zip(got, want):
+        assert g.params == w.params
+        assert g.measurements['m'].shape == (100, 4)
+        assert np.mean(np.any(g.measurements['m'] != w.measurements['m'], axis=1)) <= 0.02
+
+
+def test_density_matrix_expectation_steps_and_initial_state(cirq, DM):
+    q = cirq.LineQubit.range(3)
+    circuit = cirq.Circuit(cirq.H(q[0]), cirq.CNOT(q[0], q[1]), cirq.rx(0.4).on(q[2]))
+    obs = [cirq.Z(q[0]) * cirq.Z(q[1]), cirq.X(q[2]) + 0.5 * cirq.Y(q[2])]
+    noise = cirq.depolarize(0.03)
+    want = cirq.DensityMatrixSimulator(noise=noise).simulate_expectation_values(circuit, obs)
+    got = DM(noise=noise).simulate_expectation_values(circuit, obs)
+    np.testing.assert_allclose(got, want, atol=1e-6)
+    ref_steps = cirq.DensityMatrixSimulator(noise=noise).simulate_moment_steps(circuit)
+    for step, ref in zip(DM(noise=noise).simulate_moment_steps(circuit), ref_steps):
+        np.testing.assert_allclose(step.density_matrix(), ref.density_matrix(), atol=1e-6)
+    rho0 = cirq.testing.random_density_matrix(8, random_state=2).astype(np.complex64)
+    want = cirq.DensityMatrixSimulator().simulate(circuit, initial_state=rho0)
+    got = DM().simulate(circuit, initial_state=rho0)
+    np.testing.assert_allclose(got.final_density_matrix, want.final_density_matrix, atol=1e-6)
+    want = cirq.DensityMatrixSimulator().simulate(circuit, initial_state=5)
+    got = DM().simulate(circuit, initial_state=5)
+    np.testing.assert_allclose(got.final_density_matrix, want.final_density_matrix, atol=1e-6)

@@ -1,0 +1,120 @@
+"""Times single gate passes by target-position class (CUDA events, on a B200).
+
+    python tools/microbench.py [--n 30] [--dtype c64] [--reps 10] [--out gpurun_out/microbench.json]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch  # noqa: E402
+
+from cirq_b200.device_state import DeviceState  # noqa: E402
+
+
+def rand_unitary(rng, k):
+    d = 1 << k
+    q, r = np.linalg.qr(rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d)))
+    return q * (np.diag(r) / np.abs(np.diag(r)))
+
+
+def time_pass(dev, m, bits, reps):
+    for _ in range(3):
+        dev.apply_matrix(m, bits)
+    torch.cuda.synchronize()
+    start = torch.cuda.Event(enable_timing=True)
+    end = torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(reps):
+        dev.apply_matrix(m, bits)
+    end.record()
+    torch.cuda.synchronize()
+    return start.elapsed_time(end) / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--n', type=int, default=30)
+    ap.add_argument('--dtype', default='c64')
+    ap.add_argument('--reps', type=int, default=10)
+    ap.add_argument('--out', default='')
+    args = ap.parse_args()
+    dtype = np.complex64 if args.dtype == 'c64' else np.complex128
+    n = args.n
+    rng = np.random.RandomState(0)
+    dev = DeviceState.basis(n, dtype, 0)
+    bytes_per_pass = 2 * dev.nbytes
+    zb = 6 if dtype == np.complex64 else 5
+    hi = n - 1
+    classes = {
+        'k1_high': [hi], 'k1_mid': [zb + 2], 'k1_bit0': [0], 'k1_lane': [3],
+        'k2_high': [hi, hi - 1], 'k2_mid': [zb, zb + 1], 'k2_spread': [hi, zb + 3],
+        'k2_bit0_high': [0, hi], 'k2_lane_high': [2, hi], 'k2_lane_lane': [1, 4],
+        'k2_bit0_lane': [0, 3],
+        'k3_high': [hi, hi - 1, hi - 2], 'k3_mid': [zb, zb + 1, zb + 2],
+        'k3_lane_high': [2, hi, hi - 5], 'k3_lanes': [1, 2, 3],
+        'k4_high': [hi, hi - 1, hi - 2, hi - 3], 'k4_mid': [zb, zb + 2, zb + 4, zb + 6],
+        'k4_lane_high': [1, 3, hi, hi - 1], 'k4_lanes': [1, 2, 3, 4],
+    }
+    if dtype == np.complex64:
+        classes.update({
+            'k5_high': [hi, hi - 1, hi - 2, hi - 3, hi - 4],
+            'k5_lane_high': [2, 4, hi, hi - 1, hi - 2],
+            'k5_lanes': [1, 2, 3, 4, 5],
+        })
+    results = {}
+    for name, bits in classes.items():
+        m = rand_unitary(rng, len(bits))
+        ms = time_pass(dev, m, bits, args.reps)
+        gbs = bytes_per_pass / ms / 1e6
+        results[name] = {'bits': bits, 'ms': ms, 'GBps': gbs}
+        print(f'{name:16s} bits={bits!s:28s} {ms:8.3f} ms  {gbs:8.1f} GB/s', flush=True)
+    # reference points: torch copy (read+write) and the diagonal/scale kernels
+    other = torch.empty_like(dev.tensor)
+    for _ in range(3):
+        other.copy_(dev.tensor)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(args.reps):
+        other.copy_(dev.tensor)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / args.reps
+    results['torch_copy'] = {'ms': ms, 'GBps': bytes_per_pass / ms / 1e6}
+    print(f'torch_copy {ms:8.3f} ms {bytes_per_pass / ms / 1e6:8.1f} GB/s')
+    del other
+    s.record()
+    for _ in range(args.reps):
+        dev.scale(1.0)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / args.reps
+    results['scale_inplace'] = {'ms': ms, 'GBps': bytes_per_pass / ms / 1e6}
+    print(f'scale_inplace {ms:8.3f} ms {bytes_per_pass / ms / 1e6:8.1f} GB/s')
+    s.record()
+    nrm = dev.norm2()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e)
+    results['norm2'] = {'ms': ms, 'GBps': dev.nbytes / ms / 1e6, 'value': nrm}
+    print(f'norm2 {ms:8.3f} ms {dev.nbytes / ms / 1e6:8.1f} GB/s (read only) value={nrm}')
+    u = rng.random_sample(1_000_000)
+    s.record()
+    idx = dev.sample_indices_device(u)
+    e.record()
+    torch.cuda.synchronize()
+    results['sample_1M'] = {'ms': s.elapsed_time(e)}
+    print(f'sample 1M: {s.elapsed_time(e):8.3f} ms')
+    if args.out:
+        os.makedirs(os.path.dirname(args.out), exist_ok=True)
+        with open(args.out, 'w') as f:
+            json.dump({'n': n, 'dtype': args.dtype, 'results': results}, f, indent=1)
+
+
+if __name__ == '__main__':
+    main()
