@@ -78,6 +78,7 @@ SIGNATURES = {
 
 # Host-only helpers exported for unit tests (not part of the product ABI).
 DEBUG_SIGNATURES = {
+    'b2q_set_lane_mode': (c_int, [c_int]),
     'b2q_debug_plan': (c_int, [c_int, c_int, POINTER(c_int), c_int, POINTER(c_int)]),
     'b2q_debug_permute_matrix': (c_int, [c_void_p, POINTER(c_int), c_int, c_void_p]),
 }
@@ -99,6 +100,9 @@ def load():
             fn = getattr(lib, name)
             fn.restype = restype
             fn.argtypes = argtypes
+    mode = os.environ.get('CIRQ_B200_LANE_MODE')
+    if mode is not None:
+        lib.b2q_set_lane_mode(int(mode))
     _lib = lib
     return lib
 

@@ -31,6 +31,31 @@ constexpr int kMaxRegBits = 6;
 constexpr int kMaxIns = 6;
 constexpr int kFastThreads = 256;
 
+// Matrix entries in the kernel parameter bank.  complex128: (re, im).
+// complex64: (re, re, -im, im), the two packed operands of the Blackwell FFMA2
+// (fma.rn.f32x2) form of a complex multiply-accumulate:
+//   acc(re,im) += (re,re) * x(re,im);  acc(re,im) += (-im,im) * x(im,re)
+// — two instructions per complex MAC instead of four, the (im,re) swap being an
+// operand modifier in SASS (R.F32x2.LO_HI).
+template <typename real>
+struct MatEntry {
+  static constexpr int kReals = sizeof(real) == 4 ? 4 : 2;
+};
+
+template <typename real, typename C>
+__device__ __forceinline__ void cmac_entry(C& acc, const real* m, const C& x);
+template <>
+__device__ __forceinline__ void cmac_entry<float, float2>(float2& acc, const float* m,
+                                                          const float2& x) {
+  acc = __ffma2_rn(make_float2(m[0], m[1]), x, acc);
+  acc = __ffma2_rn(make_float2(m[2], m[3]), make_float2(x.y, x.x), acc);
+}
+template <>
+__device__ __forceinline__ void cmac_entry<double, double2>(double2& acc, const double* m,
+                                                            const double2& x) {
+  cmac<double>(acc, m[0], m[1], x);
+}
+
 template <typename real, int K>
 struct FastParams {
   typename Cplx<real>::type* state;
@@ -39,7 +64,7 @@ struct FastParams {
   int ins_pos[kMaxIns];             // their positions, ascending
   long long reg_off[kMaxRegBits];   // element offset contributed by each register bit
   int swap_lane[kMaxRegBits];       // per target slot: lane bit to exchange with, or -1
-  real mat[2 << (2 * K)];           // row-major (re, im), index bit i <-> i-th lowest target
+  real mat[MatEntry<real>::kReals << (2 * K)];  // row-major entries (see MatEntry)
 };
 
 template <typename real, int K>
@@ -47,7 +72,7 @@ struct SmallParams {
   typename Cplx<real>::type* state;
   uint64_t num_groups;
   int tpos[K];  // ascending
-  real mat[2 << (2 * K)];
+  real mat[MatEntry<real>::kReals << (2 * K)];
 };
 
 
@@ -142,6 +167,7 @@ __global__ void __launch_bounds__(kFastThreads)
   constexpr int NR = 1 << RB;
   constexpr int DIM = 1 << K;
   constexpr int ZB = kVec ? 6 : 5;
+  constexpr int ME = MatEntry<real>::kReals;
   static_assert(!(SWAPS && S), "lane exchanges only exist in the S=0 layout");
   static_assert(kVec || S == 0, "complex128 has no vector bit");
 
@@ -149,8 +175,13 @@ __global__ void __launch_bounds__(kFastThreads)
   const uint64_t item =
       (uint64_t)blockIdx.x * (kFastThreads / 32) + (uint64_t)(threadIdx.x >> 5);
   if (item >= p.num_items) return;
-  uint64_t base = insert_zero_bits(item << ZB, p.ins_pos, p.n_ins);
-  base += kVec ? (uint64_t)(lane << 1) : (uint64_t)lane;
+  // The 32 lanes enumerate the 5 lowest index bits that are neither the vector
+  // bit nor register-resident; with all register bits above the zone this is
+  // "512 contiguous bytes per warp access", with low register bits (remap
+  // mode) the lanes spread over the next free bits instead.
+  constexpr int VB = kVec ? 1 : 0;
+  (void)ZB;
+  const uint64_t base = insert_zero_bits(((item << 5) | (uint64_t)lane) << VB, p.ins_pos, p.n_ins);
   C* __restrict__ ptr = p.state + base;
 
   C x[NR];
@@ -187,8 +218,7 @@ __global__ void __launch_bounds__(kFastThreads)
         C acc = make_c<real>(0, 0);
 #pragma unroll
         for (int c = 0; c < DIM; ++c)
-          cmac<real>(acc, p.mat[2 * (r * DIM + c)], p.mat[2 * (r * DIM + c) + 1],
-                     x[(g << K) | c]);
+          cmac_entry<real, C>(acc, &p.mat[ME * (r * DIM + c)], x[(g << K) | c]);
         y[(g << K) | r] = acc;
       }
     }
@@ -221,9 +251,8 @@ __global__ void __launch_bounds__(kFastThreads)
         C a0 = make_c<real>(0, 0), a1 = make_c<real>(0, 0);
 #pragma unroll
         for (int c = 0; c < DIM; ++c) {
-          const real mr = p.mat[2 * (r * DIM + c)], mi = p.mat[2 * (r * DIM + c) + 1];
-          cmac<real>(a0, mr, mi, x[(((g << K) | c) << 1)]);
-          cmac<real>(a1, mr, mi, x[(((g << K) | c) << 1) | 1]);
+          cmac_entry<real, C>(a0, &p.mat[ME * (r * DIM + c)], x[(((g << K) | c) << 1)]);
+          cmac_entry<real, C>(a1, &p.mat[ME * (r * DIM + c)], x[(((g << K) | c) << 1) | 1]);
         }
         const int i = (g << K) | r;  // index over register bits 1..RB-1
         long long off = 0;
@@ -243,9 +272,8 @@ __global__ void __launch_bounds__(kFastThreads)
 #pragma unroll
         for (int c = 0; c < DIM; ++c) {
           const C xv = x[(g << K) | c];
-          cmac<real>(a0, p.mat[2 * ((2 * r2) * DIM + c)], p.mat[2 * ((2 * r2) * DIM + c) + 1], xv);
-          cmac<real>(a1, p.mat[2 * ((2 * r2 + 1) * DIM + c)],
-                     p.mat[2 * ((2 * r2 + 1) * DIM + c) + 1], xv);
+          cmac_entry<real, C>(a0, &p.mat[ME * ((2 * r2) * DIM + c)], xv);
+          cmac_entry<real, C>(a1, &p.mat[ME * ((2 * r2 + 1) * DIM + c)], xv);
         }
         const int i = (g << (K - 1)) | r2;  // index over register bits 1..RB-1
         long long off = 0;
@@ -263,8 +291,7 @@ __global__ void __launch_bounds__(kFastThreads)
         C acc = make_c<real>(0, 0);
 #pragma unroll
         for (int c = 0; c < DIM; ++c)
-          cmac<real>(acc, p.mat[2 * (r * DIM + c)], p.mat[2 * (r * DIM + c) + 1],
-                     x[(g << K) | c]);
+          cmac_entry<real, C>(acc, &p.mat[ME * (r * DIM + c)], x[(g << K) | c]);
         const int i = (g << K) | r;
         long long off = 0;
 #pragma unroll
@@ -282,6 +309,7 @@ __global__ void __launch_bounds__(128)
     sv_apply_small_kernel(const __grid_constant__ SmallParams<real, K> p) {
   using C = typename Cplx<real>::type;
   constexpr int DIM = 1 << K;
+  constexpr int ME = MatEntry<real>::kReals;
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= p.num_groups) return;
   const uint64_t base = insert_zero_bits(g, p.tpos, K);
@@ -299,7 +327,7 @@ __global__ void __launch_bounds__(128)
     C acc = make_c<real>(0, 0);
 #pragma unroll
     for (int c = 0; c < DIM; ++c)
-      cmac<real>(acc, p.mat[2 * (r * DIM + c)], p.mat[2 * (r * DIM + c) + 1], x[c]);
+      cmac_entry<real, C>(acc, &p.mat[ME * (r * DIM + c)], x[c]);
     uint64_t off = 0;
 #pragma unroll
     for (int b = 0; b < K; ++b)
@@ -383,6 +411,32 @@ struct FastPlan {
 
 // `sorted` = ascending target bit positions.  Mirrors the layout rules in the
 // header comment; exported through b2q_debug_plan for the host unit tests.
+// How a target bit inside the zone (a "lane target") is handled:
+//   shuffle: exchanged with a spare register bit by a warp-shuffle butterfly;
+//            every warp access stays 512 contiguous bytes, at the price of
+//            ~8 extra instructions per amplitude pair and both x and y live.
+//   remap:   it becomes an ordinary register bit and the lanes move up to the
+//            next free index bits; no shuffles, but a warp access then covers
+//            16-byte pieces at stride 2^(t+1) amplitudes that the thread's other
+//            accesses complete to full sectors through L1/L2.
+// g_lane_mode: 0 = always shuffle, 1 = always remap, 2 = per-target policy
+// fitted to the B200 measurements in profiles/microbench_r1.md (default).
+std::atomic<int> g_lane_mode{2};
+
+static bool remap_target(int mode, bool vec, int K, int t, bool both_low) {
+  if (mode == 0) return false;
+  if (mode == 1) return true;
+  if (vec) {
+    // complex64: sector = index bits 0-1; bits 1,2 split sectors when remapped
+    if (K >= 4) return t >= 3 || !both_low;
+    if (K == 3) return t >= 3;
+    return false;
+  }
+  // complex128: sector = index bit 0
+  if (K >= 4) return true;
+  return t >= 3;
+}
+
 FastPlan make_fast_plan(int dtype, int n, const int* sorted, int K) {
   FastPlan pl;
   pl.K = K;
@@ -392,9 +446,26 @@ FastPlan make_fast_plan(int dtype, int n, const int* sorted, int K) {
   const int max_k = vec ? 5 : 4;
   if (K < 1 || K > max_k) return pl;
   const bool vec_is_target = vec && sorted[0] == 0;
-  int n_lane = 0;
-  for (int i = 0; i < K; ++i)
-    if (sorted[i] >= VB && sorted[i] < ZB) ++n_lane;
+  const int mode = g_lane_mode.load(std::memory_order_relaxed);
+  bool has1 = false, has2 = false;
+  for (int i = 0; i < K; ++i) {
+    has1 |= sorted[i] == 1;
+    has2 |= sorted[i] == 2;
+  }
+  bool remap[16];
+  int n_lane = 0;  // lane targets handled by shuffles
+  for (int i = 0; i < K; ++i) {
+    const bool lane_t = sorted[i] >= VB && sorted[i] < ZB;
+    remap[i] = lane_t && remap_target(mode, vec, K, sorted[i], has1 && has2);
+    if (lane_t && !remap[i]) ++n_lane;
+  }
+  // complex64, S=0 layout: register bit 0 is physically the vector bit, so target
+  // slot 0 must be index bit 0 itself or a shuffled lane target (the vector bit
+  // then serves as its spare).  Keep that invariant under mixed policies.
+  if (vec && !vec_is_target && n_lane > 0 && remap[0]) {
+    remap[0] = false;
+    ++n_lane;
+  }
   pl.S = (vec && !vec_is_target && n_lane == 0) ? 1 : 0;
   pl.GT = pl.S ? std::max(0, 2 - K) : std::max(0, 3 - K);
   pl.swaps = n_lane > 0;
@@ -418,7 +489,7 @@ FastPlan make_fast_plan(int dtype, int n, const int* sorted, int K) {
   for (int i = 0; i < K; ++i) {
     const int rbit = pl.S + i;
     const int t = sorted[i];
-    if (t >= ZB) {
+    if (t >= ZB || remap[i]) {
       pl.reg_off[rbit] = 1ll << t;
       ins.push_back(t);
     } else if (vec && t == 0) {
@@ -449,15 +520,20 @@ FastPlan make_fast_plan(int dtype, int n, const int* sorted, int K) {
   if (n < ZB + (int)ins.size()) return pl;
   pl.n_ins = (int)ins.size();
   for (int i = 0; i < pl.n_ins; ++i) pl.ins_pos[i] = ins[i];
+  // In remap mode the spare bits must not collide with the lane bits: the
+  // extras were taken from >= ZB, but lanes may now reach above ZB; extras
+  // are register bits (inserted positions), lanes take what is left: fine.
   pl.num_items = 1ull << (n - ZB - pl.n_ins);
   pl.feasible = true;
   return pl;
 }
 
 // Reorders a gate matrix from "first target = MSB" order to "index bit i <->
-// i-th lowest target bit position" and casts it to `real`.
+// i-th lowest target bit position", casts it to `real` and lays the entries out
+// as the kernels read them (MatEntry; `packed` = false keeps plain (re, im)).
 template <typename real>
-void permute_matrix(const double* m128, const int* targets, const int* sorted, int K, real* out) {
+void permute_matrix(const double* m128, const int* targets, const int* sorted, int K, real* out,
+                    bool packed = true) {
   const int dim = 1 << K;
   // rank_of_gate_qubit[q] = index in `sorted` of targets[q]
   int rank[16];
@@ -476,8 +552,16 @@ void permute_matrix(const double* m128, const int* targets, const int* sorted, i
   for (int r = 0; r < dim; ++r)
     for (int c = 0; c < dim; ++c) {
       const double* src = m128 + 2 * ((size_t)orig[r] * dim + orig[c]);
-      out[2 * ((size_t)r * dim + c)] = (real)src[0];
-      out[2 * ((size_t)r * dim + c) + 1] = (real)src[1];
+      if (packed && sizeof(real) == 4) {
+        real* dst = out + 4 * ((size_t)r * dim + c);
+        dst[0] = (real)src[0];
+        dst[1] = (real)src[0];
+        dst[2] = -(real)src[1];
+        dst[3] = (real)src[1];
+      } else {
+        out[2 * ((size_t)r * dim + c)] = (real)src[0];
+        out[2 * ((size_t)r * dim + c) + 1] = (real)src[1];
+      }
     }
 }
 
@@ -492,7 +576,7 @@ int launch_fast(void* state, const FastPlan& pl, const real* mat, cudaStream_t s
     p.reg_off[i] = pl.reg_off[i];
     p.swap_lane[i] = pl.swap_lane[i];
   }
-  std::memcpy(p.mat, mat, sizeof(real) * (2u << (2 * K)));
+  std::memcpy(p.mat, mat, sizeof(real) * ((size_t)MatEntry<real>::kReals << (2 * K)));
   const uint64_t warps_per_block = kFastThreads / 32;
   const uint64_t blocks = (pl.num_items + warps_per_block - 1) / warps_per_block;
   if (blocks > 0x7fffffffull) return set_error(B2Q_ERR_UNSUPPORTED, "grid too large");
@@ -520,7 +604,7 @@ int launch_small(void* state, int n, const int* sorted, const real* mat, cudaStr
   p.state = reinterpret_cast<typename Cplx<real>::type*>(state);
   p.num_groups = 1ull << (n - K);
   for (int i = 0; i < K; ++i) p.tpos[i] = sorted[i];
-  std::memcpy(p.mat, mat, sizeof(real) * (2u << (2 * K)));
+  std::memcpy(p.mat, mat, sizeof(real) * ((size_t)MatEntry<real>::kReals << (2 * K)));
   const uint64_t blocks = (p.num_groups + 127) / 128;
   if (blocks > 0x7fffffffull) return set_error(B2Q_ERR_UNSUPPORTED, "grid too large");
   sv_apply_small_kernel<real, K><<<(unsigned)blocks, 128, 0, stream>>>(p);
@@ -568,7 +652,7 @@ int apply_matrix_t(void* state, int dtype, int n, const double* m128, const int*
                 sorted[i], n);
     B2Q_REQUIRE(i == 0 || sorted[i] != sorted[i - 1], "duplicate target bit %d", sorted[i]);
   }
-  std::vector<real> mat((size_t)2 << (2 * K));
+  std::vector<real> mat((size_t)MatEntry<real>::kReals << (2 * K));
   permute_matrix<real>(m128, targets, sorted, K, mat.data());
   const FastPlan pl = make_fast_plan(dtype, n, sorted, K);
   if (pl.feasible) {
@@ -596,7 +680,9 @@ int apply_matrix_t(void* state, int dtype, int n, const double* m128, const int*
         break;
     }
   }
-  return apply_generic<real>(state, n, sorted, K, mat.data(), scratch, stream);
+  std::vector<real> plain((size_t)2 << (2 * K));
+  permute_matrix<real>(m128, targets, sorted, K, plain.data(), /*packed=*/false);
+  return apply_generic<real>(state, n, sorted, K, plain.data(), scratch, stream);
 }
 
 }  // namespace b2q
@@ -672,6 +758,12 @@ extern "C" int b2q_sv_apply_diagonal(void* state, int dtype, int n_qubits,
   return B2Q_OK;
 }
 
+extern "C" int b2q_set_lane_mode(int mode) {
+  B2Q_REQUIRE(mode == 0 || mode == 1, "lane mode must be 0 or 1");
+  g_lane_mode.store(mode, std::memory_order_relaxed);
+  return B2Q_OK;
+}
+
 // Host-only: exposes the fast-path plan for unit tests (no GPU needed).
 // out[0]=feasible, [1]=S, [2]=GT, [3]=swaps, [4]=n_ins, [5..10]=ins_pos,
 // [11..16]=log2(reg_off) or -1, [17..22]=swap_lane, [23]=log2(num_items).
@@ -707,6 +799,6 @@ extern "C" int b2q_debug_permute_matrix(const double* m128, const int* targets, 
   int sorted[16];
   for (int i = 0; i < k; ++i) sorted[i] = targets[i];
   std::sort(sorted, sorted + k);
-  permute_matrix<double>(m128, targets, sorted, k, out);
+  permute_matrix<double>(m128, targets, sorted, k, out, /*packed=*/false);
   return B2Q_OK;
 }

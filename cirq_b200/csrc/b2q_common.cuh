@@ -19,6 +19,10 @@ namespace b2q {
 // ---- error plumbing ---------------------------------------------------------
 
 char* last_error_buffer();  // thread-local, 512 bytes
+// Persistent per-device scratch of at least `bytes` (partials, scalars, small
+// tables).  Grown on demand; contents are only valid within one library call.
+// Returns nullptr (and sets the error) on allocation failure.
+void* workspace(size_t bytes);
 extern std::atomic<uint64_t> g_launch_count;
 
 inline int set_error(int code, const char* fmt, ...) {

@@ -635,8 +635,8 @@ int norm2_t(const void* state, int n, double* out_host, cudaStream_t s) {
     return B2Q_OK;
   }
   const unsigned blocks = stride_grid(total / V16<real>::kElems / kStreamUnroll, 256);
-  double* partial = nullptr;
-  B2Q_CUDA_CHECK(cudaMallocAsync((void**)&partial, sizeof(double) * (blocks + 1), s));
+  double* partial = reinterpret_cast<double*>(workspace(sizeof(double) * (blocks + 1)));
+  if (partial == nullptr) return B2Q_ERR_CUDA;
   sv_norm_partial_kernel<real><<<blocks, 256, 0, s>>>(reinterpret_cast<const C*>(state), total,
                                                       partial);
   B2Q_LAUNCH_CHECK("sv_norm_partial_kernel");
@@ -645,7 +645,6 @@ int norm2_t(const void* state, int n, double* out_host, cudaStream_t s) {
   B2Q_CUDA_CHECK(
       cudaMemcpyAsync(out_host, partial + blocks, sizeof(double), cudaMemcpyDeviceToHost, s));
   B2Q_CUDA_CHECK(cudaStreamSynchronize(s));
-  B2Q_CUDA_CHECK(cudaFreeAsync(partial, s));
   return B2Q_OK;
 }
 
@@ -719,10 +718,9 @@ extern "C" int b2q_sv_gather(const void* state, int dtype, int n_qubits, const u
   for (uint64_t j = 0; j < count; ++j)
     B2Q_REQUIRE(indices[j] < total, "index %llu out of range", (unsigned long long)indices[j]);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  uint64_t* didx = nullptr;
-  double2* dout = nullptr;
-  B2Q_CUDA_CHECK(cudaMallocAsync((void**)&didx, sizeof(uint64_t) * count, s));
-  B2Q_CUDA_CHECK(cudaMallocAsync((void**)&dout, sizeof(double2) * count, s));
+  uint64_t* didx = reinterpret_cast<uint64_t*>(workspace((sizeof(uint64_t) + sizeof(double2)) * count));
+  if (didx == nullptr) return B2Q_ERR_CUDA;
+  double2* dout = reinterpret_cast<double2*>(didx + count);
   B2Q_CUDA_CHECK(
       cudaMemcpyAsync(didx, indices, sizeof(uint64_t) * count, cudaMemcpyHostToDevice, s));
   const unsigned blocks = (unsigned)((count + 255) / 256);
@@ -736,8 +734,6 @@ extern "C" int b2q_sv_gather(const void* state, int dtype, int n_qubits, const u
   B2Q_CUDA_CHECK(
       cudaMemcpyAsync(out_c128, dout, sizeof(double2) * count, cudaMemcpyDeviceToHost, s));
   B2Q_CUDA_CHECK(cudaStreamSynchronize(s));
-  B2Q_CUDA_CHECK(cudaFreeAsync(didx, s));
-  B2Q_CUDA_CHECK(cudaFreeAsync(dout, s));
   return B2Q_OK;
 }
 
@@ -872,14 +868,13 @@ extern "C" int b2q_cdf_sample(const double* probs_dev, uint64_t count, const dou
   if (reps == 0) return B2Q_OK;
   B2Q_REQUIRE(uniforms_dev != nullptr && out_indices_dev != nullptr, "null argument");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  double* cum = nullptr;
-  B2Q_CUDA_CHECK(cudaMallocAsync((void**)&cum, sizeof(double) * count, s));
+  double* cum = reinterpret_cast<double*>(workspace(sizeof(double) * count));
+  if (cum == nullptr) return B2Q_ERR_CUDA;
   scan_inclusive_kernel<<<1, 1024, 0, s>>>(probs_dev, cum, count);
   B2Q_LAUNCH_CHECK("scan_inclusive_kernel");
   cdf_search_kernel<<<(unsigned)((reps + 255) / 256), 256, 0, s>>>(cum, count, uniforms_dev, reps,
                                                                    out_indices_dev);
   B2Q_LAUNCH_CHECK("cdf_search_kernel");
-  B2Q_CUDA_CHECK(cudaFreeAsync(cum, s));
   return B2Q_OK;
 }
 
@@ -951,8 +946,8 @@ extern "C" int b2q_sv_pauli_expectation(const void* state, int dtype, int n_qubi
   const uint64_t total = 1ull << n_qubits;
   B2Q_REQUIRE(x_mask < total && z_mask < total, "mask out of range");
   const unsigned blocks = stride_grid(total, 256);
-  double* partial = nullptr;
-  B2Q_CUDA_CHECK(cudaMallocAsync((void**)&partial, sizeof(double) * 2 * (blocks + 1), s));
+  double* partial = reinterpret_cast<double*>(workspace(sizeof(double) * 2 * (blocks + 1)));
+  if (partial == nullptr) return B2Q_ERR_CUDA;
   if (dtype == B2Q_C64)
     sv_pauli_partial_kernel<float><<<blocks, 256, 0, s>>>(reinterpret_cast<const float2*>(state),
                                                           total, x_mask, z_mask, partial);
@@ -966,7 +961,6 @@ extern "C" int b2q_sv_pauli_expectation(const void* state, int dtype, int n_qubi
   B2Q_CUDA_CHECK(
       cudaMemcpyAsync(h, partial + 2 * blocks, sizeof(double) * 2, cudaMemcpyDeviceToHost, s));
   B2Q_CUDA_CHECK(cudaStreamSynchronize(s));
-  B2Q_CUDA_CHECK(cudaFreeAsync(partial, s));
   // P|i> = i^{nY} (-1)^{popcount(i & z)} |i ^ x>, nY = popcount(x & z)
   const int ny = __builtin_popcountll(x_mask & z_mask) & 3;
   double re = h[0], im = h[1];
@@ -1029,15 +1023,14 @@ extern "C" int b2q_dm_trace(const void* rho, int dtype, int n_qubits, double* ou
   B2Q_REQUIRE(rho != nullptr && out != nullptr, "null argument");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const uint64_t dim = 1ull << n_qubits;
-  double* probs = nullptr;
-  B2Q_CUDA_CHECK(cudaMallocAsync((void**)&probs, sizeof(double) * (dim + 1), s));
+  double* probs = reinterpret_cast<double*>(workspace(sizeof(double) * (dim + 1)));
+  if (probs == nullptr) return B2Q_ERR_CUDA;
   int rc = b2q_dm_diagonal(rho, dtype, n_qubits, probs, stream);
   if (rc != B2Q_OK) return rc;
   final_sum_kernel<<<1, 256, 0, s>>>(probs, dim, 1, probs + dim);
   B2Q_LAUNCH_CHECK("final_sum_kernel");
   B2Q_CUDA_CHECK(cudaMemcpyAsync(out, probs + dim, sizeof(double), cudaMemcpyDeviceToHost, s));
   B2Q_CUDA_CHECK(cudaStreamSynchronize(s));
-  B2Q_CUDA_CHECK(cudaFreeAsync(probs, s));
   return B2Q_OK;
 }
 

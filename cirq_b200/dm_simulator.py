@@ -27,6 +27,7 @@ import numpy as np
 from cirq_b200._cirq_compat import import_cirq
 from cirq_b200.device_state import DeviceState
 from cirq_b200.fusion import GateFuser
+from cirq_b200.sv_simulator import _FastConfuseMixin
 
 cirq = import_cirq()
 
@@ -49,6 +50,8 @@ class B200DensityMatrix(qis.QuantumStateRepresentation):
         self._fuser = GateFuser(self._max_fused)
         self._qid_shape = (2,) * self._n
         self.passes = 0
+        self._since_drain = 0
+        self._drain_every = max(8, 2 * self._n)
 
     @classmethod
     def create(cls, *, initial_state: Any = 0, qid_shape, dtype=np.complex64, max_fused_qubits=4):
@@ -87,6 +90,7 @@ class B200DensityMatrix(qis.QuantumStateRepresentation):
         u = np.asarray(u, dtype=np.complex128)
         self._fuser.add(u, self._row_bits(axes))
         self._fuser.add(np.conj(u), self._col_bits(axes))
+        self._maybe_drain(2)
 
     def queue_kraus(self, kraus_ops: Sequence[np.ndarray], axes: Sequence[int]) -> None:
         k = len(axes)
@@ -101,6 +105,17 @@ class B200DensityMatrix(qis.QuantumStateRepresentation):
             term = np.kron(op, np.conj(op))
             sup = term if sup is None else sup + term
         self._fuser.add(sup, self._row_bits(axes) + self._col_bits(axes))
+        self._maybe_drain(1)
+
+    def _maybe_drain(self, added: int) -> None:
+        self._since_drain += added
+        if self._since_drain < self._drain_every:
+            return
+        self._since_drain = 0
+        ready = self._fuser.pop_final_blocks()
+        if ready:
+            self._dev.apply_batch(ready)
+            self.passes += len(ready)
 
     def flush(self) -> None:
         if len(self._fuser) == 0:
@@ -272,7 +287,7 @@ def _strat_apply_channel(action: Any, args: B200DensityMatrixSimulationState, qu
     return True
 
 
-class B200DensityMatrixStepResult(_ref_dm.DensityMatrixStepResult):
+class B200DensityMatrixStepResult(_FastConfuseMixin, _ref_dm.DensityMatrixStepResult):
     """Step result; ``density_matrix()`` downloads rho on first use."""
 
 

@@ -180,6 +180,34 @@ class GateFuser:
         """Fused (matrix, wires) in execution order."""
         return [(b.matrix, b.wires) for b in self._blocks if b.alive]
 
+    def num_blocks(self) -> int:
+        return sum(1 for b in self._blocks if b.alive)
+
+    def pop_final_blocks(self) -> list[tuple[np.ndarray, tuple[int, ...]]]:
+        """Removes and returns the blocks that can no longer change.
+
+        A block is final when it is not the last block on ANY of its wires:
+        merging only ever targets last-blocks, so nothing will be added to it.
+        Final blocks are released in sequence order as long as no block that
+        stays behind precedes them on a shared wire; this lets the caller launch
+        them on the GPU while the host keeps scheduling the rest of the circuit.
+        """
+        out = []
+        kept = []
+        blocked: set[int] = set()
+        for b in self._blocks:
+            if not b.alive:
+                continue
+            final = all(self._last.get(w) is not b for w in b.wires)
+            if final and not any(w in blocked for w in b.wires):
+                out.append((b.matrix, b.wires))
+                self.num_gates -= b.count
+            else:
+                kept.append(b)
+                blocked.update(b.wires)
+        self._blocks = kept
+        return out
+
     def clear(self) -> None:
         self._blocks = []
         self._last = {}

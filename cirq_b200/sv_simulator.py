@@ -60,6 +60,8 @@ class B200StateVector(qis.QuantumStateRepresentation):
         self._fuser = GateFuser(self._max_fused)
         self._qid_shape = (2,) * self._n
         self.passes = 0  # GPU gate passes issued so far (for benchmarks)
+        self._since_drain = 0
+        self._drain_every = max(8, self._n)
 
     # ------------------------------------------------------------------ creation
 
@@ -104,6 +106,18 @@ class B200StateVector(qis.QuantumStateRepresentation):
             self._dev.scale(complex(np.asarray(matrix).reshape(-1)[0]))
             return
         self._fuser.add(matrix, self._bits(axes))
+        self._since_drain += 1
+        if self._since_drain >= self._drain_every:
+            self._drain()
+
+    def _drain(self) -> None:
+        """Launches the blocks that can no longer grow, so the GPU works while
+        the host keeps scheduling (kernel launches are asynchronous)."""
+        self._since_drain = 0
+        ready = self._fuser.pop_final_blocks()
+        if ready:
+            self._dev.apply_batch(ready)
+            self.passes += len(ready)
 
     def flush(self) -> None:
         if len(self._fuser) == 0:
@@ -350,7 +364,76 @@ def _strat_channel(action: Any, args: B200StateVectorSimulationState, qubits) ->
     return True
 
 
-class B200SimulatorStep(state_vector.StateVectorMixin, state_vector_simulator.StateVectorStepResult):
+class _FastConfuseMixin:
+    """Vectorised ``StepResult.sample_measurement_ops`` (sim/simulator.py:733-820).
+
+    Same validation, ordering, invert-mask, confusion-map and repeated-key
+    semantics as the reference, but without its per-repetition Python loops:
+    ``_confuse_results`` (:822-843) walks every repetition even when no
+    measurement has a confusion map (2 s per million samples) and the per-qubit
+    column copies are replaced by one gather."""
+
+    def _confuse_results(self, bits, qubits, confusion_map, seed=None) -> None:
+        if not confusion_map:
+            return
+        super()._confuse_results(bits, qubits, confusion_map, seed)
+
+    def sample_measurement_ops(
+        self, measurement_ops, repetitions: int = 1, seed=None, *, _allow_repeated=False
+    ):
+        import collections
+
+        for op in measurement_ops:
+            if not isinstance(op.gate, ops.MeasurementGate):
+                raise ValueError(f'{op.gate} was not a MeasurementGate')
+        result = collections.Counter(
+            key for op in measurement_ops for key in protocols.measurement_key_names(op)
+        )
+        if result and not _allow_repeated:
+            duplicates = [k for k, v in result.most_common() if v > 1]
+            if duplicates:
+                raise ValueError(f"Measurement key {','.join(duplicates)} repeated")
+
+        measured_qubits = []
+        seen_qubits = set()
+        for op in measurement_ops:
+            for q in op.qubits:
+                if q not in seen_qubits:
+                    seen_qubits.add(q)
+                    measured_qubits.append(q)
+
+        indexed_sample = self.sample(measured_qubits, repetitions, seed=seed)
+        qubits_to_index = {q: i for i, q in enumerate(measured_qubits)}
+        results = {}
+        for op in measurement_ops:
+            gate = op.gate
+            key = gate.key
+            cols = [qubits_to_index[q] for q in op.qubits]
+            if cols == list(range(indexed_sample.shape[1])):
+                arr = indexed_sample if len(measurement_ops) == 1 else indexed_sample.copy()
+            else:
+                arr = indexed_sample[:, cols]
+            # the reference returns int8 on this path (sim/simulator.py:802)
+            out = arr.view(np.int8) if arr.dtype == np.uint8 else arr.astype(np.int8, copy=False)
+            inv = [i for i, flip in enumerate(gate.full_invert_mask()) if flip]
+            if inv:
+                out[:, inv] ^= 1
+            self._confuse_results(out, op.qubits, gate.confusion_map, seed)
+            if _allow_repeated:
+                results.setdefault(key, []).append(out)
+            else:
+                results[key] = out
+        if not _allow_repeated:
+            return results
+        return {
+            k: (v[0][:, np.newaxis, :] if len(v) == 1 else np.array(v).swapaxes(0, 1))
+            for k, v in results.items()
+        }
+
+
+class B200SimulatorStep(
+    _FastConfuseMixin, state_vector.StateVectorMixin, state_vector_simulator.StateVectorStepResult
+):
     """Step result of ``B200Simulator`` (replaces ``SparseSimulatorStep``,
     sim/sparse_simulator.py:221-290)."""
 

@@ -85,3 +85,23 @@ def test_fuser_incremental_interface():
     np.testing.assert_allclose(run(4, f.blocks()), run(4, gates), atol=1e-10)
     f.clear()
     assert f.blocks() == [] and len(f) == 0
+
+
+@pytest.mark.parametrize('max_q', [2, 3, 4])
+def test_streaming_drain_preserves_semantics(max_q):
+    """Blocks released early by pop_final_blocks followed by the rest equal the
+    sequential circuit, and released blocks never reappear."""
+    rng = np.random.RandomState(50 + max_q)
+    n = 7
+    gates = random_gates(rng, n, 120, max_k=2)
+    f = GateFuser(max_q)
+    emitted = []
+    for i, (m, w) in enumerate(gates):
+        f.add(m, w)
+        if i % 9 == 8:
+            emitted += f.pop_final_blocks()
+    early = len(emitted)
+    emitted += f.blocks()
+    assert early > 0
+    np.testing.assert_allclose(run(n, emitted), run(n, gates), atol=1e-10)
+    assert len(emitted) <= len(fuse_gates(gates, max_q)) + 2

@@ -56,12 +56,12 @@ def emulate_fast_kernel(state, n, matrix, targets, dtype_code):
     reg_off = [0 if l < 0 else (1 << l) for l in pl['reg_off_log2']]
     mat = permuted_matrix(matrix, targets)
     out = state.copy()
+    vb = 1 if vec else 0
     for item in range(1 << pl['log2_items']):
-        base = insert_zero_bits(item << zb, pl['ins_pos'])
         x = np.zeros((32, nr), dtype=np.complex128)
         addr = np.zeros((32, nr), dtype=np.int64)
         for lane in range(32):
-            b = base + ((lane << 1) if vec else lane)
+            b = insert_zero_bits(((item << 5) | lane) << vb, pl['ins_pos'])
             for r in range(nr):
                 off = 0
                 if vec:
@@ -164,6 +164,80 @@ def test_five_qubit_gate_all_in_zone_c64():
     np.testing.assert_allclose(got, orc.apply_matrix(state, n, matrix, targets), atol=1e-11)
 
 
+@pytest.fixture
+def remap_mode():
+    lib = _lib.load()
+    lib.b2q_set_lane_mode(1)
+    yield
+    lib.b2q_set_lane_mode(2)
+
+
+@pytest.fixture
+def shuffle_mode():
+    lib = _lib.load()
+    lib.b2q_set_lane_mode(0)
+    yield
+    lib.b2q_set_lane_mode(2)
+
+
+@pytest.mark.parametrize('targets', CASES_C64 + [[1, 2, 3, 4, 5]])
+def test_emulated_kernel_shuffle_mode_c64(targets, shuffle_mode):
+    n = 11 if len(targets) <= 3 else 13
+    rng = np.random.RandomState(hash(tuple(targets)) % (1 << 31))
+    k = len(targets)
+    state = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    matrix = rng.standard_normal((1 << k, 1 << k)) + 1j * rng.standard_normal((1 << k, 1 << k))
+    got = emulate_fast_kernel(state, n, matrix, targets, 0)
+    np.testing.assert_allclose(got, orc.apply_matrix(state, n, matrix, targets), atol=1e-11)
+
+
+def test_auto_policy_exhaustive_small():
+    """Default (per-target) policy: every target set of size <= 4 drawn from the
+    low 8 bits plus one high bit, both dtypes."""
+    import itertools
+
+    rng = np.random.RandomState(123)
+    n = 13
+    pool = [0, 1, 2, 3, 4, 5, 6, 12]
+    state = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    for code in (0, 1):
+        for k in (1, 2, 3, 4):
+            combos = list(itertools.combinations(pool, k))
+            rng.shuffle(combos)
+            for targets in combos[: 12 if k > 1 else 8]:
+                targets = list(targets)
+                rng.shuffle(targets)
+                matrix = rng.standard_normal((1 << k, 1 << k)) + 1j * rng.standard_normal((1 << k, 1 << k))
+                got = emulate_fast_kernel(state, n, matrix, targets, code)
+                want = orc.apply_matrix(state, n, matrix, targets)
+                np.testing.assert_allclose(got, want, atol=1e-11, err_msg=f'{code} {targets}')
+
+
+@pytest.mark.parametrize('targets', CASES_C64 + [[1, 2, 3, 4, 5]])
+def test_emulated_kernel_remap_mode_c64(targets, remap_mode):
+    n = 11 if len(targets) <= 3 else 13
+    rng = np.random.RandomState(hash(tuple(targets)) % (1 << 31))
+    k = len(targets)
+    pl = get_plan(0, n, targets)
+    assert pl['feasible'] and not pl['swaps']
+    state = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    matrix = rng.standard_normal((1 << k, 1 << k)) + 1j * rng.standard_normal((1 << k, 1 << k))
+    got = emulate_fast_kernel(state, n, matrix, targets, 0)
+    np.testing.assert_allclose(got, orc.apply_matrix(state, n, matrix, targets), atol=1e-11)
+
+
+@pytest.mark.parametrize('targets', [[0], [4], [0, 1], [3, 4], [0, 2, 4], [0, 1, 2, 3], [4, 5, 6, 0]])
+def test_emulated_kernel_remap_mode_c128(targets, remap_mode):
+    n = 11
+    rng = np.random.RandomState(hash(tuple(targets)) % (1 << 31))
+    k = len(targets)
+    assert not get_plan(1, n, targets)['swaps']
+    state = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    matrix = rng.standard_normal((1 << k, 1 << k)) + 1j * rng.standard_normal((1 << k, 1 << k))
+    got = emulate_fast_kernel(state, n, matrix, targets, 1)
+    np.testing.assert_allclose(got, orc.apply_matrix(state, n, matrix, targets), atol=1e-12)
+
+
 def test_plan_covers_every_amplitude_exactly_once():
     for dtype_code, zb in ((0, 6), (1, 5)):
         for targets in ([3, 20], [0, 1, 2], [25, 26, 27, 28], [7]):
@@ -171,8 +245,8 @@ def test_plan_covers_every_amplitude_exactly_once():
             assert pl['feasible']
             rb = pl['S'] + len(targets) + pl['GT']
             assert pl['log2_items'] + zb + pl['n_ins'] == 30
-            # register-resident high bits are distinct and above the zone
-            assert len(set(pl['ins_pos'])) == pl['n_ins'] and min(pl['ins_pos']) >= zb
+            # register-resident bits are distinct and never the vector bit
+            assert len(set(pl['ins_pos'])) == pl['n_ins'] and min(pl['ins_pos']) >= (1 if dtype_code == 0 else 0)
             assert pl['n_ins'] == sum(1 for l in pl['reg_off_log2'][:rb] if l >= 0)
 
 

@@ -42,8 +42,12 @@ def main():
     ap.add_argument('--dtype', default='c64')
     ap.add_argument('--reps', type=int, default=10)
     ap.add_argument('--out', default='')
+    ap.add_argument('--lane-mode', type=int, default=None)
     args = ap.parse_args()
     dtype = np.complex64 if args.dtype == 'c64' else np.complex128
+    if args.lane_mode is not None:
+        from cirq_b200 import _lib
+        _lib.load().b2q_set_lane_mode(args.lane_mode)
     n = args.n
     rng = np.random.RandomState(0)
     dev = DeviceState.basis(n, dtype, 0)
@@ -54,11 +58,11 @@ def main():
         'k1_high': [hi], 'k1_mid': [zb + 2], 'k1_bit0': [0], 'k1_lane': [3],
         'k2_high': [hi, hi - 1], 'k2_mid': [zb, zb + 1], 'k2_spread': [hi, zb + 3],
         'k2_bit0_high': [0, hi], 'k2_lane_high': [2, hi], 'k2_lane_lane': [1, 4],
-        'k2_bit0_lane': [0, 3],
+        'k2_bit0_lane': [0, 3], 'k2_low': [1, 2], 'k2_bit01': [0, 1],
         'k3_high': [hi, hi - 1, hi - 2], 'k3_mid': [zb, zb + 1, zb + 2],
-        'k3_lane_high': [2, hi, hi - 5], 'k3_lanes': [1, 2, 3],
+        'k3_lane_high': [2, hi, hi - 5], 'k3_lanes': [1, 2, 3], 'k3_bit012': [0, 1, 2], 'k3_lanes345': [3, 4, 5],
         'k4_high': [hi, hi - 1, hi - 2, hi - 3], 'k4_mid': [zb, zb + 2, zb + 4, zb + 6],
-        'k4_lane_high': [1, 3, hi, hi - 1], 'k4_lanes': [1, 2, 3, 4],
+        'k4_lane_high': [1, 3, hi, hi - 1], 'k4_lanes': [1, 2, 3, 4], 'k4_lane5_high': [5, hi, hi - 1, hi - 2], 'k4_bit0_high': [0, hi, hi - 1, hi - 2], 'k4_lane1_high': [1, hi, hi - 1, hi - 2],
     }
     if dtype == np.complex64:
         classes.update({
