@@ -344,7 +344,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='rqc30', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default='rqc30', choices=sorted(WORKLOADS) + ['rc_hbm'])
     ap.add_argument('--max-fused', dest='max_fused', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

@@ -72,6 +72,12 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_int, c_int, POINTER(c_int), POINTER(c_int), c_int, c_double, c_void_p],
     ),
+    'b2q_dist_alloc': (c_int, [c_uint64, POINTER(c_void_p)]),
+    'b2q_dist_free': (c_int, [c_void_p]),
+    'b2q_dist_ipc_get': (c_int, [c_void_p, c_void_p]),
+    'b2q_dist_ipc_open': (c_int, [c_void_p, POINTER(c_void_p)]),
+    'b2q_dist_ipc_close': (c_int, [c_void_p]),
+    'b2q_dist_swap_bit': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'b2q_dist_pack': (c_int, [c_void_p, c_int, c_int, POINTER(c_int), c_int, c_void_p, c_void_p]),
     'b2q_dist_unpack': (c_int, [c_void_p, c_int, c_int, POINTER(c_int), c_int, c_void_p, c_void_p]),
 }

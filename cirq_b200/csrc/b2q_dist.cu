@@ -1,0 +1,137 @@
+// Sharded state vector: peer-memory exchange kernels (NVLink 5 / NVSwitch).
+//
+// The reference has no multi-device code; the closest concept is the
+// index-only qubit relabel of cirq-core/cirq/sim/simulation_product_state.py:95-108.
+// Here the top log2(P) index bits are the rank id ("global" qubits).  A gate on a
+// global qubit is served by swapping that global bit with a local bit: every
+// amplitude whose (global bit, local bit) values differ moves to the partner
+// rank.  The exchange is ONE kernel per rank that loads from and stores to the
+// partner's HBM directly through its IPC-mapped pointer (LDG/STG on peer
+// addresses over NVLink), each rank serving half of the index range so both
+// link directions carry the same traffic; there is no staging buffer, which
+// matters at 34 local qubits (137 GB shard on a 180 GB device).
+#include "b2q_common.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+namespace b2q {
+
+template <typename V>
+__device__ __forceinline__ V ld16(const V* p) {
+  return *p;
+}
+
+// 16-byte vectors.  j enumerates the 2^(n_local-1) index combinations of all
+// local bits except L (in vector units); this rank exchanges its element with
+// local bit L == (1 - gbit) against the partner's element with L == gbit.
+template <typename V, int ELEMS_LOG2>
+__global__ void __launch_bounds__(256)
+    dist_swap_bit_kernel(V* __restrict__ mine, V* __restrict__ peer, int lbit_v, int gbit,
+                         uint64_t jv_begin, uint64_t jv_end) {
+  // lbit_v: position of L in vector-index units (L - ELEMS_LOG2)
+  constexpr int U = 4;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t mine_or = (uint64_t)(1 - gbit) << lbit_v;
+  const uint64_t peer_or = (uint64_t)gbit << lbit_v;
+  uint64_t j = jv_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; j + (U - 1) * stride < jv_end; j += U * stride) {
+    V a[U], b[U];
+    uint64_t base[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      base[u] = insert_zero_bit(j + u * stride, lbit_v);
+      b[u] = peer[base[u] | peer_or];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) a[u] = mine[base[u] | mine_or];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      mine[base[u] | mine_or] = b[u];
+      peer[base[u] | peer_or] = a[u];
+    }
+  }
+  for (; j < jv_end; j += stride) {
+    const uint64_t base = insert_zero_bit(j, lbit_v);
+    const V b = peer[base | peer_or];
+    const V a = mine[base | mine_or];
+    mine[base | mine_or] = b;
+    peer[base | peer_or] = a;
+  }
+}
+
+}  // namespace b2q
+
+using namespace b2q;
+
+extern "C" int b2q_dist_alloc(uint64_t bytes, void** out_ptr) {
+  B2Q_REQUIRE(out_ptr != nullptr && bytes > 0, "bad arguments");
+  B2Q_CUDA_CHECK(cudaMalloc(out_ptr, bytes));
+  return B2Q_OK;
+}
+
+extern "C" int b2q_dist_free(void* ptr) {
+  if (ptr != nullptr) B2Q_CUDA_CHECK(cudaFree(ptr));
+  return B2Q_OK;
+}
+
+extern "C" int b2q_dist_ipc_get(void* ptr, unsigned char* handle64) {
+  B2Q_REQUIRE(ptr != nullptr && handle64 != nullptr, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  B2Q_CUDA_CHECK(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle64, &h, 64);
+  return B2Q_OK;
+}
+
+extern "C" int b2q_dist_ipc_open(const unsigned char* handle64, void** out_ptr) {
+  B2Q_REQUIRE(handle64 != nullptr && out_ptr != nullptr, "null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  B2Q_CUDA_CHECK(cudaIpcOpenMemHandle(out_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return B2Q_OK;
+}
+
+extern "C" int b2q_dist_ipc_close(void* ptr) {
+  if (ptr != nullptr) B2Q_CUDA_CHECK(cudaIpcCloseMemHandle(ptr));
+  return B2Q_OK;
+}
+
+extern "C" int b2q_dist_swap_bit(void* mine, void* peer, int dtype, int n_local, int local_bit,
+                                 int my_global_bit_value, void* stream) {
+  B2Q_REQUIRE(mine != nullptr && peer != nullptr, "null argument");
+  B2Q_REQUIRE(dtype == B2Q_C64 || dtype == B2Q_C128, "bad dtype %d", dtype);
+  B2Q_REQUIRE(my_global_bit_value == 0 || my_global_bit_value == 1, "bad global bit value");
+  const int elems_log2 = dtype == B2Q_C64 ? 1 : 0;
+  B2Q_REQUIRE(local_bit >= elems_log2 && local_bit < n_local,
+              "local bit %d must be in [%d, %d)", local_bit, elems_log2, n_local);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // vector-index space: (n_local - elems_log2) bits, minus the swapped bit
+  const uint64_t nvec_rest = 1ull << (n_local - elems_log2 - 1);
+  // Rank with global bit 0 serves the lower half of the range, the partner the
+  // upper half (a single vector in total is served by the former).
+  uint64_t b0, e0;
+  if (nvec_rest == 1) {
+    if (my_global_bit_value == 1) return B2Q_OK;
+    b0 = 0;
+    e0 = 1;
+  } else {
+    const uint64_t half = nvec_rest / 2;
+    b0 = my_global_bit_value ? half : 0;
+    e0 = my_global_bit_value ? nvec_rest : half;
+  }
+  const uint64_t work = e0 - b0;
+  const uint64_t blocks =
+      std::max<uint64_t>(1, std::min<uint64_t>((work / 4 + 255) / 256, 148ull * 16));
+  const int lbit_v = local_bit - elems_log2;
+  if (dtype == B2Q_C64)
+    dist_swap_bit_kernel<float4, 1><<<(unsigned)blocks, 256, 0, s>>>(
+        reinterpret_cast<float4*>(mine), reinterpret_cast<float4*>(peer), lbit_v,
+        my_global_bit_value, b0, e0);
+  else
+    dist_swap_bit_kernel<double2, 0><<<(unsigned)blocks, 256, 0, s>>>(
+        reinterpret_cast<double2*>(mine), reinterpret_cast<double2*>(peer), lbit_v,
+        my_global_bit_value, b0, e0);
+  B2Q_LAUNCH_CHECK("dist_swap_bit_kernel");
+  return B2Q_OK;
+}

@@ -1,0 +1,444 @@
+"""Sharded state vector over P = 2^g GPUs of one node (one process per GPU).
+
+Layout: the flat big-endian index of the n-qubit state is split
+on its top g bits — physical bits n_local .. n-1 are *global* (their value is
+the rank id), bits 0 .. n_local-1 are *local*; rank r holds the contiguous slice
+``[r * 2^n_local, (r+1) * 2^n_local)`` as an ordinary ``DeviceState``.
+
+* A fused block whose wires are all local runs the unchanged 1-GPU kernel on
+  every rank, no communication.
+* A block that is diagonal in its global wires needs no communication either:
+  each rank applies the sub-matrix selected by its rank bits.
+* Otherwise the needed global bits are exchanged with local bits
+  (``swap_global_local``): one peer-memory kernel per rank over NVLink
+  (``b2q_dist_swap_bit``), half a shard out and in per GPU.  Nothing is moved
+  back: the logical->physical bit map is updated instead, and the victim
+  local bit is the one whose next use lies furthest in the future.
+
+torch.distributed (NCCL, or gloo in the CPU tests) is used for rendezvous,
+barriers, IPC-handle exchange and scalar reductions only; the state exchange
+itself is the library's own kernel.
+
+The reference has no counterpart; the closest concept is the
+index-only SWAP relabel of cirq-core/cirq/sim/simulation_product_state.py:95-108.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Sequence
+
+import numpy as np
+
+from cirq_b200 import _lib
+from cirq_b200._lib import check
+
+
+def block_diagonal_in(matrix: np.ndarray, wires: Sequence[int], diag_wires: Sequence[int], atol=0.0):
+    """If `matrix` (on `wires`, wires[0] = MSB) never changes the basis value of
+    `diag_wires`, returns {values tuple -> sub-matrix on the remaining wires};
+    else None."""
+    k = len(wires)
+    t = np.asarray(matrix).reshape((2,) * (2 * k))
+    pos = [wires.index(w) for w in diag_wires]
+    rest = [i for i in range(k) if i not in pos]
+    subs = {}
+    for vals in np.ndindex(*(2,) * len(pos)):
+        # the off-diagonal (out != in) blocks must vanish
+        idx = [slice(None)] * (2 * k)
+        for p, v in zip(pos, vals):
+            idx[p] = v
+        row_fixed = t[tuple(idx)]  # legs: rest outs..., all ins (k)
+        # now the in legs: position of in-leg for wire index i is (len(rest) + i)
+        sel = [slice(None)] * row_fixed.ndim
+        for p, v in zip(pos, vals):
+            sel[len(rest) + p] = v
+        diag_block = row_fixed[tuple(sel)]
+        off = np.array(row_fixed, copy=True)
+        off[tuple(sel)] = 0
+        if np.sum(np.abs(off) ** 2) > atol:
+            return None
+        subs[tuple(int(v) for v in vals)] = diag_block.reshape(1 << len(rest), 1 << len(rest))
+    return subs
+
+
+class _RawShard:
+    """Device memory from b2q_dist_alloc exposed to torch (zero copy)."""
+
+    def __init__(self, ptr: int, n_elems: int, real_typestr: str):
+        self.ptr = ptr
+        self.__cuda_array_interface__ = {
+            'shape': (n_elems, 2),
+            'typestr': real_typestr,
+            'data': (ptr, False),
+            'version': 2,
+        }
+
+
+class ShardBackend:
+    """CUDA backend: shard in IPC-shared HBM, exchange by peer-memory kernel."""
+
+    def __init__(self, n_local: int, dtype, group=None):
+        import torch
+        import torch.distributed as dist
+
+        from cirq_b200.device_state import DeviceState
+
+        self.torch = torch
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.n_local = n_local
+        self.dtype = np.dtype(dtype)
+        self.lib = _lib.load()
+        code = _lib.dtype_code(self.dtype)
+        nbytes = (1 << n_local) * (8 if code == _lib.C64 else 16)
+        ptr = ctypes.c_void_p()
+        check(self.lib.b2q_dist_alloc(ctypes.c_uint64(nbytes), ctypes.byref(ptr)))
+        self._ptr = ptr.value
+        raw = _RawShard(self._ptr, 1 << n_local, '<f4' if code == _lib.C64 else '<f8')
+        self._raw = raw
+        tensor = torch.as_tensor(raw, device='cuda')
+        self.local = DeviceState(n_local, self.dtype, tensor=tensor)
+        # exchange IPC handles
+        handle = (ctypes.c_ubyte * 64)()
+        check(self.lib.b2q_dist_ipc_get(ctypes.c_void_p(self._ptr), handle))
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device='cuda')
+        gathered = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(gathered, mine, group=group)
+        self.peer_ptrs = {}
+        for r, h in enumerate(gathered):
+            if r == self.rank:
+                continue
+            buf = (ctypes.c_ubyte * 64)(*h.cpu().tolist())
+            out = ctypes.c_void_p()
+            check(self.lib.b2q_dist_ipc_open(buf, ctypes.byref(out)))
+            self.peer_ptrs[r] = out.value
+        self.barrier()
+
+    def barrier(self):
+        self.torch.cuda.current_stream().synchronize()
+        self.dist.barrier(group=self.group)
+
+    def swap_bit(self, partner: int, local_bit: int, my_gbit: int) -> None:
+        """Both ranks of every pair call this between two barriers."""
+        self.barrier()
+        stream = ctypes.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+        check(
+            self.lib.b2q_dist_swap_bit(
+                ctypes.c_void_p(self._ptr), ctypes.c_void_p(self.peer_ptrs[partner]),
+                self.local.code, self.n_local, local_bit, my_gbit, stream,
+            )
+        )
+        self.barrier()
+
+    def all_reduce_sum(self, value: float) -> float:
+        t = self.torch.tensor([value], dtype=self.torch.float64, device='cuda')
+        self.dist.all_reduce(t, group=self.group)
+        return float(t.item())
+
+    def all_gather_floats(self, value: float) -> list[float]:
+        t = self.torch.tensor([value], dtype=self.torch.float64, device='cuda')
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t, group=self.group)
+        return [float(x.item()) for x in out]
+
+    def gather_objects(self, obj):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def close(self):
+        self.barrier()
+        for p in self.peer_ptrs.values():
+            self.lib.b2q_dist_ipc_close(ctypes.c_void_p(p))
+        self.peer_ptrs = {}
+        self.barrier()
+        self.local = None
+        if self._ptr:
+            self.lib.b2q_dist_free(ctypes.c_void_p(self._ptr))
+            self._ptr = 0
+
+
+class ShardedStateVector:
+    """n-qubit state sharded over the ranks of a process group.
+
+    All ranks must call every method collectively with identical arguments
+    (SPMD), exactly like a torch.distributed collective.
+    """
+
+    def __init__(self, n_qubits: int, dtype=np.complex64, *, backend=None, group=None,
+                 initial_index: int = 0):
+        if backend is None:
+            import torch.distributed as dist
+
+            world = dist.get_world_size(group)
+            g = world.bit_length() - 1
+            if 1 << g != world:
+                raise ValueError(f'world size {world} is not a power of two')
+            backend = ShardBackend(n_qubits - g, dtype, group)
+        self.backend = backend
+        self.rank = backend.rank
+        self.world = backend.world
+        self.g = self.world.bit_length() - 1
+        if 1 << self.g != self.world:
+            raise ValueError(f'world size {self.world} is not a power of two')
+        self.n = int(n_qubits)
+        self.n_local = self.n - self.g
+        if self.n_local < 2:
+            raise ValueError('need at least 2 local qubits per rank')
+        assert backend.n_local == self.n_local
+        self.dtype = np.dtype(dtype)
+        self.local = backend.local
+        # logical bit -> physical bit (physical bits >= n_local are global)
+        self.phys = list(range(self.n))
+        self.swaps = 0
+        self.passes = 0
+        self.local_only_blocks = 0
+        self.diag_global_blocks = 0
+        self._init_basis(initial_index)
+
+    # ------------------------------------------------------------------ helpers
+
+    def _init_basis(self, index: int) -> None:
+        owner = index >> self.n_local
+        lib = _lib.load()
+        if hasattr(self.local, 'ptr'):
+            import torch
+
+            stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            if owner == self.rank:
+                check(lib.b2q_sv_init_basis(self.local.ptr, self.local.code, self.n_local,
+                                            ctypes.c_uint64(index & ((1 << self.n_local) - 1)), stream))
+            else:
+                self.local.tensor.zero_()
+        else:  # test backend
+            self.local.array[:] = 0
+            if owner == self.rank:
+                self.local.array[index & ((1 << self.n_local) - 1)] = 1
+        self.backend.barrier()
+
+    def _rank_bit(self, phys_bit: int) -> int:
+        return (self.rank >> (phys_bit - self.n_local)) & 1
+
+    def swap_global_local(self, global_phys: int, local_phys: int) -> None:
+        """Exchanges physical bits (global, local) of the index: data moves, the
+        logical->physical map follows."""
+        gi = global_phys - self.n_local
+        partner = self.rank ^ (1 << gi)
+        self.backend.swap_bit(partner, local_phys, self._rank_bit(global_phys))
+        for l in range(self.n):
+            if self.phys[l] == global_phys:
+                self.phys[l] = local_phys
+            elif self.phys[l] == local_phys:
+                self.phys[l] = global_phys
+        self.swaps += 1
+
+    # ------------------------------------------------------------------ gates
+
+    def apply_blocks(self, blocks: Sequence[tuple[np.ndarray, Sequence[int]]]) -> None:
+        """Applies fused blocks [(matrix, logical bits)], reordering commuting
+        blocks so that everything executable without communication runs before
+        the next qubit swap."""
+        remaining = [(np.asarray(m), tuple(int(w) for w in ws)) for m, ws in blocks]
+        while remaining:
+            progressed = True
+            while progressed and remaining:
+                progressed = False
+                blocked: set[int] = set()
+                keep = []
+                batch = []
+                for m, ws in remaining:
+                    if blocked.isdisjoint(ws):
+                        local_form = self._local_form(m, ws)
+                        if local_form is not None:
+                            if local_form[1]:
+                                batch.append(local_form)
+                            progressed = True
+                            continue
+                    keep.append((m, ws))
+                    blocked.update(ws)
+                if batch:
+                    self.local.apply_batch(batch)
+                    self.passes += len(batch)
+                remaining = keep
+            if not remaining:
+                break
+            # The first remaining block has no unexecuted predecessor: bring its
+            # global wires in, evicting the local bits needed furthest away.
+            m, ws = remaining[0]
+            needed = [w for w in ws if self.phys[w] >= self.n_local]
+            protected = {self.phys[w] for w in ws}
+            for w in needed:
+                victim = self._choose_victim(remaining, protected)
+                protected.add(victim)
+                self.swap_global_local(self.phys[w], victim)
+
+    def _local_form(self, m: np.ndarray, ws: tuple[int, ...]):
+        """(matrix, local physical bits) if the block can run without
+        communication on this rank, else None."""
+        pw = [self.phys[w] for w in ws]
+        glob = [p for p in pw if p >= self.n_local]
+        if not glob:
+            self.local_only_blocks += 1
+            return m, pw
+        subs = block_diagonal_in(m, pw, glob, atol=1e-24)
+        if subs is None:
+            return None
+        self.diag_global_blocks += 1
+        vals = tuple(self._rank_bit(p) for p in glob)
+        rest = [p for p in pw if p < self.n_local]
+        sub = subs[vals]
+        if not rest:
+            # pure phase on this rank
+            self.local.scale(complex(sub.reshape(-1)[0]))
+            return sub, []
+        return sub, rest
+
+    def _choose_victim(self, remaining, protected: set[int]) -> int:
+        """Local physical bit (not protected, >= 1 for 16-byte vectors) whose
+        next use is furthest in the future."""
+        next_use = {}
+        for pos, (_, ws) in enumerate(remaining):
+            for w in ws:
+                p = self.phys[w]
+                if p < self.n_local and p not in next_use:
+                    next_use[p] = pos
+        best, best_pos = None, -1
+        lowest = 1 if self.dtype == np.dtype(np.complex64) else 0
+        for p in range(self.n_local - 1, lowest - 1, -1):
+            if p in protected:
+                continue
+            pos = next_use.get(p, 1 << 60)
+            if pos > best_pos:
+                best, best_pos = p, pos
+        if best is None:
+            raise RuntimeError('no local bit available to swap with')
+        return best
+
+    # ------------------------------------------------------------------ read-out
+
+    def norm2(self) -> float:
+        return self.backend.all_reduce_sum(self.local.norm2())
+
+    def sample(self, repetitions: int, seed=None) -> np.ndarray:
+        """uint8[reps, n] bitstrings (column a = logical qubit axis a, i.e. logical
+        bit n-1-a) drawn from |psi|^2; identical on every rank.  Every rank draws
+        the same uniforms; a sample belongs to the rank whose cumulative
+        probability interval contains it and is resolved there by the 1-GPU
+        sampler."""
+        rng = np.random.RandomState(seed)
+        u = rng.random_sample(repetitions)
+        totals = np.array(self.backend.all_gather_floats(self.local.norm2()))
+        cum = np.cumsum(totals)
+        target = u * cum[-1]
+        owner = np.minimum(np.searchsorted(cum, target, side='right'), self.world - 1)
+        mine = np.nonzero(owner == self.rank)[0]
+        before = cum[self.rank] - totals[self.rank]
+        local_u = np.clip((target[mine] - before) / max(totals[self.rank], 1e-300), 0.0, 1.0 - 2**-53)
+        if mine.size:
+            local_idx = np.asarray(self.local.sample_indices(local_u), dtype=np.uint64)
+        else:
+            local_idx = np.zeros(0, dtype=np.uint64)
+        phys_idx = local_idx | (np.uint64(self.rank) << np.uint64(self.n_local))
+        parts = self.backend.gather_objects((mine, phys_idx))
+        full = np.zeros(repetitions, dtype=np.uint64)
+        for pos, idx in parts:
+            full[pos] = idx
+        out = np.zeros((repetitions, self.n), dtype=np.uint8)
+        for axis in range(self.n):
+            logical_bit = self.n - 1 - axis
+            out[:, axis] = (full >> np.uint64(self.phys[logical_bit])) & np.uint64(1)
+        return out
+
+    def gather_state(self) -> np.ndarray:
+        """Full state in LOGICAL order on every rank (tests / small n only)."""
+        parts = self.backend.gather_objects(self.local.to_numpy())
+        phys_state = np.concatenate(parts)
+        # un-permute: logical index bit l sits at physical bit phys[l]
+        idx = np.arange(1 << self.n, dtype=np.int64)
+        src = np.zeros_like(idx)
+        for l in range(self.n):
+            src |= ((idx >> l) & 1) << self.phys[l]
+        return phys_state[src]
+
+    def close(self):
+        if hasattr(self.backend, 'close'):
+            self.backend.close()
+
+
+class B200ShardedSimulator:
+    """Cirq-facing entry point of the sharded path (SPMD: every rank of the
+    process group calls it with the same circuit).
+
+    Supports what config 4 needs: unitary circuits, optionally followed by
+    terminal measurements (``run``).  Mid-circuit measurement, noise and
+    classical control stay on the single-GPU simulators.
+    """
+
+    def __init__(self, *, dtype=np.complex64, seed=None, max_fused_qubits: int = 4, group=None):
+        self.dtype = np.dtype(dtype)
+        self.seed = seed
+        self.max_fused = int(max_fused_qubits)
+        self.group = group
+
+    def _gates(self, circuit, qubits):
+        from cirq_b200._cirq_compat import import_cirq
+
+        cirq = import_cirq()
+        n = len(qubits)
+        axis = {q: i for i, q in enumerate(qubits)}
+        gates, measured = [], []
+        for moment in circuit:
+            for op in moment:
+                if cirq.is_measurement(op):
+                    measured.append(op)
+                    continue
+                if measured and any(q in {x for m in measured for x in m.qubits} for q in op.qubits):
+                    raise ValueError('B200ShardedSimulator only supports terminal measurements')
+                if not cirq.has_unitary(op):
+                    raise TypeError(f"B200ShardedSimulator doesn't support {op!r}")
+                gates.append((cirq.unitary(op), [n - 1 - axis[q] for q in op.qubits]))
+        return gates, measured
+
+    def simulate_sharded(self, circuit, qubit_order=None, initial_state: int = 0) -> ShardedStateVector:
+        """Evolves |initial_state> and returns the sharded final state."""
+        from cirq_b200._cirq_compat import import_cirq
+        from cirq_b200.fusion import fuse_gates
+
+        cirq = import_cirq()
+        qubits = cirq.QubitOrder.as_qubit_order(
+            qubit_order if qubit_order is not None else cirq.QubitOrder.DEFAULT
+        ).order_for(circuit.all_qubits())
+        gates, _ = self._gates(circuit, qubits)
+        sv = ShardedStateVector(len(qubits), self.dtype, group=self.group, initial_index=initial_state)
+        sv.apply_blocks(fuse_gates(gates, self.max_fused))
+        return sv
+
+    def run(self, circuit, repetitions: int = 1) -> dict:
+        """{key: int8[reps, n_measured]} like ``cirq.Result.measurements``,
+        identical on every rank."""
+        from cirq_b200._cirq_compat import import_cirq
+        from cirq_b200.fusion import fuse_gates
+
+        cirq = import_cirq()
+        qubits = cirq.QubitOrder.DEFAULT.order_for(circuit.all_qubits())
+        gates, measured = self._gates(circuit, qubits)
+        if not measured:
+            raise ValueError('Circuit has no measurements to sample.')
+        sv = ShardedStateVector(len(qubits), self.dtype, group=self.group)
+        try:
+            sv.apply_blocks(fuse_gates(gates, self.max_fused))
+            bits = sv.sample(repetitions, seed=self.seed)
+        finally:
+            sv.close()
+        axis = {q: i for i, q in enumerate(qubits)}
+        out = {}
+        for op in measured:
+            cols = [axis[q] for q in op.qubits]
+            arr = bits[:, cols].astype(np.int8)
+            inv = [i for i, f in enumerate(op.gate.full_invert_mask()) if f]
+            if inv:
+                arr[:, inv] ^= 1
+            out[op.gate.key] = arr
+        return out

@@ -185,6 +185,24 @@ int b2q_dist_pack(const void* shard, int dtype, int n_local, const int* local_bi
 int b2q_dist_unpack(void* shard, int dtype, int n_local, const int* local_bits, int g,
                     const void* packed, void* stream);
 
+/* Shard memory shared between the per-GPU processes of one node (CUDA IPC):
+ * b2q_dist_alloc = cudaMalloc; b2q_dist_ipc_get fills a 64-byte handle that the
+ * other ranks turn into a peer pointer with b2q_dist_ipc_open. */
+int b2q_dist_alloc(uint64_t bytes, void** out_ptr);
+int b2q_dist_free(void* ptr);
+int b2q_dist_ipc_get(void* ptr, unsigned char* handle64);
+int b2q_dist_ipc_open(const unsigned char* handle64, void** out_ptr);
+int b2q_dist_ipc_close(void* ptr);
+
+/* Global<->local qubit swap, one kernel per rank over NVLink peer memory: the
+ * caller's shard `mine` (global bit value `my_global_bit_value`) and the
+ * partner's shard `peer` (the other value) exchange, for half of the index
+ * range each, the amplitudes whose local bit `local_bit` differs from the
+ * owner's global bit.  Both ranks of a pair must call it between two barriers.
+ * local_bit >= 1 for complex64 (16-byte vectors). */
+int b2q_dist_swap_bit(void* mine, void* peer, int dtype, int n_local, int local_bit,
+                      int my_global_bit_value, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,56 @@
+"""TEST-ONLY backend for cirq_b200.dist.ShardedStateVector: numpy shards (the
+oracle-backed fake device) exchanged over torch.distributed/gloo.  Exercises
+the host-side sharding logic (bit maps, scheduler, victim choice, sampling
+routing) with world_size > 1 on a machine without GPUs."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from fake_device import OracleDeviceState
+
+
+class GlooShardBackend:
+    def __init__(self, n_local, dtype):
+        self.rank = dist.get_rank()
+        self.world = dist.get_world_size()
+        self.n_local = n_local
+        self.dtype = np.dtype(dtype)
+        self.local = OracleDeviceState(n_local, dtype)
+
+    def barrier(self):
+        dist.barrier()
+
+    def swap_bit(self, partner, local_bit, my_gbit):
+        # amplitudes with local bit != my global bit value go to the partner
+        arr = self.local.array
+        idx = np.arange(arr.size, dtype=np.int64)
+        sel = ((idx >> local_bit) & 1) == (1 - my_gbit)
+        send = np.ascontiguousarray(arr[sel]).view(np.float64 if self.dtype == np.complex128 else np.float32)
+        send_t = torch.from_numpy(send.copy())
+        recv_t = torch.empty_like(send_t)
+        if self.rank < partner:
+            dist.send(send_t, partner)
+            dist.recv(recv_t, partner)
+        else:
+            dist.recv(recv_t, partner)
+            dist.send(send_t, partner)
+        arr[sel] = recv_t.numpy().view(self.dtype)
+        dist.barrier()
+
+    def all_reduce_sum(self, value):
+        t = torch.tensor([value], dtype=torch.float64)
+        dist.all_reduce(t)
+        return float(t.item())
+
+    def all_gather_floats(self, value):
+        t = torch.tensor([value], dtype=torch.float64)
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t)
+        return [float(x.item()) for x in out]
+
+    def gather_objects(self, obj):
+        out = [None] * self.world
+        dist.all_gather_object(out, obj)
+        return out

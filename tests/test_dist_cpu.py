@@ -1,0 +1,152 @@
+"""Host logic of the sharded state vector with world_size 2 and 4 over gloo
+(CPU): the sharded run must reproduce the single-state oracle exactly, whatever
+swaps the scheduler chooses."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _diag_worker(rank, world, port, n, out_dir):
+    """Only diagonal / controlled operations touch the global qubit: the whole
+    circuit must run without a single exchange."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import torch.distributed as dist
+
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from cirq_b200.dist import ShardedStateVector
+        from fake_dist import GlooShardBackend
+        from oracle import sv_oracle as orc
+
+        rng = np.random.RandomState(9)
+        h = np.array([[1, 1], [1, -1]]) / np.sqrt(2)
+        top = n - 1  # the global qubit for world=2
+        gates = [(h, [q]) for q in range(n - 1)]
+        for q in range(n - 1):
+            cp = np.diag([1, 1, 1, np.exp(1j * rng.standard_normal())])
+            gates.append((cp, [top, q]))
+            cu = np.eye(4, dtype=complex)
+            cu[2:, 2:] = np.linalg.qr(rng.standard_normal((2, 2)) + 1j * rng.standard_normal((2, 2)))[0]
+            gates.append((cu, [top, q]))
+        gates.append((np.diag([1, 1j]), [top]))
+        sv = ShardedStateVector(n, np.complex128, backend=GlooShardBackend(n - 1, np.complex128),
+                                initial_index=1 << top)
+        sv.apply_blocks(gates)
+        got = sv.gather_state()
+        want = orc.run_gate_list(n, gates, dtype=np.complex128, initial=1 << top)
+        if rank == 0:
+            np.savez(os.path.join(out_dir, 'diag.npz'), err=float(np.max(np.abs(got - want))),
+                     swaps=sv.swaps, diag=sv.diag_global_blocks)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_diagonal_on_global_qubit_needs_no_exchange(tmp_path):
+    port = 29500 + (os.getpid() * 3 + 11) % 2000
+    mp.spawn(_diag_worker, args=(2, port, 6, str(tmp_path)), nprocs=2, join=True)
+    res = np.load(os.path.join(str(tmp_path), 'diag.npz'))
+    assert float(res['err']) < 1e-12
+    assert int(res['swaps']) == 0 and int(res['diag']) >= 10
+
+
+def _worker(rank, world, port, n, seed, max_fused, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import torch.distributed as dist
+
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from cirq_b200.dist import ShardedStateVector
+        from cirq_b200.fusion import fuse_gates
+        from fake_dist import GlooShardBackend
+        from oracle import sv_oracle as orc
+
+        rng = np.random.RandomState(seed)
+
+        def unitary(k):
+            d = 1 << k
+            q, r = np.linalg.qr(rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d)))
+            return q * (np.diag(r) / np.abs(np.diag(r)))
+
+        gates = []
+        for _ in range(60):
+            k = int(rng.randint(1, 3))
+            wires = rng.permutation(n)[:k].tolist()
+            kind = rng.randint(4)
+            if kind == 0:
+                m = np.diag(np.exp(1j * rng.standard_normal(1 << k)))  # diagonal: no swap needed
+            elif kind == 1 and k == 2:
+                m = np.eye(4, dtype=complex)
+                m[2:, 2:] = unitary(1)  # controlled-U: diagonal in its control
+            else:
+                m = unitary(k)
+            gates.append((m, wires))
+        g = world.bit_length() - 1
+        sv = ShardedStateVector(n, np.complex128, backend=GlooShardBackend(n - g, np.complex128),
+                                initial_index=3)
+        blocks = fuse_gates(gates, max_fused)
+        sv.apply_blocks(blocks)
+        got = sv.gather_state()
+        want = orc.run_gate_list(n, gates, dtype=np.complex128, initial=3)
+        err = float(np.max(np.abs(got - want)))
+        nrm = sv.norm2()
+        samples = sv.sample(4000, seed=5)
+        if rank == 0:
+            np.savez(os.path.join(out_dir, f'res_{world}_{n}_{seed}.npz'), err=err, norm=nrm,
+                     swaps=sv.swaps, passes=sv.passes, diag=sv.diag_global_blocks,
+                     samples=samples, probs=np.abs(want) ** 2, phys=np.array(sv.phys))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,n,seed,max_fused', [(2, 7, 1, 2), (2, 8, 2, 4), (4, 8, 3, 3), (4, 9, 4, 4)])
+def test_sharded_matches_oracle(tmp_path, world, n, seed, max_fused):
+    port = 29500 + (os.getpid() + seed * 7) % 2000
+    mp.spawn(_worker, args=(world, port, n, seed, max_fused, str(tmp_path)), nprocs=world, join=True)
+    res = np.load(os.path.join(str(tmp_path), f'res_{world}_{n}_{seed}.npz'))
+    assert float(res['err']) < 1e-12
+    assert abs(float(res['norm']) - 1.0) < 1e-12
+    assert int(res['swaps']) >= 1  # dense gates on global qubits forced exchanges
+    # sampled bitstrings follow |psi|^2 in LOGICAL order: chi-squared on 5 top qubits
+    samples, probs = res['samples'], res['probs']
+    top = 5
+    ints = samples[:, :top].astype(np.int64) @ (1 << np.arange(top - 1, -1, -1))
+    hist = np.bincount(ints, minlength=1 << top)
+    expect = probs.reshape(1 << top, -1).sum(axis=1) * len(samples)
+    chi2 = np.sum((hist - expect) ** 2 / np.maximum(expect, 1e-9))
+    dof = (1 << top) - 1
+    assert chi2 < dof + 6 * np.sqrt(2 * dof) + 10
+
+
+def test_block_diagonal_detection():
+    sys.path.insert(0, ROOT)
+    from cirq_b200.dist import block_diagonal_in
+
+    rng = np.random.RandomState(0)
+    u = np.linalg.qr(rng.standard_normal((2, 2)) + 1j * rng.standard_normal((2, 2)))[0]
+    cu = np.eye(4, dtype=complex)
+    cu[2:, 2:] = u
+    subs = block_diagonal_in(cu, [7, 3], [7])
+    assert subs is not None
+    np.testing.assert_allclose(subs[(0,)], np.eye(2))
+    np.testing.assert_allclose(subs[(1,)], u)
+    assert block_diagonal_in(cu, [7, 3], [3]) is None
+    # control listed second
+    sw = np.eye(4)[[0, 2, 1, 3]]
+    cu2 = sw @ cu @ sw
+    subs = block_diagonal_in(cu2, [3, 7], [7])
+    np.testing.assert_allclose(subs[(1,)], u)
+    d = np.diag(np.exp(1j * rng.standard_normal(8)))
+    subs = block_diagonal_in(d, [5, 4, 2], [5, 2])
+    assert subs is not None and subs[(1, 0)].shape == (2, 2)
+    np.testing.assert_allclose(subs[(1, 0)], np.diag([d[4, 4], d[6, 6]]))

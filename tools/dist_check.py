@@ -1,0 +1,92 @@
+"""Multi-GPU correctness + swap bandwidth check (run under torchrun on >= 2 GPUs).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tools/dist_check.py
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    rank = int(os.environ['RANK'])
+    local_rank = int(os.environ['LOCAL_RANK'])
+    world = int(os.environ['WORLD_SIZE'])
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    from cirq_b200.device_state import DeviceState
+    from cirq_b200.dist import ShardedStateVector
+    from cirq_b200.fusion import fuse_gates
+
+    rng = np.random.RandomState(7)
+
+    def unitary(k):
+        d = 1 << k
+        q, r = np.linalg.qr(rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d)))
+        return q * (np.diag(r) / np.abs(np.diag(r)))
+
+    ok = True
+    for dtype, atol in ((np.complex64, 1e-5), (np.complex128, 1e-12)):
+        for n in (12, 16, 20):
+            gates = []
+            for _ in range(80):
+                k = int(rng.randint(1, 4))
+                gates.append((unitary(k), rng.permutation(n)[:k].tolist()))
+            blocks = fuse_gates(gates, 4)
+            sv = ShardedStateVector(n, dtype, initial_index=5)
+            sv.apply_blocks(blocks)
+            got = sv.gather_state()
+            ref = DeviceState.basis(n, dtype, 5)
+            ref.apply_batch(blocks)
+            want = ref.to_numpy()
+            err = float(np.max(np.abs(got - want)))
+            nrm = sv.norm2()
+            samples = sv.sample(20000, seed=3)
+            # chi-squared of the top 4 logical qubits against the single-GPU probabilities
+            probs = np.abs(want.astype(np.complex128)) ** 2
+            ints = samples[:, :4].astype(np.int64) @ (1 << np.arange(3, -1, -1))
+            hist = np.bincount(ints, minlength=16)
+            expect = probs.reshape(16, -1).sum(axis=1) * len(samples)
+            chi2 = float(np.sum((hist - expect) ** 2 / np.maximum(expect, 1e-9)))
+            good = err <= atol and abs(nrm - 1) < 1e-4 and chi2 < 15 + 6 * np.sqrt(30) + 10
+            ok &= good
+            if rank == 0:
+                print(f'n={n} {np.dtype(dtype)} world={world}: max|diff|={err:.2e} norm={nrm:.6f} '
+                      f'swaps={sv.swaps} passes={sv.passes} chi2={chi2:.1f} {"OK" if good else "FAIL"}',
+                      flush=True)
+            sv.close()
+    # swap bandwidth at a large shard
+    n_local = int(os.environ.get('B2Q_SWAP_NLOCAL', '30'))
+    n = n_local + world.bit_length() - 1
+    sv = ShardedStateVector(n, np.complex64)
+    for lbit in (n_local - 1, n_local - 5, 8):
+        torch.cuda.synchronize()
+        dist.barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sv.swap_global_local(n_local, lbit)
+        s.record()
+        reps = 4
+        for _ in range(reps):
+            sv.swap_global_local(n_local, lbit)
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / reps
+        half = sv.local.nbytes / 2
+        if rank == 0:
+            print(f'swap global<->local bit {lbit}: {ms:.2f} ms, {half / ms / 1e6:.0f} GB/s per direction '
+                  f'(half shard {half / 1e9:.2f} GB)', flush=True)
+    sv.close()
+    if rank == 0:
+        print('DIST CHECK', 'PASSED' if ok else 'FAILED', flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
