@@ -85,6 +85,7 @@ SIGNATURES = {
 # Host-only helpers exported for unit tests (not part of the product ABI).
 DEBUG_SIGNATURES = {
     'b2q_set_lane_mode': (c_int, [c_int]),
+    'b2q_set_vec_mode': (c_int, [c_int]),
     'b2q_debug_plan': (c_int, [c_int, c_int, POINTER(c_int), c_int, POINTER(c_int)]),
     'b2q_debug_permute_matrix': (c_int, [c_void_p, POINTER(c_int), c_int, c_void_p]),
 }
@@ -109,6 +110,9 @@ def load():
     mode = os.environ.get('CIRQ_B200_LANE_MODE')
     if mode is not None:
         lib.b2q_set_lane_mode(int(mode))
+    mode = os.environ.get('CIRQ_B200_VEC_MODE')
+    if mode is not None:
+        lib.b2q_set_vec_mode(int(mode))
     _lib = lib
     return lib
 

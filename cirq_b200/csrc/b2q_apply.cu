@@ -85,6 +85,14 @@ __device__ __forceinline__ float4 ldg16(const float2* p) {
                : "l"(p));
   return v;
 }
+__device__ __forceinline__ float2 ldg_elem(const float2* p) {
+  float2 v;
+  asm volatile("ld.global.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_elem(float2* p, const float2& v) {
+  asm volatile("st.global.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
 __device__ __forceinline__ double2 ldg16(const double2* p) {
   double2 v;
   asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
@@ -98,6 +106,9 @@ __device__ __forceinline__ void stg16(float2* p, const float4& v) {
 __device__ __forceinline__ void stg16(double2* p, const double2& v) {
   asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
+
+__device__ __forceinline__ double2 ldg_elem(const double2* p) { return ldg16(p); }
+__device__ __forceinline__ void stg_elem(double2* p, const double2& v) { stg16(p, v); }
 
 template <typename C>
 __device__ __forceinline__ C shfl_xor_c(const C& v, int mask);
@@ -114,6 +125,21 @@ __device__ __forceinline__ double2 shfl_xor_c<double2>(const double2& v, int mas
   r.x = __shfl_xor_sync(0xffffffffu, v.x, mask);
   r.y = __shfl_xor_sync(0xffffffffu, v.y, mask);
   return r;
+}
+
+// acc[rr] = sum_c M[r0+rr][c] * xin(c), rr < RT: RT independent accumulator chains.
+template <typename real, typename C, int DIM, int RT, typename XF>
+__device__ __forceinline__ void rows_tile(const real* __restrict__ mat, int r0, C (&acc)[RT],
+                                          XF xin) {
+  constexpr int ME = MatEntry<real>::kReals;
+#pragma unroll
+  for (int rr = 0; rr < RT; ++rr) acc[rr] = make_c<real>(0, 0);
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) {
+    const C xv = xin(c);
+#pragma unroll
+    for (int rr = 0; rr < RT; ++rr) cmac_entry<real, C>(acc[rr], &mat[ME * ((r0 + rr) * DIM + c)], xv);
+  }
 }
 
 // Exchanges register bit RBIT with lane bit `lbit` across the warp: afterwards
@@ -158,11 +184,16 @@ __device__ __forceinline__ void swap_all(C (&x)[NR], const int* swap_lane, int l
 
 // Register index layout: [GT group bits][K target slots][S low group bit].
 // complex64: register bit 0 is always the 16-byte vector bit (index bit 0).
-template <typename real, int K, int S, int GT, bool SWAPS>
-__global__ void __launch_bounds__(kFastThreads)
+// VEC (complex64 only): lanes move 16 bytes = 2 amplitudes per access (vector
+// bit = index bit 0).  Without it every lane moves one amplitude (8 or 16 bytes):
+// half the registers per thread, twice the resident warps — used where the
+// arithmetic, not the memory system, limits the pass (k >= 4).
+template <typename real, int K, int S, int GT, bool SWAPS, bool VEC>
+__global__ void __launch_bounds__(kFastThreads, K == 4 ? (VEC ? 2 : 3) : 1)
     sv_apply_fast_kernel(const __grid_constant__ FastParams<real, K> p) {
   using C = typename Cplx<real>::type;
-  constexpr bool kVec = sizeof(real) == 4;
+  constexpr bool kVec = VEC;
+  static_assert(!VEC || sizeof(real) == 4, "16-byte vectors of 2 amplitudes are complex64 only");
   constexpr int RB = S + K + GT;
   constexpr int NR = 1 << RB;
   constexpr int DIM = 1 << K;
@@ -203,23 +234,25 @@ __global__ void __launch_bounds__(kFastThreads)
 #pragma unroll
       for (int b = 0; b < RB; ++b)
         if ((i >> b) & 1) off += p.reg_off[b];
-      x[i] = ldg16(ptr + off);
+      x[i] = ldg_elem(ptr + off);
     }
   }
 
   if constexpr (SWAPS) swap_all<K>(x, p.swap_lane, lane);
 
+  // Matrix-vector product in row tiles: RT independent accumulator chains per
+  // input stream keep the FMA pipe busy at 1-2 resident CTAs per SM.
+  constexpr int RT = DIM < 4 ? DIM : 4;
   if constexpr (SWAPS) {
     C y[NR];
 #pragma unroll
     for (int g = 0; g < (1 << GT); ++g) {
 #pragma unroll
-      for (int r = 0; r < DIM; ++r) {
-        C acc = make_c<real>(0, 0);
+      for (int r0 = 0; r0 < DIM; r0 += RT) {
+        C acc[RT];
+        rows_tile<real, C, DIM, RT>(p.mat, r0, acc, [&](int c) { return x[(g << K) | c]; });
 #pragma unroll
-        for (int c = 0; c < DIM; ++c)
-          cmac_entry<real, C>(acc, &p.mat[ME * (r * DIM + c)], x[(g << K) | c]);
-        y[(g << K) | r] = acc;
+        for (int rr = 0; rr < RT; ++rr) y[(g << K) | (r0 + rr)] = acc[rr];
       }
     }
     swap_all<K>(y, p.swap_lane, lane);
@@ -239,65 +272,66 @@ __global__ void __launch_bounds__(kFastThreads)
 #pragma unroll
         for (int b = 0; b < RB; ++b)
           if ((i >> b) & 1) off += p.reg_off[b];
-        stg16(ptr + off, y[i]);
+        stg_elem(ptr + off, y[i]);
       }
     }
   } else if constexpr (kVec && S == 1) {
-    // Vector bit is a group bit: rows r for both halves form one 16-byte store.
+    // Vector bit is a group bit: row r of both halves forms one 16-byte store.
 #pragma unroll
     for (int g = 0; g < (1 << GT); ++g) {
 #pragma unroll
-      for (int r = 0; r < DIM; ++r) {
-        C a0 = make_c<real>(0, 0), a1 = make_c<real>(0, 0);
+      for (int r0 = 0; r0 < DIM; r0 += RT) {
+        C a0[RT], a1[RT];
+        rows_tile<real, C, DIM, RT>(p.mat, r0, a0, [&](int c) { return x[((g << K) | c) << 1]; });
+        rows_tile<real, C, DIM, RT>(p.mat, r0, a1,
+                                    [&](int c) { return x[(((g << K) | c) << 1) | 1]; });
 #pragma unroll
-        for (int c = 0; c < DIM; ++c) {
-          cmac_entry<real, C>(a0, &p.mat[ME * (r * DIM + c)], x[(((g << K) | c) << 1)]);
-          cmac_entry<real, C>(a1, &p.mat[ME * (r * DIM + c)], x[(((g << K) | c) << 1) | 1]);
+        for (int rr = 0; rr < RT; ++rr) {
+          const int i = (g << K) | (r0 + rr);  // index over register bits 1..RB-1
+          long long off = 0;
+#pragma unroll
+          for (int b = 0; b < RB - 1; ++b)
+            if ((i >> b) & 1) off += p.reg_off[b + 1];
+          stg16(ptr + off, make_float4(a0[rr].x, a0[rr].y, a1[rr].x, a1[rr].y));
         }
-        const int i = (g << K) | r;  // index over register bits 1..RB-1
-        long long off = 0;
-#pragma unroll
-        for (int b = 0; b < RB - 1; ++b)
-          if ((i >> b) & 1) off += p.reg_off[b + 1];
-        stg16(ptr + off, make_float4(a0.x, a0.y, a1.x, a1.y));
       }
     }
   } else if constexpr (kVec) {
     // S == 0, vector bit is target slot 0: rows (2i, 2i+1) form one store.
+    constexpr int RT2 = 2;
 #pragma unroll
     for (int g = 0; g < (1 << GT); ++g) {
 #pragma unroll
-      for (int r2 = 0; r2 < DIM / 2; ++r2) {
-        C a0 = make_c<real>(0, 0), a1 = make_c<real>(0, 0);
+      for (int r0 = 0; r0 < DIM; r0 += RT2) {
+        C acc[RT2];
+        rows_tile<real, C, DIM, RT2>(p.mat, r0, acc, [&](int c) { return x[(g << K) | c]; });
 #pragma unroll
-        for (int c = 0; c < DIM; ++c) {
-          const C xv = x[(g << K) | c];
-          cmac_entry<real, C>(a0, &p.mat[ME * ((2 * r2) * DIM + c)], xv);
-          cmac_entry<real, C>(a1, &p.mat[ME * ((2 * r2 + 1) * DIM + c)], xv);
+        for (int rr = 0; rr < RT2; rr += 2) {
+          const int i = (g << (K - 1)) | ((r0 + rr) >> 1);  // register bits 1..RB-1
+          long long off = 0;
+#pragma unroll
+          for (int b = 0; b < RB - 1; ++b)
+            if ((i >> b) & 1) off += p.reg_off[b + 1];
+          stg16(ptr + off, make_float4(acc[rr].x, acc[rr].y, acc[rr + 1].x, acc[rr + 1].y));
         }
-        const int i = (g << (K - 1)) | r2;  // index over register bits 1..RB-1
-        long long off = 0;
-#pragma unroll
-        for (int b = 0; b < RB - 1; ++b)
-          if ((i >> b) & 1) off += p.reg_off[b + 1];
-        stg16(ptr + off, make_float4(a0.x, a0.y, a1.x, a1.y));
       }
     }
   } else {
 #pragma unroll
     for (int g = 0; g < (1 << GT); ++g) {
 #pragma unroll
-      for (int r = 0; r < DIM; ++r) {
-        C acc = make_c<real>(0, 0);
+      for (int r0 = 0; r0 < DIM; r0 += RT) {
+        C acc[RT];
+        rows_tile<real, C, DIM, RT>(p.mat, r0, acc, [&](int c) { return x[(g << K) | c]; });
 #pragma unroll
-        for (int c = 0; c < DIM; ++c)
-          cmac_entry<real, C>(acc, &p.mat[ME * (r * DIM + c)], x[(g << K) | c]);
-        const int i = (g << K) | r;
-        long long off = 0;
+        for (int rr = 0; rr < RT; ++rr) {
+          const int i = (g << K) | (r0 + rr);
+          long long off = 0;
 #pragma unroll
-        for (int b = 0; b < RB; ++b)
-          if ((i >> b) & 1) off += p.reg_off[b];
-        stg16(ptr + off, acc);
+          for (int b = 0; b < RB; ++b)
+            if ((i >> b) & 1) off += p.reg_off[b];
+          stg_elem(ptr + off, acc[rr]);
+        }
       }
     }
   }
@@ -402,6 +436,7 @@ struct FastPlan {
   bool feasible = false;
   int K = 0, S = 0, GT = 0;
   bool swaps = false;
+  bool vec = false;
   uint64_t num_items = 0;
   int n_ins = 0;
   int ins_pos[kMaxIns] = {0};
@@ -422,6 +457,11 @@ struct FastPlan {
 // g_lane_mode: 0 = always shuffle, 1 = always remap, 2 = per-target policy
 // fitted to the B200 measurements in profiles/microbench_r1.md (default).
 std::atomic<int> g_lane_mode{2};
+// complex64 access width: 0 = policy (16-byte vectors, except k >= 4 blocks that
+// need lane shuffles: those move one amplitude per lane, halving the registers
+// that take part in the exchange), 1 = always 16-byte vectors, 2 = never.
+std::atomic<int> g_vec_mode{0};
+
 
 static bool remap_target(int mode, bool vec, int K, int t, bool both_low) {
   if (mode == 0) return false;
@@ -437,13 +477,28 @@ static bool remap_target(int mode, bool vec, int K, int t, bool both_low) {
   return t >= 3;
 }
 
+static FastPlan make_fast_plan_width(int dtype, int n, const int* sorted, int K, bool vec);
+
 FastPlan make_fast_plan(int dtype, int n, const int* sorted, int K) {
+  if (dtype != B2Q_C64) return make_fast_plan_width(dtype, n, sorted, K, false);
+  const int m = g_vec_mode.load(std::memory_order_relaxed);
+  if (m == 1) return make_fast_plan_width(dtype, n, sorted, K, true);
+  if (m == 2) return make_fast_plan_width(dtype, n, sorted, K, false);
+  FastPlan pl = make_fast_plan_width(dtype, n, sorted, K, true);
+  if (K >= 4 && pl.feasible && pl.swaps) {
+    const FastPlan narrow = make_fast_plan_width(dtype, n, sorted, K, false);
+    if (narrow.feasible) return narrow;
+  }
+  return pl;
+}
+
+static FastPlan make_fast_plan_width(int dtype, int n, const int* sorted, int K, bool vec) {
   FastPlan pl;
   pl.K = K;
-  const bool vec = dtype == B2Q_C64;
+  pl.vec = vec;
   const int ZB = vec ? 6 : 5;
   const int VB = vec ? 1 : 0;
-  const int max_k = vec ? 5 : 4;
+  const int max_k = dtype == B2Q_C64 ? 5 : 4;
   if (K < 1 || K > max_k) return pl;
   const bool vec_is_target = vec && sorted[0] == 0;
   const int mode = g_lane_mode.load(std::memory_order_relaxed);
@@ -456,7 +511,7 @@ FastPlan make_fast_plan(int dtype, int n, const int* sorted, int K) {
   int n_lane = 0;  // lane targets handled by shuffles
   for (int i = 0; i < K; ++i) {
     const bool lane_t = sorted[i] >= VB && sorted[i] < ZB;
-    remap[i] = lane_t && remap_target(mode, vec, K, sorted[i], has1 && has2);
+    remap[i] = lane_t && remap_target(mode, dtype == B2Q_C64, K, sorted[i], has1 && has2);
     if (lane_t && !remap[i]) ++n_lane;
   }
   // complex64, S=0 layout: register bit 0 is physically the vector bit, so target
@@ -565,7 +620,7 @@ void permute_matrix(const double* m128, const int* targets, const int* sorted, i
     }
 }
 
-template <typename real, int K, int S, int GT, bool SWAPS>
+template <typename real, int K, int S, int GT, bool SWAPS, bool VEC>
 int launch_fast(void* state, const FastPlan& pl, const real* mat, cudaStream_t stream) {
   FastParams<real, K> p;
   p.state = reinterpret_cast<typename Cplx<real>::type*>(state);
@@ -580,7 +635,7 @@ int launch_fast(void* state, const FastPlan& pl, const real* mat, cudaStream_t s
   const uint64_t warps_per_block = kFastThreads / 32;
   const uint64_t blocks = (pl.num_items + warps_per_block - 1) / warps_per_block;
   if (blocks > 0x7fffffffull) return set_error(B2Q_ERR_UNSUPPORTED, "grid too large");
-  sv_apply_fast_kernel<real, K, S, GT, SWAPS>
+  sv_apply_fast_kernel<real, K, S, GT, SWAPS, VEC>
       <<<(unsigned)blocks, kFastThreads, 0, stream>>>(p);
   B2Q_LAUNCH_CHECK("sv_apply_fast_kernel");
   return B2Q_OK;
@@ -588,14 +643,17 @@ int launch_fast(void* state, const FastPlan& pl, const real* mat, cudaStream_t s
 
 template <typename real, int K>
 int dispatch_fast_k(void* state, const FastPlan& pl, const real* mat, cudaStream_t stream) {
-  constexpr bool vec = sizeof(real) == 4;
   constexpr int GT1 = (2 - K) > 0 ? (2 - K) : 0;
   constexpr int GT0 = (3 - K) > 0 ? (3 - K) : 0;
-  if constexpr (vec) {
-    if (pl.S == 1) return launch_fast<real, K, 1, GT1, false>(state, pl, mat, stream);
+  if constexpr (sizeof(real) == 4) {
+    if (pl.vec) {
+      if (pl.S == 1) return launch_fast<real, K, 1, GT1, false, true>(state, pl, mat, stream);
+      if (pl.swaps) return launch_fast<real, K, 0, GT0, true, true>(state, pl, mat, stream);
+      return launch_fast<real, K, 0, GT0, false, true>(state, pl, mat, stream);
+    }
   }
-  if (pl.swaps) return launch_fast<real, K, 0, GT0, true>(state, pl, mat, stream);
-  return launch_fast<real, K, 0, GT0, false>(state, pl, mat, stream);
+  if (pl.swaps) return launch_fast<real, K, 0, GT0, true, false>(state, pl, mat, stream);
+  return launch_fast<real, K, 0, GT0, false, false>(state, pl, mat, stream);
 }
 
 template <typename real, int K>
@@ -758,8 +816,14 @@ extern "C" int b2q_sv_apply_diagonal(void* state, int dtype, int n_qubits,
   return B2Q_OK;
 }
 
+extern "C" int b2q_set_vec_mode(int mode) {
+  B2Q_REQUIRE(mode >= 0 && mode <= 2, "vec mode must be 0, 1 or 2");
+  g_vec_mode.store(mode, std::memory_order_relaxed);
+  return B2Q_OK;
+}
+
 extern "C" int b2q_set_lane_mode(int mode) {
-  B2Q_REQUIRE(mode == 0 || mode == 1, "lane mode must be 0 or 1");
+  B2Q_REQUIRE(mode >= 0 && mode <= 2, "lane mode must be 0, 1 or 2");
   g_lane_mode.store(mode, std::memory_order_relaxed);
   return B2Q_OK;
 }
@@ -775,7 +839,7 @@ extern "C" int b2q_debug_plan(int dtype, int n_qubits, const int* targets, int k
   out[0] = pl.feasible;
   out[1] = pl.S;
   out[2] = pl.GT;
-  out[3] = pl.swaps;
+  out[3] = (pl.swaps ? 1 : 0) | (pl.vec ? 2 : 0);
   out[4] = pl.n_ins;
   for (int i = 0; i < 6; ++i) out[5 + i] = pl.ins_pos[i];
   for (int i = 0; i < 6; ++i) {

@@ -718,9 +718,10 @@ extern "C" int b2q_sv_gather(const void* state, int dtype, int n_qubits, const u
   for (uint64_t j = 0; j < count; ++j)
     B2Q_REQUIRE(indices[j] < total, "index %llu out of range", (unsigned long long)indices[j]);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  uint64_t* didx = reinterpret_cast<uint64_t*>(workspace((sizeof(uint64_t) + sizeof(double2)) * count));
-  if (didx == nullptr) return B2Q_ERR_CUDA;
-  double2* dout = reinterpret_cast<double2*>(didx + count);
+  // 16-byte aligned results first, then the indices
+  double2* dout = reinterpret_cast<double2*>(workspace((sizeof(uint64_t) + sizeof(double2)) * count));
+  if (dout == nullptr) return B2Q_ERR_CUDA;
+  uint64_t* didx = reinterpret_cast<uint64_t*>(dout + count);
   B2Q_CUDA_CHECK(
       cudaMemcpyAsync(didx, indices, sizeof(uint64_t) * count, cudaMemcpyHostToDevice, s));
   const unsigned blocks = (unsigned)((count + 255) / 256);

@@ -1,0 +1,59 @@
+"""Runs the REFERENCE's own simulator test files against the B200 drop-in
+classes: `cirq.Simulator` / `cirq.DensityMatrixSimulator` are replaced by
+`B200Simulator` / `B200DensityMatrixSimulator` before the reference test module
+is imported (SURVEY.md §8c "reuse plan").
+
+    python tests/ref_suite_runner.py {oracle|cuda} {sparse|density} out.json
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+import pytest  # noqa: E402
+
+
+class Collector:
+    def __init__(self):
+        self.outcomes = {}
+
+    def pytest_runtest_logreport(self, report):
+        if report.when == 'call' or (report.when == 'setup' and report.outcome != 'passed'):
+            self.outcomes[report.nodeid.split('::', 1)[1]] = report.outcome
+
+
+def main():
+    backend, which, out = sys.argv[1:4]
+    from cirq_b200._cirq_compat import import_cirq
+
+    cirq = import_cirq()
+    import cirq_b200.dm_simulator as dmm
+    import cirq_b200.sv_simulator as svm
+
+    if backend == 'oracle':
+        from fake_device import OracleDeviceState
+
+        svm.DeviceState = OracleDeviceState
+        dmm.DeviceState = OracleDeviceState
+    cirq.Simulator = svm.B200Simulator
+    cirq.DensityMatrixSimulator = dmm.B200DensityMatrixSimulator
+    import cirq.sim as cs
+
+    cs.Simulator = svm.B200Simulator
+    cs.DensityMatrixSimulator = dmm.B200DensityMatrixSimulator
+    ref_dir = os.path.join(os.path.dirname(cirq.__file__), 'sim')
+    target = os.path.join(
+        ref_dir, 'sparse_simulator_test.py' if which == 'sparse' else 'density_matrix_simulator_test.py'
+    )
+    col = Collector()
+    pytest.main([target, '-q', '-x' if False else '-q', '-p', 'no:cacheprovider', '-c', os.devnull,
+                 '--rootdir', ref_dir, '-W', 'ignore'], plugins=[col])
+    with open(out, 'w') as f:
+        json.dump(col.outcomes, f, indent=0)
+
+
+if __name__ == '__main__':
+    main()

@@ -22,7 +22,7 @@ def get_plan(dtype_code, n, targets):
     lib.b2q_debug_plan(dtype_code, n, _lib.int_array(targets), len(targets), out)
     o = list(out)
     return dict(
-        feasible=bool(o[0]), S=o[1], GT=o[2], swaps=bool(o[3]), n_ins=o[4],
+        feasible=bool(o[0]), S=o[1], GT=o[2], swaps=bool(o[3] & 1), vec=bool(o[3] & 2), n_ins=o[4],
         ins_pos=o[5:5 + o[4]], reg_off_log2=o[11:17], swap_lane=o[17:23], log2_items=o[23],
     )
 
@@ -48,7 +48,8 @@ def emulate_fast_kernel(state, n, matrix, targets, dtype_code):
     k = len(targets)
     pl = get_plan(dtype_code, n, targets)
     assert pl['feasible']
-    vec = dtype_code == 0
+    vec = pl['vec']
+    assert not (vec and dtype_code != 0)
     zb = 6 if vec else 5
     S, GT = pl['S'], pl['GT']
     rb = S + k + GT
@@ -172,6 +173,26 @@ def remap_mode():
     lib.b2q_set_lane_mode(2)
 
 
+@pytest.fixture(params=[1, 2])
+def vec_mode(request):
+    lib = _lib.load()
+    lib.b2q_set_vec_mode(request.param)
+    yield request.param
+    lib.b2q_set_vec_mode(0)
+
+
+@pytest.mark.parametrize('targets', [[9], [0], [3], [0, 9], [1, 4], [0, 1, 2], [3, 9, 1], [6, 7, 8, 9], [0, 1, 8, 9], [1, 2, 3, 4], [5, 0, 9, 3], [1, 2, 3, 4, 5], [0, 6, 7, 8, 12]])
+def test_emulated_kernel_both_access_widths_c64(targets, vec_mode):
+    n = 13
+    rng = np.random.RandomState(hash(tuple(targets)) % (1 << 31))
+    k = len(targets)
+    assert get_plan(0, n, targets)['vec'] == (vec_mode == 1)
+    state = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    matrix = rng.standard_normal((1 << k, 1 << k)) + 1j * rng.standard_normal((1 << k, 1 << k))
+    got = emulate_fast_kernel(state, n, matrix, targets, 0)
+    np.testing.assert_allclose(got, orc.apply_matrix(state, n, matrix, targets), atol=1e-11)
+
+
 @pytest.fixture
 def shuffle_mode():
     lib = _lib.load()
@@ -239,14 +260,15 @@ def test_emulated_kernel_remap_mode_c128(targets, remap_mode):
 
 
 def test_plan_covers_every_amplitude_exactly_once():
-    for dtype_code, zb in ((0, 6), (1, 5)):
+    for dtype_code in (0, 1):
         for targets in ([3, 20], [0, 1, 2], [25, 26, 27, 28], [7]):
             pl = get_plan(dtype_code, 30, targets)
             assert pl['feasible']
+            zb = 6 if pl['vec'] else 5
             rb = pl['S'] + len(targets) + pl['GT']
             assert pl['log2_items'] + zb + pl['n_ins'] == 30
             # register-resident bits are distinct and never the vector bit
-            assert len(set(pl['ins_pos'])) == pl['n_ins'] and min(pl['ins_pos']) >= (1 if dtype_code == 0 else 0)
+            assert len(set(pl['ins_pos'])) == pl['n_ins'] and min(pl['ins_pos']) >= (1 if pl['vec'] else 0)
             assert pl['n_ins'] == sum(1 for l in pl['reg_off_log2'][:rb] if l >= 0)
 
 

@@ -1,0 +1,78 @@
+"""The reference's OWN simulator test files, run against the drop-in classes
+(cirq.Simulator -> B200Simulator, cirq.DensityMatrixSimulator ->
+B200DensityMatrixSimulator): cirq-core/cirq/sim/sparse_simulator_test.py and
+density_matrix_simulator_test.py.
+
+Every reference test must pass except the documented exclusions:
+  * qudits (dimension != 2): the kernels are qubit-only;
+  * split_untangled_states representation tests (one dense tensor here);
+  * tests whose ad-hoc gates mutate the numpy state tensor inside
+    `_apply_unitary_` (the matrix is obtained from Cirq's query protocols and
+    applied on the device instead).
+Note that the reference's seed-literal tests (`test_random_seed_*`) PASS: the
+sampler consumes the same MT19937 stream as numpy's `choice`."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+EXPECTED_FAIL_PREFIXES = {
+    'sparse': [
+        'test_run_reset',  # LineQid(dimension=3)
+        'test_simulate_qudits', 'test_simulate_qudit_mixtures', 'test_qudit_invert_mask',
+        'test_pure_state_creation', 'test_separated_states_str_does_not_merge',
+        'test_does_not_modify_initial_state', 'test_state_vector_copy',
+    ],
+    'density': [
+        'test_run_qudit_increments', 'test_run_qudit_mixture', 'test_run_qudit_channel',
+        'test_run_qudits_repetitions_measure_at_end',
+        'test_run_qudits_repetitions_measurement_not_terminal',
+        'test_run_measure_multiple_qudits', 'test_simulate_qudits',
+        'test_simulate_qudit_increments', 'test_simulate_initial_qudit_state',
+        'test_simulate_measure_multiple_qudits', 'test_simulate_moment_steps_qudits',
+        'test_simulate_moment_steps_sample_qudits', 'test_simulate_with_invert_mask',
+        'test_density_matrix_copy', 'test_large_untangled_okay',
+        'test_separated_states_str_does_not_merge',
+    ],
+}
+MIN_PASSED = {'sparse': 175, 'density': 198}
+
+
+def run_suite(backend, which, tmp_path):
+    from cirq_b200._cirq_compat import cirq_available
+
+    if not cirq_available():
+        pytest.skip('cirq is not importable here')
+    out = os.path.join(str(tmp_path), f'{backend}_{which}.json')
+    proc = subprocess.run(
+        [sys.executable, os.path.join(ROOT, 'tests', 'ref_suite_runner.py'), backend, which, out],
+        capture_output=True, text=True, timeout=3000,
+    )
+    assert os.path.exists(out), proc.stdout[-3000:] + proc.stderr[-3000:]
+    with open(out) as f:
+        outcomes = json.load(f)
+    failed = sorted(k for k, v in outcomes.items() if v != 'passed')
+    unexpected = [
+        k for k in failed
+        if k.split('[')[0] not in EXPECTED_FAIL_PREFIXES[which]
+    ]
+    passed = sum(1 for v in outcomes.values() if v == 'passed')
+    assert not unexpected, f'unexpected reference-test failures: {unexpected}'
+    assert passed >= MIN_PASSED[which], f'only {passed} reference tests passed'
+
+
+@pytest.mark.parametrize('which', ['sparse', 'density'])
+def test_reference_suite_host_logic(which, tmp_path):
+    """Oracle-backed device: checks the drop-in host layer on a CPU-only box."""
+    run_suite('oracle', which, tmp_path)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('which', ['sparse', 'density'])
+def test_reference_suite_cuda(which, tmp_path):
+    """The same reference tests through the real CUDA path."""
+    run_suite('cuda', which, tmp_path)

@@ -43,8 +43,13 @@ def main():
     ap.add_argument('--reps', type=int, default=10)
     ap.add_argument('--out', default='')
     ap.add_argument('--lane-mode', type=int, default=None)
+    ap.add_argument('--only', default='')
+    ap.add_argument('--vec-mode', type=int, default=None)
     args = ap.parse_args()
     dtype = np.complex64 if args.dtype == 'c64' else np.complex128
+    if args.vec_mode is not None:
+        from cirq_b200 import _lib
+        _lib.load().b2q_set_vec_mode(args.vec_mode)
     if args.lane_mode is not None:
         from cirq_b200 import _lib
         _lib.load().b2q_set_lane_mode(args.lane_mode)
@@ -71,6 +76,8 @@ def main():
             'k5_lanes': [1, 2, 3, 4, 5],
         })
     results = {}
+    if args.only:
+        classes = {k: v for k, v in classes.items() if any(k.startswith(p) for p in args.only.split(','))}
     for name, bits in classes.items():
         m = rand_unitary(rng, len(bits))
         ms = time_pass(dev, m, bits, args.reps)
@@ -100,6 +107,7 @@ def main():
     ms = s.elapsed_time(e) / args.reps
     results['scale_inplace'] = {'ms': ms, 'GBps': bytes_per_pass / ms / 1e6}
     print(f'scale_inplace {ms:8.3f} ms {bytes_per_pass / ms / 1e6:8.1f} GB/s')
+    dev.norm2()  # first call loads the kernel (CUDA lazy module loading)
     s.record()
     nrm = dev.norm2()
     e.record()
