@@ -219,10 +219,10 @@ def run_b200_arm(args):
 
     import ctypes
 
-    ws_bytes = int(lib.b2q_sv_sample_workspace_bytes(n, reps))
+    ws_bytes = int(lib.b2q_sv_sample_workspace_bytes(n, reps)) if reps else 16
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device='cuda')
     out_idx = torch.empty(max(reps, 1), dtype=torch.int64, device='cuda')
-    out_bits = torch.empty((max(reps, 1), n), dtype=torch.uint8, device='cuda')
+    out_bits = torch.empty((max(reps, 1), n if reps else 1), dtype=torch.uint8, device='cuda')
     bits_order = _lib.int_array(list(range(n - 1, -1, -1)))
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]

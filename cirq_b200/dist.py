@@ -148,6 +148,22 @@ class ShardBackend:
         self.dist.all_gather_object(out, obj, group=self.group)
         return out
 
+    def merge_samples(self, reps: int, positions: np.ndarray, local_uniforms: np.ndarray,
+                      bits: Sequence[int]) -> np.ndarray:
+        """Resolves this rank's samples on the device, merges the physical
+        indices of all ranks with one all-reduce (disjoint positions) and
+        extracts the requested physical bits: uint8[reps, len(bits)]."""
+        from cirq_b200.device_state import DeviceState
+
+        torch = self.torch
+        full = torch.zeros(max(reps, 1), dtype=torch.int64, device='cuda')
+        if positions.size:
+            idx = self.local.sample_indices_device(local_uniforms)
+            idx = idx | (self.rank << self.n_local)
+            full[torch.from_numpy(positions).to('cuda')] = idx
+        self.dist.all_reduce(full, group=self.group)
+        return DeviceState.unpack_bits_device(full[:reps], bits).cpu().numpy()
+
     def close(self):
         self.barrier()
         for p in self.peer_ptrs.values():
@@ -241,6 +257,7 @@ class ShardedStateVector:
         blocks so that everything executable without communication runs before
         the next qubit swap."""
         remaining = [(np.asarray(m), tuple(int(w) for w in ws)) for m, ws in blocks]
+        self._diag_cache = {}
         while remaining:
             progressed = True
             while progressed and remaining:
@@ -282,7 +299,10 @@ class ShardedStateVector:
         if not glob:
             self.local_only_blocks += 1
             return m, pw
-        subs = block_diagonal_in(m, pw, glob, atol=1e-24)
+        key = (id(m), tuple(pw))
+        if key not in self._diag_cache:
+            self._diag_cache[key] = block_diagonal_in(m, pw, glob, atol=1e-24)
+        subs = self._diag_cache[key]
         if subs is None:
             return None
         self.diag_global_blocks += 1
@@ -336,20 +356,9 @@ class ShardedStateVector:
         mine = np.nonzero(owner == self.rank)[0]
         before = cum[self.rank] - totals[self.rank]
         local_u = np.clip((target[mine] - before) / max(totals[self.rank], 1e-300), 0.0, 1.0 - 2**-53)
-        if mine.size:
-            local_idx = np.asarray(self.local.sample_indices(local_u), dtype=np.uint64)
-        else:
-            local_idx = np.zeros(0, dtype=np.uint64)
-        phys_idx = local_idx | (np.uint64(self.rank) << np.uint64(self.n_local))
-        parts = self.backend.gather_objects((mine, phys_idx))
-        full = np.zeros(repetitions, dtype=np.uint64)
-        for pos, idx in parts:
-            full[pos] = idx
-        out = np.zeros((repetitions, self.n), dtype=np.uint8)
-        for axis in range(self.n):
-            logical_bit = self.n - 1 - axis
-            out[:, axis] = (full >> np.uint64(self.phys[logical_bit])) & np.uint64(1)
-        return out
+        # column `axis` of the result is logical bit n-1-axis = physical bit phys[...]
+        bits = [self.phys[self.n - 1 - axis] for axis in range(self.n)]
+        return self.backend.merge_samples(repetitions, mine, local_u, bits)
 
     def gather_state(self) -> np.ndarray:
         """Full state in LOGICAL order on every rank (tests / small n only)."""

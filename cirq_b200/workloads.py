@@ -120,3 +120,39 @@ def builtin_rqc_gates(rows: int, cols: int, depth: int, seed: int = 1):
                 if not vertical and c + 1 < cols and (r + c) % 2 == parity:
                     gates.append((fsim, [bit(r, c), bit(r, c + 1)]))
     return gates
+
+
+def qaoa_circuit(n: int = 16, p: int = 2, graph_seed: int = 0):
+    """Parameterised max-cut QAOA (config 5): examples/qaoa.py:128-158
+    ``qaoa_max_cut_circuit`` on a random 3-regular graph, symbols beta{i}, gamma{i}.
+    Returns (circuit, qubits, symbol names)."""
+    import networkx
+    import sympy
+
+    from cirq_b200._cirq_compat import import_cirq
+
+    cirq = import_cirq()
+    qubits = cirq.LineQubit.range(n)
+    graph = networkx.random_regular_graph(3, n, seed=graph_seed)
+    betas = [sympy.Symbol(f'beta{i}') for i in range(p)]
+    gammas = [sympy.Symbol(f'gamma{i}') for i in range(p)]
+
+    def rzz(rads):
+        return cirq.ZZPowGate(exponent=2 * rads / sympy.pi, global_shift=-0.5)
+
+    ops = [cirq.H.on_each(*qubits)]
+    for beta, gamma in zip(betas, gammas):
+        ops.append([rzz(-0.5 * gamma).on(qubits[i], qubits[j]) for i, j in graph.edges])
+        ops.append(cirq.rx(2 * beta).on_each(*qubits))
+    ops.append(cirq.measure(*qubits, key='m'))
+    names = [s.name for s in betas + gammas]
+    return cirq.Circuit(ops), qubits, names
+
+
+def qaoa_sweep(names, points: int = 256):
+    """`points` resolvers zipping a Linspace per symbol (config 5's run_sweep)."""
+    from cirq_b200._cirq_compat import import_cirq
+
+    cirq = import_cirq()
+    return cirq.Zip(*[cirq.Linspace(name, 0.1 + 0.05 * i, 1.1 + 0.05 * i, points)
+                      for i, name in enumerate(names)])

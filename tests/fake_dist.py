@@ -54,3 +54,16 @@ class GlooShardBackend:
         out = [None] * self.world
         dist.all_gather_object(out, obj)
         return out
+
+    def merge_samples(self, reps, positions, local_uniforms, bits):
+        from oracle import sv_oracle as orc
+
+        if positions.size:
+            idx = np.asarray(self.local.sample_indices(local_uniforms), dtype=np.int64)
+            idx = idx | (self.rank << self.n_local)
+        else:
+            idx = np.zeros(0, dtype=np.int64)
+        full = torch.zeros(max(reps, 1), dtype=torch.int64)
+        full[torch.from_numpy(positions)] = torch.from_numpy(idx)
+        dist.all_reduce(full)
+        return orc.unpack_bits(full[:reps].numpy().astype(np.uint64), list(bits))
