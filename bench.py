@@ -59,6 +59,16 @@ def load_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def measured_traffic(n_qubits):
+    """dram read+write bytes per launch of the dominant kernel from the committed
+    ncu --set full capture (profiles/), valid for the 30-qubit workload only."""
+    path = os.path.join(ROOT, 'profiles', 'r1f_ncu_apply_summary.json')
+    if n_qubits != 30 or not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return int(json.load(f)['dominant_traffic_bytes_per_launch'])
+
+
 def build_workload(name):
     """Returns dict(circuit, qubits, gates, n, reps, generator)."""
     from cirq_b200 import workloads as W
@@ -330,7 +340,7 @@ def run_b200_arm(args):
                    'l2': 'inputs larger than L2 (state %.1f GB vs 126 MB)' % (state_bytes / 1e9)
                          if state_bytes > 252e6 else 'state fits L2; not an HBM measurement'},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak_gbs, 'unit': 'GB/s',
-                     'frac': achieved / peak_gbs, 'traffic': None, 'kernel': 'sv_apply_fast_kernel',
+                     'frac': achieved / peak_gbs, 'traffic': measured_traffic(n), 'kernel': 'sv_apply_fast_kernel',
                      'peak_source': peak_src, 'bytes_per_launch': 2 * state_bytes,
                      'ms_per_launch': pass_ms},
         'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks.summary(),
