@@ -86,6 +86,7 @@ SIGNATURES = {
 DEBUG_SIGNATURES = {
     'b2q_set_lane_mode': (c_int, [c_int]),
     'b2q_set_vec_mode': (c_int, [c_int]),
+    'b2q_set_tc_mode': (c_int, [c_int]),
     'b2q_debug_plan': (c_int, [c_int, c_int, POINTER(c_int), c_int, POINTER(c_int)]),
     'b2q_debug_permute_matrix': (c_int, [c_void_p, POINTER(c_int), c_int, c_void_p]),
 }
@@ -110,6 +111,9 @@ def load():
     mode = os.environ.get('CIRQ_B200_LANE_MODE')
     if mode is not None:
         lib.b2q_set_lane_mode(int(mode))
+    mode = os.environ.get('CIRQ_B200_TC_MODE')
+    if mode is not None:
+        lib.b2q_set_tc_mode(int(mode))
     mode = os.environ.get('CIRQ_B200_VEC_MODE')
     if mode is not None:
         lib.b2q_set_vec_mode(int(mode))

@@ -1,0 +1,321 @@
+// 5-qubit fused blocks on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// A dense k-qubit block costs 4 * 2^k real FMAs per amplitude; at k = 5 that
+// is 128, past the FP32 CUDA-core roofline of a B200, so the
+// register kernel of b2q_apply.cu runs at ~0.25 of the HBM roofline.  Here the
+// multiply runs on tcgen05.mma instead while the pass stays one in-place
+// streaming sweep over HBM:
+//
+//   * one CTA = 128 threads = 128 amplitude groups = the M dimension of one
+//     UMMA tile; thread t owns group t (32 amplitudes = 64 reals, loaded with
+//     8-byte accesses that are contiguous across the warp),
+//   * the complex product is embedded in a real GEMM:  D[128 x 64] =
+//     A[128 x 64] * B^T, A row = (re0, im0, re1, im1, ...), B built on the host
+//     from the gate matrix ([[Mr, -Mi], [Mi, Mr]] interleaved),
+//   * fp32 accuracy on TF32 tensor cores by the 3xTF32 split: a = a_hi + a_lo,
+//     b = b_hi + b_lo, D = a_hi b_hi + a_lo b_hi + a_hi b_lo (fp32 accumulate in
+//     TMEM); the dropped a_lo b_lo term is ~2^-22 relative,
+//   * A never touches shared memory: each thread writes its row (hi and lo)
+//     straight from registers into TMEM (tcgen05.st), B (hi, lo; 32 KB) sits in
+//     shared memory in the UMMA K-major canonical layout for the whole life of
+//     the persistent CTA, D comes back with tcgen05.ld and is stored in place.
+//
+// Replaces the same reference call sites as b2q_apply.cu
+// (linalg/transformations.py:105-172 for 5-qubit matrices).
+#include "b2q_common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace b2q {
+
+constexpr int kTcThreads = 128;
+constexpr int kTcK = 5;                 // qubits per block
+constexpr int kTcDim = 1 << kTcK;       // 32 complex
+constexpr int kTcN = 2 * kTcDim;        // 64 reals: N and K of the real GEMM
+constexpr int kTcCols = 256;            // TMEM columns: A_hi 64 | A_lo 64 | D 64 | spare 64
+
+struct TcParams {
+  float2* state;
+  uint64_t num_tiles;  // groups / 128
+  int tpos[kTcK];      // ascending target positions
+  const float* bmat;   // device: B_hi then B_lo, UMMA K-major no-swizzle layout
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, "
+      "%12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
+        "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),
+        "r"(v[15])
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, "
+      "%12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, no swizzle (version 1 = Blackwell):
+// [0,14) start>>4, [16,30) leading byte offset>>4 (between the two 16-byte K
+// chunks of one MMA), [32,46) stride byte offset>>4 (between 8-row groups).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+  d |= (uint64_t)((lbo >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fffu) << 32;
+  d |= 1ull << 46;
+  return d;
+}
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}\n"
+      :
+      : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u),
+        "r"(0u), "r"(0u)
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kTcThreads, 2)
+    sv_apply_tc5_kernel(const __grid_constant__ TcParams p) {
+  __shared__ __align__(128) float sB[2][kTcN * kTcN];  // hi, lo (16 KB each)
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_s)),
+                 "r"((uint32_t)kTcCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.bmat);
+    float4* dst = reinterpret_cast<float4*>(&sB[0][0]);
+    for (int i = tid; i < 2 * kTcN * kTcN / 4; i += kTcThreads) dst[i] = src[i];
+  }
+  // generic-proxy writes of B must be visible to the tensor core (async proxy)
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t d_col = 2 * kTcN;  // D behind A_hi and A_lo
+
+  // instruction descriptor: D=F32, A=B=TF32, both K-major, N=64, M=128
+  constexpr uint32_t idesc =
+      (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t sb_hi = smem_u32(&sB[0][0]);
+  const uint32_t sb_lo = smem_u32(&sB[1][0]);
+  constexpr uint32_t kLbo = kTcN * 16;  // bytes between consecutive 16-byte K chunks
+  constexpr uint32_t kSbo = 128;        // bytes between 8-row groups
+
+  // element offsets of the 32 members of a group
+  uint32_t parity = 0;
+  for (uint64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const uint64_t g = tile * kTcThreads + (uint64_t)tid;
+    const uint64_t base = insert_zero_bits(g, p.tpos, kTcK);
+    float2* __restrict__ ptr = p.state + base;
+
+    float2 x[kTcDim];
+#pragma unroll
+    for (int j = 0; j < kTcDim; ++j) {
+      uint64_t off = 0;
+#pragma unroll
+      for (int b = 0; b < kTcK; ++b)
+        if ((j >> b) & 1) off += 1ull << p.tpos[b];
+      const float2* q = ptr + off;
+      asm volatile("ld.global.v2.f32 {%0,%1}, [%2];" : "=f"(x[j].x), "=f"(x[j].y) : "l"(q));
+    }
+    // A row -> TMEM, 16 columns at a time: hi at [0,64), lo at [64,128)
+#pragma unroll
+    for (int c16 = 0; c16 < kTcN / 16; ++c16) {
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int col = c16 * 16 + e;
+        const float a = (col & 1) ? x[col >> 1].y : x[col >> 1].x;
+        const uint32_t h = to_tf32(a);
+        hi[e] = h;
+        lo[e] = __float_as_uint(a - __uint_as_float(h));
+      }
+      tmem_st16(lane_base + (uint32_t)(c16 * 16), hi);
+      tmem_st16(lane_base + (uint32_t)(kTcN + c16 * 16), lo);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t acc = 0;
+#pragma unroll
+      for (int prod = 0; prod < 3; ++prod) {
+        // (A_hi, B_hi), (A_lo, B_hi), (A_hi, B_lo)
+        const uint32_t a_col = (prod == 1) ? (uint32_t)kTcN : 0u;
+        const uint32_t sb = (prod == 2) ? sb_lo : sb_hi;
+#pragma unroll
+        for (int ks = 0; ks < kTcN / 8; ++ks) {
+          const uint64_t bd = umma_desc(sb + (uint32_t)(ks * 2) * kLbo, kLbo, kSbo);
+          umma_tf32_ts(tmem_base + d_col, tmem_base + a_col + (uint32_t)(ks * 8), bd, idesc, acc);
+          acc = 1;
+        }
+      }
+      asm volatile(
+          "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+              smem_u32(&mbar))
+          : "memory");
+    }
+    mbar_wait(smem_u32(&mbar), parity);
+    parity ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // D -> registers -> HBM (in place)
+#pragma unroll
+    for (int c16 = 0; c16 < kTcN / 16; ++c16) {
+      uint32_t d[16];
+      tmem_ld16(lane_base + d_col + (uint32_t)(c16 * 16), d);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int e = 0; e < 16; e += 2) {
+        const int r = (c16 * 16 + e) >> 1;
+        uint64_t off = 0;
+#pragma unroll
+        for (int b = 0; b < kTcK; ++b)
+          if ((r >> b) & 1) off += 1ull << p.tpos[b];
+        float2* q = ptr + off;
+        asm volatile("st.global.v2.f32 [%0], {%1,%2};" ::"l"(q), "f"(__uint_as_float(d[e])),
+                     "f"(__uint_as_float(d[e + 1]))
+                     : "memory");
+      }
+    }
+    // all reads of D must finish before the next tile's MMAs overwrite it
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)kTcCols)
+                 : "memory");
+  }
+}
+
+// Round-to-nearest-even onto the TF32 grid (10 explicit mantissa bits).
+static float tf32_round_host(float x) {
+  uint32_t u;
+  std::memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return x;
+  const uint32_t lsb = (u >> 13) & 1u;
+  u += 0xfffu + lsb;
+  u &= ~0x1fffu;
+  float r;
+  std::memcpy(&r, &u, 4);
+  return r;
+}
+
+std::atomic<int> g_tc_mode{1};  // 1 = use the tensor-core kernel for k = 5 (complex64)
+
+bool tc5_applicable(int dtype, int n, int K) {
+  return g_tc_mode.load(std::memory_order_relaxed) == 1 && dtype == B2Q_C64 && K == kTcK &&
+         n >= kTcK + 7;
+}
+
+// `mat` = gate matrix in sorted-target order (index bit i <-> i-th lowest
+// target), plain (re, im) float pairs, row-major 32 x 32.
+int launch_tc5(void* state, int n, const int* sorted, const float* mat, cudaStream_t stream) {
+  // B[nn][kk], nn = 2r + {0: re, 1: im} of output row r, kk = 2c + {0: re, 1: im}
+  // of input column c:  out_re = Mr x_re - Mi x_im ; out_im = Mi x_re + Mr x_im
+  std::vector<float> host(2 * kTcN * kTcN);
+  float* hi = host.data();
+  float* lo = host.data() + kTcN * kTcN;
+  for (int r = 0; r < kTcDim; ++r)
+    for (int c = 0; c < kTcDim; ++c) {
+      const float mr = mat[2 * (r * kTcDim + c)], mi = mat[2 * (r * kTcDim + c) + 1];
+      const float vals[2][2] = {{mr, -mi}, {mi, mr}};
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          const int nn = 2 * r + a, kk = 2 * c + b;
+          const size_t idx = (size_t)(kk >> 2) * (kTcN * 4) + (size_t)nn * 4 + (kk & 3);
+          const float v = vals[a][b];
+          const float h = tf32_round_host(v);
+          hi[idx] = h;
+          lo[idx] = tf32_round_host(v - h);
+        }
+    }
+  float* dmat = nullptr;
+  B2Q_CUDA_CHECK(cudaMallocAsync((void**)&dmat, host.size() * sizeof(float), stream));
+  B2Q_CUDA_CHECK(cudaMemcpyAsync(dmat, host.data(), host.size() * sizeof(float),
+                                 cudaMemcpyHostToDevice, stream));
+  // pageable source: the copy is staged before the call returns, `host` may die
+  TcParams p;
+  p.state = reinterpret_cast<float2*>(state);
+  p.num_tiles = (1ull << (n - kTcK)) / kTcThreads;
+  for (int i = 0; i < kTcK; ++i) p.tpos[i] = sorted[i];
+  p.bmat = dmat;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const uint64_t grid = std::min<uint64_t>(p.num_tiles, (uint64_t)sms * 2);
+  sv_apply_tc5_kernel<<<(unsigned)grid, kTcThreads, 0, stream>>>(p);
+  B2Q_LAUNCH_CHECK("sv_apply_tc5_kernel");
+  B2Q_CUDA_CHECK(cudaFreeAsync(dmat, stream));
+  return B2Q_OK;
+}
+
+}  // namespace b2q
+
+extern "C" int b2q_set_tc_mode(int mode) {
+  B2Q_REQUIRE(mode == 0 || mode == 1, "tc mode must be 0 or 1");
+  b2q::g_tc_mode.store(mode, std::memory_order_relaxed);
+  return B2Q_OK;
+}
