@@ -219,8 +219,8 @@ def run_b200_arm(args):
     wl = build_workload(args.workload)
     n, reps, gates = wl['n'], wl['reps'], wl['gates']
     unit_gates = len(fuse_gates(gates, 2))
-    blocks = fuse_gates(gates, args.max_fused)
     dtype = np.complex64
+    blocks = fuse_gates(gates, args.max_fused, dtype, n)
     dev = DeviceState.basis(n, dtype, 0)
     state_bytes = dev.nbytes
     rng = np.random.RandomState(0)
@@ -334,7 +334,7 @@ def run_b200_arm(args):
         'data': 'synthetic',
         'config': {'workload': args.workload, 'generator': wl['generator'], 'n_qubits': n,
                    'raw_ops': len(gates), 'gate_unit': 'k<=2 fused blocks (reference merge_k_qubit_unitaries(k=2) count)',
-                   'unit_gates': unit_gates, 'max_fused_qubits': args.max_fused,
+                   'unit_gates': unit_gates, 'max_fused_qubits': max(len(w) for _, w in blocks),
                    'passes_per_step': len(blocks), 'repetitions': reps,
                    'state_bytes': state_bytes,
                    'l2': 'inputs larger than L2 (state %.1f GB vs 126 MB)' % (state_bytes / 1e9)
@@ -355,7 +355,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='rqc30', choices=sorted(WORKLOADS) + ['rc_hbm'])
-    ap.add_argument('--max-fused', dest='max_fused', type=int, default=4)
+    ap.add_argument('--max-fused', dest='max_fused', type=int, default=None,
+                    help='widest fused block; default = kernel-matched policy (5 for complex64)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -35,7 +35,7 @@ constexpr int kTcThreads = 128;
 constexpr int kTcK = 5;                 // qubits per block
 constexpr int kTcDim = 1 << kTcK;       // 32 complex
 constexpr int kTcN = 2 * kTcDim;        // 64 reals: N and K of the real GEMM
-constexpr int kTcCols = 256;            // TMEM columns: A_hi 64 | A_lo 64 | D 64 | spare 64
+constexpr int kTcCols = 256;            // TMEM columns: A_hi 64 | A_lo 64 | D0 64 | D1 64
 
 struct TcParams {
   float2* state;
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
         const float a = (col & 1) ? x[col >> 1].y : x[col >> 1].x;
         const uint32_t h = to_tf32(a);
         hi[e] = h;
-        lo[e] = __float_as_uint(a - __uint_as_float(h));
+        lo[e] = to_tf32(a - __uint_as_float(h));  // rounded, not truncated by the MMA: no bias
       }
       tmem_st16(lane_base + (uint32_t)(c16 * 16), hi);
       tmem_st16(lane_base + (uint32_t)(kTcN + c16 * 16), lo);
@@ -195,18 +195,32 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     __syncthreads();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint32_t acc = 0;
+      // The tensor core truncates (rounds toward zero) every time it adds an MMA
+      // result into the fp32 accumulator, which shrinks the state by ~3e-8 per
+      // accumulation of a full-size partial sum.  Keep those few: the two small
+      // cross terms (a_lo b_hi, a_hi b_lo: ~2^-11 of the result) go first, while
+      // the accumulator is still tiny, and the main product a_hi b_hi is split
+      // over two accumulators (4 K-steps each) that are added in fp32
+      // round-to-nearest by the CUDA cores in the epilogue.
+      uint32_t acc0 = 0;
 #pragma unroll
-      for (int prod = 0; prod < 3; ++prod) {
-        // (A_hi, B_hi), (A_lo, B_hi), (A_hi, B_lo)
-        const uint32_t a_col = (prod == 1) ? (uint32_t)kTcN : 0u;
-        const uint32_t sb = (prod == 2) ? sb_lo : sb_hi;
+      for (int prod = 0; prod < 2; ++prod) {
+        const uint32_t a_col = (prod == 0) ? (uint32_t)kTcN : 0u;  // A_lo, then A_hi
+        const uint32_t sb = (prod == 0) ? sb_hi : sb_lo;            // B_hi, then B_lo
 #pragma unroll
         for (int ks = 0; ks < kTcN / 8; ++ks) {
           const uint64_t bd = umma_desc(sb + (uint32_t)(ks * 2) * kLbo, kLbo, kSbo);
-          umma_tf32_ts(tmem_base + d_col, tmem_base + a_col + (uint32_t)(ks * 8), bd, idesc, acc);
-          acc = 1;
+          umma_tf32_ts(tmem_base + d_col, tmem_base + a_col + (uint32_t)(ks * 8), bd, idesc, acc0);
+          acc0 = 1;
         }
+      }
+#pragma unroll
+      for (int ks = 0; ks < kTcN / 8; ++ks) {
+        const uint64_t bd = umma_desc(sb_hi + (uint32_t)(ks * 2) * kLbo, kLbo, kSbo);
+        const bool second = ks >= kTcN / 16;
+        umma_tf32_ts(tmem_base + d_col + (second ? (uint32_t)kTcN : 0u),
+                     tmem_base + (uint32_t)(ks * 8), bd, idesc,
+                     (second && ks == kTcN / 16) ? 0u : 1u);
       }
       asm volatile(
           "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -219,9 +233,13 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     // D -> registers -> HBM (in place)
 #pragma unroll
     for (int c16 = 0; c16 < kTcN / 16; ++c16) {
-      uint32_t d[16];
+      uint32_t d[16], d1[16];
       tmem_ld16(lane_base + d_col + (uint32_t)(c16 * 16), d);
+      tmem_ld16(lane_base + d_col + (uint32_t)(kTcN + c16 * 16), d1);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        d[e] = __float_as_uint(__uint_as_float(d[e]) + __uint_as_float(d1[e]));
 #pragma unroll
       for (int e = 0; e < 16; e += 2) {
         const int r = (c16 * 16 + e) >> 1;

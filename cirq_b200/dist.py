@@ -385,10 +385,10 @@ class B200ShardedSimulator:
     classical control stay on the single-GPU simulators.
     """
 
-    def __init__(self, *, dtype=np.complex64, seed=None, max_fused_qubits: int = 4, group=None):
+    def __init__(self, *, dtype=np.complex64, seed=None, max_fused_qubits: int | None = None, group=None):
         self.dtype = np.dtype(dtype)
         self.seed = seed
-        self.max_fused = int(max_fused_qubits)
+        self.max_fused = max_fused_qubits
         self.group = group
 
     def _gates(self, circuit, qubits):
@@ -421,7 +421,7 @@ class B200ShardedSimulator:
         ).order_for(circuit.all_qubits())
         gates, _ = self._gates(circuit, qubits)
         sv = ShardedStateVector(len(qubits), self.dtype, group=self.group, initial_index=initial_state)
-        sv.apply_blocks(fuse_gates(gates, self.max_fused))
+        sv.apply_blocks(fuse_gates(gates, self.max_fused, self.dtype, sv.n_local))
         return sv
 
     def run(self, circuit, repetitions: int = 1) -> dict:
@@ -437,7 +437,7 @@ class B200ShardedSimulator:
             raise ValueError('Circuit has no measurements to sample.')
         sv = ShardedStateVector(len(qubits), self.dtype, group=self.group)
         try:
-            sv.apply_blocks(fuse_gates(gates, self.max_fused))
+            sv.apply_blocks(fuse_gates(gates, self.max_fused, self.dtype, sv.n_local))
             bits = sv.sample(repetitions, seed=self.seed)
         finally:
             sv.close()

@@ -61,7 +61,7 @@ def run(args, world, rank, local_rank):
     peak_gbs, peak_src = B.load_peaks()
     circuit, qubits, gates, n, reps, name = build(args, world)
     unit_gates = len(fuse_gates(gates, 2))
-    blocks = fuse_gates(gates, args.max_fused)
+    blocks = fuse_gates(gates, args.max_fused, np.complex64, n - (world.bit_length() - 1))
     sv = ShardedStateVector(n, np.complex64)
     shard_bytes = sv.local.nbytes
 
@@ -143,7 +143,7 @@ def run(args, world, rank, local_rank):
             'config': {'workload': name, 'n_qubits': n, 'local_qubits': n - (world.bit_length() - 1),
                        'raw_ops': len(gates), 'unit_gates': unit_gates,
                        'gate_unit': 'k<=2 fused blocks, counted as 30-qubit equivalents (x 2^(n-30))',
-                       'max_fused_qubits': args.max_fused, 'passes_per_step': passes,
+                       'max_fused_qubits': max(len(w) for _, w in blocks), 'passes_per_step': passes,
                        'qubit_swaps_per_step': swaps, 'repetitions': reps,
                        'shard_bytes': shard_bytes,
                        'swap': {'bytes_out_per_gpu': swap_bytes, 'ms': swap_ms,

@@ -26,7 +26,7 @@ import numpy as np
 
 from cirq_b200._cirq_compat import import_cirq
 from cirq_b200.device_state import DeviceState
-from cirq_b200.fusion import GateFuser
+from cirq_b200.fusion import GateFuser, fuser_for
 from cirq_b200.sv_simulator import _FastConfuseMixin
 
 cirq = import_cirq()
@@ -43,18 +43,18 @@ class B200DensityMatrix(qis.QuantumStateRepresentation):
     """Device-resident replacement of ``_BufferedDensityMatrix`` (no scratch
     buffers: the reference keeps three)."""
 
-    def __init__(self, dev: DeviceState, num_qubits: int, max_fused_qubits: int = 4):
+    def __init__(self, dev: DeviceState, num_qubits: int, max_fused_qubits: int | None = None):
         self._dev = dev
         self._n = int(num_qubits)
-        self._max_fused = int(max_fused_qubits)
-        self._fuser = GateFuser(self._max_fused)
+        self._max_fused = max_fused_qubits
+        self._fuser = fuser_for(dev.dtype, max_fused_qubits, 2 * self._n)
         self._qid_shape = (2,) * self._n
         self.passes = 0
         self._since_drain = 0
         self._drain_every = max(8, 2 * self._n)
 
     @classmethod
-    def create(cls, *, initial_state: Any = 0, qid_shape, dtype=np.complex64, max_fused_qubits=4):
+    def create(cls, *, initial_state: Any = 0, qid_shape, dtype=np.complex64, max_fused_qubits=None):
         if any(d != 2 for d in qid_shape):
             raise ValueError(
                 f'cirq_b200 simulates qubits only (dimension 2); got qid_shape={qid_shape}'
@@ -202,7 +202,7 @@ class B200DensityMatrixSimulationState(SimulationState[B200DensityMatrix]):
         initial_state: Any = 0,
         dtype=np.complex64,
         classical_data=None,
-        max_fused_qubits: int = 4,
+        max_fused_qubits: int | None = None,
     ):
         qubits = tuple(qubits) if qubits is not None else ()
         state = B200DensityMatrix.create(
@@ -320,7 +320,7 @@ class B200DensityMatrixSimulator(
         super().__init__(dtype=dtype, noise=noise, seed=seed, split_untangled_states=False)
         if dtype not in {np.complex64, np.complex128}:
             raise ValueError(f'dtype must be complex64 or complex128, was {dtype}')
-        self._max_fused = int(max_fused_qubits if max_fused_qubits is not None else 4)
+        self._max_fused = None if max_fused_qubits is None else int(max_fused_qubits)
 
     def _create_partial_simulation_state(self, initial_state, qubits, classical_data):
         if isinstance(initial_state, B200DensityMatrixSimulationState):

@@ -50,6 +50,22 @@ def expand_matrix(matrix: np.ndarray, wires: Sequence[int], out_wires: Sequence[
     return np.transpose(res, order).reshape(1 << u, 1 << u)
 
 
+def apply_to_block(block: np.ndarray, union: Sequence[int], matrix: np.ndarray,
+                   wires: Sequence[int]) -> np.ndarray:
+    """(matrix on `wires`) @ block, with `block` a 2^u x 2^u matrix on `union`
+    (a superset of `wires`): one tensor contraction on the row legs, no
+    expansion of `matrix` to the full space."""
+    u = len(union)
+    k = len(wires)
+    if k == u and tuple(wires) == tuple(union):
+        return matrix @ block
+    pos = [union.index(w) for w in wires]
+    t = block.reshape((2,) * u + (1 << u,))
+    res = np.tensordot(matrix.reshape((2,) * (2 * k)), t, axes=(list(range(k, 2 * k)), pos))
+    res = np.moveaxis(res, list(range(k)), pos)
+    return res.reshape(1 << u, 1 << u)
+
+
 class _Block:
     __slots__ = ('wires', 'matrix', 'seq', 'alive', 'count')
 
@@ -64,8 +80,12 @@ class _Block:
 class GateFuser:
     """Accumulates gates and emits fused blocks in a valid execution order."""
 
-    def __init__(self, max_qubits: int = 4):
+    def __init__(self, max_qubits: int = 4, narrow_wires: Sequence[int] = (), narrow_max: int | None = None):
+        """`narrow_wires`: wires whose presence caps a block at `narrow_max`
+        qubits (index bits on which the widest kernel is inefficient)."""
         self.max_qubits = int(max_qubits)
+        self._narrow = frozenset(int(w) for w in narrow_wires)
+        self._narrow_max = int(narrow_max) if narrow_max is not None else self.max_qubits
         self._blocks: list[_Block] = []
         self._last: dict[int, _Block] = {}
         self._seq = 0
@@ -73,6 +93,13 @@ class GateFuser:
 
     def __len__(self) -> int:
         return self.num_gates
+
+    def _fits(self, union: Sequence[int]) -> bool:
+        if len(union) <= self._narrow_max:
+            return True
+        if len(union) > self.max_qubits:
+            return False
+        return self._narrow.isdisjoint(union)
 
     def _movable(self, b: _Block) -> bool:
         return all(self._last.get(w) is b for w in b.wires)
@@ -108,7 +135,7 @@ class GateFuser:
         # 1. everything on our wires can be pulled together at the end
         if cands and len(movable) == len(cands):
             union = self._union([wires] + [b.wires for b in cands])
-            if len(union) <= self.max_qubits:
+            if self._fits(union):
                 self._merge_at_end(cands, matrix, wires, union)
                 return
         # 2. merge into the latest predecessor (order-safe: every other
@@ -118,13 +145,13 @@ class GateFuser:
             latest = max(cands, key=lambda b: b.seq)
             if len(latest.wires) <= self.max_qubits:
                 union = self._union([latest.wires, wires])
-                if len(union) <= self.max_qubits:
+                if self._fits(union):
                     extra = []
                     for b in sorted(movable, key=lambda b: len(b.wires)):
                         if b is latest:
                             continue
                         u2 = self._union([union, b.wires])
-                        if len(u2) <= self.max_qubits:
+                        if self._fits(u2):
                             union = u2
                             extra.append(b)
                     self._merge_into(latest, extra, matrix, wires, union)
@@ -134,7 +161,7 @@ class GateFuser:
         extra = []
         for b in sorted(movable, key=lambda b: len(b.wires)):
             u2 = self._union([union, b.wires])
-            if len(u2) <= self.max_qubits:
+            if self._fits(u2):
                 union = u2
                 extra.append(b)
         self._merge_at_end(extra, matrix, wires, union)
@@ -149,11 +176,14 @@ class GateFuser:
         total = None
         count = 1
         for b in sorted(blocks, key=lambda b: b.seq):
-            e = expand_matrix(b.matrix, b.wires, union)
-            total = e if total is None else e @ total
+            if total is None:
+                total = expand_matrix(b.matrix, b.wires, union)
+            else:
+                total = apply_to_block(total, union, b.matrix, b.wires)
             count += b.count
-        g = expand_matrix(matrix, wires, union)
-        return (g if total is None else g @ total), count
+        if total is None:
+            return expand_matrix(matrix, wires, union), count
+        return apply_to_block(total, union, matrix, wires), count
 
     def _merge_at_end(self, blocks, matrix, wires, union) -> None:
         m, count = self._compose(blocks, matrix, wires, union)
@@ -214,9 +244,23 @@ class GateFuser:
         self.num_gates = 0
 
 
-def fuse_gates(gates, max_qubits: int = 4):
-    """Convenience wrapper: [(matrix, wires)] -> fused [(matrix, wires)]."""
-    f = GateFuser(max_qubits)
+def fuser_for(dtype, max_qubits: int | None = None, n_bits: int | None = None) -> 'GateFuser':
+    """The fusion policy matched to the kernels: complex64 fuses
+    up to 5 wires (tensor-core kernel) except on index bits 0-1, where 8-byte
+    lanes would split 32-byte sectors, and for states too small for that kernel;
+    complex128 up to 4."""
+    is_c64 = np.dtype(dtype) == np.dtype(np.complex64)
+    if max_qubits is None:
+        max_qubits = 5 if is_c64 and (n_bits is None or n_bits >= 12) else 4
+    if is_c64 and max_qubits >= 5:
+        return GateFuser(max_qubits, narrow_wires=(0, 1), narrow_max=4)
+    return GateFuser(max_qubits)
+
+
+def fuse_gates(gates, max_qubits: int = 4, dtype=None, n_bits: int | None = None):
+    """Convenience wrapper: [(matrix, wires)] -> fused [(matrix, wires)].  With
+    `dtype` the kernel-matched policy of `fuser_for` is used."""
+    f = GateFuser(max_qubits) if dtype is None else fuser_for(dtype, max_qubits, n_bits)
     for m, w in gates:
         f.add(m, w)
     return f.blocks()

@@ -31,7 +31,7 @@ import numpy as np
 
 from cirq_b200._cirq_compat import import_cirq
 from cirq_b200.device_state import DeviceState
-from cirq_b200.fusion import GateFuser
+from cirq_b200.fusion import GateFuser, fuser_for
 
 cirq = import_cirq()
 
@@ -53,11 +53,11 @@ class B200StateVector(qis.QuantumStateRepresentation):
     place) plus the queue of not-yet-applied unitaries.
     """
 
-    def __init__(self, dev: DeviceState, num_qubits: int, max_fused_qubits: int = 4):
+    def __init__(self, dev: DeviceState, num_qubits: int, max_fused_qubits: int | None = None):
         self._dev = dev
         self._n = int(num_qubits)
-        self._max_fused = int(max_fused_qubits)
-        self._fuser = GateFuser(self._max_fused)
+        self._max_fused = max_fused_qubits
+        self._fuser = fuser_for(dev.dtype, max_fused_qubits, self._n)
         self._qid_shape = (2,) * self._n
         self.passes = 0  # GPU gate passes issued so far (for benchmarks)
         self._since_drain = 0
@@ -72,7 +72,7 @@ class B200StateVector(qis.QuantumStateRepresentation):
         initial_state: Any = 0,
         qid_shape: tuple[int, ...],
         dtype=np.complex64,
-        max_fused_qubits: int = 4,
+        max_fused_qubits: int | None = None,
     ) -> 'B200StateVector':
         if any(d != 2 for d in qid_shape):
             raise ValueError(
@@ -219,7 +219,7 @@ class B200StateVectorSimulationState(SimulationState[B200StateVector]):
         initial_state: Any = 0,
         dtype=np.complex64,
         classical_data: 'cirq.ClassicalDataStore' | None = None,
-        max_fused_qubits: int = 4,
+        max_fused_qubits: int | None = None,
     ):
         qubits = tuple(qubits) if qubits is not None else ()
         state = B200StateVector.create(
@@ -295,14 +295,38 @@ def _can_decompose(action: Any, qubits) -> bool:
     return protocols.decompose_once(action, None) is not None
 
 
+_UNITARY_CACHE: dict = {}
+_UNITARY_CACHE_MAX = 4096
+
+
+def cached_unitary(action: Any):
+    """``protocols.unitary`` with a small cache keyed by the (hashable,
+    parameter-free) gate: circuits repeat a handful of gates thousands of
+    times and building each matrix costs ~40 us of Python."""
+    gate = getattr(action, 'gate', None)
+    key = None
+    if gate is not None and type(action) is ops.GateOperation:
+        try:
+            key = gate
+            hit = _UNITARY_CACHE.get(key)
+            if hit is not None:
+                return hit
+        except TypeError:  # unhashable gate
+            key = None
+    u = protocols.unitary(action, None)
+    if key is not None and u is not None and not protocols.is_parameterized(gate):
+        if len(_UNITARY_CACHE) >= _UNITARY_CACHE_MAX:
+            _UNITARY_CACHE.clear()
+        _UNITARY_CACHE[key] = u
+    return u
+
+
 def _strat_unitary(action: Any, args: B200StateVectorSimulationState, qubits) -> bool:
     """Unitary strategy: obtain the matrix from Cirq's query protocols and queue
     it.  Replaces ``_strat_act_on_state_vector_from_apply_unitary``
     (state_vector_simulation_state.py:402-407): the per-gate ``_apply_unitary_``
     numpy fast paths are never called."""
-    if not protocols.has_unitary(action):
-        return NotImplemented
-    u = protocols.unitary(action, None)
+    u = cached_unitary(action)
     if u is None:
         return NotImplemented
     args._state.queue_unitary(u, args.get_axes(qubits))
@@ -504,9 +528,8 @@ class B200Simulator(
             raise ValueError(f'dtype must be complex64 or complex128 but was {dtype}')
         super().__init__(dtype=dtype, noise=noise, seed=seed, split_untangled_states=False)
         self._requested_split = split_untangled_states
-        if max_fused_qubits is None:
-            max_fused_qubits = 4
-        self._max_fused = int(max_fused_qubits)
+        # None = kernel-matched policy (cirq_b200.fusion.fuser_for)
+        self._max_fused = None if max_fused_qubits is None else int(max_fused_qubits)
 
     def _create_partial_simulation_state(self, initial_state, qubits, classical_data):
         if isinstance(initial_state, B200StateVectorSimulationState):

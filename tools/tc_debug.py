@@ -59,3 +59,24 @@ for tg in ([11, 10, 9, 8, 7], [7, 8, 9, 10, 11], [0, 1, 2, 3, 4], [5, 0, 11, 3, 
     got = run(M, state, 1)
     ref = run(M, state, 0)
     print('random', tg, 'max err', np.max(np.abs(got - ref)), 'rel', np.max(np.abs(got - ref)) / np.max(np.abs(ref)))
+
+# 4. norm drift over many unitary passes (bias check)
+def rand_unitary(k):
+    d = 1 << k
+    q, r = np.linalg.qr(rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d)))
+    return q * (np.diag(r) / np.abs(np.diag(r)))
+
+n = 20
+for tc in (1, 0):
+    lib.b2q_set_tc_mode(tc)
+    dev = DeviceState.basis(n, np.complex64, 0)
+    r2 = np.random.RandomState(5)
+    norms = []
+    for i in range(60):
+        tg = r2.permutation(n)[:5].tolist()
+        d = 32
+        q, r = np.linalg.qr(r2.standard_normal((d, d)) + 1j * r2.standard_normal((d, d)))
+        dev.apply_matrix(q * (np.diag(r) / np.abs(np.diag(r))), tg)
+        if i % 10 == 9:
+            norms.append(dev.norm2())
+    print('tc' if tc else 'fp32', 'norm after 10..60 passes', ['%.7f' % v for v in norms])
