@@ -22,6 +22,13 @@ _LAZY = {
     'B200DensityMatrixTrialResult': 'cirq_b200.dm_simulator',
     'DeviceState': 'cirq_b200.device_state',
     'GateFuser': 'cirq_b200.fusion',
+    'sample': 'cirq_b200.mux',
+    'sample_sweep': 'cirq_b200.mux',
+    'final_state_vector': 'cirq_b200.mux',
+    'final_density_matrix': 'cirq_b200.mux',
+    'use_b200': 'cirq_b200.mux',
+    'B200ShardedSimulator': 'cirq_b200.dist',
+    'ShardedStateVector': 'cirq_b200.dist',
 }
 
 

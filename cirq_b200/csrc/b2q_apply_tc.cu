@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 namespace b2q {
@@ -158,14 +159,16 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   constexpr uint32_t kLbo = kTcN * 16;  // bytes between consecutive 16-byte K chunks
   constexpr uint32_t kSbo = 128;        // bytes between 8-row groups
 
-  // element offsets of the 32 members of a group
+  // Software pipeline: the loads of tile i+1 are issued as soon as tile i's
+  // amplitudes have been handed to TMEM, so they are in flight while the tensor
+  // core multiplies and the epilogue stores tile i.
   uint32_t parity = 0;
-  for (uint64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-    const uint64_t g = tile * kTcThreads + (uint64_t)tid;
-    const uint64_t base = insert_zero_bits(g, p.tpos, kTcK);
-    float2* __restrict__ ptr = p.state + base;
-
-    float2 x[kTcDim];
+  uint64_t tile = blockIdx.x;
+  float2 x[kTcDim];
+  float2* ptr = p.state;
+  auto issue_loads = [&](uint64_t t) {
+    const uint64_t g = t * kTcThreads + (uint64_t)tid;
+    ptr = p.state + insert_zero_bits(g, p.tpos, kTcK);
 #pragma unroll
     for (int j = 0; j < kTcDim; ++j) {
       uint64_t off = 0;
@@ -175,6 +178,10 @@ __global__ void __launch_bounds__(kTcThreads, 2)
       const float2* q = ptr + off;
       asm volatile("ld.global.v2.f32 {%0,%1}, [%2];" : "=f"(x[j].x), "=f"(x[j].y) : "l"(q));
     }
+  };
+  if (tile < p.num_tiles) issue_loads(tile);
+  while (tile < p.num_tiles) {
+    float2* const cur = ptr;
     // A row -> TMEM, 16 columns at a time: hi at [0,64), lo at [64,128)
 #pragma unroll
     for (int c16 = 0; c16 < kTcN / 16; ++c16) {
@@ -185,13 +192,15 @@ __global__ void __launch_bounds__(kTcThreads, 2)
         const float a = (col & 1) ? x[col >> 1].y : x[col >> 1].x;
         const uint32_t h = to_tf32(a);
         hi[e] = h;
-        lo[e] = to_tf32(a - __uint_as_float(h));  // rounded, not truncated by the MMA: no bias
+        lo[e] = to_tf32(a - __uint_as_float(h));  // rounded, not truncated by the MMA
       }
       tmem_st16(lane_base + (uint32_t)(c16 * 16), hi);
       tmem_st16(lane_base + (uint32_t)(kTcN + c16 * 16), lo);
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    const uint64_t next = tile + gridDim.x;
+    if (next < p.num_tiles) issue_loads(next);
     __syncthreads();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -230,7 +239,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     mbar_wait(smem_u32(&mbar), parity);
     parity ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // D -> registers -> HBM (in place)
+    // D0 + D1 -> registers -> HBM (in place)
 #pragma unroll
     for (int c16 = 0; c16 < kTcN / 16; ++c16) {
       uint32_t d[16], d1[16];
@@ -238,23 +247,21 @@ __global__ void __launch_bounds__(kTcThreads, 2)
       tmem_ld16(lane_base + d_col + (uint32_t)(kTcN + c16 * 16), d1);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int e = 0; e < 16; ++e)
-        d[e] = __float_as_uint(__uint_as_float(d[e]) + __uint_as_float(d1[e]));
-#pragma unroll
       for (int e = 0; e < 16; e += 2) {
         const int r = (c16 * 16 + e) >> 1;
         uint64_t off = 0;
 #pragma unroll
         for (int b = 0; b < kTcK; ++b)
           if ((r >> b) & 1) off += 1ull << p.tpos[b];
-        float2* q = ptr + off;
-        asm volatile("st.global.v2.f32 [%0], {%1,%2};" ::"l"(q), "f"(__uint_as_float(d[e])),
-                     "f"(__uint_as_float(d[e + 1]))
-                     : "memory");
+        float2* q = cur + off;
+        const float re = __uint_as_float(d[e]) + __uint_as_float(d1[e]);
+        const float im = __uint_as_float(d[e + 1]) + __uint_as_float(d1[e + 1]);
+        asm volatile("st.global.v2.f32 [%0], {%1,%2};" ::"l"(q), "f"(re), "f"(im) : "memory");
       }
     }
     // all reads of D must finish before the next tile's MMAs overwrite it
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    tile = next;
   }
   __syncthreads();
   if (warp == 0) {
@@ -279,6 +286,43 @@ static float tf32_round_host(float x) {
 
 std::atomic<int> g_tc_mode{1};  // 1 = use the tensor-core kernel for k = 5 (complex64)
 
+// Gate matrices travel through a ring of pinned host / device slot pairs: a
+// cudaMemcpyAsync from PAGEABLE memory synchronises the stream first, which
+// would serialise the host scheduler with the GPU on every pass.
+struct MatrixRing {
+  static constexpr int kSlots = 64;
+  static constexpr size_t kBytes = 2 * kTcN * kTcN * sizeof(float);
+  float* host[kSlots] = {nullptr};
+  float* dev[kSlots] = {nullptr};
+  cudaEvent_t done[kSlots];
+  bool used[kSlots] = {false};
+  uint64_t next = 0;
+  bool ready = false;
+};
+static MatrixRing g_ring[64];
+static std::mutex g_ring_mutex;
+
+static int ring_acquire(MatrixRing** out_ring, int* out_slot) {
+  int devid = 0;
+  B2Q_CUDA_CHECK(cudaGetDevice(&devid));
+  B2Q_REQUIRE(devid >= 0 && devid < 64, "device index out of range");
+  MatrixRing& r = g_ring[devid];
+  if (!r.ready) {
+    for (int i = 0; i < MatrixRing::kSlots; ++i) {
+      B2Q_CUDA_CHECK(cudaHostAlloc((void**)&r.host[i], MatrixRing::kBytes, cudaHostAllocDefault));
+      B2Q_CUDA_CHECK(cudaMalloc((void**)&r.dev[i], MatrixRing::kBytes));
+      B2Q_CUDA_CHECK(cudaEventCreateWithFlags(&r.done[i], cudaEventDisableTiming));
+    }
+    r.ready = true;
+  }
+  const int slot = (int)(r.next++ % MatrixRing::kSlots);
+  if (r.used[slot]) B2Q_CUDA_CHECK(cudaEventSynchronize(r.done[slot]));
+  r.used[slot] = true;
+  *out_ring = &r;
+  *out_slot = slot;
+  return B2Q_OK;
+}
+
 bool tc5_applicable(int dtype, int n, int K) {
   return g_tc_mode.load(std::memory_order_relaxed) == 1 && dtype == B2Q_C64 && K == kTcK &&
          n >= kTcK + 7;
@@ -289,9 +333,15 @@ bool tc5_applicable(int dtype, int n, int K) {
 int launch_tc5(void* state, int n, const int* sorted, const float* mat, cudaStream_t stream) {
   // B[nn][kk], nn = 2r + {0: re, 1: im} of output row r, kk = 2c + {0: re, 1: im}
   // of input column c:  out_re = Mr x_re - Mi x_im ; out_im = Mi x_re + Mr x_im
-  std::vector<float> host(2 * kTcN * kTcN);
-  float* hi = host.data();
-  float* lo = host.data() + kTcN * kTcN;
+  std::lock_guard<std::mutex> lock(g_ring_mutex);
+  MatrixRing* ring = nullptr;
+  int slot = 0;
+  {
+    const int rc = ring_acquire(&ring, &slot);
+    if (rc != B2Q_OK) return rc;
+  }
+  float* hi = ring->host[slot];
+  float* lo = hi + kTcN * kTcN;
   for (int r = 0; r < kTcDim; ++r)
     for (int c = 0; c < kTcDim; ++c) {
       const float mr = mat[2 * (r * kTcDim + c)], mi = mat[2 * (r * kTcDim + c) + 1];
@@ -306,11 +356,9 @@ int launch_tc5(void* state, int n, const int* sorted, const float* mat, cudaStre
           lo[idx] = tf32_round_host(v - h);
         }
     }
-  float* dmat = nullptr;
-  B2Q_CUDA_CHECK(cudaMallocAsync((void**)&dmat, host.size() * sizeof(float), stream));
-  B2Q_CUDA_CHECK(cudaMemcpyAsync(dmat, host.data(), host.size() * sizeof(float),
+  float* dmat = ring->dev[slot];
+  B2Q_CUDA_CHECK(cudaMemcpyAsync(dmat, ring->host[slot], MatrixRing::kBytes,
                                  cudaMemcpyHostToDevice, stream));
-  // pageable source: the copy is staged before the call returns, `host` may die
   TcParams p;
   p.state = reinterpret_cast<float2*>(state);
   p.num_tiles = (1ull << (n - kTcK)) / kTcThreads;
@@ -326,7 +374,7 @@ int launch_tc5(void* state, int n, const int* sorted, const float* mat, cudaStre
   const uint64_t grid = std::min<uint64_t>(p.num_tiles, (uint64_t)sms * 2);
   sv_apply_tc5_kernel<<<(unsigned)grid, kTcThreads, 0, stream>>>(p);
   B2Q_LAUNCH_CHECK("sv_apply_tc5_kernel");
-  B2Q_CUDA_CHECK(cudaFreeAsync(dmat, stream));
+  B2Q_CUDA_CHECK(cudaEventRecord(ring->done[slot], stream));
   return B2Q_OK;
 }
 

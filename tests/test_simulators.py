@@ -420,3 +420,41 @@ def test_density_matrix_expectation_steps_and_initial_state(cirq, DM):
     want = cirq.DensityMatrixSimulator().simulate(circuit, initial_state=5)
     got = DM().simulate(circuit, initial_state=5)
     np.testing.assert_allclose(got.final_density_matrix, want.final_density_matrix, atol=1e-6)
+
+
+# --------------------------------------------------------------------------- mux entry points
+
+
+def test_mux_entry_points_match_reference(cirq, SV, DM):
+    """cirq_b200.sample / final_state_vector / final_density_matrix mirror
+    cirq.sample / ... (sim/mux.py) with the same signatures."""
+    import cirq_b200
+
+    q = cirq.LineQubit.range(3)
+    c = cirq.Circuit(cirq.H(q[0]), cirq.CNOT(q[0], q[1]), cirq.T(q[2]) ** 0.3, cirq.ISWAP(q[1], q[2]) ** 0.5)
+    np.testing.assert_allclose(
+        cirq_b200.final_state_vector(c, qubit_order=q), cirq.final_state_vector(c, qubit_order=q), atol=1e-6
+    )
+    np.testing.assert_allclose(
+        cirq_b200.final_state_vector(c, initial_state=5, dtype=np.complex128),
+        cirq.final_state_vector(c, initial_state=5, dtype=np.complex128), atol=1e-12,
+    )
+    noisy = c + cirq.Circuit(cirq.measure(q[0], key='m'))
+    np.testing.assert_allclose(
+        cirq_b200.final_density_matrix(noisy, noise=cirq.depolarize(0.05)),
+        cirq.final_density_matrix(noisy, noise=cirq.depolarize(0.05)), atol=1e-6,
+    )
+    # non-Clifford circuit so the mux does not take its stabilizer shortcut
+    m = c + cirq.Circuit(cirq.measure(*q, key='k'))
+    got = cirq_b200.sample(m, repetitions=200, seed=4)
+    assert got.measurements['k'].shape == (200, 3)
+    got = cirq_b200.sample(m, noise=cirq.bit_flip(0.1), repetitions=50, seed=4)
+    assert got.measurements['k'].shape == (50, 3)
+    import sympy
+
+    s = sympy.Symbol('s')
+    sweep_c = cirq.Circuit(cirq.rx(s).on(q[0]), cirq.T(q[0]), cirq.measure(q[0], key='z'))
+    res = cirq_b200.sample_sweep(sweep_c, cirq.Linspace('s', 0, 3, 4), repetitions=20, seed=1)
+    assert len(res) == 4 and res[0].measurements['z'].shape == (20, 1)
+    with pytest.raises(ValueError, match='measurement'):
+        cirq_b200.final_state_vector(m)
