@@ -700,8 +700,8 @@ int apply_generic(void* state, int n, const int* sorted, int K, const real* mat,
 }
 
 // b2q_apply_tc.cu
-bool tc5_applicable(int dtype, int n, int K);
-int launch_tc5(void* state, int n, const int* sorted, const float* mat, cudaStream_t stream);
+bool tc_applicable(int dtype, int n, int K);
+int launch_tc(void* state, int n, int K, const int* sorted, const float* mat, cudaStream_t stream);
 
 template <typename real>
 int apply_matrix_t(void* state, int dtype, int n, const double* m128, const int* targets, int K,
@@ -715,10 +715,10 @@ int apply_matrix_t(void* state, int dtype, int n, const double* m128, const int*
     B2Q_REQUIRE(i == 0 || sorted[i] != sorted[i - 1], "duplicate target bit %d", sorted[i]);
   }
   if constexpr (sizeof(real) == 4) {
-    if (tc5_applicable(dtype, n, K)) {
+    if (tc_applicable(dtype, n, K)) {
       std::vector<float> plain((size_t)2 << (2 * K));
       permute_matrix<float>(m128, targets, sorted, K, plain.data(), /*packed=*/false);
-      return launch_tc5(state, n, sorted, plain.data(), stream);
+      return launch_tc(state, n, K, sorted, plain.data(), stream);
     }
   }
   std::vector<real> mat((size_t)MatEntry<real>::kReals << (2 * K));

@@ -1,4 +1,4 @@
-// 5-qubit fused blocks on the 5th-generation tensor cores (tcgen05 + TMEM).
+// 5- and 6-qubit fused blocks on the 5th-generation tensor cores (tcgen05 + TMEM).
 //
 // A dense k-qubit block costs 4 * 2^k real FMAs per amplitude; at k = 5 that
 // is 128, past the FP32 CUDA-core roofline of a B200, so the
@@ -33,15 +33,23 @@
 namespace b2q {
 
 constexpr int kTcThreads = 128;
-constexpr int kTcK = 5;                 // qubits per block
-constexpr int kTcDim = 1 << kTcK;       // 32 complex
-constexpr int kTcN = 2 * kTcDim;        // 64 reals: N and K of the real GEMM
-constexpr int kTcCols = 256;            // TMEM columns: A_hi 64 | A_lo 64 | D0 64 | D1 64
+constexpr int kTcMaxK = 6;
+
+// K = 5: 32 complex = 64 reals per group, TMEM 256 columns, 32 KB of B, 2 CTAs/SM.
+// K = 6: 64 complex = 128 reals per group, TMEM 512 columns, 128 KB of B, 1 CTA/SM.
+template <int K>
+struct TcTraits {
+  static constexpr int kDim = 1 << K;     // complex amplitudes per group
+  static constexpr int kN = 2 * kDim;     // reals: N and K of the real GEMM
+  static constexpr int kCols = 4 * kN;    // TMEM columns: A_hi | A_lo | D0 | D1
+  static constexpr size_t kBBytes = 2ull * kN * kN * sizeof(float);  // B_hi + B_lo
+  static constexpr int kMinBlocks = K == 5 ? 2 : 1;
+};
 
 struct TcParams {
   float2* state;
   uint64_t num_tiles;  // groups / 128
-  int tpos[kTcK];      // ascending target positions
+  int tpos[kTcMaxK];   // ascending target positions
   const float* bmat;   // device: B_hi then B_lo, UMMA K-major no-swizzle layout
 };
 
@@ -117,9 +125,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
-__global__ void __launch_bounds__(kTcThreads, 2)
-    sv_apply_tc5_kernel(const __grid_constant__ TcParams p) {
-  __shared__ __align__(128) float sB[2][kTcN * kTcN];  // hi, lo (16 KB each)
+template <int K>
+__global__ void __launch_bounds__(kTcThreads, TcTraits<K>::kMinBlocks)
+    sv_apply_tc_kernel(const __grid_constant__ TcParams p) {
+  constexpr int kTcK = K;
+  constexpr int kTcDim = TcTraits<K>::kDim;
+  constexpr int kTcN = TcTraits<K>::kN;
+  constexpr int kTcCols = TcTraits<K>::kCols;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* sB = reinterpret_cast<float*>(smem_raw);  // B_hi then B_lo
   __shared__ __align__(8) uint64_t mbar;
   __shared__ uint32_t tmem_base_s;
 
@@ -139,7 +153,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   }
   {
     const float4* src = reinterpret_cast<const float4*>(p.bmat);
-    float4* dst = reinterpret_cast<float4*>(&sB[0][0]);
+    float4* dst = reinterpret_cast<float4*>(sB);
     for (int i = tid; i < 2 * kTcN * kTcN / 4; i += kTcThreads) dst[i] = src[i];
   }
   // generic-proxy writes of B must be visible to the tensor core (async proxy)
@@ -151,11 +165,11 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
   const uint32_t d_col = 2 * kTcN;  // D behind A_hi and A_lo
 
-  // instruction descriptor: D=F32, A=B=TF32, both K-major, N=64, M=128
+  // instruction descriptor: D=F32, A=B=TF32, both K-major, N=kTcN, M=128
   constexpr uint32_t idesc =
       (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((128u >> 4) << 24);
-  const uint32_t sb_hi = smem_u32(&sB[0][0]);
-  const uint32_t sb_lo = smem_u32(&sB[1][0]);
+  const uint32_t sb_hi = smem_u32(sB);
+  const uint32_t sb_lo = smem_u32(sB + kTcN * kTcN);
   constexpr uint32_t kLbo = kTcN * 16;  // bytes between consecutive 16-byte K chunks
   constexpr uint32_t kSbo = 128;        // bytes between 8-row groups
 
@@ -182,7 +196,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   if (tile < p.num_tiles) issue_loads(tile);
   while (tile < p.num_tiles) {
     float2* const cur = ptr;
-    // A row -> TMEM, 16 columns at a time: hi at [0,64), lo at [64,128)
+    // A row -> TMEM, 16 columns at a time: hi at [0,N), lo at [N,2N)
 #pragma unroll
     for (int c16 = 0; c16 < kTcN / 16; ++c16) {
       uint32_t hi[16], lo[16];
@@ -291,7 +305,7 @@ std::atomic<int> g_tc_mode{1};  // 1 = use the tensor-core kernel for k = 5 (com
 // would serialise the host scheduler with the GPU on every pass.
 struct MatrixRing {
   static constexpr int kSlots = 64;
-  static constexpr size_t kBytes = 2 * kTcN * kTcN * sizeof(float);
+  static constexpr size_t kBytes = TcTraits<kTcMaxK>::kBBytes;  // sized for the widest block
   float* host[kSlots] = {nullptr};
   float* dev[kSlots] = {nullptr};
   cudaEvent_t done[kSlots];
@@ -323,14 +337,18 @@ static int ring_acquire(MatrixRing** out_ring, int* out_slot) {
   return B2Q_OK;
 }
 
-bool tc5_applicable(int dtype, int n, int K) {
-  return g_tc_mode.load(std::memory_order_relaxed) == 1 && dtype == B2Q_C64 && K == kTcK &&
-         n >= kTcK + 7;
+bool tc_applicable(int dtype, int n, int K) {
+  return g_tc_mode.load(std::memory_order_relaxed) == 1 && dtype == B2Q_C64 && (K == 5 || K == 6) &&
+         n >= K + 7;
 }
 
 // `mat` = gate matrix in sorted-target order (index bit i <-> i-th lowest
-// target), plain (re, im) float pairs, row-major 32 x 32.
-int launch_tc5(void* state, int n, const int* sorted, const float* mat, cudaStream_t stream) {
+// target), plain (re, im) float pairs, row-major 2^K x 2^K.
+template <int K>
+int launch_tc_k(void* state, int n, const int* sorted, const float* mat, cudaStream_t stream) {
+  constexpr int kTcK = K;
+  constexpr int kTcDim = TcTraits<K>::kDim;
+  constexpr int kTcN = TcTraits<K>::kN;
   // B[nn][kk], nn = 2r + {0: re, 1: im} of output row r, kk = 2c + {0: re, 1: im}
   // of input column c:  out_re = Mr x_re - Mi x_im ; out_im = Mi x_re + Mr x_im
   std::lock_guard<std::mutex> lock(g_ring_mutex);
@@ -357,7 +375,7 @@ int launch_tc5(void* state, int n, const int* sorted, const float* mat, cudaStre
         }
     }
   float* dmat = ring->dev[slot];
-  B2Q_CUDA_CHECK(cudaMemcpyAsync(dmat, ring->host[slot], MatrixRing::kBytes,
+  B2Q_CUDA_CHECK(cudaMemcpyAsync(dmat, ring->host[slot], TcTraits<K>::kBBytes,
                                  cudaMemcpyHostToDevice, stream));
   TcParams p;
   p.state = reinterpret_cast<float2*>(state);
@@ -371,11 +389,24 @@ int launch_tc5(void* state, int n, const int* sorted, const float* mat, cudaStre
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
   }
-  const uint64_t grid = std::min<uint64_t>(p.num_tiles, (uint64_t)sms * 2);
-  sv_apply_tc5_kernel<<<(unsigned)grid, kTcThreads, 0, stream>>>(p);
-  B2Q_LAUNCH_CHECK("sv_apply_tc5_kernel");
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2Q_CUDA_CHECK(cudaFuncSetAttribute(sv_apply_tc_kernel<K>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)TcTraits<K>::kBBytes));
+    attr_set = true;
+  }
+  const uint64_t grid =
+      std::min<uint64_t>(p.num_tiles, (uint64_t)sms * TcTraits<K>::kMinBlocks);
+  sv_apply_tc_kernel<K><<<(unsigned)grid, kTcThreads, TcTraits<K>::kBBytes, stream>>>(p);
+  B2Q_LAUNCH_CHECK("sv_apply_tc_kernel");
   B2Q_CUDA_CHECK(cudaEventRecord(ring->done[slot], stream));
   return B2Q_OK;
+}
+
+int launch_tc(void* state, int n, int K, const int* sorted, const float* mat, cudaStream_t stream) {
+  if (K == 5) return launch_tc_k<5>(state, n, sorted, mat, stream);
+  return launch_tc_k<6>(state, n, sorted, mat, stream);
 }
 
 }  // namespace b2q

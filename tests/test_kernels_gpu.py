@@ -94,6 +94,29 @@ def test_every_single_and_pair_position(DS, dtype):
         assert err <= ATOL[np.dtype(dtype)], (a, b, err)
 
 
+@pytest.mark.parametrize('k', [5, 6])
+def test_tensor_core_kernels_match_oracle(DS, k):
+    """tcgen05 path (complex64, k = 5 and 6): every position class, 3xTF32 split
+    must stay within the complex64 tolerance."""
+    rng = np.random.RandomState(60 + k)
+    for n in (k + 7, 16, 20):
+        sets = [list(range(n - k, n)), list(range(k)), list(range(2, 2 + k))]
+        sets += [rng.permutation(n)[:k].tolist() for _ in range(4)]
+        for targets in sets:
+            state = rand_state(rng, n, np.complex64)
+            m = rand_unitary(rng, k)
+            dev = DS.from_numpy(state)
+            dev.apply_matrix(m, targets)
+            err = np.max(np.abs(dev.to_numpy() - orc.apply_matrix(state, n, m, targets)))
+            assert err <= 1e-5 * 2.0 ** (-n / 2) * 64, (n, targets, err)
+    # norm is preserved over a long run of unitary blocks
+    n = 18
+    dev = DS.basis(n, np.complex64, 1)
+    for _ in range(40):
+        dev.apply_matrix(rand_unitary(rng, k), rng.permutation(n)[:k].tolist())
+    assert abs(dev.norm2() - 1.0) < 5e-5
+
+
 def test_generic_kernel_large_k(DS):
     rng = np.random.RandomState(5)
     for dtype, ks in ((np.complex64, (6, 7)), (np.complex128, (5, 6))):
