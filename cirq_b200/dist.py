@@ -390,6 +390,24 @@ class B200ShardedSimulator:
         self.seed = seed
         self.max_fused = max_fused_qubits
         self.group = group
+        self._backend = None  # shard memory + IPC mappings, reused by successive run() calls
+
+    def _backend_for(self, n_qubits: int):
+        import torch.distributed as dist
+
+        world = dist.get_world_size(self.group)
+        n_local = n_qubits - (world.bit_length() - 1)
+        if self._backend is not None and self._backend.n_local != n_local:
+            self.close()
+        if self._backend is None:
+            self._backend = ShardBackend(n_local, self.dtype, self.group)
+        return self._backend
+
+    def close(self) -> None:
+        """Releases the cached shard (collective: call on every rank)."""
+        if self._backend is not None:
+            self._backend.close()
+            self._backend = None
 
     def _gates(self, circuit, qubits):
         from cirq_b200._cirq_compat import import_cirq
@@ -435,12 +453,10 @@ class B200ShardedSimulator:
         gates, measured = self._gates(circuit, qubits)
         if not measured:
             raise ValueError('Circuit has no measurements to sample.')
-        sv = ShardedStateVector(len(qubits), self.dtype, group=self.group)
-        try:
-            sv.apply_blocks(fuse_gates(gates, self.max_fused, self.dtype, sv.n_local))
-            bits = sv.sample(repetitions, seed=self.seed)
-        finally:
-            sv.close()
+        sv = ShardedStateVector(len(qubits), self.dtype, group=self.group,
+                                backend=self._backend_for(len(qubits)))
+        sv.apply_blocks(fuse_gates(gates, self.max_fused, self.dtype, sv.n_local))
+        bits = sv.sample(repetitions, seed=self.seed)
         axis = {q: i for i, q in enumerate(qubits)}
         out = {}
         for op in measured:

@@ -133,6 +133,7 @@ def run(args, world, rank, local_rank):
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_s = float(dt.item())
 
+    sim.close()
     if rank == 0:
         achieved = 2 * shard_bytes / (pass_ms * 1e-3) / 1e9
         line = {
