@@ -43,7 +43,7 @@ struct TcTraits {
   static constexpr int kN = 2 * kDim;     // reals: N and K of the real GEMM
   static constexpr int kCols = 4 * kN;    // TMEM columns: A_hi | A_lo | D0 | D1
   static constexpr size_t kBBytes = 2ull * kN * kN * sizeof(float);  // B_hi + B_lo
-  static constexpr int kMinBlocks = K == 5 ? 2 : 1;
+  static constexpr int kMinBlocks = K == 4 ? 4 : (K == 5 ? 2 : 1);
 };
 
 struct TcParams {
@@ -337,9 +337,11 @@ static int ring_acquire(MatrixRing** out_ring, int* out_slot) {
   return B2Q_OK;
 }
 
+// mode 1: k = 5, 6 on the tensor cores; mode 2: also k = 4.
 bool tc_applicable(int dtype, int n, int K) {
-  return g_tc_mode.load(std::memory_order_relaxed) == 1 && dtype == B2Q_C64 && (K == 5 || K == 6) &&
-         n >= K + 7;
+  const int mode = g_tc_mode.load(std::memory_order_relaxed);
+  if (mode == 0 || dtype != B2Q_C64 || n < K + 7) return false;
+  return K == 5 || K == 6 || (K == 4 && mode == 2);
 }
 
 // `mat` = gate matrix in sorted-target order (index bit i <-> i-th lowest
@@ -389,12 +391,16 @@ int launch_tc_k(void* state, int n, const int* sorted, const float* mat, cudaStr
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2Q_CUDA_CHECK(cudaFuncSetAttribute(sv_apply_tc_kernel<K>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)TcTraits<K>::kBBytes));
-    attr_set = true;
+  static bool attr_set[64] = {false};
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+      B2Q_CUDA_CHECK(cudaFuncSetAttribute(sv_apply_tc_kernel<K>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)TcTraits<K>::kBBytes));
+      attr_set[dev] = true;
+    }
   }
   const uint64_t grid =
       std::min<uint64_t>(p.num_tiles, (uint64_t)sms * TcTraits<K>::kMinBlocks);
@@ -405,6 +411,7 @@ int launch_tc_k(void* state, int n, const int* sorted, const float* mat, cudaStr
 }
 
 int launch_tc(void* state, int n, int K, const int* sorted, const float* mat, cudaStream_t stream) {
+  if (K == 4) return launch_tc_k<4>(state, n, sorted, mat, stream);
   if (K == 5) return launch_tc_k<5>(state, n, sorted, mat, stream);
   return launch_tc_k<6>(state, n, sorted, mat, stream);
 }
@@ -412,7 +419,7 @@ int launch_tc(void* state, int n, int K, const int* sorted, const float* mat, cu
 }  // namespace b2q
 
 extern "C" int b2q_set_tc_mode(int mode) {
-  B2Q_REQUIRE(mode == 0 || mode == 1, "tc mode must be 0 or 1");
+  B2Q_REQUIRE(mode >= 0 && mode <= 2, "tc mode must be 0, 1 or 2");
   b2q::g_tc_mode.store(mode, std::memory_order_relaxed);
   return B2Q_OK;
 }

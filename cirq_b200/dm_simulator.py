@@ -47,7 +47,9 @@ class B200DensityMatrix(qis.QuantumStateRepresentation):
         self._dev = dev
         self._n = int(num_qubits)
         self._max_fused = max_fused_qubits
-        self._fuser = fuser_for(dev.dtype, max_fused_qubits, 2 * self._n)
+        # rho's natural block is 4 index bits (row+column bits of a qubit pair):
+        # 5-bit blocks save no passes here
+        self._fuser = fuser_for(dev.dtype, 4 if max_fused_qubits is None else max_fused_qubits, 2 * self._n)
         self._qid_shape = (2,) * self._n
         self.passes = 0
         self._since_drain = 0

@@ -75,9 +75,11 @@ int b2q_sv_scale(void* state, int dtype, int n_qubits, double re, double im, voi
  * :310-380 (apply_matrix_to_slices) and the per-gate slice fast paths in
  * ops/*.py::_apply_unitary_.  M need not be unitary (Kraus operators, and the
  * superoperators of the density-matrix path use the same entry point).
- * k = number of targets (1 <= k <= 10; k <= 5 (c64) / 4 (c128) take the
- * register-tiled streaming kernels, larger k a generic out-of-place kernel
- * that needs `scratch`, a device buffer of the state's size, else NULL). */
+ * k = number of targets (1 <= k <= 10).  complex64: k <= 4 register-tiled
+ * streaming kernel, k = 5, 6 tcgen05/TMEM tensor-core kernel (3xTF32, fp32
+ * accuracy) when n_qubits >= k + 7; complex128: k <= 4 register-tiled kernel.
+ * Anything else takes a generic out-of-place kernel that needs `scratch`, a
+ * device buffer of the state's size (NULL otherwise). */
 int b2q_sv_apply_matrix(void* state, int dtype, int n_qubits, const double* matrix_c128,
                         const int* targets, int k, void* scratch, void* stream);
 
@@ -202,6 +204,24 @@ int b2q_dist_ipc_close(void* ptr);
  * local_bit >= 1 for complex64 (16-byte vectors). */
 int b2q_dist_swap_bit(void* mine, void* peer, int dtype, int n_local, int local_bit,
                       int my_global_bit_value, void* stream);
+
+/* ---- tuning knobs and host-only test hooks (not needed by a binding) -------- */
+
+/* How target bits inside the 512-byte warp zone are handled by the register
+ * kernel: 0 = warp shuffles, 1 = lane remap, 2 = measured per-target policy
+ * (default). */
+int b2q_set_lane_mode(int mode);
+/* complex64 access width of the register kernel: 0 = policy (default), 1 = always
+ * 16-byte vectors, 2 = always one amplitude per lane. */
+int b2q_set_vec_mode(int mode);
+/* Tensor-core (tcgen05) kernels for complex64 blocks: 0 = off, 1 = k = 5 and 6
+ * (default), 2 = also k = 4. */
+int b2q_set_tc_mode(int mode);
+/* Host-only: the register kernel's plan for a target set (see
+ * tests/test_plan_host.py for the layout of `out`, 24 ints) and the matrix
+ * permutation to sorted-target order; no GPU needed. */
+int b2q_debug_plan(int dtype, int n_qubits, const int* targets, int k, int* out);
+int b2q_debug_permute_matrix(const double* matrix_c128, const int* targets, int k, double* out);
 
 #ifdef __cplusplus
 }

@@ -45,8 +45,12 @@ def main():
     ap.add_argument('--lane-mode', type=int, default=None)
     ap.add_argument('--only', default='')
     ap.add_argument('--vec-mode', type=int, default=None)
+    ap.add_argument('--tc-mode', type=int, default=None)
     args = ap.parse_args()
     dtype = np.complex64 if args.dtype == 'c64' else np.complex128
+    if args.tc_mode is not None:
+        from cirq_b200 import _lib
+        _lib.load().b2q_set_tc_mode(args.tc_mode)
     if args.vec_mode is not None:
         from cirq_b200 import _lib
         _lib.load().b2q_set_vec_mode(args.vec_mode)
