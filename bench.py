@@ -59,14 +59,21 @@ def load_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-def measured_traffic(n_qubits):
-    """dram read+write bytes per launch of the dominant kernel from the committed
-    ncu --set full capture (profiles/), valid for the 30-qubit workload only."""
-    path = os.path.join(ROOT, 'profiles', 'r1f_ncu_apply_summary.json')
+def measured_traffic(n_qubits, kernel):
+    """dram read+write bytes per launch of `kernel` from the committed ncu --set
+    full captures (profiles/ncu_traffic.json), valid for 30-qubit states only."""
+    path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
     if n_qubits != 30 or not os.path.exists(path):
         return None
     with open(path) as f:
-        return int(json.load(f)['dominant_traffic_bytes_per_launch'])
+        table = json.load(f)['bytes_per_launch_30q']
+    return table.get(kernel)
+
+
+def kernel_class(num_wires):
+    """Name of the kernel a fused block of this width runs on (complex64)."""
+    return 'sv_apply_tc_kernel<5>' if num_wires == 5 else (
+        'sv_apply_tc_kernel<6>' if num_wires == 6 else f'sv_apply_fast_kernel<float,{num_wires}>')
 
 
 def build_workload(name):
@@ -238,13 +245,26 @@ def run_b200_arm(args):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     gate_ms = []
 
+    per_kernel = {}
+
     def step(record=False):
         _lib.check(lib.b2q_sv_init_basis(dev.ptr, dev.code, n, 0, stream))
         if record:
+            # one event pair per launch, on the launching stream: per-kernel durations
+            pairs = []
             ev[0].record()
-        dev.apply_batch(blocks)
-        if record:
+            for m, w in blocks:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                dev.apply_matrix(m, w)
+                b.record()
+                pairs.append((kernel_class(len(w)), a, b))
             ev[1].record()
+            torch.cuda.synchronize()
+            for name, a, b in pairs:
+                per_kernel.setdefault(name, []).append(a.elapsed_time(b))
+        else:
+            dev.apply_batch(blocks)
         if reps:
             _lib.check(lib.b2q_sv_sample(dev.ptr, dev.code, n, ctypes.c_void_p(u_dev.data_ptr()), reps,
                                          ctypes.c_void_p(out_idx.data_ptr()),
@@ -272,7 +292,13 @@ def run_b200_arm(args):
         # per-kernel duration of the gate passes (separate, event-bracketed steps)
         for _ in range(min(3, args.steps)):
             step(record=True)
-    pass_ms = float(np.mean(gate_ms)) / len(blocks)
+    mean_pass_ms = float(np.mean(gate_ms)) / len(blocks)
+    breakdown = {k: {'launches_per_step': len(v) // max(1, min(3, args.steps)),
+                     'ms_per_launch': float(np.mean(v)),
+                     'share_of_gate_time': float(np.sum(v) / sum(np.sum(x) for x in per_kernel.values()))}
+                 for k, v in per_kernel.items()}
+    dominant = max(breakdown, key=lambda k: breakdown[k]['share_of_gate_time'])
+    pass_ms = breakdown[dominant]['ms_per_launch']
     achieved = 2 * state_bytes / (pass_ms * 1e-3) / 1e9
     value = unit_gates / (ms_per_step * 1e-3)
 
@@ -340,9 +366,10 @@ def run_b200_arm(args):
                    'l2': 'inputs larger than L2 (state %.1f GB vs 126 MB)' % (state_bytes / 1e9)
                          if state_bytes > 252e6 else 'state fits L2; not an HBM measurement'},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak_gbs, 'unit': 'GB/s',
-                     'frac': achieved / peak_gbs, 'traffic': measured_traffic(n), 'kernel': 'sv_apply_fast_kernel',
+                     'frac': achieved / peak_gbs, 'traffic': measured_traffic(n, dominant), 'kernel': dominant,
                      'peak_source': peak_src, 'bytes_per_launch': 2 * state_bytes,
-                     'ms_per_launch': pass_ms},
+                     'ms_per_launch': pass_ms, 'mean_ms_over_all_passes': mean_pass_ms,
+                     'kernels': breakdown},
         'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks.summary(),
     }
     print(json.dumps(line), flush=True)
