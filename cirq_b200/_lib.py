@@ -65,6 +65,13 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_int, c_int, c_uint64, c_uint64, POINTER(c_double), c_void_p],
     ),
+    'b2q_sv_kron': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    'b2q_sv_permute_bits': (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_int), c_void_p]),
+    'b2q_sv_argmax_abs': (c_int, [c_void_p, c_int, c_int, POINTER(c_uint64), c_void_p]),
+    'b2q_sv_kron_allclose': (
+        c_int,
+        [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_double, c_double, POINTER(c_int), c_void_p],
+    ),
     'b2q_dm_diagonal': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'b2q_probs_marginal': (c_int, [c_void_p, c_int, POINTER(c_int), c_int, c_void_p, c_void_p]),
     'b2q_dm_trace': (c_int, [c_void_p, c_int, c_int, POINTER(c_double), c_void_p]),

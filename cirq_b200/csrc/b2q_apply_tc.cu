@@ -57,10 +57,11 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Round to the TF32 grid (10 explicit mantissa bits), ties away from zero: two
+// integer instructions.  cvt.rna.tf32.f32 compiles to ~5 (NaN/Inf handling the
+// amplitudes never need).
 __device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
+  return (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
 }
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -136,6 +137,9 @@ __global__ void __launch_bounds__(kTcThreads, TcTraits<K>::kMinBlocks)
   float* sB = reinterpret_cast<float*>(smem_raw);  // B_hi then B_lo
   __shared__ __align__(8) uint64_t mbar;
   __shared__ uint32_t tmem_base_s;
+  // element offset of member j of a group (same for every tile): one LDS instead
+  // of ~10 integer instructions per access
+  __shared__ __align__(8) uint64_t s_off[TcTraits<K>::kDim];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -150,6 +154,12 @@ __global__ void __launch_bounds__(kTcThreads, TcTraits<K>::kMinBlocks)
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int j = tid; j < kTcDim; j += kTcThreads) {
+    uint64_t off = 0;
+    for (int b = 0; b < kTcK; ++b)
+      if ((j >> b) & 1) off += 1ull << p.tpos[b];
+    s_off[j] = off;
   }
   {
     const float4* src = reinterpret_cast<const float4*>(p.bmat);
@@ -185,11 +195,7 @@ __global__ void __launch_bounds__(kTcThreads, TcTraits<K>::kMinBlocks)
     ptr = p.state + insert_zero_bits(g, p.tpos, kTcK);
 #pragma unroll
     for (int j = 0; j < kTcDim; ++j) {
-      uint64_t off = 0;
-#pragma unroll
-      for (int b = 0; b < kTcK; ++b)
-        if ((j >> b) & 1) off += 1ull << p.tpos[b];
-      const float2* q = ptr + off;
+      const float2* q = ptr + s_off[j];
       asm volatile("ld.global.v2.f32 {%0,%1}, [%2];" : "=f"(x[j].x), "=f"(x[j].y) : "l"(q));
     }
   };
@@ -263,11 +269,7 @@ __global__ void __launch_bounds__(kTcThreads, TcTraits<K>::kMinBlocks)
 #pragma unroll
       for (int e = 0; e < 16; e += 2) {
         const int r = (c16 * 16 + e) >> 1;
-        uint64_t off = 0;
-#pragma unroll
-        for (int b = 0; b < kTcK; ++b)
-          if ((r >> b) & 1) off += 1ull << p.tpos[b];
-        float2* q = cur + off;
+        float2* q = cur + s_off[r];
         const float re = __uint_as_float(d[e]) + __uint_as_float(d1[e]);
         const float im = __uint_as_float(d[e + 1]) + __uint_as_float(d1[e + 1]);
         asm volatile("st.global.v2.f32 [%0], {%1,%2};" ::"l"(q), "f"(re), "f"(im) : "memory");

@@ -293,6 +293,58 @@ class DeviceState:
         )
         return complex(out[0], out[1])
 
+    # ------------------------------------------------------------------ layout
+
+    def kron(self, other: 'DeviceState') -> 'DeviceState':
+        """|self> (x) |other>: self's bits become the high bits."""
+        torch = _torch()
+        out = DeviceState(self.n_bits + other.n_bits, self.dtype)
+        check(
+            self._lib.b2q_sv_kron(
+                self.ptr, self.n_bits, other.ptr, other.n_bits, self.code, out.ptr,
+                _stream_ptr(torch),
+            )
+        )
+        return out
+
+    def permute_bits(self, src_bit: Sequence[int]) -> 'DeviceState':
+        """New state with out[o] = self[i], bit k of o == bit src_bit[k] of i."""
+        torch = _torch()
+        out = DeviceState(self.n_bits, self.dtype)
+        check(
+            self._lib.b2q_sv_permute_bits(
+                self.ptr, out.ptr, self.code, self.n_bits, _lib.int_array(src_bit),
+                _stream_ptr(torch),
+            )
+        )
+        return out
+
+    def argmax_abs(self) -> int:
+        torch = _torch()
+        out = ctypes.c_uint64(0)
+        check(
+            self._lib.b2q_sv_argmax_abs(
+                self.ptr, self.code, self.n_bits, ctypes.byref(out), _stream_ptr(torch)
+            )
+        )
+        return int(out.value)
+
+    def slice_copy(self, start: int, n_bits: int) -> 'DeviceState':
+        """Copy of the 2^n_bits amplitudes starting at `start`."""
+        return DeviceState(n_bits, self.dtype, tensor=self.tensor[start : start + (1 << n_bits)].clone())
+
+    def kron_allclose(self, a: 'DeviceState', b: 'DeviceState', atol: float, rtol: float = 1e-5) -> bool:
+        """np.allclose(kron(a, b), self, atol=atol, rtol=rtol) on the device."""
+        torch = _torch()
+        ok = ctypes.c_int(0)
+        check(
+            self._lib.b2q_sv_kron_allclose(
+                a.ptr, a.n_bits, b.ptr, b.n_bits, self.ptr, self.code, float(atol), float(rtol),
+                ctypes.byref(ok), _stream_ptr(torch),
+            )
+        )
+        return bool(ok.value)
+
     # ------------------------------------------------------------------ density matrix view
 
     def dm_diagonal_device(self):

@@ -44,6 +44,9 @@ from cirq.sim.simulation_state import SimulationState, strat_act_on_from_apply_d
 # protocols/apply_unitary_protocol.py:375-399, one wider because a 5-qubit
 # matrix is still a single streaming pass here).
 _MAX_DIRECT_UNITARY_QUBITS = 5
+# Above this many qubits split_untangled_states is ignored (see
+# B200Simulator._create_simulation_state).
+_MAX_SPLIT_QUBITS = 30
 
 
 class B200StateVector(qis.QuantumStateRepresentation):
@@ -62,6 +65,7 @@ class B200StateVector(qis.QuantumStateRepresentation):
         self.passes = 0  # GPU gate passes issued so far (for benchmarks)
         self._since_drain = 0
         self._drain_every = max(8, self._n)
+        self._host = None  # cached host copy of the state, dropped on every mutation
 
     # ------------------------------------------------------------------ creation
 
@@ -100,6 +104,7 @@ class B200StateVector(qis.QuantumStateRepresentation):
         return [self._n - 1 - int(a) for a in axes]
 
     def queue_unitary(self, matrix: np.ndarray, axes: Sequence[int]) -> None:
+        self._host = None
         if len(axes) == 0:
             # a global phase / scalar: fold it into the state
             self.flush()
@@ -146,6 +151,7 @@ class B200StateVector(qis.QuantumStateRepresentation):
         if not axes:
             return []
         self.flush()
+        self._host = None
         prng = value.parse_random_state(seed)
         bits = self._bits(axes)
         m = len(bits)
@@ -188,23 +194,88 @@ class B200StateVector(qis.QuantumStateRepresentation):
 
     @property
     def supports_factor(self) -> bool:
-        # One dense tensor on the device; unentangled qubits are not split off.
-        return False
+        return True
+
+    # ---- layout: Kronecker product, factoring, axis order (split_untangled_states) ----------
+
+    def kron(self, other: 'B200StateVector') -> 'B200StateVector':
+        """``state_vector_kronecker_product`` (linalg/transformations.py:603-613)."""
+        dev = self.device_state.kron(other.device_state)
+        out = B200StateVector(dev, self._n + other._n, self._max_fused)
+        out.passes = self.passes + other.passes
+        return out
+
+    def reindex(self, axes: Sequence[int]) -> 'B200StateVector':
+        """``transpose_state_vector_to_axis_order``: new axis k = old axis axes[k]."""
+        axes = [int(a) for a in axes]
+        n = self._n
+        if axes == list(range(n)):
+            return B200StateVector(self.device_state.copy(), n, self._max_fused)
+        src_bit = [0] * n
+        for k, a in enumerate(axes):
+            src_bit[n - 1 - k] = n - 1 - a
+        out = B200StateVector(self.device_state.permute_bits(src_bit), n, self._max_fused)
+        out.passes = self.passes
+        return out
+
+    def factor(self, axes: Sequence[int], *, validate=True, atol=1e-07):
+        """``factor_state_vector`` (linalg/transformations.py:647-691): pivot on the
+        largest amplitude, slice the two factors through it, normalise."""
+        axes = [int(a) for a in axes]
+        n, k = self._n, len(axes)
+        rest = [a for a in range(n) if a not in axes]
+        t1 = self.reindex(axes + rest)._dev  # factored axes in front
+        nr = n - k
+        pivot = t1.argmax_abs()
+        pf, pr = pivot >> nr, pivot & ((1 << nr) - 1)
+        real = np.float32 if t1.dtype == np.complex64 else np.float64
+        ext = t1.amplitudes([(e << nr) | pr for e in range(1 << k)]).astype(t1.dtype)
+        pivot_amp = ext[pf]
+        ext = ext / real(np.linalg.norm(ext))
+        extracted = DeviceState.from_numpy(ext, t1.dtype)
+        remainder = t1.slice_copy(pf << nr, nr)
+        rnorm = np.sqrt(remainder.norm2())
+        remainder.scale(1.0 / (complex(rnorm) * complex(pivot_amp) / abs(complex(pivot_amp))))
+        if validate:
+            if not t1.kron_allclose(extracted, remainder, atol):
+                if not np.isclose(np.sqrt(t1.norm2()), 1):
+                    raise ValueError('Input state must be normalized.')
+                raise cirq.linalg.transformations.EntangledStateError(
+                    'The tensor cannot be factored by the requested axes'
+                )
+        e_state = B200StateVector(extracted, k, self._max_fused)
+        r_state = B200StateVector(remainder, nr, self._max_fused)
+        r_state.passes = self.passes
+        return e_state, r_state
 
     # ------------------------------------------------------------------ non-unitary helpers
 
     def apply_matrix_now(self, matrix: np.ndarray, axes: Sequence[int]) -> None:
         self.flush()
+        self._host = None
         self._dev.apply_matrix(matrix, self._bits(axes))
         self.passes += 1
+
+    def scale(self, factor: complex) -> None:
+        self.flush()
+        self._host = None
+        self._dev.scale(factor)
+
+    def replace_device_state(self, dev: DeviceState) -> None:
+        self._fuser.clear()
+        self._host = None
+        self._dev = dev
 
     def norm2(self) -> float:
         self.flush()
         return self._dev.norm2()
 
     def to_numpy_tensor(self) -> np.ndarray:
-        self.flush()
-        return self._dev.to_numpy().reshape(self._qid_shape)
+        """Host copy as a ``(2,)*n`` tensor, cached until the state changes."""
+        if self._host is None:
+            self.flush()
+            self._host = self._dev.to_numpy().reshape(self._qid_shape)
+        return self._host
 
 
 class B200StateVectorSimulationState(SimulationState[B200StateVector]):
@@ -229,14 +300,34 @@ class B200StateVectorSimulationState(SimulationState[B200StateVector]):
             max_fused_qubits=max_fused_qubits,
         )
         super().__init__(state=state, prng=prng, qubits=qubits, classical_data=classical_data)
-        self._host_cache = None
+        self._dtype = np.dtype(dtype)
+        self._max_fused_qubits = max_fused_qubits
+
+    def add_qubits(self, qubits):
+        """Ancilla / late-joining qubits in |0> (state_vector_simulation_state.py:357-363)."""
+        ret = super().add_qubits(qubits)
+        if ret is not NotImplemented:
+            return ret
+        fresh = type(self)(
+            qubits=qubits, dtype=self._dtype, prng=self._prng,
+            max_fused_qubits=self._max_fused_qubits,
+        )
+        return self.kronecker_product(fresh, inplace=True)
+
+    def remove_qubits(self, qubits):
+        """(state_vector_simulation_state.py:365-371)"""
+        ret = super().remove_qubits(qubits)
+        if ret is not NotImplemented:
+            return ret
+        extracted, remainder = self.factor(qubits, inplace=True)
+        remainder._state.scale(complex(extracted._state.device_state.amplitudes([0])[0]))
+        return remainder
 
     # ---- act_on entry point (protocols/act_on_protocol.py:90-170) ------------------------
 
     def _act_on_fallback_(
         self, action: Any, qubits: Sequence['cirq.Qid'], allow_decompose: bool = True
     ) -> bool:
-        self._host_cache = None
         strats = [_strat_unitary, _strat_mixture, _strat_channel]
         if allow_decompose:
             if (
@@ -260,23 +351,12 @@ class B200StateVectorSimulationState(SimulationState[B200StateVector]):
             f"SupportsMixture or is a measurement: {action!r}"
         )
 
-    def _perform_measurement(self, qubits: Sequence['cirq.Qid']) -> list[int]:
-        self._host_cache = None
-        return super()._perform_measurement(qubits)
-
-    def copy(self, deep_copy_buffers: bool = True):
-        out = super().copy(deep_copy_buffers)
-        out._host_cache = None
-        return out
-
     # ---- read-out ------------------------------------------------------------------------
 
     @property
     def target_tensor(self) -> np.ndarray:
         """Host copy of the state as a ``(2,)*n`` tensor (downloads 2^n amplitudes)."""
-        if self._host_cache is None:
-            self._host_cache = self._state.to_numpy_tensor()
-        return self._host_cache
+        return self._state.to_numpy_tensor()
 
     @property
     def device_state(self) -> DeviceState:
@@ -381,7 +461,7 @@ def _strat_channel(action: Any, args: B200StateVectorSimulationState, qubits) ->
         weight = fallback_weight
         index = fallback_index
     chosen._dev.scale(1.0 / np.sqrt(weight))
-    state._dev = chosen._dev
+    state.replace_device_state(chosen._dev)
     if protocols.is_measurement(action):
         key = protocols.measurement_key_obj(action)
         args._classical_data.record_channel_measurement(key, index)
@@ -508,8 +588,10 @@ class B200Simulator(
     Args:
         dtype: ``np.complex64`` or ``np.complex128``.
         noise, seed: as ``cirq.Simulator``.
-        split_untangled_states: accepted for compatibility; the device state is
-            always one dense tensor.
+        split_untangled_states: as ``cirq.Simulator`` (default True): unentangled
+            qubit sets are kept as separate device states and joined by a
+            Kronecker-product kernel when a gate couples them; ignored above
+            30 qubits.
         max_fused_qubits: widest fused block (one GPU pass each).
     """
 
@@ -526,8 +608,9 @@ class B200Simulator(
             raise ValueError(f'dtype must be a complex type but was {dtype}')
         if np.dtype(dtype) not in (np.dtype(np.complex64), np.dtype(np.complex128)):
             raise ValueError(f'dtype must be complex64 or complex128 but was {dtype}')
-        super().__init__(dtype=dtype, noise=noise, seed=seed, split_untangled_states=False)
-        self._requested_split = split_untangled_states
+        super().__init__(
+            dtype=dtype, noise=noise, seed=seed, split_untangled_states=split_untangled_states
+        )
         # None = kernel-matched policy (cirq_b200.fusion.fuser_for)
         self._max_fused = None if max_fused_qubits is None else int(max_fused_qubits)
 
@@ -542,6 +625,19 @@ class B200Simulator(
             dtype=self._dtype,
             max_fused_qubits=self._max_fused,
         )
+
+    def _create_simulation_state(self, initial_state, qubits):
+        """As SimulatorBase (sim/simulator_base.py:322-352), except that states too
+        large to be transposed out of place at the end (the product state's final
+        merge needs a second buffer of the state's size) are kept as one dense
+        tensor from the start."""
+        if self._split_untangled_states and len(qubits) > _MAX_SPLIT_QUBITS:
+            self._split_untangled_states = False
+            try:
+                return super()._create_simulation_state(initial_state, qubits)
+            finally:
+                self._split_untangled_states = True
+        return super()._create_simulation_state(initial_state, qubits)
 
     def _create_step_result(self, sim_state):
         return B200SimulatorStep(sim_state=sim_state, dtype=self._dtype)

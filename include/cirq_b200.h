@@ -155,6 +155,26 @@ int b2q_sv_collapse(void* state, int dtype, int n_qubits, const int* bits, const
 int b2q_sv_pauli_expectation(const void* state, int dtype, int n_qubits, uint64_t x_mask,
                              uint64_t z_mask, double* out_re_im, void* stream);
 
+/* ---- state layout: Kronecker product, axis permutation, factoring ---------- */
+
+/* out[(i << nb) | j] = a[i] * b[j]: linalg/transformations.py:603-613
+ * (state_vector_kronecker_product), used when unentangled sub-states are
+ * joined (sim/simulation_product_state.py:110-117) and for ancilla qubits. */
+int b2q_sv_kron(const void* a, int na, const void* b, int nb, int dtype, void* out, void* stream);
+/* out[o] = in[i] with bit k of o == bit src_bit[k] of i (out-of-place):
+ * np.moveaxis of linalg/transformations.py:743-754
+ * (transpose_state_vector_to_axis_order) in bit-position form. */
+int b2q_sv_permute_bits(const void* in, void* out, int dtype, int n_qubits, const int* src_bit,
+                        void* stream);
+/* Index of the largest |amplitude| (first one on ties): the pivot of
+ * factor_state_vector (linalg/transformations.py:677). */
+int b2q_sv_argmax_abs(const void* state, int dtype, int n_qubits, uint64_t* index_out,
+                      void* stream);
+/* *ok_out = np.allclose(kron(a, b), t, atol, rtol): the validation step of
+ * factor_state_vector (:684-690). */
+int b2q_sv_kron_allclose(const void* a, int na, const void* b, int nb, const void* t, int dtype,
+                         double atol, double rtol, int* ok_out, void* stream);
+
 /* ---- density matrix (rho as a 2n-qubit vector) ---------------------------- */
 
 /* probs_dev[i] = Re rho[i,i], float64[2^n]: sim/density_matrix_utils.py:185-192. */

@@ -115,6 +115,25 @@ class OracleDeviceState:
     def pauli_expectation(self, x_mask, z_mask):
         return orc.pauli_expectation(self.array, self.n_bits, x_mask, z_mask)
 
+    def kron(self, other):
+        return OracleDeviceState(self.n_bits + other.n_bits, self.dtype, np.kron(self.array, other.array))
+
+    def permute_bits(self, src_bit):
+        o = np.arange(1 << self.n_bits, dtype=np.int64)
+        i = np.zeros_like(o)
+        for k, sb in enumerate(src_bit):
+            i |= ((o >> k) & 1) << sb
+        return OracleDeviceState(self.n_bits, self.dtype, self.array[i])
+
+    def argmax_abs(self):
+        return int(np.argmax(np.abs(self.array.astype(np.complex128)) ** 2))
+
+    def slice_copy(self, start, n_bits):
+        return OracleDeviceState(n_bits, self.dtype, self.array[start : start + (1 << n_bits)].copy())
+
+    def kron_allclose(self, a, b, atol, rtol=1e-5):
+        return bool(np.allclose(np.kron(a.array, b.array), self.array, atol=atol, rtol=rtol))
+
     def dm_diagonal_device(self):
         return _ft(orc.dm_diagonal(self.array, self.n_bits // 2))
 

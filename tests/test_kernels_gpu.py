@@ -326,6 +326,32 @@ def test_density_matrix_golden_and_helpers(DS, dtype):
 
 
 @pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
+def test_layout_ops_kron_permute_argmax(DS, dtype):
+    rng = np.random.RandomState(71)
+    a = rand_state(rng, 3, dtype)
+    b = rand_state(rng, 5, dtype)
+    k = DS.from_numpy(a).kron(DS.from_numpy(b))
+    np.testing.assert_allclose(k.to_numpy(), np.kron(a, b), atol=ATOL[np.dtype(dtype)])
+    n = 9
+    s = rand_state(rng, n, dtype)
+    src = rng.permutation(n).tolist()
+    got = DS.from_numpy(s).permute_bits(src).to_numpy()
+    o = np.arange(1 << n)
+    i = np.zeros_like(o)
+    for kk, sb in enumerate(src):
+        i |= ((o >> kk) & 1) << sb
+    np.testing.assert_array_equal(got, s[i])
+    assert DS.from_numpy(s).argmax_abs() == int(np.argmax(np.abs(s.astype(np.complex128)) ** 2))
+    t = DS.from_numpy(np.kron(a, b))
+    assert t.kron_allclose(DS.from_numpy(a), DS.from_numpy(b), 1e-6)
+    bad = b.copy()
+    bad[3] += 0.01
+    assert not t.kron_allclose(DS.from_numpy(a), DS.from_numpy(bad), 1e-6)
+    sl = DS.from_numpy(s).slice_copy(64, 5).to_numpy()
+    np.testing.assert_array_equal(sl, s[64:96])
+
+
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
 def test_dist_pack_unpack(DS, dtype):
     import torch
 

@@ -5,7 +5,8 @@ density_matrix_simulator_test.py.
 
 Every reference test must pass except the documented exclusions:
   * qudits (dimension != 2): the kernels are qubit-only (DESIGN.md §7);
-  * split_untangled_states representation tests (one dense tensor here);
+  * density matrix only: split_untangled_states representation tests (rho is
+    one dense tensor; the state-vector simulator implements the split);
   * tests whose ad-hoc gates mutate the numpy state tensor inside
     `_apply_unitary_` (the matrix is obtained from Cirq's query protocols and
     applied on the device instead).
@@ -24,7 +25,6 @@ EXPECTED_FAIL_PREFIXES = {
     'sparse': [
         'test_run_reset',  # LineQid(dimension=3)
         'test_simulate_qudits', 'test_simulate_qudit_mixtures', 'test_qudit_invert_mask',
-        'test_pure_state_creation', 'test_separated_states_str_does_not_merge',
         'test_does_not_modify_initial_state', 'test_state_vector_copy',
     ],
     'density': [
@@ -39,7 +39,7 @@ EXPECTED_FAIL_PREFIXES = {
         'test_separated_states_str_does_not_merge',
     ],
 }
-MIN_PASSED = {'sparse': 175, 'density': 198}
+MIN_PASSED = {'sparse': 178, 'density': 198}
 
 
 def run_suite(backend, which, tmp_path):

@@ -44,6 +44,14 @@ def SV(backend):
     return cirq_b200.B200Simulator
 
 
+@pytest.fixture(params=[False, True], ids=['dense', 'split'])
+def split(request):
+    """split_untangled_states, applied to BOTH simulators in seeded comparisons:
+    the random stream is consumed per unentangled factor, so seeded results
+    agree between simulators configured alike."""
+    return request.param
+
+
 @pytest.fixture(scope='module')
 def DM(backend):
     import cirq_b200
@@ -103,15 +111,15 @@ def test_qubit_order_and_initial_states(cirq, SV):
     got = SV().simulate(circuit, initial_state=(1, 0, 1))
     np.testing.assert_allclose(got.final_state_vector, want.final_state_vector, atol=1e-6)
     with pytest.raises(ValueError):
-        SV().simulate(circuit, initial_state=8)
+        SV(split_untangled_states=False).simulate(circuit, initial_state=8)
 
 
-def test_run_terminal_measurements_seeded_like_reference(cirq, SV):
+def test_run_terminal_measurements_seeded_like_reference(cirq, SV, split):
     qubits = cirq.LineQubit.range(6)
     circuit = cirq.testing.random_circuit(qubits, 8, 0.9, random_state=7)
     circuit.append(cirq.measure(*qubits, key='m'))
-    want = cirq.Simulator(seed=11, split_untangled_states=False).run(circuit, repetitions=400)
-    got = SV(seed=11).run(circuit, repetitions=400)
+    want = cirq.Simulator(seed=11, split_untangled_states=split).run(circuit, repetitions=400)
+    got = SV(seed=11, split_untangled_states=split).run(circuit, repetitions=400)
     w, g = want.measurements['m'], got.measurements['m']
     assert g.shape == w.shape and g.dtype == w.dtype
     assert np.mean(np.any(w != g, axis=1)) <= 0.01
@@ -123,8 +131,8 @@ def test_run_terminal_measurements_seeded_like_reference(cirq, SV):
             cirq.measure(qubits[0], key='b'),
         ]
     )
-    want = cirq.Simulator(seed=3, split_untangled_states=False).run(circuit2, repetitions=300)
-    got = SV(seed=3).run(circuit2, repetitions=300)
+    want = cirq.Simulator(seed=3, split_untangled_states=split).run(circuit2, repetitions=300)
+    got = SV(seed=3, split_untangled_states=split).run(circuit2, repetitions=300)
     for key in ('a', 'b'):
         assert got.measurements[key].shape == want.measurements[key].shape
         assert np.mean(np.any(want.measurements[key] != got.measurements[key], axis=1)) <= 0.01
@@ -146,7 +154,7 @@ def test_run_histogram_chi_squared(cirq, SV):
     assert hist[~mask].sum() <= 6 * max(1.0, (probs[~mask] * reps).sum()) + 5
 
 
-def test_mid_circuit_measurement_classical_control_reset(cirq, SV):
+def test_mid_circuit_measurement_classical_control_reset(cirq, SV, split):
     a, b = cirq.LineQubit.range(2)
     circuit = cirq.Circuit(
         cirq.H(a),
@@ -156,8 +164,8 @@ def test_mid_circuit_measurement_classical_control_reset(cirq, SV):
         cirq.reset(a),
         cirq.measure(a, key='z'),
     )
-    want = cirq.Simulator(seed=5, split_untangled_states=False).run(circuit, repetitions=60)
-    got = SV(seed=5).run(circuit, repetitions=60)
+    want = cirq.Simulator(seed=5, split_untangled_states=split).run(circuit, repetitions=60)
+    got = SV(seed=5, split_untangled_states=split).run(circuit, repetitions=60)
     for k in ('x', 'y', 'z'):
         np.testing.assert_array_equal(got.measurements[k], want.measurements[k])
         assert got.measurements[k].dtype == want.measurements[k].dtype
@@ -171,12 +179,14 @@ def test_mid_circuit_measurement_classical_control_reset(cirq, SV):
     np.testing.assert_allclose(got.final_state_vector, want.final_state_vector, atol=1e-6)
 
 
-def test_simulate_moment_steps_matches_reference(cirq, SV):
+def test_simulate_moment_steps_matches_reference(cirq, SV, split):
     qubits = cirq.LineQubit.range(4)
     circuit = cirq.testing.random_circuit(qubits, 6, 0.9, random_state=31)
     circuit.append(cirq.measure(qubits[0], qubits[2], key='m'))
-    ref_steps = cirq.Simulator(seed=2, split_untangled_states=False).simulate_moment_steps(circuit, qubit_order=qubits)
-    steps = SV(seed=2).simulate_moment_steps(circuit, qubit_order=qubits)
+    ref_steps = cirq.Simulator(seed=2, split_untangled_states=split).simulate_moment_steps(circuit, qubit_order=qubits)
+    steps = SV(seed=2, split_untangled_states=split).simulate_moment_steps(
+        circuit, qubit_order=qubits
+    )
     count = 0
     for i, (step, ref) in enumerate(zip(steps, ref_steps)):
         np.testing.assert_allclose(step.state_vector(), ref.state_vector(), atol=1e-6)
@@ -190,7 +200,7 @@ def test_simulate_moment_steps_matches_reference(cirq, SV):
     assert step.dirac_notation() == ref.dirac_notation()
 
 
-def test_param_sweeps(cirq, SV):
+def test_param_sweeps(cirq, SV, split):
     q = cirq.LineQubit.range(3)
     t, s = sympy.Symbol('t'), sympy.Symbol('s')
     circuit = cirq.Circuit(
@@ -204,19 +214,17 @@ def test_param_sweeps(cirq, SV):
         assert g.params == w.params
         np.testing.assert_allclose(g.final_state_vector, w.final_state_vector, atol=1e-6)
     circuit.append(cirq.measure(*q, key='m'))
-    # seeded parity is with the unsplit reference: with split_untangled_states=True the
-    # reference samples each unentangled factor separately (same distribution, other stream)
-    want = cirq.Simulator(seed=9, split_untangled_states=False).run_sweep(
+    want = cirq.Simulator(seed=9, split_untangled_states=split).run_sweep(
         circuit, sweep, repetitions=50
     )
-    got = SV(seed=9).run_sweep(circuit, sweep, repetitions=50)
+    got = SV(seed=9, split_untangled_states=split).run_sweep(circuit, sweep, repetitions=50)
     for g, w in zip(got, want):
         np.testing.assert_array_equal(g.measurements['m'], w.measurements['m'])
     with pytest.raises(ValueError, match='symbols'):
         SV().simulate(circuit)
 
 
-def test_noisy_state_vector_trajectories_seeded(cirq, SV):
+def test_noisy_state_vector_trajectories_seeded(cirq, SV, split):
     q = cirq.LineQubit.range(3)
     circuit = cirq.Circuit(
         cirq.H(q[0]),
@@ -226,11 +234,13 @@ def test_noisy_state_vector_trajectories_seeded(cirq, SV):
         cirq.depolarize(0.2).on(q[2]),
         cirq.measure(*q, key='m'),
     )
-    want = cirq.Simulator(seed=17, split_untangled_states=False).run(circuit, repetitions=80)
-    got = SV(seed=17).run(circuit, repetitions=80)
+    want = cirq.Simulator(seed=17, split_untangled_states=split).run(circuit, repetitions=80)
+    got = SV(seed=17, split_untangled_states=split).run(circuit, repetitions=80)
     np.testing.assert_array_equal(got.measurements['m'], want.measurements['m'])
-    want = cirq.Simulator(seed=4, noise=cirq.depolarize(0.1), split_untangled_states=False).run(circuit, repetitions=40)
-    got = SV(seed=4, noise=cirq.depolarize(0.1)).run(circuit, repetitions=40)
+    want = cirq.Simulator(seed=4, noise=cirq.depolarize(0.1), split_untangled_states=split).run(circuit, repetitions=40)
+    got = SV(seed=4, noise=cirq.depolarize(0.1), split_untangled_states=split).run(
+        circuit, repetitions=40
+    )
     np.testing.assert_array_equal(got.measurements['m'], want.measurements['m'])
 
 
@@ -289,11 +299,11 @@ def test_errors_match_reference(cirq, SV):
         SV().simulate(cirq.Circuit(cirq.IdentityGate(qid_shape=(3,)).on(cirq.LineQid(0, 3))))
 
 
-def test_repeated_keys_and_empty_circuit(cirq, SV):
+def test_repeated_keys_and_empty_circuit(cirq, SV, split):
     q = cirq.LineQubit.range(2)
     circuit = cirq.Circuit(cirq.X(q[0]), cirq.measure(q[0], key='k'), cirq.measure(q[1], key='k'))
-    want = cirq.Simulator(seed=1, split_untangled_states=False).run(circuit, repetitions=7)
-    got = SV(seed=1).run(circuit, repetitions=7)
+    want = cirq.Simulator(seed=1, split_untangled_states=split).run(circuit, repetitions=7)
+    got = SV(seed=1, split_untangled_states=split).run(circuit, repetitions=7)
     np.testing.assert_array_equal(got.records['k'], want.records['k'])
     assert got.records['k'].shape == (7, 2, 1)
     res = SV().simulate(cirq.Circuit(), qubit_order=q)
