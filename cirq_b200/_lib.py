@@ -72,6 +72,12 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_double, c_double, POINTER(c_int), c_void_p],
     ),
+    'b2q_sv_allclose': (
+        c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_double, POINTER(c_int), c_void_p]
+    ),
+    'b2q_dm_partial_trace': (
+        c_int, [c_void_p, c_int, c_int, POINTER(c_int), c_int, c_void_p, c_void_p]
+    ),
     'b2q_dm_diagonal': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'b2q_probs_marginal': (c_int, [c_void_p, c_int, POINTER(c_int), c_int, c_void_p, c_void_p]),
     'b2q_dm_trace': (c_int, [c_void_p, c_int, c_int, POINTER(c_double), c_void_p]),

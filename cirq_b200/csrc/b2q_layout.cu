@@ -111,6 +111,64 @@ __global__ void __launch_bounds__(256)
   if (bad) atomicExch(flag, 1);
 }
 
+struct PartialTraceParams {
+  int n;          // qubits of rho
+  int k;          // kept qubits
+  int keep[20];   // kept column-bit positions, keep[0] = MSB of the output index
+  int traced[20]; // traced column-bit positions (any order)
+};
+
+// out[(R << k) | C] = sum_x rho[row(R, x), col(C, x)]; one warp per output element.
+template <typename real>
+__global__ void __launch_bounds__(256)
+    dm_partial_trace_kernel(const typename Cplx<real>::type* __restrict__ rho,
+                            typename Cplx<real>::type* __restrict__ out,
+                            const __grid_constant__ PartialTraceParams p) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t o = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint64_t total_out = 1ull << (2 * p.k);
+  if (o >= total_out) return;
+  const uint64_t R = o >> p.k, C = o & ((1ull << p.k) - 1ull);
+  uint64_t rbase = 0, cbase = 0;
+  for (int q = 0; q < p.k; ++q) {
+    rbase |= ((R >> (p.k - 1 - q)) & 1ull) << p.keep[q];
+    cbase |= ((C >> (p.k - 1 - q)) & 1ull) << p.keep[q];
+  }
+  const int nt = p.n - p.k;
+  double ar = 0.0, ai = 0.0;
+  for (uint64_t x = lane; x < (1ull << nt); x += 32) {
+    uint64_t dep = 0;
+    for (int t = 0; t < nt; ++t) dep |= ((x >> t) & 1ull) << p.traced[t];
+    const auto v = rho[((rbase | dep) << p.n) | (cbase | dep)];
+    ar += (double)v.x;
+    ai += (double)v.y;
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    ar += __shfl_xor_sync(0xffffffffu, ar, s);
+    ai += __shfl_xor_sync(0xffffffffu, ai, s);
+  }
+  if (lane == 0) out[o] = make_c<real>((real)ar, (real)ai);
+}
+
+// flag[0] = 1 if some |a[i] - b[i]| > atol + rtol*|b[i]|  (np.allclose(a, b))
+template <typename real>
+__global__ void __launch_bounds__(256)
+    sv_mismatch_kernel(const typename Cplx<real>::type* __restrict__ a,
+                       const typename Cplx<real>::type* __restrict__ b, uint64_t total,
+                       double atol, double rtol, int* __restrict__ flag) {
+  bool bad = false;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const auto x = a[i];
+    const auto y = b[i];
+    const double dr = (double)x.x - (double)y.x, di = (double)x.y - (double)y.y;
+    if (sqrt(dr * dr + di * di) > atol + rtol * sqrt((double)y.x * y.x + (double)y.y * y.y))
+      bad = true;
+  }
+  if (bad) atomicExch(flag, 1);
+}
+
 inline unsigned layout_grid(uint64_t total) {
   return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((total + 255) / 256, 148ull * 64));
 }
@@ -216,6 +274,63 @@ extern "C" int b2q_sv_kron_allclose(const void* a, int na, const void* b, int nb
         reinterpret_cast<const double2*>(a), reinterpret_cast<const double2*>(b), nb,
         reinterpret_cast<const double2*>(t), total, atol, rtol, flag);
   B2Q_LAUNCH_CHECK("sv_kron_mismatch_kernel");
+  int h = 0;
+  B2Q_CUDA_CHECK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  B2Q_CUDA_CHECK(cudaStreamSynchronize(s));
+  *ok_out = h ? 0 : 1;
+  return B2Q_OK;
+}
+
+extern "C" int b2q_dm_partial_trace(const void* rho, int dtype, int n_qubits, const int* keep_bits,
+                                    int k, void* out, void* stream) {
+  B2Q_REQUIRE(rho != nullptr && out != nullptr && (k == 0 || keep_bits != nullptr), "null argument");
+  B2Q_REQUIRE(dtype == B2Q_C64 || dtype == B2Q_C128, "bad dtype %d", dtype);
+  B2Q_REQUIRE(n_qubits >= 0 && n_qubits <= 20 && k >= 0 && k <= n_qubits, "sizes out of range");
+  PartialTraceParams p;
+  p.n = n_qubits;
+  p.k = k;
+  uint64_t seen = 0;
+  for (int q = 0; q < k; ++q) {
+    B2Q_REQUIRE(keep_bits[q] >= 0 && keep_bits[q] < n_qubits, "bit out of range");
+    B2Q_REQUIRE(!((seen >> keep_bits[q]) & 1ull), "duplicate bit");
+    seen |= 1ull << keep_bits[q];
+    p.keep[q] = keep_bits[q];
+  }
+  int t = 0;
+  for (int b = 0; b < n_qubits; ++b)
+    if (!((seen >> b) & 1ull)) p.traced[t++] = b;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const uint64_t total_out = 1ull << (2 * k);
+  const uint64_t blocks = (total_out + 7) / 8;
+  B2Q_REQUIRE(blocks <= 0x7fffffffull, "grid too large");
+  if (dtype == B2Q_C64)
+    dm_partial_trace_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(
+        reinterpret_cast<const float2*>(rho), reinterpret_cast<float2*>(out), p);
+  else
+    dm_partial_trace_kernel<double><<<(unsigned)blocks, 256, 0, s>>>(
+        reinterpret_cast<const double2*>(rho), reinterpret_cast<double2*>(out), p);
+  B2Q_LAUNCH_CHECK("dm_partial_trace_kernel");
+  return B2Q_OK;
+}
+
+extern "C" int b2q_sv_allclose(const void* a, const void* b, int dtype, int n_qubits, double atol,
+                               double rtol, int* ok_out, void* stream) {
+  B2Q_REQUIRE(a && b && ok_out, "null argument");
+  B2Q_REQUIRE(dtype == B2Q_C64 || dtype == B2Q_C128, "bad dtype %d", dtype);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const uint64_t total = 1ull << n_qubits;
+  int* flag = reinterpret_cast<int*>(workspace(sizeof(int)));
+  if (flag == nullptr) return B2Q_ERR_CUDA;
+  B2Q_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), s));
+  if (dtype == B2Q_C64)
+    sv_mismatch_kernel<float><<<layout_grid(total), 256, 0, s>>>(
+        reinterpret_cast<const float2*>(a), reinterpret_cast<const float2*>(b), total, atol, rtol,
+        flag);
+  else
+    sv_mismatch_kernel<double><<<layout_grid(total), 256, 0, s>>>(
+        reinterpret_cast<const double2*>(a), reinterpret_cast<const double2*>(b), total, atol,
+        rtol, flag);
+  B2Q_LAUNCH_CHECK("sv_mismatch_kernel");
   int h = 0;
   B2Q_CUDA_CHECK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
   B2Q_CUDA_CHECK(cudaStreamSynchronize(s));

@@ -46,6 +46,13 @@ class DeviceState:
         self.code = _lib.dtype_code(self.dtype)
         self._real = torch.float32 if self.code == _lib.C64 else torch.float64
         if tensor is None:
+            nbytes = (1 << self.n_bits) * (8 if self.code == _lib.C64 else 16)
+            if self.n_bits > 40 or nbytes > torch.cuda.get_device_properties(0).total_memory:
+                # same exception type and wording as numpy's allocation failure in the
+                # reference (its tests match on it)
+                raise MemoryError(
+                    f'Unable to allocate {nbytes} bytes for a {self.n_bits}-bit state in HBM'
+                )
             tensor = torch.empty((1 << self.n_bits, 2), dtype=self._real, device='cuda')
         self.tensor = tensor
         self._lib = _lib.load()
@@ -344,6 +351,32 @@ class DeviceState:
             )
         )
         return bool(ok.value)
+
+    def allclose(self, other: 'DeviceState', atol: float, rtol: float = 1e-5) -> bool:
+        """np.allclose(self, other, atol=atol, rtol=rtol) on the device."""
+        torch = _torch()
+        ok = ctypes.c_int(0)
+        check(
+            self._lib.b2q_sv_allclose(
+                self.ptr, other.ptr, self.code, self.n_bits, float(atol), float(rtol),
+                ctypes.byref(ok), _stream_ptr(torch),
+            )
+        )
+        return bool(ok.value)
+
+    def dm_partial_trace(self, keep_bits: Sequence[int]) -> 'DeviceState':
+        """Reduced density matrix on the qubits whose column bits are `keep_bits`
+        (keep_bits[0] = most significant qubit of the result)."""
+        torch = _torch()
+        k = len(keep_bits)
+        out = DeviceState(2 * k, self.dtype)
+        check(
+            self._lib.b2q_dm_partial_trace(
+                self.ptr, self.code, self.n_bits // 2, _lib.int_array(keep_bits), k, out.ptr,
+                _stream_ptr(torch),
+            )
+        )
+        return out
 
     # ------------------------------------------------------------------ density matrix view
 

@@ -16,7 +16,8 @@ kernels as the state-vector path:
 
 Operations are queued and fused exactly as in the state-vector simulator, so
 e.g. a 2-qubit gate followed by depolarising noise on both qubits is a single
-4-"qubit" pass over rho.
+4-"qubit" pass over rho.  ``split_untangled_states`` is honoured through device
+kron / partial-trace / axis-permutation kernels (``kron``, ``factor``, ``reindex``).
 """
 from __future__ import annotations
 
@@ -54,6 +55,7 @@ class B200DensityMatrix(qis.QuantumStateRepresentation):
         self.passes = 0
         self._since_drain = 0
         self._drain_every = max(8, 2 * self._n)
+        self._host = None  # cached host copy, dropped on every mutation
 
     @classmethod
     def create(cls, *, initial_state: Any = 0, qid_shape, dtype=np.complex64, max_fused_qubits=None):
@@ -87,6 +89,7 @@ class B200DensityMatrix(qis.QuantumStateRepresentation):
     # ---- queue ------------------------------------------------------------------------------
 
     def queue_unitary(self, u: np.ndarray, axes: Sequence[int]) -> None:
+        self._host = None
         if len(axes) == 0:
             return  # |c|^2 = 1 for a unitary scalar: rho is unchanged
         u = np.asarray(u, dtype=np.complex128)
@@ -95,6 +98,7 @@ class B200DensityMatrix(qis.QuantumStateRepresentation):
         self._maybe_drain(2)
 
     def queue_kraus(self, kraus_ops: Sequence[np.ndarray], axes: Sequence[int]) -> None:
+        self._host = None
         k = len(axes)
         if k == 0:
             scale = sum(abs(complex(np.asarray(op).reshape(-1)[0])) ** 2 for op in kraus_ops)
@@ -150,6 +154,7 @@ class B200DensityMatrix(qis.QuantumStateRepresentation):
         if not axes:
             return []
         self.flush()
+        self._host = None
         prng = value.parse_random_state(seed)
         m = len(axes)
         u = float(prng.random_sample())
@@ -181,15 +186,80 @@ class B200DensityMatrix(qis.QuantumStateRepresentation):
 
     @property
     def supports_factor(self) -> bool:
-        return False
+        return True
 
     @property
     def can_represent_mixed_states(self) -> bool:
         return True
 
-    def to_numpy_tensor(self) -> np.ndarray:
+    # ---- layout: Kronecker product, factoring, axis order (split_untangled_states) ----------
+
+    def kron(self, other: 'B200DensityMatrix') -> 'B200DensityMatrix':
+        """``density_matrix_kronecker_product`` (linalg/transformations.py:616-644):
+        vec(rho) (x) vec(sigma) has bits [r1 c1 r2 c2]; regroup to [r1 r2 c1 c2]."""
+        n1, n2 = self._n, other._n
+        k = self.device_state.kron(other.device_state)
+        src = [0] * (2 * (n1 + n2))
+        for j in range(n2):  # c2
+            src[j] = j
+        for j in range(n1):  # c1
+            src[n2 + j] = 2 * n2 + j
+        for j in range(n2):  # r2
+            src[n1 + n2 + j] = n2 + j
+        for j in range(n1):  # r1
+            src[n1 + 2 * n2 + j] = 2 * n2 + n1 + j
+        dev = k if src == list(range(len(src))) else k.permute_bits(src)
+        out = B200DensityMatrix(dev, n1 + n2, self._max_fused)
+        out.passes = self.passes + other.passes
+        return out
+
+    def reindex(self, axes: Sequence[int]) -> 'B200DensityMatrix':
+        """``transpose_density_matrix_to_axis_order``: new axis k = old axis axes[k],
+        on rows and columns alike."""
+        axes = [int(a) for a in axes]
+        n = self._n
+        if axes == list(range(n)):
+            return B200DensityMatrix(self.device_state.copy(), n, self._max_fused)
+        src = [0] * (2 * n)
+        for k, a in enumerate(axes):
+            src[n - 1 - k] = n - 1 - a  # column bits
+            src[2 * n - 1 - k] = 2 * n - 1 - a  # row bits
+        out = B200DensityMatrix(self.device_state.permute_bits(src), n, self._max_fused)
+        out.passes = self.passes
+        return out
+
+    def factor(self, axes: Sequence[int], *, validate=True, atol=1e-07):
+        """``factor_density_matrix`` (linalg/transformations.py:694-727): the two
+        factors are the partial traces onto `axes` and onto the rest."""
+        axes = [int(a) for a in axes]
+        n = self._n
+        rest = [a for a in range(n) if a not in axes]
+        dev = self.device_state
+        extracted = dev.dm_partial_trace([n - 1 - a for a in axes])
+        remainder = dev.dm_partial_trace([n - 1 - a for a in rest])
+        e_state = B200DensityMatrix(extracted, len(axes), self._max_fused)
+        r_state = B200DensityMatrix(remainder, len(rest), self._max_fused)
+        r_state.passes = self.passes
+        if validate:
+            product = e_state.kron(r_state)  # axes order: axes + rest
+            order = axes + rest
+            inverse = [order.index(a) for a in range(n)]
+            back = product.reindex(inverse)
+            if not back.device_state.allclose(dev, atol):
+                raise ValueError('The tensor cannot be factored by the requested axes')
+        return e_state, r_state
+
+    def scale(self, factor: complex) -> None:
         self.flush()
-        return self._dev.to_numpy().reshape(self._qid_shape * 2)
+        self._host = None
+        self._dev.scale(factor)
+
+    def to_numpy_tensor(self) -> np.ndarray:
+        """Host copy as a ``(2,)*2n`` tensor, cached until the state changes."""
+        if self._host is None:
+            self.flush()
+            self._host = self._dev.to_numpy().reshape(self._qid_shape * 2)
+        return self._host
 
 
 class B200DensityMatrixSimulationState(SimulationState[B200DensityMatrix]):
@@ -214,10 +284,30 @@ class B200DensityMatrixSimulationState(SimulationState[B200DensityMatrix]):
             max_fused_qubits=max_fused_qubits,
         )
         super().__init__(state=state, prng=prng, qubits=qubits, classical_data=classical_data)
-        self._host_cache = None
+        self._dtype = dtype
+        self._max_fused_qubits = max_fused_qubits
+
+    def add_qubits(self, qubits):
+        """(density_matrix_simulation_state.py:289-295)"""
+        ret = super().add_qubits(qubits)
+        if ret is not NotImplemented:
+            return ret
+        fresh = type(self)(
+            qubits=qubits, dtype=self._dtype, prng=self._prng,
+            max_fused_qubits=self._max_fused_qubits,
+        )
+        return self.kronecker_product(fresh, inplace=True)
+
+    def remove_qubits(self, qubits):
+        """(density_matrix_simulation_state.py:297-303)"""
+        ret = super().remove_qubits(qubits)
+        if ret is not NotImplemented:
+            return ret
+        extracted, remainder = self.factor(qubits, inplace=True)
+        remainder._state.scale(complex(extracted._state.device_state.amplitudes([0])[0]))
+        return remainder
 
     def _act_on_fallback_(self, action: Any, qubits, allow_decompose: bool = True) -> bool:
-        self._host_cache = None
         strats = [_strat_apply_channel]
         if allow_decompose:
             strats.append(strat_act_on_from_apply_decompose)
@@ -232,20 +322,9 @@ class B200DensityMatrixSimulationState(SimulationState[B200DensityMatrix]):
             f"SupportsMixture or SupportsKraus or is a measurement: {action!r}"
         )
 
-    def _perform_measurement(self, qubits) -> list[int]:
-        self._host_cache = None
-        return super()._perform_measurement(qubits)
-
-    def copy(self, deep_copy_buffers: bool = True):
-        out = super().copy(deep_copy_buffers)
-        out._host_cache = None
-        return out
-
     @property
     def target_tensor(self) -> np.ndarray:
-        if self._host_cache is None:
-            self._host_cache = self._state.to_numpy_tensor()
-        return self._host_cache
+        return self._state.to_numpy_tensor()
 
     @property
     def device_state(self) -> DeviceState:
@@ -319,7 +398,9 @@ class B200DensityMatrixSimulator(
         split_untangled_states: bool = True,
         max_fused_qubits: int | None = None,
     ):
-        super().__init__(dtype=dtype, noise=noise, seed=seed, split_untangled_states=False)
+        super().__init__(
+            dtype=dtype, noise=noise, seed=seed, split_untangled_states=split_untangled_states
+        )
         if dtype not in {np.complex64, np.complex128}:
             raise ValueError(f'dtype must be complex64 or complex128, was {dtype}')
         self._max_fused = None if max_fused_qubits is None else int(max_fused_qubits)

@@ -175,7 +175,17 @@ int b2q_sv_argmax_abs(const void* state, int dtype, int n_qubits, uint64_t* inde
 int b2q_sv_kron_allclose(const void* a, int na, const void* b, int nb, const void* t, int dtype,
                          double atol, double rtol, int* ok_out, void* stream);
 
+/* *ok_out = np.allclose(a, b, atol, rtol) for two states of n_qubits. */
+int b2q_sv_allclose(const void* a, const void* b, int dtype, int n_qubits, double atol,
+                    double rtol, int* ok_out, void* stream);
+
 /* ---- density matrix (rho as a 2n-qubit vector) ---------------------------- */
+
+/* out = Tr_rest(rho) over every qubit whose column bit is not in `keep_bits`
+ * (keep_bits[0] = most significant qubit of the k-qubit result): the
+ * partial_trace calls of factor_density_matrix (linalg/transformations.py:694-727). */
+int b2q_dm_partial_trace(const void* rho, int dtype, int n_qubits, const int* keep_bits, int k,
+                         void* out, void* stream);
 
 /* probs_dev[i] = Re rho[i,i], float64[2^n]: sim/density_matrix_utils.py:185-192. */
 int b2q_dm_diagonal(const void* rho, int dtype, int n_qubits, double* probs_dev, void* stream);

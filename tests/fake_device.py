@@ -28,6 +28,8 @@ class OracleDeviceState:
     def __init__(self, n_bits, dtype, array=None):
         self.n_bits = int(n_bits)
         self.dtype = np.dtype(dtype)
+        if array is None and self.n_bits > 34:
+            raise MemoryError(f'Unable to allocate a {self.n_bits}-bit state')
         self.array = (
             np.zeros(1 << self.n_bits, dtype=self.dtype) if array is None else np.array(array, dtype=self.dtype)
         )
@@ -133,6 +135,23 @@ class OracleDeviceState:
 
     def kron_allclose(self, a, b, atol, rtol=1e-5):
         return bool(np.allclose(np.kron(a.array, b.array), self.array, atol=atol, rtol=rtol))
+
+    def allclose(self, other, atol, rtol=1e-5):
+        return bool(np.allclose(self.array, other.array, atol=atol, rtol=rtol))
+
+    def dm_partial_trace(self, keep_bits):
+        n = self.n_bits // 2
+        k = len(keep_bits)
+        rho = self.array.reshape((2,) * (2 * n))
+        # axis of column bit b is (2n-1-b); row bit b+n is axis (n-1-b)
+        keep_axes = [n - 1 - b for b in keep_bits]
+        traced = [a for a in range(n) if a not in keep_axes]
+        letters = 'abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOP'
+        rows = [letters[a] for a in range(n)]
+        cols = [letters[n + a] if a in keep_axes else letters[a] for a in range(n)]
+        out = [letters[a] for a in keep_axes] + [letters[n + a] for a in keep_axes]
+        res = np.einsum(''.join(rows + cols) + '->' + ''.join(out), rho)
+        return OracleDeviceState(2 * k, self.dtype, res.reshape(-1))
 
     def dm_diagonal_device(self):
         return _ft(orc.dm_diagonal(self.array, self.n_bits // 2))

@@ -399,3 +399,24 @@ def test_full_size_properties_30q(DS):
     hist = np.bincount((idx >> np.uint64(26)).astype(np.int64), minlength=16)
     chi2 = np.sum((hist - 256.0) ** 2 / 256.0)
     assert chi2 < 15 + 6 * np.sqrt(30) + 10
+    # a non-uniform 30-qubit state: 1M samples against the state's own exact
+    # 12-qubit marginal (device reduction), the check BASELINE asks for at 30 q
+    dev.apply_batch(gates)
+    bits = [29, 3, 17, 0, 22, 9, 11, 28, 5, 14, 1, 20]
+    probs = dev.marginal_probs(bits)
+    probs = probs / probs.sum()
+    reps = 1_000_000
+    samples = dev.sample_bits(bits, rng.random_sample(reps))
+    keys = samples.astype(np.int64) @ (1 << np.arange(len(bits) - 1, -1, -1))
+    hist = np.bincount(keys, minlength=1 << len(bits))
+    mask = probs * reps > 5
+    chi2 = np.sum((hist[mask] - probs[mask] * reps) ** 2 / (probs[mask] * reps))
+    dof = int(mask.sum()) - 1
+    assert chi2 < dof + 6 * np.sqrt(2 * dof) + 10, (chi2, dof)
+    full = dev.sample_indices(rng.random_sample(reps))
+    keys = np.zeros(reps, dtype=np.int64)
+    for b in bits:
+        keys = (keys << 1) | ((full >> np.uint64(b)) & np.uint64(1)).astype(np.int64)
+    hist = np.bincount(keys, minlength=1 << len(bits))
+    chi2 = np.sum((hist[mask] - probs[mask] * reps) ** 2 / (probs[mask] * reps))
+    assert chi2 < dof + 6 * np.sqrt(2 * dof) + 10, (chi2, dof)

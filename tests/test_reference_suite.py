@@ -5,8 +5,6 @@ density_matrix_simulator_test.py.
 
 Every reference test must pass except the documented exclusions:
   * qudits (dimension != 2): the kernels are qubit-only (DESIGN.md §7);
-  * density matrix only: split_untangled_states representation tests (rho is
-    one dense tensor; the state-vector simulator implements the split);
   * tests whose ad-hoc gates mutate the numpy state tensor inside
     `_apply_unitary_` (the matrix is obtained from Cirq's query protocols and
     applied on the device instead).
@@ -35,11 +33,10 @@ EXPECTED_FAIL_PREFIXES = {
         'test_simulate_qudit_increments', 'test_simulate_initial_qudit_state',
         'test_simulate_measure_multiple_qudits', 'test_simulate_moment_steps_qudits',
         'test_simulate_moment_steps_sample_qudits', 'test_simulate_with_invert_mask',
-        'test_density_matrix_copy', 'test_large_untangled_okay',
-        'test_separated_states_str_does_not_merge',
+        'test_density_matrix_copy',
     ],
 }
-MIN_PASSED = {'sparse': 178, 'density': 198}
+MIN_PASSED = {'sparse': 178, 'density': 202}
 
 
 def run_suite(backend, which, tmp_path):

@@ -359,7 +359,7 @@ def test_density_matrix_equals_state_vector_outer_product(cirq, DM):
     np.testing.assert_allclose(rho, np.outer(psi, psi.conj()), atol=1e-10)
 
 
-def test_density_matrix_run_and_measurement_seeded(cirq, DM):
+def test_density_matrix_run_and_measurement_seeded(cirq, DM, split):
     q = cirq.LineQubit.range(3)
     circuit = cirq.Circuit(
         cirq.H(q[0]),
@@ -370,9 +370,11 @@ def test_density_matrix_run_and_measurement_seeded(cirq, DM):
         cirq.measure(q[1], key='b', invert_mask=(True,)),
     )
     want = cirq.DensityMatrixSimulator(
-        seed=6, noise=cirq.depolarize(0.05), split_untangled_states=False
+        seed=6, noise=cirq.depolarize(0.05), split_untangled_states=split
     ).run(circuit, repetitions=200)
-    got = DM(seed=6, noise=cirq.depolarize(0.05)).run(circuit, repetitions=200)
+    got = DM(seed=6, noise=cirq.depolarize(0.05), split_untangled_states=split).run(
+        circuit, repetitions=200
+    )
     for k in ('a', 'b'):
         assert got.measurements[k].dtype == want.measurements[k].dtype
         assert np.mean(np.any(got.measurements[k] != want.measurements[k], axis=1)) <= 0.01
@@ -381,15 +383,17 @@ def test_density_matrix_run_and_measurement_seeded(cirq, DM):
         cirq.H(q[0]), cirq.CNOT(q[0], q[1]), cirq.measure(q[0], key='m'), cirq.H(q[2]),
         cirq.X(q[2]).with_classical_controls('m'),
     )
-    want = cirq.DensityMatrixSimulator(seed=8, split_untangled_states=False).simulate(c2, qubit_order=q)
-    got = DM(seed=8).simulate(c2, qubit_order=q)
+    want = cirq.DensityMatrixSimulator(seed=8, split_untangled_states=split).simulate(
+        c2, qubit_order=q
+    )
+    got = DM(seed=8, split_untangled_states=split).simulate(c2, qubit_order=q)
     assert dict(got.measurements) == dict(want.measurements) or np.array_equal(
         got.measurements['m'], want.measurements['m']
     )
     np.testing.assert_allclose(got.final_density_matrix, want.final_density_matrix, atol=1e-6)
 
 
-def test_density_matrix_sweep_qaoa_style(cirq, DM):
+def test_density_matrix_sweep_qaoa_style(cirq, DM, split):
     """BASELINE config 5 shape at a CPU-friendly size: noisy QAOA, run_sweep."""
     q = cirq.LineQubit.range(4)
     beta, gamma = sympy.Symbol('beta0'), sympy.Symbol('gamma0')
@@ -400,11 +404,13 @@ def test_density_matrix_sweep_qaoa_style(cirq, DM):
     circuit.append(cirq.measure(*q, key='m'))
     sweep = cirq.Zip(cirq.Linspace('beta0', 0.1, 0.9, 4), cirq.Linspace('gamma0', 0.2, 0.8, 4))
     want = cirq.DensityMatrixSimulator(
-        noise=cirq.depolarize(0.01), seed=0, split_untangled_states=False
+        noise=cirq.depolarize(0.01), seed=0, split_untangled_states=split
     ).run_sweep(
         circuit, sweep, repetitions=100
     )
-    got = DM(noise=cirq.depolarize(0.01), seed=0).run_sweep(circuit, sweep, repetitions=100)
+    got = DM(noise=cirq.depolarize(0.01), seed=0, split_untangled_states=split).run_sweep(
+        circuit, sweep, repetitions=100
+    )
     assert len(got) == 4
     for g, w in zip(got, want):
         assert g.params == w.params
