@@ -411,6 +411,7 @@ class B200ShardedSimulator:
 
     def _gates(self, circuit, qubits):
         from cirq_b200._cirq_compat import import_cirq
+        from cirq_b200.sv_simulator import cached_unitary
 
         cirq = import_cirq()
         n = len(qubits)
@@ -423,9 +424,10 @@ class B200ShardedSimulator:
                     continue
                 if measured and any(q in {x for m in measured for x in m.qubits} for q in op.qubits):
                     raise ValueError('B200ShardedSimulator only supports terminal measurements')
-                if not cirq.has_unitary(op):
+                u = cached_unitary(op)
+                if u is None:
                     raise TypeError(f"B200ShardedSimulator doesn't support {op!r}")
-                gates.append((cirq.unitary(op), [n - 1 - axis[q] for q in op.qubits]))
+                gates.append((u, [n - 1 - axis[q] for q in op.qubits]))
         return gates, measured
 
     def simulate_sharded(self, circuit, qubit_order=None, initial_state: int = 0) -> ShardedStateVector:
