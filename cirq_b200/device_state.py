@@ -259,26 +259,33 @@ class DeviceState:
             )
         return out
 
-    def sample_bits(self, bits: Sequence[int], uniforms: np.ndarray) -> np.ndarray:
+    def sample_bits(self, bits: Sequence[int], uniforms: np.ndarray,
+                    out_columns: Sequence[int] | None = None) -> np.ndarray:
         """uint8[reps, len(bits)] drawn from |psi|^2; mirrors sample_state_vector.
 
         All bits in natural order -> hierarchical sampler on the full state
         (same CDF order as the reference); up to 24 bits -> marginal in the
         requested order (again the reference's CDF order); otherwise full-state
         draw followed by bit extraction (same distribution).
+
+        `out_columns` (a permutation of range(len(bits))): column c of the result
+        is the measured bit bits[out_columns[c]] — the draw itself (and hence a
+        seeded result) is that of the order `bits`, only the columns are emitted
+        in another order, on the device.
         """
         bits = [int(b) for b in bits]
         m = len(bits)
         u = np.asarray(uniforms, dtype=np.float64).reshape(-1)
         if m == 0 or u.size == 0:
             return np.zeros((u.size, m), dtype=np.uint8)
+        cols = list(range(m)) if out_columns is None else [int(c) for c in out_columns]
         natural = bits == list(range(self.n_bits - 1, -1, -1))
         if natural or m > 24:
             idx = self.sample_indices_device(u)
-            return self.unpack_bits_device(idx, bits).cpu().numpy()
+            return self.unpack_bits_device(idx, [bits[c] for c in cols]).cpu().numpy()
         probs = self.marginal_probs_device(bits)
         idx = self.cdf_sample_device(probs, u)
-        return self.unpack_bits_device(idx, [m - 1 - q for q in range(m)]).cpu().numpy()
+        return self.unpack_bits_device(idx, [m - 1 - c for c in cols]).cpu().numpy()
 
     def collapse(self, bits: Sequence[int], values: Sequence[int], prob: float) -> None:
         torch = _torch()

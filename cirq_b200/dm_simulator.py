@@ -28,7 +28,7 @@ import numpy as np
 from cirq_b200._cirq_compat import import_cirq
 from cirq_b200.device_state import DeviceState
 from cirq_b200.fusion import GateFuser, fuser_for
-from cirq_b200.sv_simulator import _FastConfuseMixin
+from cirq_b200.sv_simulator import _FastConfuseMixin, create_product_state
 
 cirq = import_cirq()
 
@@ -165,8 +165,10 @@ class B200DensityMatrix(qis.QuantumStateRepresentation):
         self._dev.dm_collapse(self._col_bits(axes), values, float(p[pick] / p.sum()))
         return values
 
-    def sample(self, axes: Sequence[int], repetitions: int = 1, seed=None) -> np.ndarray:
-        """``sample_density_matrix`` (sim/density_matrix_utils.py:31-94)."""
+    def sample(self, axes: Sequence[int], repetitions: int = 1, seed=None,
+               out_columns: Sequence[int] | None = None) -> np.ndarray:
+        """``sample_density_matrix`` (sim/density_matrix_utils.py:31-94);
+        `out_columns` reorders the result's columns on the device."""
         if repetitions < 0:
             raise ValueError(f'Number of repetitions cannot be negative. Was {repetitions}')
         axes = [int(a) for a in axes]
@@ -181,7 +183,8 @@ class B200DensityMatrix(qis.QuantumStateRepresentation):
         uniforms = prng.random_sample(repetitions)
         probs = self._marginal_device(axes)
         idx = DeviceState.cdf_sample_device(probs, uniforms)
-        bits = DeviceState.unpack_bits_device(idx, [m - 1 - q for q in range(m)])
+        cols = list(range(m)) if out_columns is None else [int(c) for c in out_columns]
+        bits = DeviceState.unpack_bits_device(idx, [m - 1 - c for c in cols])
         return bits.cpu().numpy().astype(np.int8)
 
     @property
@@ -416,6 +419,9 @@ class B200DensityMatrixSimulator(
             dtype=self._dtype,
             max_fused_qubits=self._max_fused,
         )
+
+    def _create_simulation_state(self, initial_state, qubits):
+        return create_product_state(self, initial_state, qubits)
 
     def _can_be_in_run_prefix(self, val: Any):
         return not protocols.measurement_keys_touched(val)

@@ -37,6 +37,7 @@ cirq = import_cirq()
 
 from cirq import ops, protocols, qis, value  # noqa: E402
 from cirq.sim import simulator, state_vector, state_vector_simulator  # noqa: E402
+from cirq.sim.simulation_product_state import SimulationProductState  # noqa: E402
 from cirq.sim.simulation_state import SimulationState, strat_act_on_from_apply_decompose  # noqa: E402
 
 # Widest gate whose full unitary is requested from Cirq before falling back to
@@ -177,8 +178,11 @@ class B200StateVector(qis.QuantumStateRepresentation):
         axes: Sequence[int],
         repetitions: int = 1,
         seed: 'cirq.RANDOM_STATE_OR_SEED_LIKE' = None,
+        out_columns: Sequence[int] | None = None,
     ) -> np.ndarray:
-        """``sample_state_vector`` (sim/state_vector.py:170-232) on the device."""
+        """``sample_state_vector`` (sim/state_vector.py:170-232) on the device.
+        `out_columns` reorders the result's columns on the device (see
+        ``DeviceState.sample_bits``)."""
         if repetitions < 0:
             raise ValueError(f'Number of repetitions cannot be negative. Was {repetitions}')
         axes = [int(a) for a in axes]
@@ -190,7 +194,7 @@ class B200StateVector(qis.QuantumStateRepresentation):
         self.flush()
         prng = value.parse_random_state(seed)
         uniforms = prng.random_sample(repetitions)
-        return self._dev.sample_bits(self._bits(axes), uniforms)
+        return self._dev.sample_bits(self._bits(axes), uniforms, out_columns)
 
     @property
     def supports_factor(self) -> bool:
@@ -276,6 +280,68 @@ class B200StateVector(qis.QuantumStateRepresentation):
             self.flush()
             self._host = self._dev.to_numpy().reshape(self._qid_shape)
         return self._host
+
+
+class B200ProductState(SimulationProductState):
+    """``SimulationProductState`` (sim/simulation_product_state.py:31-181) with a
+    sampling fast path: when every requested qubit lives in ONE sub-state — the
+    usual case once a circuit has entangled its qubits — the draw is made in that
+    sub-state's own qubit order exactly as the reference does (so seeded results
+    agree), but the columns are emitted in the requested order by the device
+    kernel instead of two host-side shuffles of a (repetitions x qubits) array."""
+
+    def copy(self, deep_copy_buffers: bool = True):
+        base = super().copy(deep_copy_buffers)
+        return B200ProductState(
+            dict(base.sim_states), base.qubits, base.split_untangled_states,
+            classical_data=base.classical_data,
+        )
+
+    def sample(self, qubits, repetitions: int = 1, seed=None) -> np.ndarray:
+        q_set = set(qubits)
+        owners = [v for v in dict.fromkeys(self.sim_states.values()) if any(q in q_set for q in v.qubits)]
+        if len(owners) == 1 and len(q_set) == len(qubits) and hasattr(owners[0]._state, 'sample'):
+            v = owners[0]
+            qs = [q for q in v.qubits if q in q_set]
+            if len(qs) == len(qubits):
+                position = {q: i for i, q in enumerate(qs)}
+                try:
+                    return v._state.sample(
+                        v.get_axes(qs), repetitions, seed,
+                        out_columns=[position[q] for q in qubits],
+                    )
+                except TypeError:
+                    pass  # a state representation without the out_columns extension
+        return super().sample(qubits, repetitions, seed)
+
+
+def create_product_state(simulator, initial_state, qubits):
+    """``SimulatorBase._create_simulation_state`` (sim/simulator_base.py:322-352)
+    building a ``B200ProductState`` when split_untangled_states is on."""
+    from cirq.sim.simulation_state_base import SimulationStateBase
+
+    if isinstance(initial_state, SimulationStateBase):
+        return initial_state
+    classical_data = value.ClassicalDataDictionaryStore()
+    if not simulator._split_untangled_states:
+        return simulator._create_partial_simulation_state(
+            initial_state=initial_state, qubits=qubits, classical_data=classical_data
+        )
+    args_map = {}
+    if isinstance(initial_state, int):
+        for q in reversed(qubits):
+            args_map[q] = simulator._create_partial_simulation_state(
+                initial_state=initial_state % q.dimension, qubits=[q], classical_data=classical_data
+            )
+            initial_state = int(initial_state / q.dimension)
+    else:
+        args = simulator._create_partial_simulation_state(
+            initial_state=initial_state, qubits=qubits, classical_data=classical_data
+        )
+        for q in qubits:
+            args_map[q] = args
+    args_map[None] = simulator._create_partial_simulation_state(0, (), classical_data)
+    return B200ProductState(args_map, qubits, True, classical_data=classical_data)
 
 
 class B200StateVectorSimulationState(SimulationState[B200StateVector]):
@@ -634,10 +700,10 @@ class B200Simulator(
         if self._split_untangled_states and len(qubits) > _MAX_SPLIT_QUBITS:
             self._split_untangled_states = False
             try:
-                return super()._create_simulation_state(initial_state, qubits)
+                return create_product_state(self, initial_state, qubits)
             finally:
                 self._split_untangled_states = True
-        return super()._create_simulation_state(initial_state, qubits)
+        return create_product_state(self, initial_state, qubits)
 
     def _create_step_result(self, sim_state):
         return B200SimulatorStep(sim_state=sim_state, dtype=self._dtype)

@@ -104,12 +104,13 @@ class OracleDeviceState:
             key = (key << 1) | ((i >> b) & 1)
         return _ft(np.bincount(key, weights=p, minlength=1 << len(bits)))
 
-    def sample_bits(self, bits, uniforms):
+    def sample_bits(self, bits, uniforms, out_columns=None):
         bits = [int(b) for b in bits]
         u = np.asarray(uniforms, dtype=np.float64).reshape(-1)
         if len(bits) == 0 or u.size == 0:
             return np.zeros((u.size, len(bits)), dtype=np.uint8)
-        return orc.sample(self.array, self.n_bits, bits, u)
+        out = orc.sample(self.array, self.n_bits, bits, u)
+        return out if out_columns is None else np.ascontiguousarray(out[:, list(out_columns)])
 
     def collapse(self, bits, values, prob):
         self.array = orc.collapse(self.array, self.n_bits, list(bits), list(values), prob)
