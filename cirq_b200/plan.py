@@ -49,6 +49,10 @@ class _Component:
 class SplitExecutor:
     """State of n logical bits kept as a product of device states."""
 
+    # Joining sub-states is out of place (inputs + output live together), so above
+    # this size the state is one dense tensor from the start.
+    MAX_SPLIT_BITS = 30
+
     def __init__(self, n_bits: int, dtype=np.complex64, max_fused_qubits: int | None = None,
                  device_state_cls=None):
         if device_state_cls is None:
@@ -58,9 +62,17 @@ class SplitExecutor:
         self.dtype = np.dtype(dtype)
         self.max_fused = max_fused_qubits
         self._comp = {}
-        for b in range(self.n):
-            c = _Component([b], self._DS.basis(1, self.dtype, 0), fuser_for(self.dtype, max_fused_qubits, 1))
-            self._comp[b] = c
+        if self.n > self.MAX_SPLIT_BITS:
+            bits = list(range(self.n - 1, -1, -1))
+            c = _Component(bits, self._DS.basis(self.n, self.dtype, 0),
+                           fuser_for(self.dtype, max_fused_qubits, self.n))
+            for b in bits:
+                self._comp[b] = c
+        else:
+            for b in range(self.n):
+                c = _Component([b], self._DS.basis(1, self.dtype, 0),
+                               fuser_for(self.dtype, max_fused_qubits, 1))
+                self._comp[b] = c
         self.kron_count = 0
         self._since_drain = 0
 
