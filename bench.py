@@ -70,10 +70,15 @@ def measured_traffic(n_qubits, kernel):
     return table.get(kernel)
 
 
-def kernel_class(num_wires):
-    """Name of the kernel a fused block of this width runs on (complex64)."""
-    return 'sv_apply_tc_kernel<5>' if num_wires == 5 else (
-        'sv_apply_tc_kernel<6>' if num_wires == 6 else f'sv_apply_fast_kernel<float,{num_wires}>')
+def kernel_class(wires):
+    """Name of the kernel a fused block on these index bits runs on (complex64,
+    default knobs: b2q_apply_tc.cu launch_tc_k / b2q_apply.cu apply_matrix_t)."""
+    k = len(wires)
+    if k == 5:
+        return 'sv_apply_tc_staged_kernel<5>' if min(wires) < 2 else 'sv_apply_tc_kernel<5>'
+    if k == 6:
+        return 'sv_apply_tc_kernel<6>'
+    return f'sv_apply_fast_kernel<float,{k}>'
 
 
 def build_workload(name):
@@ -255,7 +260,7 @@ def run_b200_arm(args):
             a.record()
             state.apply_matrix(m, w)
             b.record()
-            timed_apply.pairs.append((state.n_bits, kernel_class(len(w)), a, b))
+            timed_apply.pairs.append((state.n_bits, kernel_class(w), a, b))
 
     timed_apply.pairs = []
 

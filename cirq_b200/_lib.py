@@ -100,6 +100,9 @@ DEBUG_SIGNATURES = {
     'b2q_set_lane_mode': (c_int, [c_int]),
     'b2q_set_vec_mode': (c_int, [c_int]),
     'b2q_set_tc_mode': (c_int, [c_int]),
+    'b2q_set_tc_stage_mode': (c_int, [c_int]),
+    'b2q_set_tc_stage_opts': (c_int, [c_int, c_int]),
+    'b2q_debug_tc_stage_plan': (c_int, [c_int, POINTER(c_int), c_int, POINTER(ctypes.c_int64)]),
     'b2q_debug_plan': (c_int, [c_int, c_int, POINTER(c_int), c_int, POINTER(c_int)]),
     'b2q_debug_permute_matrix': (c_int, [c_void_p, POINTER(c_int), c_int, c_void_p]),
 }
@@ -127,6 +130,13 @@ def load():
     mode = os.environ.get('CIRQ_B200_TC_MODE')
     if mode is not None:
         lib.b2q_set_tc_mode(int(mode))
+    mode = os.environ.get('CIRQ_B200_TC_STAGE_MODE')
+    if mode is not None:
+        lib.b2q_set_tc_stage_mode(int(mode))
+    mode = os.environ.get('CIRQ_B200_TC_STAGE_OPTS')
+    if mode is not None:
+        early, ahead = (int(v) for v in mode.split(','))
+        lib.b2q_set_tc_stage_opts(early, ahead)
     mode = os.environ.get('CIRQ_B200_VEC_MODE')
     if mode is not None:
         lib.b2q_set_vec_mode(int(mode))

@@ -126,7 +126,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
-template <int K>
+// LOW selects the HBM access pattern for targets on the lowest index bits, so
+// that every warp request still covers whole 32-byte sectors:
+//   0: no target on index bit 0 (and bit 1 free or bit 0/1 both free): 8-byte
+//      accesses, consecutive threads = consecutive amplitudes;
+//   1: index bit 0 is a target: members (2i, 2i+1) of a group are adjacent, one
+//      16-byte access per member pair;
+//   2: index bit 1 is a target and bit 0 is not: groups (g, g+1) interleave at
+//      8 bytes; the even thread of a pair fetches member 2i of both groups, the
+//      odd thread member 2i+1 (16 bytes each), and they trade halves by shuffle.
+template <int K, int LOW>
 __global__ void __launch_bounds__(kTcThreads, TcTraits<K>::kMinBlocks)
     sv_apply_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int kTcK = K;
@@ -190,18 +199,45 @@ __global__ void __launch_bounds__(kTcThreads, TcTraits<K>::kMinBlocks)
   uint64_t tile = blockIdx.x;
   float2 x[kTcDim];
   float2* ptr = p.state;
+  const int odd = tid & 1;
   auto issue_loads = [&](uint64_t t) {
     const uint64_t g = t * kTcThreads + (uint64_t)tid;
-    ptr = p.state + insert_zero_bits(g, p.tpos, kTcK);
+    if constexpr (LOW == 0) {
+      ptr = p.state + insert_zero_bits(g, p.tpos, kTcK);
 #pragma unroll
-    for (int j = 0; j < kTcDim; ++j) {
-      const float2* q = ptr + s_off[j];
-      asm volatile("ld.global.v2.f32 {%0,%1}, [%2];" : "=f"(x[j].x), "=f"(x[j].y) : "l"(q));
+      for (int j = 0; j < kTcDim; ++j) {
+        const float2* q = ptr + s_off[j];
+        asm volatile("ld.global.v2.f32 {%0,%1}, [%2];" : "=f"(x[j].x), "=f"(x[j].y) : "l"(q));
+      }
+    } else {
+      // LOW == 2: `ptr` is the base of the thread PAIR (group g & ~1)
+      ptr = p.state + insert_zero_bits(LOW == 2 ? (g & ~1ull) : g, p.tpos, kTcK);
+#pragma unroll
+      for (int i = 0; i < kTcDim / 2; ++i) {
+        const float2* q = ptr + s_off[2 * i + (LOW == 2 ? odd : 0)];
+        asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(x[2 * i].x), "=f"(x[2 * i].y), "=f"(x[2 * i + 1].x), "=f"(x[2 * i + 1].y)
+                     : "l"(q));
+      }
     }
   };
   if (tile < p.num_tiles) issue_loads(tile);
   while (tile < p.num_tiles) {
     float2* const cur = ptr;
+    if constexpr (LOW == 2) {
+      // raw: x[2i] = member (2i + odd) of group g & ~1, x[2i+1] = same member of
+      // the next group.  Keep the half that is ours, trade the other.
+#pragma unroll
+      for (int i = 0; i < kTcDim / 2; ++i) {
+        const float2 keep = odd ? x[2 * i + 1] : x[2 * i];
+        const float2 send = odd ? x[2 * i] : x[2 * i + 1];
+        float2 recv;
+        recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+        recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+        x[2 * i] = odd ? recv : keep;
+        x[2 * i + 1] = odd ? keep : recv;
+      }
+    }
     // A row -> TMEM, 16 columns at a time: hi at [0,N), lo at [N,2N)
 #pragma unroll
     for (int c16 = 0; c16 < kTcN / 16; ++c16) {
@@ -266,13 +302,40 @@ __global__ void __launch_bounds__(kTcThreads, TcTraits<K>::kMinBlocks)
       tmem_ld16(lane_base + d_col + (uint32_t)(c16 * 16), d);
       tmem_ld16(lane_base + d_col + (uint32_t)(kTcN + c16 * 16), d1);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if constexpr (LOW == 0) {
 #pragma unroll
-      for (int e = 0; e < 16; e += 2) {
-        const int r = (c16 * 16 + e) >> 1;
-        float2* q = cur + s_off[r];
-        const float re = __uint_as_float(d[e]) + __uint_as_float(d1[e]);
-        const float im = __uint_as_float(d[e + 1]) + __uint_as_float(d1[e + 1]);
-        asm volatile("st.global.v2.f32 [%0], {%1,%2};" ::"l"(q), "f"(re), "f"(im) : "memory");
+        for (int e = 0; e < 16; e += 2) {
+          const int r = (c16 * 16 + e) >> 1;
+          float2* q = cur + s_off[r];
+          const float re = __uint_as_float(d[e]) + __uint_as_float(d1[e]);
+          const float im = __uint_as_float(d[e + 1]) + __uint_as_float(d1[e + 1]);
+          asm volatile("st.global.v2.f32 [%0], {%1,%2};" ::"l"(q), "f"(re), "f"(im) : "memory");
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          const int r = (c16 * 16 + e) >> 1;  // even member; r + 1 is its neighbour
+          float2 o0, o1;
+          o0.x = __uint_as_float(d[e]) + __uint_as_float(d1[e]);
+          o0.y = __uint_as_float(d[e + 1]) + __uint_as_float(d1[e + 1]);
+          o1.x = __uint_as_float(d[e + 2]) + __uint_as_float(d1[e + 2]);
+          o1.y = __uint_as_float(d[e + 3]) + __uint_as_float(d1[e + 3]);
+          if constexpr (LOW == 2) {
+            // even thread writes member r of both groups, odd thread member r + 1
+            const float2 send = odd ? o0 : o1;
+            float2 recv;
+            recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+            recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+            const float2 first = odd ? recv : o0;
+            const float2 second = odd ? o1 : recv;
+            o0 = first;
+            o1 = second;
+          }
+          float2* q = cur + s_off[r + (LOW == 2 ? odd : 0)];
+          asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(q), "f"(o0.x), "f"(o0.y),
+                       "f"(o1.x), "f"(o1.y)
+                       : "memory");
+        }
       }
     }
     // all reads of D must finish before the next tile's MMAs overwrite it
@@ -284,6 +347,325 @@ __global__ void __launch_bounds__(kTcThreads, TcTraits<K>::kMinBlocks)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"((uint32_t)kTcCols)
                  : "memory");
+  }
+}
+
+// ---- staged variant: coalesced for ANY target positions ----------------------
+//
+// With targets on the lowest index bits the amplitudes of one group sit next to
+// each other in memory, so "thread = group" addressing makes every warp request
+// touch 16-32 different cache lines (4.9 ms per pass for targets 0-4).  Here a
+// warp instead moves its REGION — 32 groups x 2^K members = the index bits
+// {targets} U {5 lowest non-target bits}, which always contains index bits 0-4 —
+// between HBM and shared memory with 16-byte lane accesses that are contiguous
+// over 256-512 bytes (cp.async, double buffered, no registers involved), and
+// the per-group gather / scatter happens on shared memory.  An XOR swizzle of
+// local-index bits 1-3, derived on the host from where the group bits fall,
+// makes both access patterns bank-conflict free.
+constexpr int kStageMaxK = 5;
+
+struct TcStagedParams {
+  float2* state;
+  uint64_t num_tiles;  // CTA tiles (4 warp regions each)
+  const float* bmat;
+  int rpos[kStageMaxK + 5];  // ascending index positions of the region bits
+  int p5;                    // rpos[5]: index position behind lane bit 4 of a request
+  int gpos[5];               // local positions of the 5 group bits (lane bit i)
+  int swz_src[3];            // local bit swz_src[i] (>= 4, or 20 = unused) is XORed ...
+  int swz_dst[3];            // ... into local bit swz_dst[i] (1..3)
+  int early;      // 1: the next region's copy is issued at the top of the iteration
+  int l2_ahead;   // > 0: regions this many iterations ahead are prefetched into L2
+  uint64_t goff[1 << (kStageMaxK - 1)];  // request r -> element offset in the state
+  uint32_t sreq[1 << (kStageMaxK - 1)];  // request r -> swizzled local offset
+  uint32_t smem_j[1 << kStageMaxK];      // member j  -> swizzled local offset
+};
+
+B2Q_HD uint32_t stage_swizzle(uint32_t x, const int* src, const int* dst) {
+  for (int i = 0; i < 3; ++i) x ^= ((x >> src[i]) & 1u) << dst[i];
+  return x;
+}
+
+template <int K, bool VEC>
+__global__ void __launch_bounds__(kTcThreads, TcTraits<K>::kMinBlocks)
+    sv_apply_tc_staged_kernel(const __grid_constant__ TcStagedParams p) {
+  constexpr int kTcDim = TcTraits<K>::kDim;
+  constexpr int kTcN = TcTraits<K>::kN;
+  constexpr int kTcCols = TcTraits<K>::kCols;
+  constexpr int kReq = 1 << (K - 1);     // 64-amplitude requests per warp region
+  constexpr int kRegion = 1 << (K + 5);  // amplitudes per warp region
+  constexpr uint32_t kBufBytes = 4u * kRegion * sizeof(float2);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* sB = reinterpret_cast<float*>(smem_raw);  // B_hi then B_lo
+  unsigned char* stage = smem_raw + TcTraits<K>::kBBytes;  // [2 buffers][4 warps][kRegion]
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_s)),
+                 "r"((uint32_t)kTcCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.bmat);
+    float4* dst = reinterpret_cast<float4*>(sB);
+    for (int i = tid; i < 2 * kTcN * kTcN / 4; i += kTcThreads) dst[i] = src[i];
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t d_col = 2 * kTcN;
+  constexpr uint32_t idesc =
+      (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t sb_hi = smem_u32(sB);
+  const uint32_t sb_lo = smem_u32(sB + kTcN * kTcN);
+  constexpr uint32_t kLbo = kTcN * 16;
+  constexpr uint32_t kSbo = 128;
+
+  // HBM <-> shared: lane l of request r moves local elements (r << 6) + 2l, +1
+  const uint64_t lane_goff = (uint64_t)((lane & 15) << 1) + ((uint64_t)(lane >> 4) << p.p5);
+  const uint32_t lane_s = stage_swizzle((uint32_t)lane << 1, p.swz_src, p.swz_dst);
+  // shared <-> registers: this thread's group
+  uint32_t group_local = 0;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) group_local |= (uint32_t)((lane >> i) & 1) << p.gpos[i];
+  const uint32_t sg = stage_swizzle(group_local, p.swz_src, p.swz_dst);
+  unsigned char* const stage_warp = stage + (size_t)warp * kRegion * sizeof(float2);
+  const uint32_t stage_warp_s = smem_u32(stage_warp);
+
+  auto region_base = [&](uint64_t t) {
+    return insert_zero_bits(t * 4 + (uint64_t)warp, p.rpos, K + 5);
+  };
+  auto prefetch = [&](uint64_t base, uint32_t buf) {
+    const float2* src = p.state + base + lane_goff;
+    const uint32_t dst = stage_warp_s + buf * kBufBytes;
+#pragma unroll
+    for (int r = 0; r < kReq; ++r) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + ((lane_s ^ p.sreq[r]) << 3)),
+                   "l"(src + p.goff[r])
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  uint32_t parity = 0, buf = 0;
+  uint64_t tile = blockIdx.x;
+  uint64_t base = 0;
+  if (tile < p.num_tiles) {
+    base = region_base(tile);
+    prefetch(base, 0);
+  }
+  // lane -> one 256-byte run of the region (L2 prefetch: kReq requests x 2 runs)
+  const uint64_t lane_run_off =
+      (lane < 2 * kReq) ? p.goff[lane >> 1] + ((uint64_t)(lane & 1) << p.p5) : 0;
+  while (tile < p.num_tiles) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    const uint64_t next = tile + gridDim.x;
+    uint64_t next_base = 0;
+    if (next < p.num_tiles) next_base = region_base(next);
+    if (p.early && next < p.num_tiles) prefetch(next_base, buf ^ 1u);
+    if (p.l2_ahead > 0) {
+      const uint64_t far = tile + (uint64_t)p.l2_ahead * gridDim.x;
+      if (far < p.num_tiles && lane < 2 * kReq) {
+        const float2* q = p.state + region_base(far) + lane_run_off;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], 256;" ::"l"(q) : "memory");
+      }
+    }
+    unsigned char* const sbuf = stage_warp + (size_t)buf * kBufBytes;
+    float2 x[kTcDim];
+    if constexpr (VEC) {
+#pragma unroll
+      for (int i = 0; i < kTcDim / 2; ++i) {
+        const float4 v = *reinterpret_cast<const float4*>(sbuf + ((sg ^ p.smem_j[2 * i]) << 3));
+        x[2 * i] = make_float2(v.x, v.y);
+        x[2 * i + 1] = make_float2(v.z, v.w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kTcDim; ++j)
+        x[j] = *reinterpret_cast<const float2*>(sbuf + ((sg ^ p.smem_j[j]) << 3));
+    }
+#pragma unroll
+    for (int c16 = 0; c16 < kTcN / 16; ++c16) {
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int col = c16 * 16 + e;
+        const float a = (col & 1) ? x[col >> 1].y : x[col >> 1].x;
+        const uint32_t h = to_tf32(a);
+        hi[e] = h;
+        lo[e] = to_tf32(a - __uint_as_float(h));
+      }
+      tmem_st16(lane_base + (uint32_t)(c16 * 16), hi);
+      tmem_st16(lane_base + (uint32_t)(kTcN + c16 * 16), lo);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    // next region -> the other buffer while the tensor core works on this one
+    if (!p.early && next < p.num_tiles) prefetch(next_base, buf ^ 1u);
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // same product order as sv_apply_tc_kernel (see the comment there)
+      uint32_t acc0 = 0;
+#pragma unroll
+      for (int prod = 0; prod < 2; ++prod) {
+        const uint32_t a_col = (prod == 0) ? (uint32_t)kTcN : 0u;
+        const uint32_t sb = (prod == 0) ? sb_hi : sb_lo;
+#pragma unroll
+        for (int ks = 0; ks < kTcN / 8; ++ks) {
+          const uint64_t bd = umma_desc(sb + (uint32_t)(ks * 2) * kLbo, kLbo, kSbo);
+          umma_tf32_ts(tmem_base + d_col, tmem_base + a_col + (uint32_t)(ks * 8), bd, idesc, acc0);
+          acc0 = 1;
+        }
+      }
+#pragma unroll
+      for (int ks = 0; ks < kTcN / 8; ++ks) {
+        const uint64_t bd = umma_desc(sb_hi + (uint32_t)(ks * 2) * kLbo, kLbo, kSbo);
+        const bool second = ks >= kTcN / 16;
+        umma_tf32_ts(tmem_base + d_col + (second ? (uint32_t)kTcN : 0u),
+                     tmem_base + (uint32_t)(ks * 8), bd, idesc,
+                     (second && ks == kTcN / 16) ? 0u : 1u);
+      }
+      asm volatile(
+          "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+              smem_u32(&mbar))
+          : "memory");
+    }
+    mbar_wait(smem_u32(&mbar), parity);
+    parity ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // D0 + D1 -> this thread's slots of the region (all lanes finished reading
+    // their inputs before the __syncthreads above)
+#pragma unroll
+    for (int c16 = 0; c16 < kTcN / 16; ++c16) {
+      uint32_t d[16], d1[16];
+      tmem_ld16(lane_base + d_col + (uint32_t)(c16 * 16), d);
+      tmem_ld16(lane_base + d_col + (uint32_t)(kTcN + c16 * 16), d1);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if constexpr (VEC) {
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          const int r = (c16 * 16 + e) >> 1;
+          float4 o;
+          o.x = __uint_as_float(d[e]) + __uint_as_float(d1[e]);
+          o.y = __uint_as_float(d[e + 1]) + __uint_as_float(d1[e + 1]);
+          o.z = __uint_as_float(d[e + 2]) + __uint_as_float(d1[e + 2]);
+          o.w = __uint_as_float(d[e + 3]) + __uint_as_float(d1[e + 3]);
+          *reinterpret_cast<float4*>(sbuf + ((sg ^ p.smem_j[r]) << 3)) = o;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+          const int r = (c16 * 16 + e) >> 1;
+          float2 o;
+          o.x = __uint_as_float(d[e]) + __uint_as_float(d1[e]);
+          o.y = __uint_as_float(d[e + 1]) + __uint_as_float(d1[e + 1]);
+          *reinterpret_cast<float2*>(sbuf + ((sg ^ p.smem_j[r]) << 3)) = o;
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    // region -> HBM, 512 contiguous bytes per warp request
+    {
+      float2* const dst = p.state + base + lane_goff;
+      constexpr int kBatch = kReq < 8 ? kReq : 8;
+#pragma unroll
+      for (int r0 = 0; r0 < kReq; r0 += kBatch) {
+        float4 v[kBatch];
+#pragma unroll
+        for (int r = 0; r < kBatch; ++r)
+          v[r] = *reinterpret_cast<const float4*>(sbuf + ((lane_s ^ p.sreq[r0 + r]) << 3));
+#pragma unroll
+        for (int r = 0; r < kBatch; ++r)
+          *reinterpret_cast<float4*>(dst + p.goff[r0 + r]) = v[r];
+      }
+    }
+    __syncwarp();  // this buffer is refilled by the prefetch issued one iteration later
+    tile = next;
+    base = next_base;
+    buf ^= 1u;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)kTcCols)
+                 : "memory");
+  }
+}
+
+// Host side of the staged layout (also exported for the host unit tests).
+static void make_staged_params(int n, int K, const int* sorted, TcStagedParams* p) {
+  bool is_target[64] = {false};
+  for (int i = 0; i < K; ++i) is_target[sorted[i]] = true;
+  int free_low[5];
+  for (int b = 0, c = 0; c < 5; ++b)
+    if (!is_target[b]) free_low[c++] = b;
+  // region bits, ascending
+  int nr = 0;
+  {
+    bool in_region[64] = {false};
+    for (int i = 0; i < K; ++i) in_region[sorted[i]] = true;
+    for (int i = 0; i < 5; ++i) in_region[free_low[i]] = true;
+    for (int b = 0; b < n; ++b)
+      if (in_region[b]) p->rpos[nr++] = b;
+  }
+  auto local_pos = [&](int bit) {
+    for (int i = 0; i < nr; ++i)
+      if (p->rpos[i] == bit) return i;
+    return -1;
+  };
+  p->p5 = p->rpos[5];
+  for (int i = 0; i < 5; ++i) p->gpos[i] = local_pos(free_low[i]);
+  // swizzle: the three lowest group positions >= 1 must land on distinct bits of 1..3
+  {
+    int cand[3], nc = 0;
+    for (int i = 0; i < 5 && nc < 3; ++i)
+      if (p->gpos[i] >= 1) cand[nc++] = p->gpos[i];
+    bool used[4] = {false, false, false, false};
+    for (int i = 0; i < nc; ++i)
+      if (cand[i] <= 3) used[cand[i]] = true;
+    int ns = 0, next_free = 1;
+    for (int i = 0; i < 3; ++i) {
+      p->swz_src[i] = 20;
+      p->swz_dst[i] = 1;
+    }
+    for (int i = 0; i < nc; ++i) {
+      if (cand[i] <= 3) continue;
+      while (next_free <= 3 && used[next_free]) ++next_free;
+      p->swz_src[ns] = cand[i];
+      p->swz_dst[ns] = next_free;
+      used[next_free] = true;
+      ++ns;
+    }
+  }
+  const int nreq = 1 << (K - 1);
+  for (int r = 0; r < nreq; ++r) {
+    uint64_t off = 0;
+    for (int i = 0; i < K - 1; ++i)
+      if ((r >> i) & 1) off += 1ull << p->rpos[6 + i];
+    p->goff[r] = off;
+    p->sreq[r] = stage_swizzle((uint32_t)r << 6, p->swz_src, p->swz_dst);
+  }
+  for (int j = 0; j < (1 << K); ++j) {
+    uint32_t loc = 0;
+    for (int b = 0; b < K; ++b)
+      if ((j >> b) & 1) loc |= 1u << local_pos(sorted[b]);
+    p->smem_j[j] = stage_swizzle(loc, p->swz_src, p->swz_dst);
   }
 }
 
@@ -301,6 +683,11 @@ static float tf32_round_host(float x) {
 }
 
 std::atomic<int> g_tc_mode{1};  // 1 = use the tensor-core kernel for k = 5 (complex64)
+// 0 = never stage through shared memory, 1 = stage when a target sits on index
+// bit 0 or 1, 2 = always (k <= 5)
+std::atomic<int> g_tc_stage_mode{1};
+std::atomic<int> g_tc_stage_early{0};
+std::atomic<int> g_tc_stage_l2_ahead{0};
 
 // Gate matrices travel through a ring of pinned host / device slot pairs: a
 // cudaMemcpyAsync from PAGEABLE memory synchronises the stream first, which
@@ -346,6 +733,60 @@ bool tc_applicable(int dtype, int n, int K) {
   return K == 5 || K == 6 || (K == 4 && mode == 2);
 }
 
+template <int K, int LOW>
+static int launch_tc_kernel(const TcParams& p, cudaStream_t stream) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  static bool attr_set[64] = {false};
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+      B2Q_CUDA_CHECK(cudaFuncSetAttribute(sv_apply_tc_kernel<K, LOW>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)TcTraits<K>::kBBytes));
+      attr_set[dev] = true;
+    }
+  }
+  const uint64_t grid =
+      std::min<uint64_t>(p.num_tiles, (uint64_t)sms * TcTraits<K>::kMinBlocks);
+  sv_apply_tc_kernel<K, LOW><<<(unsigned)grid, kTcThreads, TcTraits<K>::kBBytes, stream>>>(p);
+  B2Q_LAUNCH_CHECK("sv_apply_tc_kernel");
+  return B2Q_OK;
+}
+
+template <int K, bool VEC>
+static int launch_tc_staged_kernel(const TcStagedParams& p, cudaStream_t stream) {
+  constexpr size_t kSmem = TcTraits<K>::kBBytes + 2ull * 4ull * (1ull << (K + 5)) * sizeof(float2);
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  static bool attr_set[64] = {false};
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+      B2Q_CUDA_CHECK(cudaFuncSetAttribute(sv_apply_tc_staged_kernel<K, VEC>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+      attr_set[dev] = true;
+    }
+  }
+  const uint64_t grid =
+      std::min<uint64_t>(p.num_tiles, (uint64_t)sms * TcTraits<K>::kMinBlocks);
+  sv_apply_tc_staged_kernel<K, VEC><<<(unsigned)grid, kTcThreads, kSmem, stream>>>(p);
+  B2Q_LAUNCH_CHECK("sv_apply_tc_staged_kernel");
+  return B2Q_OK;
+}
+
 // `mat` = gate matrix in sorted-target order (index bit i <-> i-th lowest
 // target), plain (re, im) float pairs, row-major 2^K x 2^K.
 template <int K>
@@ -386,28 +827,32 @@ int launch_tc_k(void* state, int n, const int* sorted, const float* mat, cudaStr
   p.num_tiles = (1ull << (n - kTcK)) / kTcThreads;
   for (int i = 0; i < kTcK; ++i) p.tpos[i] = sorted[i];
   p.bmat = dmat;
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  static bool attr_set[64] = {false};
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-      B2Q_CUDA_CHECK(cudaFuncSetAttribute(sv_apply_tc_kernel<K>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)TcTraits<K>::kBBytes));
-      attr_set[dev] = true;
+  const int low = sorted[0] == 0 ? 1 : (sorted[0] == 1 ? 2 : 0);
+  const int stage_mode = g_tc_stage_mode.load(std::memory_order_relaxed);
+  int rc;
+  if constexpr (K <= kStageMaxK) {
+    if (stage_mode == 2 || (stage_mode == 1 && low != 0)) {
+      TcStagedParams sp;
+      sp.state = p.state;
+      sp.num_tiles = p.num_tiles;
+      sp.bmat = dmat;
+      make_staged_params(n, K, sorted, &sp);
+      sp.early = g_tc_stage_early.load(std::memory_order_relaxed);
+      sp.l2_ahead = g_tc_stage_l2_ahead.load(std::memory_order_relaxed);
+      rc = low == 1 ? launch_tc_staged_kernel<K, true>(sp, stream)
+                    : launch_tc_staged_kernel<K, false>(sp, stream);
+      if (rc != B2Q_OK) return rc;
+      B2Q_CUDA_CHECK(cudaEventRecord(ring->done[slot], stream));
+      return B2Q_OK;
     }
   }
-  const uint64_t grid =
-      std::min<uint64_t>(p.num_tiles, (uint64_t)sms * TcTraits<K>::kMinBlocks);
-  sv_apply_tc_kernel<K><<<(unsigned)grid, kTcThreads, TcTraits<K>::kBBytes, stream>>>(p);
-  B2Q_LAUNCH_CHECK("sv_apply_tc_kernel");
+  if (low == 1)
+    rc = launch_tc_kernel<K, 1>(p, stream);
+  else if (low == 2)
+    rc = launch_tc_kernel<K, 2>(p, stream);
+  else
+    rc = launch_tc_kernel<K, 0>(p, stream);
+  if (rc != B2Q_OK) return rc;
   B2Q_CUDA_CHECK(cudaEventRecord(ring->done[slot], stream));
   return B2Q_OK;
 }
@@ -419,6 +864,42 @@ int launch_tc(void* state, int n, int K, const int* sorted, const float* mat, cu
 }
 
 }  // namespace b2q
+
+extern "C" int b2q_set_tc_stage_opts(int early, int l2_ahead) {
+  B2Q_REQUIRE(early >= 0 && early <= 1 && l2_ahead >= 0 && l2_ahead <= 8, "bad stage options");
+  b2q::g_tc_stage_early.store(early, std::memory_order_relaxed);
+  b2q::g_tc_stage_l2_ahead.store(l2_ahead, std::memory_order_relaxed);
+  return B2Q_OK;
+}
+
+extern "C" int b2q_set_tc_stage_mode(int mode) {
+  B2Q_REQUIRE(mode >= 0 && mode <= 2, "tc stage mode must be 0, 1 or 2");
+  b2q::g_tc_stage_mode.store(mode, std::memory_order_relaxed);
+  return B2Q_OK;
+}
+
+// out: rpos[10] | p5 | gpos[5] | swz_src[3] | swz_dst[3] | goff[16] | sreq[16] | smem_j[32]
+extern "C" int b2q_debug_tc_stage_plan(int n_qubits, const int* sorted_targets, int k, int64_t* out) {
+  B2Q_REQUIRE(sorted_targets != nullptr && out != nullptr, "null argument");
+  B2Q_REQUIRE(k >= 2 && k <= b2q::kStageMaxK && n_qubits >= k + 7, "unsupported shape");
+  for (int i = 0; i < k; ++i)
+    B2Q_REQUIRE(sorted_targets[i] >= 0 && sorted_targets[i] < n_qubits &&
+                    (i == 0 || sorted_targets[i] > sorted_targets[i - 1]),
+                "targets must be ascending and in range");
+  b2q::TcStagedParams p;
+  memset(&p, 0, sizeof(p));
+  b2q::make_staged_params(n_qubits, k, sorted_targets, &p);
+  int o = 0;
+  for (int i = 0; i < 10; ++i) out[o++] = i < k + 5 ? p.rpos[i] : -1;
+  out[o++] = p.p5;
+  for (int i = 0; i < 5; ++i) out[o++] = p.gpos[i];
+  for (int i = 0; i < 3; ++i) out[o++] = p.swz_src[i];
+  for (int i = 0; i < 3; ++i) out[o++] = p.swz_dst[i];
+  for (int i = 0; i < 16; ++i) out[o++] = i < (1 << (k - 1)) ? (int64_t)p.goff[i] : -1;
+  for (int i = 0; i < 16; ++i) out[o++] = i < (1 << (k - 1)) ? (int64_t)p.sreq[i] : -1;
+  for (int i = 0; i < 32; ++i) out[o++] = i < (1 << k) ? (int64_t)p.smem_j[i] : -1;
+  return B2Q_OK;
+}
 
 extern "C" int b2q_set_tc_mode(int mode) {
   B2Q_REQUIRE(mode >= 0 && mode <= 2, "tc mode must be 0, 1 or 2");

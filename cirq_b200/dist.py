@@ -114,15 +114,24 @@ class ShardBackend:
             out = ctypes.c_void_p()
             check(self.lib.b2q_dist_ipc_open(buf, ctypes.byref(out)))
             self.peer_ptrs[r] = out.value
+        self._token = torch.zeros(1, dtype=torch.int32, device='cuda')
         self.barrier()
 
     def barrier(self):
+        """Host barrier: this rank's stream is drained, then all ranks meet."""
         self.torch.cuda.current_stream().synchronize()
         self.dist.barrier(group=self.group)
 
+    def device_barrier(self):
+        """Stream-ordered barrier: kernels enqueued after it on ANY rank start only
+        once every rank's kernels enqueued before it have finished.  A 4-byte NCCL
+        all-reduce; the host does not wait, so the scheduler keeps running ahead."""
+        self.dist.all_reduce(self._token, group=self.group)
+
     def swap_bit(self, partner: int, local_bit: int, my_gbit: int) -> None:
-        """Both ranks of every pair call this between two barriers."""
-        self.barrier()
+        """Both ranks of every pair call this; the exchange kernel touches the
+        partner's shard, so it sits between two stream-ordered barriers."""
+        self.device_barrier()
         stream = ctypes.c_void_p(self.torch.cuda.current_stream().cuda_stream)
         check(
             self.lib.b2q_dist_swap_bit(
@@ -130,7 +139,7 @@ class ShardBackend:
                 self.local.code, self.n_local, local_bit, my_gbit, stream,
             )
         )
-        self.barrier()
+        self.device_barrier()
 
     def all_reduce_sum(self, value: float) -> float:
         t = self.torch.tensor([value], dtype=self.torch.float64, device='cuda')
@@ -160,9 +169,13 @@ class ShardBackend:
         if positions.size:
             idx = self.local.sample_indices_device(local_uniforms)
             idx = idx | (self.rank << self.n_local)
-            full[torch.from_numpy(positions).to('cuda')] = idx
+            full[torch.from_numpy(positions).to('cuda', non_blocking=True)] = idx
         self.dist.all_reduce(full, group=self.group)
-        return DeviceState.unpack_bits_device(full[:reps], bits).cpu().numpy()
+        dev = DeviceState.unpack_bits_device(full[:reps], bits)
+        host = torch.empty(dev.shape, dtype=dev.dtype, pin_memory=True)
+        host.copy_(dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host.numpy()
 
     def close(self):
         self.barrier()
@@ -232,7 +245,7 @@ class ShardedStateVector:
             self.local.array[:] = 0
             if owner == self.rank:
                 self.local.array[index & ((1 << self.n_local) - 1)] = 1
-        self.backend.barrier()
+        getattr(self.backend, 'device_barrier', self.backend.barrier)()
 
     def _rank_bit(self, phys_bit: int) -> int:
         return (self.rank >> (phys_bit - self.n_local)) & 1
@@ -341,9 +354,10 @@ class ShardedStateVector:
     def norm2(self) -> float:
         return self.backend.all_reduce_sum(self.local.norm2())
 
-    def sample(self, repetitions: int, seed=None) -> np.ndarray:
-        """uint8[reps, n] bitstrings (column a = logical qubit axis a, i.e. logical
-        bit n-1-a) drawn from |psi|^2; identical on every rank.  Every rank draws
+    def sample(self, repetitions: int, seed=None, axes: Sequence[int] | None = None) -> np.ndarray:
+        """uint8[reps, len(axes)] bitstrings (column i = logical qubit axis axes[i],
+        i.e. logical bit n-1-axes[i]; all n axes in order by default) drawn from
+        |psi|^2; identical on every rank.  Every rank draws
         the same uniforms; a sample belongs to the rank whose cumulative
         probability interval contains it and is resolved there by the 1-GPU
         sampler."""
@@ -357,7 +371,7 @@ class ShardedStateVector:
         before = cum[self.rank] - totals[self.rank]
         local_u = np.clip((target[mine] - before) / max(totals[self.rank], 1e-300), 0.0, 1.0 - 2**-53)
         # column `axis` of the result is logical bit n-1-axis = physical bit phys[...]
-        bits = [self.phys[self.n - 1 - axis] for axis in range(self.n)]
+        bits = [self.phys[self.n - 1 - axis] for axis in (range(self.n) if axes is None else axes)]
         return self.backend.merge_samples(repetitions, mine, local_u, bits)
 
     def gather_state(self) -> np.ndarray:
@@ -458,14 +472,18 @@ class B200ShardedSimulator:
         sv = ShardedStateVector(len(qubits), self.dtype, group=self.group,
                                 backend=self._backend_for(len(qubits)))
         sv.apply_blocks(fuse_gates(gates, self.max_fused, self.dtype, sv.n_local))
-        bits = sv.sample(repetitions, seed=self.seed)
         axis = {q: i for i, q in enumerate(qubits)}
+        cols = [axis[q] for op in measured for q in op.qubits]
+        # only the measured columns leave the device, already in result order
+        bits = sv.sample(repetitions, seed=self.seed, axes=cols).view(np.int8)
         out = {}
+        start = 0
         for op in measured:
-            cols = [axis[q] for q in op.qubits]
-            arr = bits[:, cols].astype(np.int8)
+            arr = bits[:, start:start + len(op.qubits)]
+            start += len(op.qubits)
             inv = [i for i, f in enumerate(op.gate.full_invert_mask()) if f]
             if inv:
+                arr = arr.copy()
                 arr[:, inv] ^= 1
             out[op.gate.key] = arr
         return out

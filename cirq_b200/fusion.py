@@ -25,6 +25,8 @@ from __future__ import annotations
 
 from typing import Iterable, Sequence
 
+import os
+
 import numpy as np
 
 
@@ -246,16 +248,20 @@ class GateFuser:
 
 def fuser_for(dtype, max_qubits: int | None = None, n_bits: int | None = None) -> 'GateFuser':
     """The fusion policy matched to the kernels: complex64 fuses
-    up to 5 wires (tensor-core kernel) except on index bits 0-1, where 8-byte
-    lanes would split 32-byte sectors, and for states too small for that
-    kernel; complex128 up to 4.  (A 6-qubit tensor-core kernel exists and is
-    selected with max_qubits=6, but at 5.2 ms per 30-qubit pass against 2.7 ms
-    for 5 qubits it does not pay for the passes it saves.)"""
+    up to 5 wires (tensor-core kernels; blocks touching index bits 0-1 take the
+    shared-memory-staged variant, so no wire needs a narrower cap any more —
+    ``CIRQ_B200_NARROW_WIRES=0,1`` restores the old cap of 4 on those wires for
+    experiments), except for states too small for that kernel; complex128 up to
+    4.  (A 6-qubit tensor-core kernel exists and is selected with max_qubits=6,
+    but at 5.2 ms per 30-qubit pass against 2.7 ms for 5 qubits it does not pay
+    for the passes it saves.)"""
     is_c64 = np.dtype(dtype) == np.dtype(np.complex64)
     if max_qubits is None:
         max_qubits = 5 if is_c64 and (n_bits is None or n_bits >= 12) else 4
     if is_c64 and max_qubits >= 5:
-        return GateFuser(max_qubits, narrow_wires=(0, 1), narrow_max=4)
+        narrow = os.environ.get('CIRQ_B200_NARROW_WIRES', '')
+        wires = tuple(int(w) for w in narrow.split(',') if w.strip())
+        return GateFuser(max_qubits, narrow_wires=wires, narrow_max=4)
     return GateFuser(max_qubits)
 
 

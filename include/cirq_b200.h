@@ -247,11 +247,23 @@ int b2q_set_vec_mode(int mode);
 /* Tensor-core (tcgen05) kernels for complex64 blocks: 0 = off, 1 = k = 5 and 6
  * (default), 2 = also k = 4. */
 int b2q_set_tc_mode(int mode);
+/* Shared-memory staging of the tensor-core kernels (coalesced HBM access for any
+ * target positions): 0 = never, 1 = when a target sits on index bit 0 or 1
+ * (default), 2 = always. */
+int b2q_set_tc_stage_mode(int mode);
+/* Staged kernel pipeline experiments (profiles/README.md, r1p): early = 1 issues the
+ * next region's copy at the top of an iteration instead of after the operands are in
+ * TMEM (default 0), l2_ahead > 0 adds an L2 prefetch that many iterations ahead
+ * (default 0; both measured slower under the power cap). */
+int b2q_set_tc_stage_opts(int early, int l2_ahead);
 /* Host-only: the register kernel's plan for a target set (see
  * tests/test_plan_host.py for the layout of `out`, 24 ints) and the matrix
  * permutation to sorted-target order; no GPU needed. */
 int b2q_debug_plan(int dtype, int n_qubits, const int* targets, int k, int* out);
 int b2q_debug_permute_matrix(const double* matrix_c128, const int* targets, int k, double* out);
+/* Host-only: address tables of the staged tensor-core kernel for ascending
+ * targets (layout of `out`, 86 int64: see tests/test_plan_host.py). */
+int b2q_debug_tc_stage_plan(int n_qubits, const int* sorted_targets, int k, int64_t* out);
 
 #ifdef __cplusplus
 }

@@ -101,6 +101,9 @@ def test_tensor_core_kernels_match_oracle(DS, k):
     rng = np.random.RandomState(60 + k)
     for n in (k + 7, 16, 20):
         sets = [list(range(n - k, n)), list(range(k)), list(range(2, 2 + k))]
+        # low index bits pick the 16-byte / pair-exchange access patterns
+        sets += [list(range(1, 1 + k)), [0] + list(range(n - k + 1, n)), [1] + list(range(n - k + 1, n)),
+                 [0, 1] + list(range(n - k + 2, n)), [n - 1, 0, 3, 5, 2, 7][:k], [4, 1, n - 2, 6, 9, 3][:k]]
         sets += [rng.permutation(n)[:k].tolist() for _ in range(4)]
         for targets in sets:
             state = rand_state(rng, n, np.complex64)

@@ -291,3 +291,127 @@ def test_matrix_permutation_is_consistent_with_target_order():
         a = orc.apply_matrix(state, n, m, targets)
         b = orc.apply_matrix(state, n, pm, srt[::-1])
         np.testing.assert_allclose(a, b, atol=1e-12)
+
+
+# ---- staged tensor-core kernel: shared-memory layout ---------------------------
+# b2q_debug_tc_stage_plan layout (int64[86]): rpos[10] | p5 | gpos[5] | swz_src[3] |
+# swz_dst[3] | goff[16] | sreq[16] | smem_j[32].  The emulation replays both access
+# phases of sv_apply_tc_staged_kernel for one warp region: every element must land
+# where the group/member gather expects it, and no phase may have bank conflicts.
+
+def _stage_plan(lib, n, targets):
+    k = len(targets)
+    arr = (ctypes.c_int * k)(*targets)
+    out = (ctypes.c_int64 * 86)()
+    _lib.check(lib.b2q_debug_tc_stage_plan(n, arr, k, out))
+    o = list(out)
+    return dict(rpos=o[0:k + 5], p5=o[10], gpos=o[11:16], src=o[16:19], dst=o[19:22],
+                goff=o[22:22 + (1 << (k - 1))], sreq=o[38:38 + (1 << (k - 1))], smem_j=o[54:54 + (1 << k)])
+
+def _stage_swz(x, p):
+    for s, d in zip(p['src'], p['dst']):
+        x ^= ((x >> s) & 1) << d
+    return x
+
+def _stage_insert_zero_bits(x, pos):
+    for q in pos:
+        low = x & ((1 << q) - 1)
+        x = ((x >> q) << (q + 1)) | low
+    return x
+
+def _stage_check(lib, n, targets):
+    k = len(targets)
+    p = _stage_plan(lib, n, targets)
+    region = 1 << (k + 5)
+    free = [b for b in range(n) if b not in targets]
+    for wt in (0, 1, 5, (1 << (n - k - 5)) - 1):
+        base = _stage_insert_zero_bits(wt, p['rpos'])
+        smem = {}
+        # write phase
+        for r in range(1 << (k - 1)):
+            banks_q = {}
+            for lane in range(32):
+                goff = ((lane & 15) << 1) + ((lane >> 4) << p['p5'])
+                s = _stage_swz(lane << 1, p) ^ p['sreq'][r]
+                assert s % 2 == 0
+                for e in (0, 1):
+                    assert (s + e) not in smem
+                    smem[s + e] = base + goff + p['goff'][r] + e
+                q = lane // 8
+                banks_q.setdefault(q, set()).add((s >> 1) & 7)
+            for q, bs in banks_q.items():
+                assert len(bs) == 8, ('write conflict', targets, r, q)
+        assert sorted(smem) == list(range(region))
+        # all region elements distinct and the right set
+        want = set()
+        for g in range(32):
+            for j in range(1 << k):
+                idx = base
+                for i in range(5):
+                    if (g >> i) & 1: idx += 1 << free[i]
+                for b in range(k):
+                    if (j >> b) & 1: idx += 1 << targets[b]
+                want.add(idx)
+        assert set(smem.values()) == want
+        # read phase
+        vec = targets[0] == 0
+        for j in range(0, 1 << k, 2 if vec else 1):
+            groups = {}
+            for lane in range(32):
+                gl = 0
+                for i in range(5):
+                    if (lane >> i) & 1: gl |= 1 << p['gpos'][i]
+                s = _stage_swz(gl, p) ^ p['smem_j'][j]
+                idx = base
+                for i in range(5):
+                    if (lane >> i) & 1: idx += 1 << free[i]
+                for b in range(k):
+                    if (j >> b) & 1: idx += 1 << targets[b]
+                assert smem[s] == idx, (targets, lane, j)
+                if vec:
+                    assert s % 2 == 0 and smem[s + 1] == idx + 1
+                    groups.setdefault(lane // 8, set()).add((s >> 1) & 7)
+                else:
+                    groups.setdefault(lane // 16, set()).add(s & 15)
+            for q, bs in groups.items():
+                assert len(bs) == (8 if vec else 16), ('read conflict', targets, j, q, bs)
+
+
+def test_tc_staged_layout_is_a_conflict_free_bijection():
+    import ctypes  # noqa: F401
+
+    lib = _lib.load()
+    rng = np.random.RandomState(0)
+    for k in (4, 5):
+        for n in (k + 7, 14, 20, 30):
+            sets = [list(range(k)), list(range(1, k + 1)), list(range(n - k, n)),
+                    [0] + list(range(n - k + 1, n)), [1] + list(range(n - k + 1, n)),
+                    [0, 1] + list(range(n - k + 2, n))]
+            sets += [sorted(rng.permutation(n)[:k].tolist()) for _ in range(20)]
+            sets += [sorted(rng.permutation(min(n, 9))[:k].tolist()) for _ in range(20)]
+            for t in sets:
+                _stage_check(lib, n, t)
+
+
+# ---- C-ABI surface --------------------------------------------------------------
+
+def test_library_exports_every_symbol_the_header_declares():
+    """include/cirq_b200.h is the drop-in boundary: each declared entry point
+    must be exported by libcirq_b200.so and bound (with a signature) by the
+    ctypes loader.  No compute call is made, so this runs without a GPU."""
+    import os
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, 'include', 'cirq_b200.h')) as f:
+        text = re.sub(r'/\*.*?\*/', '', f.read(), flags=re.S)
+    declared = set(re.findall(r'\b(b2q_[a-z0-9_]+)\s*\(', text))
+    assert len(declared) >= 40
+    lib = _lib.load()
+    missing = [name for name in sorted(declared) if not hasattr(lib, name)]
+    assert not missing, f'declared in the header but not exported: {missing}'
+    bound = set(_lib.SIGNATURES) | set(_lib.DEBUG_SIGNATURES)
+    assert declared <= bound, f'no ctypes signature for: {sorted(declared - bound)}'
+    assert bound <= declared, f'bound but not declared in the header: {sorted(bound - declared)}'
+    assert lib.b2q_version() > 0
+    assert isinstance(lib.b2q_last_error(), bytes)

@@ -22,9 +22,48 @@ def rand_unitary(rng, k):
     return q * (np.diag(r) / np.abs(np.diag(r)))
 
 
+WARM_MS = 0.0
+CLOCKS = {}
+
+
+def _nvml_clock():
+    """(SM MHz, power W) right now, via NVML (None when unavailable)."""
+    try:
+        import pynvml
+
+        if not CLOCKS:
+            pynvml.nvmlInit()
+            CLOCKS['h'] = pynvml.nvmlDeviceGetHandleByIndex(0)
+        h = CLOCKS['h']
+        return (pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM),
+                pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+    except Exception:
+        return None
+
+
 def time_pass(dev, m, bits, reps):
     for _ in range(3):
         dev.apply_matrix(m, bits)
+    if WARM_MS > 0:
+        # sustained mode: keep the GPU under this kernel's load until clocks settle
+        torch.cuda.synchronize()
+        import time
+
+        t0 = time.perf_counter()
+        while (time.perf_counter() - t0) * 1e3 < WARM_MS:
+            for _ in range(20):
+                dev.apply_matrix(m, bits)
+            torch.cuda.synchronize()
+        start = torch.cuda.Event(enable_timing=True)
+        end = torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(reps):
+            dev.apply_matrix(m, bits)
+        end.record()
+        time.sleep(reps * 0.0027 * 0.6)
+        time_pass.last_clock = _nvml_clock()
+        torch.cuda.synchronize()
+        return start.elapsed_time(end) / reps
     torch.cuda.synchronize()
     start = torch.cuda.Event(enable_timing=True)
     end = torch.cuda.Event(enable_timing=True)
@@ -46,11 +85,25 @@ def main():
     ap.add_argument('--only', default='')
     ap.add_argument('--vec-mode', type=int, default=None)
     ap.add_argument('--tc-mode', type=int, default=None)
+    ap.add_argument('--tc-stage-mode', type=int, default=None)
+    ap.add_argument('--dense', action='store_true', help='start from a dense random state')
+    ap.add_argument('--stage-opts', default=None, help='early,l2_ahead for the staged TC kernel')
+    ap.add_argument('--warm-ms', type=float, default=0.0,
+                    help='sustained mode: run each class this long before timing it')
     args = ap.parse_args()
+    global WARM_MS
+    WARM_MS = args.warm_ms
     dtype = np.complex64 if args.dtype == 'c64' else np.complex128
     if args.tc_mode is not None:
         from cirq_b200 import _lib
         _lib.load().b2q_set_tc_mode(args.tc_mode)
+    if args.stage_opts is not None:
+        from cirq_b200 import _lib
+        e, a = (int(v) for v in args.stage_opts.split(','))
+        _lib.check(_lib.load().b2q_set_tc_stage_opts(e, a))
+    if args.tc_stage_mode is not None:
+        from cirq_b200 import _lib
+        _lib.load().b2q_set_tc_stage_mode(args.tc_stage_mode)
     if args.vec_mode is not None:
         from cirq_b200 import _lib
         _lib.load().b2q_set_vec_mode(args.vec_mode)
@@ -60,6 +113,11 @@ def main():
     n = args.n
     rng = np.random.RandomState(0)
     dev = DeviceState.basis(n, dtype, 0)
+    if args.dense:
+        # a dense random state: data-dependent power draw like a real circuit's
+        g = torch.Generator(device='cuda').manual_seed(1)
+        dev.tensor.normal_(generator=g)
+        dev.tensor.mul_(1.0 / float(np.sqrt(2.0 * (1 << n))))
     bytes_per_pass = 2 * dev.nbytes
     zb = 6 if dtype == np.complex64 else 5
     hi = n - 1
@@ -78,6 +136,12 @@ def main():
             'k5_high': [hi, hi - 1, hi - 2, hi - 3, hi - 4],
             'k5_lane_high': [2, 4, hi, hi - 1, hi - 2],
             'k5_lanes': [1, 2, 3, 4, 5],
+            'k5_bit0_high': [0, hi, hi - 1, hi - 2, hi - 3],
+            'k5_bit1_high': [1, hi, hi - 1, hi - 2, hi - 3],
+            'k5_bit01_high': [0, 1, hi, hi - 1, hi - 2],
+            'k5_low': [0, 1, 2, 3, 4],
+            'k5_bit0_mid': [0, 3, 7, 12, 20],
+            'k5_bit1_mid': [1, 3, 7, 12, 20],
         })
     results = {}
     if args.only:
@@ -87,7 +151,10 @@ def main():
         ms = time_pass(dev, m, bits, args.reps)
         gbs = bytes_per_pass / ms / 1e6
         results[name] = {'bits': bits, 'ms': ms, 'GBps': gbs}
-        print(f'{name:16s} bits={bits!s:28s} {ms:8.3f} ms  {gbs:8.1f} GB/s', flush=True)
+        clock = getattr(time_pass, 'last_clock', None)
+        if clock:
+            results[name]['sm_mhz'], results[name]['power_w'] = clock
+        print(f'{name:16s} bits={bits!s:28s} {ms:8.3f} ms  {gbs:8.1f} GB/s  {clock or ""}', flush=True)
     # reference points: torch copy (read+write) and the diagonal/scale kernels
     other = torch.empty_like(dev.tensor)
     for _ in range(3):
