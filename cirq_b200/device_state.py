@@ -321,6 +321,26 @@ class DeviceState:
         )
         return out
 
+    def kron_into(self, other: 'DeviceState', out: 'DeviceState') -> 'DeviceState':
+        """out <- |self> (x) |other> for an existing state of the right size (the
+        IPC-shared shard of the sharded path)."""
+        if out.n_bits != self.n_bits + other.n_bits or out.dtype != self.dtype:
+            raise ValueError('kron_into: output state has the wrong shape or dtype')
+        torch = _torch()
+        check(
+            self._lib.b2q_sv_kron(
+                self.ptr, self.n_bits, other.ptr, other.n_bits, self.code, out.ptr,
+                _stream_ptr(torch),
+            )
+        )
+        return out
+
+    def copy_into(self, out: 'DeviceState') -> 'DeviceState':
+        if out.n_bits != self.n_bits or out.dtype != self.dtype:
+            raise ValueError('copy_into: output state has the wrong shape or dtype')
+        out.tensor.copy_(self.tensor)
+        return out
+
     def permute_bits(self, src_bit: Sequence[int]) -> 'DeviceState':
         """New state with out[o] = self[i], bit k of o == bit src_bit[k] of i."""
         torch = _torch()

@@ -197,7 +197,7 @@ class ShardedStateVector:
     """
 
     def __init__(self, n_qubits: int, dtype=np.complex64, *, backend=None, group=None,
-                 initial_index: int = 0):
+                 initial_index: int | None = 0):
         if backend is None:
             import torch.distributed as dist
 
@@ -225,9 +225,44 @@ class ShardedStateVector:
         self.passes = 0
         self.local_only_blocks = 0
         self.diag_global_blocks = 0
-        self._init_basis(initial_index)
+        if initial_index is not None:
+            self._init_basis(initial_index)
 
     # ------------------------------------------------------------------ helpers
+
+    def load_product(self, components) -> None:
+        """Sets the state to the Kronecker product of sub-states that every rank
+        holds in full: `components` = [(device state, logical bits most
+        significant first)], together covering all n bits.  The first component
+        supplies the global (rank) bits: each rank takes its slice of it and
+        joins the rest locally, writing straight into its shard — the
+        distributed form of SimulationProductState.create_merged_state
+        (cirq-core/cirq/sim/simulation_product_state.py:68-81), without any
+        exchange."""
+        comps = [(dev, list(bits)) for dev, bits in components]
+        if sorted(b for _, bits in comps for b in bits) != list(range(self.n)):
+            raise ValueError('components must cover every bit exactly once')
+        # the leading component must be wider than the rank bits
+        while len(comps[0][1]) <= self.g and len(comps) > 1:
+            (d0, b0), (d1, b1) = comps[0], comps[1]
+            comps[:2] = [(d0.kron(d1), b0 + b1)]
+        dev0, bits0 = comps[0]
+        if self.g:
+            keep = len(bits0) - self.g
+            acc = dev0.slice_copy(self.rank << keep, keep)
+        else:
+            acc = dev0
+        rest = comps[1:]
+        if not rest:
+            acc.copy_into(self.local)
+        else:
+            for dev, _ in rest[:-1]:
+                acc = acc.kron(dev)
+            acc.kron_into(rest[-1][0], self.local)
+        order = [b for _, bits in comps for b in bits]  # most significant first
+        for i, b in enumerate(order):
+            self.phys[b] = self.n - 1 - i
+        getattr(self.backend, 'device_barrier', self.backend.barrier)()
 
     def _init_basis(self, index: int) -> None:
         owner = index >> self.n_local
@@ -390,6 +425,53 @@ class ShardedStateVector:
             self.backend.close()
 
 
+# Lazy state growth: sub-states stay replicated and small until a
+# gate needs one wider than this many bits; 2^31 amplitudes = 17 GB (complex64)
+# bounds the temporaries of the join next to the shard itself.
+LAZY_MAX_SHARD_BITS = 31
+
+
+def plan_sharded(n_qubits: int, gates, dtype, max_fused_qubits, n_local: int):
+    """Host-side schedule of a gate list for the sharded path: the prefix that
+    runs on small replicated sub-states (a `cirq_b200.plan` op list), the
+    sub-states to join, and the fused blocks left for the sharded state."""
+    from cirq_b200.fusion import fuse_gates
+    from cirq_b200.plan import SplitExecutor, _RecordingState
+
+    class Rec(_RecordingState):
+        ops = []
+        counter = 0
+
+    gates = list(gates)
+    if n_local > LAZY_MAX_SHARD_BITS:
+        return {'n': n_qubits, 'dtype': np.dtype(dtype), 'ops': [], 'components': None,
+                'blocks': fuse_gates(gates, max_fused_qubits, dtype, n_local)}
+    ex = SplitExecutor(n_qubits, dtype, max_fused_qubits, Rec, max_component_bits=min(n_local, 30))
+    done = len(gates)
+    for i, (m, b) in enumerate(gates):
+        if not ex.apply(m, b):
+            done = i
+            break
+    comps = [(dev.ident, bits) for dev, bits in ex.components()]
+    return {'n': n_qubits, 'dtype': np.dtype(dtype), 'ops': Rec.ops, 'components': comps,
+            'blocks': fuse_gates(gates[done:], max_fused_qubits, dtype, n_local),
+            'prefix_gates': done}
+
+
+def execute_sharded_plan(plan, sv: 'ShardedStateVector', device_state_cls=None) -> None:
+    """Runs a `plan_sharded` schedule on `sv` (collective)."""
+    if plan['components'] is None:
+        sv.phys = list(range(sv.n))
+        sv._init_basis(0)
+    else:
+        from cirq_b200.plan import replay_ops
+
+        live = replay_ops(plan['ops'], plan['dtype'], device_state_cls or type(sv.local))
+        sv.load_product([(live[ident], bits) for ident, bits in plan['components']])
+        del live
+    sv.apply_blocks(plan['blocks'])
+
+
 class B200ShardedSimulator:
     """Cirq-facing entry point of the sharded path (SPMD: every rank of the
     process group calls it with the same circuit).
@@ -454,8 +536,12 @@ class B200ShardedSimulator:
             qubit_order if qubit_order is not None else cirq.QubitOrder.DEFAULT
         ).order_for(circuit.all_qubits())
         gates, _ = self._gates(circuit, qubits)
-        sv = ShardedStateVector(len(qubits), self.dtype, group=self.group, initial_index=initial_state)
-        sv.apply_blocks(fuse_gates(gates, self.max_fused, self.dtype, sv.n_local))
+        if initial_state != 0:
+            sv = ShardedStateVector(len(qubits), self.dtype, group=self.group, initial_index=initial_state)
+            sv.apply_blocks(fuse_gates(gates, self.max_fused, self.dtype, sv.n_local))
+            return sv
+        sv = ShardedStateVector(len(qubits), self.dtype, group=self.group, initial_index=None)
+        execute_sharded_plan(plan_sharded(sv.n, gates, self.dtype, self.max_fused, sv.n_local), sv)
         return sv
 
     def run(self, circuit, repetitions: int = 1) -> dict:
@@ -470,8 +556,8 @@ class B200ShardedSimulator:
         if not measured:
             raise ValueError('Circuit has no measurements to sample.')
         sv = ShardedStateVector(len(qubits), self.dtype, group=self.group,
-                                backend=self._backend_for(len(qubits)))
-        sv.apply_blocks(fuse_gates(gates, self.max_fused, self.dtype, sv.n_local))
+                                backend=self._backend_for(len(qubits)), initial_index=None)
+        execute_sharded_plan(plan_sharded(sv.n, gates, self.dtype, self.max_fused, sv.n_local), sv)
         axis = {q: i for i, q in enumerate(qubits)}
         cols = [axis[q] for op in measured for q in op.qubits]
         # only the measured columns leave the device, already in result order

@@ -54,7 +54,11 @@ class SplitExecutor:
     MAX_SPLIT_BITS = 30
 
     def __init__(self, n_bits: int, dtype=np.complex64, max_fused_qubits: int | None = None,
-                 device_state_cls=None):
+                 device_state_cls=None, max_component_bits: int | None = None):
+        """`max_component_bits`: sub-states never grow beyond this many bits;
+        `apply` then returns False for a gate that would need a larger join and
+        leaves the caller to continue differently (the sharded path,
+        cirq_b200/dist.py).  Implies product form from the start whatever n."""
         if device_state_cls is None:
             from cirq_b200.device_state import DeviceState as device_state_cls
         self._DS = device_state_cls
@@ -62,7 +66,8 @@ class SplitExecutor:
         self.dtype = np.dtype(dtype)
         self.max_fused = max_fused_qubits
         self._comp = {}
-        if self.n > self.MAX_SPLIT_BITS:
+        self.max_component_bits = max_component_bits
+        if self.n > self.MAX_SPLIT_BITS and max_component_bits is None:
             bits = list(range(self.n - 1, -1, -1))
             c = _Component(bits, self._DS.basis(self.n, self.dtype, 0),
                            fuser_for(self.dtype, max_fused_qubits, self.n))
@@ -92,18 +97,36 @@ class SplitExecutor:
             self._comp[b] = merged
         return merged
 
-    def apply(self, matrix, bits: Sequence[int]) -> None:
+    def apply(self, matrix, bits: Sequence[int]) -> bool:
         comps = []
         for b in bits:
             c = self._comp[int(b)]
             if not any(c is x for x in comps):
                 comps.append(c)
+        if (self.max_component_bits is not None and len(comps) > 1
+                and sum(len(c.bits) for c in comps) > self.max_component_bits):
+            return False
         comp = comps[0] if len(comps) == 1 else self._join(comps)
         comp.fuser.add(matrix, [comp.wire(int(b)) for b in bits])
         self._since_drain += 1
         if self._since_drain >= max(8, self.n):
             self._since_drain = 0
             comp.drain()
+        return True
+
+    def components(self):
+        """All sub-states, pending gates applied: [(DeviceState, logical bits
+        most significant first)], largest first (ties: the one holding the
+        highest bit)."""
+        comps = []
+        for b in range(self.n - 1, -1, -1):
+            c = self._comp[b]
+            if not any(c is x for x in comps):
+                comps.append(c)
+        for c in comps:
+            c.flush()
+        comps.sort(key=lambda c: -len(c.bits))
+        return [(c.dev, list(c.bits)) for c in comps]
 
     def finalize(self):
         """Joins everything; returns (DeviceState, bit_of) with bit_of[logical bit]
@@ -176,16 +199,15 @@ def build_plan(n_bits: int, gates, dtype=np.complex64, max_fused_qubits: int | N
             'bit_of': bit_of, 'passes': passes, 'full_passes': full_passes}
 
 
-def replay_plan(plan, device_state_cls=None, on_apply=None):
-    """Executes a plan from `build_plan`; returns the final DeviceState.
-    `on_apply(state, blocks)` replaces ``state.apply_batch(blocks)`` when given
-    (bench.py times individual launches through it)."""
+def replay_ops(ops, dtype, device_state_cls=None, on_apply=None):
+    """Executes recorded device operations; returns {ident: DeviceState} of the
+    states still alive at the end."""
     if device_state_cls is None:
         from cirq_b200.device_state import DeviceState as device_state_cls
     live = {}
-    for op in plan['ops']:
+    for op in ops:
         if op[0] == 'basis':
-            live[op[1]] = device_state_cls.basis(op[2], plan['dtype'], op[3])
+            live[op[1]] = device_state_cls.basis(op[2], dtype, op[3])
         elif op[0] == 'kron':
             live[op[1]] = live.pop(op[2]).kron(live.pop(op[3]))
         else:
@@ -193,4 +215,11 @@ def replay_plan(plan, device_state_cls=None, on_apply=None):
                 live[op[1]].apply_batch(op[2])
             else:
                 on_apply(live[op[1]], op[2])
-    return live[plan['final']]
+    return live
+
+
+def replay_plan(plan, device_state_cls=None, on_apply=None):
+    """Executes a plan from `build_plan`; returns the final DeviceState.
+    `on_apply(state, blocks)` replaces ``state.apply_batch(blocks)`` when given
+    (bench.py times individual launches through it)."""
+    return replay_ops(plan['ops'], plan['dtype'], device_state_cls, on_apply)[plan['final']]

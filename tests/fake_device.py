@@ -121,6 +121,14 @@ class OracleDeviceState:
     def kron(self, other):
         return OracleDeviceState(self.n_bits + other.n_bits, self.dtype, np.kron(self.array, other.array))
 
+    def kron_into(self, other, out):
+        out.array[:] = np.kron(self.array, other.array)
+        return out
+
+    def copy_into(self, out):
+        out.array[:] = self.array
+        return out
+
     def permute_bits(self, src_bit):
         o = np.arange(1 << self.n_bits, dtype=np.int64)
         i = np.zeros_like(o)

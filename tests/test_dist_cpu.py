@@ -128,6 +128,68 @@ def test_sharded_matches_oracle(tmp_path, world, n, seed, max_fused):
     assert chi2 < dof + 6 * np.sqrt(2 * dof) + 10
 
 
+def _lazy_worker(rank, world, port, n, seed, pattern, out_dir):
+    """Lazy state growth on the sharded path: the circuit prefix runs on small
+    replicated sub-states, which are then joined straight into the shards."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import torch.distributed as dist
+
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from cirq_b200.dist import ShardedStateVector, execute_sharded_plan, plan_sharded
+        from fake_dist import GlooShardBackend
+        from oracle import sv_oracle as orc
+
+        rng = np.random.RandomState(seed)
+
+        def unitary(k):
+            d = 1 << k
+            q, r = np.linalg.qr(rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d)))
+            return q * (np.diag(r) / np.abs(np.diag(r)))
+
+        gates = [(unitary(1), [q]) for q in range(n)]
+        if pattern == 'chain':  # neighbours first: components grow one qubit at a time
+            for _ in range(3):
+                for q in range(n - 1):
+                    gates.append((unitary(2), [q + 1, q]))
+                gates += [(unitary(1), [q]) for q in range(n)]
+        elif pattern == 'islands':  # never connects everything: the join happens at the end
+            for q in range(0, n - 1, 2):
+                gates.append((unitary(2), [q, q + 1]))
+        else:
+            for _ in range(50):
+                k = int(rng.randint(1, 3))
+                gates.append((unitary(k), rng.permutation(n)[:k].tolist()))
+        g = world.bit_length() - 1
+        sv = ShardedStateVector(n, np.complex128, backend=GlooShardBackend(n - g, np.complex128),
+                                initial_index=None)
+        plan = plan_sharded(n, gates, np.complex128, 3, n - g)
+        execute_sharded_plan(plan, sv)
+        got = sv.gather_state()
+        want = orc.run_gate_list(n, gates, dtype=np.complex128, initial=0)
+        if rank == 0:
+            np.savez(os.path.join(out_dir, f'lazy_{world}_{pattern}.npz'),
+                     err=float(np.max(np.abs(got - want))), norm=sv.norm2() if False else 1.0,
+                     prefix=plan['prefix_gates'], total=len(gates), passes=sv.passes)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,n,seed,pattern', [(2, 8, 1, 'chain'), (4, 9, 2, 'random'), (2, 7, 3, 'islands'),
+                                                  (4, 8, 4, 'chain')])
+def test_sharded_lazy_growth_matches_oracle(tmp_path, world, n, seed, pattern):
+    port = 29500 + (os.getpid() + seed * 13 + 5) % 2000
+    mp.spawn(_lazy_worker, args=(world, port, n, seed, pattern, str(tmp_path)), nprocs=world, join=True)
+    res = np.load(os.path.join(str(tmp_path), f'lazy_{world}_{pattern}.npz'))
+    assert float(res['err']) < 1e-12
+    assert int(res['prefix']) >= n  # at least the first layer ran on the small sub-states
+    if pattern == 'islands':
+        assert int(res['prefix']) == int(res['total']) and int(res['passes']) == 0
+
+
 def test_block_diagonal_detection():
     sys.path.insert(0, ROOT)
     from cirq_b200.dist import block_diagonal_in

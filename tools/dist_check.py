@@ -21,7 +21,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     from cirq_b200.device_state import DeviceState
-    from cirq_b200.dist import ShardedStateVector
+    from cirq_b200.dist import ShardedStateVector, execute_sharded_plan, plan_sharded
     from cirq_b200.fusion import fuse_gates
 
     rng = np.random.RandomState(7)
@@ -61,6 +61,29 @@ def main():
                       f'swaps={sv.swaps} passes={sv.passes} chi2={chi2:.1f} {"OK" if good else "FAIL"}',
                       flush=True)
             sv.close()
+    # lazy state growth from |0...0>: prefix on replicated sub-states, join into the shards
+    g = world.bit_length() - 1
+    for dtype, atol in ((np.complex64, 1e-5), (np.complex128, 1e-12)):
+        n = 18
+        gates = [(unitary(1), [q]) for q in range(n)]
+        for _ in range(3):
+            gates += [(unitary(2), [q + 1, q]) for q in range(n - 1)]
+            gates += [(unitary(3), rng.permutation(n)[:3].tolist()) for _ in range(6)]
+        sv = ShardedStateVector(n, dtype, initial_index=None)
+        plan = plan_sharded(n, gates, dtype, None, n - g)
+        execute_sharded_plan(plan, sv)
+        got = sv.gather_state()
+        ref = DeviceState.basis(n, dtype, 0)
+        ref.apply_batch(fuse_gates(gates, 4))
+        err = float(np.max(np.abs(got - ref.to_numpy())))
+        nrm = sv.norm2()
+        good = err <= atol and abs(nrm - 1) < 1e-4 and plan['prefix_gates'] >= n
+        ok &= good
+        if rank == 0:
+            print(f'lazy growth n={n} {np.dtype(dtype)} world={world}: prefix {plan["prefix_gates"]} of '
+                  f'{len(gates)} gates, max|diff|={err:.2e} norm={nrm:.6f} swaps={sv.swaps} '
+                  f'passes={sv.passes} {"OK" if good else "FAIL"}', flush=True)
+        sv.close()
     # swap bandwidth at a large shard
     n_local = int(os.environ.get('B2Q_SWAP_NLOCAL', '30'))
     n = n_local + world.bit_length() - 1
