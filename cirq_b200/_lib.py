@@ -92,6 +92,8 @@ SIGNATURES = {
     'b2q_dist_ipc_close': (c_int, [c_void_p]),
     'b2q_dist_swap_bit': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'b2q_dist_pack': (c_int, [c_void_p, c_int, c_int, POINTER(c_int), c_int, c_void_p, c_void_p]),
+    'b2q_dist_apply_exchange': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                                        POINTER(c_int), c_int, c_int, c_int, c_void_p]),
     'b2q_dist_unpack': (c_int, [c_void_p, c_int, c_int, POINTER(c_int), c_int, c_void_p, c_void_p]),
 }
 

@@ -702,6 +702,8 @@ int apply_generic(void* state, int n, const int* sorted, int K, const real* mat,
 // b2q_apply_tc.cu
 bool tc_applicable(int dtype, int n, int K);
 int launch_tc(void* state, int n, int K, const int* sorted, const float* mat, cudaStream_t stream);
+int launch_tc_exchange(void* state, int n, int K, const int* sorted, const float* mat,
+                       void* out_local, void* out_peer, int xbit, int gval, cudaStream_t stream);
 
 template <typename real>
 int apply_matrix_t(void* state, int dtype, int n, const double* m128, const int* targets, int K,
@@ -842,6 +844,34 @@ extern "C" int b2q_set_lane_mode(int mode) {
 // Host-only: exposes the fast-path plan for unit tests (no GPU needed).
 // out[0]=feasible, [1]=S, [2]=GT, [3]=swaps, [4]=n_ins, [5..10]=ins_pos,
 // [11..16]=log2(reg_off) or -1, [17..22]=swap_lane, [23]=log2(num_items).
+extern "C" int b2q_dist_apply_exchange(const void* shard_in, void* out_local, void* out_peer,
+                                       int dtype, int n_local, const double* matrix_c128,
+                                       const int* targets, int k, int local_bit,
+                                       int my_global_bit_value, void* stream) {
+  B2Q_REQUIRE(shard_in != nullptr && out_local != nullptr && out_peer != nullptr &&
+                  matrix_c128 != nullptr && targets != nullptr,
+              "null argument");
+  B2Q_REQUIRE(shard_in != out_local, "the fused exchange is out of place");
+  B2Q_REQUIRE(dtype == B2Q_C64, "fused apply+exchange is complex64 only");
+  B2Q_REQUIRE(k == 4 || k == 5, "fused apply+exchange needs a 4- or 5-qubit block, got %d", k);
+  B2Q_REQUIRE(n_local >= k + 7, "shard too small: %d local qubits", n_local);
+  B2Q_REQUIRE(local_bit >= 1 && local_bit < n_local, "local bit %d must be in [1, %d)", local_bit,
+              n_local);
+  B2Q_REQUIRE(my_global_bit_value == 0 || my_global_bit_value == 1, "bad global bit value");
+  int sorted[8];
+  for (int i = 0; i < k; ++i) sorted[i] = targets[i];
+  std::sort(sorted, sorted + k);
+  for (int i = 0; i < k; ++i) {
+    B2Q_REQUIRE(sorted[i] >= 0 && sorted[i] < n_local, "target bit %d out of range", sorted[i]);
+    B2Q_REQUIRE(i == 0 || sorted[i] != sorted[i - 1], "duplicate target bit %d", sorted[i]);
+  }
+  std::vector<float> plain((size_t)2 << (2 * k));
+  permute_matrix<float>(matrix_c128, targets, sorted, k, plain.data(), /*packed=*/false);
+  return launch_tc_exchange(const_cast<void*>(shard_in), n_local, k, sorted, plain.data(), out_local,
+                            out_peer, local_bit, my_global_bit_value,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" int b2q_debug_plan(int dtype, int n_qubits, const int* targets, int k, int* out) {
   int sorted[16];
   for (int i = 0; i < k; ++i) sorted[i] = targets[i];

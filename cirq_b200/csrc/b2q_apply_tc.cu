@@ -373,6 +373,15 @@ struct TcStagedParams {
   int gpos[5];               // local positions of the 5 group bits (lane bit i)
   int swz_src[3];            // local bit swz_src[i] (>= 4, or 20 = unused) is XORed ...
   int swz_dst[3];            // ... into local bit swz_dst[i] (1..3)
+  // Results go to out_local (== state for an in-place pass).  With xbit >= 0 the
+  // pass is fused with a global<->local qubit exchange (b2q_dist_apply_exchange):
+  // an amplitude whose index bit `xbit` differs from this rank's global bit value
+  // `gval` is stored into the PARTNER's buffer out_peer (peer memory over
+  // NVLink), with that bit set to gval; the others stay in out_local.
+  float2* out_local;
+  float2* out_peer;
+  int xbit;
+  int gval;
   int early;      // 1: the next region's copy is issued at the top of the iteration
   int l2_ahead;   // > 0: regions this many iterations ahead are prefetched into L2
   uint64_t goff[1 << (kStageMaxK - 1)];  // request r -> element offset in the state
@@ -582,17 +591,28 @@ __global__ void __launch_bounds__(kTcThreads, TcTraits<K>::kMinBlocks)
     __syncwarp();
     // region -> HBM, 512 contiguous bytes per warp request
     {
-      float2* const dst = p.state + base + lane_goff;
       constexpr int kBatch = kReq < 8 ? kReq : 8;
+      const uint64_t idx0 = base + lane_goff;
 #pragma unroll
       for (int r0 = 0; r0 < kReq; r0 += kBatch) {
         float4 v[kBatch];
 #pragma unroll
         for (int r = 0; r < kBatch; ++r)
           v[r] = *reinterpret_cast<const float4*>(sbuf + ((lane_s ^ p.sreq[r0 + r]) << 3));
+        if (p.xbit < 0) {
 #pragma unroll
-        for (int r = 0; r < kBatch; ++r)
-          *reinterpret_cast<float4*>(dst + p.goff[r0 + r]) = v[r];
+          for (int r = 0; r < kBatch; ++r)
+            *reinterpret_cast<float4*>(p.out_local + idx0 + p.goff[r0 + r]) = v[r];
+        } else {
+#pragma unroll
+          for (int r = 0; r < kBatch; ++r) {
+            const uint64_t idx = idx0 + p.goff[r0 + r];
+            const bool stays = (int)((idx >> p.xbit) & 1ull) == p.gval;
+            const uint64_t idx2 = (idx & ~(1ull << p.xbit)) | ((uint64_t)p.gval << p.xbit);
+            float2* const buf = stays ? p.out_local : p.out_peer;
+            *reinterpret_cast<float4*>(buf + idx2) = v[r];
+          }
+        }
       }
     }
     __syncwarp();  // this buffer is refilled by the prefetch issued one iteration later
@@ -787,10 +807,19 @@ static int launch_tc_staged_kernel(const TcStagedParams& p, cudaStream_t stream)
   return B2Q_OK;
 }
 
+struct TcExchange {
+  void* out_local;
+  void* out_peer;
+  int xbit;
+  int gval;
+};
+
 // `mat` = gate matrix in sorted-target order (index bit i <-> i-th lowest
-// target), plain (re, im) float pairs, row-major 2^K x 2^K.
+// target), plain (re, im) float pairs, row-major 2^K x 2^K.  `ex` != nullptr:
+// out-of-place pass fused with a qubit exchange (staged kernel only).
 template <int K>
-int launch_tc_k(void* state, int n, const int* sorted, const float* mat, cudaStream_t stream) {
+int launch_tc_k(void* state, int n, const int* sorted, const float* mat, cudaStream_t stream,
+                const TcExchange* ex = nullptr) {
   constexpr int kTcK = K;
   constexpr int kTcDim = TcTraits<K>::kDim;
   constexpr int kTcN = TcTraits<K>::kN;
@@ -831,12 +860,16 @@ int launch_tc_k(void* state, int n, const int* sorted, const float* mat, cudaStr
   const int stage_mode = g_tc_stage_mode.load(std::memory_order_relaxed);
   int rc;
   if constexpr (K <= kStageMaxK) {
-    if (stage_mode == 2 || (stage_mode == 1 && low != 0)) {
+    if (ex != nullptr || stage_mode == 2 || (stage_mode == 1 && low != 0)) {
       TcStagedParams sp;
       sp.state = p.state;
       sp.num_tiles = p.num_tiles;
       sp.bmat = dmat;
       make_staged_params(n, K, sorted, &sp);
+      sp.out_local = ex ? reinterpret_cast<float2*>(ex->out_local) : p.state;
+      sp.out_peer = ex ? reinterpret_cast<float2*>(ex->out_peer) : nullptr;
+      sp.xbit = ex ? ex->xbit : -1;
+      sp.gval = ex ? ex->gval : 0;
       sp.early = g_tc_stage_early.load(std::memory_order_relaxed);
       sp.l2_ahead = g_tc_stage_l2_ahead.load(std::memory_order_relaxed);
       rc = low == 1 ? launch_tc_staged_kernel<K, true>(sp, stream)
@@ -846,6 +879,7 @@ int launch_tc_k(void* state, int n, const int* sorted, const float* mat, cudaStr
       return B2Q_OK;
     }
   }
+  if (ex != nullptr) return set_error(B2Q_ERR_INVALID, "exchange needs the staged kernel (k <= 5)");
   if (low == 1)
     rc = launch_tc_kernel<K, 1>(p, stream);
   else if (low == 2)
@@ -855,6 +889,13 @@ int launch_tc_k(void* state, int n, const int* sorted, const float* mat, cudaStr
   if (rc != B2Q_OK) return rc;
   B2Q_CUDA_CHECK(cudaEventRecord(ring->done[slot], stream));
   return B2Q_OK;
+}
+
+int launch_tc_exchange(void* state, int n, int K, const int* sorted, const float* mat,
+                       void* out_local, void* out_peer, int xbit, int gval, cudaStream_t stream) {
+  const TcExchange ex{out_local, out_peer, xbit, gval};
+  if (K == 4) return launch_tc_k<4>(state, n, sorted, mat, stream, &ex);
+  return launch_tc_k<5>(state, n, sorted, mat, stream, &ex);
 }
 
 int launch_tc(void* state, int n, int K, const int* sorted, const float* mat, cudaStream_t stream) {

@@ -33,6 +33,11 @@ from cirq_b200 import _lib
 from cirq_b200._lib import check
 
 
+# Shards up to this many bits (17 GB complex64) get a second buffer for the fused
+# gate + exchange kernel.
+FUSED_EXCHANGE_MAX_BITS = 31
+
+
 def block_diagonal_in(matrix: np.ndarray, wires: Sequence[int], diag_wires: Sequence[int], atol=0.0):
     """If `matrix` (on `wires`, wires[0] = MSB) never changes the basis value of
     `diag_wires`, returns {values tuple -> sub-matrix on the remaining wires};
@@ -92,30 +97,59 @@ class ShardBackend:
         self.dtype = np.dtype(dtype)
         self.lib = _lib.load()
         code = _lib.dtype_code(self.dtype)
-        nbytes = (1 << n_local) * (8 if code == _lib.C64 else 16)
+        self._nbytes = (1 << n_local) * (8 if code == _lib.C64 else 16)
+        # Buffer 0 is the shard.  A second, equally shared buffer makes the fused
+        # gate + exchange kernel possible (it is out of place); it is only worth
+        # its memory while shards are small next to the 180 GB of HBM.
+        self.can_fuse_exchange = bool(code == _lib.C64 and 12 <= n_local <= FUSED_EXCHANGE_MAX_BITS)
+        self._bufs, self._states, self._peers = [], [], []
+        for _ in range(2 if self.can_fuse_exchange else 1):
+            self._add_buffer()
+        self._cur = 0
+        self._token = torch.zeros(1, dtype=torch.int32, device='cuda')
+        self.barrier()
+
+    def _add_buffer(self) -> None:
+        """Allocates one shard-sized buffer and maps every peer's (collective)."""
+        from cirq_b200.device_state import DeviceState
+
+        torch, dist = self.torch, self.dist
+        code = _lib.dtype_code(self.dtype)
         ptr = ctypes.c_void_p()
-        check(self.lib.b2q_dist_alloc(ctypes.c_uint64(nbytes), ctypes.byref(ptr)))
-        self._ptr = ptr.value
-        raw = _RawShard(self._ptr, 1 << n_local, '<f4' if code == _lib.C64 else '<f8')
-        self._raw = raw
+        check(self.lib.b2q_dist_alloc(ctypes.c_uint64(self._nbytes), ctypes.byref(ptr)))
+        raw = _RawShard(ptr.value, 1 << self.n_local, '<f4' if code == _lib.C64 else '<f8')
         tensor = torch.as_tensor(raw, device='cuda')
-        self.local = DeviceState(n_local, self.dtype, tensor=tensor)
-        # exchange IPC handles
+        state = DeviceState(self.n_local, self.dtype, tensor=tensor)
+        state._raw_owner = raw
         handle = (ctypes.c_ubyte * 64)()
-        check(self.lib.b2q_dist_ipc_get(ctypes.c_void_p(self._ptr), handle))
+        check(self.lib.b2q_dist_ipc_get(ctypes.c_void_p(ptr.value), handle))
         mine = torch.tensor(list(handle), dtype=torch.uint8, device='cuda')
         gathered = [torch.empty_like(mine) for _ in range(self.world)]
-        dist.all_gather(gathered, mine, group=group)
-        self.peer_ptrs = {}
+        dist.all_gather(gathered, mine, group=self.group)
+        peers = {}
         for r, h in enumerate(gathered):
             if r == self.rank:
                 continue
             buf = (ctypes.c_ubyte * 64)(*h.cpu().tolist())
             out = ctypes.c_void_p()
             check(self.lib.b2q_dist_ipc_open(buf, ctypes.byref(out)))
-            self.peer_ptrs[r] = out.value
-        self._token = torch.zeros(1, dtype=torch.int32, device='cuda')
-        self.barrier()
+            peers[r] = out.value
+        self._bufs.append(ptr.value)
+        self._states.append(state)
+        self._peers.append(peers)
+
+    @property
+    def local(self):
+        """The buffer that currently holds this rank's shard."""
+        return self._states[self._cur]
+
+    @property
+    def _ptr(self):
+        return self._bufs[self._cur]
+
+    @property
+    def peer_ptrs(self):
+        return self._peers[self._cur]
 
     def barrier(self):
         """Host barrier: this rank's stream is drained, then all ranks meet."""
@@ -140,6 +174,25 @@ class ShardBackend:
             )
         )
         self.device_barrier()
+
+    def apply_exchange(self, matrix, bits: Sequence[int], partner: int, local_bit: int,
+                       my_gbit: int) -> None:
+        """One 4/5-qubit block and the exchange of `local_bit` with the pair's
+        global bit in a single kernel: reads the current buffer, writes the spare
+        ones (its own and the partner's), which then become current."""
+        other = 1 - self._cur
+        m = np.ascontiguousarray(matrix, dtype=np.complex128)
+        self.device_barrier()
+        stream = ctypes.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+        check(
+            self.lib.b2q_dist_apply_exchange(
+                ctypes.c_void_p(self._bufs[self._cur]), ctypes.c_void_p(self._bufs[other]),
+                ctypes.c_void_p(self._peers[other][partner]), self.local.code, self.n_local,
+                m.ctypes.data, _lib.int_array(list(bits)), len(bits), local_bit, my_gbit, stream,
+            )
+        )
+        self.device_barrier()
+        self._cur = other
 
     def all_reduce_sum(self, value: float) -> float:
         t = self.torch.tensor([value], dtype=self.torch.float64, device='cuda')
@@ -179,14 +232,15 @@ class ShardBackend:
 
     def close(self):
         self.barrier()
-        for p in self.peer_ptrs.values():
-            self.lib.b2q_dist_ipc_close(ctypes.c_void_p(p))
-        self.peer_ptrs = {}
+        for peers in self._peers:
+            for p in peers.values():
+                self.lib.b2q_dist_ipc_close(ctypes.c_void_p(p))
+        self._peers = [{} for _ in self._peers]
         self.barrier()
-        self.local = None
-        if self._ptr:
-            self.lib.b2q_dist_free(ctypes.c_void_p(self._ptr))
-            self._ptr = 0
+        self._states = []
+        for ptr in self._bufs:
+            self.lib.b2q_dist_free(ctypes.c_void_p(ptr))
+        self._bufs = []
 
 
 class ShardedStateVector:
@@ -218,15 +272,20 @@ class ShardedStateVector:
             raise ValueError('need at least 2 local qubits per rank')
         assert backend.n_local == self.n_local
         self.dtype = np.dtype(dtype)
-        self.local = backend.local
         # logical bit -> physical bit (physical bits >= n_local are global)
         self.phys = list(range(self.n))
         self.swaps = 0
+        self.fused_exchanges = 0
         self.passes = 0
         self.local_only_blocks = 0
         self.diag_global_blocks = 0
         if initial_index is not None:
             self._init_basis(initial_index)
+
+    @property
+    def local(self):
+        """This rank's shard (the backend may move it between two buffers)."""
+        return self.backend.local
 
     # ------------------------------------------------------------------ helpers
 
@@ -285,12 +344,19 @@ class ShardedStateVector:
     def _rank_bit(self, phys_bit: int) -> int:
         return (self.rank >> (phys_bit - self.n_local)) & 1
 
-    def swap_global_local(self, global_phys: int, local_phys: int) -> None:
+    def swap_global_local(self, global_phys: int, local_phys: int, fused_block=None) -> None:
         """Exchanges physical bits (global, local) of the index: data moves, the
-        logical->physical map follows."""
+        logical->physical map follows.  `fused_block` = (matrix, local bits) is
+        applied first, inside the exchange kernel."""
         gi = global_phys - self.n_local
         partner = self.rank ^ (1 << gi)
-        self.backend.swap_bit(partner, local_phys, self._rank_bit(global_phys))
+        if fused_block is not None:
+            self.backend.apply_exchange(fused_block[0], fused_block[1], partner, local_phys,
+                                        self._rank_bit(global_phys))
+            self.passes += 1
+            self.fused_exchanges += 1
+        else:
+            self.backend.swap_bit(partner, local_phys, self._rank_bit(global_phys))
         for l in range(self.n):
             if self.phys[l] == global_phys:
                 self.phys[l] = local_phys
@@ -308,36 +374,64 @@ class ShardedStateVector:
         self._diag_cache = {}
         while remaining:
             progressed = True
+            pending = []  # local passes scheduled since the last exchange, in order
             while progressed and remaining:
                 progressed = False
                 blocked: set[int] = set()
                 keep = []
-                batch = []
                 for m, ws in remaining:
                     if blocked.isdisjoint(ws):
                         local_form = self._local_form(m, ws)
                         if local_form is not None:
                             if local_form[1]:
-                                batch.append(local_form)
+                                pending.append(local_form)
                             progressed = True
                             continue
                     keep.append((m, ws))
                     blocked.update(ws)
-                if batch:
-                    self.local.apply_batch(batch)
-                    self.passes += len(batch)
                 remaining = keep
             if not remaining:
+                self._run_local(pending)
                 break
             # The first remaining block has no unexecuted predecessor: bring its
             # global wires in, evicting the local bits needed furthest away.
             m, ws = remaining[0]
             needed = [w for w in ws if self.phys[w] >= self.n_local]
             protected = {self.phys[w] for w in ws}
-            for w in needed:
+            for i, w in enumerate(needed):
                 victim = self._choose_victim(remaining, protected)
                 protected.add(victim)
+                if i == 0:
+                    fused = self._fusable(pending, victim)
+                    if fused is not None:
+                        # the last local pass and the exchange travel as ONE kernel
+                        self._run_local(pending[:-1])
+                        self.swap_global_local(self.phys[w], victim, fused_block=fused)
+                        continue
+                    self._run_local(pending)
                 self.swap_global_local(self.phys[w], victim)
+
+    def _run_local(self, batch) -> None:
+        if batch:
+            self.local.apply_batch(batch)
+            self.passes += len(batch)
+
+    def _fusable(self, pending, victim: int):
+        """(matrix, bits) of the last pending pass widened to the 4/5 qubits the
+        fused gate + exchange kernel takes, or None if it cannot be used."""
+        if not pending or not getattr(self.backend, 'can_fuse_exchange', False) or victim < 1:
+            return None
+        m, bits = pending[-1]
+        bits = list(bits)
+        k = len(bits)
+        if k > 5:
+            return None
+        if k < 4:
+            # identity on spare wires (the highest free local bits)
+            pad = [p for p in range(self.n_local - 1, -1, -1) if p not in bits][: 4 - k]
+            m = np.kron(np.eye(1 << len(pad)), np.asarray(m).reshape(1 << k, 1 << k))
+            bits = pad + bits
+        return m, bits
 
     def _local_form(self, m: np.ndarray, ws: tuple[int, ...]):
         """(matrix, local physical bits) if the block can run without

@@ -91,18 +91,25 @@ def run(args, world, rank, local_rank):
     for _ in range(args.warmup):
         step()
     launches0 = int(lib.b2q_launch_count())
-    sv.swaps = sv.passes = 0
+    sv.swaps = sv.passes = sv.fused_exchanges = 0
     with B.ClockSampler(local_rank) as clocks:
         ms_per_step = timed(step, args.steps)
     launches = (int(lib.b2q_launch_count()) - launches0) // max(args.steps, 1)
     swaps = sv.swaps // max(args.steps, 1)
     passes = sv.passes // max(args.steps, 1)
+    fused_per_step = sv.fused_exchanges // max(args.steps, 1)
 
     # instrumented pieces: one local pass and one qubit swap, timed alone
     h = np.array([[1, 1], [1, -1]]) / np.sqrt(2)
     u2 = np.kron(h, h)
     pass_ms = timed(lambda: sv.local.apply_matrix(u2, [sv.n_local - 1, sv.n_local - 2]), 5)
     swap_ms = timed(lambda: sv.swap_global_local(sv.n_local, sv.n_local - 1), 4)
+    fused_ms = None
+    if getattr(sv.backend, 'can_fuse_exchange', False):
+        rs = np.random.RandomState(5)
+        q5, _ = np.linalg.qr(rs.standard_normal((32, 32)) + 1j * rs.standard_normal((32, 32)))
+        bits5 = [sv.n_local - 3, 12, 9, 7, 3]
+        fused_ms = timed(lambda: sv.swap_global_local(sv.n_local, sv.n_local - 1, fused_block=(q5, bits5)), 4)
     swap_bytes = shard_bytes // 2
     equiv = 2.0 ** (n - 30)
     value = unit_gates * equiv / (ms_per_step * 1e-3)
@@ -150,12 +157,17 @@ def run(args, world, rank, local_rank):
                        'schedule': ('fusion + lazy state growth: %d of %d raw gates run on replicated '
                                     'sub-states before the join into the shards; planned once outside '
                                     'the timed region' % (plan.get('prefix_gates', 0), len(gates))),
-                       'qubit_swaps_per_step': swaps, 'repetitions': reps,
+                       'qubit_swaps_per_step': swaps,
+                       'swaps_fused_with_a_gate_pass_per_step': fused_per_step, 'repetitions': reps,
                        'shard_bytes': shard_bytes,
                        'swap': {'bytes_out_per_gpu': swap_bytes, 'ms': swap_ms,
                                 'GBps_per_direction': swap_bytes / (swap_ms * 1e-3) / 1e9,
                                 'nvlink_ref_GBps': 770.0,
-                                'how': 'one b2q_dist_swap_bit kernel per rank over peer memory'},
+                                'how': 'one b2q_dist_swap_bit kernel per rank over peer memory',
+                                'fused_gate_plus_swap_ms': fused_ms,
+                                'fused_how': ('b2q_dist_apply_exchange: a 5-qubit tensor-core pass whose '
+                                              'results are written straight to the partner over NVLink '
+                                              '(vs pass + swap as two kernels: ms + local pass ms)')},
                        'l2': 'inputs larger than L2 (shard %.1f GB)' % (shard_bytes / 1e9)},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak_gbs, 'unit': 'GB/s',
                          'frac': achieved / peak_gbs, 'traffic': None,

@@ -235,6 +235,17 @@ int b2q_dist_ipc_close(void* ptr);
 int b2q_dist_swap_bit(void* mine, void* peer, int dtype, int n_local, int local_bit,
                       int my_global_bit_value, void* stream);
 
+/* One 4- or 5-qubit block (complex64) applied to `shard_in` and, in the same
+ * kernel, the global<->local exchange of b2q_dist_swap_bit: results whose index
+ * bit `local_bit` equals this rank's value of the global bit are written to
+ * `out_local`, the others into the partner's buffer `out_peer` (peer memory, with
+ * that bit set to this rank's value).  Out of place: both ranks of a pair call it
+ * with their spare buffers, between two stream-ordered barriers; afterwards the
+ * spare buffers hold the state.  The HBM pass hides behind the NVLink transfer. */
+int b2q_dist_apply_exchange(const void* shard_in, void* out_local, void* out_peer, int dtype,
+                            int n_local, const double* matrix_c128, const int* targets, int k,
+                            int local_bit, int my_global_bit_value, void* stream);
+
 /* ---- tuning knobs and host-only test hooks (not needed by a binding) -------- */
 
 /* How target bits inside the 512-byte warp zone are handled by the register

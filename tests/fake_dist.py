@@ -39,6 +39,15 @@ class GlooShardBackend:
         arr[sel] = recv_t.numpy().view(self.dtype)
         dist.barrier()
 
+    can_fuse_exchange = True
+
+    def apply_exchange(self, matrix, bits, partner, local_bit, my_gbit):
+        """Same result as the fused CUDA kernel: the block, then the exchange."""
+        assert len(bits) in (4, 5) and local_bit >= 1
+        self.local.apply_matrix(np.asarray(matrix), list(bits))
+        self.swap_bit(partner, local_bit, my_gbit)
+        self.fused_calls = getattr(self, 'fused_calls', 0) + 1
+
     def all_reduce_sum(self, value):
         t = torch.tensor([value], dtype=torch.float64)
         dist.all_reduce(t)

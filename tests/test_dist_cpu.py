@@ -103,7 +103,7 @@ def _worker(rank, world, port, n, seed, max_fused, out_dir):
         samples = sv.sample(4000, seed=5)
         if rank == 0:
             np.savez(os.path.join(out_dir, f'res_{world}_{n}_{seed}.npz'), err=err, norm=nrm,
-                     swaps=sv.swaps, passes=sv.passes, diag=sv.diag_global_blocks,
+                     swaps=sv.swaps, passes=sv.passes, diag=sv.diag_global_blocks, fused=sv.fused_exchanges,
                      samples=samples, probs=np.abs(want) ** 2, phys=np.array(sv.phys))
     finally:
         dist.destroy_process_group()
@@ -117,6 +117,7 @@ def test_sharded_matches_oracle(tmp_path, world, n, seed, max_fused):
     assert float(res['err']) < 1e-12
     assert abs(float(res['norm']) - 1.0) < 1e-12
     assert int(res['swaps']) >= 1  # dense gates on global qubits forced exchanges
+    assert 1 <= int(res['fused']) <= int(res['swaps'])  # some rode along with a local pass
     # sampled bitstrings follow |psi|^2 in LOGICAL order: chi-squared on 5 top qubits
     samples, probs = res['samples'], res['probs']
     top = 5
