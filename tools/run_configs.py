@@ -81,7 +81,10 @@ def main():
         # trace / hermiticity spot check on one resolver through simulate
         nomeas = cirq.Circuit(op for op in circuit.all_operations() if not cirq.is_measurement(op))
         t1 = time.perf_counter()
-        fin = sim.simulate(nomeas, resolvers[0], qubit_order=qubits)
+        # one dense rho from the start, so that `passes` counts 34 GB passes only
+        dense = cirq_b200.B200DensityMatrixSimulator(noise=cirq.depolarize(0.01), seed=0,
+                                                     split_untangled_states=False)
+        fin = dense.simulate(nomeas, resolvers[0], qubit_order=qubits)
         tr = fin.device_state.dm_trace()
         torch.cuda.synchronize()
         dt1 = time.perf_counter() - t1
