@@ -94,6 +94,13 @@ SIGNATURES = {
     'b2q_dist_pack': (c_int, [c_void_p, c_int, c_int, POINTER(c_int), c_int, c_void_p, c_void_p]),
     'b2q_dist_apply_exchange': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                         POINTER(c_int), c_int, c_int, c_int, c_void_p]),
+    'b2q_bsv_apply_select': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, POINTER(c_int), c_int,
+                                     c_void_p, c_void_p, c_int, c_void_p]),
+    'b2q_bsv_apply_select_multi': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, POINTER(c_int), c_int,
+                                           c_void_p, c_int, c_void_p]),
+    'b2q_bsv_kraus_weights': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, POINTER(c_int), c_int,
+                                      c_void_p, c_void_p]),
+    'b2q_bsv_collapse': (c_int, [c_void_p, c_int, c_int, c_int, c_uint64, c_void_p, c_void_p, c_void_p]),
     'b2q_dist_unpack': (c_int, [c_void_p, c_int, c_int, POINTER(c_int), c_int, c_void_p, c_void_p]),
 }
 

@@ -321,6 +321,87 @@ class DeviceState:
         )
         return out
 
+    # ---- batched trajectories: 2^(n_bits - n_qubits) states of n_qubits back to back ----
+
+    def bsv_apply_select(self, n_qubits: int, matrices: np.ndarray, bits: Sequence[int],
+                         choice: np.ndarray, scale: np.ndarray | None = None, skip: int = -1) -> None:
+        """psi_t <- scale[t] * matrices[choice[t]] psi_t on `bits` for every
+        trajectory t (choice[t] == skip: untouched)."""
+        torch = _torch()
+        m = np.ascontiguousarray(matrices, dtype=np.complex128)
+        k = len(bits)
+        count = m.shape[0]
+        assert m.shape == (count, 1 << k, 1 << k)
+        batch = self.n_bits - n_qubits
+        c = np.ascontiguousarray(np.asarray(choice, dtype=np.int32).reshape(-1))
+        assert c.size == 1 << batch
+        c_dev = torch.from_numpy(c).to('cuda')
+        s_dev = None
+        if scale is not None:
+            s_dev = torch.from_numpy(np.ascontiguousarray(np.asarray(scale, dtype=np.float64).reshape(-1))).to('cuda')
+        check(
+            self._lib.b2q_bsv_apply_select(
+                self.ptr, self.code, n_qubits, batch, m.ctypes.data, count, _lib.int_array(list(bits)), k,
+                ctypes.c_void_p(c_dev.data_ptr()),
+                ctypes.c_void_p(s_dev.data_ptr() if s_dev is not None else 0), int(skip), _stream_ptr(torch),
+            )
+        )
+
+    def bsv_apply_select_multi(self, n_qubits: int, matrices: np.ndarray, bits: Sequence[int],
+                               choices: np.ndarray, skip: int = -1) -> None:
+        """For j in order: psi_t <- matrices[choices[j, t]] psi_t on bits[j] (1-qubit
+        operators; choices[j, t] == skip: untouched), all in one launch."""
+        torch = _torch()
+        m = np.ascontiguousarray(matrices, dtype=np.complex128)
+        count = m.shape[0]
+        assert m.shape == (count, 2, 2)
+        batch = self.n_bits - n_qubits
+        c = np.ascontiguousarray(np.asarray(choices, dtype=np.int32).reshape(len(bits), 1 << batch))
+        c_dev = torch.from_numpy(c).to('cuda')
+        check(
+            self._lib.b2q_bsv_apply_select_multi(
+                self.ptr, self.code, n_qubits, batch, m.ctypes.data, count, _lib.int_array(list(bits)),
+                len(bits), ctypes.c_void_p(c_dev.data_ptr()), int(skip), _stream_ptr(torch),
+            )
+        )
+
+    def bsv_kraus_weights(self, n_qubits: int, matrices: np.ndarray, bits: Sequence[int]) -> np.ndarray:
+        """float64[trajectories, count]: || matrices[i] psi_t ||^2."""
+        torch = _torch()
+        m = np.ascontiguousarray(matrices, dtype=np.complex128)
+        k = len(bits)
+        count = m.shape[0]
+        assert m.shape == (count, 1 << k, 1 << k)
+        batch = self.n_bits - n_qubits
+        out = torch.empty((1 << batch, count), dtype=torch.float64, device='cuda')
+        check(
+            self._lib.b2q_bsv_kraus_weights(
+                self.ptr, self.code, n_qubits, batch, m.ctypes.data, count, _lib.int_array(list(bits)), k,
+                ctypes.c_void_p(out.data_ptr()), _stream_ptr(torch),
+            )
+        )
+        return out.cpu().numpy()
+
+    def bsv_collapse(self, n_qubits: int, bits: Sequence[int], values: np.ndarray, scale: np.ndarray) -> None:
+        """Projects trajectory t onto bits == values[t] (values[t, i] = value of
+        bits[i]) and multiplies it by scale[t]."""
+        torch = _torch()
+        batch = self.n_bits - n_qubits
+        vals = np.asarray(values, dtype=np.uint64).reshape(1 << batch, len(bits))
+        mask = 0
+        pattern = np.zeros(1 << batch, dtype=np.uint64)
+        for i, b in enumerate(bits):
+            mask |= 1 << int(b)
+            pattern |= vals[:, i] << np.uint64(int(b))
+        p_dev = torch.from_numpy(pattern.view(np.int64)).to('cuda')
+        s_dev = torch.from_numpy(np.ascontiguousarray(np.asarray(scale, dtype=np.float64).reshape(-1))).to('cuda')
+        check(
+            self._lib.b2q_bsv_collapse(
+                self.ptr, self.code, n_qubits, batch, ctypes.c_uint64(mask),
+                ctypes.c_void_p(p_dev.data_ptr()), ctypes.c_void_p(s_dev.data_ptr()), _stream_ptr(torch),
+            )
+        )
+
     def kron_into(self, other: 'DeviceState', out: 'DeviceState') -> 'DeviceState':
         """out <- |self> (x) |other> for an existing state of the right size (the
         IPC-shared shard of the sharded path)."""

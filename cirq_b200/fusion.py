@@ -209,8 +209,9 @@ class GateFuser:
                 self._last[w] = target
 
     def blocks(self) -> list[tuple[np.ndarray, tuple[int, ...]]]:
-        """Fused (matrix, wires) in execution order."""
-        return [(b.matrix, b.wires) for b in self._blocks if b.alive]
+        """Fused (matrix, wires) in execution order, independent narrow blocks
+        packed side by side (`pack_disjoint`)."""
+        return pack_disjoint([(b.matrix, b.wires) for b in self._blocks if b.alive], self._fits)
 
     def num_blocks(self) -> int:
         return sum(1 for b in self._blocks if b.alive)
@@ -238,12 +239,55 @@ class GateFuser:
                 kept.append(b)
                 blocked.update(b.wires)
         self._blocks = kept
-        return out
+        return pack_disjoint(out, self._fits)
 
     def clear(self) -> None:
         self._blocks = []
         self._last = {}
         self.num_gates = 0
+
+
+def pack_disjoint(blocks, fits) -> list[tuple[np.ndarray, tuple[int, ...]]]:
+    """Packs blocks that act on disjoint wires into one wider block (Kronecker
+    product), as long as `fits(wires)` allows the union.
+
+    The frontier rule of `GateFuser.add` only joins gates that share a wire, so a
+    layer of sixteen 1-qubit gates with nothing after it (the last layer of a
+    circuit, or every layer of a noisy circuit, where each channel forces a
+    flush) leaves sixteen blocks = sixteen passes.  Since a pass costs the same
+    HBM traffic for any width, side-by-side blocks are merged: a block may move
+    up to any position after the last earlier block it shares a wire with (all
+    blocks in between act on other wires and commute with it), and joins the
+    first group there that still has room."""
+    groups: list[list] = []  # [wire set, [(matrix, wires), ...]]
+    for m, ws in blocks:
+        wset = set(ws)
+        first = 0
+        for gi in range(len(groups) - 1, -1, -1):
+            if not groups[gi][0].isdisjoint(wset):
+                first = gi + 1
+                break
+        for gi in range(first, len(groups)):
+            g = groups[gi]
+            if fits(tuple(g[0] | wset)) and fits(tuple(g[0])) and fits(tuple(ws)):
+                g[0] |= wset
+                g[1].append((m, ws))
+                break
+        else:
+            groups.append([wset, [(m, ws)]])
+    out = []
+    for _, members in groups:
+        if len(members) == 1:
+            out.append(members[0])
+            continue
+        matrix = np.asarray(members[0][0])
+        wires = tuple(members[0][1])
+        for m, ws in members[1:]:
+            k = len(ws)
+            matrix = np.kron(matrix, np.asarray(m).reshape(1 << k, 1 << k))
+            wires += tuple(ws)
+        out.append((matrix, wires))
+    return out
 
 
 def fuser_for(dtype, max_qubits: int | None = None, n_bits: int | None = None) -> 'GateFuser':

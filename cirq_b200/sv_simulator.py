@@ -35,7 +35,7 @@ from cirq_b200.fusion import GateFuser, fuser_for
 
 cirq = import_cirq()
 
-from cirq import ops, protocols, qis, value  # noqa: E402
+from cirq import ops, protocols, qis, study, value  # noqa: E402
 from cirq.sim import simulator, state_vector, state_vector_simulator  # noqa: E402
 from cirq.sim.simulation_product_state import SimulationProductState  # noqa: E402
 from cirq.sim.simulation_state import SimulationState, strat_act_on_from_apply_decompose  # noqa: E402
@@ -659,6 +659,11 @@ class B200Simulator(
             Kronecker-product kernel when a gate couples them; ignored above
             30 qubits.
         max_fused_qubits: widest fused block (one GPU pass each).
+        trajectory_batch: 0 (default) keeps the reference's one-simulation-per-
+            repetition loop for noisy / mid-circuit-measured ``run`` calls, with
+            its seeded results.  N > 1 advances up to N repetitions together as
+            one device array (``cirq_b200.trajectories``): same distribution of
+            results, random numbers consumed in a different order.
     """
 
     def __init__(
@@ -669,6 +674,7 @@ class B200Simulator(
         seed: 'cirq.RANDOM_STATE_OR_SEED_LIKE' = None,
         split_untangled_states: bool = True,
         max_fused_qubits: int | None = None,
+        trajectory_batch: int = 0,
     ):
         if np.dtype(dtype).kind != 'c':
             raise ValueError(f'dtype must be a complex type but was {dtype}')
@@ -679,6 +685,51 @@ class B200Simulator(
         )
         # None = kernel-matched policy (cirq_b200.fusion.fuser_for)
         self._max_fused = None if max_fused_qubits is None else int(max_fused_qubits)
+        self._trajectory_batch = int(trajectory_batch)
+        self.last_run_info: dict = {}
+
+    def _run(self, circuit, param_resolver, repetitions: int):
+        """``SimulatorBase._run`` (sim/simulator_base.py:215-275) with the
+        per-repetition loop (:249-264) replaced by batched trajectories when
+        ``trajectory_batch`` asks for it and every suffix operation can be
+        batched; anything else takes the reference's loop unchanged."""
+        self.last_run_info = {'path': 'reference loop'}
+        if self._trajectory_batch <= 1 or repetitions <= 1:
+            return super()._run(circuit, param_resolver, repetitions)
+        from cirq.sim.simulator import check_all_resolved, split_into_matching_protocol_then_general
+        from cirq_b200 import trajectories
+
+        resolver = param_resolver or study.ParamResolver({})
+        resolved = protocols.resolve_parameters(circuit, resolver)
+        check_all_resolved(resolved)
+        qubits = tuple(sorted(resolved.all_qubits()))
+        prefix, suffix = (
+            split_into_matching_protocol_then_general(resolved, self._can_be_in_run_prefix)
+            if self._can_be_in_run_prefix(self.noise)
+            else (resolved[0:0], resolved)
+        )
+        suffix_ops = list(suffix.all_operations())
+        if not qubits or all(isinstance(op.gate, ops.MeasurementGate) for op in suffix_ops):
+            return super()._run(circuit, param_resolver, repetitions)
+        noisy = list(self.noise.noisy_moments(suffix, sorted(suffix.all_qubits())))
+        plan = trajectories.plan_suffix(noisy, qubits)
+        if plan is None or len(qubits) > trajectories.MAX_BATCH_STATE_BITS:
+            return super()._run(circuit, param_resolver, repetitions)
+        sim_state = self._create_simulation_state(0, qubits)
+        step_result = None
+        for step_result in self._core_iterator(circuit=prefix, sim_state=sim_state):
+            pass
+        merged = step_result._merged_sim_state
+        # canonical order: axis i of the merged state is qubits[i]
+        assert tuple(merged.qubits) == qubits
+        info: dict = {}
+        out = trajectories.run_plan(
+            plan, merged.device_state, len(qubits), repetitions, self._dtype, self._prng,
+            self._trajectory_batch, self._max_fused, info=info,
+        )
+        info['path'] = 'batched trajectories'
+        self.last_run_info = info
+        return out
 
     def _create_partial_simulation_state(self, initial_state, qubits, classical_data):
         if isinstance(initial_state, B200StateVectorSimulationState):

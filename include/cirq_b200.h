@@ -246,6 +246,44 @@ int b2q_dist_apply_exchange(const void* shard_in, void* out_local, void* out_pee
                             int n_local, const double* matrix_c128, const int* targets, int k,
                             int local_bit, int my_global_bit_value, void* stream);
 
+/* ---- batched Monte-Carlo trajectories ---------------------------------------
+ * 2^batch_bits independent n_qubits-qubit states stored back to back (trajectory
+ * t = index bits [n_qubits, n_qubits + batch_bits)).  Unitary gates are ordinary
+ * b2q_sv_apply_* calls on the (n_qubits + batch_bits)-bit array; the calls below
+ * are the per-trajectory part of the stochastic operations that the reference
+ * performs once per repetition (sim/simulator_base.py:249-264).  `*_dev` arrays
+ * are device pointers with one entry per trajectory. */
+
+/* psi_t <- scale_t * M[choice_t] psi_t on `targets` (k <= 3): the chosen unitary
+ * of a mixture (sim/state_vector_simulation_state.py:183-203) or the chosen Kraus
+ * operator with its 1/sqrt(weight) (:205-257).  matrices_c128 = count row-major
+ * 2^k x 2^k complex128 matrices on the host; scale_dev may be NULL (= 1);
+ * trajectories whose choice == skip_index are not touched (pass -1 for none). */
+int b2q_bsv_apply_select(void* state, int dtype, int n_qubits, int batch_bits,
+                         const double* matrices_c128, int count, const int* targets, int k,
+                         const int* choice_dev, const double* scale_dev, int skip_index,
+                         void* stream);
+/* m selections of 1-qubit operators in one launch: operator j acts on targets[j],
+ * trajectory t applies matrices[choice_dev[j * 2^batch_bits + t]] there, in the
+ * order j = 0..m-1 (m <= 32; targets may repeat).  A noise model's layer of
+ * identical 1-qubit mixtures after a moment (sim/simulator_base.py:196 ->
+ * noise_model.noisy_moments) is one call.  matrices_c128 = count row-major 2 x 2
+ * complex128 matrices. */
+int b2q_bsv_apply_select_multi(void* state, int dtype, int n_qubits, int batch_bits,
+                               const double* matrices_c128, int count, const int* targets, int m,
+                               const int* choice_dev, int skip_index, void* stream);
+/* weights_dev[t * count + i] = || K_i psi_t ||^2 (float64): the trial weights of
+ * the Kraus loop of sim/state_vector_simulation_state.py:228-245, all operators
+ * and all trajectories in one read-only pass. */
+int b2q_bsv_kraus_weights(const void* state, int dtype, int n_qubits, int batch_bits,
+                          const double* matrices_c128, int count, const int* targets, int k,
+                          double* weights_dev, void* stream);
+/* psi_t[i] <- scale_t * psi_t[i] if (i & mask) == pattern_t else 0: the
+ * measurement collapse of sim/state_vector.py:300-318 with one outcome per
+ * trajectory. */
+int b2q_bsv_collapse(void* state, int dtype, int n_qubits, int batch_bits, uint64_t mask,
+                     const uint64_t* pattern_dev, const double* scale_dev, void* stream);
+
 /* ---- tuning knobs and host-only test hooks (not needed by a binding) -------- */
 
 /* How target bits inside the 512-byte warp zone are handled by the register

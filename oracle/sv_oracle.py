@@ -270,3 +270,47 @@ def run_gate_list(n_qubits: int, gates, dtype=np.complex64, initial: int = 0) ->
     for m, tg in gates:
         psi = apply_matrix(psi, n_qubits, m, tg)
     return psi
+
+
+# ---- batched trajectories (B states of n qubits back to back) ---------------------------
+# Per trajectory these are the reference's per-repetition operations:
+# apply_mixture (cirq-core/cirq/sim/state_vector_simulation_state.py:183-203),
+# apply_channel (:205-257) and the collapse of measure_state_vector
+# (cirq-core/cirq/sim/state_vector.py:300-318).
+
+
+def bsv_apply_select(states, n, matrices, targets, choice, scale=None, skip=-1):
+    """states: complex[B * 2^n]; returns the array with trajectory t replaced by
+    scale[t] * matrices[choice[t]] applied on `targets` (choice == skip: untouched)."""
+    out = np.array(states).reshape(-1, 1 << n)
+    for t in range(out.shape[0]):
+        c = int(choice[t])
+        if c == skip:
+            continue
+        v = apply_matrix(out[t], n, np.asarray(matrices[c]), list(targets))
+        out[t] = v * (1.0 if scale is None else scale[t])
+    return out.reshape(-1)
+
+
+def bsv_kraus_weights(states, n, matrices, targets):
+    """float64[B, count]: squared norm of matrices[i] applied to trajectory t."""
+    st = np.asarray(states).reshape(-1, 1 << n)
+    out = np.zeros((st.shape[0], len(matrices)), dtype=np.float64)
+    for t in range(st.shape[0]):
+        for i, m in enumerate(matrices):
+            v = apply_matrix(st[t].astype(np.complex128), n, np.asarray(m), list(targets))
+            out[t, i] = float(np.sum(np.abs(v) ** 2))
+    return out
+
+
+def bsv_collapse(states, n, bits, values, scale):
+    """Trajectory t keeps the amplitudes whose `bits` equal values[t] (times scale[t])."""
+    out = np.array(states).reshape(-1, 1 << n)
+    idx = np.arange(1 << n, dtype=np.int64)
+    vals = np.asarray(values).reshape(out.shape[0], len(bits))
+    for t in range(out.shape[0]):
+        keep = np.ones(1 << n, dtype=bool)
+        for i, b in enumerate(bits):
+            keep &= ((idx >> int(b)) & 1) == int(vals[t, i])
+        out[t] = np.where(keep, out[t] * scale[t], 0)
+    return out.reshape(-1)

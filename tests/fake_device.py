@@ -121,6 +121,21 @@ class OracleDeviceState:
     def kron(self, other):
         return OracleDeviceState(self.n_bits + other.n_bits, self.dtype, np.kron(self.array, other.array))
 
+    def bsv_apply_select(self, n_qubits, matrices, bits, choice, scale=None, skip=-1):
+        self.array = orc.bsv_apply_select(self.array, n_qubits, np.asarray(matrices), list(bits), choice,
+                                          scale, skip).astype(self.dtype)
+
+    def bsv_apply_select_multi(self, n_qubits, matrices, bits, choices, skip=-1):
+        choices = np.asarray(choices).reshape(len(bits), -1)
+        for j, b in enumerate(bits):
+            self.bsv_apply_select(n_qubits, matrices, [b], choices[j], None, skip)
+
+    def bsv_kraus_weights(self, n_qubits, matrices, bits):
+        return orc.bsv_kraus_weights(self.array, n_qubits, np.asarray(matrices), list(bits))
+
+    def bsv_collapse(self, n_qubits, bits, values, scale):
+        self.array = orc.bsv_collapse(self.array, n_qubits, list(bits), values, scale).astype(self.dtype)
+
     def kron_into(self, other, out):
         out.array[:] = np.kron(self.array, other.array)
         return out

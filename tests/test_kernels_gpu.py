@@ -372,6 +372,62 @@ def test_dist_pack_unpack(DS, dtype):
         np.testing.assert_array_equal(dev2.to_numpy(), state)
 
 
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
+def test_batched_trajectory_kernels_match_oracle(DS, dtype):
+    """b2q_bsv_apply_select / b2q_bsv_kraus_weights / b2q_bsv_collapse against the
+    per-trajectory oracle (reference: sim/state_vector_simulation_state.py:183-257,
+    sim/state_vector.py:300-318)."""
+    rng = np.random.default_rng(77)
+    atol = ATOL[np.dtype(dtype)]
+    for n, b in ((1, 3), (3, 0), (4, 5), (7, 6), (11, 4), (2, 13)):
+        B = 1 << b
+        states = np.concatenate([rand_state(rng, n, dtype) for _ in range(B)])
+        for k in (1, 2, 3):
+            if k > n:
+                continue
+            for count in (1, 2, 4, 5):
+                targets = rng.permutation(n)[:k].tolist()
+                mats = np.stack([rand_matrix(rng, k) for _ in range(count)])
+                mats[0] = np.eye(1 << k)
+                choice = rng.integers(0, count, size=B)
+                scale = rng.uniform(0.5, 2.0, size=B)
+                for skip, sc in ((-1, None), (0, None), (-1, scale), (0, scale)):
+                    dev = DS.from_numpy(states, dtype)
+                    dev.bsv_apply_select(n, mats, targets, choice, sc, skip)
+                    want = orc.bsv_apply_select(states, n, mats, targets, choice, sc, skip)
+                    np.testing.assert_allclose(dev.to_numpy(), want, atol=4 * atol, rtol=0)
+                dev = DS.from_numpy(states, dtype)
+                got = dev.bsv_kraus_weights(n, mats, targets)
+                want = orc.bsv_kraus_weights(states, n, mats, targets)
+                np.testing.assert_allclose(got, want, rtol=2e-5 if dtype == np.complex64 else 1e-12, atol=atol)
+                np.testing.assert_array_equal(dev.to_numpy(), states)
+        # a layer of 1-qubit selections in one launch (targets may repeat)
+        for count, layer in ((4, min(n, 5)), (3, n + 2), (2, 32)):
+            mats = np.stack([rand_matrix(rng, 1) for _ in range(count)])
+            mats[0] = np.eye(2)
+            tg = rng.integers(0, n, size=layer).tolist()
+            choices = rng.integers(0, count, size=(layer, B))
+            choices[rng.random((layer, B)) < 0.6] = 0
+            for skip in (0, -1):
+                dev = DS.from_numpy(states, dtype)
+                dev.bsv_apply_select_multi(n, mats, tg, choices, skip)
+                want = states
+                for j, bit in enumerate(tg):
+                    want = orc.bsv_apply_select(want, n, mats, [bit], choices[j], None, skip)
+                scale_up = max(1.0, float(np.max(np.abs(want))) * 4)
+                np.testing.assert_allclose(dev.to_numpy(), want, atol=scale_up * 4 * atol, rtol=0)
+        m = int(rng.integers(1, n + 1))
+        bits = rng.permutation(n)[:m].tolist()
+        values = rng.integers(0, 2, size=(B, m))
+        scale = rng.uniform(0.5, 2.0, size=B)
+        dev = DS.from_numpy(states, dtype)
+        dev.bsv_collapse(n, bits, values, scale)
+        want = orc.bsv_collapse(states, n, bits, values, scale)
+        np.testing.assert_allclose(dev.to_numpy(), want, atol=4 * atol, rtol=0)
+        # exact zeros outside the selected slice (bit-exact index work)
+        assert np.array_equal(dev.to_numpy() == 0, want == 0)
+
+
 def test_full_size_properties_30q(DS):
     """BASELINE config sizes: size-independent properties at 30 qubits c64
     (8.6 GB state): unitarity round trip, norm, basis-state sampling."""

@@ -244,6 +244,132 @@ def test_noisy_state_vector_trajectories_seeded(cirq, SV, split):
     np.testing.assert_array_equal(got.measurements['m'], want.measurements['m'])
 
 
+def _chi2_ok(counts, probs, reps):
+    """Pearson chi-squared of a histogram against exact probabilities, bins of
+    expected count < 5 pooled; passes below the 99.99 % quantile."""
+    from scipy import stats
+
+    expected = np.asarray(probs, dtype=np.float64) * reps
+    small = expected < 5
+    obs = np.append(counts[~small], counts[small].sum())
+    exp = np.append(expected[~small], expected[small].sum())
+    keep = exp > 0
+    assert obs[~keep].sum() == 0, 'samples landed on zero-probability outcomes'
+    obs, exp = obs[keep], exp[keep]
+    if len(obs) < 2:
+        return True
+    chi2 = float(((obs - exp) ** 2 / exp).sum())
+    return chi2 < stats.chi2.ppf(0.9999, len(obs) - 1)
+
+
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
+def test_batched_trajectories_distribution(cirq, SV, dtype):
+    """trajectory_batch: same distribution as the reference's per-repetition loop
+    (sim/simulator_base.py:249-264); checked against the exact outcome
+    probabilities from cirq.DensityMatrixSimulator."""
+    q = cirq.LineQubit.range(4)
+    circuit = cirq.Circuit(
+        cirq.H(q[0]),
+        cirq.CNOT(q[0], q[1]),
+        cirq.ry(0.7).on(q[2]),
+        cirq.bit_flip(0.3).on(q[1]),
+        cirq.amplitude_damp(0.4).on(q[0]),
+        cirq.CZ(q[1], q[2]) ** 0.5,
+        cirq.depolarize(0.2).on(q[2]),
+        cirq.rx(0.4).on(q[3]),
+        cirq.ISWAP(q[2], q[3]) ** 0.5,
+        cirq.asymmetric_depolarize(0.05, 0.1, 0.15).on(q[3]),
+        cirq.measure(q[2], q[0], q[3], q[1], key='m'),
+    )
+    reps = 6000
+    rho = cirq.DensityMatrixSimulator(dtype=np.complex128).simulate(circuit[:-1]).final_density_matrix
+    p = np.real(np.diag(rho))  # index = q0 q1 q2 q3 big-endian
+    for batch in (64, 4096):
+        sim = SV(seed=11, dtype=dtype, trajectory_batch=batch)
+        res = sim.run(circuit, repetitions=reps)
+        assert sim.last_run_info['path'] == 'batched trajectories'
+        m = res.measurements['m']
+        assert m.shape == (reps, 4) and m.dtype == np.uint8
+        idx = (m[:, 1].astype(int) << 3) | (m[:, 3] << 2) | (m[:, 0] << 1) | m[:, 2]
+        counts = np.bincount(idx, minlength=16)
+        assert _chi2_ok(counts, p, reps)
+    # noise model on the simulator + invert mask
+    circuit2 = cirq.Circuit(
+        cirq.X(q[0]), cirq.H(q[1]), cirq.CNOT(q[1], q[2]),
+        cirq.measure(q[0], q[1], q[2], key='z', invert_mask=(True, False, True)),
+    )
+    noise = cirq.depolarize(0.1)
+    noisy = cirq.Circuit(cirq.ConstantQubitNoiseModel(noise).noisy_moments(circuit2[:-1], q[:3]))
+    rho = cirq.DensityMatrixSimulator(dtype=np.complex128).simulate(noisy, qubit_order=q[:3]).final_density_matrix
+    # the measurement moment gets noise after it, which does not change the record
+    p = np.real(np.diag(rho))
+    sim = SV(seed=3, dtype=dtype, noise=noise, trajectory_batch=1024)
+    m = sim.run(circuit2, repetitions=4000).measurements['z']
+    assert sim.last_run_info['path'] == 'batched trajectories'
+    idx = ((m[:, 0] ^ 1).astype(int) << 2) | (m[:, 1] << 1) | (m[:, 2] ^ 1)
+    assert _chi2_ok(np.bincount(idx, minlength=8), p, 4000)
+
+
+def test_batched_trajectories_mid_circuit_measurement(cirq, SV):
+    """Mid-circuit measurements collapse per trajectory: correlations between a
+    mid-circuit record, a later record of the same qubit and a terminal record."""
+    q = cirq.LineQubit.range(3)
+    circuit = cirq.Circuit(
+        cirq.H(q[0]),
+        cirq.CNOT(q[0], q[1]),
+        cirq.measure(q[0], key='a'),
+        cirq.H(q[2]),
+        cirq.CNOT(q[1], q[2]),
+        cirq.measure(q[1], key='b'),
+        cirq.reset(q[1]),
+        cirq.X(q[0]),
+        cirq.measure(q[0], q[1], key='c'),
+        cirq.measure(q[2], key='d'),
+        cirq.measure(q[2], key='d'),
+    )
+    reps = 3000
+    sim = SV(seed=5, trajectory_batch=512)
+    res = sim.run(circuit, repetitions=reps)
+    assert sim.last_run_info['path'] == 'batched trajectories'
+    a, b, c = res.records['a'][:, 0], res.records['b'][:, 0], res.records['c'][:, 0]
+    d = res.records['d']
+    assert a.shape == (reps, 1) and c.shape == (reps, 2) and d.shape == (reps, 2, 1)
+    np.testing.assert_array_equal(a, b)  # Bell pair
+    np.testing.assert_array_equal(c[:, 0], 1 - a[:, 0])  # X after the collapse
+    assert not c[:, 1].any()  # reset
+    np.testing.assert_array_equal(d[:, 0], d[:, 1])
+    # q2 = H-random XOR q1: uniform and independent of a
+    joint = np.bincount(2 * a[:, 0].astype(int) + d[:, 0, 0], minlength=4)
+    assert _chi2_ok(joint, np.full(4, 0.25), reps)
+    # same seed, same records
+    again = SV(seed=5, trajectory_batch=512).run(circuit, repetitions=reps)
+    np.testing.assert_array_equal(again.records['a'][:, 0], a)
+    np.testing.assert_array_equal(again.records['d'], d)
+
+
+def test_batched_trajectories_fall_back_to_reference_loop(cirq, SV):
+    """Operations that cannot be batched (classical control here) take the
+    reference's per-repetition loop, with its seeded results."""
+    q = cirq.LineQubit.range(2)
+    circuit = cirq.Circuit(
+        cirq.H(q[0]),
+        cirq.measure(q[0], key='a'),
+        cirq.X(q[1]).with_classical_controls('a'),
+        cirq.measure(q[1], key='b'),
+    )
+    want = cirq.Simulator(seed=8).run(circuit, repetitions=30)
+    sim = SV(seed=8, trajectory_batch=256)
+    got = sim.run(circuit, repetitions=30)
+    assert sim.last_run_info['path'] == 'reference loop'
+    np.testing.assert_array_equal(got.measurements['a'], want.measurements['a'])
+    np.testing.assert_array_equal(got.measurements['b'], want.measurements['b'])
+    # terminal-measurement-only circuits keep the sample-once path
+    c2 = cirq.Circuit(cirq.H(q[0]), cirq.CNOT(q[0], q[1]), cirq.measure(*q, key='m'))
+    want = cirq.Simulator(seed=2).run(c2, repetitions=50)
+    got = SV(seed=2, trajectory_batch=256).run(c2, repetitions=50)
+    np.testing.assert_array_equal(got.measurements['m'], want.measurements['m'])
+
+
 def test_expectation_values_and_amplitudes(cirq, SV):
     q = cirq.LineQubit.range(4)
     circuit = cirq.testing.random_circuit(q, 8, 0.9, random_state=5)
