@@ -583,6 +583,103 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- reduced density matrix ---------------------------------------------------
+
+// rho[a][b] = sum_rest psi[a, rest] conj(psi[b, rest]) over the M kept bits
+// (qis/states.py:623-693 density_matrix_from_state_vector with `indices`).  A
+// thread walks `rest` values grid-stride, holds the D = 2^M amplitudes of one
+// rest value in registers and accumulates R rows of the outer product (row
+// tile = blockIdx.y, so wide reductions re-read the state D/R times); partial
+// sums are folded per warp in float64 and added to out[D*D*2] with one atomic
+// per entry per warp.  sorted_pos = kept bit positions ascending; index a uses
+// them LSB first (the host permutes to the caller's qubit order).
+struct RdmParams {
+  int pos[6];
+};
+
+template <typename real, int M, int R>
+__global__ void __launch_bounds__(256)
+    sv_reduced_dm_kernel(const typename Cplx<real>::type* __restrict__ state, uint64_t rest_total,
+                         const __grid_constant__ RdmParams p, double* __restrict__ out) {
+  using C = typename Cplx<real>::type;
+  constexpr int D = 1 << M;
+  const int row0 = blockIdx.y * R;
+  // per-thread partial sums in the state's precision (a thread sees a few hundred
+  // terms); the cross-thread fold is float64
+  real acc_re[R][D], acc_im[R][D];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int b = 0; b < D; ++b) acc_re[r][b] = acc_im[r][b] = 0;
+  uint64_t row_off[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    row_off[r] = 0;
+#pragma unroll
+    for (int b = 0; b < M; ++b)
+      if (((row0 + r) >> b) & 1) row_off[r] += 1ull << p.pos[b];
+  }
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < rest_total;
+       g += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t base = insert_zero_bits(g, p.pos, M);
+    C xa[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) xa[r] = state[base + row_off[r]];
+#pragma unroll
+    for (int b = 0; b < D; ++b) {
+      uint64_t off = 0;
+#pragma unroll
+      for (int q = 0; q < M; ++q)
+        if ((b >> q) & 1) off += 1ull << p.pos[q];
+      const C xb = state[base + off];  // the row loads above brought the lines in
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        // xa * conj(xb)
+        acc_re[r][b] = fma(xa[r].x, xb.x, fma(xa[r].y, xb.y, acc_re[r][b]));
+        acc_im[r][b] = fma(xa[r].y, xb.x, fma(-xa[r].x, xb.y, acc_im[r][b]));
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int b = 0; b < D; ++b) {
+      const double re = warp_sum((double)acc_re[r][b]);
+      const double im = warp_sum((double)acc_im[r][b]);
+      if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&out[2 * ((row0 + r) * D + b)], re);
+        atomicAdd(&out[2 * ((row0 + r) * D + b) + 1], im);
+      }
+    }
+}
+
+template <typename real, int M, int R>
+static int reduced_dm_launch(const void* state, int n, const RdmParams& p, double* out_dev,
+                             cudaStream_t s) {
+  using C = typename Cplx<real>::type;
+  constexpr int D = 1 << M;
+  const uint64_t rest_total = 1ull << (n - M);
+  const unsigned bx = (unsigned)std::max<uint64_t>(
+      1, std::min<uint64_t>((rest_total + 255) / 256, 148ull * 4));
+  const dim3 grid(bx, D / R);
+  sv_reduced_dm_kernel<real, M, R>
+      <<<grid, 256, 0, s>>>(reinterpret_cast<const C*>(state), rest_total, p, out_dev);
+  B2Q_LAUNCH_CHECK("sv_reduced_dm_kernel");
+  return B2Q_OK;
+}
+
+template <typename real>
+static int reduced_dm_t(const void* state, int n, int m, const RdmParams& p, double* out_dev,
+                        cudaStream_t s) {
+  switch (m) {
+    case 1: return reduced_dm_launch<real, 1, 2>(state, n, p, out_dev, s);
+    case 2: return reduced_dm_launch<real, 2, 4>(state, n, p, out_dev, s);
+    case 3: return reduced_dm_launch<real, 3, sizeof(real) == 4 ? 4 : 2>(state, n, p, out_dev, s);
+    case 4: return reduced_dm_launch<real, 4, sizeof(real) == 4 ? 2 : 1>(state, n, p, out_dev, s);
+    default: return reduced_dm_launch<real, 5, 1>(state, n, p, out_dev, s);
+  }
+}
+
 // ---- dist pack / unpack -----------------------------------------------------
 
 struct PackParams {
@@ -972,6 +1069,51 @@ extern "C" int b2q_sv_pauli_expectation(const void* state, int dtype, int n_qubi
   }
   out_re_im[0] = re;
   out_re_im[1] = im;
+  return B2Q_OK;
+}
+
+extern "C" int b2q_sv_reduced_density_matrix(const void* state, int dtype, int n_qubits,
+                                             const int* bits, int m, double* out_c128,
+                                             void* stream) {
+  B2Q_REQUIRE(state != nullptr && bits != nullptr && out_c128 != nullptr, "null argument");
+  B2Q_CHECK_DTYPE(dtype);
+  B2Q_REQUIRE(m >= 1 && m <= 5 && m <= n_qubits, "1..5 kept qubits, got %d", m);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  RdmParams p;
+  int sorted[6];
+  for (int q = 0; q < m; ++q) {
+    B2Q_REQUIRE(bits[q] >= 0 && bits[q] < n_qubits, "bit %d out of range", bits[q]);
+    sorted[q] = bits[q];
+  }
+  std::sort(sorted, sorted + m);
+  for (int q = 0; q < 6; ++q) p.pos[q] = q < m ? sorted[q] : 0;
+  for (int q = 1; q < m; ++q) B2Q_REQUIRE(sorted[q] != sorted[q - 1], "duplicate bit %d", sorted[q]);
+  const int d = 1 << m;
+  double* out_dev = reinterpret_cast<double*>(workspace(sizeof(double) * 2 * d * d));
+  if (out_dev == nullptr) return B2Q_ERR_CUDA;
+  B2Q_CUDA_CHECK(cudaMemsetAsync(out_dev, 0, sizeof(double) * 2 * d * d, s));
+  const int rc = dtype == B2Q_C64 ? reduced_dm_t<float>(state, n_qubits, m, p, out_dev, s)
+                                  : reduced_dm_t<double>(state, n_qubits, m, p, out_dev, s);
+  if (rc != B2Q_OK) return rc;
+  std::vector<double> h((size_t)2 * d * d);
+  B2Q_CUDA_CHECK(cudaMemcpyAsync(h.data(), out_dev, sizeof(double) * 2 * d * d,
+                                 cudaMemcpyDeviceToHost, s));
+  B2Q_CUDA_CHECK(cudaStreamSynchronize(s));
+  // kernel index: sorted positions, LSB first  ->  caller's: bits[0] = MSB
+  auto to_kernel = [&](int idx) {
+    int k = 0;
+    for (int q = 0; q < m; ++q)
+      if ((idx >> (m - 1 - q)) & 1)
+        for (int i = 0; i < m; ++i)
+          if (sorted[i] == bits[q]) k |= 1 << i;
+    return k;
+  };
+  for (int a = 0; a < d; ++a)
+    for (int b = 0; b < d; ++b) {
+      const size_t src = 2 * ((size_t)to_kernel(a) * d + to_kernel(b));
+      out_c128[2 * (a * d + b)] = h[src];
+      out_c128[2 * (a * d + b) + 1] = h[src + 1];
+    }
   return B2Q_OK;
 }
 

@@ -307,6 +307,20 @@ class DeviceState:
         )
         return complex(out[0], out[1])
 
+    def reduced_density_matrix(self, bits: Sequence[int]) -> np.ndarray:
+        """complex128[2^m, 2^m]: the state with every bit not in `bits` traced out
+        (bits[0] = most significant index bit of the result), m <= 5."""
+        torch = _torch()
+        m = len(bits)
+        out = np.empty((1 << m, 1 << m), dtype=np.complex128)
+        check(
+            self._lib.b2q_sv_reduced_density_matrix(
+                self.ptr, self.code, self.n_bits, _lib.int_array(list(bits)), m, out.ctypes.data,
+                _stream_ptr(torch),
+            )
+        )
+        return out
+
     # ------------------------------------------------------------------ layout
 
     def kron(self, other: 'DeviceState') -> 'DeviceState':

@@ -601,8 +601,42 @@ class _FastConfuseMixin:
         }
 
 
+class _DeviceReducedStateMixin:
+    """``density_matrix_of`` / ``bloch_vector_of`` (sim/state_vector.py:109-167)
+    evaluated by a reduction kernel on the device state instead of an einsum over
+    a host copy (qis/states.py:676-693) — which at 34 qubits would first download
+    137 GB, and which the reference refuses above 25 qubits.  Up to 5 kept
+    qubits; wider requests (and ``qubits=None``, the full outer product) take
+    the reference's host route."""
+
+    _MAX_KEPT = 5
+
+    def _merged_device_state(self):
+        raise NotImplementedError
+
+    def density_matrix_of(self, qubits=None) -> np.ndarray:
+        if qubits is None or not 1 <= len(qubits) <= self._MAX_KEPT:
+            return super().density_matrix_of(qubits)
+        axes = [self.qubit_map[q] for q in qubits]  # KeyError for foreign qubits, as the reference
+        if len(set(axes)) != len(axes):
+            return super().density_matrix_of(qubits)
+        dev = self._merged_device_state()
+        n = dev.n_bits
+        rho = dev.reduced_density_matrix([n - 1 - a for a in axes])
+        return rho.astype(dev.dtype)
+
+    def bloch_vector_of(self, qubit) -> np.ndarray:
+        rho = self.density_matrix_of([qubit])
+        v = np.zeros(3, dtype=np.float32)  # qis/states.py:614-620
+        v[0] = 2 * np.real(rho[0][1])
+        v[1] = 2 * np.imag(rho[1][0])
+        v[2] = np.real(rho[0][0] - rho[1][1])
+        return v
+
+
 class B200SimulatorStep(
-    _FastConfuseMixin, state_vector.StateVectorMixin, state_vector_simulator.StateVectorStepResult
+    _FastConfuseMixin, _DeviceReducedStateMixin, state_vector.StateVectorMixin,
+    state_vector_simulator.StateVectorStepResult,
 ):
     """Step result of ``B200Simulator`` (replaces ``SparseSimulatorStep``,
     sim/sparse_simulator.py:221-290)."""
@@ -612,6 +646,9 @@ class B200SimulatorStep(
         super().__init__(sim_state=sim_state, qubit_map=qubit_map)
         self._dtype = dtype
         self._state_vector: np.ndarray | None = None
+
+    def _merged_device_state(self):
+        return self._merged_sim_state.device_state
 
     def state_vector(self, copy: bool = False) -> np.ndarray:
         """Host copy of the state vector (big-endian), downloaded on first use."""
@@ -630,8 +667,11 @@ class B200SimulatorStep(
         )
 
 
-class B200StateVectorTrialResult(state_vector_simulator.StateVectorTrialResult):
+class B200StateVectorTrialResult(_DeviceReducedStateMixin, state_vector_simulator.StateVectorTrialResult):
     """Trial result whose final state stays on the device until asked for."""
+
+    def _merged_device_state(self):
+        return self.device_state
 
     @property
     def device_state(self) -> DeviceState:

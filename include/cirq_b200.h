@@ -155,6 +155,16 @@ int b2q_sv_collapse(void* state, int dtype, int n_qubits, const int* bits, const
 int b2q_sv_pauli_expectation(const void* state, int dtype, int n_qubits, uint64_t x_mask,
                              uint64_t z_mask, double* out_re_im, void* stream);
 
+/* Reduced density matrix of m <= 5 qubits, the rest traced out:
+ * out[a * 2^m + b] = sum_rest psi[a, rest] conj(psi[b, rest]) as 4^m complex128
+ * values on the host, bits[0] = most significant bit of a and b.  Replaces
+ * qis/states.py:623-693 (density_matrix_from_state_vector) behind
+ * StateVectorMixin.density_matrix_of / bloch_vector_of (sim/state_vector.py:109-167),
+ * which the reference evaluates on a host copy of the state (and refuses above
+ * 25 qubits).  Synchronises the stream. */
+int b2q_sv_reduced_density_matrix(const void* state, int dtype, int n_qubits, const int* bits,
+                                  int m, double* out_c128, void* stream);
+
 /* ---- state layout: Kronecker product, axis permutation, factoring ---------- */
 
 /* out[(i << nb) | j] = a[i] * b[j]: linalg/transformations.py:603-613

@@ -314,3 +314,16 @@ def bsv_collapse(states, n, bits, values, scale):
             keep &= ((idx >> int(b)) & 1) == int(vals[t, i])
         out[t] = np.where(keep, out[t] * scale[t], 0)
     return out.reshape(-1)
+
+
+def reduced_density_matrix(state: np.ndarray, n_qubits: int, bits) -> np.ndarray:
+    """rho[a, b] = sum_rest psi[a, rest] conj(psi[b, rest]) over the kept `bits`
+    (bits[0] = MSB of a, b): cirq-core/cirq/qis/states.py:676-693 with
+    indices = [n-1-b for b in bits]."""
+    bits = [int(b) for b in bits]
+    m = len(bits)
+    psi = np.asarray(state, dtype=np.complex128).reshape((2,) * n_qubits)
+    axes = [n_qubits - 1 - b for b in bits]
+    rest = [a for a in range(n_qubits) if a not in axes]
+    mat = np.transpose(psi, axes + rest).reshape(1 << m, -1)
+    return mat @ mat.conj().T

@@ -125,6 +125,9 @@ class OracleDeviceState:
         self.array = orc.bsv_apply_select(self.array, n_qubits, np.asarray(matrices), list(bits), choice,
                                           scale, skip).astype(self.dtype)
 
+    def reduced_density_matrix(self, bits):
+        return orc.reduced_density_matrix(self.array, self.n_bits, list(bits))
+
     def bsv_apply_select_multi(self, n_qubits, matrices, bits, choices, skip=-1):
         choices = np.asarray(choices).reshape(len(bits), -1)
         for j, b in enumerate(bits):

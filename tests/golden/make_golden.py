@@ -220,6 +220,74 @@ def golden_reference_test_vectors():
     return 2
 
 
+def golden_reduced_density_matrix():
+    """qis/states.py:586-693 density_matrix_from_state_vector / bloch_vector_from_state_vector."""
+    rng = np.random.RandomState(11)
+    out = {}
+    case = 0
+    for n in (1, 2, 4, 7, 9):
+        state = rand_state(rng, n, np.complex128)
+        for m in range(1, min(n, 5) + 1):
+            indices = rng.permutation(n)[:m]
+            out[f'c{case}_state'] = state
+            out[f'c{case}_n'] = np.array(n)
+            out[f'c{case}_indices'] = indices  # cirq axes, result index big-endian over them
+            out[f'c{case}_rho'] = cirq.density_matrix_from_state_vector(state, [int(i) for i in indices])
+            out[f'c{case}_bloch'] = cirq.bloch_vector_from_state_vector(state, int(indices[0]))
+            case += 1
+    out['num_cases'] = np.array(case)
+    np.savez_compressed(os.path.join(HERE, 'reduced_density_matrix.npz'), **out)
+    return case
+
+
+def golden_trajectory_ops():
+    """Per-trajectory pieces of the reference's per-repetition loop
+    (sim/simulator_base.py:249-264) on B independent states:
+    the Kraus trial weights of sim/state_vector_simulation_state.py:228-245
+    (targeted_left_multiply + squared norm), the state after the chosen operator
+    and its renormalisation (:246-257), and measure_state_vector's collapse
+    (sim/state_vector.py:235-322) with the outcome it drew."""
+    rng = np.random.RandomState(13)
+    out = {}
+    case = 0
+    channels = [cirq.amplitude_damp(0.3), cirq.depolarize(0.2), cirq.phase_damp(0.4),
+                cirq.generalized_amplitude_damp(0.6, 0.25), cirq.depolarize(0.1, n_qubits=2)]
+    for n, B in ((1, 4), (3, 8), (6, 4)):
+        states = np.stack([rand_state(rng, n, np.complex128) for _ in range(B)])
+        for ch in channels:
+            k = cirq.num_qubits(ch)
+            if k > n:
+                continue
+            kraus = np.stack(cirq.kraus(ch))
+            axes = [int(a) for a in rng.permutation(n)[:k]]
+            weights = np.zeros((B, len(kraus)))
+            applied = np.zeros((B, len(kraus), 1 << n), dtype=np.complex128)
+            for t in range(B):
+                psi = states[t].reshape((2,) * n)
+                for i, op in enumerate(kraus):
+                    res = cirq.linalg.targeted_left_multiply(op.reshape((2,) * (2 * k)), psi, axes)
+                    weights[t, i] = np.linalg.norm(res) ** 2
+                    applied[t, i] = res.reshape(-1)
+            out[f'c{case}_states'] = states
+            out[f'c{case}_n'] = np.array(n)
+            out[f'c{case}_axes'] = np.array(axes)
+            out[f'c{case}_kraus'] = kraus
+            out[f'c{case}_weights'] = weights
+            out[f'c{case}_applied'] = applied
+            # measurement collapse of every trajectory on the same axes
+            results, collapsed = [], []
+            for t in range(B):
+                bits, post = cirq.measure_state_vector(states[t], axes, seed=int(rng.randint(1 << 30)))
+                results.append(bits)
+                collapsed.append(post)
+            out[f'c{case}_results'] = np.array(results)
+            out[f'c{case}_collapsed'] = np.stack(collapsed)
+            case += 1
+    out['num_cases'] = np.array(case)
+    np.savez_compressed(os.path.join(HERE, 'trajectory_ops.npz'), **out)
+    return case
+
+
 if __name__ == '__main__':
     print('cirq', cirq.__version__, cirq.__file__)
     print('targeted_left_multiply cases:', golden_targeted_left_multiply())
@@ -228,3 +296,5 @@ if __name__ == '__main__':
     print('density matrix cases:', golden_density_matrix())
     print('pauli cases:', golden_pauli())
     print('reference test vectors:', golden_reference_test_vectors())
+    print('reduced density matrix cases:', golden_reduced_density_matrix())
+    print('trajectory op cases:', golden_trajectory_ops())

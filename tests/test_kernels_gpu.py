@@ -372,6 +372,54 @@ def test_dist_pack_unpack(DS, dtype):
         np.testing.assert_array_equal(dev2.to_numpy(), state)
 
 
+def test_golden_reduced_density_matrix_and_trajectory_ops(DS):
+    """CUDA path against the committed reference outputs (tests/golden/make_golden.py)."""
+    g = load_golden('reduced_density_matrix.npz')
+    for c in range(int(g['num_cases'])):
+        n = int(g[f'c{c}_n'])
+        bits = [n - 1 - int(a) for a in g[f'c{c}_indices']]
+        dev = DS.from_numpy(g[f'c{c}_state'], np.complex128)
+        np.testing.assert_allclose(dev.reduced_density_matrix(bits), g[f'c{c}_rho'], atol=1e-12)
+    g = load_golden('trajectory_ops.npz')
+    for c in range(int(g['num_cases'])):
+        n = int(g[f'c{c}_n'])
+        states = g[f'c{c}_states']
+        B = states.shape[0]
+        bits = [n - 1 - int(a) for a in g[f'c{c}_axes']]
+        kraus = g[f'c{c}_kraus']
+        dev = DS.from_numpy(states.reshape(-1), np.complex128)
+        w = dev.bsv_kraus_weights(n, kraus, bits)
+        np.testing.assert_allclose(w, g[f'c{c}_weights'], atol=1e-12)
+        for i in range(len(kraus)):
+            dev = DS.from_numpy(states.reshape(-1), np.complex128)
+            dev.bsv_apply_select(n, kraus, bits, np.full(B, i))
+            np.testing.assert_allclose(dev.to_numpy().reshape(B, -1), g[f'c{c}_applied'][:, i], atol=1e-12)
+        results = g[f'c{c}_results']
+        probs = np.array([
+            orc.marginal_probs(states[t], n, bits)[int(''.join(str(int(b)) for b in results[t]), 2)]
+            for t in range(B)
+        ])
+        dev = DS.from_numpy(states.reshape(-1), np.complex128)
+        dev.bsv_collapse(n, bits, results, 1.0 / np.sqrt(probs))
+        np.testing.assert_allclose(dev.to_numpy().reshape(B, -1), g[f'c{c}_collapsed'].reshape(B, -1), atol=1e-12)
+
+
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
+def test_reduced_density_matrix_matches_oracle(DS, dtype):
+    """b2q_sv_reduced_density_matrix vs qis/states.py:676-693 restated."""
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 5, 9, 14, 21):
+        psi = rand_state(rng, n, dtype)
+        dev = DS.from_numpy(psi, dtype)
+        for m in range(1, min(n, 5) + 1):
+            for _ in range(3):
+                bits = rng.permutation(n)[:m].tolist()
+                got = dev.reduced_density_matrix(bits)
+                want = orc.reduced_density_matrix(psi, n, bits)
+                np.testing.assert_allclose(got, want, atol=2e-6 if dtype == np.complex64 else 1e-13, rtol=0)
+                assert abs(np.trace(got) - 1) < (1e-5 if dtype == np.complex64 else 1e-12)
+
+
 @pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
 def test_batched_trajectory_kernels_match_oracle(DS, dtype):
     """b2q_bsv_apply_select / b2q_bsv_kraus_weights / b2q_bsv_collapse against the

@@ -138,3 +138,45 @@ def test_dist_pack_roundtrip():
         i = np.arange(64)
         mask = sum(1 << b for b in bits)
         np.testing.assert_array_equal(p[:seg], s[(i & mask) == 0])
+
+
+def test_reduced_density_matrix_matches_reference():
+    g = load_golden('reduced_density_matrix.npz')
+    for c in range(int(g['num_cases'])):
+        n = int(g[f'c{c}_n'])
+        bits = [n - 1 - int(a) for a in g[f'c{c}_indices']]
+        rho = orc.reduced_density_matrix(g[f'c{c}_state'], n, bits)
+        np.testing.assert_allclose(rho, g[f'c{c}_rho'], atol=1e-13)
+        r1 = orc.reduced_density_matrix(g[f'c{c}_state'], n, bits[:1])
+        bloch = [2 * r1[0, 1].real, 2 * r1[1, 0].imag, (r1[0, 0] - r1[1, 1]).real]
+        np.testing.assert_allclose(bloch, g[f'c{c}_bloch'], atol=1e-6)  # reference returns float32
+
+
+def test_trajectory_ops_match_reference():
+    """bsv_* oracle functions against the reference's per-repetition pieces."""
+    g = load_golden('trajectory_ops.npz')
+    for c in range(int(g['num_cases'])):
+        n = int(g[f'c{c}_n'])
+        states = g[f'c{c}_states']
+        B = states.shape[0]
+        bits = [n - 1 - int(a) for a in g[f'c{c}_axes']]
+        kraus = g[f'c{c}_kraus']
+        w = orc.bsv_kraus_weights(states.reshape(-1), n, kraus, bits)
+        np.testing.assert_allclose(w, g[f'c{c}_weights'], atol=1e-13)
+        for i in range(len(kraus)):
+            got = orc.bsv_apply_select(states.reshape(-1), n, kraus, bits, np.full(B, i))
+            np.testing.assert_allclose(got.reshape(B, -1), g[f'c{c}_applied'][:, i], atol=1e-13)
+        # skip index leaves trajectories untouched; scale multiplies
+        choice = np.arange(B) % len(kraus)
+        scale = 1.0 / np.sqrt(w[np.arange(B), choice])
+        got = orc.bsv_apply_select(states.reshape(-1), n, kraus, bits, choice, scale, skip=0).reshape(B, -1)
+        for t in range(B):
+            want = states[t] if choice[t] == 0 else g[f'c{c}_applied'][t, choice[t]] * scale[t]
+            np.testing.assert_allclose(got[t], want, atol=1e-13)
+        results = g[f'c{c}_results']
+        probs = np.array([
+            orc.marginal_probs(states[t], n, bits)[int(''.join(str(int(b)) for b in results[t]), 2)]
+            for t in range(B)
+        ])
+        got = orc.bsv_collapse(states.reshape(-1), n, bits, results, 1.0 / np.sqrt(probs)).reshape(B, -1)
+        np.testing.assert_allclose(got, g[f'c{c}_collapsed'].reshape(B, -1), atol=1e-12)

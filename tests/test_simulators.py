@@ -392,6 +392,32 @@ def test_expectation_values_and_amplitudes(cirq, SV):
         )
 
 
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
+def test_density_matrix_of_and_bloch_vector_on_device(cirq, SV, dtype):
+    """sim/state_vector.py:109-167 through the device reduction kernel."""
+    q = cirq.LineQubit.range(7)
+    circuit = cirq.testing.random_circuit(q, 10, 0.9, random_state=21)
+    circuit.append(cirq.I.on_each(*q))
+    want = cirq.Simulator(dtype=dtype).simulate(circuit, qubit_order=q)
+    got = SV(dtype=dtype).simulate(circuit, qubit_order=q)
+    atol = 1e-6 if dtype == np.complex64 else 1e-12
+    for keep in ([q[3]], [q[0], q[6]], [q[5], q[1], q[2]], [q[6], q[0], q[3], q[4]],
+                 [q[2], q[4], q[1], q[6], q[0]], [q[1], q[2], q[3], q[4], q[5], q[6]]):
+        np.testing.assert_allclose(got.density_matrix_of(keep), want.density_matrix_of(keep), atol=atol)
+    for x in q:
+        np.testing.assert_allclose(got.bloch_vector_of(x), want.bloch_vector_of(x), atol=atol * 4)
+    np.testing.assert_allclose(got.density_matrix_of(), want.density_matrix_of(), atol=atol)
+    with pytest.raises(KeyError):
+        got.density_matrix_of([cirq.LineQubit(99)])
+    steps_w = list(cirq.Simulator(dtype=dtype).simulate_moment_steps(circuit, qubit_order=q))
+    steps_g = list(SV(dtype=dtype).simulate_moment_steps(circuit, qubit_order=q))
+    for i in (0, 4, len(steps_w) - 1):
+        np.testing.assert_allclose(
+            steps_g[i].density_matrix_of([q[2], q[5]]), steps_w[i].density_matrix_of([q[2], q[5]]), atol=atol
+        )
+        np.testing.assert_allclose(steps_g[i].bloch_vector_of(q[4]), steps_w[i].bloch_vector_of(q[4]), atol=atol * 4)
+
+
 def test_wide_and_composite_operations(cirq, SV):
     q = cirq.LineQubit.range(7)
     circuit = cirq.Circuit(
