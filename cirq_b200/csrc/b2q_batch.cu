@@ -22,8 +22,8 @@
 
 namespace b2q {
 
-constexpr int kSelMaxK = 3;
-constexpr int kSelMaxCount = 64;
+constexpr int kSelMaxK = 4;
+constexpr int kSelMaxCount = 1 << 16;
 
 struct SelParams {
   int n;               // qubits per trajectory
@@ -269,7 +269,8 @@ static int apply_select_t(void* state, int n, int b, const double* m128, int cou
   switch (k) {
     case 1: bsv_apply_select_kernel<real, 1><<<blocks, 256, 0, stream>>>(s, total_groups, mats, choice, scale, p); break;
     case 2: bsv_apply_select_kernel<real, 2><<<blocks, 256, 0, stream>>>(s, total_groups, mats, choice, scale, p); break;
-    default: bsv_apply_select_kernel<real, 3><<<blocks, 256, 0, stream>>>(s, total_groups, mats, choice, scale, p); break;
+    case 3: bsv_apply_select_kernel<real, 3><<<blocks, 256, 0, stream>>>(s, total_groups, mats, choice, scale, p); break;
+    default: bsv_apply_select_kernel<real, 4><<<blocks, 256, 0, stream>>>(s, total_groups, mats, choice, scale, p); break;
   }
   B2Q_LAUNCH_CHECK("bsv_apply_select_kernel");
   return B2Q_OK;
@@ -301,7 +302,8 @@ static int kraus_weights_t(const void* state, int n, int b, const double* m128, 
     switch (k) {
       case 1: bsv_kraus_weights_kernel<real, 1><<<grid, 256, smem, stream>>>(s, mats, out, t0, p); break;
       case 2: bsv_kraus_weights_kernel<real, 2><<<grid, 256, smem, stream>>>(s, mats, out, t0, p); break;
-      default: bsv_kraus_weights_kernel<real, 3><<<grid, 256, smem, stream>>>(s, mats, out, t0, p); break;
+      case 3: bsv_kraus_weights_kernel<real, 3><<<grid, 256, smem, stream>>>(s, mats, out, t0, p); break;
+      default: bsv_kraus_weights_kernel<real, 4><<<grid, 256, smem, stream>>>(s, mats, out, t0, p); break;
     }
     B2Q_LAUNCH_CHECK("bsv_kraus_weights_kernel");
   }
@@ -378,7 +380,7 @@ extern "C" int b2q_bsv_kraus_weights(const void* state, int dtype, int n_qubits,
   B2Q_REQUIRE(state != nullptr && matrices_c128 != nullptr && targets != nullptr &&
                   weights_dev != nullptr,
               "null argument");
-  B2Q_REQUIRE(count >= 1 && count <= kSelMaxCount, "1..%d operators, got %d", kSelMaxCount, count);
+  B2Q_REQUIRE(count >= 1 && count <= 256, "1..256 Kraus operators, got %d", count);
   int sorted[kSelMaxK];
   const int rc = check_batch_args(dtype, n_qubits, batch_bits, targets, k, sorted);
   if (rc != B2Q_OK) return rc;

@@ -280,12 +280,15 @@ class B200DensityMatrixSimulationState(SimulationState[B200DensityMatrix]):
         max_fused_qubits: int | None = None,
     ):
         qubits = tuple(qubits) if qubits is not None else ()
-        state = B200DensityMatrix.create(
-            initial_state=initial_state,
-            qid_shape=tuple(q.dimension for q in qubits),
-            dtype=dtype,
-            max_fused_qubits=max_fused_qubits,
-        )
+        if isinstance(initial_state, B200DensityMatrix):
+            state = initial_state  # an existing device state, adopted as is
+        else:
+            state = B200DensityMatrix.create(
+                initial_state=initial_state,
+                qid_shape=tuple(q.dimension for q in qubits),
+                dtype=dtype,
+                max_fused_qubits=max_fused_qubits,
+            )
         super().__init__(state=state, prng=prng, qubits=qubits, classical_data=classical_data)
         self._dtype = dtype
         self._max_fused_qubits = max_fused_qubits
@@ -400,6 +403,7 @@ class B200DensityMatrixSimulator(
         seed: 'cirq.RANDOM_STATE_OR_SEED_LIKE' = None,
         split_untangled_states: bool = True,
         max_fused_qubits: int | None = None,
+        sweep_batch: bool = False,
     ):
         super().__init__(
             dtype=dtype, noise=noise, seed=seed, split_untangled_states=split_untangled_states
@@ -407,6 +411,28 @@ class B200DensityMatrixSimulator(
         if dtype not in {np.complex64, np.complex128}:
             raise ValueError(f'dtype must be complex64 or complex128, was {dtype}')
         self._max_fused = None if max_fused_qubits is None else int(max_fused_qubits)
+        # True: run_sweep advances all resolvers as one device array (cirq_b200.sweeps)
+        self._sweep_batch = bool(sweep_batch)
+        self.last_run_info: dict = {}
+
+    def _state_from_device(self, dev: DeviceState, qubits):
+        """Simulation state adopting an existing device array (cirq_b200.sweeps)."""
+        return B200DensityMatrixSimulationState(
+            qubits=qubits, prng=self._prng, dtype=self._dtype, max_fused_qubits=self._max_fused,
+            initial_state=B200DensityMatrix(dev, len(qubits), self._max_fused),
+        )
+
+    def run_sweep_iter(self, program, params, repetitions: int = 1):
+        """``SimulatesSamples.run_sweep_iter`` (sim/simulator.py:62-94), optionally
+        batched over the resolvers."""
+        if self._sweep_batch:
+            from cirq_b200 import sweeps
+
+            batched = sweeps.run_sweep_batched(self, 'dm', program, params, repetitions, DeviceState)
+            if batched is not None:
+                yield from batched
+                return
+        yield from super().run_sweep_iter(program, params, repetitions)
 
     def _create_partial_simulation_state(self, initial_state, qubits, classical_data):
         if isinstance(initial_state, B200DensityMatrixSimulationState):

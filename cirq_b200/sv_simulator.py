@@ -359,12 +359,15 @@ class B200StateVectorSimulationState(SimulationState[B200StateVector]):
         max_fused_qubits: int | None = None,
     ):
         qubits = tuple(qubits) if qubits is not None else ()
-        state = B200StateVector.create(
-            initial_state=initial_state,
-            qid_shape=tuple(q.dimension for q in qubits),
-            dtype=dtype,
-            max_fused_qubits=max_fused_qubits,
-        )
+        if isinstance(initial_state, B200StateVector):
+            state = initial_state  # an existing device state, adopted as is
+        else:
+            state = B200StateVector.create(
+                initial_state=initial_state,
+                qid_shape=tuple(q.dimension for q in qubits),
+                dtype=dtype,
+                max_fused_qubits=max_fused_qubits,
+            )
         super().__init__(state=state, prng=prng, qubits=qubits, classical_data=classical_data)
         self._dtype = np.dtype(dtype)
         self._max_fused_qubits = max_fused_qubits
@@ -699,6 +702,9 @@ class B200Simulator(
             Kronecker-product kernel when a gate couples them; ignored above
             30 qubits.
         max_fused_qubits: widest fused block (one GPU pass each).
+        sweep_batch: False (default) runs ``run_sweep`` resolver by resolver like
+            the reference; True lays all resolvers out as one device array and
+            walks the circuit once (``cirq_b200.sweeps``) — same results.
         trajectory_batch: 0 (default) keeps the reference's one-simulation-per-
             repetition loop for noisy / mid-circuit-measured ``run`` calls, with
             its seeded results.  N > 1 advances up to N repetitions together as
@@ -715,6 +721,7 @@ class B200Simulator(
         split_untangled_states: bool = True,
         max_fused_qubits: int | None = None,
         trajectory_batch: int = 0,
+        sweep_batch: bool = False,
     ):
         if np.dtype(dtype).kind != 'c':
             raise ValueError(f'dtype must be a complex type but was {dtype}')
@@ -726,7 +733,28 @@ class B200Simulator(
         # None = kernel-matched policy (cirq_b200.fusion.fuser_for)
         self._max_fused = None if max_fused_qubits is None else int(max_fused_qubits)
         self._trajectory_batch = int(trajectory_batch)
+        self._sweep_batch = bool(sweep_batch)
         self.last_run_info: dict = {}
+
+    def _state_from_device(self, dev: DeviceState, qubits):
+        """Simulation state adopting an existing device array (cirq_b200.sweeps)."""
+        return B200StateVectorSimulationState(
+            qubits=qubits, prng=self._prng, dtype=self._dtype, max_fused_qubits=self._max_fused,
+            initial_state=B200StateVector(dev, len(qubits), self._max_fused),
+        )
+
+    def run_sweep_iter(self, program, params, repetitions: int = 1):
+        """``SimulatesSamples.run_sweep_iter`` (sim/simulator.py:62-94); with
+        ``sweep_batch=True`` all resolvers advance together as one device array
+        when the circuit allows it (cirq_b200.sweeps)."""
+        if self._sweep_batch:
+            from cirq_b200 import sweeps
+
+            batched = sweeps.run_sweep_batched(self, 'sv', program, params, repetitions, DeviceState)
+            if batched is not None:
+                yield from batched
+                return
+        yield from super().run_sweep_iter(program, params, repetitions)
 
     def _run(self, circuit, param_resolver, repetitions: int):
         """``SimulatorBase._run`` (sim/simulator_base.py:215-275) with the

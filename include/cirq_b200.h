@@ -264,7 +264,7 @@ int b2q_dist_apply_exchange(const void* shard_in, void* out_local, void* out_pee
  * performs once per repetition (sim/simulator_base.py:249-264).  `*_dev` arrays
  * are device pointers with one entry per trajectory. */
 
-/* psi_t <- scale_t * M[choice_t] psi_t on `targets` (k <= 3): the chosen unitary
+/* psi_t <- scale_t * M[choice_t] psi_t on `targets` (k <= 4, count <= 65536): the chosen unitary
  * of a mixture (sim/state_vector_simulation_state.py:183-203) or the chosen Kraus
  * operator with its 1/sqrt(weight) (:205-257).  matrices_c128 = count row-major
  * 2^k x 2^k complex128 matrices on the host; scale_dev may be NULL (= 1);

@@ -593,6 +593,85 @@ def test_density_matrix_expectation_steps_and_initial_state(cirq, DM):
 # --------------------------------------------------------------------------- mux entry points
 
 
+def _qaoa_like(cirq, n, seed):
+    import networkx as nx
+
+    q = cirq.LineQubit.range(n)
+    graph = nx.random_regular_graph(3, n, seed=seed)
+    g0, g1, b0, b1 = sympy.symbols('g0 g1 b0 b1')
+    c = cirq.Circuit(cirq.H.on_each(*q))
+    for g, b in ((g0, b0), (g1, b1)):
+        c.append(cirq.ZZ(q[i], q[j]) ** g for i, j in graph.edges)
+        c.append(cirq.rx(2 * b).on_each(*q))
+    c.append(cirq.measure(*q, key='m'))
+    sweep = cirq.Zip(
+        cirq.Linspace('g0', 0.1, 0.9, 7), cirq.Linspace('g1', 0.8, 0.2, 7),
+        cirq.Linspace('b0', 0.3, 1.2, 7), cirq.Points('b1', [0.5] * 7),
+    )
+    return c, q, sweep
+
+
+def test_batched_sweep_state_vector_matches_sequential(cirq, SV):
+    """sweep_batch=True: every resolver's samples equal the reference's
+    resolver-by-resolver run_sweep (sim/simulator.py:62-94) under the same seed."""
+    c, q, sweep = _qaoa_like(cirq, 6, 3)
+    c.insert(1, cirq.FSimGate(sympy.Symbol('g0'), 0.3).on(q[0], q[3]))  # non-EigenGate symbol
+    c.insert(2, cirq.CZ(q[1], q[2]))
+    want = cirq.Simulator(seed=7, split_untangled_states=False).run_sweep(c, sweep, repetitions=40)
+    sim = SV(seed=7, sweep_batch=True)
+    got = sim.run_sweep(c, sweep, repetitions=40)
+    assert sim.last_run_info['path'] == 'batched sweep' and sim.last_run_info['resolvers'] == 7
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g.params == w.params
+        np.testing.assert_array_equal(g.measurements['m'], w.measurements['m'])
+    # complex128, invert mask + two keys
+    c2 = c[:-1] + cirq.Circuit(
+        cirq.measure(q[0], q[2], key='a', invert_mask=(True, False)), cirq.measure(q[4], key='b'))
+    want = cirq.Simulator(seed=1, dtype=np.complex128, split_untangled_states=False).run_sweep(c2, sweep, repetitions=25)
+    got = SV(seed=1, dtype=np.complex128, sweep_batch=True).run_sweep(c2, sweep, repetitions=25)
+    for g, w in zip(got, want):
+        np.testing.assert_array_equal(g.measurements['a'], w.measurements['a'])
+        np.testing.assert_array_equal(g.measurements['b'], w.measurements['b'])
+
+
+def test_batched_sweep_falls_back(cirq, SV):
+    """Shapes the batch cannot take (mid-circuit measurement, noise on a state
+    vector) use the reference loop and still match it."""
+    q = cirq.LineQubit.range(3)
+    t = sympy.Symbol('t')
+    c = cirq.Circuit(cirq.rx(t).on(q[0]), cirq.measure(q[0], key='a'), cirq.CNOT(q[0], q[1]),
+                     cirq.measure(q[1], q[2], key='b'))
+    sweep = cirq.Linspace('t', 0, 2, 4)
+    want = cirq.Simulator(seed=3).run_sweep(c, sweep, repetitions=20)
+    sim = SV(seed=3, sweep_batch=True)
+    got = sim.run_sweep(c, sweep, repetitions=20)
+    assert sim.last_run_info.get('path') != 'batched sweep'
+    for g, w in zip(got, want):
+        np.testing.assert_array_equal(g.measurements['b'], w.measurements['b'])
+    with pytest.raises(ValueError, match='no measurements'):
+        SV(sweep_batch=True).run_sweep(cirq.Circuit(cirq.X(q[0])), sweep)
+    with pytest.raises(ValueError, match='symbols|resolved'):
+        SV(sweep_batch=True).run_sweep(c, cirq.Linspace('other', 0, 1, 3), repetitions=2)
+
+
+@pytest.mark.parametrize('noise_p', [0.0, 0.02])
+def test_batched_sweep_density_matrix_matches_sequential(cirq, DM, noise_p):
+    """Config-5 shape (noisy QAOA, run_sweep) on a small graph: batched over the
+    resolvers = the reference resolver by resolver, seeded."""
+    c, q, sweep = _qaoa_like(cirq, 4, 1)
+    c.insert(3, cirq.X(q[2]).with_probability(sympy.Symbol('g1') / 2))  # symbolic channel
+    noise = cirq.depolarize(noise_p) if noise_p else None
+    want = cirq.DensityMatrixSimulator(seed=5, noise=noise, split_untangled_states=False).run_sweep(
+        c, sweep, repetitions=30)
+    sim = DM(seed=5, noise=noise, sweep_batch=True)
+    got = sim.run_sweep(c, sweep, repetitions=30)
+    assert sim.last_run_info['path'] == 'batched sweep'
+    for g, w in zip(got, want):
+        assert g.params == w.params
+        np.testing.assert_array_equal(g.measurements['m'], w.measurements['m'])
+
+
 def test_mux_entry_points_match_reference(cirq, SV, DM):
     """cirq_b200.sample / final_state_vector / final_density_matrix mirror
     cirq.sample / ... (sim/mux.py) with the same signatures."""
