@@ -20,6 +20,13 @@ roofline  dominant kernel (sv_apply_fast_kernel): algorithmic bytes per launch
           events around the gate passes, vs the measured copy peak.
 cpu_baseline  the reference cirq.Simulator on the box's host cores on a bounded
           sample of the same generator (fewer qubits), timed in the same run.
+          Its gates are counted in the workload's own unit — gates on the
+          workload's state size: a gate pass over 2^m amplitudes counts as
+          2^(m-n) gates of the n-qubit workload (the same convention the N > 1
+          arm uses for its larger states); the raw number measured on the sample
+          is reported next to it.  The reference's time per gate grows at least
+          linearly in 2^n (20 -> 24 qubits: x24 for x16 amplitudes), so this
+          favours the reference.
 """
 from __future__ import annotations
 
@@ -48,7 +55,18 @@ WORKLOADS = {
 # bounded CPU samples (same generator, fewer qubits): ~5-20 s of reference time per step
 CPU_SAMPLE = {'rqc30': 'rqc20', 'rqc24': 'rqc20', 'rqc20': 'rqc20', 'qft34': 'qft22', 'qft30': 'qft22',
               'qft22': 'qft22', 'rc20': 'rc20'}
+# the reference arm (`--impl reference`) has minutes, not seconds: a larger sample
+REFERENCE_ARM_SAMPLE = dict(CPU_SAMPLE, rqc30='rqc24', qft34='qft24', qft30='qft24')
 WORKLOADS['qft22'] = ('qft', dict(n=22), 0)
+WORKLOADS['qft24'] = ('qft', dict(n=24), 0)
+
+
+def workload_equivalent(value, n_sample, workload):
+    """gates/s measured on an n_sample-qubit sample -> gates/s in units of the
+    workload's state size (a pass over 2^m amplitudes = 2^(m-n) workload gates)."""
+    kind, params, _ = WORKLOADS[workload]
+    n = params['rows'] * params['cols'] if kind == 'rqc' else params['n']
+    return value * 2.0 ** (n_sample - n), n
 
 
 def load_peaks():
@@ -74,8 +92,8 @@ def kernel_class(wires):
     """Name of the kernel a fused block on these index bits runs on (complex64,
     default knobs: b2q_apply_tc.cu launch_tc_k / b2q_apply.cu apply_matrix_t)."""
     k = len(wires)
-    if k == 5:
-        return 'sv_apply_tc_staged_kernel<5>' if min(wires) < 2 else 'sv_apply_tc_kernel<5>'
+    if k in (4, 5):  # b2q_set_tc_mode default 2: 4- and 5-qubit blocks on tcgen05
+        return f'sv_apply_tc_staged_kernel<{k}>' if min(wires) < 2 else f'sv_apply_tc_kernel<{k}>'
     if k == 6:
         return 'sv_apply_tc_kernel<6>'
     return f'sv_apply_fast_kernel<float,{k}>'
@@ -185,10 +203,13 @@ def run_reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    sample = CPU_SAMPLE[args.workload]
-    steps = max(1, min(args.steps, 3))
-    warmup = min(args.warmup, 1)
+    sample = REFERENCE_ARM_SAMPLE[args.workload]
+    big = sample != CPU_SAMPLE[args.workload]  # ~90 s per step: keep the run within minutes
+    steps = max(1, min(args.steps, 2 if big else 3))
+    warmup = 0 if big else min(args.warmup, 1)
     r = time_reference(sample, steps, warmup)
+    raw = r['value']
+    r['value'], n_workload = workload_equivalent(raw, r['n'], args.workload)
     line = {
         'impl': 'reference', 'metric': 'fused_gates_per_s', 'value': r['value'], 'unit': 'gates/s',
         'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup,
@@ -196,10 +217,16 @@ def run_reference_arm(args):
         'vs_baseline': None, 'dtype': 'c64', 'data': 'synthetic',
         'config': {'workload': args.workload, 'gate_unit': 'k<=2 fused blocks',
                    'reference_sample': sample, 'n_qubits': r['n'], 'raw_ops': r['raw_ops'],
-                   'unit_gates': r['unit_gates'], 'repetitions': r['reps']},
+                   'unit_gates': r['unit_gates'], 'repetitions': r['reps'],
+                   'gates_per_s_on_sample': raw,
+                   'value_unit': f"{n_workload}-qubit-equivalent gates/s = gates/s on the "
+                                 f"{r['n']}-qubit sample x 2^({r['n']}-{n_workload})"},
         'cpu_baseline': {'value': r['value'], 'unit': 'gates/s', 'cores': 1, 'kind': 'reference',
-                         'sample': f"cirq.Simulator(complex64) on {sample} ({r['n']} qubits, same generator; "
-                                   f"numpy path is single-threaded; host has {os.cpu_count()} cores)"},
+                         'raw_value_on_sample': raw,
+                         'sample': f"cirq.Simulator(complex64) on {sample} ({r['n']} qubits, same generator, "
+                                   f"{r['seconds_per_step']:.1f} s per step): {raw:.3g} gates/s there, counted as "
+                                   f"{n_workload}-qubit-equivalent gates (x 2^({r['n']}-{n_workload})); "
+                                   f"numpy path is single-threaded; host has {os.cpu_count()} cores"},
         'e2e': {'value': r['value'], 'unit': 'gates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -258,9 +285,14 @@ def run_b200_arm(args):
         for m, w in blocks:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            state.apply_matrix(m, w)
+            if np.ndim(m) == 1:  # a diagonal block (its table in shared memory)
+                state.apply_diagonal(m, w)
+                name = 'sv_apply_diag_smem_kernel<float>'
+            else:
+                state.apply_matrix(m, w)
+                name = kernel_class(w)
             b.record()
-            timed_apply.pairs.append((state.n_bits, kernel_class(w), a, b))
+            timed_apply.pairs.append((state.n_bits, name, a, b))
 
     timed_apply.pairs = []
 
@@ -352,11 +384,14 @@ def run_b200_arm(args):
     if not args.no_cpu_baseline:
         try:
             sample = CPU_SAMPLE[args.workload]
-            r = time_reference(sample, 1, 0)
-            cpu = {'value': r['value'], 'unit': 'gates/s', 'cores': 1, 'kind': 'reference',
+            r = time_reference(sample, 3, 0)
+            eq, _ = workload_equivalent(r['value'], r['n'], args.workload)
+            cpu = {'value': eq, 'unit': 'gates/s', 'cores': 1, 'kind': 'reference',
+                   'raw_value_on_sample': r['value'],
                    'sample': f"cirq.Simulator(complex64) on {sample}: {r['n']} qubits, {r['raw_ops']} ops = "
-                             f"{r['unit_gates']} k<=2 blocks, {r['reps']} repetitions, {r['seconds_per_step']:.2f} s; "
-                             f"single-threaded numpy, host has {os.cpu_count()} cores"}
+                             f"{r['unit_gates']} k<=2 blocks, {r['reps']} repetitions, 3 x {r['seconds_per_step']:.2f} s: "
+                             f"{r['value']:.3g} gates/s there, counted as {n}-qubit-equivalent gates "
+                             f"(x 2^({r['n']}-{n})); single-threaded numpy, host has {os.cpu_count()} cores"}
         except Exception as exc:  # reference not importable on this box
             cpu = {'value': None, 'unit': 'gates/s', 'cores': 1, 'kind': 'reference',
                    'sample': f'unavailable: {exc}'}
@@ -368,7 +403,8 @@ def run_b200_arm(args):
         'data': 'synthetic',
         'config': {'workload': args.workload, 'generator': wl['generator'], 'n_qubits': n,
                    'raw_ops': len(gates), 'gate_unit': 'k<=2 fused blocks (reference merge_k_qubit_unitaries(k=2) count)',
-                   'unit_gates': unit_gates, 'max_fused_qubits': max(len(w) for _, w in blocks),
+                   'unit_gates': unit_gates, 'max_fused_qubits': max(len(w) for m, w in blocks if np.ndim(m) == 2),
+                   'diagonal_passes_per_step': sum(1 for m, _ in blocks if np.ndim(m) == 1),
                    'passes_per_step': len(blocks), 'full_size_passes_per_step': full_passes,
                    'schedule': 'fusion + lazy state growth (kron-joined sub-states), planned once outside the timed region',
                    'repetitions': reps,

@@ -430,6 +430,73 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Diagonal block with its table in shared memory (k <= 13 complex64 / 12
+// complex128 wires: 64 KB).  A CTA walks chunks of 2^c contiguous amplitudes with
+// 16-byte lane accesses; the table index of an amplitude is the OR of a part
+// that depends on the chunk only (targets at or above bit c: computed once per
+// chunk) and a part read from a 2^c-entry uint16 table built once per CTA
+// (targets below bit c).  One read + one write of the state: HBM-bound.
+struct DiagSmemParams {
+  int n;
+  int k;
+  int c;         // log2 amplitudes per chunk
+  int tpos[16];  // tpos[b] <-> bit b of the table index
+};
+
+template <typename real>
+__global__ void __launch_bounds__(512)
+    sv_apply_diag_smem_kernel(typename Cplx<real>::type* __restrict__ state,
+                              const typename Cplx<real>::type* __restrict__ diag,
+                              const __grid_constant__ DiagSmemParams p) {
+  using C = typename Cplx<real>::type;
+  extern __shared__ __align__(16) unsigned char diag_smem[];
+  C* tab = reinterpret_cast<C*>(diag_smem);
+  uint16_t* low_tab = reinterpret_cast<uint16_t*>(tab + (1u << p.k));
+  const uint32_t chunk_elems = 1u << p.c;
+  for (uint32_t i = threadIdx.x; i < (1u << p.k); i += blockDim.x) tab[i] = diag[i];
+  for (uint32_t j = threadIdx.x; j < chunk_elems; j += blockDim.x) {
+    uint32_t v = 0;
+    for (int b = 0; b < p.k; ++b)
+      if (p.tpos[b] < p.c) v |= ((j >> p.tpos[b]) & 1u) << b;
+    low_tab[j] = (uint16_t)v;
+  }
+  __syncthreads();
+  constexpr int kPer = 16 / sizeof(C);  // amplitudes per 16-byte access
+  const uint64_t chunks = 1ull << (p.n - p.c);
+  for (uint64_t chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) {
+    const uint64_t base = chunk << p.c;
+    uint32_t vh = 0;
+    for (int b = 0; b < p.k; ++b)
+      if (p.tpos[b] >= p.c) vh |= (uint32_t)((base >> p.tpos[b]) & 1ull) << b;
+    if (chunk_elems >= (uint32_t)kPer) {
+#pragma unroll 4
+      for (uint32_t j = threadIdx.x * kPer; j < chunk_elems; j += blockDim.x * kPer) {
+        if constexpr (sizeof(C) == 8) {
+          float4 x = *reinterpret_cast<const float4*>(state + base + j);
+          const C d0 = tab[vh | low_tab[j]];
+          const C d1 = tab[vh | low_tab[j + 1]];
+          float4 y;
+          y.x = d0.x * x.x - d0.y * x.y;
+          y.y = d0.x * x.y + d0.y * x.x;
+          y.z = d1.x * x.z - d1.y * x.w;
+          y.w = d1.x * x.w + d1.y * x.z;
+          *reinterpret_cast<float4*>(state + base + j) = y;
+        } else {
+          const C a = state[base + j];
+          const C d = tab[vh | low_tab[j]];
+          state[base + j] = cmul<real>(d.x, d.y, a);
+        }
+      }
+    } else {  // a 1-amplitude complex64 state
+      if (threadIdx.x == 0) {
+        const C a = state[base];
+        const C d = tab[vh | low_tab[0]];
+        state[base] = cmul<real>(d.x, d.y, a);
+      }
+    }
+  }
+}
+
 // ---- host-side planning -----------------------------------------------------
 
 struct FastPlan {
@@ -807,22 +874,55 @@ extern "C" int b2q_sv_apply_diagonal(void* state, int dtype, int n_qubits,
   const size_t dim = (size_t)1 << k;
   const uint64_t total = 1ull << n_qubits;
   const uint64_t blocks = std::min<uint64_t>((total + 255) / 256, 148ull * 64);
+  const size_t esize = dtype == B2Q_C64 ? sizeof(float2) : sizeof(double2);
+  // table in shared memory when it fits 64 KB (k <= 13 complex64, 12 complex128)
+  const bool smem_path = dim * esize <= (64u << 10);
+  DiagSmemParams sp;
+  size_t smem_bytes = 0;
+  unsigned smem_grid = 1;
+  if (smem_path) {
+    sp.n = n_qubits;
+    sp.k = k;
+    sp.c = std::min(n_qubits, 13);
+    for (int b = 0; b < 16; ++b) sp.tpos[b] = p.tpos[b];
+    smem_bytes = dim * esize + (sizeof(uint16_t) << sp.c);
+    smem_grid = (unsigned)std::min<uint64_t>(1ull << (n_qubits - sp.c), 148ull * 2);
+    static bool attr_set[64][2] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev][dtype == B2Q_C64 ? 0 : 1]) {
+      if (dtype == B2Q_C64)
+        B2Q_CUDA_CHECK(cudaFuncSetAttribute(sv_apply_diag_smem_kernel<float>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 96 << 10));
+      else
+        B2Q_CUDA_CHECK(cudaFuncSetAttribute(sv_apply_diag_smem_kernel<double>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 96 << 10));
+      attr_set[dev][dtype == B2Q_C64 ? 0 : 1] = true;
+    }
+  }
   void* ddiag = nullptr;
   if (dtype == B2Q_C64) {
     std::vector<float> h(2 * dim);
     for (size_t i = 0; i < 2 * dim; ++i) h[i] = (float)diag_c128[i];
     B2Q_CUDA_CHECK(cudaMallocAsync(&ddiag, sizeof(float2) * dim, s));
+    // (a copy from pageable memory returns once the source has been staged)
     B2Q_CUDA_CHECK(cudaMemcpyAsync(ddiag, h.data(), sizeof(float2) * dim, cudaMemcpyHostToDevice, s));
-    B2Q_CUDA_CHECK(cudaStreamSynchronize(s));
-    sv_apply_diag_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(
-        reinterpret_cast<float2*>(state), reinterpret_cast<const float2*>(ddiag), p);
+    if (smem_path)
+      sv_apply_diag_smem_kernel<float><<<smem_grid, 512, smem_bytes, s>>>(
+          reinterpret_cast<float2*>(state), reinterpret_cast<const float2*>(ddiag), sp);
+    else
+      sv_apply_diag_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(
+          reinterpret_cast<float2*>(state), reinterpret_cast<const float2*>(ddiag), p);
   } else {
     B2Q_CUDA_CHECK(cudaMallocAsync(&ddiag, sizeof(double2) * dim, s));
     B2Q_CUDA_CHECK(
         cudaMemcpyAsync(ddiag, diag_c128, sizeof(double2) * dim, cudaMemcpyHostToDevice, s));
-    B2Q_CUDA_CHECK(cudaStreamSynchronize(s));
-    sv_apply_diag_kernel<double><<<(unsigned)blocks, 256, 0, s>>>(
-        reinterpret_cast<double2*>(state), reinterpret_cast<const double2*>(ddiag), p);
+    if (smem_path)
+      sv_apply_diag_smem_kernel<double><<<smem_grid, 512, smem_bytes, s>>>(
+          reinterpret_cast<double2*>(state), reinterpret_cast<const double2*>(ddiag), sp);
+    else
+      sv_apply_diag_kernel<double><<<(unsigned)blocks, 256, 0, s>>>(
+          reinterpret_cast<double2*>(state), reinterpret_cast<const double2*>(ddiag), p);
   }
   B2Q_LAUNCH_CHECK("sv_apply_diag_kernel");
   B2Q_CUDA_CHECK(cudaFreeAsync(ddiag, s));

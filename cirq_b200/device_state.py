@@ -133,6 +133,18 @@ class DeviceState:
         torch = _torch()
         if not gates:
             return
+        if any(np.ndim(m) == 1 for m, _ in gates):
+            # diagonal blocks (1-D: the diagonal entries) between runs of dense ones
+            run: list = []
+            for m, b in gates:
+                if np.ndim(m) == 1:
+                    self.apply_batch(run)
+                    run = []
+                    self.apply_diagonal(m, b)
+                else:
+                    run.append((m, b))
+            self.apply_batch(run)
+            return
         max_fast = 5 if self.code == _lib.C64 else 4
         if any(len(b) > max_fast for _, b in gates):
             for m, b in gates:

@@ -69,23 +69,63 @@ def apply_to_block(block: np.ndarray, union: Sequence[int], matrix: np.ndarray,
 
 
 class _Block:
-    __slots__ = ('wires', 'matrix', 'seq', 'alive', 'count')
+    __slots__ = ('wires', 'matrix', 'seq', 'alive', 'count', 'diag')
 
-    def __init__(self, wires, matrix, seq, count=1):
+    def __init__(self, wires, matrix, seq, count=1, diag=False):
         self.wires = tuple(wires)
-        self.matrix = matrix
+        self.matrix = matrix  # 2^k x 2^k, or the 2^k diagonal entries when `diag`
         self.seq = seq
         self.alive = True
         self.count = count
+        self.diag = diag
+
+    def dense(self) -> np.ndarray:
+        return np.diag(self.matrix) if self.diag else self.matrix
+
+
+_SWAP = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
+
+
+def is_diagonal(matrix: np.ndarray) -> bool:
+    m = np.asarray(matrix)
+    return m.ndim == 2 and not np.count_nonzero(m - np.diag(np.diagonal(m)))
+
+
+def expand_diagonal(diag: np.ndarray, wires: Sequence[int], out_wires: Sequence[int]) -> np.ndarray:
+    """The 2^u diagonal of (diag on `wires`) embedded in `out_wires` (a superset)."""
+    k, u = len(wires), len(out_wires)
+    idx = np.arange(1 << u)
+    sub = np.zeros(1 << u, dtype=np.int64)
+    for q, w in enumerate(wires):
+        pos = u - 1 - out_wires.index(w)  # bit of the big index holding wire w
+        sub |= ((idx >> pos) & 1) << (k - 1 - q)
+    return np.asarray(diag)[sub]
 
 
 class GateFuser:
     """Accumulates gates and emits fused blocks in a valid execution order."""
 
-    def __init__(self, max_qubits: int = 4, narrow_wires: Sequence[int] = (), narrow_max: int | None = None):
+    def __init__(self, max_qubits: int = 4, narrow_wires: Sequence[int] = (), narrow_max: int | None = None,
+                 diag_max: int = 0, relabel_swaps: bool = False):
         """`narrow_wires`: wires whose presence caps a block at `narrow_max`
-        qubits (index bits on which the widest kernel is inefficient)."""
+        qubits (index bits on which the widest kernel is inefficient).
+
+        `diag_max` > max_qubits turns on diagonal blocks: diagonal gates that do
+        not fit into a dense block with their predecessors are collected in
+        diagonal blocks of up to `diag_max` wires (one table-lookup pass each);
+        diagonal gates commute, so such a gate may join any diagonal block that
+        has no dense block after it on the gate's wires.
+
+        `relabel_swaps`: a SWAP gate moves no data — the two wires trade names
+        (as SimulationProductState does for whole qubits,
+        sim/simulation_product_state.py:95-108); `blocks()` restores the order
+        with real swaps at the end unless the caller takes the permutation
+        (`blocks(restore=False)` + `take_permutation()`)."""
         self.max_qubits = int(max_qubits)
+        self.diag_max = int(diag_max) if diag_max and diag_max > max_qubits else 0
+        self.relabel_swaps = bool(relabel_swaps)
+        self._map: dict[int, int] = {}  # caller's wire -> wire currently holding it
+        self._last_dense: dict[int, int] = {}  # wire -> seq of the last non-diagonal block on it
         self._narrow = frozenset(int(w) for w in narrow_wires)
         self._narrow_max = int(narrow_max) if narrow_max is not None else self.max_qubits
         self._blocks: list[_Block] = []
@@ -121,12 +161,24 @@ class GateFuser:
     def add(self, matrix: np.ndarray, wires: Sequence[int]) -> None:
         wires = tuple(int(w) for w in wires)
         k = len(wires)
-        self.num_gates += 1
         matrix = np.asarray(matrix, dtype=np.complex128).reshape(1 << k, 1 << k)
+        if self.relabel_swaps:
+            if k == 2 and np.array_equal(matrix, _SWAP):
+                a, b = wires
+                self._map[a], self._map[b] = self._map.get(b, b), self._map.get(a, a)
+                return
+            if self._map:
+                wires = tuple(self._map.get(w, w) for w in wires)
+        self._add(matrix, wires)
+
+    def _add(self, matrix: np.ndarray, wires: tuple[int, ...]) -> None:
+        k = len(wires)
+        self.num_gates += 1
         if k > self.max_qubits:
             # Too wide to fuse with anything: its own block at the end.
             self._append(_Block(wires, matrix, self._new_seq()))
             return
+        diag_gate = bool(self.diag_max) and k >= 2 and is_diagonal(matrix)
         cands: list[_Block] = []
         for w in wires:
             b = self._last.get(w)
@@ -134,8 +186,11 @@ class GateFuser:
                 cands.append(b)
         movable = [b for b in cands if self._movable(b)]
 
+        # (a diagonal gate never drags a diagonal block into a dense one)
+        diag_pred = diag_gate and any(b.diag for b in cands)
+
         # 1. everything on our wires can be pulled together at the end
-        if cands and len(movable) == len(cands):
+        if cands and len(movable) == len(cands) and not diag_pred:
             union = self._union([wires] + [b.wires for b in cands])
             if self._fits(union):
                 self._merge_at_end(cands, matrix, wires, union)
@@ -145,7 +200,7 @@ class GateFuser:
         #    touches any of our wires), plus movable neighbours that fit
         if cands:
             latest = max(cands, key=lambda b: b.seq)
-            if len(latest.wires) <= self.max_qubits:
+            if len(latest.wires) <= self.max_qubits and not (diag_gate and latest.diag):
                 union = self._union([latest.wires, wires])
                 if self._fits(union):
                     extra = []
@@ -158,6 +213,11 @@ class GateFuser:
                             extra.append(b)
                     self._merge_into(latest, extra, matrix, wires, union)
                     return
+        # 2b. a diagonal gate that found no room in a dense block: into a diagonal
+        #     block that no dense block follows on these wires (diagonals commute)
+        if diag_gate and cands:
+            self._add_diagonal(np.diagonal(matrix).copy(), wires)
+            return
         # 3. new block, pulling in movable predecessors that fit
         union = tuple(sorted(wires, reverse=True))
         extra = []
@@ -172,6 +232,31 @@ class GateFuser:
         self._blocks.append(block)
         for w in block.wires:
             self._last[w] = block
+            if not block.diag:
+                self._last_dense[w] = block.seq
+
+    def _add_diagonal(self, diag: np.ndarray, wires: tuple[int, ...]) -> None:
+        floor = max(self._last_dense.get(w, 0) for w in wires)
+        best, best_overlap = None, 0
+        for b in self._blocks:
+            if not (b.alive and b.diag and b.seq > floor):
+                continue
+            overlap = len(set(b.wires) & set(wires))
+            if overlap > best_overlap and len(set(b.wires) | set(wires)) <= self.diag_max:
+                best, best_overlap = b, overlap
+        if best is None:
+            self._append(_Block(tuple(sorted(wires, reverse=True)),
+                                expand_diagonal(diag, wires, tuple(sorted(wires, reverse=True))),
+                                self._new_seq(), diag=True))
+            return
+        union = self._union([best.wires, wires])
+        best.matrix = expand_diagonal(best.matrix, best.wires, union) * expand_diagonal(diag, wires, union)
+        best.wires = union
+        best.count += 1
+        for w in wires:
+            last = self._last.get(w)
+            if last is None or last.seq < best.seq:
+                self._last[w] = best
 
     def _compose(self, blocks: Sequence[_Block], matrix, wires, union) -> tuple[np.ndarray, int]:
         """G . (product of the given blocks, seq order) on `union`."""
@@ -179,9 +264,9 @@ class GateFuser:
         count = 1
         for b in sorted(blocks, key=lambda b: b.seq):
             if total is None:
-                total = expand_matrix(b.matrix, b.wires, union)
+                total = expand_matrix(b.dense(), b.wires, union)
             else:
-                total = apply_to_block(total, union, b.matrix, b.wires)
+                total = apply_to_block(total, union, b.dense(), b.wires)
             count += b.count
         if total is None:
             return expand_matrix(matrix, wires, union), count
@@ -197,9 +282,11 @@ class GateFuser:
         m, count = self._compose([target] + list(extra), matrix, wires, union)
         for b in extra:
             b.alive = False
+        was_diag = target.diag
         target.wires = union
         target.matrix = m
         target.count = count
+        target.diag = False
         # Only the wires that gained an operation move their frontier here; the
         # target's other wires may already have later blocks.
         for w in wires:
@@ -207,11 +294,39 @@ class GateFuser:
         for b in extra:
             for w in b.wires:
                 self._last[w] = target
+        for w in (union if was_diag else [x for b in extra for x in b.wires] + list(wires)):
+            self._last_dense[w] = max(self._last_dense.get(w, 0), target.seq)
 
-    def blocks(self) -> list[tuple[np.ndarray, tuple[int, ...]]]:
+    def blocks(self, restore: bool = True) -> list[tuple[np.ndarray, tuple[int, ...]]]:
         """Fused (matrix, wires) in execution order, independent narrow blocks
-        packed side by side (`pack_disjoint`)."""
+        packed side by side (`pack_disjoint`).  A 1-D `matrix` is a diagonal
+        block (its 2^k diagonal entries).  With relabelled SWAPs pending,
+        `restore` appends the real swaps that put every wire back in place."""
+        if restore and self._map:
+            self._restore_order()
         return pack_disjoint([(b.matrix, b.wires) for b in self._blocks if b.alive], self._fits)
+
+    def _restore_order(self) -> None:
+        """Real SWAP gates undoing the pending relabelling (cycle by cycle)."""
+        holder = {w: self._map.get(w, w) for w in self._map}  # caller's wire -> current wire
+        self._map = {}
+        at = {cur: w for w, cur in holder.items()}  # current wire -> caller's wire living there
+        for w in sorted(holder):
+            cur = holder[w]
+            if cur == w:
+                continue
+            # bring caller's wire w home: exchange the contents of wires `cur` and `w`
+            self._add(_SWAP, (cur, w))
+            other = at[w]  # the caller's wire that was living at position w
+            at[cur], holder[other] = other, cur
+            at[w], holder[w] = w, w
+
+    def take_permutation(self) -> dict[int, int]:
+        """{caller's wire: wire that holds it now} of the pending relabelling, which
+        is then forgotten (the caller renames its wires instead of moving data)."""
+        perm = {w: c for w, c in self._map.items() if w != c}
+        self._map = {}
+        return perm
 
     def num_blocks(self) -> int:
         return sum(1 for b in self._blocks if b.alive)
@@ -231,7 +346,12 @@ class GateFuser:
         for b in self._blocks:
             if not b.alive:
                 continue
-            final = all(self._last.get(w) is not b for w in b.wires)
+            if b.diag:
+                # may still grow while no dense block has closed one of its wires
+                final = len(b.wires) >= self.diag_max or all(
+                    self._last_dense.get(w, 0) > b.seq for w in b.wires)
+            else:
+                final = all(self._last.get(w) is not b for w in b.wires)
             if final and not any(w in blocked for w in b.wires):
                 out.append((b.matrix, b.wires))
                 self.num_gates -= b.count
@@ -242,8 +362,10 @@ class GateFuser:
         return pack_disjoint(out, self._fits)
 
     def clear(self) -> None:
+        """Forgets the scheduled blocks (a pending SWAP relabelling stays)."""
         self._blocks = []
         self._last = {}
+        self._last_dense = {}
         self.num_gates = 0
 
 
@@ -267,8 +389,11 @@ def pack_disjoint(blocks, fits) -> list[tuple[np.ndarray, tuple[int, ...]]]:
             if not groups[gi][0].isdisjoint(wset):
                 first = gi + 1
                 break
+        diagonal = np.ndim(m) == 1  # diagonal blocks keep their place and their shape
         for gi in range(first, len(groups)):
             g = groups[gi]
+            if diagonal or np.ndim(g[1][0][0]) == 1:
+                continue
             if fits(tuple(g[0] | wset)) and fits(tuple(g[0])) and fits(tuple(ws)):
                 g[0] |= wset
                 g[1].append((m, ws))
@@ -290,23 +415,34 @@ def pack_disjoint(blocks, fits) -> list[tuple[np.ndarray, tuple[int, ...]]]:
     return out
 
 
-def fuser_for(dtype, max_qubits: int | None = None, n_bits: int | None = None) -> 'GateFuser':
+# widest diagonal block whose table the kernel keeps in shared memory (64 KB)
+DIAG_MAX_WIRES = {np.dtype(np.complex64): 13, np.dtype(np.complex128): 12}
+
+
+def fuser_for(dtype, max_qubits: int | None = None, n_bits: int | None = None,
+              state_vector: bool = False) -> 'GateFuser':
     """The fusion policy matched to the kernels: complex64 fuses
     up to 5 wires (tensor-core kernels; blocks touching index bits 0-1 take the
     shared-memory-staged variant, so no wire needs a narrower cap any more —
     ``CIRQ_B200_NARROW_WIRES=0,1`` restores the old cap of 4 on those wires for
     experiments), except for states too small for that kernel; complex128 up to
-    4.  (A 6-qubit tensor-core kernel exists and is selected with max_qubits=6,
+    4.  `state_vector=True` adds diagonal blocks and SWAP relabelling (GateFuser).  (A 6-qubit tensor-core kernel exists and is selected with max_qubits=6,
     but at 5.2 ms per 30-qubit pass against 2.7 ms for 5 qubits it does not pay
     for the passes it saves.)"""
     is_c64 = np.dtype(dtype) == np.dtype(np.complex64)
     if max_qubits is None:
         max_qubits = 5 if is_c64 and (n_bits is None or n_bits >= 12) else 4
+    extra = {}
+    if state_vector and os.environ.get('CIRQ_B200_SMART_FUSION', '1') != '0':
+        # pure-state schedules also get diagonal blocks and relabelled SWAPs
+        # (density matrices fuse a gate with the noise that follows it into one
+        # dense 4-bit block, which diagonal blocks would only break up)
+        extra = dict(diag_max=DIAG_MAX_WIRES[np.dtype(dtype)], relabel_swaps=True)
     if is_c64 and max_qubits >= 5:
         narrow = os.environ.get('CIRQ_B200_NARROW_WIRES', '')
         wires = tuple(int(w) for w in narrow.split(',') if w.strip())
-        return GateFuser(max_qubits, narrow_wires=wires, narrow_max=4)
-    return GateFuser(max_qubits)
+        return GateFuser(max_qubits, narrow_wires=wires, narrow_max=4, **extra)
+    return GateFuser(max_qubits, **extra)
 
 
 def fuse_gates(gates, max_qubits: int = 4, dtype=None, n_bits: int | None = None):

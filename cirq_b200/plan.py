@@ -34,10 +34,18 @@ class _Component:
 
     def flush(self) -> None:
         if len(self.fuser):
-            blocks = self.fuser.blocks()
+            # relabelled SWAPs are not undone: the component renames its bits
+            blocks = self.fuser.blocks(restore=False)
             self.fuser.clear()
             self.dev.apply_batch(blocks)
             self.passes += len(blocks)
+        perm = self.fuser.take_permutation()
+        if perm:
+            top = len(self.bits) - 1
+            moved = list(self.bits)
+            for w, now in perm.items():
+                moved[top - now] = self.bits[top - w]
+            self.bits = moved
 
     def drain(self) -> None:
         ready = self.fuser.pop_final_blocks()
@@ -70,13 +78,13 @@ class SplitExecutor:
         if self.n > self.MAX_SPLIT_BITS and max_component_bits is None:
             bits = list(range(self.n - 1, -1, -1))
             c = _Component(bits, self._DS.basis(self.n, self.dtype, 0),
-                           fuser_for(self.dtype, max_fused_qubits, self.n))
+                           fuser_for(self.dtype, max_fused_qubits, self.n, state_vector=True))
             for b in bits:
                 self._comp[b] = c
         else:
             for b in range(self.n):
                 c = _Component([b], self._DS.basis(1, self.dtype, 0),
-                               fuser_for(self.dtype, max_fused_qubits, 1))
+                               fuser_for(self.dtype, max_fused_qubits, 1, state_vector=True))
                 self._comp[b] = c
         self.kron_count = 0
         self._since_drain = 0
@@ -91,7 +99,7 @@ class SplitExecutor:
             bits += other.bits
             passes += other.passes
             self.kron_count += 1
-        merged = _Component(bits, dev, fuser_for(self.dtype, self.max_fused, len(bits)))
+        merged = _Component(bits, dev, fuser_for(self.dtype, self.max_fused, len(bits), state_vector=True))
         merged.passes = passes
         for b in bits:
             self._comp[b] = merged

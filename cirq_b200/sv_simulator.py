@@ -61,7 +61,7 @@ class B200StateVector(qis.QuantumStateRepresentation):
         self._dev = dev
         self._n = int(num_qubits)
         self._max_fused = max_fused_qubits
-        self._fuser = fuser_for(dev.dtype, max_fused_qubits, self._n)
+        self._fuser = fuser_for(dev.dtype, max_fused_qubits, self._n, state_vector=True)
         self._qid_shape = (2,) * self._n
         self.passes = 0  # GPU gate passes issued so far (for benchmarks)
         self._since_drain = 0

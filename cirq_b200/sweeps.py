@@ -230,7 +230,7 @@ def execute_sweep(simulator, plan: SweepPlan, repetitions: int, device_state_cls
     max_fused = simulator._max_fused
     if plan.kind == 'dm' and max_fused is None:
         max_fused = 4
-    fuser = fuser_for(dtype, max_fused, sb + b)
+    fuser = fuser_for(dtype, max_fused, sb + b, state_vector=plan.kind == 'sv')
     passes = 0
 
     def flush():

@@ -126,7 +126,7 @@ class TrajectoryBatch:
         else:
             ones = type(psi0).from_numpy(np.ones(self.count, dtype=self.dtype))
             self.dev = ones.kron(psi0)
-        self.fuser = fuser_for(self.dtype, max_fused_qubits, self.n + self.b)
+        self.fuser = fuser_for(self.dtype, max_fused_qubits, self.n + self.b, state_vector=True)
         self.passes = 0
 
     # -- unitary part ---------------------------------------------------------------------

@@ -60,7 +60,10 @@ class OracleDeviceState:
 
     def apply_batch(self, gates):
         for m, b in gates:
-            self.apply_matrix(m, b)
+            if np.ndim(m) == 1:  # a diagonal block
+                self.apply_diagonal(m, b)
+            else:
+                self.apply_matrix(m, b)
 
     def apply_diagonal(self, diag, bits):
         self.array = orc.apply_diagonal(self.array, self.n_bits, diag, list(bits))

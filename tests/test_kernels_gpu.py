@@ -94,9 +94,9 @@ def test_every_single_and_pair_position(DS, dtype):
         assert err <= ATOL[np.dtype(dtype)], (a, b, err)
 
 
-@pytest.mark.parametrize('k', [5, 6])
+@pytest.mark.parametrize('k', [4, 5, 6])
 def test_tensor_core_kernels_match_oracle(DS, k):
-    """tcgen05 path (complex64, k = 5 and 6): every position class, 3xTF32 split
+    """tcgen05 path (complex64, k = 4, 5 and 6): every position class, 3xTF32 split
     must stay within the complex64 tolerance."""
     rng = np.random.RandomState(60 + k)
     for n in (k + 7, 16, 20):
@@ -186,6 +186,52 @@ def test_diagonal_scale_init(DS, dtype):
         idx = int(rng.randint(1 << n))
         b = DS.basis(n, dtype, idx).to_numpy()
         assert b[idx] == 1 and np.count_nonzero(b) == 1
+
+
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
+def test_wide_diagonal_blocks(DS, dtype):
+    """Diagonal blocks of up to 16 wires: shared-memory table kernel (<= 13 wires
+    complex64 / 12 complex128) and the global-table kernel above, every position
+    class (chunk-local bits, chunk-selecting bits, mixed), bit-exact table indexing."""
+    rng = np.random.RandomState(31)
+    for n in (1, 3, 12, 13, 14, 18, 22):
+        state = rand_state(rng, n, dtype)
+        widths = sorted({1, min(n, 2), min(n, 7), min(n, 12), min(n, 13), min(n, 14), min(n, 16)})
+        for k in widths:
+            picks = [rng.permutation(n)[:k].tolist(), list(range(k)), list(range(n - k, n))[::-1]]
+            for targets in picks:
+                d = np.exp(1j * rng.standard_normal(1 << k))
+                dev = DS.from_numpy(state)
+                dev.apply_diagonal(d, targets)
+                err = np.max(np.abs(dev.to_numpy() - orc.apply_diagonal(state, n, d, targets)))
+                assert err <= ATOL[np.dtype(dtype)], (n, k, targets, err)
+    # index mapping is exact: a table of distinct integers reproduces the index bits
+    n, targets = 15, [14, 0, 7, 3, 9, 1, 12]
+    d = np.arange(1 << len(targets)).astype(np.complex128)
+    dev = DS.from_numpy(np.ones(1 << n, dtype=dtype))
+    dev.apply_diagonal(d, targets)
+    idx = np.arange(1 << n)
+    want = np.zeros(1 << n, dtype=np.int64)
+    for t in targets:
+        want = (want << 1) | ((idx >> t) & 1)
+    np.testing.assert_array_equal(dev.to_numpy().real.astype(np.int64), want)
+    # mixed batches: dense blocks and diagonal blocks in one apply_batch call
+    n = 16
+    state = rand_state(rng, n, dtype)
+    gates = []
+    for i in range(12):
+        if i % 3 == 1:
+            k = int(rng.randint(2, 13))
+            gates.append((np.exp(1j * rng.standard_normal(1 << k)), rng.permutation(n)[:k].tolist()))
+        else:
+            k = int(rng.randint(1, 4))
+            gates.append((rand_unitary(rng, k), rng.permutation(n)[:k].tolist()))
+    dev = DS.from_numpy(state)
+    dev.apply_batch(gates)
+    want = state.astype(np.complex128)
+    for m, w in gates:
+        want = orc.apply_diagonal(want, n, m, w) if np.ndim(m) == 1 else orc.apply_matrix(want, n, m, w)
+    assert np.max(np.abs(dev.to_numpy() - want)) <= 4 * ATOL[np.dtype(dtype)]
 
 
 @pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
