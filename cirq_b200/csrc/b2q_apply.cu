@@ -436,6 +436,8 @@ __global__ void __launch_bounds__(256)
 // that depends on the chunk only (targets at or above bit c: computed once per
 // chunk) and a part read from a 2^c-entry uint16 table built once per CTA
 // (targets below bit c).  One read + one write of the state: HBM-bound.
+constexpr int kDiagVec = 8;  // 16-byte accesses per thread per full chunk
+
 struct DiagSmemParams {
   int n;
   int k;
@@ -468,7 +470,39 @@ __global__ void __launch_bounds__(512)
     uint32_t vh = 0;
     for (int b = 0; b < p.k; ++b)
       if (p.tpos[b] >= p.c) vh |= (uint32_t)((base >> p.tpos[b]) & 1ull) << b;
-    if (chunk_elems >= (uint32_t)kPer) {
+    if (chunk_elems == (uint32_t)kPer * kDiagVec * 512u) {
+      // full-size chunk: all of a thread's loads are issued before the first
+      // store (in-place updates otherwise serialise load -> store -> load)
+      float4 x[kDiagVec];
+#pragma unroll
+      for (int u = 0; u < kDiagVec; ++u) {
+        const uint32_t j = (threadIdx.x + u * 512u) * kPer;
+        x[u] = __ldcs(reinterpret_cast<const float4*>(state + base + j));
+      }
+      // barrier (uniform: the chunk loop is CTA-wide): ptxas moves no memory
+      // access across it; without it the later loads sink below the first stores
+      // to save registers and only four stay in flight
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < kDiagVec; ++u) {
+        const uint32_t j = (threadIdx.x + u * 512u) * kPer;
+        float4 y;
+        if constexpr (sizeof(C) == 8) {
+          const C d0 = tab[vh | low_tab[j]];
+          const C d1 = tab[vh | low_tab[j + 1]];
+          y.x = d0.x * x[u].x - d0.y * x[u].y;
+          y.y = d0.x * x[u].y + d0.y * x[u].x;
+          y.z = d1.x * x[u].z - d1.y * x[u].w;
+          y.w = d1.x * x[u].w + d1.y * x[u].z;
+        } else {
+          const C d = tab[vh | low_tab[j]];
+          const double2 a = *reinterpret_cast<const double2*>(&x[u]);
+          const double2 r = cmul<double>(d.x, d.y, a);
+          y = *reinterpret_cast<const float4*>(&r);
+        }
+        __stcs(reinterpret_cast<float4*>(state + base + j), y);
+      }
+    } else if (chunk_elems >= (uint32_t)kPer) {
 #pragma unroll 4
       for (uint32_t j = threadIdx.x * kPer; j < chunk_elems; j += blockDim.x * kPer) {
         if constexpr (sizeof(C) == 8) {
@@ -883,7 +917,7 @@ extern "C" int b2q_sv_apply_diagonal(void* state, int dtype, int n_qubits,
   if (smem_path) {
     sp.n = n_qubits;
     sp.k = k;
-    sp.c = std::min(n_qubits, 13);
+    sp.c = std::min(n_qubits, dtype == B2Q_C64 ? 13 : 12);  // 4096 16-byte vectors per chunk
     for (int b = 0; b < 16; ++b) sp.tpos[b] = p.tpos[b];
     smem_bytes = dim * esize + (sizeof(uint16_t) << sp.c);
     smem_grid = (unsigned)std::min<uint64_t>(1ull << (n_qubits - sp.c), 148ull * 2);

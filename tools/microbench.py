@@ -41,7 +41,21 @@ def _nvml_clock():
         return None
 
 
+class _Applier:
+    """dev.apply_matrix, or dev.apply_diagonal for a 1-D `m` (a diagonal block)."""
+
+    def __init__(self, dev):
+        self.dev = dev
+
+    def apply_matrix(self, m, bits):
+        if np.ndim(m) == 1:
+            self.dev.apply_diagonal(m, bits)
+        else:
+            self.dev.apply_matrix(m, bits)
+
+
 def time_pass(dev, m, bits, reps):
+    dev = _Applier(dev)
     for _ in range(3):
         dev.apply_matrix(m, bits)
     if WARM_MS > 0:
@@ -143,11 +157,23 @@ def main():
             'k5_bit0_mid': [0, 3, 7, 12, 20],
             'k5_bit1_mid': [1, 3, 7, 12, 20],
         })
+    # diagonal blocks (table in shared memory up to 13 / 12 wires)
+    kd = 13 if dtype == np.complex64 else 12
+    classes.update({
+        'diag2_high': [hi, hi - 1],
+        f'diag{kd}_low': list(range(kd)),
+        f'diag{kd}_high': list(range(hi, hi - kd, -1)),
+        f'diag{kd}_mixed': [0, 2, 5, 9, 11, 12, 14, 17, 20, 23, 25, hi - 1, hi][:kd],
+        'diag16_mixed': [0, 2, 5, 9, 11, 12, 13, 14, 17, 19, 20, 23, 25, 27, hi - 1, hi],
+    })
     results = {}
     if args.only:
         classes = {k: v for k, v in classes.items() if any(k.startswith(p) for p in args.only.split(','))}
     for name, bits in classes.items():
-        m = rand_unitary(rng, len(bits))
+        if name.startswith('diag'):
+            m = np.exp(1j * rng.standard_normal(1 << len(bits)))
+        else:
+            m = rand_unitary(rng, len(bits))
         ms = time_pass(dev, m, bits, args.reps)
         gbs = bytes_per_pass / ms / 1e6
         results[name] = {'bits': bits, 'ms': ms, 'GBps': gbs}
