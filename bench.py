@@ -92,7 +92,8 @@ def kernel_class(wires):
     """Name of the kernel a fused block on these index bits runs on (complex64,
     default knobs: b2q_apply_tc.cu launch_tc_k / b2q_apply.cu apply_matrix_t)."""
     k = len(wires)
-    if k in (4, 5):  # b2q_set_tc_mode default 2: 4- and 5-qubit blocks on tcgen05
+    tc4 = os.environ.get('CIRQ_B200_TC_MODE') == '2'  # opt-in: 4-qubit blocks on tcgen05 too
+    if k == 5 or (k == 4 and tc4):
         return f'sv_apply_tc_staged_kernel<{k}>' if min(wires) < 2 else f'sv_apply_tc_kernel<{k}>'
     if k == 6:
         return 'sv_apply_tc_kernel<6>'

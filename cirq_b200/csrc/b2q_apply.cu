@@ -479,10 +479,10 @@ __global__ void __launch_bounds__(512)
         const uint32_t j = (threadIdx.x + u * 512u) * kPer;
         x[u] = __ldcs(reinterpret_cast<const float4*>(state + base + j));
       }
-      // barrier (uniform: the chunk loop is CTA-wide): ptxas moves no memory
-      // access across it; without it the later loads sink below the first stores
-      // to save registers and only four stay in flight
-      __syncthreads();
+      // warp barrier: ptxas moves no memory access across it; without it the
+      // later loads sink below the first stores to save registers and only four
+      // stay in flight (a CTA-wide barrier here cost 12 stall cycles per issue)
+      __syncwarp();
 #pragma unroll
       for (int u = 0; u < kDiagVec; ++u) {
         const uint32_t j = (threadIdx.x + u * 512u) * kPer;
@@ -904,6 +904,36 @@ extern "C" int b2q_sv_apply_diagonal(void* state, int dtype, int n_qubits,
   for (int q = 0; q < k; ++q) {
     B2Q_REQUIRE(targets[q] >= 0 && targets[q] < n_qubits, "target bit out of range");
     p.tpos[k - 1 - q] = targets[q];
+  }
+  // The kernels want index bit b <-> the b-th LOWEST target (neighbouring
+  // amplitudes then read neighbouring table entries: no shared-memory bank
+  // conflicts, cache-line locality for the global table); other orders get their
+  // table permuted here.
+  std::vector<double> permuted;
+  {
+    bool ascending = true;
+    for (int b = 1; b < k; ++b) ascending = ascending && p.tpos[b] > p.tpos[b - 1];
+    if (!ascending) {
+      int sorted[16], from_bit[16];
+      for (int b = 0; b < k; ++b) sorted[b] = p.tpos[b];
+      std::sort(sorted, sorted + k);
+      for (int b = 1; b < k; ++b)
+        B2Q_REQUIRE(sorted[b] != sorted[b - 1], "duplicate target bit %d", sorted[b]);
+      for (int b = 0; b < k; ++b)
+        for (int o = 0; o < k; ++o)
+          if (p.tpos[o] == sorted[b]) from_bit[b] = o;  // new index bit b = old index bit o
+      const size_t dim0 = (size_t)1 << k;
+      permuted.resize(2 * dim0);
+      for (size_t v = 0; v < dim0; ++v) {
+        size_t old = 0;
+        for (int b = 0; b < k; ++b)
+          if ((v >> b) & 1) old |= (size_t)1 << from_bit[b];
+        permuted[2 * v] = diag_c128[2 * old];
+        permuted[2 * v + 1] = diag_c128[2 * old + 1];
+      }
+      diag_c128 = permuted.data();
+      for (int b = 0; b < k; ++b) p.tpos[b] = sorted[b];
+    }
   }
   const size_t dim = (size_t)1 << k;
   const uint64_t total = 1ull << n_qubits;

@@ -702,7 +702,7 @@ static float tf32_round_host(float x) {
   return r;
 }
 
-std::atomic<int> g_tc_mode{2};  // 0 = off, 1 = tensor cores for k = 5, 6 (complex64), 2 = also k = 4
+std::atomic<int> g_tc_mode{1};  // 0 = off, 1 = tensor cores for k = 5, 6 (complex64), 2 = also k = 4
 // 0 = never stage through shared memory, 1 = stage when a target sits on index
 // bit 0 or 1, 2 = always (k <= 5)
 std::atomic<int> g_tc_stage_mode{1};

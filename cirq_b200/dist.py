@@ -424,7 +424,7 @@ class ShardedStateVector:
         m, bits = pending[-1]
         bits = list(bits)
         k = len(bits)
-        if k > 5:
+        if k > 5 or np.ndim(m) == 1:
             return None
         if k < 4:
             # identity on spare wires (the highest free local bits)
@@ -441,6 +441,19 @@ class ShardedStateVector:
         if not glob:
             self.local_only_blocks += 1
             return m, pw
+        if np.ndim(m) == 1:
+            # a diagonal block never needs communication: this rank applies the
+            # entries selected by its rank bits
+            k = len(pw)
+            t = np.asarray(m).reshape((2,) * k)
+            sel = tuple(self._rank_bit(p) if p >= self.n_local else slice(None) for p in pw)
+            rest = [p for p in pw if p < self.n_local]
+            self.diag_global_blocks += 1
+            sub = np.ascontiguousarray(t[sel]).reshape(-1)
+            if not rest:
+                self.local.scale(complex(sub[0]))
+                return sub, []
+            return sub, rest
         key = (id(m), tuple(pw))
         if key not in self._diag_cache:
             self._diag_cache[key] = block_diagonal_in(m, pw, glob, atol=1e-24)
@@ -539,7 +552,7 @@ def plan_sharded(n_qubits: int, gates, dtype, max_fused_qubits, n_local: int):
     gates = list(gates)
     if n_local > LAZY_MAX_SHARD_BITS:
         return {'n': n_qubits, 'dtype': np.dtype(dtype), 'ops': [], 'components': None,
-                'blocks': fuse_gates(gates, max_fused_qubits, dtype, n_local)}
+                'blocks': fuse_gates(gates, max_fused_qubits, dtype, n_local, diagonal_blocks=True)}
     ex = SplitExecutor(n_qubits, dtype, max_fused_qubits, Rec, max_component_bits=min(n_local, 30))
     done = len(gates)
     for i, (m, b) in enumerate(gates):
@@ -548,7 +561,7 @@ def plan_sharded(n_qubits: int, gates, dtype, max_fused_qubits, n_local: int):
             break
     comps = [(dev.ident, bits) for dev, bits in ex.components()]
     return {'n': n_qubits, 'dtype': np.dtype(dtype), 'ops': Rec.ops, 'components': comps,
-            'blocks': fuse_gates(gates[done:], max_fused_qubits, dtype, n_local),
+            'blocks': fuse_gates(gates[done:], max_fused_qubits, dtype, n_local, diagonal_blocks=True),
             'prefix_gates': done}
 
 
@@ -632,7 +645,7 @@ class B200ShardedSimulator:
         gates, _ = self._gates(circuit, qubits)
         if initial_state != 0:
             sv = ShardedStateVector(len(qubits), self.dtype, group=self.group, initial_index=initial_state)
-            sv.apply_blocks(fuse_gates(gates, self.max_fused, self.dtype, sv.n_local))
+            sv.apply_blocks(fuse_gates(gates, self.max_fused, self.dtype, sv.n_local, diagonal_blocks=True))
             return sv
         sv = ShardedStateVector(len(qubits), self.dtype, group=self.group, initial_index=None)
         execute_sharded_plan(plan_sharded(sv.n, gates, self.dtype, self.max_fused, sv.n_local), sv)

@@ -445,10 +445,14 @@ def fuser_for(dtype, max_qubits: int | None = None, n_bits: int | None = None,
     return GateFuser(max_qubits, **extra)
 
 
-def fuse_gates(gates, max_qubits: int = 4, dtype=None, n_bits: int | None = None):
+def fuse_gates(gates, max_qubits: int = 4, dtype=None, n_bits: int | None = None,
+               diagonal_blocks: bool = False):
     """Convenience wrapper: [(matrix, wires)] -> fused [(matrix, wires)].  With
-    `dtype` the kernel-matched policy of `fuser_for` is used."""
+    `dtype` the kernel-matched policy of `fuser_for` is used; `diagonal_blocks`
+    adds diagonal blocks (1-D matrices) without SWAP relabelling."""
     f = GateFuser(max_qubits) if dtype is None else fuser_for(dtype, max_qubits, n_bits)
+    if diagonal_blocks and dtype is not None:
+        f.diag_max = DIAG_MAX_WIRES[np.dtype(dtype)]
     for m, w in gates:
         f.add(m, w)
     return f.blocks()

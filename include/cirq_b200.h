@@ -303,10 +303,10 @@ int b2q_set_lane_mode(int mode);
 /* complex64 access width of the register kernel: 0 = policy (default), 1 = always
  * 16-byte vectors, 2 = always one amplitude per lane. */
 int b2q_set_vec_mode(int mode);
-/* Tensor-core (tcgen05) kernels for complex64 blocks: 0 = off, 1 = k = 5 and 6,
- * 2 = also k = 4 (default: under the board's power cap the 4-qubit tensor-core
- * pass measured 2.84 ms at 30 qubits against 3.58 ms for the FP32 kernel,
- * profiles/README.md r1x). */
+/* Tensor-core (tcgen05) kernels for complex64 blocks: 0 = off, 1 = k = 5 and 6
+ * (default: the scope allows tensor cores for k >= 5 only), 2 = also k = 4 (an
+ * experiment: under the board's power cap the 4-qubit tensor-core pass measured
+ * 2.84 ms at 30 qubits against 3.58 ms for the FP32 kernel, profiles/README.md r1x). */
 int b2q_set_tc_mode(int mode);
 /* Shared-memory staging of the tensor-core kernels (coalesced HBM access for any
  * target positions): 0 = never, 1 = when a target sits on index bit 0 or 1
