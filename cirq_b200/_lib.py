@@ -80,6 +80,7 @@ SIGNATURES = {
     ),
     'b2q_dm_diagonal': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'b2q_probs_marginal': (c_int, [c_void_p, c_int, POINTER(c_int), c_int, c_void_p, c_void_p]),
+    'b2q_dm_pauli_expectation': (c_int, [c_void_p, c_int, c_int, c_uint64, c_uint64, POINTER(c_double), c_void_p]),
     'b2q_dm_trace': (c_int, [c_void_p, c_int, c_int, POINTER(c_double), c_void_p]),
     'b2q_dm_collapse': (
         c_int,

@@ -680,6 +680,41 @@ static int reduced_dm_t(const void* state, int n, int m, const RdmParams& p, dou
   }
 }
 
+// tr(rho P) = sum_i rho[i, i ^ x] * sign(i): only 2^n of rho's 4^n entries are read.
+// partial[b] = the block's (re, im) sum.
+template <typename real>
+__global__ void __launch_bounds__(256)
+    dm_pauli_partial_kernel(const typename Cplx<real>::type* __restrict__ rho, int n,
+                            uint64_t xmask, uint64_t zmask, double* __restrict__ partial) {
+  using C = typename Cplx<real>::type;
+  const uint64_t dim = 1ull << n;
+  double ar = 0.0, ai = 0.0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < dim;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const C a = rho[(i << n) | (i ^ xmask)];
+    const bool neg = __popcll(i & zmask) & 1;
+    ar += neg ? -(double)a.x : (double)a.x;
+    ai += neg ? -(double)a.y : (double)a.y;
+  }
+  __shared__ double sm[16];
+  ar = warp_sum(ar);
+  ai = warp_sum(ai);
+  if ((threadIdx.x & 31) == 0) {
+    sm[2 * (threadIdx.x >> 5)] = ar;
+    sm[2 * (threadIdx.x >> 5) + 1] = ai;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tr = 0, ti = 0;
+    for (int w = 0; w < 8; ++w) {
+      tr += sm[2 * w];
+      ti += sm[2 * w + 1];
+    }
+    partial[2 * blockIdx.x] = tr;
+    partial[2 * blockIdx.x + 1] = ti;
+  }
+}
+
 // ---- dist pack / unpack -----------------------------------------------------
 
 struct PackParams {
@@ -1114,6 +1149,43 @@ extern "C" int b2q_sv_reduced_density_matrix(const void* state, int dtype, int n
       out_c128[2 * (a * d + b)] = h[src];
       out_c128[2 * (a * d + b) + 1] = h[src + 1];
     }
+  return B2Q_OK;
+}
+
+extern "C" int b2q_dm_pauli_expectation(const void* rho, int dtype, int n_qubits, uint64_t x_mask,
+                                        uint64_t z_mask, double* out_re_im, void* stream) {
+  B2Q_REQUIRE(rho != nullptr && out_re_im != nullptr, "null argument");
+  B2Q_CHECK_DTYPE(dtype);
+  B2Q_REQUIRE(n_qubits >= 1 && 2 * n_qubits <= 40, "density matrix too large");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const uint64_t dim = 1ull << n_qubits;
+  B2Q_REQUIRE(x_mask < dim && z_mask < dim, "mask out of range");
+  const unsigned blocks = stride_grid(dim, 256);
+  double* partial = reinterpret_cast<double*>(workspace(sizeof(double) * 2 * (blocks + 1)));
+  if (partial == nullptr) return B2Q_ERR_CUDA;
+  if (dtype == B2Q_C64)
+    dm_pauli_partial_kernel<float><<<blocks, 256, 0, s>>>(reinterpret_cast<const float2*>(rho),
+                                                          n_qubits, x_mask, z_mask, partial);
+  else
+    dm_pauli_partial_kernel<double><<<blocks, 256, 0, s>>>(reinterpret_cast<const double2*>(rho),
+                                                           n_qubits, x_mask, z_mask, partial);
+  B2Q_LAUNCH_CHECK("dm_pauli_partial_kernel");
+  final_sum_kernel<<<1, 256, 0, s>>>(partial, blocks, 2, partial + 2 * blocks);
+  B2Q_LAUNCH_CHECK("final_sum_kernel");
+  double h[2];
+  B2Q_CUDA_CHECK(
+      cudaMemcpyAsync(h, partial + 2 * blocks, sizeof(double) * 2, cudaMemcpyDeviceToHost, s));
+  B2Q_CUDA_CHECK(cudaStreamSynchronize(s));
+  // <i ^ x| P |i> = i^{nY} (-1)^{popcount(i & z)}, nY = popcount(x & z)
+  const int ny = __builtin_popcountll(x_mask & z_mask) & 3;
+  double re = h[0], im = h[1];
+  for (int t = 0; t < ny; ++t) {  // multiply by i
+    const double nr = -im, ni = re;
+    re = nr;
+    im = ni;
+  }
+  out_re_im[0] = re;
+  out_re_im[1] = im;
   return B2Q_OK;
 }
 

@@ -540,6 +540,18 @@ class DeviceState:
         )
         return out
 
+    def dm_pauli_expectation(self, x_mask: int, z_mask: int) -> complex:
+        """tr(rho P) for this 2n-bit array read as an n-qubit density matrix."""
+        torch = _torch()
+        out = (ctypes.c_double * 2)()
+        check(
+            self._lib.b2q_dm_pauli_expectation(
+                self.ptr, self.code, self.n_bits // 2, ctypes.c_uint64(int(x_mask)),
+                ctypes.c_uint64(int(z_mask)), out, _stream_ptr(torch),
+            )
+        )
+        return complex(out[0], out[1])
+
     def dm_trace(self) -> float:
         torch = _torch()
         out = ctypes.c_double(0.0)

@@ -486,10 +486,26 @@ class B200DensityMatrixSimulator(
             result = self.simulate(
                 program, param_resolver, qubit_order=qubit_order, initial_state=initial_state
             )
-            swept_evs.append(
-                [
-                    obs.expectation_from_density_matrix(result.final_density_matrix, qmap)
-                    for obs in pslist
-                ]
-            )
+            # tr(rho P) per Pauli string on the device (2^n entries of rho each)
+            # instead of the reference's einsum over a host copy of rho
+            dev = result.device_state
+            swept_evs.append([dm_pauli_sum_expectation(dev, obs, qmap) for obs in pslist])
         return swept_evs
+
+
+def dm_pauli_sum_expectation(dev: DeviceState, pauli_sum, qubit_map) -> float:
+    """sum_k c_k tr(rho P_k) (ops/linear_combinations.py expectation_from_density_matrix:
+    the real part of each term, as ops/pauli_string.py:732 returns)."""
+    from cirq_b200.sv_simulator import pauli_masks
+
+    n = dev.n_bits // 2
+    total = 0.0
+    for ps in pauli_sum:
+        if abs(complex(ps.coefficient).imag) > 0.0001:
+            raise NotImplementedError(
+                'Cannot compute expectation value of a non-Hermitian '
+                f'PauliString <{ps}>. Coefficient must be real.'
+            )
+        x, z = pauli_masks(ps, qubit_map, n)
+        total += complex(ps.coefficient).real * dev.dm_pauli_expectation(x, z).real
+    return total

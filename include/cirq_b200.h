@@ -207,6 +207,13 @@ int b2q_probs_marginal(const double* probs_dev, int n_qubits, const int* bits, i
                        double* out_dev, void* stream);
 /* *out = Re trace(rho). */
 int b2q_dm_trace(const void* rho, int dtype, int n_qubits, double* out, void* stream);
+/* tr(rho P) for a Pauli string given as x_mask/z_mask over the n_qubits bit
+ * positions (same convention as b2q_sv_pauli_expectation); reads 2^n entries of
+ * rho.  Replaces ops/pauli_string.py:734-770
+ * (_expectation_from_density_matrix_no_validation), which
+ * sim/density_matrix_simulator.py:204-235 evaluates on a host copy of rho. */
+int b2q_dm_pauli_expectation(const void* rho, int dtype, int n_qubits, uint64_t x_mask,
+                             uint64_t z_mask, double* out_re_im, void* stream);
 /* Zeroes rows and columns whose measured bits differ from `values`, divides
  * by prob: sim/density_matrix_utils.py:167-180. */
 int b2q_dm_collapse(void* rho, int dtype, int n_qubits, const int* bits, const int* values, int m,

@@ -327,3 +327,15 @@ def reduced_density_matrix(state: np.ndarray, n_qubits: int, bits) -> np.ndarray
     rest = [a for a in range(n_qubits) if a not in axes]
     mat = np.transpose(psi, axes + rest).reshape(1 << m, -1)
     return mat @ mat.conj().T
+
+
+def dm_pauli_expectation(rho: np.ndarray, n_qubits: int, x_mask: int, z_mask: int) -> complex:
+    """tr(rho P) with P given by bit masks (Y = both), rho flat (row bits above
+    column bits): cirq-core/cirq/ops/pauli_string.py:734-770 in index form,
+    P|i> = i^{#Y} (-1)^{popcount(i & z)} |i ^ x>."""
+    d = 1 << n_qubits
+    m = np.asarray(rho, dtype=np.complex128).reshape(d, d)
+    i = np.arange(d, dtype=np.int64)
+    sign = 1 - 2 * (np.array([bin(int(v) & z_mask).count('1') for v in i]) & 1)
+    ny = bin(x_mask & z_mask).count('1')
+    return complex((1j ** ny) * np.sum(m[i, i ^ x_mask] * sign))

@@ -186,6 +186,9 @@ class OracleDeviceState:
     def dm_diagonal_device(self):
         return _ft(orc.dm_diagonal(self.array, self.n_bits // 2))
 
+    def dm_pauli_expectation(self, x_mask, z_mask):
+        return orc.dm_pauli_expectation(self.array, self.n_bits // 2, x_mask, z_mask)
+
     def dm_trace(self):
         return float(orc.dm_diagonal(self.array, self.n_bits // 2).sum())
 

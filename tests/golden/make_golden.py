@@ -288,6 +288,32 @@ def golden_trajectory_ops():
     return case
 
 
+def golden_dm_pauli():
+    """ops/pauli_string.py:657-770 expectation_from_density_matrix on random
+    (valid) density matrices."""
+    rng = np.random.RandomState(17)
+    out = {}
+    case = 0
+    paulis = [cirq.I, cirq.X, cirq.Y, cirq.Z]
+    for n in (1, 2, 4, 6):
+        qubits = cirq.LineQubit.range(n)
+        a = rand_matrix(rng, n)
+        rho = a @ a.conj().T
+        rho /= np.trace(rho)
+        for _ in range(6):
+            codes = rng.randint(0, 4, size=n)
+            ps = cirq.PauliString({q: paulis[c] for q, c in zip(qubits, codes) if c != 0})
+            val = ps.expectation_from_density_matrix(rho, {q: i for i, q in enumerate(qubits)})
+            out[f'c{case}_rho'] = rho
+            out[f'c{case}_n'] = np.array(n)
+            out[f'c{case}_codes'] = codes  # per axis: 0 I, 1 X, 2 Y, 3 Z
+            out[f'c{case}_value'] = np.array(val)
+            case += 1
+    out['num_cases'] = np.array(case)
+    np.savez_compressed(os.path.join(HERE, 'dm_pauli_expectation.npz'), **out)
+    return case
+
+
 if __name__ == '__main__':
     print('cirq', cirq.__version__, cirq.__file__)
     print('targeted_left_multiply cases:', golden_targeted_left_multiply())
@@ -298,3 +324,4 @@ if __name__ == '__main__':
     print('reference test vectors:', golden_reference_test_vectors())
     print('reduced density matrix cases:', golden_reduced_density_matrix())
     print('trajectory op cases:', golden_trajectory_ops())
+    print('dm pauli cases:', golden_dm_pauli())

@@ -180,3 +180,24 @@ def test_trajectory_ops_match_reference():
         ])
         got = orc.bsv_collapse(states.reshape(-1), n, bits, results, 1.0 / np.sqrt(probs)).reshape(B, -1)
         np.testing.assert_allclose(got, g[f'c{c}_collapsed'].reshape(B, -1), atol=1e-12)
+
+
+def _masks(codes, n):
+    x = z = 0
+    for axis, code in enumerate(codes):
+        b = n - 1 - axis
+        if code in (1, 2):
+            x |= 1 << b
+        if code in (2, 3):
+            z |= 1 << b
+    return x, z
+
+
+def test_dm_pauli_expectation_matches_reference():
+    g = load_golden('dm_pauli_expectation.npz')
+    for c in range(int(g['num_cases'])):
+        n = int(g[f'c{c}_n'])
+        x, z = _masks(g[f'c{c}_codes'], n)
+        val = orc.dm_pauli_expectation(g[f'c{c}_rho'].reshape(-1), n, x, z)
+        np.testing.assert_allclose(val.real, float(g[f'c{c}_value']), atol=1e-12)
+        assert abs(val.imag) < 1e-12
