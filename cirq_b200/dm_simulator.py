@@ -477,11 +477,18 @@ class B200DensityMatrixSimulator(
                 'permit_terminal_measurements=True.'
             )
         swept_evs = []
-        qubit_order = ops.QubitOrder.as_qubit_order(qubit_order)
-        qmap = {q: i for i, q in enumerate(qubit_order.order_for(program.all_qubits()))}
         if not isinstance(observables, list):
             observables = [observables]
         pslist = [ops.PauliSum.wrap(pslike) for pslike in observables]
+        if self._sweep_batch and initial_state is None and qubit_order is ops.QubitOrder.DEFAULT:
+            from cirq_b200 import sweeps
+
+            batched = sweeps.expectation_sweep_batched(
+                self, 'dm', program, pslist, params, DeviceState, dm_pauli_sum_expectation)
+            if batched is not None:
+                return batched
+        qubit_order = ops.QubitOrder.as_qubit_order(qubit_order)
+        qmap = {q: i for i, q in enumerate(qubit_order.order_for(program.all_qubits()))}
         for param_resolver in study.to_resolvers(params):
             result = self.simulate(
                 program, param_resolver, qubit_order=qubit_order, initial_state=initial_state

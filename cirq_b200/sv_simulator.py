@@ -874,11 +874,19 @@ class B200Simulator(
                 'skew expectation values. If this is intentional, set '
                 'permit_terminal_measurements=True.'
             )
-        qubit_order = ops.QubitOrder.as_qubit_order(qubit_order)
-        qmap = {q: i for i, q in enumerate(qubit_order.order_for(program.all_qubits()))}
         if not isinstance(observables, list):
             observables = [observables]
         pslist = [ops.PauliSum.wrap(pslike) for pslike in observables]
+        if self._sweep_batch and initial_state is None and qubit_order is ops.QubitOrder.DEFAULT:
+            from cirq_b200 import sweeps
+
+            batched = sweeps.expectation_sweep_batched(
+                self, 'sv', program, pslist, params, DeviceState, pauli_sum_expectation)
+            if batched is not None:
+                yield from batched
+                return
+        qubit_order = ops.QubitOrder.as_qubit_order(qubit_order)
+        qmap = {q: i for i, q in enumerate(qubit_order.order_for(program.all_qubits()))}
         for result in self.simulate_sweep_iter(
             program, params, qubit_order=qubit_order, initial_state=initial_state
         ):

@@ -175,9 +175,11 @@ class SweepPlan:
         return True
 
 
-def plan_sweep(simulator, kind: str, program, resolvers) -> SweepPlan | None:
+def plan_sweep(simulator, kind: str, program, resolvers, sampled: bool = True) -> SweepPlan | None:
     """The batched schedule of `program` for `resolvers`, or None when the sweep
-    has to take the per-resolver loop."""
+    has to take the per-resolver loop.  `sampled`: a run_sweep (the circuit must
+    end in measurements, which are sampled); otherwise a final-state sweep (the
+    circuit must not measure at all)."""
     noise = simulator.noise
     if noise is not devices.NO_NOISE and not isinstance(noise, devices.ConstantQubitNoiseModel):
         return None
@@ -201,7 +203,10 @@ def plan_sweep(simulator, kind: str, program, resolvers) -> SweepPlan | None:
     prefix, suffix = split_into_matching_protocol_then_general(
         program, lambda op: not protocols.measurement_keys_touched(op))
     suffix_ops = list(suffix.all_operations())
-    if not suffix_ops or not all(isinstance(op.gate, ops.MeasurementGate) for op in suffix_ops):
+    if sampled:
+        if not suffix_ops or not all(isinstance(op.gate, ops.MeasurementGate) for op in suffix_ops):
+            return None
+    elif suffix_ops or program.has_measurements():
         return None
     system = sorted(program.all_qubits())
     for part, skip_measurements in ((prefix, False), (suffix, True)):
@@ -217,8 +222,9 @@ def plan_sweep(simulator, kind: str, program, resolvers) -> SweepPlan | None:
     return plan
 
 
-def execute_sweep(simulator, plan: SweepPlan, repetitions: int, device_state_cls, info: dict | None = None):
-    """Runs a SweepPlan; yields one {key: records} dict per resolver, in order."""
+def evolve_sweep(simulator, plan: SweepPlan, device_state_cls, info: dict | None = None):
+    """Runs the gates of a SweepPlan; returns the batch array (state of resolver
+    i at offset i << plan.state_bits)."""
     P = len(plan.resolvers)
     b = (P - 1).bit_length()
     count = 1 << b
@@ -254,9 +260,21 @@ def execute_sweep(simulator, plan: SweepPlan, repetitions: int, device_state_cls
     if info is not None:
         info.update(path='batched sweep', resolvers=P, batch_bits=b, passes=passes,
                     select_passes=sum(1 for it in plan.items if it[0] == 'select'))
-    for i in range(P):
-        piece = dev.slice_copy(i << sb, sb) if b else dev
-        sim_state = simulator._state_from_device(piece, plan.qubits)
+    return dev
+
+
+def resolver_state(dev, plan: SweepPlan, i: int):
+    """The state of resolver i inside the batch array, as a device state of its own."""
+    if dev.n_bits == plan.state_bits:
+        return dev
+    return dev.slice_copy(i << plan.state_bits, plan.state_bits)
+
+
+def execute_sweep(simulator, plan: SweepPlan, repetitions: int, device_state_cls, info: dict | None = None):
+    """Runs a SweepPlan; yields one {key: records} dict per resolver, in order."""
+    dev = evolve_sweep(simulator, plan, device_state_cls, info)
+    for i in range(len(plan.resolvers)):
+        sim_state = simulator._state_from_device(resolver_state(dev, plan, i), plan.qubits)
         step = simulator._create_step_result(sim_state)
         yield step.sample_measurement_ops(
             plan.measurement_ops, repetitions, seed=simulator._prng, _allow_repeated=True)
@@ -279,3 +297,27 @@ def run_sweep_batched(simulator, kind: str, program, params, repetitions: int, d
             yield study.ResultDict(params=r, records=records)
 
     return results()
+
+
+def expectation_sweep_batched(simulator, kind: str, program, pauli_sums, params, device_state_cls,
+                              expectation):
+    """[[<O_j> for j] for each resolver] with all resolvers evolved as one device
+    array, or None if the sweep cannot be batched.  `expectation(dev, pauli_sum,
+    qubit_map)` evaluates one observable on one resolver's device state (the
+    simulators' own reduction kernels).  Replaces the per-resolver loops of
+    sim/sparse_simulator.py:193-218 and sim/density_matrix_simulator.py:204-235."""
+    resolvers = list(study.to_resolvers(params))
+    plan = plan_sweep(simulator, kind, program, resolvers, sampled=False)
+    if plan is None:
+        return None
+    qmap = {q: i for i, q in enumerate(plan.qubits)}
+    if any(q not in qmap for obs in pauli_sums for q in obs.qubits):
+        return None
+    info: dict = {}
+    dev = evolve_sweep(simulator, plan, device_state_cls, info)
+    simulator.last_run_info = info
+    out = []
+    for i in range(len(resolvers)):
+        piece = resolver_state(dev, plan, i)
+        out.append([expectation(piece, obs, qmap) for obs in pauli_sums])
+    return out

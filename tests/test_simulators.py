@@ -672,6 +672,32 @@ def test_batched_sweep_density_matrix_matches_sequential(cirq, DM, noise_p):
         np.testing.assert_array_equal(g.measurements['m'], w.measurements['m'])
 
 
+def test_batched_sweep_expectation_values(cirq, SV, DM):
+    """simulate_expectation_values_sweep with sweep_batch=True equals the
+    reference's per-resolver loop (sim/sparse_simulator.py:193-218,
+    sim/density_matrix_simulator.py:204-235)."""
+    c, q, sweep = _qaoa_like(cirq, 6, 2)
+    c = c[:-1]  # no measurement
+    obs = [cirq.Z(q[0]) * cirq.Z(q[3]), 0.5 * cirq.X(q[1]) - 1.5 * cirq.Y(q[2]) * cirq.Z(q[5]),
+           cirq.PauliString()]
+    want = cirq.Simulator(dtype=np.complex128).simulate_expectation_values_sweep(c, obs, sweep)
+    sim = SV(dtype=np.complex128, sweep_batch=True)
+    got = sim.simulate_expectation_values_sweep(c, obs, sweep)
+    assert sim.last_run_info['path'] == 'batched sweep'
+    np.testing.assert_allclose(got, want, atol=1e-10)
+    noise = cirq.depolarize(0.03)
+    want = cirq.DensityMatrixSimulator(dtype=np.complex128, noise=noise).simulate_expectation_values_sweep(
+        c, obs, sweep)
+    dsim = DM(dtype=np.complex128, noise=noise, sweep_batch=True)
+    got = dsim.simulate_expectation_values_sweep(c, obs, sweep)
+    assert dsim.last_run_info['path'] == 'batched sweep'
+    np.testing.assert_allclose(got, want, atol=1e-10)
+    # a measured circuit takes the reference loop
+    c2 = c + cirq.Circuit(cirq.measure(q[0], key='m'))
+    with pytest.raises(ValueError, match='terminal measurements'):
+        SV(sweep_batch=True).simulate_expectation_values_sweep(c2, obs, sweep)
+
+
 def test_mux_entry_points_match_reference(cirq, SV, DM):
     """cirq_b200.sample / final_state_vector / final_density_matrix mirror
     cirq.sample / ... (sim/mux.py) with the same signatures."""

@@ -1,6 +1,8 @@
-python tools/microbench.py --only diag,k5_high,k2_high --dense --reps 20 --out gpurun_out/mb_r1z_diag.json 2>&1 | grep -E "diag|k5_high|k2_high|torch_copy"
-python tools/microbench.py --only diag --dense --reps 20 --dtype c128 --n 29 2>&1 | grep -E "diag|torch_copy"
-python bench.py --workload qft34 --no-cpu-baseline --steps 3 > gpurun_out/bench_r1z_qft34.json 2> gpurun_out/bench_r1z_qft34.err; python -c "
-import json; d=json.load(open('gpurun_out/bench_r1z_qft34.json')); print('qft34', d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['passes_per_step'], d['roofline']['frac'], d['roofline']['kernel'], {k:(v['launches_per_step'], round(v['ms_per_launch'],3)) for k,v in d['roofline']['kernels'].items()})"
-ncu --set full --clock-control none --import-source on -k regex:sv_apply_diag_smem -c 2 -o gpurun_out/prof_diag_r1z python tools/microbench.py --only diag13_mixed --dense --reps 1 > gpurun_out/ncu_diag_r1z.log 2>&1; tail -2 gpurun_out/ncu_diag_r1z.log | cut -c1-200
-ncu --set full --clock-control none --import-source on -k regex:bsv_ --launch-skip 12 -c 16 -o gpurun_out/prof_bsv_r1z python tools/traj_bench.py --qubits 16 --reps 4096 --batch 4096 --loop-reps 1 --ref-reps 0 > gpurun_out/ncu_bsv_r1z.log 2>&1; tail -2 gpurun_out/ncu_bsv_r1z.log | cut -c1-200
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python tools/microbench.py --only diag --dense --reps 20 2>&1 | grep -E "diag|torch_copy"
+python bench.py > gpurun_out/bench_r1A.json 2> gpurun_out/bench_r1A.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_r1A.json')); print('rqc30', d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['kernel'], {k:(v['launches_per_step'], round(v['ms_per_launch'],3)) for k,v in d['roofline']['kernels'].items()})"
+python bench.py --workload qft34 --no-cpu-baseline --steps 3 > gpurun_out/bench_r1A_qft34.json 2> gpurun_out/bench_r1A_qft34.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_r1A_qft34.json')); print('qft34', d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['passes_per_step'], d['roofline']['frac'], d['roofline']['kernel'], {k:(v['launches_per_step'], round(v['ms_per_launch'],3)) for k,v in d['roofline']['kernels'].items()})"
+( time python bench.py --impl reference --steps 1 --warmup 0 ) 2>&1 | tail -5 | cut -c1-900

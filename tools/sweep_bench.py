@@ -26,6 +26,8 @@ def main():
     ap.add_argument('--reps', type=int, default=1000)
     ap.add_argument('--seq-resolvers', type=int, default=16)
     ap.add_argument('--ref-resolvers', type=int, default=2)
+    ap.add_argument('--expect', action='store_true',
+                    help='simulate_expectation_values_sweep of the max-cut cost instead of run_sweep')
     ap.add_argument('--out', default='')
     args = ap.parse_args()
     import torch
@@ -54,6 +56,39 @@ def main():
 
     rep = dict(kind=args.kind, n_qubits=args.qubits, resolvers=args.resolvers, repetitions=args.reps,
                ops=len(list(circuit.all_operations())))
+    if args.expect:
+        # the QAOA cost: sum over the graph's edges of Z_i Z_j, on the circuit without its measurement
+        body = cirq.Circuit(op for op in circuit.all_operations() if not cirq.is_measurement(op))
+        edges = {tuple(sorted(op.qubits)) for op in body.all_operations() if len(op.qubits) == 2}
+        cost = sum(cirq.Z(a) * cirq.Z(b) for a, b in sorted(edges))
+        rep['mode'] = f'simulate_expectation_values_sweep, {len(edges)} ZZ terms'
+        sim = make(sweep_batch=True)
+        sim.simulate_expectation_values_sweep(body, [cost], resolvers[:4])
+        got, dt = timed(lambda: sim.simulate_expectation_values_sweep(body, [cost], resolvers))
+        assert sim.last_run_info.get('path') == 'batched sweep', sim.last_run_info
+        rep['batched'] = dict(seconds=dt, resolvers_per_s=len(resolvers) / dt, **sim.last_run_info)
+        seq = make()
+        seq.simulate_expectation_values_sweep(body, [cost], resolvers[:2])
+        want, dt = timed(lambda: seq.simulate_expectation_values_sweep(body, [cost], resolvers[: args.seq_resolvers]))
+        rep['sequential'] = dict(resolvers=args.seq_resolvers, seconds=dt, resolvers_per_s=args.seq_resolvers / dt)
+        rep['max_abs_diff_batched_vs_sequential'] = float(
+            np.max(np.abs(np.asarray(got[: args.seq_resolvers]) - np.asarray(want))))
+        if args.ref_resolvers:
+            t0 = time.perf_counter()
+            ref_vals = ref.simulate_expectation_values_sweep(body, [cost], resolvers[: args.ref_resolvers])
+            dt = time.perf_counter() - t0
+            rep['reference_cpu'] = dict(resolvers=args.ref_resolvers, seconds=dt,
+                                        resolvers_per_s=args.ref_resolvers / dt, cores=1, host_cores=os.cpu_count())
+            rep['max_abs_diff_vs_reference'] = float(
+                np.max(np.abs(np.asarray(got[: args.ref_resolvers]) - np.asarray(ref_vals))))
+            rep['speedup_vs_reference_cpu'] = rep['batched']['resolvers_per_s'] / rep['reference_cpu']['resolvers_per_s']
+        rep['speedup_vs_sequential'] = rep['batched']['resolvers_per_s'] / rep['sequential']['resolvers_per_s']
+        line = json.dumps(rep)
+        print(line)
+        if args.out:
+            with open(args.out, 'w') as f:
+                f.write(line + '\n')
+        return
     sim = make(sweep_batch=True)
     sim.run_sweep(circuit, resolvers[:4], repetitions=10)  # warm-up
     res, dt = timed(lambda: sim.run_sweep(circuit, resolvers, repetitions=args.reps))
