@@ -344,6 +344,14 @@ class ShardedStateVector:
     def _rank_bit(self, phys_bit: int) -> int:
         return (self.rank >> (phys_bit - self.n_local)) & 1
 
+    def rename_bits(self, permutation: dict) -> None:
+        """Applies a SWAP relabelling from the scheduler: the content of logical
+        bit w now lives where logical bit permutation[w] used to be."""
+        if permutation:
+            old = list(self.phys)
+            for w, now in permutation.items():
+                self.phys[w] = old[now]
+
     def swap_global_local(self, global_phys: int, local_phys: int, fused_block=None) -> None:
         """Exchanges physical bits (global, local) of the index: data moves, the
         logical->physical map follows.  `fused_block` = (matrix, local bits) is
@@ -550,9 +558,12 @@ def plan_sharded(n_qubits: int, gates, dtype, max_fused_qubits, n_local: int):
         counter = 0
 
     gates = list(gates)
+    perm: dict = {}  # SWAP gates of the sharded part: wires renamed, no data moved
     if n_local > LAZY_MAX_SHARD_BITS:
         return {'n': n_qubits, 'dtype': np.dtype(dtype), 'ops': [], 'components': None,
-                'blocks': fuse_gates(gates, max_fused_qubits, dtype, n_local, diagonal_blocks=True)}
+                'blocks': fuse_gates(gates, max_fused_qubits, dtype, n_local, diagonal_blocks=True,
+                                     permutation=perm),
+                'permutation': perm}
     ex = SplitExecutor(n_qubits, dtype, max_fused_qubits, Rec, max_component_bits=min(n_local, 30))
     done = len(gates)
     for i, (m, b) in enumerate(gates):
@@ -561,8 +572,9 @@ def plan_sharded(n_qubits: int, gates, dtype, max_fused_qubits, n_local: int):
             break
     comps = [(dev.ident, bits) for dev, bits in ex.components()]
     return {'n': n_qubits, 'dtype': np.dtype(dtype), 'ops': Rec.ops, 'components': comps,
-            'blocks': fuse_gates(gates[done:], max_fused_qubits, dtype, n_local, diagonal_blocks=True),
-            'prefix_gates': done}
+            'blocks': fuse_gates(gates[done:], max_fused_qubits, dtype, n_local, diagonal_blocks=True,
+                                 permutation=perm),
+            'permutation': perm, 'prefix_gates': done}
 
 
 def execute_sharded_plan(plan, sv: 'ShardedStateVector', device_state_cls=None) -> None:
@@ -577,6 +589,7 @@ def execute_sharded_plan(plan, sv: 'ShardedStateVector', device_state_cls=None) 
         sv.load_product([(live[ident], bits) for ident, bits in plan['components']])
         del live
     sv.apply_blocks(plan['blocks'])
+    sv.rename_bits(plan.get('permutation') or {})
 
 
 class B200ShardedSimulator:
@@ -645,7 +658,10 @@ class B200ShardedSimulator:
         gates, _ = self._gates(circuit, qubits)
         if initial_state != 0:
             sv = ShardedStateVector(len(qubits), self.dtype, group=self.group, initial_index=initial_state)
-            sv.apply_blocks(fuse_gates(gates, self.max_fused, self.dtype, sv.n_local, diagonal_blocks=True))
+            perm: dict = {}
+            sv.apply_blocks(fuse_gates(gates, self.max_fused, self.dtype, sv.n_local, diagonal_blocks=True,
+                                       permutation=perm))
+            sv.rename_bits(perm)
             return sv
         sv = ShardedStateVector(len(qubits), self.dtype, group=self.group, initial_index=None)
         execute_sharded_plan(plan_sharded(sv.n, gates, self.dtype, self.max_fused, sv.n_local), sv)

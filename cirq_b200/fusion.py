@@ -446,13 +446,22 @@ def fuser_for(dtype, max_qubits: int | None = None, n_bits: int | None = None,
 
 
 def fuse_gates(gates, max_qubits: int = 4, dtype=None, n_bits: int | None = None,
-               diagonal_blocks: bool = False):
+               diagonal_blocks: bool = False, permutation: dict | None = None):
     """Convenience wrapper: [(matrix, wires)] -> fused [(matrix, wires)].  With
     `dtype` the kernel-matched policy of `fuser_for` is used; `diagonal_blocks`
-    adds diagonal blocks (1-D matrices) without SWAP relabelling."""
+    adds diagonal blocks (1-D matrices).  With a dict as `permutation`, SWAP gates
+    are relabelled instead of executed and the dict receives {wire: wire that
+    holds its content afterwards} for the caller to rename its wires."""
     f = GateFuser(max_qubits) if dtype is None else fuser_for(dtype, max_qubits, n_bits)
     if diagonal_blocks and dtype is not None:
         f.diag_max = DIAG_MAX_WIRES[np.dtype(dtype)]
+    if permutation is not None:
+        f.relabel_swaps = True
+        for m, w in gates:
+            f.add(m, w)
+        blocks = f.blocks(restore=False)
+        permutation.update(f.take_permutation())
+        return blocks
     for m, w in gates:
         f.add(m, w)
     return f.blocks()

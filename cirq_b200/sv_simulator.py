@@ -762,6 +762,9 @@ class B200Simulator(
         ``trajectory_batch`` asks for it and every suffix operation can be
         batched; anything else takes the reference's loop unchanged."""
         self.last_run_info = {'path': 'reference loop'}
+        fast = self._run_unitary_then_measure(circuit, param_resolver, repetitions)
+        if fast is not None:
+            return fast
         if self._trajectory_batch <= 1 or repetitions <= 1:
             return super()._run(circuit, param_resolver, repetitions)
         from cirq.sim.simulator import check_all_resolved, split_into_matching_protocol_then_general
@@ -798,6 +801,50 @@ class B200Simulator(
         info['path'] = 'batched trajectories'
         self.last_run_info = info
         return out
+
+    def _run_unitary_then_measure(self, circuit, param_resolver, repetitions: int):
+        """The most common shape — a noise-free circuit of unitary gates whose last
+        moments are measurements — without the reference's generic prefix/suffix
+        split (sim/simulator.py:952-985: ~15 ms of Python on a 900-operation
+        circuit before the GPU gets its first gate).  For this shape the split is
+        simply "moments before the first measurement | the rest", and the rest of
+        `_run` (sim/simulator_base.py:229-244) follows unchanged.  Returns None for
+        any other shape."""
+        from cirq import devices
+
+        if self.noise is not devices.NO_NOISE:
+            return None
+        if param_resolver and protocols.is_parameterized(circuit):
+            return None  # sweeps over symbols: the generic path resolves them
+        first = None
+        for i, moment in enumerate(circuit):
+            measuring = [isinstance(op.gate, ops.MeasurementGate) for op in moment]
+            if first is None:
+                if any(measuring):
+                    if not all(measuring):
+                        return None
+                    first = i
+                else:
+                    for op in moment:
+                        if type(op) is not ops.GateOperation or cached_unitary(op) is None:
+                            return None
+            elif not all(measuring):
+                return None
+        if first is None:
+            return None
+        qubits = tuple(sorted(circuit.all_qubits()))
+        sim_state = self._create_simulation_state(0, qubits)
+        step_result = None
+        for step_result in self._core_iterator(circuit=circuit[:first], sim_state=sim_state):
+            pass
+        suffix = circuit[first:]
+        for step_result in self._core_iterator(
+            circuit=suffix, sim_state=sim_state, all_measurements_are_terminal=True
+        ):
+            pass
+        return step_result.sample_measurement_ops(
+            list(suffix.all_operations()), repetitions, seed=self._prng, _allow_repeated=True
+        )
 
     def _create_partial_simulation_state(self, initial_state, qubits, classical_data):
         if isinstance(initial_state, B200StateVectorSimulationState):

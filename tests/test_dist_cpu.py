@@ -88,14 +88,19 @@ def _worker(rank, world, port, n, seed, max_fused, out_dir):
             elif kind == 1 and k == 2:
                 m = np.eye(4, dtype=complex)
                 m[2:, 2:] = unitary(1)  # controlled-U: diagonal in its control
+            elif kind == 2 and k == 2 and rng.randint(2):
+                m = np.eye(4, dtype=complex)[[0, 2, 1, 3]]  # SWAP: relabelled, never exchanged
             else:
                 m = unitary(k)
             gates.append((m, wires))
         g = world.bit_length() - 1
         sv = ShardedStateVector(n, np.complex128, backend=GlooShardBackend(n - g, np.complex128),
                                 initial_index=3)
-        blocks = fuse_gates(gates, max_fused)
+        # the production schedule (dist.plan_sharded): diagonal blocks + relabelled SWAPs
+        perm = {}
+        blocks = fuse_gates(gates, max_fused, np.complex128, n - g, diagonal_blocks=True, permutation=perm)
         sv.apply_blocks(blocks)
+        sv.rename_bits(perm)
         got = sv.gather_state()
         want = orc.run_gate_list(n, gates, dtype=np.complex128, initial=3)
         err = float(np.max(np.abs(got - want)))
@@ -161,9 +166,15 @@ def _lazy_worker(rank, world, port, n, seed, pattern, out_dir):
             for q in range(0, n - 1, 2):
                 gates.append((unitary(2), [q, q + 1]))
         else:
-            for _ in range(50):
+            for i in range(50):
                 k = int(rng.randint(1, 3))
-                gates.append((unitary(k), rng.permutation(n)[:k].tolist()))
+                wires = rng.permutation(n)[:k].tolist()
+                if k == 2 and i % 5 == 0:
+                    gates.append((np.eye(4, dtype=complex)[[0, 2, 1, 3]], wires))  # SWAP
+                elif k == 2 and i % 5 == 1:
+                    gates.append((np.diag(np.exp(1j * rng.standard_normal(4))), wires))
+                else:
+                    gates.append((unitary(k), wires))
         g = world.bit_length() - 1
         sv = ShardedStateVector(n, np.complex128, backend=GlooShardBackend(n - g, np.complex128),
                                 initial_index=None)

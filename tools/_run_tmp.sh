@@ -1,8 +1,3 @@
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-python tools/microbench.py --only diag --dense --reps 20 2>&1 | grep -E "diag|torch_copy"
-python bench.py > gpurun_out/bench_r1A.json 2> gpurun_out/bench_r1A.err; python -c "
-import json; d=json.load(open('gpurun_out/bench_r1A.json')); print('rqc30', d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['kernel'], {k:(v['launches_per_step'], round(v['ms_per_launch'],3)) for k,v in d['roofline']['kernels'].items()})"
-python bench.py --workload qft34 --no-cpu-baseline --steps 3 > gpurun_out/bench_r1A_qft34.json 2> gpurun_out/bench_r1A_qft34.err; python -c "
-import json; d=json.load(open('gpurun_out/bench_r1A_qft34.json')); print('qft34', d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['passes_per_step'], d['roofline']['frac'], d['roofline']['kernel'], {k:(v['launches_per_step'], round(v['ms_per_launch'],3)) for k,v in d['roofline']['kernels'].items()})"
-( time python bench.py --impl reference --steps 1 --warmup 0 ) 2>&1 | tail -5 | cut -c1-900
+python tools/e2e_profile.py --top 45 2>&1 | cut -c1-170 | tail -70
+python tools/sweep_bench.py --kind sv --qubits 16 --resolvers 256 --expect --out gpurun_out/sweep_r1B_sv16_expect.json 2>&1 | tail -1 | cut -c1-1200
+python tools/sweep_bench.py --kind dm --qubits 10 --resolvers 256 --expect --ref-resolvers 1 --out gpurun_out/sweep_r1B_dm10_expect.json 2>&1 | tail -1 | cut -c1-1200
