@@ -1,4 +1,4 @@
-timeout 900 python -m pytest tests/test_dist_gpu.py -m gpu -x -q 2>&1 | tail -5
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/dist_check.py 2>&1 | grep -E "diagonal blocks|lazy growth|DIST CHECK|swap global" | head -12
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_r1B_2gpu.json 2> gpurun_out/bench_r1B_2gpu.err; tail -1 gpurun_out/bench_r1B_2gpu.json | python -c "
-import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('2gpu', d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['passes_per_step'], d['config']['qubit_swaps_per_step'], d['config'].get('swaps_fused_with_a_gate_pass_per_step'))"
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python bench.py > gpurun_out/bench_r1C.json 2> gpurun_out/bench_r1C.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_r1C.json')); print('rqc30', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e']['ms_per_step'], d['roofline']['frac'], d['roofline']['kernel'], {k:(v['launches_per_step'], round(v['ms_per_launch'],3)) for k,v in d['roofline']['kernels'].items()})"
+python tools/e2e_profile.py --top 12 2>&1 | grep "e2e step"
