@@ -349,6 +349,15 @@ class DeviceState:
 
     # ---- batched trajectories: 2^(n_bits - n_qubits) states of n_qubits back to back ----
 
+    @staticmethod
+    def _upload_async(array: np.ndarray):
+        """Host array -> device tensor without waiting for the GPU: staged in
+        pinned memory (torch's caching host allocator keeps it alive until the copy
+        has run) and copied stream-ordered.  A pageable `.to('cuda')` would block
+        the host until every queued pass has finished, once per stochastic layer."""
+        torch = _torch()
+        return torch.from_numpy(np.ascontiguousarray(array)).pin_memory().to('cuda', non_blocking=True)
+
     def bsv_apply_select(self, n_qubits: int, matrices: np.ndarray, bits: Sequence[int],
                          choice: np.ndarray, scale: np.ndarray | None = None, skip: int = -1) -> None:
         """psi_t <- scale[t] * matrices[choice[t]] psi_t on `bits` for every
@@ -361,10 +370,10 @@ class DeviceState:
         batch = self.n_bits - n_qubits
         c = np.ascontiguousarray(np.asarray(choice, dtype=np.int32).reshape(-1))
         assert c.size == 1 << batch
-        c_dev = torch.from_numpy(c).to('cuda')
+        c_dev = self._upload_async(c)
         s_dev = None
         if scale is not None:
-            s_dev = torch.from_numpy(np.ascontiguousarray(np.asarray(scale, dtype=np.float64).reshape(-1))).to('cuda')
+            s_dev = self._upload_async(np.asarray(scale, dtype=np.float64).reshape(-1))
         check(
             self._lib.b2q_bsv_apply_select(
                 self.ptr, self.code, n_qubits, batch, m.ctypes.data, count, _lib.int_array(list(bits)), k,
@@ -383,7 +392,7 @@ class DeviceState:
         assert m.shape == (count, 2, 2)
         batch = self.n_bits - n_qubits
         c = np.ascontiguousarray(np.asarray(choices, dtype=np.int32).reshape(len(bits), 1 << batch))
-        c_dev = torch.from_numpy(c).to('cuda')
+        c_dev = self._upload_async(c)
         check(
             self._lib.b2q_bsv_apply_select_multi(
                 self.ptr, self.code, n_qubits, batch, m.ctypes.data, count, _lib.int_array(list(bits)),
@@ -419,8 +428,8 @@ class DeviceState:
         for i, b in enumerate(bits):
             mask |= 1 << int(b)
             pattern |= vals[:, i] << np.uint64(int(b))
-        p_dev = torch.from_numpy(pattern.view(np.int64)).to('cuda')
-        s_dev = torch.from_numpy(np.ascontiguousarray(np.asarray(scale, dtype=np.float64).reshape(-1))).to('cuda')
+        p_dev = self._upload_async(pattern.view(np.int64))
+        s_dev = self._upload_async(np.asarray(scale, dtype=np.float64).reshape(-1))
         check(
             self._lib.b2q_bsv_collapse(
                 self.ptr, self.code, n_qubits, batch, ctypes.c_uint64(mask),

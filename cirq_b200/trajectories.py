@@ -146,18 +146,44 @@ class TrajectoryBatch:
     def mixture(self, probs: np.ndarray, unitaries: np.ndarray, bits: Sequence[int], skip: int) -> None:
         """sim/state_vector_simulation_state.py:183-203, all trajectories at once."""
         self.flush()
-        choice = self.prng.choice(len(probs), size=self.count, p=probs)
+        choice = self._draw(probs, (self.count,), skip)
         if skip >= 0 and np.all(choice == skip):
             return
         self.dev.bsv_apply_select(self.n, unitaries, bits, choice, None, skip)
         self.passes += 1
+
+    def _draw(self, probs: np.ndarray, shape: tuple, skip: int) -> np.ndarray:
+        """Independent draws from `probs` of the given shape.  Weak noise (the
+        identity, `skip`, takes most of the weight) is drawn sparsely: how many
+        draws are NOT the identity (binomial), where they are (a uniform subset),
+        and which operator each one is — the same joint distribution as one
+        categorical draw per entry, at a cost proportional to the number of hits."""
+        total = int(np.prod(shape))
+        if skip < 0 or probs[skip] < 0.75 or total < 1024:
+            return self.prng.choice(len(probs), size=shape, p=probs)
+        rest = np.delete(np.arange(len(probs)), skip)
+        p_rest = probs[rest]
+        weight = float(p_rest.sum())
+        out = np.full(total, skip, dtype=np.int64)
+        hits = int(self.prng.binomial(total, weight)) if weight > 0 else 0
+        if hits:
+            # a uniform `hits`-subset: the first `hits` distinct values of a stream of
+            # uniform integers (choice(..., replace=False) would permute all `total`)
+            where = np.zeros(0, dtype=np.int64)
+            while where.size < hits:
+                draws = np.concatenate([where, self.prng.randint(0, total, size=hits - where.size + 16)])
+                _, first = np.unique(draws, return_index=True)
+                where = draws[np.sort(first)]
+            where = where[:hits]
+            out[where] = rest[self.prng.choice(len(rest), size=hits, p=p_rest / weight)]
+        return out.reshape(shape)
 
     def mixture_layer(self, probs: np.ndarray, unitaries: np.ndarray, bits: Sequence[int], skip: int) -> None:
         """The same 1-qubit mixture on each of `bits` (a noise model's layer after a
         moment): all draws in one ``prng.choice`` call, all applications in one
         launch (``b2q_bsv_apply_select_multi``)."""
         self.flush()
-        choices = self.prng.choice(len(probs), size=(len(bits), self.count), p=probs)
+        choices = self._draw(probs, (len(bits), self.count), skip)
         if skip >= 0:
             hit = np.flatnonzero((choices != skip).any(axis=1))
             if hit.size == 0:
@@ -252,6 +278,11 @@ def run_plan(plan: list, psi0, n_qubits: int, repetitions: int, dtype, prng, max
     records: dict[str, list[list[np.ndarray]]] = {}
     done = 0
     batches = passes = 0
+    # nothing observes the state after the last measurement of a `run`: operations
+    # behind it (a noise model's layer after the measurement moment) are dropped
+    plan = list(plan)
+    while plan and plan[-1][0] != 'measure':
+        plan.pop()
     # measurements after which nothing else touches the state can be sampled, not collapsed
     last_non_measure = max((i for i, it in enumerate(plan) if it[0] != 'measure'), default=-1)
     seen_bits: set[int] = set()
