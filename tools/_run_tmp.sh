@@ -1,5 +1,4 @@
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29555 bench.py --gpus 8 --steps 3 --warmup 3 > gpurun_out/bench_r1D_8gpu.json 2> gpurun_out/bench_r1D_8gpu.err; tail -1 gpurun_out/bench_r1D_8gpu.json | python -c "
-import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('8gpu 33q', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['config']['passes_per_step'], d['config']['qubit_swaps_per_step'], d['config'].get('swaps_fused_with_a_gate_pass_per_step'))"
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29566 bench.py --gpus 8 --steps 2 --warmup 1 --workload rc_hbm > gpurun_out/bench_r1D_8gpu_37q.json 2> gpurun_out/bench_r1D_8gpu_37q.err; tail -1 gpurun_out/bench_r1D_8gpu_37q.json | python -c "
-import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('8gpu 37q', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['config']['passes_per_step'], d['config']['qubit_swaps_per_step'])"
-tail -3 gpurun_out/bench_r1D_8gpu_37q.err | cut -c1-300
+timeout 900 python -m pytest tests -m gpu -x -q -k "batched or trajector" 2>&1 | tail -3
+python tools/traj_bench.py --qubits 16 --depth 8 --reps 4096 --batch 4096 --out gpurun_out/traj_r1E_16q.json 2>&1 | tail -1 | cut -c1-700
+python tools/traj_bench.py --qubits 10 --depth 8 --reps 65536 --batch 65536 --loop-reps 128 --ref-reps 64 --out gpurun_out/traj_r1E_10q.json 2>&1 | tail -1 | cut -c1-500
+python tools/traj_bench.py --qubits 20 --depth 8 --reps 1024 --batch 1024 --loop-reps 32 --ref-reps 2 --out gpurun_out/traj_r1E_20q.json 2>&1 | tail -1 | cut -c1-500
