@@ -28,8 +28,6 @@ to batch) returns None and the caller falls back to the reference loop.
 """
 from __future__ import annotations
 
-from typing import Any, Sequence
-
 import numpy as np
 
 from cirq_b200._cirq_compat import import_cirq
@@ -37,7 +35,7 @@ from cirq_b200.fusion import fuser_for
 
 cirq = import_cirq()
 from cirq import devices, ops, protocols, study  # noqa: E402
-from cirq.sim.simulator import check_all_resolved, split_into_matching_protocol_then_general  # noqa: E402
+from cirq.sim.simulator import split_into_matching_protocol_then_general  # noqa: E402
 
 # largest batch array (state bits + resolver bits): 2^30 complex64 = 8.6 GB
 MAX_BATCH_ARRAY_BITS = 30

@@ -27,7 +27,7 @@ repetition), so seeded bit-for-bit equality with ``cirq.Simulator`` is given up
 """
 from __future__ import annotations
 
-from typing import Any, Sequence
+from typing import Sequence
 
 import numpy as np
 
