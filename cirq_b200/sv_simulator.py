@@ -766,6 +766,19 @@ class B200Simulator(
             initial_state=B200StateVector(dev, len(qubits), self._max_fused),
         )
 
+    def simulate_sweep_iter(self, program, params, qubit_order=ops.QubitOrder.DEFAULT, initial_state=None):
+        """``SimulatorBase.simulate_sweep_iter`` (sim/simulator_base.py:277-320); with
+        ``sweep_batch=True`` a measurement-free sweep from |0...0> in the default
+        qubit order advances all resolvers as one device array."""
+        if self._sweep_batch and initial_state is None and qubit_order is ops.QubitOrder.DEFAULT:
+            from cirq_b200 import sweeps
+
+            batched = sweeps.simulate_sweep_batched(self, 'sv', program, params, DeviceState)
+            if batched is not None:
+                yield from batched
+                return
+        yield from super().simulate_sweep_iter(program, params, qubit_order, initial_state)
+
     def run_sweep_iter(self, program, params, repetitions: int = 1):
         """``SimulatesSamples.run_sweep_iter`` (sim/simulator.py:62-94); with
         ``sweep_batch=True`` all resolvers advance together as one device array

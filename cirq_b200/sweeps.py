@@ -319,3 +319,25 @@ def expectation_sweep_batched(simulator, kind: str, program, pauli_sums, params,
         piece = resolver_state(dev, plan, i)
         out.append([expectation(piece, obs, qmap) for obs in pauli_sums])
     return out
+
+
+def simulate_sweep_batched(simulator, kind: str, program, params, device_state_cls):
+    """Iterator of trial results (one per resolver, final state = that resolver's
+    slice of the batch array), or None if the sweep cannot be batched.  Replaces
+    the per-resolver loop of sim/simulator.py:585-606 for measurement-free
+    circuits from |0...0> in the default qubit order."""
+    resolvers = list(study.to_resolvers(params))
+    plan = plan_sweep(simulator, kind, program, resolvers, sampled=False)
+    if plan is None:
+        return None
+
+    def results():
+        info: dict = {}
+        dev = evolve_sweep(simulator, plan, device_state_cls, info)
+        simulator.last_run_info = info
+        for i, r in enumerate(resolvers):
+            sim_state = simulator._state_from_device(resolver_state(dev, plan, i), plan.qubits)
+            yield simulator._create_simulator_trial_result(
+                params=r, measurements={}, final_simulator_state=sim_state)
+
+    return results()

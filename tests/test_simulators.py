@@ -698,6 +698,31 @@ def test_batched_sweep_expectation_values(cirq, SV, DM):
         SV(sweep_batch=True).simulate_expectation_values_sweep(c2, obs, sweep)
 
 
+def test_batched_simulate_sweep(cirq, SV, DM):
+    """simulate_sweep with sweep_batch=True: every resolver's final state equals
+    the reference's (sim/simulator_base.py:277-320)."""
+    c, q, sweep = _qaoa_like(cirq, 6, 5)
+    c = c[:-1]
+    want = cirq.Simulator(dtype=np.complex128).simulate_sweep(c, sweep)
+    sim = SV(dtype=np.complex128, sweep_batch=True)
+    got = sim.simulate_sweep(c, sweep)
+    assert sim.last_run_info['path'] == 'batched sweep' and len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g.params == w.params and g.qubit_map == w.qubit_map
+        np.testing.assert_allclose(g.final_state_vector, w.final_state_vector, atol=1e-12)
+    noise = cirq.depolarize(0.02)
+    want = cirq.DensityMatrixSimulator(dtype=np.complex128, noise=noise).simulate_sweep(c, sweep)
+    dsim = DM(dtype=np.complex128, noise=noise, sweep_batch=True)
+    got = dsim.simulate_sweep(c, sweep)
+    assert dsim.last_run_info['path'] == 'batched sweep'
+    for g, w in zip(got, want):
+        np.testing.assert_allclose(g.final_density_matrix, w.final_density_matrix, atol=1e-12)
+    # a given initial state or qubit order takes the reference loop
+    want = cirq.Simulator(dtype=np.complex128).simulate_sweep(c, sweep, initial_state=3)
+    got = SV(dtype=np.complex128, sweep_batch=True).simulate_sweep(c, sweep, initial_state=3)
+    np.testing.assert_allclose(got[2].final_state_vector, want[2].final_state_vector, atol=1e-12)
+
+
 def test_mux_entry_points_match_reference(cirq, SV, DM):
     """cirq_b200.sample / final_state_vector / final_density_matrix mirror
     cirq.sample / ... (sim/mux.py) with the same signatures."""
