@@ -362,8 +362,9 @@ def run_b200_arm(args):
             if reps:
                 res = sim.run(circuit, repetitions=reps)
                 return res.measurements['m'].shape
-            res = sim.simulate(circuit, qubit_order=wl['qubits'])
-            return res.device_state.amplitudes([0, 1])
+            # the reference's own API for reading a few amplitudes of a state too
+            # large to download (SimulatesAmplitudes, sim/simulator.py:120-182)
+            return sim.compute_amplitudes(circuit, [0, 1], qubit_order=wl['qubits'])
 
         torch.cuda.empty_cache()
         e2e_step()
@@ -378,7 +379,7 @@ def run_b200_arm(args):
                'h2d_bytes_per_step': int(8 * reps + mat_bytes),
                'd2h_bytes_per_step': int(reps * n if reps else 32),
                'api': 'cirq_b200.B200Simulator(seed=0).run(circuit, repetitions)' if reps
-                      else 'cirq_b200.B200Simulator().simulate(circuit)'}
+                      else 'cirq_b200.B200Simulator().compute_amplitudes(circuit, [0, 1])'}
 
     # ---- CPU baseline (reference on host cores, bounded sample) ---------------------------
     cpu = None

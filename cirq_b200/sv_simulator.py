@@ -67,6 +67,9 @@ class B200StateVector(qis.QuantumStateRepresentation):
         self._since_drain = 0
         self._drain_every = max(8, self._n)
         self._host = None  # cached host copy of the state, dropped on every mutation
+        # logical bit -> index bit holding it, after SWAP gates that were relabelled
+        # instead of executed and not yet undone (None: every bit in its place)
+        self._where: list[int] | None = None
 
     # ------------------------------------------------------------------ creation
 
@@ -102,7 +105,9 @@ class B200StateVector(qis.QuantumStateRepresentation):
     # ------------------------------------------------------------------ queue
 
     def _bits(self, axes: Sequence[int]) -> list[int]:
-        return [self._n - 1 - int(a) for a in axes]
+        if self._where is None:
+            return [self._n - 1 - int(a) for a in axes]
+        return [self._where[self._n - 1 - int(a)] for a in axes]
 
     def queue_unitary(self, matrix: np.ndarray, axes: Sequence[int]) -> None:
         self._host = None
@@ -125,18 +130,45 @@ class B200StateVector(qis.QuantumStateRepresentation):
             self._dev.apply_batch(ready)
             self.passes += len(ready)
 
-    def flush(self) -> None:
-        if len(self._fuser) == 0:
-            return
-        blocks = self._fuser.blocks()
+    def flush(self, restore: bool = True) -> None:
+        """Applies the queued gates.  SWAP gates the scheduler relabelled are undone
+        with real swaps (`restore`, the default: every reader of the raw array
+        expects the canonical bit order) or kept as a bit map (`restore=False`, for
+        the readers that can translate bit positions: `mapped_device_state`)."""
+        if restore:
+            if self._where is not None:
+                # fold the kept map into the fuser's, which then undoes both
+                pending = self._fuser._map
+                self._fuser._map = {
+                    b: pending.get(w, w) for b, w in enumerate(self._where) if pending.get(w, w) != b
+                }
+                self._where = None
+            blocks = self._fuser.blocks()
+        else:
+            blocks = self._fuser.blocks(restore=False)
         self._fuser.clear()
-        self._dev.apply_batch(blocks)
-        self.passes += len(blocks)
+        if blocks:
+            self._host = None
+            self._dev.apply_batch(blocks)
+            self.passes += len(blocks)
+        if not restore:
+            moved = self._fuser.take_permutation()
+            if moved:
+                where = self._where if self._where is not None else list(range(self._n))
+                self._where = [moved.get(w, w) for w in where]
 
     @property
     def device_state(self) -> DeviceState:
         self.flush()
         return self._dev
+
+    def mapped_device_state(self) -> tuple[DeviceState, list[int]]:
+        """(device array, where): logical bit b of the state is index bit where[b]
+        of the array.  Spares the passes that would put relabelled SWAPs back —
+        for readers that address the array by bit position (amplitude gathers,
+        Pauli expectations, reduced density matrices)."""
+        self.flush(restore=False)
+        return self._dev, (self._where if self._where is not None else list(range(self._n)))
 
     # ------------------------------------------------------------------ QuantumStateRepresentation
 
@@ -637,7 +669,9 @@ class _DeviceReducedStateMixin:
 
     _MAX_KEPT = 5
 
-    def _merged_device_state(self):
+    def _merged_mapped_device_state(self):
+        """(device array, where) of the merged state, see
+        ``B200StateVector.mapped_device_state``."""
         raise NotImplementedError
 
     def density_matrix_of(self, qubits=None) -> np.ndarray:
@@ -646,9 +680,9 @@ class _DeviceReducedStateMixin:
         axes = [self.qubit_map[q] for q in qubits]  # KeyError for foreign qubits, as the reference
         if len(set(axes)) != len(axes):
             return super().density_matrix_of(qubits)
-        dev = self._merged_device_state()
+        dev, where = self._merged_mapped_device_state()
         n = dev.n_bits
-        rho = dev.reduced_density_matrix([n - 1 - a for a in axes])
+        rho = dev.reduced_density_matrix([where[n - 1 - a] for a in axes])
         return rho.astype(dev.dtype)
 
     def bloch_vector_of(self, qubit) -> np.ndarray:
@@ -673,8 +707,8 @@ class B200SimulatorStep(
         self._dtype = dtype
         self._state_vector: np.ndarray | None = None
 
-    def _merged_device_state(self):
-        return self._merged_sim_state.device_state
+    def _merged_mapped_device_state(self):
+        return self._merged_sim_state._state.mapped_device_state()
 
     def state_vector(self, copy: bool = False) -> np.ndarray:
         """Host copy of the state vector (big-endian), downloaded on first use."""
@@ -696,8 +730,8 @@ class B200SimulatorStep(
 class B200StateVectorTrialResult(_DeviceReducedStateMixin, state_vector_simulator.StateVectorTrialResult):
     """Trial result whose final state stays on the device until asked for."""
 
-    def _merged_device_state(self):
-        return self.device_state
+    def _merged_mapped_device_state(self):
+        return self._get_merged_sim_state()._state.mapped_device_state()
 
     @property
     def device_state(self) -> DeviceState:
@@ -945,12 +979,15 @@ class B200Simulator(
             )
         idx = [int(b) for b in bitstrings]
         for trial_result in self.simulate_sweep_iter(program, params, qubit_order):
-            dev = trial_result.device_state
+            # (no passes spent on putting relabelled SWAPs back: indices are translated)
+            dev, where = trial_result._get_merged_sim_state()._state.mapped_device_state()
             total = 1 << dev.n_bits
             wrapped = [i % total if -total <= i < total else i for i in idx]
             for i in wrapped:
                 if i < 0 or i >= total:
                     raise IndexError(f'index {i} is out of bounds for axis 0 with size {total}')
+            if where != list(range(dev.n_bits)):
+                wrapped = [sum(((i >> b) & 1) << w for b, w in enumerate(where)) for i in wrapped]
             amps = dev.amplitudes(wrapped).astype(self._dtype)
             yield amps.tolist()
 
@@ -988,17 +1025,20 @@ class B200Simulator(
         for result in self.simulate_sweep_iter(
             program, params, qubit_order=qubit_order, initial_state=initial_state
         ):
-            dev = result.device_state
-            yield [pauli_sum_expectation(dev, obs, qmap) for obs in pslist]
+            dev, where = result._get_merged_sim_state()._state.mapped_device_state()
+            yield [pauli_sum_expectation(dev, obs, qmap, where) for obs in pslist]
 
 
-def pauli_masks(pauli_string, qubit_map, n_qubits: int) -> tuple[int, int]:
-    """x/z bit masks of a PauliString under axis -> bit p = n-1-axis."""
+def pauli_masks(pauli_string, qubit_map, n_qubits: int, where: Sequence[int] | None = None) -> tuple[int, int]:
+    """x/z bit masks of a PauliString under axis -> bit p = n-1-axis (-> where[p]
+    for a state whose bits were relabelled, ``B200StateVector.mapped_device_state``)."""
     x = z = 0
     for q, p in pauli_string.items():
         if q not in qubit_map:
             raise ValueError(f'Qubit {q} of the observable is not in the circuit')
         bit = n_qubits - 1 - qubit_map[q]
+        if where is not None:
+            bit = where[bit]
         if p == ops.X or p == ops.Y:
             x |= 1 << bit
         if p == ops.Z or p == ops.Y:
@@ -1006,7 +1046,7 @@ def pauli_masks(pauli_string, qubit_map, n_qubits: int) -> tuple[int, int]:
     return x, z
 
 
-def pauli_sum_expectation(dev: DeviceState, pauli_sum, qubit_map) -> complex:
+def pauli_sum_expectation(dev: DeviceState, pauli_sum, qubit_map, where: Sequence[int] | None = None) -> complex:
     """sum_k c_k <psi|P_k|psi>, each term one device reduction."""
     n = dev.n_bits
     total = 0.0 + 0.0j
@@ -1016,6 +1056,6 @@ def pauli_sum_expectation(dev: DeviceState, pauli_sum, qubit_map) -> complex:
                 'Cannot compute expectation value of a non-Hermitian '
                 f'PauliString <{ps}>. Coefficient must be real.'
             )
-        x, z = pauli_masks(ps, qubit_map, n)
+        x, z = pauli_masks(ps, qubit_map, n, where)
         total += ps.coefficient * dev.pauli_expectation(x, z)
     return total

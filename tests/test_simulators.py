@@ -418,6 +418,43 @@ def test_density_matrix_of_and_bloch_vector_on_device(cirq, SV, dtype):
         np.testing.assert_allclose(steps_g[i].bloch_vector_of(q[4]), steps_w[i].bloch_vector_of(q[4]), atol=atol * 4)
 
 
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
+def test_relabelled_swaps_and_bit_addressed_readers(cirq, SV, dtype):
+    """A dense state (split_untangled_states=False) with SWAP-heavy circuits: the
+    scheduler relabels the SWAPs; amplitudes, expectation values and reduced
+    density matrices read through the bit map, the raw state restores the order."""
+    from cirq_b200 import workloads as W
+
+    atol = 2e-6 if dtype == np.complex64 else 1e-12
+    qft, q = W.qft_circuit(9)
+    rng_circuit = cirq.testing.random_circuit(q, 12, 0.9, random_state=11)
+    for circuit in (rng_circuit + qft, qft + rng_circuit + cirq.Circuit(cirq.SWAP(q[0], q[5]), cirq.SWAP(q[5], q[8]))):
+        ref = cirq.Simulator(dtype=dtype, split_untangled_states=False)
+        sim = SV(dtype=dtype, split_untangled_states=False)
+        idx = [0, 5, 77, 300, 511]
+        np.testing.assert_allclose(
+            sim.compute_amplitudes(circuit, idx, qubit_order=q), ref.compute_amplitudes(circuit, idx, qubit_order=q),
+            atol=atol)
+        obs = [cirq.Z(q[0]) * cirq.X(q[7]), cirq.Y(q[3]) + 0.5 * cirq.Z(q[8]) * cirq.Z(q[1])]
+        np.testing.assert_allclose(
+            sim.simulate_expectation_values(circuit, obs, qubit_order=q),
+            ref.simulate_expectation_values(circuit, obs, qubit_order=q), atol=atol * 4)
+        want = ref.simulate(circuit, qubit_order=q)
+        got = sim.simulate(circuit, qubit_order=q)
+        state = got._get_merged_sim_state()._state
+        np.testing.assert_allclose(got.density_matrix_of([q[6], q[0]]), want.density_matrix_of([q[6], q[0]]), atol=atol)
+        np.testing.assert_allclose(got.bloch_vector_of(q[8]), want.bloch_vector_of(q[8]), atol=atol * 4)
+        assert state._where is not None  # the readers above left the SWAPs relabelled
+        # ... and the raw state comes back in canonical order
+        np.testing.assert_allclose(got.final_state_vector, want.final_state_vector, atol=atol)
+        assert state._where is None
+        # sampling after a mapped read: canonical order again, seeded like the reference
+        c2 = circuit + cirq.Circuit(cirq.measure(*q, key='m'))
+        a = SV(dtype=dtype, seed=3, split_untangled_states=False).run(c2, repetitions=40)
+        b = cirq.Simulator(dtype=dtype, seed=3, split_untangled_states=False).run(c2, repetitions=40)
+        np.testing.assert_array_equal(a.measurements['m'], b.measurements['m'])
+
+
 def test_wide_and_composite_operations(cirq, SV):
     q = cirq.LineQubit.range(7)
     circuit = cirq.Circuit(

@@ -37,7 +37,7 @@ def main():
         sim = cirq_b200.B200Simulator(dtype=np.complex64, seed=0)
         if reps:
             return sim.run(circuit, repetitions=reps).measurements['m'].shape
-        return sim.simulate(circuit, qubit_order=wl['qubits']).device_state.amplitudes([0, 1])
+        return sim.compute_amplitudes(circuit, [0, 1], qubit_order=wl['qubits'])
 
     step()
     torch.cuda.synchronize()
