@@ -1,3 +1,4 @@
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r1F.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch_r1F.log 2>&1; tail -1 gpurun_out/ncu_launch_r1F.log | cut -c1-200
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1F_qft34.csv python bench.py --workload qft34 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch_r1F_qft34.log 2>&1; tail -1 gpurun_out/ncu_launch_r1F_qft34.log | cut -c1-200
-wc -l gpurun_out/launches_r1F.csv gpurun_out/launches_r1F_qft34.csv
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python bench.py --workload qft34 --no-cpu-baseline --steps 3 > gpurun_out/bench_r1G_qft34.json 2> gpurun_out/bench_r1G_qft34.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_r1G_qft34.json')); print('qft34', d['value'], d['ms_per_step'], 'e2e', d['e2e'], d['config']['passes_per_step'], d['roofline']['frac'], d['roofline']['kernel'], {k:(v['launches_per_step'], round(v['ms_per_launch'],3)) for k,v in d['roofline']['kernels'].items()})"
+tail -3 gpurun_out/bench_r1G_qft34.err
