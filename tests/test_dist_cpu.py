@@ -224,3 +224,54 @@ def test_block_diagonal_detection():
     subs = block_diagonal_in(d, [5, 4, 2], [5, 2])
     assert subs is not None and subs[(1, 0)].shape == (2, 2)
     np.testing.assert_allclose(subs[(1, 0)], np.diag([d[4, 4], d[6, 6]]))
+
+
+def _sweep_worker(rank, world, port, out_dir):
+    """run_sweep_sharded: resolvers dealt out over the ranks (replicas), results
+    gathered in resolver order."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import torch.distributed as dist
+
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import sympy
+
+        import cirq_b200
+        import cirq_b200.dm_simulator as dmm
+        from cirq_b200._cirq_compat import import_cirq
+        from cirq_b200.dist import run_sweep_sharded
+        from fake_device import OracleDeviceState
+
+        dmm.DeviceState = OracleDeviceState
+        cirq = import_cirq()
+        q = cirq.LineQubit.range(3)
+        t = sympy.Symbol('t')
+        # X**t with t in {0, 1, 2, 3}: deterministic outcomes t % 2 per resolver; plus a fair coin
+        circuit = cirq.Circuit(cirq.X(q[0]) ** t, cirq.CNOT(q[0], q[1]), cirq.H(q[2]),
+                               cirq.measure(*q, key='m'))
+        sweep = cirq.Points('t', [0, 1, 2, 3, 1, 0, 1])
+        results = run_sweep_sharded(
+            lambda s: cirq_b200.B200DensityMatrixSimulator(seed=s), circuit, sweep, repetitions=200, seed=5)
+        ok = len(results) == 7
+        for r, tv in zip(results, [0, 1, 2, 3, 1, 0, 1]):
+            m = r.measurements['m']
+            ok &= r.params.value_of('t') == tv and m.shape == (200, 3)
+            ok &= bool(np.all(m[:, 0] == tv % 2) and np.all(m[:, 1] == tv % 2))
+            ok &= 60 < int(m[:, 2].sum()) < 140
+        np.savez(os.path.join(out_dir, f'sweep_{rank}.npz'), ok=ok,
+                 first=results[1].measurements['m'])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_run_sweep_sharded_replicas(tmp_path):
+    world = 2
+    port = 29500 + (os.getpid() * 3 + 11) % 2000
+    mp.spawn(_sweep_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    a = np.load(os.path.join(str(tmp_path), 'sweep_0.npz'))
+    b = np.load(os.path.join(str(tmp_path), 'sweep_1.npz'))
+    assert bool(a['ok']) and bool(b['ok'])
+    np.testing.assert_array_equal(a['first'], b['first'])  # every rank holds the same gathered results
