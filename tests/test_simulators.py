@@ -760,6 +760,75 @@ def test_batched_simulate_sweep(cirq, SV, DM):
     np.testing.assert_allclose(got[2].final_state_vector, want[2].final_state_vector, atol=1e-12)
 
 
+@pytest.mark.parametrize('seed', [1, 2])
+def test_differential_fuzz_state_vector(cirq, SV, seed):
+    """Random circuits over a gate set rich in diagonal gates, SWAPs and 3-qubit
+    gates, random sizes / fusion widths / split settings: final states, device-side
+    amplitude gathers and seeded samples against cirq.Simulator."""
+    rng = np.random.RandomState(seed)
+    domain = {cirq.CNOT: 2, cirq.CZ: 2, cirq.H: 1, cirq.ISWAP: 2, cirq.CZPowGate(exponent=0.3): 2,
+              cirq.S: 1, cirq.SWAP: 2, cirq.T: 1, cirq.X: 1, cirq.Y ** 0.5: 1, cirq.Z: 1, cirq.CCZ: 3,
+              cirq.ZZPowGate(exponent=0.7): 2, cirq.FSimGate(0.4, 0.9): 2, cirq.rz(0.3): 1}
+    for trial in range(60):
+        n = int(rng.randint(2, 10))
+        q = cirq.LineQubit.range(n)
+        c = cirq.testing.random_circuit(
+            q, int(rng.randint(3, 25)), float(rng.uniform(0.4, 1.0)),
+            gate_domain={g: k for g, k in domain.items() if k <= n}, random_state=int(rng.randint(1 << 30)))
+        c.append(cirq.I.on_each(*q))
+        split = bool(rng.randint(2))
+        dtype = [np.complex64, np.complex128][rng.randint(2)]
+        mf = [None, 2, 3, 4][rng.randint(4)]
+        atol = 2e-5 if dtype == np.complex64 else 1e-11
+        want = cirq.Simulator(dtype=dtype, split_untangled_states=split).simulate(c, qubit_order=q).final_state_vector
+        sim = SV(dtype=dtype, split_untangled_states=split, max_fused_qubits=mf)
+        idx = [int(x) for x in rng.randint(0, 1 << n, size=4)]
+        amps = sim.compute_amplitudes(c, idx, qubit_order=q)
+        got = sim.simulate(c, qubit_order=q).final_state_vector
+        assert np.max(np.abs(got - want)) <= atol, (trial, n, split, dtype, mf)
+        assert np.max(np.abs(np.array(amps) - want[idx])) <= atol, (trial, n, split, dtype, mf)
+        c2 = c + cirq.Circuit(cirq.measure(*q, key='m'))
+        a = SV(dtype=dtype, seed=trial, split_untangled_states=split, max_fused_qubits=mf).run(c2, repetitions=20)
+        b = cirq.Simulator(dtype=dtype, seed=trial, split_untangled_states=split).run(c2, repetitions=20)
+        # (complex64 rounding can move a draw across a CDF bin edge: rare, never systematic)
+        assert np.mean(a.measurements['m'] != b.measurements['m']) <= 0.05, (trial, n, split, dtype)
+
+
+def test_differential_fuzz_density_matrix(cirq, DM):
+    """Random circuits with channels sprinkled in (and optionally a noise model):
+    final density matrices and seeded samples against cirq.DensityMatrixSimulator."""
+    rng = np.random.RandomState(4)
+    domain = {cirq.CNOT: 2, cirq.CZ: 2, cirq.H: 1, cirq.ISWAP: 2, cirq.S: 1, cirq.SWAP: 2, cirq.T: 1,
+              cirq.X: 1, cirq.Y ** 0.5: 1, cirq.ZZPowGate(exponent=0.7): 2, cirq.FSimGate(0.4, 0.9): 2}
+    chans = [cirq.depolarize(0.1), cirq.amplitude_damp(0.2), cirq.phase_damp(0.3), cirq.bit_flip(0.15),
+             cirq.depolarize(0.05, n_qubits=2)]
+    for trial in range(40):
+        n = int(rng.randint(1, 6))
+        q = cirq.LineQubit.range(n)
+        c = cirq.testing.random_circuit(
+            q, int(rng.randint(2, 12)), 0.8, gate_domain={g: k for g, k in domain.items() if k <= n},
+            random_state=int(rng.randint(1 << 30)))
+        for _ in range(rng.randint(1, 6)):
+            ch = chans[rng.randint(len(chans))]
+            k = cirq.num_qubits(ch)
+            if k <= n:
+                c.insert(int(rng.randint(0, len(c) + 1)), ch.on(*[q[i] for i in rng.permutation(n)[:k]]))
+        c.append(cirq.I.on_each(*q))
+        noise = [None, cirq.depolarize(0.02)][rng.randint(2)]
+        split = bool(rng.randint(2))
+        dtype = [np.complex64, np.complex128][rng.randint(2)]
+        atol = 2e-5 if dtype == np.complex64 else 1e-11
+        want = cirq.DensityMatrixSimulator(dtype=dtype, noise=noise, split_untangled_states=split).simulate(
+            c, qubit_order=q).final_density_matrix
+        got = DM(dtype=dtype, noise=noise, split_untangled_states=split).simulate(c, qubit_order=q).final_density_matrix
+        assert np.max(np.abs(got - want)) <= atol, (trial, n, split, dtype, noise)
+        c2 = c + cirq.Circuit(cirq.measure(*q, key='m'))
+        a = DM(dtype=dtype, noise=noise, seed=trial, split_untangled_states=split).run(c2, repetitions=15)
+        b = cirq.DensityMatrixSimulator(dtype=dtype, noise=noise, seed=trial, split_untangled_states=split).run(
+            c2, repetitions=15)
+        assert np.mean(a.measurements['m'] != b.measurements['m']) <= 0.05, (trial, n, split, dtype)
+
+
 def test_mux_entry_points_match_reference(cirq, SV, DM):
     """cirq_b200.sample / final_state_vector / final_density_matrix mirror
     cirq.sample / ... (sim/mux.py) with the same signatures."""
