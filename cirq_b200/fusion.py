@@ -321,6 +321,13 @@ class GateFuser:
             at[cur], holder[other] = other, cur
             at[w], holder[w] = w, w
 
+    def fold_permutation(self, where: Sequence[int]) -> None:
+        """Merges a permutation the caller kept from earlier `take_permutation`
+        calls (its wire b lives on wire where[b]) back into the pending relabelling,
+        so that the next `blocks()` restores the caller's original order."""
+        pending = self._map
+        self._map = {b: pending.get(w, w) for b, w in enumerate(where) if pending.get(w, w) != b}
+
     def take_permutation(self) -> dict[int, int]:
         """{caller's wire: wire that holds it now} of the pending relabelling, which
         is then forgotten (the caller renames its wires instead of moving data)."""

@@ -138,10 +138,7 @@ class B200StateVector(qis.QuantumStateRepresentation):
         if restore:
             if self._where is not None:
                 # fold the kept map into the fuser's, which then undoes both
-                pending = self._fuser._map
-                self._fuser._map = {
-                    b: pending.get(w, w) for b, w in enumerate(self._where) if pending.get(w, w) != b
-                }
+                self._fuser.fold_permutation(self._where)
                 self._where = None
             blocks = self._fuser.blocks()
         else:
