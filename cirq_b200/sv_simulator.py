@@ -500,13 +500,19 @@ _UNITARY_CACHE: dict = {}
 _UNITARY_CACHE_MAX = 4096
 
 
+# Operation types that are nothing but "this gate on these qubits": cirq.X(q) and
+# friends come as SingleQubitPauliStringGateOperation, a GateOperation subclass
+# whose unitary is its gate's.
+PLAIN_GATE_OPERATIONS = (ops.GateOperation, ops.SingleQubitPauliStringGateOperation)
+
+
 def cached_unitary(action: Any):
     """``protocols.unitary`` with a small cache keyed by the (hashable,
     parameter-free) gate: circuits repeat a handful of gates thousands of
     times and building each matrix costs ~40 us of Python."""
     gate = getattr(action, 'gate', None)
     key = None
-    if gate is not None and type(action) is ops.GateOperation:
+    if gate is not None and type(action) in PLAIN_GATE_OPERATIONS:
         try:
             key = gate
             hit = _UNITARY_CACHE.get(key)
@@ -808,7 +814,16 @@ class B200Simulator(
             if batched is not None:
                 yield from batched
                 return
-        yield from super().simulate_sweep_iter(program, params, qubit_order, initial_state)
+        resolvers = list(study.to_resolvers(params))
+        if len(resolvers) == 1:
+            # a plain simulate(): nothing to share between resolvers, so the
+            # reference's split into a resolver-independent prefix and the rest
+            # (sim/simulator_base.py:304-320: ~40 us of Python per operation before
+            # the first gate reaches the GPU) is skipped — same result
+            yield from simulator.SimulatesIntermediateState.simulate_sweep_iter(
+                self, program, resolvers, qubit_order, initial_state)
+            return
+        yield from super().simulate_sweep_iter(program, resolvers, qubit_order, initial_state)
 
     def run_sweep_iter(self, program, params, repetitions: int = 1):
         """``SimulatesSamples.run_sweep_iter`` (sim/simulator.py:62-94); with
@@ -887,7 +902,7 @@ class B200Simulator(
         product = isinstance(sim_state, B200ProductState)
         dense = isinstance(sim_state, B200StateVectorSimulationState)
         lean = product or dense
-        gate_operation, moment_type = ops.GateOperation, circuits.Moment
+        plain, moment_type = PLAIN_GATE_OPERATIONS, circuits.Moment
         for moment in noisy_moments:
             moment_ops = moment.operations if type(moment) is moment_type else ops.flatten_to_ops(moment)
             for op in moment_ops:
@@ -898,7 +913,7 @@ class B200Simulator(
                         measured[op.qubits] = True
                         if all_measurements_are_terminal:
                             continue
-                    if lean and type(op) is gate_operation and 0 < len(op.qubits) <= 5:
+                    if lean and type(op) in plain and 0 < len(op.qubits) <= 5:
                         u = cached_unitary(op)
                         if u is not None:
                             if product:
@@ -935,7 +950,7 @@ class B200Simulator(
                     first = i
                 else:
                     for op in moment:
-                        if type(op) is not ops.GateOperation or cached_unitary(op) is None:
+                        if type(op) not in PLAIN_GATE_OPERATIONS or cached_unitary(op) is None:
                             return None
             elif not all(measuring):
                 return None

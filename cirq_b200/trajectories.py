@@ -61,7 +61,7 @@ def _classify(op, axis_bit, cache: dict | None = None) -> tuple | None:
         return ('measure', bits, str(protocols.measurement_key_obj(op)), list(op.gate.full_invert_mask()))
     key = None
     # (noise models tag what they insert: look through the tags)
-    if cache is not None and type(op.untagged) is ops.GateOperation:
+    if cache is not None and isinstance(op.untagged, ops.GateOperation):
         try:
             hit = cache.get(op.gate)
             key = op.gate
