@@ -66,3 +66,62 @@ extern "C" int b2q_device_info(int* sm_count, uint64_t* hbm_bytes, int* cc) {
   if (cc) *cc = prop.major * 10 + prop.minor;
   return B2Q_OK;
 }
+
+// ---- host-side scheduler helper ---------------------------------------------------------
+// block <- (matrix on the row-index bits bitpos[]) . block, for the gate fuser
+// (cirq_b200/fusion.py apply_to_block / expand_matrix): block is a 2^u x 2^u
+// complex128 row-major matrix on the HOST, matrix a 2^k x 2^k complex128 whose
+// first wire is its most significant index bit, bitpos[j] the bit of the block's
+// row index that wire j acts on.  Small (u <= 6) and called once per circuit
+// gate; numpy's tensordot + moveaxis cost ~10x more in dispatch than the
+// arithmetic is worth.
+extern "C" int b2q_host_left_apply(double* block, int u, const double* matrix, const int* bitpos,
+                                   int k) {
+  B2Q_REQUIRE(block != nullptr && matrix != nullptr && bitpos != nullptr, "null argument");
+  B2Q_REQUIRE(u >= 1 && u <= 6 && k >= 1 && k <= u, "bad sizes u=%d k=%d", u, k);
+  const int dim = 1 << u, d = 1 << k;
+  int sorted[6];
+  for (int j = 0; j < k; ++j) {
+    B2Q_REQUIRE(bitpos[j] >= 0 && bitpos[j] < u, "bit position %d out of range", bitpos[j]);
+    sorted[j] = bitpos[j];
+  }
+  for (int a = 1; a < k; ++a)
+    for (int b = a; b > 0 && sorted[b - 1] > sorted[b]; --b) {
+      const int t = sorted[b];
+      sorted[b] = sorted[b - 1];
+      sorted[b - 1] = t;
+    }
+  for (int a = 1; a < k; ++a) B2Q_REQUIRE(sorted[a] != sorted[a - 1], "duplicate bit position");
+  int offset[64];
+  for (int t = 0; t < d; ++t) {
+    int o = 0;
+    for (int j = 0; j < k; ++j)
+      if ((t >> (k - 1 - j)) & 1) o |= 1 << bitpos[j];
+    offset[t] = o;
+  }
+  double tmp[64 * 64 * 2];  // d rows of dim complex numbers
+  const int groups = 1 << (u - k);
+  for (int g = 0; g < groups; ++g) {
+    const int base = (int)b2q::insert_zero_bits((uint64_t)g, sorted, k);
+    for (int r = 0; r < d; ++r) {
+      double* out = tmp + (size_t)r * dim * 2;
+      for (int c = 0; c < 2 * dim; ++c) out[c] = 0.0;
+      for (int t = 0; t < d; ++t) {
+        const double mr = matrix[2 * (r * d + t)], mi = matrix[2 * (r * d + t) + 1];
+        if (mr == 0.0 && mi == 0.0) continue;
+        const double* row = block + (size_t)(base | offset[t]) * dim * 2;
+        for (int c = 0; c < dim; ++c) {
+          const double xr = row[2 * c], xi = row[2 * c + 1];
+          out[2 * c] += mr * xr - mi * xi;
+          out[2 * c + 1] += mr * xi + mi * xr;
+        }
+      }
+    }
+    for (int r = 0; r < d; ++r) {
+      double* row = block + (size_t)(base | offset[r]) * dim * 2;
+      const double* out = tmp + (size_t)r * dim * 2;
+      for (int c = 0; c < 2 * dim; ++c) row[c] = out[c];
+    }
+  }
+  return B2Q_OK;
+}

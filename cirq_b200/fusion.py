@@ -25,9 +25,40 @@ from __future__ import annotations
 
 from typing import Iterable, Sequence
 
+import ctypes
 import os
 
 import numpy as np
+
+
+_NATIVE = None  # libcirq_b200.so's host helper, False when the library is not built
+
+
+def _native():
+    global _NATIVE
+    if _NATIVE is None:
+        _NATIVE = False
+        if os.environ.get('CIRQ_B200_NATIVE_FUSER', '1') != '0':
+            try:
+                from cirq_b200 import _lib
+
+                lib = _lib.load()
+                if hasattr(lib, 'b2q_host_left_apply'):
+                    _NATIVE = lib
+            except Exception:  # library not built (host-only use of the scheduler): numpy path
+                _NATIVE = False
+    return _NATIVE
+
+
+def _left_apply_native(lib, block: np.ndarray, union, matrix: np.ndarray, wires) -> np.ndarray | None:
+    """(matrix on `wires`) @ block through b2q_host_left_apply; `block` is consumed."""
+    u, k = len(union), len(wires)
+    m = np.ascontiguousarray(matrix, dtype=np.complex128)
+    top = u - 1
+    pos = (ctypes.c_int * k)(*[top - union.index(w) for w in wires])
+    if lib.b2q_host_left_apply(block.ctypes.data, u, m.ctypes.data, pos, k) != 0:
+        return None
+    return block
 
 
 def expand_matrix(matrix: np.ndarray, wires: Sequence[int], out_wires: Sequence[int]) -> np.ndarray:
@@ -38,6 +69,12 @@ def expand_matrix(matrix: np.ndarray, wires: Sequence[int], out_wires: Sequence[
     m = np.asarray(matrix, dtype=np.complex128).reshape((2,) * (2 * k))
     if tuple(wires) == tuple(out_wires):
         return m.reshape(1 << k, 1 << k)
+    lib = _native()
+    if lib and u <= 6:
+        out = _left_apply_native(lib, np.eye(1 << u, dtype=np.complex128), tuple(out_wires),
+                                 m.reshape(1 << k, 1 << k), wires)
+        if out is not None:
+            return out
     pos = [out_wires.index(w) for w in wires]
     full = np.eye(1 << u, dtype=np.complex128).reshape((2,) * (2 * u))
     # contract the input legs of m with the row legs `pos` of the identity
@@ -61,6 +98,12 @@ def apply_to_block(block: np.ndarray, union: Sequence[int], matrix: np.ndarray,
     k = len(wires)
     if k == u and tuple(wires) == tuple(union):
         return matrix @ block
+    lib = _native()
+    if lib and u <= 6:
+        out = _left_apply_native(lib, np.array(block, dtype=np.complex128, order='C'), tuple(union),
+                                 matrix, wires)
+        if out is not None:
+            return out
     pos = [union.index(w) for w in wires]
     t = block.reshape((2,) * u + (1 << u,))
     res = np.tensordot(matrix.reshape((2,) * (2 * k)), t, axes=(list(range(k, 2 * k)), pos))

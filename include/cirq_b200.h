@@ -301,6 +301,16 @@ int b2q_bsv_kraus_weights(const void* state, int dtype, int n_qubits, int batch_
 int b2q_bsv_collapse(void* state, int dtype, int n_qubits, int batch_bits, uint64_t mask,
                      const uint64_t* pattern_dev, const double* scale_dev, void* stream);
 
+/* ---- host-side scheduler helper --------------------------------------------- */
+
+/* block <- (matrix on row-index bits bitpos[]) . block on the HOST: block is a
+ * 2^u x 2^u complex128 row-major matrix (u <= 6), matrix 2^k x 2^k complex128 with
+ * its first wire as the most significant index bit, bitpos[j] the row-index bit of
+ * wire j.  The gate fuser's block product (the host part of
+ * transformers/merge_k_qubit_gates.py:70-114, whose merged unitary the reference
+ * obtains from protocols.unitary(CircuitOperation)); no GPU involved. */
+int b2q_host_left_apply(double* block, int u, const double* matrix, const int* bitpos, int k);
+
 /* ---- tuning knobs and host-only test hooks (not needed by a binding) -------- */
 
 /* How target bits inside the 512-byte warp zone are handled by the register
