@@ -113,6 +113,12 @@ class B200DensityMatrix(qis.QuantumStateRepresentation):
         self._fuser.add(sup, self._row_bits(axes) + self._col_bits(axes))
         self._maybe_drain(1)
 
+    def queue_superoperator(self, sup: np.ndarray, axes: Sequence[int]) -> None:
+        """A channel already in superoperator form (sum_i K_i (x) conj(K_i))."""
+        self._host = None
+        self._fuser.add(sup, self._row_bits(axes) + self._col_bits(axes))
+        self._maybe_drain(1)
+
     def _maybe_drain(self, added: int) -> None:
         self._since_drain += added
         if self._since_drain < self._drain_every:
@@ -374,6 +380,51 @@ def _strat_apply_channel(action: Any, args: B200DensityMatrixSimulationState, qu
     return True
 
 
+_FORM_CACHE: dict = {}
+_FORM_CACHE_MAX = 4096
+
+
+def cached_channel_form(op) -> tuple | None:
+    """('unitary', U) or ('super', sum_i K_i (x) conj(K_i)) for a plain gate operation
+    (tags looked through) on at most 3 qubits, cached per gate — what
+    ``_strat_apply_channel`` computes, once instead of per operation (a noise model
+    inserts the same channel hundreds of times).  None for everything that must
+    take ``protocols.act_on``: measurements, resets (the product state factors the
+    qubit out afterwards), classical control, composite or symbolic operations."""
+    from cirq_b200.sv_simulator import PLAIN_GATE_OPERATIONS
+
+    base = op.untagged if type(op) is ops.TaggedOperation else op
+    if type(base) not in PLAIN_GATE_OPERATIONS:
+        return None
+    gate = base.gate
+    try:
+        hit = _FORM_CACHE.get(gate)
+    except TypeError:  # unhashable gate
+        return None
+    if hit is not None:
+        return hit or None
+    form: Any = False
+    n = len(base.qubits)
+    if (
+        0 < n <= _MAX_DIRECT_QUBITS
+        and not isinstance(gate, (ops.MeasurementGate, ops.ResetChannel, ops.IdentityGate, ops.SwapPowGate))
+        and not protocols.is_parameterized(gate)
+        and not protocols.is_measurement(base)
+        and all(d == 2 for d in protocols.qid_shape(base))
+    ):
+        u = protocols.unitary(base, None) if protocols.has_unitary(base) else None
+        if u is not None:
+            form = ('unitary', np.asarray(u, dtype=np.complex128))
+        else:
+            ks = protocols.kraus(base, default=None)
+            if ks is not None:
+                form = ('super', sum(np.kron(k, np.conj(k)) for k in ks))
+    if len(_FORM_CACHE) >= _FORM_CACHE_MAX:
+        _FORM_CACHE.clear()
+    _FORM_CACHE[gate] = form
+    return form or None
+
+
 class B200DensityMatrixStepResult(_FastConfuseMixin, _ref_dm.DensityMatrixStepResult):
     """Step result; ``density_matrix()`` downloads rho on first use."""
 
@@ -472,6 +523,46 @@ class B200DensityMatrixSimulator(
         return B200DensityMatrixTrialResult(
             params=params, measurements=measurements, final_simulator_state=final_simulator_state
         )
+
+    def _core_iterator(self, circuit, sim_state, all_measurements_are_terminal: bool = False):
+        """``SimulatorBase._core_iterator`` (sim/simulator_base.py:169-214) with the
+        shortcut of ``B200Simulator._core_iterator``: a plain unitary gate or channel
+        on at most 3 qubits goes straight into the density matrix's queue as U (x)
+        conj(U) / its cached superoperator, instead of through ``protocols.act_on``
+        and a fresh ``protocols.kraus`` + Kronecker products per operation."""
+        import collections
+
+        from cirq_b200.sv_simulator import B200ProductState
+
+        if len(circuit) == 0:
+            yield self._create_step_result(sim_state)
+            return
+        noisy_moments = self.noise.noisy_moments(circuit, sorted(circuit.all_qubits()))
+        measured: dict = collections.defaultdict(bool)
+        product = isinstance(sim_state, B200ProductState)
+        dense = isinstance(sim_state, B200DensityMatrixSimulationState)
+        for moment in noisy_moments:
+            for op in ops.flatten_to_ops(moment):
+                try:
+                    if all_measurements_are_terminal and measured[op.qubits]:
+                        continue
+                    if isinstance(op.gate, ops.MeasurementGate):
+                        measured[op.qubits] = True
+                        if all_measurements_are_terminal:
+                            continue
+                    form = cached_channel_form(op) if (product or dense) else None
+                    if form is not None:
+                        target = sim_state.join_for(op.qubits) if product else sim_state
+                        axes = target.get_axes(op.qubits)
+                        if form[0] == 'unitary':
+                            target._state.queue_unitary(form[1], axes)
+                        else:
+                            target._state.queue_superoperator(form[1], axes)
+                        continue
+                    protocols.act_on(op, sim_state)
+                except TypeError:
+                    raise TypeError(f"{self.__class__.__name__} doesn't support {op!r}")
+            yield self._create_step_result(sim_state)
 
     def simulate_expectation_values_sweep(
         self,

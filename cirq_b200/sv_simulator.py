@@ -336,7 +336,12 @@ class B200ProductState(SimulationProductState):
         if isinstance(gate, (ops.IdentityGate, ops.SwapPowGate)):
             self._act_on_fallback_(op, op.qubits)
             return
-        qubits = op.qubits
+        target = self.join_for(op.qubits)
+        target._state.queue_unitary(unitary, target.get_axes(op.qubits))
+
+    def join_for(self, qubits):
+        """The sub-state holding all of `qubits`, joining sub-states by Kronecker
+        products when they live apart (sim/simulation_product_state.py:110-123)."""
         states = self._sim_states
         target = states[qubits[0]]
         joined = False
@@ -347,7 +352,7 @@ class B200ProductState(SimulationProductState):
         if joined:
             for q in target.qubits:
                 states[q] = target
-        target._state.queue_unitary(unitary, target.get_axes(qubits))
+        return target
 
     def sample(self, qubits, repetitions: int = 1, seed=None) -> np.ndarray:
         q_set = set(qubits)
