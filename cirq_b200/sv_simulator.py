@@ -533,6 +533,41 @@ def cached_unitary(action: Any):
     return u
 
 
+_MIXTURE_CACHE: dict = {}
+
+
+def cached_mixture(base_op) -> tuple | None:
+    """(probabilities, unitaries, is_identity flags) of a plain gate operation that
+    is a mixture of unitaries but not a unitary itself and records nothing (the
+    Pauli channels a noise model inserts hundreds of times), cached per gate; None
+    otherwise."""
+    gate = base_op.gate
+    try:
+        hit = _MIXTURE_CACHE.get(gate)
+    except TypeError:  # unhashable gate
+        return None
+    if hit is not None:
+        return hit or None
+    form: Any = False
+    if (
+        0 < len(base_op.qubits) <= 3
+        and not protocols.is_parameterized(gate)
+        and not protocols.is_measurement(base_op)
+        and all(d == 2 for d in protocols.qid_shape(base_op))
+        and not protocols.has_unitary(base_op)
+    ):
+        mixture = protocols.mixture(base_op, default=None)
+        if mixture is not None:
+            probabilities, unitaries = zip(*mixture)
+            unitaries = [np.asarray(u, dtype=np.complex128) for u in unitaries]
+            eye = np.eye(unitaries[0].shape[0])
+            form = (probabilities, unitaries, [np.array_equal(u, eye) for u in unitaries])
+    if len(_MIXTURE_CACHE) >= _UNITARY_CACHE_MAX:
+        _MIXTURE_CACHE.clear()
+    _MIXTURE_CACHE[gate] = form
+    return form or None
+
+
 def _strat_unitary(action: Any, args: B200StateVectorSimulationState, qubits) -> bool:
     """Unitary strategy: obtain the matrix from Cirq's query protocols and queue
     it.  Replaces ``_strat_act_on_state_vector_from_apply_unitary``
@@ -907,7 +942,7 @@ class B200Simulator(
         product = isinstance(sim_state, B200ProductState)
         dense = isinstance(sim_state, B200StateVectorSimulationState)
         lean = product or dense
-        plain, moment_type = PLAIN_GATE_OPERATIONS, circuits.Moment
+        plain, moment_type, tagged = PLAIN_GATE_OPERATIONS, circuits.Moment, ops.TaggedOperation
         for moment in noisy_moments:
             moment_ops = moment.operations if type(moment) is moment_type else ops.flatten_to_ops(moment)
             for op in moment_ops:
@@ -918,13 +953,23 @@ class B200Simulator(
                         measured[op.qubits] = True
                         if all_measurements_are_terminal:
                             continue
-                    if lean and type(op) in plain and 0 < len(op.qubits) <= 5:
-                        u = cached_unitary(op)
+                    base = op.untagged if type(op) is tagged else op
+                    if lean and type(base) in plain and 0 < len(base.qubits) <= 5:
+                        u = cached_unitary(base)
                         if u is not None:
                             if product:
-                                sim_state.apply_unitary_op(op, u)
+                                sim_state.apply_unitary_op(base, u)
                             else:
-                                sim_state._state.queue_unitary(u, sim_state.get_axes(op.qubits))
+                                sim_state._state.queue_unitary(u, sim_state.get_axes(base.qubits))
+                            continue
+                        mix = cached_mixture(base)
+                        if mix is not None:
+                            # _strat_mixture with the gate's mixture cached: the same
+                            # single draw; an identity pick queues nothing
+                            target = sim_state.join_for(base.qubits) if product else sim_state
+                            index = target.prng.choice(range(len(mix[1])), p=mix[0])
+                            if not mix[2][index]:
+                                target._state.queue_unitary(mix[1][index], target.get_axes(base.qubits))
                             continue
                     protocols.act_on(op, sim_state)
                 except TypeError:
