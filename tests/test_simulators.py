@@ -794,6 +794,42 @@ def test_differential_fuzz_state_vector(cirq, SV, seed):
         assert np.mean(a.measurements['m'] != b.measurements['m']) <= 0.05, (trial, n, split, dtype)
 
 
+def test_differential_fuzz_noisy_state_vector_seeded(cirq, SV):
+    """Noisy / mid-circuit-measured random circuits: the per-repetition loop
+    consumes the simulator's random stream exactly like cirq.Simulator (mixtures,
+    Kraus trajectories, resets, measurements, noise models), so seeded records agree."""
+    rng = np.random.RandomState(1)
+    domain = {cirq.CNOT: 2, cirq.CZ: 2, cirq.H: 1, cirq.ISWAP: 2, cirq.S: 1, cirq.SWAP: 2, cirq.T: 1,
+              cirq.X: 1, cirq.Y ** 0.5: 1, cirq.FSimGate(0.4, 0.9): 2}
+    chans = [cirq.depolarize(0.2), cirq.amplitude_damp(0.3), cirq.phase_damp(0.3), cirq.bit_flip(0.25),
+             cirq.phase_flip(0.2), cirq.asymmetric_depolarize(0.1, 0.1, 0.2), cirq.depolarize(0.1, n_qubits=2),
+             cirq.reset]
+    for trial in range(25):
+        n = int(rng.randint(1, 6))
+        q = cirq.LineQubit.range(n)
+        c = cirq.testing.random_circuit(
+            q, int(rng.randint(2, 10)), 0.8, gate_domain={g: k for g, k in domain.items() if k <= n},
+            random_state=int(rng.randint(1 << 30)))
+        for _ in range(rng.randint(1, 6)):
+            ch = chans[rng.randint(len(chans))]
+            if ch is cirq.reset:
+                c.insert(int(rng.randint(0, len(c) + 1)), cirq.reset(q[rng.randint(n)]))
+                continue
+            k = cirq.num_qubits(ch)
+            if k <= n:
+                c.insert(int(rng.randint(0, len(c) + 1)), ch.on(*[q[i] for i in rng.permutation(n)[:k]]))
+        if rng.randint(2):
+            c.insert(int(rng.randint(0, len(c) + 1)), cirq.measure(q[rng.randint(n)], key='mid'))
+        c.append(cirq.measure(*q, key='m'))
+        noise = [None, cirq.depolarize(0.05), cirq.bit_flip(0.1)][rng.randint(3)]
+        split = bool(rng.randint(2))
+        a = SV(noise=noise, seed=trial, split_untangled_states=split).run(c, repetitions=12)
+        b = cirq.Simulator(noise=noise, seed=trial, split_untangled_states=split).run(c, repetitions=12)
+        for key in b.records:
+            # (a complex64 rounding difference at a probability bin edge may flip a draw)
+            assert np.mean(a.records[key] != b.records[key]) <= 0.1, (trial, n, key, split, noise)
+
+
 def test_differential_fuzz_density_matrix(cirq, DM):
     """Random circuits with channels sprinkled in (and optionally a noise model):
     final density matrices and seeded samples against cirq.DensityMatrixSimulator."""
