@@ -514,7 +514,10 @@ PLAIN_GATE_OPERATIONS = (ops.GateOperation, ops.SingleQubitPauliStringGateOperat
 def cached_unitary(action: Any):
     """``protocols.unitary`` with a small cache keyed by the (hashable,
     parameter-free) gate: circuits repeat a handful of gates thousands of
-    times and building each matrix costs ~40 us of Python."""
+    times and building each matrix costs ~40 us of Python.  "Has no unitary" is
+    cached too (False): for a channel the protocol tries ``_unitary_``,
+    ``_apply_unitary_`` and a decomposition before giving up, ~120 us that a noise
+    model would pay once per inserted operation."""
     gate = getattr(action, 'gate', None)
     key = None
     if gate is not None and type(action) in PLAIN_GATE_OPERATIONS:
@@ -522,14 +525,14 @@ def cached_unitary(action: Any):
             key = gate
             hit = _UNITARY_CACHE.get(key)
             if hit is not None:
-                return hit
+                return None if hit is False else hit
         except TypeError:  # unhashable gate
             key = None
     u = protocols.unitary(action, None)
-    if key is not None and u is not None and not protocols.is_parameterized(gate):
+    if key is not None and not protocols.is_parameterized(gate):
         if len(_UNITARY_CACHE) >= _UNITARY_CACHE_MAX:
             _UNITARY_CACHE.clear()
-        _UNITARY_CACHE[key] = u
+        _UNITARY_CACHE[key] = False if u is None else u
     return u
 
 
