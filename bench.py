@@ -61,6 +61,25 @@ WORKLOADS['qft22'] = ('qft', dict(n=22), 0)
 WORKLOADS['qft24'] = ('qft', dict(n=24), 0)
 
 
+def quiet_stdout():
+    """Sends everything libraries write to stdout (NCCL prints a version banner
+    there) to stderr and keeps the real stdout for the ONE JSON line.  The saved
+    descriptor travels in the environment: bench.py runs as __main__, while
+    cirq_b200.dist_bench imports it a second time as `bench`."""
+    if 'B2Q_BENCH_RESULT_FD' not in os.environ:
+        sys.stdout.flush()
+        os.environ['B2Q_BENCH_RESULT_FD'] = str(os.dup(1))
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    """The bench result: one JSON line on the process's original stdout."""
+    text = (json.dumps(line) + '\n').encode()
+    sys.stdout.flush()
+    fd = os.environ.get('B2Q_BENCH_RESULT_FD')
+    os.write(int(fd) if fd is not None else 1, text)
+
+
 def workload_equivalent(value, n_sample, workload):
     """gates/s measured on an n_sample-qubit sample -> gates/s in units of the
     workload's state size (a pass over 2^m amplitudes = 2^(m-n) workload gates)."""
@@ -231,7 +250,7 @@ def run_reference_arm(args):
         'e2e': {'value': r['value'], 'unit': 'gates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_b200_arm(args):
@@ -420,7 +439,7 @@ def run_b200_arm(args):
                      'kernels': breakdown},
         'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks.summary(),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -434,6 +453,7 @@ def main():
                     help='widest fused block; default = kernel-matched policy (5 for complex64)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == 'reference':
         run_reference_arm(args)
     else:

@@ -180,6 +180,6 @@ def run(args, world, rank, local_rank):
                     'api': 'cirq_b200.dist.B200ShardedSimulator.run(circuit, repetitions)'},
             'gpu_launches': launches, 'clocks': clocks.summary(),
         }
-        print(json.dumps(line), flush=True)
+        B.emit(line)
     dist.barrier()
     dist.destroy_process_group()
