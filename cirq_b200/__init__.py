@@ -29,6 +29,7 @@ _LAZY = {
     'use_b200': 'cirq_b200.mux',
     'B200ShardedSimulator': 'cirq_b200.dist',
     'ShardedStateVector': 'cirq_b200.dist',
+    'run_sweep_sharded': 'cirq_b200.dist',
 }
 
 
