@@ -546,10 +546,15 @@ class ShardedStateVector:
 LAZY_MAX_SHARD_BITS = 31
 
 
-def plan_sharded(n_qubits: int, gates, dtype, max_fused_qubits, n_local: int):
+def plan_sharded(n_qubits: int, gates, dtype, max_fused_qubits, n_local: int, live_cls=None):
     """Host-side schedule of a gate list for the sharded path: the prefix that
     runs on small replicated sub-states (a `cirq_b200.plan` op list), the
-    sub-states to join, and the fused blocks left for the sharded state."""
+    sub-states to join, and the fused blocks left for the sharded state.
+
+    `live_cls` (a DeviceState class): the prefix is EXECUTED on device states of
+    that class while it is being scheduled instead of recorded for a later replay,
+    so the GPU works on the sub-states while the host fuses the rest of the
+    circuit (the end-to-end path; the recorded form is for plan-once / replay)."""
     from cirq_b200.fusion import fuse_gates
     from cirq_b200.plan import SplitExecutor, _RecordingState
 
@@ -564,12 +569,19 @@ def plan_sharded(n_qubits: int, gates, dtype, max_fused_qubits, n_local: int):
                 'blocks': fuse_gates(gates, max_fused_qubits, dtype, n_local, diagonal_blocks=True,
                                      permutation=perm),
                 'permutation': perm}
-    ex = SplitExecutor(n_qubits, dtype, max_fused_qubits, Rec, max_component_bits=min(n_local, 30))
+    ex = SplitExecutor(n_qubits, dtype, max_fused_qubits, live_cls or Rec,
+                       max_component_bits=min(n_local, 30))
     done = len(gates)
     for i, (m, b) in enumerate(gates):
         if not ex.apply(m, b):
             done = i
             break
+    if live_cls is not None:
+        comps = ex.components()  # live (device state, bits): launched already
+        return {'n': n_qubits, 'dtype': np.dtype(dtype), 'ops': None, 'components': comps,
+                'blocks': fuse_gates(gates[done:], max_fused_qubits, dtype, n_local, diagonal_blocks=True,
+                                     permutation=perm),
+                'permutation': perm, 'prefix_gates': done}
     comps = [(dev.ident, bits) for dev, bits in ex.components()]
     return {'n': n_qubits, 'dtype': np.dtype(dtype), 'ops': Rec.ops, 'components': comps,
             'blocks': fuse_gates(gates[done:], max_fused_qubits, dtype, n_local, diagonal_blocks=True,
@@ -582,6 +594,9 @@ def execute_sharded_plan(plan, sv: 'ShardedStateVector', device_state_cls=None) 
     if plan['components'] is None:
         sv.phys = list(range(sv.n))
         sv._init_basis(0)
+    elif plan['ops'] is None:  # scheduled live: the sub-states exist already
+        sv.load_product(plan['components'])
+        plan['components'] = []  # (release the sub-states)
     else:
         from cirq_b200.plan import replay_ops
 
@@ -664,7 +679,8 @@ class B200ShardedSimulator:
             sv.rename_bits(perm)
             return sv
         sv = ShardedStateVector(len(qubits), self.dtype, group=self.group, initial_index=None)
-        execute_sharded_plan(plan_sharded(sv.n, gates, self.dtype, self.max_fused, sv.n_local), sv)
+        execute_sharded_plan(plan_sharded(sv.n, gates, self.dtype, self.max_fused, sv.n_local,
+                                          live_cls=type(sv.local)), sv)
         return sv
 
     def run(self, circuit, repetitions: int = 1) -> dict:
@@ -680,7 +696,8 @@ class B200ShardedSimulator:
             raise ValueError('Circuit has no measurements to sample.')
         sv = ShardedStateVector(len(qubits), self.dtype, group=self.group,
                                 backend=self._backend_for(len(qubits)), initial_index=None)
-        execute_sharded_plan(plan_sharded(sv.n, gates, self.dtype, self.max_fused, sv.n_local), sv)
+        execute_sharded_plan(plan_sharded(sv.n, gates, self.dtype, self.max_fused, sv.n_local,
+                                          live_cls=type(sv.local)), sv)
         axis = {q: i for i, q in enumerate(qubits)}
         cols = [axis[q] for op in measured for q in op.qubits]
         # only the measured columns leave the device, already in result order
