@@ -3,7 +3,7 @@ classes: `cirq.Simulator` / `cirq.DensityMatrixSimulator` are replaced by
 `B200Simulator` / `B200DensityMatrixSimulator` before the reference test module
 is imported (SURVEY.md §8c "reuse plan").
 
-    python tests/ref_suite_runner.py {oracle|cuda} {sparse|density} out.json
+    python tests/ref_suite_runner.py {oracle|cuda} {sparse|density|mux} out.json
 """
 import json
 import os
@@ -45,9 +45,16 @@ def main():
     cs.Simulator = svm.B200Simulator
     cs.DensityMatrixSimulator = dmm.B200DensityMatrixSimulator
     ref_dir = os.path.join(os.path.dirname(cirq.__file__), 'sim')
-    target = os.path.join(
-        ref_dir, 'sparse_simulator_test.py' if which == 'sparse' else 'density_matrix_simulator_test.py'
-    )
+    if which == 'mux':
+        # cirq.sample / final_state_vector / final_density_matrix look their simulator
+        # classes up in these modules at call time (sim/mux.py:53-333)
+        from cirq.sim import density_matrix_simulator, sparse_simulator
+
+        sparse_simulator.Simulator = svm.B200Simulator
+        density_matrix_simulator.DensityMatrixSimulator = dmm.B200DensityMatrixSimulator
+    files = {'sparse': 'sparse_simulator_test.py', 'density': 'density_matrix_simulator_test.py',
+             'mux': 'mux_test.py'}
+    target = os.path.join(ref_dir, files[which])
     col = Collector()
     pytest.main([target, '-q', '-x' if False else '-q', '-p', 'no:cacheprovider', '-c', os.devnull,
                  '--rootdir', ref_dir, '-W', 'ignore'], plugins=[col])

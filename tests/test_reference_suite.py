@@ -1,7 +1,7 @@
 """The reference's OWN simulator test files, run against the drop-in classes
 (cirq.Simulator -> B200Simulator, cirq.DensityMatrixSimulator ->
-B200DensityMatrixSimulator): cirq-core/cirq/sim/sparse_simulator_test.py and
-density_matrix_simulator_test.py.
+B200DensityMatrixSimulator): cirq-core/cirq/sim/sparse_simulator_test.py,
+density_matrix_simulator_test.py and (host logic) mux_test.py.
 
 Every reference test must pass except the documented exclusions:
   * qudits (dimension != 2): the kernels are qubit-only;
@@ -35,8 +35,9 @@ EXPECTED_FAIL_PREFIXES = {
         'test_simulate_moment_steps_sample_qudits', 'test_simulate_with_invert_mask',
         'test_density_matrix_copy',
     ],
+    'mux': [],
 }
-MIN_PASSED = {'sparse': 178, 'density': 202}
+MIN_PASSED = {'sparse': 178, 'density': 202, 'mux': 25}
 
 
 def run_suite(backend, which, tmp_path):
@@ -62,7 +63,7 @@ def run_suite(backend, which, tmp_path):
     assert passed >= MIN_PASSED[which], f'only {passed} reference tests passed'
 
 
-@pytest.mark.parametrize('which', ['sparse', 'density'])
+@pytest.mark.parametrize('which', ['sparse', 'density', 'mux'])
 def test_reference_suite_host_logic(which, tmp_path):
     """Oracle-backed device: checks the drop-in host layer on a CPU-only box."""
     run_suite('oracle', which, tmp_path)
