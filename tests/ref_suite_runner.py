@@ -45,7 +45,7 @@ def main():
     cs.Simulator = svm.B200Simulator
     cs.DensityMatrixSimulator = dmm.B200DensityMatrixSimulator
     ref_dir = os.path.join(os.path.dirname(cirq.__file__), 'sim')
-    if which == 'mux':
+    if which == 'mux' or which.endswith('.py'):
         # cirq.sample / final_state_vector / final_density_matrix look their simulator
         # classes up in these modules at call time (sim/mux.py:53-333)
         from cirq.sim import density_matrix_simulator, sparse_simulator
@@ -54,9 +54,16 @@ def main():
         density_matrix_simulator.DensityMatrixSimulator = dmm.B200DensityMatrixSimulator
     files = {'sparse': 'sparse_simulator_test.py', 'density': 'density_matrix_simulator_test.py',
              'mux': 'mux_test.py'}
-    target = os.path.join(ref_dir, files[which])
+    if which.endswith('.py'):
+        # other reference test modules that build cirq.Simulator() /
+        # cirq.DensityMatrixSimulator() themselves: comma-separated paths relative
+        # to the cirq package
+        targets = [os.path.join(os.path.dirname(cirq.__file__), w) for w in which.split(',')]
+        ref_dir = os.path.dirname(cirq.__file__)
+    else:
+        targets = [os.path.join(ref_dir, files[which])]
     col = Collector()
-    pytest.main([target, '-q', '-x' if False else '-q', '-p', 'no:cacheprovider', '-c', os.devnull,
+    pytest.main([*targets, '-q', '-q', '-p', 'no:cacheprovider', '-c', os.devnull,
                  '--rootdir', ref_dir, '-W', 'ignore'], plugins=[col])
     with open(out, 'w') as f:
         json.dump(col.outcomes, f, indent=0)

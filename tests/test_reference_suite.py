@@ -74,3 +74,40 @@ def test_reference_suite_host_logic(which, tmp_path):
 def test_reference_suite_cuda(which, tmp_path):
     """The same reference tests through the real CUDA path."""
     run_suite('cuda', which, tmp_path)
+
+
+# Reference test modules OUTSIDE cirq/sim that build cirq.Simulator() /
+# cirq.DensityMatrixSimulator() to check gates, channels, classical control,
+# circuit operations, transformers and samplers: with the classes swapped they
+# exercise the drop-in on everything a Cirq user throws at a simulator.
+USER_MODULES = [
+    'ops/classically_controlled_operation_test.py', 'ops/common_gates_test.py', 'ops/kraus_channel_test.py',
+    'ops/mixed_unitary_channel_test.py', 'ops/pauli_measurement_gate_test.py', 'ops/if_op_test.py',
+    'ops/boolean_hamiltonian_test.py', 'circuits/circuit_operation_test.py',
+    'transformers/measurement_transformers_test.py', 'transformers/dynamical_decoupling_test.py',
+    'work/observable_measurement_test.py', 'experiments/xeb_simulation_test.py',
+]
+USER_EXPECTED_FAIL = {  # qudits: the kernels are qubit-only (DESIGN.md §7)
+    'test_sympy_qudits', 'test_xpow_dim_3', 'test_xpow_dim_4', 'test_zpow_dim_3', 'test_zpow_dim_4',
+    'test_qudits', 'test_sympy_control_complex_qudit', 'test_confusion_map_qudits', 'test_drop_terminal_qudit',
+}
+
+
+def test_reference_user_modules_host_logic(tmp_path):
+    from cirq_b200._cirq_compat import cirq_available
+
+    if not cirq_available():
+        pytest.skip('cirq is not importable here')
+    out = os.path.join(str(tmp_path), 'user_modules.json')
+    proc = subprocess.run(
+        [sys.executable, os.path.join(ROOT, 'tests', 'ref_suite_runner.py'), 'oracle', ','.join(USER_MODULES), out],
+        capture_output=True, text=True, timeout=3000,
+    )
+    assert os.path.exists(out), proc.stdout[-3000:] + proc.stderr[-3000:]
+    with open(out) as f:
+        outcomes = json.load(f)
+    failed = sorted(k for k, v in outcomes.items() if v not in ('passed', 'skipped'))
+    unexpected = [k for k in failed if k.split('[')[0] not in USER_EXPECTED_FAIL]
+    passed = sum(1 for v in outcomes.values() if v == 'passed')
+    assert not unexpected, f'unexpected reference-test failures: {unexpected}'
+    assert passed >= 560, f'only {passed} reference tests passed'  # (same-named tests of different modules count once)
