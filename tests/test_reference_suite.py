@@ -86,6 +86,9 @@ USER_MODULES = [
     'ops/boolean_hamiltonian_test.py', 'circuits/circuit_operation_test.py',
     'transformers/measurement_transformers_test.py', 'transformers/dynamical_decoupling_test.py',
     'work/observable_measurement_test.py', 'experiments/xeb_simulation_test.py',
+    'contrib/quantum_volume/quantum_volume_test.py', 'experiments/n_qubit_tomography_test.py',
+    'contrib/bayesian_network/bayesian_network_gate_test.py',
+    'transformers/analytical_decompositions/single_to_two_qubit_isometry_test.py', 'study/result_test.py',
 ]
 USER_EXPECTED_FAIL = {  # qudits: the kernels are qubit-only
     'test_sympy_qudits', 'test_xpow_dim_3', 'test_xpow_dim_4', 'test_zpow_dim_3', 'test_zpow_dim_4',
@@ -110,4 +113,4 @@ def test_reference_user_modules_host_logic(tmp_path):
     unexpected = [k for k in failed if k.split('[')[0] not in USER_EXPECTED_FAIL]
     passed = sum(1 for v in outcomes.values() if v == 'passed')
     assert not unexpected, f'unexpected reference-test failures: {unexpected}'
-    assert passed >= 560, f'only {passed} reference tests passed'  # (same-named tests of different modules count once)
+    assert passed >= 690, f'only {passed} reference tests passed'  # (same-named tests of different modules count once)
