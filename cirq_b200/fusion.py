@@ -179,6 +179,13 @@ class GateFuser:
     def __len__(self) -> int:
         return self.num_gates
 
+    @property
+    def pending(self) -> bool:
+        """Whether a flush has anything to do: queued gates, or SWAP gates that
+        were relabelled (they are not counted as gates) and still have to be
+        put back or handed over."""
+        return bool(self.num_gates or self._map)
+
     def _fits(self, union: Sequence[int]) -> bool:
         if len(union) <= self._narrow_max:
             return True

@@ -857,12 +857,15 @@ class B200Simulator(
             if batched is not None:
                 yield from batched
                 return
+        from cirq import devices
+
         resolvers = list(study.to_resolvers(params))
-        if len(resolvers) == 1:
+        if len(resolvers) == 1 and self.noise is devices.NO_NOISE:
             # a plain simulate(): nothing to share between resolvers, so the
             # reference's split into a resolver-independent prefix and the rest
             # (sim/simulator_base.py:304-320: ~40 us of Python per operation before
-            # the first gate reaches the GPU) is skipped — same result
+            # the first gate reaches the GPU) is skipped — same result (with a noise
+            # model the split decides where noise lands, so it is kept)
             yield from simulator.SimulatesIntermediateState.simulate_sweep_iter(
                 self, program, resolvers, qubit_order, initial_state)
             return

@@ -196,21 +196,31 @@ def plan_sweep(simulator, kind: str, program, resolvers, sampled: bool = True) -
         for name in names:
             if protocols.is_parameterized(r.value_of(name, recursive=True)):
                 return None
-    # the reference's split (simulator_base.py:224-244): a prefix without
-    # measurements, then a suffix that must consist of measurements only
-    prefix, suffix = split_into_matching_protocol_then_general(
-        program, lambda op: not protocols.measurement_keys_touched(op))
-    suffix_ops = list(suffix.all_operations())
+    # The reference walks the circuit in two parts and hands the noise model each
+    # part's own moments and qubits, so the split decides where noise lands:
+    #  * run_sweep (simulator_base.py:224-244): a prefix without measurements, then
+    #    a suffix that must consist of measurements only;
+    #  * simulate_sweep (simulator_base.py:304-320): a prefix of operations without
+    #    symbols (shared by the resolvers), then the rest.
     if sampled:
+        prefix, suffix = split_into_matching_protocol_then_general(
+            program, lambda op: not protocols.measurement_keys_touched(op))
+        suffix_ops = list(suffix.all_operations())
         if not suffix_ops or not all(isinstance(op.gate, ops.MeasurementGate) for op in suffix_ops):
             return None
-    elif suffix_ops or program.has_measurements():
-        return None
-    system = sorted(program.all_qubits())
+    else:
+        if program.has_measurements():
+            return None
+        prefix, suffix = split_into_matching_protocol_then_general(
+            program, lambda op: not protocols.is_parameterized(op))
+        suffix_ops = []
     for part, skip_measurements in ((prefix, False), (suffix, True)):
         if len(part) == 0:
             continue
-        for moment in noise.noisy_moments(part, system):
+        # (the reference hands the noise model the qubits of the PART it is walking,
+        # sim/simulator_base.py:196: a qubit that is only measured gets no noise
+        # during the prefix)
+        for moment in noise.noisy_moments(part, sorted(part.all_qubits())):
             for op in ops.flatten_to_ops(moment):
                 if skip_measurements and isinstance(op.gate, ops.MeasurementGate):
                     continue
@@ -239,7 +249,7 @@ def evolve_sweep(simulator, plan: SweepPlan, device_state_cls, info: dict | None
 
     def flush():
         nonlocal passes
-        if len(fuser):
+        if fuser.pending:  # (a trailing relabelled SWAP counts: blocks() puts it back)
             blocks = fuser.blocks()
             fuser.clear()
             dev.apply_batch(blocks)

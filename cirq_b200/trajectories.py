@@ -135,7 +135,7 @@ class TrajectoryBatch:
         self.fuser.add(u, list(bits))
 
     def flush(self) -> None:
-        if len(self.fuser):
+        if self.fuser.pending:  # (a trailing relabelled SWAP counts: blocks() puts it back)
             blocks = self.fuser.blocks()
             self.fuser.clear()
             self.dev.apply_batch(blocks)
