@@ -929,6 +929,13 @@ def test_differential_fuzz_batched_sweeps(cirq, SV, DM, backend):
         for g, w in zip(sim.simulate_sweep(full, sweep), ref.simulate_sweep(full, sweep)):
             assert np.max(np.abs(final(g) - final(w))) <= atol, (trial, n, dtype)
         assert sim.last_run_info.get('path') == 'batched sweep'
+        paulis = [cirq.X, cirq.Y, cirq.Z]
+        obs = [cirq.PauliString({x: paulis[rng.randint(3)] for x in q if rng.randint(2)},
+                                coefficient=float(rng.uniform(-2, 2))) for _ in range(2)]
+        obs.append(obs[0] + 0.5 * obs[1])
+        got_ev = sim.simulate_expectation_values_sweep(full, obs, sweep)
+        want_ev = ref.simulate_expectation_values_sweep(full, obs, sweep)
+        assert np.max(np.abs(np.asarray(got_ev) - np.asarray(want_ev))) <= atol * 20, (trial, n, dtype)
 
 
 def test_batched_trajectories_trailing_swap(cirq, SV):
