@@ -58,11 +58,17 @@ def _resolved_matrices(op, resolvers) -> np.ndarray | None:
             if exps is not None and np.all(exps.imag == 0):
                 e = exps.real
                 total = None
-                for half_turns, component in gate._eigen_components():
-                    phase = np.exp(1j * np.pi * e * (half_turns + shift))
-                    term = phase[:, None, None] * np.asarray(component, dtype=np.complex128)[None]
-                    total = term if total is None else total + term
-                return total
+                try:
+                    # (eigen-components may themselves depend on another symbol, e.g.
+                    # PhasedISwapPowGate(phase_exponent=a): then the generic loop below)
+                    for half_turns, component in gate._eigen_components():
+                        phase = np.exp(1j * np.pi * e * (float(half_turns) + float(shift)))
+                        term = phase[:, None, None] * np.asarray(component, dtype=np.complex128)[None]
+                        total = term if total is None else total + term
+                except (TypeError, ValueError):
+                    total = None
+                if total is not None:
+                    return total
     names = sorted(protocols.parameter_names(op))
     memo: dict = {}
     out = []
@@ -106,6 +112,7 @@ class SweepPlan:
         self.resolvers = list(resolvers)
         self.items: list[tuple] = []
         self.measurement_ops: list = []
+        self.scalar = 1.0 + 0.0j  # product of the zero-qubit (global phase) operations
         self._axis = {q: i for i, q in enumerate(self.qubits)}
         self._channel_cache: dict = {}
 
@@ -125,7 +132,16 @@ class SweepPlan:
             return False
         row, col = self._bits(op)
         if not row:
-            return not protocols.is_parameterized(op)  # global phases: no effect on samples
+            # a global phase: no effect on samples or on rho; a final STATE VECTOR
+            # carries it (simulate_sweep), so the scalar is kept for the end
+            if protocols.is_parameterized(op):
+                return False
+            if self.kind == 'sv':
+                u = protocols.unitary(op, None)
+                if u is None:
+                    return False
+                self.scalar *= complex(np.asarray(u).reshape(-1)[0])
+            return True
         if not protocols.is_parameterized(op):
             u = cached_unitary(op)
             if u is not None:
@@ -220,10 +236,18 @@ def plan_sweep(simulator, kind: str, program, resolvers, sampled: bool = True) -
         # (the reference hands the noise model the qubits of the PART it is walking,
         # sim/simulator_base.py:196: a qubit that is only measured gets no noise
         # during the prefix)
+        # (all_measurements_are_terminal walk of sim/simulator_base.py:196-209: once a
+        # qubit tuple has been measured, every later operation on exactly that tuple —
+        # the noise the model adds behind a terminal measurement — is skipped too)
+        measured: dict = {}
         for moment in noise.noisy_moments(part, sorted(part.all_qubits())):
             for op in ops.flatten_to_ops(moment):
-                if skip_measurements and isinstance(op.gate, ops.MeasurementGate):
-                    continue
+                if skip_measurements:
+                    if measured.get(op.qubits):
+                        continue
+                    if isinstance(op.gate, ops.MeasurementGate):
+                        measured[op.qubits] = True
+                        continue
                 if not plan.add_op(op):
                     return None
     plan.measurement_ops = suffix_ops
@@ -265,6 +289,8 @@ def evolve_sweep(simulator, plan: SweepPlan, device_state_cls, info: dict | None
             dev.bsv_apply_select(sb, item[1], item[2], choice)
             passes += 1
     flush()
+    if plan.scalar != 1.0:
+        dev.scale(plan.scalar)
     if info is not None:
         info.update(path='batched sweep', resolvers=P, batch_bits=b, passes=passes,
                     select_passes=sum(1 for it in plan.items if it[0] == 'select'))

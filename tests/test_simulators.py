@@ -872,11 +872,6 @@ def test_differential_fuzz_batched_sweeps(cirq, SV, DM, backend):
     two bugs when it was written: a trailing relabelled SWAP that was never put
     back, and noise applied to qubits the reference leaves alone (it hands the
     noise model the qubits of the circuit PART it is walking)."""
-    if backend == 'cuda':
-        # host-side scheduling logic; written after the round's GPU budget was spent,
-        # so the CUDA variant has not been run yet (the kernels it would reach are
-        # covered by the batched sweep tests above and test_kernels_gpu.py)
-        pytest.skip('not yet validated on a GPU box: enable next round')
     rng = np.random.RandomState(5)
     a, b = sympy.symbols('a b')
 
@@ -936,6 +931,64 @@ def test_differential_fuzz_batched_sweeps(cirq, SV, DM, backend):
         got_ev = sim.simulate_expectation_values_sweep(full, obs, sweep)
         want_ev = ref.simulate_expectation_values_sweep(full, obs, sweep)
         assert np.max(np.abs(np.asarray(got_ev) - np.asarray(want_ev))) <= atol * 20, (trial, n, dtype)
+
+
+def test_batched_sweep_noise_behind_per_qubit_measurements(cirq, DM):
+    """Terminal measure-each pattern with a noise model: the reference's terminal
+    walk (sim/simulator_base.py:203-209) skips every later operation on an already
+    measured qubit tuple — the noise layer behind the measurements included.  A
+    batched sweep has to do the same (it used to apply that noise: m0 = 0)."""
+    a = sympy.Symbol('a')
+    q0, q1 = cirq.LineQubit.range(2)
+    c = cirq.Circuit(cirq.rx(a).on(q0), cirq.rx(a).on(q1), cirq.measure(q0, key='m0'),
+                     cirq.measure(q1, key='m1'))
+    sweep = cirq.Points('a', [0.0, np.pi, 0.0])
+    noise = cirq.bit_flip(1.0)
+    want = cirq.DensityMatrixSimulator(noise=noise, seed=1).run_sweep(c, sweep, repetitions=8)
+    sim = DM(noise=noise, seed=1, sweep_batch=True)
+    got = sim.run_sweep(c, sweep, repetitions=8)
+    assert sim.last_run_info['path'] == 'batched sweep'
+    plain = DM(noise=noise, seed=1).run_sweep(c, sweep, repetitions=8)
+    for g, w, p in zip(got, want, plain):
+        for key in ('m0', 'm1'):
+            np.testing.assert_array_equal(g.measurements[key], w.measurements[key])
+            np.testing.assert_array_equal(p.measurements[key], w.measurements[key])
+
+
+def test_batched_simulate_sweep_keeps_global_phase(cirq, SV):
+    """A zero-qubit operation (global phase) is part of the final state vector of a
+    batched simulate_sweep, as in the per-resolver path and the reference."""
+    a = sympy.Symbol('a')
+    q0, q1 = cirq.LineQubit.range(2)
+    c = cirq.Circuit(cirq.rx(a).on(q0), cirq.global_phase_operation(1j), cirq.H(q1),
+                     cirq.global_phase_operation(np.exp(0.3j)))
+    sweep = cirq.Points('a', [0.1, 0.7, 2.0])
+    want = cirq.Simulator(dtype=np.complex128).simulate_sweep(c, sweep)
+    sim = SV(dtype=np.complex128, sweep_batch=True)
+    got = sim.simulate_sweep(c, sweep)
+    assert sim.last_run_info['path'] == 'batched sweep'
+    for g, w in zip(got, want):
+        np.testing.assert_allclose(g.final_state_vector, w.final_state_vector, atol=1e-12)
+
+
+def test_batched_sweep_symbolic_eigen_components(cirq, SV):
+    """EigenGates whose eigen-components depend on a second symbol
+    (PhasedISwapPowGate(phase_exponent=a, exponent=b)) take the generic
+    per-resolver resolution instead of the vectorised eigen-decomposition."""
+    a, b = sympy.symbols('a b')
+    q0, q1 = cirq.LineQubit.range(2)
+    c = cirq.Circuit(cirq.H(q0), cirq.PhasedISwapPowGate(phase_exponent=a, exponent=b).on(q0, q1),
+                     cirq.rx(b).on(q1))
+    sweep = cirq.Zip(cirq.Points('a', [0.1, 0.4, 0.9]), cirq.Points('b', [0.3, 0.5, 1.2]))
+    want = cirq.Simulator(dtype=np.complex128).simulate_sweep(c, sweep)
+    got = SV(dtype=np.complex128, sweep_batch=True).simulate_sweep(c, sweep)
+    for g, w in zip(got, want):
+        np.testing.assert_allclose(g.final_state_vector, w.final_state_vector, atol=1e-12)
+    m = c + cirq.Circuit(cirq.measure(q0, q1, key='m'))
+    want = cirq.Simulator(seed=3, split_untangled_states=False).run_sweep(m, sweep, repetitions=20)
+    got = SV(seed=3, sweep_batch=True).run_sweep(m, sweep, repetitions=20)
+    for g, w in zip(got, want):
+        np.testing.assert_array_equal(g.measurements['m'], w.measurements['m'])
 
 
 def test_batched_trajectories_trailing_swap(cirq, SV):
