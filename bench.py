@@ -4,29 +4,44 @@
 
 One "step" = one pass of the hot path over one synthetic circuit: |0..0> on the
 device, every fused gate block applied (one streaming HBM pass each), and (for
-the Sycamore-style config) 1M bitstrings sampled.  Prints ONE JSON line.
+the sampled configs) the bitstrings drawn.  Prints ONE JSON line.
+
+N = 1: the headline (`value`, `roofline`, `e2e`, `cpu_baseline`) is BASELINE
+config 2 (`rqc30`: 30-qubit Sycamore-style circuit, 1M samples); the same line
+carries `configs`: one entry per other single-GPU BASELINE config, each with its
+own `value`, `ms_per_step`, `roofline`, `e2e` and `cpu_baseline`:
+  rc20    config 1  cirq.testing.random_circuit, 20 qubits (lives in L2: latency-bound)
+  qft34   config 3  34-qubit QFT, 137 GB state
+  qaoa16  config 5  16-qubit noisy QAOA density matrix (34 GB rho), one resolver per step
+  rqc24   the sample the reference arm runs, so that ONE ratio is same-config
+N > 1 (`cirq_b200/dist_bench.py`): BASELINE config 4, the sharded state vector
+with 34 local qubits per GPU (35 / 36 / 37 qubits on 2 / 4 / 8 GPUs).
 
 value     fused gates/s with all inputs resident in HBM (plan pre-built, uniforms
           uploaded before the timed region).  The gate unit is the k<=2 fused
-          block — what cirq.merge_k_qubit_unitaries(k=2) yields (245 for the
-          30-qubit config) — so numbers are comparable with BASELINE.md even
-          though this backend fuses wider and needs fewer passes.
-e2e       the same metric through the public API a Cirq user calls:
-          B200Simulator(seed=0).run(circuit, repetitions=...) on the cirq.Circuit,
-          host scheduling, uploads and the device->host copy of the samples
-          inside the timed region.
-roofline  dominant kernel (sv_apply_fast_kernel): algorithmic bytes per launch
-          (2 * sizeof(complex) * 2^n) / mean launch duration measured with CUDA
+          block — the operation count of cirq.merge_k_qubit_unitaries(circuit,
+          k=2) (245 for the 30-qubit config) — so numbers are comparable with
+          BASELINE.md even though this backend fuses wider and needs fewer passes.
+e2e       the same metric through the public API a Cirq user calls
+          (B200Simulator.run / compute_amplitudes, B200DensityMatrixSimulator
+          .run_sweep) on the cirq.Circuit: host scheduling, uploads and the
+          device->host copy of the result inside the timed region.  `first_call_ms`
+          is the cold call (per-gate unitary cache empty), `ms_per_step` the warm one.
+roofline  dominant in-step kernel: algorithmic bytes per launch
+          (2 * sizeof(complex) * 2^bits) / mean launch duration measured with CUDA
           events around the gate passes, vs the measured copy peak.
-cpu_baseline  the reference cirq.Simulator on the box's host cores on a bounded
-          sample of the same generator (fewer qubits), timed in the same run.
-          Its gates are counted in the workload's own unit — gates on the
-          workload's state size: a gate pass over 2^m amplitudes counts as
-          2^(m-n) gates of the n-qubit workload (the same convention the N > 1
-          arm uses for its larger states); the raw number measured on the sample
-          is reported next to it.  The reference's time per gate grows at least
-          linearly in 2^n (20 -> 24 qubits: x24 for x16 amplitudes), so this
-          favours the reference.
+cpu_baseline  the reference (cirq.Simulator / cirq.DensityMatrixSimulator) on the
+          box's host cores on a bounded sample of the same generator (fewer
+          qubits), timed in the same run.  Its gates are counted in the workload's
+          own unit: a gate pass over 2^m amplitudes counts as 2^(m-n) gates of the
+          n-qubit workload; the raw number measured on the sample is reported next
+          to it.  The reference's time per gate grows at least linearly in 2^n, so
+          this favours the reference.
+
+`--impl reference` runs ONLY the unmodified reference (no library of this repo is
+loaded): its top-level value is measured on a sample (`same_config: false`,
+`extrapolated: true` in `config`), and `configs.rqc24` is the like-for-like entry
+(`same_config: true`) that the repo arm also reports.
 """
 from __future__ import annotations
 
@@ -46,19 +61,26 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (kind, params, repetitions)
     'rqc30': ('rqc', dict(rows=5, cols=6, depth=20, seed=1), 1_000_000),
-    'rqc24': ('rqc', dict(rows=4, cols=6, depth=20, seed=1), 100_000),
-    'rqc20': ('rqc', dict(rows=4, cols=5, depth=20, seed=1), 100_000),
+    'rqc24': ('rqc', dict(rows=4, cols=6, depth=20, seed=1), 10_000),
+    'rqc20': ('rqc', dict(rows=4, cols=5, depth=20, seed=1), 10_000),
     'qft34': ('qft', dict(n=34), 0),
     'qft30': ('qft', dict(n=30), 0),
+    'qft24': ('qft', dict(n=24), 0),
+    'qft22': ('qft', dict(n=22), 0),
     'rc20': ('rc', dict(n=20, depth=20, seed=1234), 0),
+    'qaoa16': ('qaoa', dict(n=16, p=2, graph_seed=0, noise=0.01, resolvers=256), 1000),
+    'qaoa12': ('qaoa', dict(n=12, p=2, graph_seed=0, noise=0.01, resolvers=256), 1000),
+    'qaoa10': ('qaoa', dict(n=10, p=2, graph_seed=0, noise=0.01, resolvers=256), 1000),
+    'qaoa8': ('qaoa', dict(n=8, p=2, graph_seed=0, noise=0.01, resolvers=256), 1000),
 }
-# bounded CPU samples (same generator, fewer qubits): ~5-20 s of reference time per step
+# bounded CPU samples (same generator, fewer qubits): ~5-20 s of reference time in all
 CPU_SAMPLE = {'rqc30': 'rqc20', 'rqc24': 'rqc20', 'rqc20': 'rqc20', 'qft34': 'qft22', 'qft30': 'qft22',
-              'qft22': 'qft22', 'rc20': 'rc20'}
+              'qft24': 'qft22', 'qft22': 'qft22', 'rc20': 'rc20', 'qaoa16': 'qaoa10', 'qaoa12': 'qaoa10',
+              'qaoa10': 'qaoa10', 'qaoa8': 'qaoa8'}
 # the reference arm (`--impl reference`) has minutes, not seconds: a larger sample
 REFERENCE_ARM_SAMPLE = dict(CPU_SAMPLE, rqc30='rqc24', qft34='qft24', qft30='qft24')
-WORKLOADS['qft22'] = ('qft', dict(n=22), 0)
-WORKLOADS['qft24'] = ('qft', dict(n=24), 0)
+# sub-entries of the N = 1 line
+SUB_CONFIGS = ('rc20', 'rqc24', 'qft34', 'qaoa16')
 
 
 def quiet_stdout():
@@ -80,12 +102,20 @@ def emit(line: dict) -> None:
     os.write(int(fd) if fd is not None else 1, text)
 
 
-def workload_equivalent(value, n_sample, workload):
-    """gates/s measured on an n_sample-qubit sample -> gates/s in units of the
-    workload's state size (a pass over 2^m amplitudes = 2^(m-n) workload gates)."""
+def workload_bits(workload):
+    """Index bits of the workload's state (2n for a density matrix)."""
     kind, params, _ = WORKLOADS[workload]
-    n = params['rows'] * params['cols'] if kind == 'rqc' else params['n']
-    return value * 2.0 ** (n_sample - n), n
+    if kind == 'rqc':
+        return params['rows'] * params['cols']
+    return 2 * params['n'] if kind == 'qaoa' else params['n']
+
+
+def workload_equivalent(value, bits_sample, workload):
+    """gates/s measured on a sample with 2^bits_sample amplitudes -> gates/s in
+    units of the workload's state size (a pass over 2^m amplitudes = 2^(m-n)
+    workload gates)."""
+    n = workload_bits(workload)
+    return value * 2.0 ** (bits_sample - n), n
 
 
 def load_peaks():
@@ -96,50 +126,75 @@ def load_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-def measured_traffic(n_qubits, kernel):
+def measured_traffic(n_bits, kernel):
     """dram read+write bytes per launch of `kernel` from the committed ncu --set
-    full captures (profiles/ncu_traffic.json), valid for 30-qubit states only."""
+    full captures (profiles/ncu_traffic.json: measured on 30-bit states; traffic
+    scales with the state size, so other sizes are scaled and marked)."""
     path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
-    if n_qubits != 30 or not os.path.exists(path):
+    if not os.path.exists(path):
         return None
     with open(path) as f:
         table = json.load(f)['bytes_per_launch_30q']
-    return table.get(kernel)
+    base = kernel.split(' ')[0]
+    got = table.get(kernel, table.get(base))
+    if got is None:
+        return None
+    return int(got * 2.0 ** (n_bits - 30))
 
 
-def kernel_class(wires):
+def kernel_class(wires, n_bits=30):
     """Name of the kernel a fused block on these index bits runs on (complex64,
     default knobs: b2q_apply_tc.cu launch_tc_k / b2q_apply.cu apply_matrix_t)."""
     k = len(wires)
     tc4 = os.environ.get('CIRQ_B200_TC_MODE') == '2'  # opt-in: 4-qubit blocks on tcgen05 too
-    if k == 5 or (k == 4 and tc4):
+    if n_bits >= k + 7 and (k == 5 or (k == 4 and tc4)):
         return f'sv_apply_tc_staged_kernel<{k}>' if min(wires) < 2 else f'sv_apply_tc_kernel<{k}>'
-    if k == 6:
+    if k == 6 and n_bits >= 13:
         return 'sv_apply_tc_kernel<6>'
     return f'sv_apply_fast_kernel<float,{k}>'
 
 
-def build_workload(name):
-    """Returns dict(circuit, qubits, gates, n, reps, generator)."""
-    from cirq_b200 import workloads as W
-    from cirq_b200._cirq_compat import cirq_available
+def block_kernel_name(m, w, n_bits):
+    """(kernel name, blocks in the launch) of one scheduled item."""
+    if isinstance(m, (tuple, list)):  # a tile group: several blocks in one pass
+        return f'sv_apply_tc_tile_kernel<{len(m)} blocks>', len(m)
+    if np.ndim(m) == 1:
+        return 'sv_apply_diag_smem_kernel<float>', 1
+    return kernel_class(w, n_bits), 1
 
+
+def ref_unit_gates(cirq, circuit):
+    """Gate unit of the metric: operations left by the reference's own fuser,
+    cirq.merge_k_qubit_unitaries(k=2) (transformers/merge_k_qubit_gates.py:70-114),
+    on the circuit without its measurements.  Needs nothing but cirq."""
+    body = cirq.Circuit(op for op in circuit.all_operations() if not cirq.is_measurement(op))
+    return sum(1 for _ in cirq.merge_k_qubit_unitaries(body, k=2).all_operations())
+
+
+def build_workload(name):
+    """Returns dict(kind, circuit, qubits, n, bits, reps, unit_gates, ...); cirq only."""
+    from cirq_b200 import workloads as W
+    from cirq_b200._cirq_compat import import_cirq
+
+    cirq = import_cirq()
     kind, params, reps = WORKLOADS[name]
-    if not cirq_available():
-        if kind != 'rqc':
-            raise RuntimeError('cirq is not importable and only the rqc workload has a builtin generator')
-        gates = W.builtin_rqc_gates(**params)
-        return dict(circuit=None, qubits=None, gates=gates, n=params['rows'] * params['cols'],
-                    reps=reps, generator='builtin (cirq not importable)')
+    out = dict(kind=kind, name=name, reps=reps, generator='cirq ' + kind)
+    if kind == 'qaoa':
+        circuit, qubits, names = W.qaoa_circuit(params['n'], params['p'], params['graph_seed'])
+        resolvers = list(cirq.to_resolvers(W.qaoa_sweep(names, params['resolvers'])))
+        out.update(circuit=circuit, qubits=list(qubits), resolvers=resolvers, noise_p=params['noise'],
+                   n=len(qubits), bits=2 * len(qubits),
+                   unit_gates=ref_unit_gates(cirq, cirq.resolve_parameters(circuit, resolvers[0])))
+        return out
     if kind == 'rqc':
         circuit, qubits = W.rqc_circuit(**params)
     elif kind == 'qft':
         circuit, qubits = W.qft_circuit(**params)
     else:
         circuit, qubits = W.random_circuit(**params)
-    gates = W.circuit_to_gates(circuit, qubits)
-    return dict(circuit=circuit, qubits=qubits, gates=gates, n=len(qubits), reps=reps,
-                generator='cirq ' + kind)
+    out.update(circuit=circuit, qubits=list(qubits), n=len(qubits), bits=len(qubits),
+               unit_gates=ref_unit_gates(cirq, circuit))
+    return out
 
 
 class ClockSampler:
@@ -188,26 +243,40 @@ class ClockSampler:
                 'samples': len(self.samples)}
 
 
+# ---- the reference on the host cores -------------------------------------------------------
+
+_REF_CACHE: dict = {}
+
+
 def time_reference(name, steps, warmup):
-    """Times the unmodified reference (cirq.Simulator, numpy) on the host."""
+    """Times the unmodified reference (cirq.Simulator / cirq.DensityMatrixSimulator,
+    numpy) on the host; nothing of this repo's library is involved."""
+    key = (name, steps, warmup)
+    if key in _REF_CACHE:
+        return _REF_CACHE[key]
     from cirq_b200._cirq_compat import import_cirq
-    from cirq_b200.fusion import fuse_gates
 
     cirq = import_cirq()
     wl = build_workload(name)
     circuit, qubits, reps = wl['circuit'], wl['qubits'], wl['reps']
-    unit_gates = len(fuse_gates(wl['gates'], 2))
-    run_circuit = circuit
-    reps_ref = min(reps, 10_000)
-    if reps:
-        run_circuit = circuit + cirq.Circuit(cirq.measure(*qubits, key='m'))
+    if wl['kind'] == 'qaoa':
+        resolvers = wl['resolvers']
+        state = {'i': 0}
 
-    def step():
-        sim = cirq.Simulator(dtype=np.complex64, seed=0)
-        if reps:
-            sim.run(run_circuit, repetitions=reps_ref)
-        else:
-            sim.simulate(run_circuit, qubit_order=qubits)
+        def step():
+            sim = cirq.DensityMatrixSimulator(dtype=np.complex64, noise=cirq.depolarize(wl['noise_p']), seed=0)
+            r = resolvers[state['i'] % len(resolvers)]
+            state['i'] += 1
+            sim.run_sweep(circuit, [r], repetitions=reps)
+    else:
+        run_circuit = circuit + cirq.Circuit(cirq.measure(*qubits, key='m')) if reps else circuit
+
+        def step():
+            sim = cirq.Simulator(dtype=np.complex64, seed=0)
+            if reps:
+                sim.run(run_circuit, repetitions=reps)
+            else:
+                sim.simulate(run_circuit, qubit_order=qubits)
 
     for _ in range(warmup):
         step()
@@ -215,83 +284,138 @@ def time_reference(name, steps, warmup):
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return dict(value=unit_gates / dt, seconds_per_step=dt, unit_gates=unit_gates, n=wl['n'],
-                raw_ops=len(wl['gates']), reps=reps_ref)
+    out = dict(value=wl['unit_gates'] / dt, seconds_per_step=dt, unit_gates=wl['unit_gates'], n=wl['n'],
+               bits=wl['bits'], raw_ops=sum(1 for _ in circuit.all_operations()), reps=reps, steps=steps)
+    _REF_CACHE[key] = out
+    return out
+
+
+def cpu_baseline_for(workload, steps=3):
+    """cpu_baseline object of `workload`: the reference on CPU_SAMPLE[workload]."""
+    try:
+        sample = CPU_SAMPLE[workload]
+        r = time_reference(sample, steps, 0)
+        eq, n = workload_equivalent(r['value'], r['bits'], workload)
+        api = 'cirq.DensityMatrixSimulator(noise=depolarize).run_sweep, one resolver per step' \
+            if WORKLOADS[sample][0] == 'qaoa' else 'cirq.Simulator(complex64)'
+        return {'value': eq, 'unit': 'gates/s', 'cores': 1, 'kind': 'reference',
+                'raw_value_on_sample': r['value'], 'same_config': sample == workload,
+                'sample': f"{api} on {sample}: {r['n']} qubits, {r['raw_ops']} ops = {r['unit_gates']} k<=2 "
+                          f"blocks, {r['reps']} repetitions, {r['steps']} x {r['seconds_per_step']:.2f} s: "
+                          f"{r['value']:.3g} gates/s there, counted as {n}-bit-equivalent gates "
+                          f"(x 2^({r['bits']}-{n})); single-threaded numpy, host has {os.cpu_count()} cores"}
+    except Exception as exc:  # reference not importable on this box
+        return {'value': None, 'unit': 'gates/s', 'cores': 1, 'kind': 'reference',
+                'sample': f'unavailable: {exc!r}'}
+
+
+def reference_entry(sample, workload, steps, warmup):
+    """One reference measurement as a (sub-)line: value in `workload` units."""
+    r = time_reference(sample, steps, warmup)
+    value, n = workload_equivalent(r['value'], r['bits'], workload)
+    same = sample == workload
+    return {
+        'impl': 'reference', 'metric': 'fused_gates_per_s', 'value': value, 'unit': 'gates/s',
+        'steps': steps, 'warmup': warmup, 'ms_per_step': r['seconds_per_step'] * 1e3,
+        'higher_is_better': True, 'dtype': 'c64', 'data': 'synthetic',
+        'config': {'workload': workload, 'gate_unit': 'k<=2 fused blocks (cirq.merge_k_qubit_unitaries(k=2) count)',
+                   'same_config': same, 'extrapolated': not same,
+                   'reference_sample': sample, 'n_qubits': r['n'], 'raw_ops': r['raw_ops'],
+                   'unit_gates': r['unit_gates'], 'repetitions': r['reps'],
+                   'gates_per_s_on_sample': r['value'],
+                   'value_unit': ('gates/s on the workload itself' if same else
+                                  f"{n}-bit-equivalent gates/s = gates/s on the {r['bits']}-bit sample "
+                                  f"x 2^({r['bits']}-{n})")},
+        'cpu_baseline': {'value': value, 'unit': 'gates/s', 'cores': 1, 'kind': 'reference',
+                         'raw_value_on_sample': r['value'], 'same_config': same,
+                         'sample': f"the reference on {sample} ({r['n']} qubits, same generator, "
+                                   f"{r['seconds_per_step']:.1f} s per step): {r['value']:.3g} gates/s there"
+                                   + ('' if same else f", counted as {n}-bit-equivalent gates "
+                                                      f"(x 2^({r['bits']}-{n}))")
+                                   + f"; numpy path is single-threaded; host has {os.cpu_count()} cores"},
+        'e2e': {'value': value, 'unit': 'gates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    sample = REFERENCE_ARM_SAMPLE[args.workload]
-    big = sample != CPU_SAMPLE[args.workload]  # ~90 s per step: keep the run within minutes
+    workload = 'rqc30' if args.workload in (None, 'rc_hbm', 'rqc_weak') else args.workload
+    sample = REFERENCE_ARM_SAMPLE[workload]
+    big = sample != CPU_SAMPLE[workload]  # ~55 s per step: keep the run within minutes
     steps = max(1, min(args.steps, 2 if big else 3))
     warmup = 0 if big else min(args.warmup, 1)
-    r = time_reference(sample, steps, warmup)
-    raw = r['value']
-    r['value'], n_workload = workload_equivalent(raw, r['n'], args.workload)
-    line = {
-        'impl': 'reference', 'metric': 'fused_gates_per_s', 'value': r['value'], 'unit': 'gates/s',
-        'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup,
-        'ms_per_step': r['seconds_per_step'] * 1e3, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'c64', 'data': 'synthetic',
-        'config': {'workload': args.workload, 'gate_unit': 'k<=2 fused blocks',
-                   'reference_sample': sample, 'n_qubits': r['n'], 'raw_ops': r['raw_ops'],
-                   'unit_gates': r['unit_gates'], 'repetitions': r['reps'],
-                   'gates_per_s_on_sample': raw,
-                   'value_unit': f"{n_workload}-qubit-equivalent gates/s = gates/s on the "
-                                 f"{r['n']}-qubit sample x 2^({r['n']}-{n_workload})"},
-        'cpu_baseline': {'value': r['value'], 'unit': 'gates/s', 'cores': 1, 'kind': 'reference',
-                         'raw_value_on_sample': raw,
-                         'sample': f"cirq.Simulator(complex64) on {sample} ({r['n']} qubits, same generator, "
-                                   f"{r['seconds_per_step']:.1f} s per step): {raw:.3g} gates/s there, counted as "
-                                   f"{n_workload}-qubit-equivalent gates (x 2^({r['n']}-{n_workload})); "
-                                   f"numpy path is single-threaded; host has {os.cpu_count()} cores"},
-        'e2e': {'value': r['value'], 'unit': 'gates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'gpu_launches': 0,
-    }
+    line = reference_entry(sample, workload, steps, warmup)
+    line.update({'n_gpus': args.gpus, 'scaling': 'weak', 'vs_baseline': None, 'gpu_launches': 0})
+    if sample != workload:
+        # the like-for-like entry: the repo arm reports configs[sample] on the SAME
+        # circuit, repetitions and gate unit (no extrapolation)
+        sub = reference_entry(sample, sample, steps, warmup)
+        line['configs'] = {sample: sub}
     emit(line)
 
 
-def run_b200_arm(args):
+# ---- the B200 arm, one GPU -----------------------------------------------------------------
+
+
+def _roofline(per_kernel, record_steps, bytes_per_launch, n_bits, peak_gbs, peak_src):
+    total_ms = sum(np.sum(v) for v in per_kernel.values())
+    count = sum(len(v) for v in per_kernel.values())
+    breakdown = {k: {'launches_per_step': len(v) // record_steps, 'ms_per_launch': float(np.mean(v)),
+                     'share_of_gate_time': float(np.sum(v) / total_ms)} for k, v in per_kernel.items()}
+    dominant = max(breakdown, key=lambda k: breakdown[k]['share_of_gate_time'])
+    pass_ms = breakdown[dominant]['ms_per_launch']
+    achieved = bytes_per_launch / (pass_ms * 1e-3) / 1e9
+    return {'bound': 'hbm', 'achieved': achieved, 'peak': peak_gbs, 'unit': 'GB/s',
+            'frac': achieved / peak_gbs, 'traffic': measured_traffic(n_bits, dominant), 'kernel': dominant,
+            'peak_source': peak_src, 'bytes_per_launch': bytes_per_launch, 'ms_per_launch': pass_ms,
+            'mean_ms_over_all_passes': float(total_ms / max(1, count)),
+            'frac_over_all_passes': float(bytes_per_launch / (total_ms / max(1, count) * 1e-3) / 1e9 / peak_gbs),
+            'kernels': breakdown}, count // record_steps
+
+
+def _time_e2e(fn, steps):
     import torch
-    import torch.distributed as dist
 
-    from cirq_b200 import _lib
-    from cirq_b200.device_state import DeviceState
-    from cirq_b200.fusion import fuse_gates
+    torch.cuda.empty_cache()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    fn()
+    torch.cuda.synchronize()
+    first = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / steps, first
 
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    if world > 1:
-        from cirq_b200 import dist_bench
 
-        dist_bench.run(args, world, rank, local_rank)
-        return
+def measure_sv(name, steps, warmup, args, local_rank=0):
+    """One state-vector workload on one GPU: device-resident value, per-kernel
+    roofline, e2e through B200Simulator, cpu_baseline."""
+    import ctypes
+
+    import torch
+
+    from cirq_b200 import _lib, workloads as W
+    from cirq_b200.plan import build_plan, replay_plan
 
     lib = _lib.load()
     peak_gbs, peak_src = load_peaks()
-    wl = build_workload(args.workload)
-    n, reps, gates = wl['n'], wl['reps'], wl['gates']
-    unit_gates = len(fuse_gates(gates, 2))
+    wl = build_workload(name)
+    n, reps = wl['n'], wl['reps']
+    gates = W.circuit_to_gates(wl['circuit'], wl['qubits'])
+    unit_gates = wl['unit_gates']
     dtype = np.complex64
-    from cirq_b200.plan import build_plan, replay_plan
-
     # Host scheduling happens ONCE, outside the timed region: fusion + lazy state
     # growth (sub-states joined by the kron kernel, as with split_untangled_states).
     plan = build_plan(n, gates, dtype, args.max_fused)
-    full_blocks = [blk for op in plan['ops'] if op[0] == 'apply' for blk in op[2]]
+    blocks = [blk for op in plan['ops'] if op[0] == 'apply' for blk in op[2]]
     state_bytes = (8 << n)
     rng = np.random.RandomState(0)
     uniforms = rng.random_sample(max(reps, 1))
     u_dev = torch.from_numpy(uniforms).to('cuda')
-
-    import ctypes
-
     ws_bytes = int(lib.b2q_sv_sample_workspace_bytes(n, reps)) if reps else 16
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device='cuda')
     out_idx = torch.empty(max(reps, 1), dtype=torch.int64, device='cuda')
@@ -299,22 +423,16 @@ def run_b200_arm(args):
     # column a of the samples = logical qubit axis a = logical bit n-1-a
     bits_order = _lib.int_array([plan['bit_of'][n - 1 - a] for a in range(n)])
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    per_kernel = {}
+    per_kernel: dict = {}
+    pairs: list = []
 
-    def timed_apply(state, blocks):
-        for m, w in blocks:
+    def timed_apply(state, blks):
+        for m, w in blks:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            if np.ndim(m) == 1:  # a diagonal block (its table in shared memory)
-                state.apply_diagonal(m, w)
-                name = 'sv_apply_diag_smem_kernel<float>'
-            else:
-                state.apply_matrix(m, w)
-                name = kernel_class(w)
+            state.apply_batch([(m, w)])
             b.record()
-            timed_apply.pairs.append((state.n_bits, name, a, b))
-
-    timed_apply.pairs = []
+            pairs.append((state.n_bits, block_kernel_name(m, w, state.n_bits)[0], a, b))
 
     def step(record=False):
         dev = replay_plan(plan, on_apply=timed_apply if record else None)
@@ -326,13 +444,13 @@ def run_b200_arm(args):
                                            ctypes.c_void_p(out_bits.data_ptr()), stream))
         if record:
             torch.cuda.synchronize()
-            for nb, name, a, b in timed_apply.pairs:
+            for nb, kname, a, b in pairs:
                 if nb == n:  # launches on the full-size state: the HBM-bound ones
-                    per_kernel.setdefault(name, []).append(a.elapsed_time(b))
-            timed_apply.pairs = []
+                    per_kernel.setdefault(kname, []).append(a.elapsed_time(b))
+            pairs.clear()
         del dev
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     torch.cuda.synchronize()
     launches0 = int(lib.b2q_launch_count())
@@ -340,105 +458,263 @@ def run_b200_arm(args):
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         start.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             step()
         end.record()
         torch.cuda.synchronize()
-        ms_per_step = start.elapsed_time(end) / args.steps
-        launches = (int(lib.b2q_launch_count()) - launches0) // max(args.steps, 1)
+        ms_per_step = start.elapsed_time(end) / steps
+        launches = (int(lib.b2q_launch_count()) - launches0) // max(steps, 1)
         # per-kernel duration of the gate passes (separate, event-bracketed steps)
-        record_steps = min(3, args.steps)
+        record_steps = min(3, steps)
         for _ in range(record_steps):
             step(record=True)
-    total_gate_ms = sum(np.sum(v) for v in per_kernel.values())
-    full_passes = sum(len(v) for v in per_kernel.values()) // record_steps
-    mean_pass_ms = float(total_gate_ms / max(1, sum(len(v) for v in per_kernel.values())))
-    breakdown = {k: {'launches_per_step': len(v) // record_steps,
-                     'ms_per_launch': float(np.mean(v)),
-                     'share_of_gate_time': float(np.sum(v) / total_gate_ms)}
-                 for k, v in per_kernel.items()}
-    dominant = max(breakdown, key=lambda k: breakdown[k]['share_of_gate_time'])
-    pass_ms = breakdown[dominant]['ms_per_launch']
-    achieved = 2 * state_bytes / (pass_ms * 1e-3) / 1e9
+    roofline, full_passes = _roofline(per_kernel, record_steps, 2 * state_bytes, n, peak_gbs, peak_src)
     value = unit_gates / (ms_per_step * 1e-3)
-    blocks = full_blocks
+    del u_dev, ws, out_idx, out_bits
+    torch.cuda.empty_cache()
 
     # ---- e2e through the public Cirq-facing API -------------------------------------------
-    e2e = None
-    if wl['circuit'] is not None:
-        from cirq_b200._cirq_compat import import_cirq
+    from cirq_b200._cirq_compat import import_cirq
 
-        cirq = import_cirq()
-        import cirq_b200
+    cirq = import_cirq()
+    import cirq_b200
 
-        circuit = wl['circuit']
+    circuit = wl['circuit']
+    if reps:
+        circuit = circuit + cirq.Circuit(cirq.measure(*wl['qubits'], key='m'))
+    e2e_steps = max(1, min(steps, 3))
+
+    def e2e_step():
+        sim = cirq_b200.B200Simulator(dtype=dtype, seed=0, max_fused_qubits=args.max_fused)
         if reps:
-            circuit = circuit + cirq.Circuit(cirq.measure(*wl['qubits'], key='m'))
-        e2e_steps = max(1, min(args.steps, 3))
+            res = sim.run(circuit, repetitions=reps)
+            return res.measurements['m'].shape
+        # the reference's own API for reading a few amplitudes of a state too
+        # large to download (SimulatesAmplitudes, sim/simulator.py:120-182)
+        return sim.compute_amplitudes(circuit, [0, 1], qubit_order=wl['qubits'])
 
-        def e2e_step():
-            sim = cirq_b200.B200Simulator(dtype=dtype, seed=0, max_fused_qubits=args.max_fused)
-            if reps:
-                res = sim.run(circuit, repetitions=reps)
-                return res.measurements['m'].shape
-            # the reference's own API for reading a few amplitudes of a state too
-            # large to download (SimulatesAmplitudes, sim/simulator.py:120-182)
-            return sim.compute_amplitudes(circuit, [0, 1], qubit_order=wl['qubits'])
+    dt, first = _time_e2e(e2e_step, e2e_steps)
+    mat_bytes = int(sum(16 * np.size(m) for m, _ in _flat_blocks(blocks)))
+    e2e = {'value': unit_gates / dt, 'unit': 'gates/s', 'ms_per_step': dt * 1e3, 'first_call_ms': first * 1e3,
+           'h2d_bytes_per_step': int(8 * reps + mat_bytes),
+           'd2h_bytes_per_step': int(reps * n if reps else 32),
+           'api': 'cirq_b200.B200Simulator(seed=0).run(circuit, repetitions)' if reps
+                  else 'cirq_b200.B200Simulator().compute_amplitudes(circuit, [0, 1])'}
+    torch.cuda.empty_cache()
 
-        torch.cuda.empty_cache()
-        e2e_step()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / e2e_steps
-        mat_bytes = int(sum(16 * m.size for m, _ in blocks))
-        e2e = {'value': unit_gates / dt, 'unit': 'gates/s', 'ms_per_step': dt * 1e3,
-               'h2d_bytes_per_step': int(8 * reps + mat_bytes),
-               'd2h_bytes_per_step': int(reps * n if reps else 32),
-               'api': 'cirq_b200.B200Simulator(seed=0).run(circuit, repetitions)' if reps
-                      else 'cirq_b200.B200Simulator().compute_amplitudes(circuit, [0, 1])'}
-
-    # ---- CPU baseline (reference on host cores, bounded sample) ---------------------------
-    cpu = None
-    if not args.no_cpu_baseline:
-        try:
-            sample = CPU_SAMPLE[args.workload]
-            r = time_reference(sample, 3, 0)
-            eq, _ = workload_equivalent(r['value'], r['n'], args.workload)
-            cpu = {'value': eq, 'unit': 'gates/s', 'cores': 1, 'kind': 'reference',
-                   'raw_value_on_sample': r['value'],
-                   'sample': f"cirq.Simulator(complex64) on {sample}: {r['n']} qubits, {r['raw_ops']} ops = "
-                             f"{r['unit_gates']} k<=2 blocks, {r['reps']} repetitions, 3 x {r['seconds_per_step']:.2f} s: "
-                             f"{r['value']:.3g} gates/s there, counted as {n}-qubit-equivalent gates "
-                             f"(x 2^({r['n']}-{n})); single-threaded numpy, host has {os.cpu_count()} cores"}
-        except Exception as exc:  # reference not importable on this box
-            cpu = {'value': None, 'unit': 'gates/s', 'cores': 1, 'kind': 'reference',
-                   'sample': f'unavailable: {exc}'}
-
-    line = {
-        'metric': 'fused_gates_per_s', 'value': value, 'unit': 'gates/s', 'n_gpus': 1,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'c64',
-        'data': 'synthetic',
-        'config': {'workload': args.workload, 'generator': wl['generator'], 'n_qubits': n,
-                   'raw_ops': len(gates), 'gate_unit': 'k<=2 fused blocks (reference merge_k_qubit_unitaries(k=2) count)',
-                   'unit_gates': unit_gates, 'max_fused_qubits': max(len(w) for m, w in blocks if np.ndim(m) == 2),
-                   'diagonal_passes_per_step': sum(1 for m, _ in blocks if np.ndim(m) == 1),
-                   'passes_per_step': len(blocks), 'full_size_passes_per_step': full_passes,
-                   'schedule': 'fusion + lazy state growth (kron-joined sub-states), planned once outside the timed region',
-                   'repetitions': reps,
-                   'state_bytes': state_bytes,
+    flat = _flat_blocks(blocks)
+    dense_widths = [len(w) for m, w in flat if np.ndim(m) == 2]
+    return {
+        'metric': 'fused_gates_per_s', 'value': value, 'unit': 'gates/s', 'steps': steps, 'warmup': warmup,
+        'ms_per_step': ms_per_step, 'dtype': 'c64',
+        'config': {'workload': name, 'generator': wl['generator'], 'n_qubits': n,
+                   'raw_ops': len(gates),
+                   'gate_unit': 'k<=2 fused blocks (cirq.merge_k_qubit_unitaries(k=2) count)',
+                   'unit_gates': unit_gates, 'max_fused_qubits': max(dense_widths) if dense_widths else 0,
+                   'diagonal_passes_per_step': sum(1 for m, _ in flat if np.ndim(m) == 1),
+                   'blocks_per_step': len(flat), 'launches_per_step_gate_passes': len(blocks),
+                   'full_size_passes_per_step': full_passes,
+                   'schedule': 'fusion + lazy state growth (kron-joined sub-states) + tile groups, planned '
+                               'once outside the timed region',
+                   'repetitions': reps, 'state_bytes': state_bytes,
                    'l2': 'inputs larger than L2 (state %.1f GB vs 126 MB)' % (state_bytes / 1e9)
                          if state_bytes > 252e6 else 'state fits L2; not an HBM measurement'},
-        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak_gbs, 'unit': 'GB/s',
-                     'frac': achieved / peak_gbs, 'traffic': measured_traffic(n, dominant), 'kernel': dominant,
-                     'peak_source': peak_src, 'bytes_per_launch': 2 * state_bytes,
-                     'ms_per_launch': pass_ms, 'mean_ms_over_all_passes': mean_pass_ms,
-                     'kernels': breakdown},
-        'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks.summary(),
+        'roofline': roofline, 'cpu_baseline': None if args.no_cpu_baseline else cpu_baseline_for(name),
+        'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks.summary(),
     }
+
+
+def _flat_blocks(blocks):
+    """Scheduled items with tile groups expanded to their member blocks."""
+    out = []
+    for m, w in blocks:
+        if isinstance(m, (tuple, list)):
+            out.extend(m)
+        else:
+            out.append((m, w))
+    return out
+
+
+def dm_gate_list(cirq, wl, resolver):
+    """[(matrix, bits)] over the 2n index bits of rho for one resolver, exactly what
+    B200DensityMatrixSimulator queues (U on the row bits + conj(U) on the column
+    bits, a channel as its superoperator), built by the sweep planner's walk."""
+    from cirq_b200.sweeps import SweepPlan
+
+    resolved = cirq.resolve_parameters(wl['circuit'], resolver)
+    body = cirq.Circuit(op for op in resolved.all_operations() if not cirq.is_measurement(op))
+    noise = cirq.ConstantQubitNoiseModel(cirq.depolarize(wl['noise_p']))
+    plan = SweepPlan('dm', wl['qubits'], [resolver])
+    for moment in noise.noisy_moments(body, sorted(body.all_qubits())):
+        for op in cirq.flatten_to_ops(moment):
+            if not plan.add_op(op):
+                raise RuntimeError(f'cannot schedule {op!r}')
+    return [(item[1], list(item[2])) for item in plan.items]
+
+
+def measure_dm(name, steps, warmup, args, local_rank=0):
+    """Config 5: noisy QAOA on a density matrix; one step = one resolver of the
+    sweep (rho evolved from |0><0| + `repetitions` samples of the diagonal)."""
+    import torch
+
+    import cirq_b200
+    from cirq_b200 import _lib
+    from cirq_b200._cirq_compat import import_cirq
+    from cirq_b200.device_state import DeviceState
+    from cirq_b200.fusion import fuser_for
+
+    cirq = import_cirq()
+    lib = _lib.load()
+    peak_gbs, peak_src = load_peaks()
+    wl = build_workload(name)
+    n, bits, reps = wl['n'], wl['bits'], wl['reps']
+    dtype = np.complex64
+    resolvers = wl['resolvers']
+    unit_gates = wl['unit_gates']
+    max_fused = 4 if args.max_fused is None else args.max_fused
+
+    def schedule(resolver):
+        f = fuser_for(dtype, max_fused, bits)
+        for m, b in dm_gate_list(cirq, wl, resolver):
+            f.add(m, b)
+        return f.blocks()
+
+    # one schedule per step's resolver, built outside the timed region
+    plans = [schedule(resolvers[(i * 37) % len(resolvers)]) for i in range(min(4, max(steps, 1)))]
+    state_bytes = 8 << bits
+    rng = np.random.RandomState(0)
+    uniforms = rng.random_sample(reps)
+    meas_bits = list(range(n - 1, -1, -1))
+    per_kernel: dict = {}
+    pairs: list = []
+
+    def step(i, record=False):
+        dev = DeviceState.basis(bits, dtype, 0)
+        for m, w in plans[i % len(plans)]:
+            if record:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+            dev.apply_batch([(m, w)])
+            if record:
+                b.record()
+                pairs.append((block_kernel_name(m, w, bits)[0], a, b))
+        probs = dev.dm_diagonal_device()
+        idx = DeviceState.cdf_sample_device(DeviceState.probs_marginal_device(probs, n, meas_bits), uniforms)
+        out = DeviceState.unpack_bits_device(idx, [n - 1 - c for c in range(n)])
+        if record:
+            torch.cuda.synchronize()
+            for kname, a, b in pairs:
+                per_kernel.setdefault(kname, []).append(a.elapsed_time(b))
+            pairs.clear()
+        del dev, out
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    launches0 = int(lib.b2q_launch_count())
+    with ClockSampler(local_rank) as clocks:
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for i in range(steps):
+            step(i)
+        end.record()
+        torch.cuda.synchronize()
+        ms_per_step = start.elapsed_time(end) / steps
+        launches = (int(lib.b2q_launch_count()) - launches0) // max(steps, 1)
+        record_steps = min(2, steps)
+        for i in range(record_steps):
+            step(i, record=True)
+    roofline, passes = _roofline(per_kernel, record_steps, 2 * state_bytes, bits, peak_gbs, peak_src)
+    value = unit_gates / (ms_per_step * 1e-3)
+    torch.cuda.empty_cache()
+
+    # e2e: the public sweep API on the first resolvers (measurement records to the host)
+    e2e_res = 2
+    circuit = wl['circuit']
+
+    def e2e_step():
+        sim = cirq_b200.B200DensityMatrixSimulator(noise=cirq.depolarize(wl['noise_p']), seed=0, dtype=dtype)
+        res = sim.run_sweep(circuit, resolvers[:e2e_res], repetitions=reps)
+        return [r.measurements['m'].shape for r in res]
+
+    dt, first = _time_e2e(e2e_step, 1)
+    dt /= e2e_res
+    mat_bytes = int(sum(16 * np.size(m) for m, _ in _flat_blocks(plans[0])))
+    e2e = {'value': unit_gates / dt, 'unit': 'gates/s', 'ms_per_step': dt * 1e3,
+           'first_call_ms': first * 1e3 / e2e_res,
+           'h2d_bytes_per_step': int(8 * reps + mat_bytes), 'd2h_bytes_per_step': int(reps * n),
+           'api': f'cirq_b200.B200DensityMatrixSimulator(noise=depolarize({wl["noise_p"]}), seed=0)'
+                  f'.run_sweep(circuit, resolvers[:{e2e_res}], repetitions={reps}), per resolver'}
+    torch.cuda.empty_cache()
+    flat = _flat_blocks(plans[0])
+    return {
+        'metric': 'fused_gates_per_s', 'value': value, 'unit': 'gates/s', 'steps': steps, 'warmup': warmup,
+        'ms_per_step': ms_per_step, 'dtype': 'c64',
+        'config': {'workload': name, 'generator': 'examples/qaoa.py qaoa_max_cut_circuit, random 3-regular graph',
+                   'n_qubits': n, 'state_bits': bits, 'noise': f'depolarize({wl["noise_p"]}) after every moment',
+                   'step': 'one resolver of the 256-point sweep: rho from |0><0| + sampling',
+                   'resolvers_in_sweep': len(resolvers),
+                   'resolvers_per_s': 1e3 / ms_per_step,
+                   'full_sweep_seconds_estimate': len(resolvers) * ms_per_step / 1e3,
+                   'gate_unit': 'k<=2 fused blocks of the noiseless circuit (cirq.merge_k_qubit_unitaries(k=2) count)',
+                   'unit_gates': unit_gates, 'blocks_per_step': len(flat),
+                   'full_size_passes_per_step': passes,
+                   'max_fused_bits': max(len(w) for m, w in flat if np.ndim(m) == 2),
+                   'repetitions': reps, 'state_bytes': state_bytes,
+                   'l2': 'inputs larger than L2 (rho %.1f GB vs 126 MB)' % (state_bytes / 1e9)},
+        'roofline': roofline, 'cpu_baseline': None if args.no_cpu_baseline else cpu_baseline_for(name, steps=1),
+        'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks.summary(),
+    }
+
+
+def measure(name, steps, warmup, args, local_rank=0):
+    if WORKLOADS[name][0] == 'qaoa':
+        return measure_dm(name, steps, warmup, args, local_rank)
+    return measure_sv(name, steps, warmup, args, local_rank)
+
+
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        from cirq_b200 import dist_bench
+
+        dist_bench.run(args, world, rank, local_rank)
+        return
+
+    workload = args.workload or 'rqc30'
+    if workload in ('rc_hbm', 'rqc_weak'):
+        raise SystemExit(f'--workload {workload} is the sharded path: launch with --gpus N > 1 under torchrun')
+    head = measure(workload, args.steps, args.warmup, args, local_rank)
+    line = {
+        'metric': head['metric'], 'value': head['value'], 'unit': head['unit'], 'n_gpus': 1,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': head['ms_per_step'],
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'c64',
+        'data': 'synthetic', 'config': head['config'], 'roofline': head['roofline'],
+        'cpu_baseline': head['cpu_baseline'], 'e2e': head['e2e'], 'gpu_launches': head['gpu_launches'],
+        'clocks': head['clocks'],
+    }
+    if not args.no_configs and args.workload is None:
+        # The other single-GPU BASELINE configs, each a full measurement of its own
+        # (fewer steps: a 34-qubit step moves 7 TB).  A failure is recorded, not fatal.
+        configs = {}
+        sub_steps = max(3, min(args.steps, 5))
+        sub_warm = max(3, min(args.warmup, 3))
+        for sub in SUB_CONFIGS:
+            t0 = time.perf_counter()
+            try:
+                configs[sub] = measure(sub, sub_steps, sub_warm, args, local_rank)
+            except Exception as exc:  # keep the headline even if a sub-config cannot run here
+                configs[sub] = {'error': repr(exc)}
+                torch.cuda.empty_cache()
+            configs[sub]['wall_s'] = time.perf_counter() - t0
+        line['configs'] = configs
     emit(line)
 
 
@@ -448,10 +724,12 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='rqc30', choices=sorted(WORKLOADS) + ['rc_hbm'])
+    ap.add_argument('--workload', default=None, choices=sorted(WORKLOADS) + ['rc_hbm', 'rqc_weak'],
+                    help='default: rqc30 (+ the other configs as sub-entries) on 1 GPU, rc_hbm on N > 1')
     ap.add_argument('--max-fused', dest='max_fused', type=int, default=None,
                     help='widest fused block; default = kernel-matched policy (5 for complex64)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-configs', action='store_true', help='headline workload only')
     args = ap.parse_args()
     quiet_stdout()
     if args.impl == 'reference':

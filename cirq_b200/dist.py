@@ -275,6 +275,8 @@ class ShardedStateVector:
         # logical bit -> physical bit (physical bits >= n_local are global)
         self.phys = list(range(self.n))
         self.swaps = 0
+        # bench.py's instrumentation: on_kernel(kind, block, run) must call run()
+        self.on_kernel = None
         self.fused_exchanges = 0
         self.passes = 0
         self.local_only_blocks = 0
@@ -359,12 +361,20 @@ class ShardedStateVector:
         gi = global_phys - self.n_local
         partner = self.rank ^ (1 << gi)
         if fused_block is not None:
-            self.backend.apply_exchange(fused_block[0], fused_block[1], partner, local_phys,
-                                        self._rank_bit(global_phys))
+            run = lambda: self.backend.apply_exchange(fused_block[0], fused_block[1], partner, local_phys,
+                                                      self._rank_bit(global_phys))
+            if self.on_kernel is None:
+                run()
+            else:
+                self.on_kernel('pass+exchange', fused_block, run)
             self.passes += 1
             self.fused_exchanges += 1
         else:
-            self.backend.swap_bit(partner, local_phys, self._rank_bit(global_phys))
+            run = lambda: self.backend.swap_bit(partner, local_phys, self._rank_bit(global_phys))
+            if self.on_kernel is None:
+                run()
+            else:
+                self.on_kernel('exchange', None, run)
         for l in range(self.n):
             if self.phys[l] == global_phys:
                 self.phys[l] = local_phys
@@ -421,7 +431,12 @@ class ShardedStateVector:
 
     def _run_local(self, batch) -> None:
         if batch:
-            self.local.apply_batch(batch)
+            if self.on_kernel is None:
+                self.local.apply_batch(batch)
+            else:
+                # instrumented (bench.py): one call per block, bracketed by the hook
+                for blk in batch:
+                    self.on_kernel('pass', blk, lambda blk=blk: self.local.apply_batch([blk]))
             self.passes += len(batch)
 
     def _fusable(self, pending, victim: int):

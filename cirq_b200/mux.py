@@ -10,6 +10,7 @@ so behaviour and signatures are the reference's by construction.
 from __future__ import annotations
 
 import contextlib
+import threading
 
 from cirq_b200._cirq_compat import import_cirq
 
@@ -21,16 +22,38 @@ from cirq_b200.dm_simulator import B200DensityMatrixSimulator  # noqa: E402
 from cirq_b200.sv_simulator import B200Simulator  # noqa: E402
 
 
+_LOCK = threading.RLock()
+_DEPTH = 0
+_SAVED = None
+
+
 @contextlib.contextmanager
 def use_b200():
-    """Within the block, Cirq's mux functions simulate on the B200."""
-    saved = (sparse_simulator.Simulator, density_matrix_simulator.DensityMatrixSimulator)
-    sparse_simulator.Simulator = B200Simulator
-    density_matrix_simulator.DensityMatrixSimulator = B200DensityMatrixSimulator
+    """Within the block, Cirq's mux functions simulate on the B200.
+
+    The reference looks its simulator classes up as module globals at call time
+    (sim/mux.py:90, 163, 322), so the switch is a swap of those two globals.  It is
+    re-entrant (nested blocks, and the functions below calling each other) and
+    safe against concurrent use: a process-wide lock guards the swap and a depth
+    counter restores the reference classes only when the LAST block exits, so a
+    thread leaving its block never un-binds the classes under another thread that
+    is still inside one.  (While any block is open, every thread's
+    ``cirq.sample`` runs on the B200 — the globals are process-wide.)"""
+    global _DEPTH, _SAVED
+    with _LOCK:
+        if _DEPTH == 0:
+            _SAVED = (sparse_simulator.Simulator, density_matrix_simulator.DensityMatrixSimulator)
+            sparse_simulator.Simulator = B200Simulator
+            density_matrix_simulator.DensityMatrixSimulator = B200DensityMatrixSimulator
+        _DEPTH += 1
     try:
         yield
     finally:
-        sparse_simulator.Simulator, density_matrix_simulator.DensityMatrixSimulator = saved
+        with _LOCK:
+            _DEPTH -= 1
+            if _DEPTH == 0:
+                sparse_simulator.Simulator, density_matrix_simulator.DensityMatrixSimulator = _SAVED
+                _SAVED = None
 
 
 def sample(program, **kwargs):

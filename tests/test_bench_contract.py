@@ -38,3 +38,43 @@ def test_workload_equivalent_units():
     assert n == 30 and abs(value - 1.0) < 1e-12
     value, n = bench.workload_equivalent(5.0, 20, 'rc20')
     assert n == 20 and value == 5.0
+
+
+def test_density_matrix_bench_schedule_matches_reference(cirq):
+    """The device-resident leg of the qaoa workload replays a gate list built by
+    bench.dm_gate_list; applied by the oracle it must give the reference's rho."""
+    sys.path.insert(0, ROOT)
+    import numpy as np
+
+    import bench
+    from cirq_b200.fusion import fuser_for
+    from oracle import sv_oracle as orc
+
+    bench.WORKLOADS['qaoa4'] = ('qaoa', dict(n=4, p=2, graph_seed=0, noise=0.01, resolvers=8), 10)
+    wl = bench.build_workload('qaoa4')
+    resolver = wl['resolvers'][3]
+    f = fuser_for(np.complex128, 4, wl['bits'])
+    for m, b in bench.dm_gate_list(cirq, wl, resolver):
+        f.add(m, b)
+    rho = np.zeros(1 << wl['bits'], dtype=np.complex128)
+    rho[0] = 1
+    for m, b in f.blocks():
+        rho = orc.apply_matrix(rho, wl['bits'], m, list(b))
+    body = cirq.Circuit(op for op in wl['circuit'].all_operations() if not cirq.is_measurement(op))
+    want = cirq.DensityMatrixSimulator(dtype=np.complex128, noise=cirq.depolarize(0.01)).simulate(
+        body, resolver, qubit_order=wl['qubits']).final_density_matrix
+    np.testing.assert_allclose(rho.reshape(16, 16), want, atol=1e-12)
+    assert wl['unit_gates'] == bench.ref_unit_gates(cirq, cirq.resolve_parameters(wl['circuit'], resolver))
+
+
+def test_unit_gates_equal_reference_fuser_count(cirq):
+    """The metric's gate unit, counted with cirq alone, equals this repo's own
+    k <= 2 fusion of the same circuit (so both arms divide by the same number)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from cirq_b200 import workloads as W
+    from cirq_b200.fusion import fuse_gates
+
+    for name in ('rqc20', 'rc20', 'qft22'):
+        wl = bench.build_workload(name)
+        assert wl['unit_gates'] == len(fuse_gates(W.circuit_to_gates(wl['circuit'], wl['qubits']), 2)), name

@@ -1037,3 +1037,93 @@ def test_mux_entry_points_match_reference(cirq, SV, DM):
     assert len(res) == 4 and res[0].measurements['z'].shape == (20, 1)
     with pytest.raises(ValueError, match='measurement'):
         cirq_b200.final_state_vector(m)
+
+
+def test_qvm_simulator_class_contract(cirq, SV, DM):
+    """The Google QVM hook (cirq-google/cirq_google/engine/virtual_engine_factory.py:437-478)
+    builds ``simulator_class(noise=noise_model, **kwargs)`` and uses the object as the
+    processor's ``cirq.Sampler``.  Same construction and calls here with a
+    NoiseModelFromNoiseProperties model (the base class of the QVM's
+    NoiseModelFromGoogleNoiseProperties: per-gate depolarising + Kraus damping), and
+    the real factory when cirq_google is importable."""
+    from cirq.devices import noise_properties as nprop
+    from cirq.devices.insertion_noise_model import InsertionNoiseModel
+    from cirq.devices.noise_utils import OpIdentifier, PHYSICAL_GATE_TAG
+
+    q = cirq.LineQubit.range(3)
+
+    class Props(nprop.NoiseProperties):
+        def build_noise_models(self):
+            add = {OpIdentifier(cirq.HPowGate, x): cirq.depolarize(0.05).on(x) for x in q}
+            add.update({OpIdentifier(cirq.CZPowGate, a, b): cirq.amplitude_damp(0.1).on(b)
+                        for a, b in ((q[0], q[1]), (q[1], q[2]))})
+            return [InsertionNoiseModel(ops_added=add, require_physical_tag=True)]
+
+        def _value_equality_values_(self):
+            return 'props'
+
+    noise_model = nprop.NoiseModelFromNoiseProperties(Props())
+    circuit = cirq.Circuit(cirq.H(q[0]), cirq.CZ(q[0], q[1]), cirq.H(q[1]), cirq.CZ(q[1], q[2]),
+                           cirq.H(q[2]), cirq.measure(*q, key='m'))
+    for simulator_class, ref_class, kwargs in (
+            (SV, cirq.Simulator, dict(seed=11)),
+            (DM, cirq.DensityMatrixSimulator, dict(seed=11))):
+        sampler = simulator_class(noise=noise_model, **kwargs)  # the factory's exact call
+        assert isinstance(sampler, cirq.Sampler) and isinstance(sampler, cirq.SimulatesSamples)
+        want = ref_class(noise=noise_model, **kwargs).run(circuit, repetitions=40)
+        got = sampler.run(circuit, repetitions=40)
+        assert got.measurements['m'].shape == (40, 3)
+        assert np.mean(got.measurements['m'] != want.measurements['m']) <= 0.05
+        batch = sampler.run_batch([circuit, circuit], repetitions=5)  # SimulatedLocalProcessor's path
+        assert len(batch) == 2 and batch[0][0].measurements['m'].shape == (5, 3)
+    # with trajectory batching (the documented QVM recipe) the distribution is the same
+    exact = cirq.DensityMatrixSimulator(noise=noise_model, dtype=np.complex128).simulate(
+        circuit[:-1], qubit_order=q).final_density_matrix
+    probs = np.real(np.diag(exact))
+    m = SV(noise=noise_model, seed=5, trajectory_batch=512).run(circuit, repetitions=4000).measurements['m']
+    hist = np.bincount(m @ (1 << np.arange(2, -1, -1)), minlength=8)
+    expect = probs * 4000
+    chi2 = float(np.sum((hist - expect) ** 2 / np.maximum(expect, 1e-9)))
+    assert chi2 < 40, chi2  # 7 degrees of freedom
+    try:
+        import cirq_google
+    except Exception:
+        return  # not importable in this image (generated protobuf modules need `tunits`)
+    engine = cirq_google.engine.create_default_noisy_quantum_virtual_machine(
+        'rainbow', simulator_class=SV, seed=0)
+    dev_q = sorted(engine.get_processor('rainbow').get_device().metadata.qubit_set)[:2]
+    res = engine.get_sampler('rainbow').run(
+        cirq.Circuit(cirq.X(dev_q[0]) ** 0.5, cirq.measure(*dev_q, key='z')), repetitions=20)
+    assert res.measurements['z'].shape == (20, 2)
+
+
+def test_use_b200_is_reentrant_and_thread_safe(cirq, SV):
+    import threading
+
+    import cirq_b200
+    from cirq.sim import sparse_simulator
+
+    original = sparse_simulator.Simulator
+    q = cirq.LineQubit.range(2)
+    c = cirq.Circuit(cirq.H(q[0]), cirq.T(q[0]), cirq.CNOT(q[0], q[1]))
+    want = cirq.final_state_vector(c)
+    with cirq_b200.use_b200():
+        with cirq_b200.use_b200():
+            assert sparse_simulator.Simulator is SV
+        assert sparse_simulator.Simulator is SV  # the inner exit must not restore
+        errors = []
+
+        def work():
+            try:
+                for _ in range(5):
+                    np.testing.assert_allclose(cirq_b200.final_state_vector(c), want, atol=1e-6)
+            except Exception as exc:  # pragma: no cover
+                errors.append(exc)
+
+        threads = [threading.Thread(target=work) for _ in range(3)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors and sparse_simulator.Simulator is SV
+    assert sparse_simulator.Simulator is original
