@@ -155,12 +155,18 @@ def kernel_class(wires, n_bits=30):
 
 
 def block_kernel_name(m, w, n_bits):
-    """(kernel name, blocks in the launch) of one scheduled item."""
-    if isinstance(m, (tuple, list)):  # a tile group: several blocks in one pass
-        return f'sv_apply_tc_tile_kernel<{len(m)} blocks>', len(m)
+    """(kernel name, blocks in the launch) of one scheduled block."""
     if np.ndim(m) == 1:
         return 'sv_apply_diag_smem_kernel<float>', 1
     return kernel_class(w, n_bits), 1
+
+
+def pass_kernel_name(group, n_bits):
+    """Kernel of one pass from DeviceState.plan_passes: a single block, or two
+    blocks in one tile pass."""
+    if len(group) == 2:
+        return 'sv_apply_tc_tile_kernel (2 blocks per pass)'
+    return block_kernel_name(group[0][0], group[0][1], n_bits)[0]
 
 
 def ref_unit_gates(cirq, circuit):
@@ -427,12 +433,12 @@ def measure_sv(name, steps, warmup, args, local_rank=0):
     pairs: list = []
 
     def timed_apply(state, blks):
-        for m, w in blks:
+        for group in state.plan_passes(blks):  # one launch each: a block, or two in a tile pass
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            state.apply_batch([(m, w)])
+            state.apply_batch(group)
             b.record()
-            pairs.append((state.n_bits, block_kernel_name(m, w, state.n_bits)[0], a, b))
+            pairs.append((state.n_bits, pass_kernel_name(group, state.n_bits), a, b))
 
     def step(record=False):
         dev = replay_plan(plan, on_apply=timed_apply if record else None)
@@ -512,7 +518,7 @@ def measure_sv(name, steps, warmup, args, local_rank=0):
                    'gate_unit': 'k<=2 fused blocks (cirq.merge_k_qubit_unitaries(k=2) count)',
                    'unit_gates': unit_gates, 'max_fused_qubits': max(dense_widths) if dense_widths else 0,
                    'diagonal_passes_per_step': sum(1 for m, _ in flat if np.ndim(m) == 1),
-                   'blocks_per_step': len(flat), 'launches_per_step_gate_passes': len(blocks),
+                   'blocks_per_step': len(flat),
                    'full_size_passes_per_step': full_passes,
                    'schedule': 'fusion + lazy state growth (kron-joined sub-states) + tile groups, planned '
                                'once outside the timed region',
@@ -525,14 +531,7 @@ def measure_sv(name, steps, warmup, args, local_rank=0):
 
 
 def _flat_blocks(blocks):
-    """Scheduled items with tile groups expanded to their member blocks."""
-    out = []
-    for m, w in blocks:
-        if isinstance(m, (tuple, list)):
-            out.extend(m)
-        else:
-            out.append((m, w))
-    return out
+    return list(blocks)
 
 
 def dm_gate_list(cirq, wl, resolver):
@@ -590,14 +589,14 @@ def measure_dm(name, steps, warmup, args, local_rank=0):
 
     def step(i, record=False):
         dev = DeviceState.basis(bits, dtype, 0)
-        for m, w in plans[i % len(plans)]:
+        for group in dev.plan_passes(plans[i % len(plans)]):
             if record:
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-            dev.apply_batch([(m, w)])
+            dev.apply_batch(group)
             if record:
                 b.record()
-                pairs.append((block_kernel_name(m, w, bits)[0], a, b))
+                pairs.append((pass_kernel_name(group, bits), a, b))
         probs = dev.dm_diagonal_device()
         idx = DeviceState.cdf_sample_device(DeviceState.probs_marginal_device(probs, n, meas_bits), uniforms)
         out = DeviceState.unpack_bits_device(idx, [n - 1 - c for c in range(n)])

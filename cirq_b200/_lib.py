@@ -105,6 +105,11 @@ SIGNATURES = {
                                       c_void_p, c_void_p]),
     'b2q_bsv_collapse': (c_int, [c_void_p, c_int, c_int, c_int, c_uint64, c_void_p, c_void_p, c_void_p]),
     'b2q_dist_unpack': (c_int, [c_void_p, c_int, c_int, POINTER(c_int), c_int, c_void_p, c_void_p]),
+    'b2q_dist_swap_bits': (c_int, [c_void_p, POINTER(c_void_p), c_int, c_int, POINTER(c_int), c_int, c_int,
+                                   c_void_p]),
+    'b2q_tile_blocks_feasible': (c_int, [c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
+    'b2q_sv_apply_tile_blocks': (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int),
+                                         c_void_p, c_void_p]),
 }
 
 # Host-only helpers exported for unit tests (not part of the product ABI).
@@ -116,6 +121,7 @@ DEBUG_SIGNATURES = {
     'b2q_set_tc_stage_opts': (c_int, [c_int, c_int]),
     'b2q_debug_tc_stage_plan': (c_int, [c_int, POINTER(c_int), c_int, POINTER(ctypes.c_int64)]),
     'b2q_debug_plan': (c_int, [c_int, c_int, POINTER(c_int), c_int, POINTER(c_int)]),
+    'b2q_debug_tile_plan': (c_int, [c_int, c_int, POINTER(c_int), POINTER(ctypes.c_int64)]),
     'b2q_debug_permute_matrix': (c_int, [c_void_p, POINTER(c_int), c_int, c_void_p]),
 }
 

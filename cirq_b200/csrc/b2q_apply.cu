@@ -808,6 +808,38 @@ int launch_tc(void* state, int n, int K, const int* sorted, const float* mat, cu
 int launch_tc_exchange(void* state, int n, int K, const int* sorted, const float* mat,
                        void* out_local, void* out_peer, int xbit, int gval, cudaStream_t stream);
 
+bool tile_bits_for(int n, int nb, const int* ks, const int* targets, int* tbits);
+int launch_tc_tile(void* state, int n, int nb, const int (*sorted)[5], const int* tbits,
+                   const float* const* mats, cudaStream_t stream);
+
+// Widens block (m128 on targets[0..k)) to 5 targets inside the tile bits (identity
+// on the added wires, which become the most significant ones) and brings it to
+// sorted-target order: `sorted5` and `plain` (32 x 32 (re, im) float pairs).
+static void widen_block_to_5(const double* m128, const int* targets, int k, const int* tbits,
+                             int* sorted5, float* plain) {
+  int wide[5];
+  const int extra = 5 - k;
+  int e = 0;
+  for (int i = 11; i >= 0 && e < extra; --i) {
+    bool used = false;
+    for (int q = 0; q < k; ++q) used |= targets[q] == tbits[i];
+    if (!used) wide[e++] = tbits[i];
+  }
+  for (int q = 0; q < k; ++q) wide[extra + q] = targets[q];
+  const int dk = 1 << k;
+  std::vector<double> big((size_t)2 * 32 * 32, 0.0);
+  for (int hi = 0; hi < (1 << extra); ++hi)
+    for (int r = 0; r < dk; ++r)
+      for (int c = 0; c < dk; ++c) {
+        const size_t dst = 2 * ((size_t)(hi * dk + r) * 32 + (size_t)(hi * dk + c));
+        big[dst] = m128[2 * ((size_t)r * dk + c)];
+        big[dst + 1] = m128[2 * ((size_t)r * dk + c) + 1];
+      }
+  for (int i = 0; i < 5; ++i) sorted5[i] = wide[i];
+  std::sort(sorted5, sorted5 + 5);
+  permute_matrix<float>(big.data(), wide, sorted5, 5, plain, /*packed=*/false);
+}
+
 template <typename real>
 int apply_matrix_t(void* state, int dtype, int n, const double* m128, const int* targets, int K,
                    void* scratch, cudaStream_t stream) {
@@ -890,6 +922,44 @@ extern "C" int b2q_sv_apply_batch(void* state, int dtype, int n_qubits, int num_
     moff += (size_t)2 << (2 * k);
   }
   return B2Q_OK;
+}
+
+extern "C" int b2q_tile_blocks_feasible(int dtype, int n_qubits, int num_blocks, const int* ks,
+                                        const int* targets) {
+  if (dtype != B2Q_C64 || ks == nullptr || targets == nullptr) return 0;
+  if (!tc_applicable(dtype, n_qubits, 5)) return 0;
+  int tbits[12];
+  return tile_bits_for(n_qubits, num_blocks, ks, targets, tbits) ? 1 : 0;
+}
+
+extern "C" int b2q_sv_apply_tile_blocks(void* state, int dtype, int n_qubits, int num_blocks,
+                                        const int* ks, const int* targets,
+                                        const double* matrices_c128, void* stream) {
+  B2Q_REQUIRE(state != nullptr && ks != nullptr && targets != nullptr && matrices_c128 != nullptr,
+              "null argument");
+  B2Q_REQUIRE(dtype == B2Q_C64, "tile passes are complex64 only");
+  B2Q_REQUIRE(num_blocks >= 1 && num_blocks <= 2, "a tile pass takes 1 or 2 blocks, got %d", num_blocks);
+  B2Q_REQUIRE(tc_applicable(dtype, n_qubits, 5), "tensor-core kernels not applicable (n=%d)", n_qubits);
+  int tbits[12];
+  B2Q_REQUIRE(tile_bits_for(n_qubits, num_blocks, ks, targets, tbits),
+              "blocks do not fit one 12-bit tile (or bad targets)");
+  int sorted[2][5];
+  std::vector<float> plain[2];
+  const float* mats[2] = {nullptr, nullptr};
+  size_t toff = 0, moff = 0;
+  for (int b = 0; b < num_blocks; ++b) {
+    const int k = ks[b];
+    for (int i = 0; i < k; ++i)
+      for (int j = 0; j < i; ++j)
+        B2Q_REQUIRE(targets[toff + i] != targets[toff + j], "duplicate target bit %d", targets[toff + i]);
+    plain[b].resize((size_t)2 * 32 * 32);
+    widen_block_to_5(matrices_c128 + moff, targets + toff, k, tbits, sorted[b], plain[b].data());
+    mats[b] = plain[b].data();
+    toff += k;
+    moff += (size_t)2 << (2 * k);
+  }
+  return launch_tc_tile(state, n_qubits, num_blocks, sorted, tbits, mats,
+                        reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int b2q_sv_apply_diagonal(void* state, int dtype, int n_qubits,

@@ -807,6 +807,499 @@ static int launch_tc_staged_kernel(const TcStagedParams& p, cudaStream_t stream)
   return B2Q_OK;
 }
 
+
+// ---- tile kernel: SEVERAL blocks in one pass over HBM -------------------------
+//
+// A pass costs 2.6 ms of HBM time at 30 qubits however little it computes, and
+// the 5-qubit tensor-core pass already runs at ~0.9 of the copy rate — the
+// remaining lever is the NUMBER of passes.  Two consecutive 5-qubit blocks
+// touch at most 10 index bits; a CTA tile of 2^12 amplitudes (32 KB) over those
+// bits plus the lowest free ones holds every amplitude group of BOTH blocks.
+// The tile is staged once (cp.async, 16-byte lanes), block A and block B are
+// applied to it in shared memory — gather a group -> 3xTF32 split -> TMEM ->
+// tcgen05.mma -> TMEM -> scatter, exactly the arithmetic of the one-block
+// kernels — and it is written back once: half the HBM traffic per block.
+//
+//   * 4096 amplitudes / 32 per group = 128 groups = ONE UMMA M tile per block.
+//   * A CTA holds two independent compute groups of 128 threads (own tile
+//     buffers, own TMEM half, own mbarrier, named barriers) that share the B
+//     matrices: while one group waits for the tensor core the other moves
+//     data.  Each group double-buffers its tile: the next tile's copy is in
+//     flight while the current one is multiplied.  Shared memory: 2 x 32 KB of
+//     B + 4 x 32 KB of tiles = 192 KB, one CTA per SM, all 512 TMEM columns.
+//   * The tile is stored swizzled: slot bits 1-3 (the 8-byte bank pairs) are
+//     parities of local-index bits chosen on the host so that the linear copy
+//     pattern and the group gather / scatter of BOTH blocks are free of bank
+//     conflicts (make_tile_params; replayed on the CPU in tests/test_plan_host.py).
+constexpr int kTileBits = 12;
+constexpr int kTileAmps = 1 << kTileBits;
+constexpr int kTileMaxBlocks = 2;
+constexpr int kTileGroups = 2;
+constexpr int kTileThreads = kTileGroups * kTcThreads;
+constexpr uint32_t kTileBufBytes = kTileAmps * sizeof(float2);
+constexpr size_t kTileBBytes = TcTraits<5>::kBBytes;  // per block: B_hi + B_lo
+constexpr size_t kTileSmemBytes =
+    kTileMaxBlocks * kTileBBytes + (size_t)kTileGroups * 2 * kTileBufBytes;
+
+struct TcTileParams {
+  float2* state;
+  uint64_t num_tiles;
+  const float* bmat;  // num_blocks x (B_hi, B_lo), UMMA K-major layout
+  int num_blocks;
+  int tbits[kTileBits];  // ascending index positions of the tile bits (tbits[0] = 0, tbits[1] = 1)
+  uint32_t xmask[3];     // slot bit d + 1 = parity(local index & xmask[d])
+  uint64_t rgoff[16];    // copy round r (local bits 8-11) -> element offset in the state
+  uint32_t rslot[16];    // copy round r -> slot offset
+  int vec[kTileMaxBlocks];              // 1: local bit 0 is a target (members 2i, 2i+1 adjacent)
+  int gbit[kTileMaxBlocks][7];          // local position behind thread bit i (lane 0-4, warp 5-6)
+  uint32_t mslot[kTileMaxBlocks][32];   // member j -> slot offset
+};
+
+B2Q_HD uint32_t tile_slot(uint32_t local, const uint32_t* xmask) {
+  uint32_t s = local & ~0xeu;
+  for (int d = 0; d < 3; ++d) {
+    uint32_t v = local & xmask[d];
+    v ^= v >> 16;
+    v ^= v >> 8;
+    v ^= v >> 4;
+    v ^= v >> 2;
+    v ^= v >> 1;
+    s |= (v & 1u) << (d + 1);
+  }
+  return s;
+}
+
+__device__ __forceinline__ void group_barrier(int group) {
+  asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(kTcThreads) : "memory");
+}
+
+__global__ void __launch_bounds__(kTileThreads, 1)
+    sv_apply_tc_tile_kernel(const __grid_constant__ TcTileParams p) {
+  constexpr int kTcDim = 32;
+  constexpr int kTcN = 64;
+  constexpr int kGroupCols = 4 * kTcN;  // A_hi | A_lo | D0 | D1
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* sB = reinterpret_cast<float*>(smem_raw);
+  __shared__ __align__(8) uint64_t mbar[kTileGroups];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x;
+  const int group = tid >> 7;
+  const int gt = tid & (kTcThreads - 1);  // thread within the group = UMMA row
+  const int warp_g = gt >> 5;
+  const int lane = tid & 31;
+
+  if (tid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_s)),
+                 "r"((uint32_t)(kTileGroups * kGroupCols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int g = 0; g < kTileGroups; ++g)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[g])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.bmat);
+    float4* dst = reinterpret_cast<float4*>(sB);
+    const int count = p.num_blocks * (int)(kTileBBytes / sizeof(float4));
+    for (int i = tid; i < count; i += kTileThreads) dst[i] = src[i];
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_group = tmem_base_s + (uint32_t)(group * kGroupCols);
+  const uint32_t lane_base = tmem_group + ((uint32_t)(warp_g * 32) << 16);
+  const uint32_t d_col = 2 * kTcN;
+  constexpr uint32_t idesc =
+      (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((128u >> 4) << 24);
+  constexpr uint32_t kLbo = kTcN * 16;
+  constexpr uint32_t kSbo = 128;
+  const uint32_t mbar_s = smem_u32(&mbar[group]);
+
+  // copy pattern: this thread moves local elements (2 * lane | warp << 6 | round << 8), +1
+  const uint32_t thr_local = ((uint32_t)lane << 1) | ((uint32_t)warp_g << 6);
+  uint64_t thr_goff = 0;
+#pragma unroll
+  for (int i = 1; i < 8; ++i) thr_goff += (uint64_t)((thr_local >> i) & 1u) << p.tbits[i];
+  const uint32_t thr_slot = tile_slot(thr_local, p.xmask);
+  // gather pattern: this thread's group, per block
+  uint32_t sg[kTileMaxBlocks];
+#pragma unroll
+  for (int b = 0; b < kTileMaxBlocks; ++b) {
+    uint32_t gl = 0;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) gl |= (uint32_t)((gt >> i) & 1) << p.gbit[b][i];
+    sg[b] = tile_slot(gl, p.xmask);
+  }
+  unsigned char* const tiles =
+      smem_raw + kTileMaxBlocks * kTileBBytes + (size_t)group * 2 * kTileBufBytes;
+  const uint32_t tiles_s = smem_u32(tiles);
+
+  auto prefetch = [&](uint64_t base, uint32_t buf) {
+    const float2* src = p.state + base + thr_goff;
+    const uint32_t dst = tiles_s + buf * kTileBufBytes;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + ((thr_slot ^ p.rslot[r]) << 3)),
+                   "l"(src + p.rgoff[r])
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const uint64_t stride = (uint64_t)gridDim.x * kTileGroups;
+  uint64_t tile = (uint64_t)blockIdx.x * kTileGroups + (uint64_t)group;
+  uint64_t base = 0;
+  uint32_t parity = 0, buf = 0;
+  if (tile < p.num_tiles) {
+    base = insert_zero_bits(tile, p.tbits, kTileBits);
+    prefetch(base, 0);
+  }
+  while (tile < p.num_tiles) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    group_barrier(group);  // the tile is complete and visible to the whole group
+    const uint64_t next = tile + stride;
+    uint64_t next_base = 0;
+    if (next < p.num_tiles) next_base = insert_zero_bits(next, p.tbits, kTileBits);
+    unsigned char* const sbuf = tiles + (size_t)buf * kTileBufBytes;
+    for (int b = 0; b < p.num_blocks; ++b) {
+      const uint32_t sgb = b == 0 ? sg[0] : sg[1];
+      const uint32_t* const mslot = p.mslot[b];
+      const bool vec = p.vec[b] != 0;
+      float2 x[kTcDim];
+      if (vec) {
+#pragma unroll
+        for (int i = 0; i < kTcDim / 2; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(sbuf + ((sgb ^ mslot[2 * i]) << 3));
+          x[2 * i] = make_float2(v.x, v.y);
+          x[2 * i + 1] = make_float2(v.z, v.w);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kTcDim; ++j)
+          x[j] = *reinterpret_cast<const float2*>(sbuf + ((sgb ^ mslot[j]) << 3));
+      }
+#pragma unroll
+      for (int c16 = 0; c16 < kTcN / 16; ++c16) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int col = c16 * 16 + e;
+          const float a = (col & 1) ? x[col >> 1].y : x[col >> 1].x;
+          const uint32_t h = to_tf32(a);
+          hi[e] = h;
+          lo[e] = to_tf32(a - __uint_as_float(h));
+        }
+        tmem_st16(lane_base + (uint32_t)(c16 * 16), hi);
+        tmem_st16(lane_base + (uint32_t)(kTcN + c16 * 16), lo);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      // next tile -> the other buffer while the tensor core works on this one
+      if (b == 0 && next < p.num_tiles) prefetch(next_base, buf ^ 1u);
+      group_barrier(group);
+      if (gt == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // same product order as sv_apply_tc_kernel (see the comment there)
+        const uint32_t sb_hi = smem_u32(sB) + (uint32_t)b * (uint32_t)kTileBBytes;
+        const uint32_t sb_lo = sb_hi + (uint32_t)(kTcN * kTcN * sizeof(float));
+        uint32_t acc0 = 0;
+#pragma unroll
+        for (int prod = 0; prod < 2; ++prod) {
+          const uint32_t a_col = (prod == 0) ? (uint32_t)kTcN : 0u;
+          const uint32_t sb = (prod == 0) ? sb_hi : sb_lo;
+#pragma unroll
+          for (int ks = 0; ks < kTcN / 8; ++ks) {
+            const uint64_t bd = umma_desc(sb + (uint32_t)(ks * 2) * kLbo, kLbo, kSbo);
+            umma_tf32_ts(tmem_group + d_col, tmem_group + a_col + (uint32_t)(ks * 8), bd, idesc, acc0);
+            acc0 = 1;
+          }
+        }
+#pragma unroll
+        for (int ks = 0; ks < kTcN / 8; ++ks) {
+          const uint64_t bd = umma_desc(sb_hi + (uint32_t)(ks * 2) * kLbo, kLbo, kSbo);
+          const bool second = ks >= kTcN / 16;
+          umma_tf32_ts(tmem_group + d_col + (second ? (uint32_t)kTcN : 0u),
+                       tmem_group + (uint32_t)(ks * 8), bd, idesc,
+                       (second && ks == kTcN / 16) ? 0u : 1u);
+        }
+        asm volatile(
+            "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar_s)
+            : "memory");
+      }
+      mbar_wait(mbar_s, parity);
+      parity ^= 1;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int c16 = 0; c16 < kTcN / 16; ++c16) {
+        uint32_t d[16], d1[16];
+        tmem_ld16(lane_base + d_col + (uint32_t)(c16 * 16), d);
+        tmem_ld16(lane_base + d_col + (uint32_t)(kTcN + c16 * 16), d1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (vec) {
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            const int r = (c16 * 16 + e) >> 1;
+            float4 o;
+            o.x = __uint_as_float(d[e]) + __uint_as_float(d1[e]);
+            o.y = __uint_as_float(d[e + 1]) + __uint_as_float(d1[e + 1]);
+            o.z = __uint_as_float(d[e + 2]) + __uint_as_float(d1[e + 2]);
+            o.w = __uint_as_float(d[e + 3]) + __uint_as_float(d1[e + 3]);
+            *reinterpret_cast<float4*>(sbuf + ((sgb ^ mslot[r]) << 3)) = o;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            const int r = (c16 * 16 + e) >> 1;
+            float2 o;
+            o.x = __uint_as_float(d[e]) + __uint_as_float(d1[e]);
+            o.y = __uint_as_float(d[e + 1]) + __uint_as_float(d1[e + 1]);
+            *reinterpret_cast<float2*>(sbuf + ((sgb ^ mslot[r]) << 3)) = o;
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      group_barrier(group);  // results visible before the next block regroups them
+    }
+    // tile -> HBM
+    {
+      float2* const dstp = p.state + base + thr_goff;
+#pragma unroll
+      for (int r0 = 0; r0 < 16; r0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          v[r] = *reinterpret_cast<const float4*>(sbuf + ((thr_slot ^ p.rslot[r0 + r]) << 3));
+#pragma unroll
+        for (int r = 0; r < 8; ++r) *reinterpret_cast<float4*>(dstp + p.rgoff[r0 + r]) = v[r];
+      }
+    }
+    // (this buffer is refilled by the prefetch issued in the NEXT iteration, after
+    // that iteration's first group barrier: every thread has read it by then)
+    tile = next;
+    base = next_base;
+    buf ^= 1u;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s),
+                 "r"((uint32_t)(kTileGroups * kGroupCols))
+                 : "memory");
+  }
+}
+
+// Host side of the tile layout.  `sorted[b]` = the 5 ascending targets of block b
+// (already widened to 5), `tbits` = the 12 ascending tile bits (a superset of all
+// targets, containing index bits 0 and 1).  Returns false if no conflict-free
+// swizzle exists (not observed; the caller then applies the blocks one by one).
+static bool make_tile_params(int nb, const int (*sorted)[5], const int* tbits, TcTileParams* p) {
+  for (int i = 0; i < kTileBits; ++i) p->tbits[i] = tbits[i];
+  p->num_blocks = nb;
+  auto local_pos = [&](int bit) {
+    for (int i = 0; i < kTileBits; ++i)
+      if (tbits[i] == bit) return i;
+    return -1;
+  };
+  int tl[kTileMaxBlocks][5];            // local positions of the targets, ascending
+  int grp[kTileMaxBlocks][7];           // local positions of the group bits, ascending
+  for (int b = 0; b < nb; ++b) {
+    bool is_t[kTileBits] = {false};
+    for (int i = 0; i < 5; ++i) {
+      tl[b][i] = local_pos(sorted[b][i]);
+      if (tl[b][i] < 0) return false;
+      is_t[tl[b][i]] = true;
+    }
+    int c = 0;
+    for (int l = 0; l < kTileBits; ++l)
+      if (!is_t[l]) grp[b][c++] = l;
+    p->vec[b] = is_t[0] ? 1 : 0;
+  }
+  // Bank directions: slot bit d (1..3) of a local index is local bit d XOR the local
+  // bits h >= 4 with dir[h] == d.  Every block needs, among its group bits other than
+  // local bit 0, one bit per direction (then 16 lanes x 8 bytes, or 8 lanes x 16 bytes,
+  // cover all 32 banks).  Small backtracking search over the high bits.
+  int dir[kTileBits] = {0};
+  struct Need { int b, d; };
+  Need needs[3 * kTileMaxBlocks];
+  int nn = 0;
+  for (int b = 0; b < nb; ++b)
+    for (int d = 1; d <= 3; ++d) {
+      bool have = false;
+      for (int i = 0; i < 7; ++i) have |= grp[b][i] == d;
+      if (!have) needs[nn++] = Need{b, d};
+    }
+  int pick[3 * kTileMaxBlocks];
+  // iterative DFS
+  int depth = 0;
+  for (int i = 0; i < nn; ++i) pick[i] = -1;
+  bool ok = nn == 0;
+  while (nn > 0) {
+    if (depth == nn) { ok = true; break; }
+    if (depth < 0) break;
+    const Need& nd = needs[depth];
+    // undo the previous choice at this depth (if it was the one that set dir)
+    int start = 0;
+    if (pick[depth] >= 0) {
+      const int h = grp[nd.b][pick[depth] & 0xff];
+      if (pick[depth] & 0x100) dir[h] = 0;
+      start = (pick[depth] & 0xff) + 1;
+      pick[depth] = -1;
+    }
+    bool placed = false;
+    for (int i = start; i < 7; ++i) {
+      const int h = grp[nd.b][i];
+      if (h < 4) continue;
+      if (dir[h] == nd.d) { pick[depth] = i; placed = true; break; }
+      if (dir[h] == 0) { dir[h] = nd.d; pick[depth] = i | 0x100; placed = true; break; }
+    }
+    if (placed) ++depth; else --depth;
+  }
+  if (!ok) return false;
+  for (int d = 1; d <= 3; ++d) {
+    uint32_t m = 1u << d;
+    for (int h = 4; h < kTileBits; ++h)
+      if (dir[h] == d) m |= 1u << h;
+    p->xmask[d - 1] = m;
+  }
+  // thread bits of the gather: [local 0 if it is a group bit], one group bit per
+  // direction, then the rest ascending
+  for (int b = 0; b < nb; ++b) {
+    bool used[kTileBits] = {false};
+    int out = 0;
+    if (!p->vec[b]) { p->gbit[b][out++] = 0; used[0] = true; }
+    for (int d = 1; d <= 3; ++d) {
+      int chosen = -1;
+      for (int i = 0; i < 7 && chosen < 0; ++i)
+        if (grp[b][i] == d) chosen = d;
+      for (int i = 0; i < 7 && chosen < 0; ++i)
+        if (grp[b][i] >= 4 && dir[grp[b][i]] == d && !used[grp[b][i]]) chosen = grp[b][i];
+      if (chosen < 0) return false;
+      p->gbit[b][out++] = chosen;
+      used[chosen] = true;
+    }
+    for (int i = 0; i < 7; ++i)
+      if (!used[grp[b][i]]) p->gbit[b][out++] = grp[b][i];
+    if (out != 7) return false;
+    for (int j = 0; j < 32; ++j) {
+      uint32_t loc = 0;
+      for (int i = 0; i < 5; ++i)
+        if ((j >> i) & 1) loc |= 1u << tl[b][i];
+      p->mslot[b][j] = tile_slot(loc, p->xmask);
+    }
+  }
+  for (int b = nb; b < kTileMaxBlocks; ++b) {
+    p->vec[b] = 0;
+    for (int i = 0; i < 7; ++i) p->gbit[b][i] = i;
+    for (int j = 0; j < 32; ++j) p->mslot[b][j] = 0;
+  }
+  for (int r = 0; r < 16; ++r) {
+    uint64_t off = 0;
+    for (int i = 0; i < 4; ++i)
+      if ((r >> i) & 1) off += 1ull << tbits[8 + i];
+    p->rgoff[r] = off;
+    p->rslot[r] = tile_slot((uint32_t)r << 8, p->xmask);
+  }
+  return true;
+}
+
+// Tile bits of a group of blocks: the union of their targets, index bits 0 and 1,
+// and the lowest other bits up to 12.  Returns false if the union is too wide.
+bool tile_bits_for(int n, int nb, const int* ks, const int* targets, int* tbits) {
+  if (n < kTileBits || nb < 1 || nb > kTileMaxBlocks) return false;
+  bool in[64] = {false};
+  in[0] = in[1] = true;
+  int count = 2;
+  size_t off = 0;
+  for (int b = 0; b < nb; ++b) {
+    if (ks[b] < 1 || ks[b] > 5) return false;
+    for (int i = 0; i < ks[b]; ++i) {
+      const int t = targets[off + i];
+      if (t < 0 || t >= n) return false;
+      if (!in[t]) { in[t] = true; ++count; }
+    }
+    off += ks[b];
+  }
+  if (count > kTileBits) return false;
+  for (int bit = 0; bit < n && count < kTileBits; ++bit)
+    if (!in[bit]) { in[bit] = true; ++count; }
+  int c = 0;
+  for (int bit = 0; bit < n; ++bit)
+    if (in[bit]) tbits[c++] = bit;
+  return c == kTileBits;
+}
+
+static void fill_b_matrix(const float* mat, float* hi, float* lo) {
+  constexpr int kTcDim = 32, kTcN = 64;
+  for (int r = 0; r < kTcDim; ++r)
+    for (int c = 0; c < kTcDim; ++c) {
+      const float mr = mat[2 * (r * kTcDim + c)], mi = mat[2 * (r * kTcDim + c) + 1];
+      const float vals[2][2] = {{mr, -mi}, {mi, mr}};
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          const int nn = 2 * r + a, kk = 2 * c + b;
+          const size_t idx = (size_t)(kk >> 2) * (kTcN * 4) + (size_t)nn * 4 + (kk & 3);
+          const float v = vals[a][b];
+          const float h = tf32_round_host(v);
+          hi[idx] = h;
+          lo[idx] = tf32_round_host(v - h);
+        }
+    }
+}
+
+// `mats[b]` = block b's matrix in sorted-target order (plain (re, im) pairs, 32 x 32).
+int launch_tc_tile(void* state, int n, int nb, const int (*sorted)[5], const int* tbits,
+                   const float* const* mats, cudaStream_t stream) {
+  TcTileParams p;
+  memset(&p, 0, sizeof(p));
+  if (!make_tile_params(nb, sorted, tbits, &p))
+    return set_error(B2Q_ERR_UNSUPPORTED, "no conflict-free tile layout for these blocks");
+  std::lock_guard<std::mutex> lock(g_ring_mutex);
+  MatrixRing* ring = nullptr;
+  int slot = 0;
+  {
+    const int rc = ring_acquire(&ring, &slot);
+    if (rc != B2Q_OK) return rc;
+  }
+  static_assert(kTileMaxBlocks * kTileBBytes <= MatrixRing::kBytes, "ring slot too small");
+  for (int b = 0; b < nb; ++b) {
+    float* hi = ring->host[slot] + (size_t)b * (kTileBBytes / sizeof(float));
+    fill_b_matrix(mats[b], hi, hi + 64 * 64);
+  }
+  B2Q_CUDA_CHECK(cudaMemcpyAsync(ring->dev[slot], ring->host[slot], nb * kTileBBytes,
+                                 cudaMemcpyHostToDevice, stream));
+  p.state = reinterpret_cast<float2*>(state);
+  p.num_tiles = 1ull << (n - kTileBits);
+  p.bmat = ring->dev[slot];
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  static bool attr_set[64] = {false};
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+      B2Q_CUDA_CHECK(cudaFuncSetAttribute(sv_apply_tc_tile_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kTileSmemBytes));
+      attr_set[dev] = true;
+    }
+  }
+  const uint64_t ctas = (p.num_tiles + kTileGroups - 1) / kTileGroups;
+  const uint64_t grid = std::min<uint64_t>(ctas, (uint64_t)sms);
+  sv_apply_tc_tile_kernel<<<(unsigned)grid, kTileThreads, kTileSmemBytes, stream>>>(p);
+  B2Q_LAUNCH_CHECK("sv_apply_tc_tile_kernel");
+  B2Q_CUDA_CHECK(cudaEventRecord(ring->done[slot], stream));
+  return B2Q_OK;
+}
+
 struct TcExchange {
   void* out_local;
   void* out_peer;
@@ -939,6 +1432,39 @@ extern "C" int b2q_debug_tc_stage_plan(int n_qubits, const int* sorted_targets, 
   for (int i = 0; i < 16; ++i) out[o++] = i < (1 << (k - 1)) ? (int64_t)p.goff[i] : -1;
   for (int i = 0; i < 16; ++i) out[o++] = i < (1 << (k - 1)) ? (int64_t)p.sreq[i] : -1;
   for (int i = 0; i < 32; ++i) out[o++] = i < (1 << k) ? (int64_t)p.smem_j[i] : -1;
+  return B2Q_OK;
+}
+
+// Host-only: the tile kernel's address tables for `num_blocks` blocks of 5 ascending
+// targets each.  out (int64): tbits[12] | xmask[3] | rgoff[16] | rslot[16] | then per
+// block: vec | gbit[7] | mslot[32].  Returns B2Q_ERR_UNSUPPORTED if the blocks do not
+// fit one tile.
+extern "C" int b2q_debug_tile_plan(int n_qubits, int num_blocks, const int* sorted_targets,
+                                   int64_t* out) {
+  B2Q_REQUIRE(sorted_targets != nullptr && out != nullptr, "null argument");
+  B2Q_REQUIRE(num_blocks >= 1 && num_blocks <= b2q::kTileMaxBlocks, "bad block count");
+  int ks[b2q::kTileMaxBlocks];
+  for (int b = 0; b < num_blocks; ++b) ks[b] = 5;
+  int tbits[b2q::kTileBits];
+  if (!b2q::tile_bits_for(n_qubits, num_blocks, ks, sorted_targets, tbits))
+    return b2q::set_error(B2Q_ERR_UNSUPPORTED, "blocks do not fit one tile");
+  int sorted[b2q::kTileMaxBlocks][5];
+  for (int b = 0; b < num_blocks; ++b)
+    for (int i = 0; i < 5; ++i) sorted[b][i] = sorted_targets[5 * b + i];
+  b2q::TcTileParams p;
+  memset(&p, 0, sizeof(p));
+  if (!b2q::make_tile_params(num_blocks, sorted, tbits, &p))
+    return b2q::set_error(B2Q_ERR_UNSUPPORTED, "no conflict-free tile layout");
+  int o = 0;
+  for (int i = 0; i < 12; ++i) out[o++] = p.tbits[i];
+  for (int i = 0; i < 3; ++i) out[o++] = p.xmask[i];
+  for (int i = 0; i < 16; ++i) out[o++] = (int64_t)p.rgoff[i];
+  for (int i = 0; i < 16; ++i) out[o++] = p.rslot[i];
+  for (int b = 0; b < num_blocks; ++b) {
+    out[o++] = p.vec[b];
+    for (int i = 0; i < 7; ++i) out[o++] = p.gbit[b][i];
+    for (int j = 0; j < 32; ++j) out[o++] = p.mslot[b][j];
+  }
   return B2Q_OK;
 }
 

@@ -60,9 +60,109 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Multi-bit exchange: m global bits trade places with m local bits in ONE pass.
+// Sub-block c of a shard = the amplitudes whose exchanged local bits read c; rank
+// with sub-rank rho (its values of the exchanged global bits) keeps sub-block rho
+// and swaps sub-block c with sub-block rho of the rank whose sub-rank is c: every
+// rank streams (1 - 2^-m) of its shard out and in once, instead of m times a half
+// (m = 3: 7/8 against 3/2).  blockIdx.y selects the partner; of each pair the
+// lower sub-rank serves the lower half of the index range, the higher one the
+// upper half, so both link directions carry equal traffic.  In place.
+struct SwapMultiParams {
+  void* peers[8];    // by sub-rank value (entry [rho] unused)
+  int lbits_v[3];    // exchanged local bits, ascending, in vector-index units
+  int m;
+  int rho;
+  uint64_t nvec_rest;  // vectors per sub-block
+};
+
+template <typename V>
+__global__ void __launch_bounds__(256)
+    dist_swap_multi_kernel(V* __restrict__ mine, const __grid_constant__ SwapMultiParams p) {
+  constexpr int U = 4;
+  const int c = (int)blockIdx.y < p.rho ? (int)blockIdx.y : (int)blockIdx.y + 1;
+  V* __restrict__ peer = reinterpret_cast<V*>(p.peers[c]);
+  uint64_t mine_or = 0, peer_or = 0;
+  for (int i = 0; i < p.m; ++i) {
+    mine_or |= (uint64_t)((c >> i) & 1) << p.lbits_v[i];
+    peer_or |= (uint64_t)((p.rho >> i) & 1) << p.lbits_v[i];
+  }
+  uint64_t jb, je;
+  if (p.nvec_rest == 1) {
+    if (p.rho > c) return;
+    jb = 0;
+    je = 1;
+  } else {
+    const uint64_t half = p.nvec_rest / 2;
+    jb = p.rho < c ? 0 : half;
+    je = p.rho < c ? half : p.nvec_rest;
+  }
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t j = jb + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; j + (U - 1) * stride < je; j += U * stride) {
+    V a[U], b[U];
+    uint64_t base[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      base[u] = insert_zero_bits(j + u * stride, p.lbits_v, p.m);
+      b[u] = peer[base[u] | peer_or];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) a[u] = mine[base[u] | mine_or];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      mine[base[u] | mine_or] = b[u];
+      peer[base[u] | peer_or] = a[u];
+    }
+  }
+  for (; j < je; j += stride) {
+    const uint64_t base = insert_zero_bits(j, p.lbits_v, p.m);
+    const V b = peer[base | peer_or];
+    const V a = mine[base | mine_or];
+    mine[base | mine_or] = b;
+    peer[base | peer_or] = a;
+  }
+}
+
 }  // namespace b2q
 
 using namespace b2q;
+
+extern "C" int b2q_dist_swap_bits(void* mine, void* const* peers, int dtype, int n_local,
+                                  const int* local_bits, int m, int my_sub_rank, void* stream) {
+  B2Q_REQUIRE(mine != nullptr && peers != nullptr && local_bits != nullptr, "null argument");
+  B2Q_REQUIRE(dtype == B2Q_C64 || dtype == B2Q_C128, "bad dtype %d", dtype);
+  B2Q_REQUIRE(m >= 1 && m <= 3, "1 to 3 bits per exchange, got %d", m);
+  B2Q_REQUIRE(my_sub_rank >= 0 && my_sub_rank < (1 << m), "bad sub-rank %d", my_sub_rank);
+  const int elems_log2 = dtype == B2Q_C64 ? 1 : 0;
+  B2Q_REQUIRE(n_local - elems_log2 - m >= 0, "shard too small");
+  SwapMultiParams p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < m; ++i) {
+    B2Q_REQUIRE(local_bits[i] >= elems_log2 && local_bits[i] < n_local,
+                "local bit %d must be in [%d, %d)", local_bits[i], elems_log2, n_local);
+    B2Q_REQUIRE(i == 0 || local_bits[i] > local_bits[i - 1], "local bits must be ascending");
+    p.lbits_v[i] = local_bits[i] - elems_log2;
+  }
+  for (int c = 0; c < (1 << m); ++c) {
+    B2Q_REQUIRE(c == my_sub_rank || peers[c] != nullptr, "null peer pointer for sub-rank %d", c);
+    p.peers[c] = peers[c];
+  }
+  p.m = m;
+  p.rho = my_sub_rank;
+  p.nvec_rest = 1ull << (n_local - elems_log2 - m);
+  const uint64_t work = std::max<uint64_t>(1, p.nvec_rest / 2);
+  const uint64_t per_partner = std::max<uint64_t>(1, (148ull * 16) / ((1u << m) - 1));
+  const uint64_t blocks = std::max<uint64_t>(1, std::min<uint64_t>((work / 4 + 255) / 256, per_partner));
+  const dim3 grid((unsigned)blocks, (1u << m) - 1);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == B2Q_C64)
+    dist_swap_multi_kernel<float4><<<grid, 256, 0, s>>>(reinterpret_cast<float4*>(mine), p);
+  else
+    dist_swap_multi_kernel<double2><<<grid, 256, 0, s>>>(reinterpret_cast<double2*>(mine), p);
+  B2Q_LAUNCH_CHECK("dist_swap_multi_kernel");
+  return B2Q_OK;
+}
 
 extern "C" int b2q_dist_alloc(uint64_t bytes, void** out_ptr) {
   B2Q_REQUIRE(out_ptr != nullptr && bytes > 0, "bad arguments");

@@ -15,6 +15,7 @@ method raises ``B200Error``.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Sequence
 
 import numpy as np
@@ -128,22 +129,101 @@ class DeviceState:
             )
         )
 
+    # ---- tile passes: two consecutive blocks in ONE pass over HBM -------------------------
+    # (b2q_sv_apply_tile_blocks; complex64 states of at least TILE_MIN_BITS bits —
+    # below that a pass is not HBM-bound and pairing buys nothing)
+    TILE_MIN_BITS = 22
+
+    def tile_pairing(self) -> bool:
+        return (self.code == _lib.C64 and self.n_bits >= self.TILE_MIN_BITS
+                and os.environ.get('CIRQ_B200_TILE_PAIRS', '1') != '0')
+
+    def _pairable(self, m, b) -> bool:
+        return np.ndim(m) == 2 and len(b) <= 5
+
+    def plan_passes(self, gates: Sequence[tuple]) -> list[list[tuple]]:
+        """Groups [(matrix, bits), ...] into kernel launches, in order: each inner
+        list is ONE pass over the state — a single block, or two consecutive dense
+        blocks of <= 5 bits each, whose targets always fit one 12-bit tile."""
+        gates = list(gates)
+        if not self.tile_pairing():
+            return [[g] for g in gates]
+        out, i = [], 0
+        while i < len(gates):
+            if (i + 1 < len(gates) and self._pairable(*gates[i]) and self._pairable(*gates[i + 1])
+                    and len(set(gates[i][1]) | set(gates[i + 1][1]) | {0, 1}) <= 12):
+                out.append([gates[i], gates[i + 1]])
+                i += 2
+            else:
+                out.append([gates[i]])
+                i += 1
+        return out
+
+    def split_unpaired_tail(self, gates: Sequence[tuple]):
+        """(apply now, hold back): while more blocks are still being scheduled, a
+        trailing dense block without a partner is worth keeping for the next batch."""
+        gates = list(gates)
+        if not gates or not self.tile_pairing():
+            return gates, []
+        passes = self.plan_passes(gates)
+        if len(passes[-1]) == 1 and self._pairable(*passes[-1][0]):
+            return gates[:-1], gates[-1:]
+        return gates, []
+
+    def apply_tile_blocks(self, group: Sequence[tuple]) -> None:
+        """The blocks of `group` (1 or 2), in order, in one pass over HBM."""
+        torch = _torch()
+        ks = [len(b) for _, b in group]
+        targets = [int(t) for _, b in group for t in b]
+        mats = np.concatenate([_lib.as_c128_buffer(m).reshape(-1) for m, _ in group])
+        check(
+            self._lib.b2q_sv_apply_tile_blocks(
+                self.ptr, self.code, self.n_bits, len(group), _lib.int_array(ks),
+                _lib.int_array(targets), mats.ctypes.data, _stream_ptr(torch),
+            )
+        )
+
     def apply_batch(self, gates: Sequence[tuple]) -> None:
-        """Applies [(matrix, bits), ...] in order with one library call."""
+        """Applies [(matrix, bits), ...] in order; consecutive dense blocks travel
+        two per pass where the tile kernel applies (`plan_passes`)."""
         torch = _torch()
         if not gates:
             return
-        if any(np.ndim(m) == 1 for m, _ in gates):
-            # diagonal blocks (1-D: the diagonal entries) between runs of dense ones
+        if self.tile_pairing() and len(gates) > 1:
             run: list = []
+            for group in self.plan_passes(gates):
+                if len(group) == 2:
+                    self._apply_singles(run)
+                    run = []
+                    self.apply_tile_blocks(group)
+                else:
+                    run.append(group[0])
+            self._apply_singles(run)
+            return
+        self._apply_singles(gates)
+
+    def _apply_singles(self, gates: Sequence[tuple]) -> None:
+        """One pass per block: diagonal blocks (1-D: the diagonal entries) between
+        runs of dense ones."""
+        if not gates:
+            return
+        if any(np.ndim(m) == 1 for m, _ in gates):
+            run = []
             for m, b in gates:
                 if np.ndim(m) == 1:
-                    self.apply_batch(run)
+                    self._apply_dense_run(run)
                     run = []
                     self.apply_diagonal(m, b)
                 else:
                     run.append((m, b))
-            self.apply_batch(run)
+            self._apply_dense_run(run)
+            return
+        self._apply_dense_run(gates)
+
+    def _apply_dense_run(self, gates: Sequence[tuple]) -> None:
+        """Dense blocks, one pass each, with one library call."""
+        torch = _torch()
+        if not gates:
             return
         max_fast = 5 if self.code == _lib.C64 else 4
         if any(len(b) > max_fast for _, b in gates):

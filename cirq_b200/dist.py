@@ -175,6 +175,32 @@ class ShardBackend:
         )
         self.device_barrier()
 
+    def swap_bits(self, pairs: Sequence[tuple[int, int]]) -> None:
+        """Multi-bit exchange, one kernel per rank: `pairs` = [(rank bit index,
+        local bit)], ascending in the local bit.  All ranks call it."""
+        m = len(pairs)
+        rho = 0
+        for i, (gi, _) in enumerate(pairs):
+            rho |= ((self.rank >> gi) & 1) << i
+        base = self.rank
+        for gi, _ in pairs:
+            base &= ~(1 << gi)
+        peers = (ctypes.c_void_p * (1 << m))()
+        for c in range(1 << m):
+            r = base
+            for i, (gi, _) in enumerate(pairs):
+                r |= ((c >> i) & 1) << gi
+            peers[c] = None if r == self.rank else self.peer_ptrs[r]
+        self.device_barrier()
+        stream = ctypes.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+        check(
+            self.lib.b2q_dist_swap_bits(
+                ctypes.c_void_p(self._ptr), peers, self.local.code, self.n_local,
+                _lib.int_array([l for _, l in pairs]), m, rho, stream,
+            )
+        )
+        self.device_barrier()
+
     def apply_exchange(self, matrix, bits: Sequence[int], partner: int, local_bit: int,
                        my_gbit: int) -> None:
         """One 4/5-qubit block and the exchange of `local_bit` with the pair's
@@ -275,12 +301,17 @@ class ShardedStateVector:
         # logical bit -> physical bit (physical bits >= n_local are global)
         self.phys = list(range(self.n))
         self.swaps = 0
+        self.exchanges = 0        # exchange kernels (a multi-bit exchange counts once)
+        self.exchange_volume = 0.0  # shard fractions sent per rank, summed
         # bench.py's instrumentation: on_kernel(kind, block, run) must call run()
         self.on_kernel = None
         self.fused_exchanges = 0
         self.passes = 0
         self.local_only_blocks = 0
         self.diag_global_blocks = 0
+        import os
+
+        self.multi_bit_exchange = os.environ.get('CIRQ_B200_MULTI_BIT_EXCHANGE', '1') != '0'
         if initial_index is not None:
             self._init_basis(initial_index)
 
@@ -381,6 +412,31 @@ class ShardedStateVector:
             elif self.phys[l] == local_phys:
                 self.phys[l] = global_phys
         self.swaps += 1
+        self.exchanges += 1
+        self.exchange_volume += 0.5
+
+    def exchange_bits(self, pairs: Sequence[tuple[int, int]]) -> None:
+        """Exchanges several (global physical bit, local physical bit) pairs with ONE
+        kernel per rank: (1 - 2^-m) of the shard travels instead of m halves."""
+        pairs = sorted(pairs, key=lambda gl: gl[1])
+        if len(pairs) == 1 or not hasattr(self.backend, 'swap_bits'):
+            for g, l in pairs:
+                self.swap_global_local(g, l)
+            return
+        run = lambda: self.backend.swap_bits([(g - self.n_local, l) for g, l in pairs])
+        if self.on_kernel is None:
+            run()
+        else:
+            self.on_kernel('exchange%d' % len(pairs), None, run)
+        for g, l in pairs:
+            for w in range(self.n):
+                if self.phys[w] == g:
+                    self.phys[w] = l
+                elif self.phys[w] == l:
+                    self.phys[w] = g
+        self.swaps += len(pairs)
+        self.exchanges += 1
+        self.exchange_volume += 1.0 - 0.5 ** len(pairs)
 
     # ------------------------------------------------------------------ gates
 
@@ -416,28 +472,56 @@ class ShardedStateVector:
             m, ws = remaining[0]
             needed = [w for w in ws if self.phys[w] >= self.n_local]
             protected = {self.phys[w] for w in ws}
-            for i, w in enumerate(needed):
+            pairs = []
+            for w in needed:
                 victim = self._choose_victim(remaining, protected)
                 protected.add(victim)
-                if i == 0:
-                    fused = self._fusable(pending, victim)
-                    if fused is not None:
-                        # the last local pass and the exchange travel as ONE kernel
-                        self._run_local(pending[:-1])
-                        self.swap_global_local(self.phys[w], victim, fused_block=fused)
-                        continue
-                    self._run_local(pending)
-                self.swap_global_local(self.phys[w], victim)
+                pairs.append((self.phys[w], victim))
+            # Look ahead: a global wire that a later block needs BEFORE the local bit
+            # it would evict is used again joins this exchange — a 3-bit exchange
+            # moves 7/8 of a shard once, three 1-bit swaps 3/2 of it.
+            if self.multi_bit_exchange and hasattr(self.backend, 'swap_bits'):
+                first_use = {}
+                for pos, (_, bws) in enumerate(remaining):
+                    for w in bws:
+                        first_use.setdefault(w, pos)
+                cands = sorted((pos, w) for w, pos in first_use.items()
+                               if self.phys[w] >= self.n_local and w not in needed)
+                for pos, w in cands:
+                    if len(pairs) >= 3:
+                        break
+                    try:
+                        victim, victim_pos = self._choose_victim(remaining, protected, with_pos=True)
+                    except RuntimeError:
+                        break
+                    if victim_pos <= pos:
+                        break  # the evicted bit would be needed first: no gain
+                    protected.add(victim)
+                    pairs.append((self.phys[w], victim))
+            if len(pairs) == 1 or not self.multi_bit_exchange or not hasattr(self.backend, 'swap_bits'):
+                for i, (gbit, victim) in enumerate(pairs):
+                    if i == 0:
+                        fused = self._fusable(pending, victim)
+                        if fused is not None:
+                            # the last local pass and the exchange travel as ONE kernel
+                            self._run_local(pending[:-1])
+                            self.swap_global_local(gbit, victim, fused_block=fused)
+                            continue
+                        self._run_local(pending)
+                    self.swap_global_local(gbit, victim)
+            else:
+                self._run_local(pending)
+                self.exchange_bits(pairs)
 
     def _run_local(self, batch) -> None:
         if batch:
             if self.on_kernel is None:
                 self.local.apply_batch(batch)
             else:
-                # instrumented (bench.py): one call per block, bracketed by the hook
-                for blk in batch:
-                    self.on_kernel('pass', blk, lambda blk=blk: self.local.apply_batch([blk]))
-            self.passes += len(batch)
+                # instrumented (bench.py): one call per pass, bracketed by the hook
+                for group in self.local.plan_passes(batch):
+                    self.on_kernel('pass', group, lambda group=group: self.local.apply_batch(group))
+            self.passes += len(self.local.plan_passes(batch)) if hasattr(self.local, 'plan_passes') else len(batch)
 
     def _fusable(self, pending, victim: int):
         """(matrix, bits) of the last pending pass widened to the 4/5 qubits the
@@ -493,9 +577,9 @@ class ShardedStateVector:
             return sub, []
         return sub, rest
 
-    def _choose_victim(self, remaining, protected: set[int]) -> int:
+    def _choose_victim(self, remaining, protected: set[int], with_pos: bool = False):
         """Local physical bit (not protected, >= 1 for 16-byte vectors) whose
-        next use is furthest in the future."""
+        next use is furthest in the future (`with_pos`: also that position)."""
         next_use = {}
         for pos, (_, ws) in enumerate(remaining):
             for w in ws:
@@ -512,7 +596,7 @@ class ShardedStateVector:
                 best, best_pos = p, pos
         if best is None:
             raise RuntimeError('no local bit available to swap with')
-        return best
+        return (best, best_pos) if with_pos else best
 
     # ------------------------------------------------------------------ read-out
 

@@ -176,7 +176,7 @@ def measure(workload, args, world, rank, local_rank, steps, warmup, n_local=None
             elif kind == 'pass+exchange':
                 kname = 'sv_apply_tc_staged_kernel + exchange (b2q_dist_apply_exchange)'
             else:
-                kname = B.block_kernel_name(blk[0], blk[1], sv.n_local)[0]
+                kname = B.pass_kernel_name(blk, sv.n_local)
             events.append((kname, a, b))
 
         record_steps = 2

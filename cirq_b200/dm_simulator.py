@@ -55,6 +55,7 @@ class B200DensityMatrix(qis.QuantumStateRepresentation):
         self.passes = 0
         self._since_drain = 0
         self._drain_every = max(8, 2 * self._n)
+        self._held: list = []  # final blocks kept back by a drain to be paired later
         self._host = None  # cached host copy, dropped on every mutation
 
     @classmethod
@@ -124,18 +125,22 @@ class B200DensityMatrix(qis.QuantumStateRepresentation):
         if self._since_drain < self._drain_every:
             return
         self._since_drain = 0
-        ready = self._fuser.pop_final_blocks()
+        ready = self._held + self._fuser.pop_final_blocks()
+        # (a trailing block without a partner waits for the next batch: two blocks
+        # share one pass over HBM, DeviceState.plan_passes)
+        ready, self._held = self._dev.split_unpaired_tail(ready)
         if ready:
             self._dev.apply_batch(ready)
-            self.passes += len(ready)
+            self.passes += len(self._dev.plan_passes(ready))
 
     def flush(self) -> None:
-        if len(self._fuser) == 0:
+        if len(self._fuser) == 0 and not self._held:
             return
-        blocks = self._fuser.blocks()
+        blocks = self._held + self._fuser.blocks()
+        self._held = []
         self._fuser.clear()
         self._dev.apply_batch(blocks)
-        self.passes += len(blocks)
+        self.passes += len(self._dev.plan_passes(blocks))
 
     @property
     def device_state(self) -> DeviceState:

@@ -21,21 +21,23 @@ from cirq_b200.fusion import fuser_for
 
 
 class _Component:
-    __slots__ = ('bits', 'dev', 'fuser', 'passes')
+    __slots__ = ('bits', 'dev', 'fuser', 'passes', 'held')
 
     def __init__(self, bits, dev, fuser):
         self.bits = list(bits)  # logical bits, most significant first
         self.dev = dev
         self.fuser = fuser
         self.passes = 0
+        self.held = []  # final blocks kept back by drain() to be paired later
 
     def wire(self, bit: int) -> int:
         return len(self.bits) - 1 - self.bits.index(bit)
 
     def flush(self) -> None:
-        if len(self.fuser):
+        if len(self.fuser) or self.held:
             # relabelled SWAPs are not undone: the component renames its bits
-            blocks = self.fuser.blocks(restore=False)
+            blocks = self.held + self.fuser.blocks(restore=False)
+            self.held = []
             self.fuser.clear()
             self.dev.apply_batch(blocks)
             self.passes += len(blocks)
@@ -48,7 +50,11 @@ class _Component:
             self.bits = moved
 
     def drain(self) -> None:
-        ready = self.fuser.pop_final_blocks()
+        ready = self.held + self.fuser.pop_final_blocks()
+        split = getattr(self.dev, 'split_unpaired_tail', None)
+        # (a trailing block without a partner waits for the next batch: two blocks
+        # share one pass over HBM, DeviceState.plan_passes)
+        ready, self.held = split(ready) if split else (ready, [])
         if ready:
             self.dev.apply_batch(ready)
             self.passes += len(ready)
@@ -169,21 +175,47 @@ class _RecordingState:
     ops: list = []
     counter = 0
 
-    def __init__(self, n_bits, ident):
+    def __init__(self, n_bits, ident, dtype=np.complex64):
+        from cirq_b200 import _lib
+
         self.n_bits = n_bits
         self.ident = ident
+        self.dtype = np.dtype(dtype)
+        self.code = _lib.dtype_code(self.dtype)
 
     @classmethod
     def basis(cls, n_bits, dtype, index=0):
         cls.counter += 1
         cls.ops.append(('basis', cls.counter, n_bits, index))
-        return cls(n_bits, cls.counter)
+        return cls(n_bits, cls.counter, dtype)
 
     def kron(self, other):
         cls = type(self)
         cls.counter += 1
         cls.ops.append(('kron', cls.counter, self.ident, other.ident))
-        return cls(self.n_bits + other.n_bits, cls.counter)
+        return cls(self.n_bits + other.n_bits, cls.counter, self.dtype)
+
+    # the pass grouping of the device state the plan will be replayed on, so that a
+    # recorded schedule holds back unpaired blocks exactly like a live one
+    def tile_pairing(self):
+        from cirq_b200.device_state import DeviceState
+
+        return DeviceState.tile_pairing(self)
+
+    TILE_MIN_BITS = 22
+
+    def _pairable(self, m, b):
+        return np.ndim(m) == 2 and len(b) <= 5
+
+    def plan_passes(self, gates):
+        from cirq_b200.device_state import DeviceState
+
+        return DeviceState.plan_passes(self, gates)
+
+    def split_unpaired_tail(self, gates):
+        from cirq_b200.device_state import DeviceState
+
+        return DeviceState.split_unpaired_tail(self, gates)
 
     def apply_batch(self, blocks):
         type(self).ops.append(('apply', self.ident, [(np.asarray(m), tuple(w)) for m, w in blocks]))

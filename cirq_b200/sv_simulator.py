@@ -66,6 +66,7 @@ class B200StateVector(qis.QuantumStateRepresentation):
         self.passes = 0  # GPU gate passes issued so far (for benchmarks)
         self._since_drain = 0
         self._drain_every = max(8, self._n)
+        self._held: list = []  # final blocks kept back by _drain to be paired later
         self._host = None  # cached host copy of the state, dropped on every mutation
         # logical bit -> index bit holding it, after SWAP gates that were relabelled
         # instead of executed and not yet undone (None: every bit in its place)
@@ -125,10 +126,13 @@ class B200StateVector(qis.QuantumStateRepresentation):
         """Launches the blocks that can no longer grow, so the GPU works while
         the host keeps scheduling (kernel launches are asynchronous)."""
         self._since_drain = 0
-        ready = self._fuser.pop_final_blocks()
+        ready = self._held + self._fuser.pop_final_blocks()
+        # (a trailing block without a partner waits for the next batch: two blocks
+        # share one pass over HBM, DeviceState.plan_passes)
+        ready, self._held = self._dev.split_unpaired_tail(ready)
         if ready:
             self._dev.apply_batch(ready)
-            self.passes += len(ready)
+            self.passes += len(self._dev.plan_passes(ready))
 
     def flush(self, restore: bool = True) -> None:
         """Applies the queued gates.  SWAP gates the scheduler relabelled are undone
@@ -144,10 +148,12 @@ class B200StateVector(qis.QuantumStateRepresentation):
         else:
             blocks = self._fuser.blocks(restore=False)
         self._fuser.clear()
+        blocks = self._held + blocks
+        self._held = []
         if blocks:
             self._host = None
             self._dev.apply_batch(blocks)
-            self.passes += len(blocks)
+            self.passes += len(self._dev.plan_passes(blocks))
         if not restore:
             moved = self._fuser.take_permutation()
             if moved:
@@ -296,6 +302,7 @@ class B200StateVector(qis.QuantumStateRepresentation):
 
     def replace_device_state(self, dev: DeviceState) -> None:
         self._fuser.clear()
+        self._held = []
         self._host = None
         self._dev = dev
 

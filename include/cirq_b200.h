@@ -91,6 +91,21 @@ int b2q_sv_apply_batch(void* state, int dtype, int n_qubits, int num_gates, cons
                        const int* targets, const double* matrices_c128, void* scratch,
                        void* stream);
 
+/* Applies `num_blocks` (1 or 2) fused blocks IN ORDER with ONE pass over HBM
+ * (complex64, each k <= 5): a CTA stages a tile of 2^12 amplitudes spanning the
+ * union of the blocks' targets in shared memory, applies every block to it on
+ * the tensor cores (3xTF32, fp32 accuracy) and writes it back once — half the
+ * HBM traffic per block of b2q_sv_apply_batch.  ks / targets / matrices_c128 as
+ * in b2q_sv_apply_batch.  The union of all targets together with index bits 0
+ * and 1 must not exceed 12 bits and n_qubits >= 12: b2q_tile_blocks_feasible
+ * (host-only, returns 1/0) tells; otherwise B2Q_ERR_INVALID.  Same reference
+ * call sites as b2q_sv_apply_batch (sim/simulator_base.py:199-212 over
+ * linalg/transformations.py:105-172). */
+int b2q_sv_apply_tile_blocks(void* state, int dtype, int n_qubits, int num_blocks, const int* ks,
+                             const int* targets, const double* matrices_c128, void* stream);
+int b2q_tile_blocks_feasible(int dtype, int n_qubits, int num_blocks, const int* ks,
+                             const int* targets);
+
 /* psi[i] <- diag[bits of i at `targets`] * psi[i]  (diag: complex128[2^k],
  * first target = MSB).  Replaces the diagonal slice fast paths
  * ops/common_gates.py:658-669 (Z), :1072-1083 (CZ) and
@@ -252,6 +267,18 @@ int b2q_dist_ipc_close(void* ptr);
 int b2q_dist_swap_bit(void* mine, void* peer, int dtype, int n_local, int local_bit,
                       int my_global_bit_value, void* stream);
 
+/* Multi-bit exchange: the m (1..3) local bits `local_bits` (ascending) trade places
+ * with m global bits in ONE kernel per rank.  `my_sub_rank` = this rank's values of
+ * the exchanged global bits (bit i pairs with local_bits[i]); `peers[c]` = the shard
+ * (peer-mapped) of the rank whose exchanged global bits read c and whose other rank
+ * bits equal this rank's (entry [my_sub_rank] is ignored).  Each rank keeps the
+ * sub-block whose local bits read my_sub_rank and swaps every other sub-block c
+ * with sub-block my_sub_rank of peers[c]: (1 - 2^-m) of the shard out and in per
+ * rank instead of m halves.  In place; all 2^m ranks of a group call it between
+ * two barriers.  local bits >= 1 for complex64 (16-byte vectors). */
+int b2q_dist_swap_bits(void* mine, void* const* peers, int dtype, int n_local,
+                       const int* local_bits, int m, int my_sub_rank, void* stream);
+
 /* One 4- or 5-qubit block (complex64) applied to `shard_in` and, in the same
  * kernel, the global<->local exchange of b2q_dist_swap_bit: results whose index
  * bit `local_bit` equals this rank's value of the global bit are written to
@@ -339,6 +366,10 @@ int b2q_set_tc_stage_opts(int early, int l2_ahead);
  * permutation to sorted-target order; no GPU needed. */
 int b2q_debug_plan(int dtype, int n_qubits, const int* targets, int k, int* out);
 int b2q_debug_permute_matrix(const double* matrix_c128, const int* targets, int k, double* out);
+/* Host-only: address tables of the tile kernel (b2q_sv_apply_tile_blocks) for
+ * `num_blocks` blocks of 5 ascending targets each (layout of `out`: see
+ * tests/test_plan_host.py). */
+int b2q_debug_tile_plan(int n_qubits, int num_blocks, const int* sorted_targets, int64_t* out);
 /* Host-only: address tables of the staged tensor-core kernel for ascending
  * targets (layout of `out`, 86 int64: see tests/test_plan_host.py). */
 int b2q_debug_tc_stage_plan(int n_qubits, const int* sorted_targets, int k, int64_t* out);

@@ -58,12 +58,36 @@ class OracleDeviceState:
     def apply_matrix(self, matrix, bits):
         self.array = orc.apply_matrix(self.array, self.n_bits, np.asarray(matrix), list(bits))
 
+    # tile pairing, as in DeviceState but from 4 bits on so that the CPU tests
+    # exercise the host logic around it (held-back blocks, pass grouping)
+    TILE_MIN_BITS = 4
+    tile_calls = 0
+
+    def tile_pairing(self):
+        return self.dtype == np.dtype(np.complex64) and self.n_bits >= self.TILE_MIN_BITS
+
+    def _pairable(self, m, b):
+        return np.ndim(m) == 2 and len(b) <= 5
+
+    def plan_passes(self, gates):
+        from cirq_b200.device_state import DeviceState
+
+        return DeviceState.plan_passes(self, gates)
+
+    def split_unpaired_tail(self, gates):
+        from cirq_b200.device_state import DeviceState
+
+        return DeviceState.split_unpaired_tail(self, gates)
+
     def apply_batch(self, gates):
-        for m, b in gates:
-            if np.ndim(m) == 1:  # a diagonal block
-                self.apply_diagonal(m, b)
-            else:
-                self.apply_matrix(m, b)
+        for group in self.plan_passes(gates):
+            if len(group) == 2:
+                type(self).tile_calls += 1
+            for m, b in group:
+                if np.ndim(m) == 1:  # a diagonal block
+                    self.apply_diagonal(m, b)
+                else:
+                    self.apply_matrix(m, b)
 
     def apply_diagonal(self, diag, bits):
         self.array = orc.apply_diagonal(self.array, self.n_bits, diag, list(bits))

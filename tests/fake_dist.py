@@ -39,6 +39,41 @@ class GlooShardBackend:
         arr[sel] = recv_t.numpy().view(self.dtype)
         dist.barrier()
 
+    def swap_bits(self, pairs):
+        """Multi-bit exchange (same result as the CUDA kernel): sub-block c of this
+        rank trades places with sub-block rho of the rank whose sub-rank is c."""
+        m = len(pairs)
+        arr = self.local.array
+        idx = np.arange(arr.size, dtype=np.int64)
+        sub = np.zeros_like(idx)
+        rho = 0
+        base = self.rank
+        for i, (gi, l) in enumerate(pairs):
+            sub |= ((idx >> l) & 1) << i
+            rho |= ((self.rank >> gi) & 1) << i
+            base &= ~(1 << gi)
+        real = np.float64 if self.dtype == np.complex128 else np.float32
+        incoming = {}
+        for c in range(1 << m):
+            if c == rho:
+                continue
+            partner = base
+            for i, (gi, _) in enumerate(pairs):
+                partner |= ((c >> i) & 1) << gi
+            send_t = torch.from_numpy(np.ascontiguousarray(arr[sub == c]).view(real).copy())
+            recv_t = torch.empty_like(send_t)
+            if self.rank < partner:
+                dist.send(send_t, partner)
+                dist.recv(recv_t, partner)
+            else:
+                dist.recv(recv_t, partner)
+                dist.send(send_t, partner)
+            incoming[c] = recv_t.numpy().view(self.dtype)
+        for c, data in incoming.items():
+            arr[sub == c] = data
+        dist.barrier()
+        self.multi_calls = getattr(self, 'multi_calls', 0) + 1
+
     can_fuse_exchange = True
 
     def apply_exchange(self, matrix, bits, partner, local_bit, my_gbit):

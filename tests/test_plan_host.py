@@ -415,3 +415,150 @@ def test_library_exports_every_symbol_the_header_declares():
     assert bound <= declared, f'bound but not declared in the header: {sorted(bound - declared)}'
     assert lib.b2q_version() > 0
     assert isinstance(lib.b2q_last_error(), bytes)
+
+
+# ---- tile kernel (two blocks per HBM pass): replay of its address tables ----------------
+
+def _tile_slot(local, xmask):
+    s = local & ~0xE
+    for d in range(3):
+        s |= (bin(local & xmask[d]).count('1') & 1) << (d + 1)
+    return s
+
+
+def _tile_plan(lib, n, blocks_sorted):
+    import ctypes
+
+    nb = len(blocks_sorted)
+    flat = _lib.int_array([t for b in blocks_sorted for t in b])
+    out = (ctypes.c_int64 * (12 + 3 + 16 + 16 + nb * 40))()
+    rc = lib.b2q_debug_tile_plan(n, nb, flat, out)
+    if rc != 0:
+        return None
+    v = list(out)
+    plan = dict(tbits=v[0:12], xmask=v[12:15], rgoff=v[15:31], rslot=v[31:47], blocks=[])
+    o = 47
+    for _ in range(nb):
+        plan['blocks'].append(dict(vec=v[o], gbit=v[o + 1:o + 8], mslot=v[o + 8:o + 40]))
+        o += 40
+    return plan
+
+
+def _tile_emulate(lib, n, state, blocks):
+    """Replays sv_apply_tc_tile_kernel's data movement on the CPU: blocks =
+    [(matrix 32x32 in the caller's target order, targets[5])].  Returns the new
+    state; asserts bijections and bank-conflict freedom on the way."""
+    import ctypes
+
+    sorted_blocks = [sorted(t) for _, t in blocks]
+    plan = _tile_plan(lib, n, sorted_blocks)
+    assert plan is not None
+    tbits, xmask = plan['tbits'], plan['xmask']
+    assert tbits[0] == 0 and tbits[1] == 1 and tbits == sorted(tbits)
+    mats = []
+    for m, t in blocks:
+        out = np.empty((32, 32), dtype=np.complex128)
+        src = np.ascontiguousarray(m, dtype=np.complex128)
+        assert lib.b2q_debug_permute_matrix(src.ctypes.data, _lib.int_array(t), 5, out.ctypes.data) == 0
+        mats.append(out)
+    state = state.copy()
+    threads = np.arange(128)
+    lane, warp = threads & 31, threads >> 5
+    thr_local = (lane << 1) | (warp << 6)
+    thr_goff = np.zeros(128, dtype=np.int64)
+    for i in range(1, 8):
+        thr_goff += ((thr_local >> i) & 1).astype(np.int64) << tbits[i]
+    thr_slot = np.array([_tile_slot(int(x), xmask) for x in thr_local])
+    # copy pattern: a bijection onto the 4096 slots, quarter-warps conflict free
+    slots = (thr_slot[:, None] ^ np.array(plan['rslot'])[None, :])
+    assert sorted(np.concatenate([slots.reshape(-1), slots.reshape(-1) + 1]).tolist()) == list(range(4096))
+    for r in range(16):
+        for q0 in range(0, 128, 8):
+            assert len({(int(s) >> 1) & 7 for s in slots[q0:q0 + 8, r]}) == 8
+    goffs = thr_goff[:, None] + np.array(plan['rgoff'], dtype=np.int64)[None, :]
+    for tile in range(1 << (n - 12)):
+        base = tile
+        for pos in tbits:
+            base = ((base >> pos) << (pos + 1)) | (base & ((1 << pos) - 1))
+        smem = np.zeros(4096, dtype=state.dtype)
+        smem[slots] = state[base + goffs]
+        smem[slots + 1] = state[base + goffs + 1]
+        for blk, m in zip(plan['blocks'], mats):
+            gl = np.zeros(128, dtype=np.int64)
+            for i in range(7):
+                gl |= ((threads >> i) & 1) << blk['gbit'][i]
+            sg = np.array([_tile_slot(int(x), xmask) for x in gl])
+            addr = sg[:, None] ^ np.array(blk['mslot'])[None, :]
+            if tile == 0:
+                assert sorted(addr.reshape(-1).tolist()) == list(range(4096))
+                if blk['vec']:
+                    assert np.all(addr[:, 1::2] == addr[:, 0::2] + 1) and np.all(addr[:, 0::2] % 2 == 0)
+                    for j in range(0, 32, 2):
+                        for q0 in range(0, 128, 8):
+                            assert len({(int(s) >> 1) & 7 for s in addr[q0:q0 + 8, j]}) == 8
+                else:
+                    for j in range(32):
+                        for h0 in range(0, 128, 16):
+                            assert len({int(s) & 15 for s in addr[h0:h0 + 16, j]}) == 16
+            x = smem[addr]  # [thread, member]
+            smem[addr] = x @ m.T
+        state[base + goffs] = smem[slots]
+        state[base + goffs + 1] = smem[slots + 1]
+    return state
+
+
+def test_tile_kernel_plan_replays_to_the_oracle():
+    """Host emulation of the two-blocks-per-pass kernel against the oracle, over
+    target sets that exercise every layout case (low bits, overlaps, widest union)."""
+    lib = _lib.load()
+    rng = np.random.RandomState(11)
+
+    def unitary(k):
+        d = 1 << k
+        q, r = np.linalg.qr(rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d)))
+        return q * (np.diag(r) / np.abs(np.diag(r)))
+
+    n = 14
+    cases = [([0, 1, 2, 3, 4], [5, 6, 7, 8, 9]), ([9, 10, 11, 12, 13], [4, 5, 6, 7, 8]),
+             ([13, 0, 5, 2, 9], [9, 2, 11, 3, 7]), ([2, 3, 4, 5, 6], [2, 3, 4, 5, 6]),
+             ([1, 3, 5, 7, 9], [0, 2, 4, 6, 8]), ([13, 12, 11, 10, 9], [8, 7, 6, 5, 4]),
+             ([4, 13, 8, 6, 11], [12, 5, 4, 10, 3])]
+    for _ in range(25):
+        a = rng.permutation(n)[:5].tolist()
+        pool = [b for b in range(n)]
+        b = rng.permutation(pool)[:5].tolist()
+        cases.append((a, b))
+    checked = 0
+    for ta, tb in cases:
+        if len(set(ta) | set(tb) | {0, 1}) > 12:
+            assert _tile_plan(lib, n, [sorted(ta), sorted(tb)]) is None
+            continue
+        state = (rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)) / 2 ** (n / 2)
+        ma, mb = unitary(5), unitary(5)
+        got = _tile_emulate(lib, n, state, [(ma, ta), (mb, tb)])
+        want = orc.apply_matrix(orc.apply_matrix(state, n, ma, ta), n, mb, tb)
+        np.testing.assert_allclose(got, want, atol=1e-12)
+        checked += 1
+    assert checked >= 20
+    # a single block is a valid tile pass too
+    state = (rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)) / 2 ** (n / 2)
+    m = unitary(5)
+    got = _tile_emulate(lib, n, state, [(m, [3, 12, 0, 7, 9])])
+    np.testing.assert_allclose(got, orc.apply_matrix(state, n, m, [3, 12, 0, 7, 9]), atol=1e-12)
+
+
+def test_tile_blocks_feasibility():
+    lib = _lib.load()
+    ok = lib.b2q_tile_blocks_feasible(_lib.C64, 30, 2, _lib.int_array([5, 5]),
+                                      _lib.int_array([29, 28, 27, 26, 25, 24, 23, 22, 21, 20]))
+    assert ok == 1
+    # 11 distinct high bits + bits 0, 1 = 13 > 12
+    assert lib.b2q_tile_blocks_feasible(_lib.C64, 30, 2, _lib.int_array([5, 5]),
+                                        _lib.int_array([29, 28, 27, 26, 25, 24, 23, 22, 21, 20][:5] +
+                                                       [19, 18, 17, 16, 15])) == 1
+    assert lib.b2q_tile_blocks_feasible(_lib.C128, 30, 2, _lib.int_array([5, 5]),
+                                        _lib.int_array(list(range(2, 12)))) == 0
+    assert lib.b2q_tile_blocks_feasible(_lib.C64, 11, 2, _lib.int_array([5, 5]),
+                                        _lib.int_array(list(range(0, 10)))) == 0
+    assert lib.b2q_tile_blocks_feasible(_lib.C64, 30, 2, _lib.int_array([3, 2]),
+                                        _lib.int_array([4, 9, 1, 0, 17])) == 1
