@@ -67,6 +67,7 @@ SIGNATURES = {
     ),
     'b2q_sv_kron': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'b2q_sv_permute_bits': (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_int), c_void_p]),
+    'b2q_sv_permute_bits_inplace': (c_int, [c_void_p, c_int, c_int, POINTER(c_int), POINTER(c_int), c_void_p]),
     'b2q_sv_argmax_abs': (c_int, [c_void_p, c_int, c_int, POINTER(c_uint64), c_void_p]),
     'b2q_sv_kron_allclose': (
         c_int,
@@ -121,6 +122,7 @@ DEBUG_SIGNATURES = {
     'b2q_set_tc_stage_opts': (c_int, [c_int, c_int]),
     'b2q_debug_tc_stage_plan': (c_int, [c_int, POINTER(c_int), c_int, POINTER(ctypes.c_int64)]),
     'b2q_debug_plan': (c_int, [c_int, c_int, POINTER(c_int), c_int, POINTER(c_int)]),
+    'b2q_debug_permute_plan': (c_int, [c_int, c_int, POINTER(c_int), c_int, POINTER(c_int), POINTER(c_int)]),
     'b2q_debug_tile_plan': (c_int, [c_int, c_int, POINTER(c_int), POINTER(ctypes.c_int64)]),
     'b2q_debug_permute_matrix': (c_int, [c_void_p, POINTER(c_int), c_int, c_void_p]),
 }

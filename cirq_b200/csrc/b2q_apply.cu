@@ -820,7 +820,7 @@ static void widen_block_to_5(const double* m128, const int* targets, int k, cons
   int wide[5];
   const int extra = 5 - k;
   int e = 0;
-  for (int i = 11; i >= 0 && e < extra; --i) {
+  for (int i = 12; i >= 0 && e < extra; --i) {
     bool used = false;
     for (int q = 0; q < k; ++q) used |= targets[q] == tbits[i];
     if (!used) wide[e++] = tbits[i];
@@ -928,7 +928,7 @@ extern "C" int b2q_tile_blocks_feasible(int dtype, int n_qubits, int num_blocks,
                                         const int* targets) {
   if (dtype != B2Q_C64 || ks == nullptr || targets == nullptr) return 0;
   if (!tc_applicable(dtype, n_qubits, 5)) return 0;
-  int tbits[12];
+  int tbits[16];
   return tile_bits_for(n_qubits, num_blocks, ks, targets, tbits) ? 1 : 0;
 }
 
@@ -940,9 +940,9 @@ extern "C" int b2q_sv_apply_tile_blocks(void* state, int dtype, int n_qubits, in
   B2Q_REQUIRE(dtype == B2Q_C64, "tile passes are complex64 only");
   B2Q_REQUIRE(num_blocks >= 1 && num_blocks <= 2, "a tile pass takes 1 or 2 blocks, got %d", num_blocks);
   B2Q_REQUIRE(tc_applicable(dtype, n_qubits, 5), "tensor-core kernels not applicable (n=%d)", n_qubits);
-  int tbits[12];
+  int tbits[16];
   B2Q_REQUIRE(tile_bits_for(n_qubits, num_blocks, ks, targets, tbits),
-              "blocks do not fit one 12-bit tile (or bad targets)");
+              "blocks do not fit one 13-bit tile (or bad targets)");
   int sorted[2][5];
   std::vector<float> plain[2];
   const float* mats[2] = {nullptr, nullptr};

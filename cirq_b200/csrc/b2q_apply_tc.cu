@@ -813,46 +813,53 @@ static int launch_tc_staged_kernel(const TcStagedParams& p, cudaStream_t stream)
 // A pass costs 2.6 ms of HBM time at 30 qubits however little it computes, and
 // the 5-qubit tensor-core pass already runs at ~0.9 of the copy rate — the
 // remaining lever is the NUMBER of passes.  Two consecutive 5-qubit blocks
-// touch at most 10 index bits; a CTA tile of 2^12 amplitudes (32 KB) over those
-// bits plus the lowest free ones holds every amplitude group of BOTH blocks.
-// The tile is staged once (cp.async, 16-byte lanes), block A and block B are
-// applied to it in shared memory — gather a group -> 3xTF32 split -> TMEM ->
-// tcgen05.mma -> TMEM -> scatter, exactly the arithmetic of the one-block
-// kernels — and it is written back once: half the HBM traffic per block.
+// touch at most 10 index bits; a CTA tile of 2^13 amplitudes (64 KB) over those
+// bits plus index bits 0-2 (so the tile moves in runs of >= 64 bytes) and the
+// lowest free ones holds every amplitude group of BOTH blocks.  The tile is
+// staged once (cp.async, 16-byte lanes), block A and block B are applied to it
+// in shared memory — gather a group -> 3xTF32 split -> TMEM -> tcgen05.mma ->
+// TMEM -> scatter, exactly the arithmetic of the one-block kernels — and it is
+// written back once: half the HBM traffic per block.
 //
-//   * 4096 amplitudes / 32 per group = 128 groups = ONE UMMA M tile per block.
-//   * A CTA holds two independent compute groups of 128 threads (own tile
-//     buffers, own TMEM half, own mbarrier, named barriers) that share the B
-//     matrices: while one group waits for the tensor core the other moves
-//     data.  Each group double-buffers its tile: the next tile's copy is in
-//     flight while the current one is multiplied.  Shared memory: 2 x 32 KB of
-//     B + 4 x 32 KB of tiles = 192 KB, one CTA per SM, all 512 TMEM columns.
+//   * 8192 amplitudes / 32 per group = 256 groups = TWO UMMA M tiles per block,
+//     each with its own half of TMEM (A_hi | A_lo | D0 | D1) and its own
+//     mbarrier; they share the tile and the B matrices.  512 threads: TWO per
+//     UMMA row (each moves 16 of the group's 32 members, through the two warps
+//     that may touch that TMEM lane quarter), so 16 warps hide the shared-memory,
+//     conversion and TMEM latencies of one another.  Both M tiles gather at the
+//     same time, their MMAs run back to back on the tensor core, and the first
+//     one's epilogue overlaps the second one's MMAs.
+//   * The tile is double buffered, and all HBM traffic is issued while block A is
+//     on the tensor core: the previous tile's write-back and the next tile's copy.  Shared memory: 2 x 32 KB of B + 2 x 64 KB of tile
+//     = 192 KB, one CTA per SM, all 512 TMEM columns.
 //   * The tile is stored swizzled: slot bits 1-3 (the 8-byte bank pairs) are
 //     parities of local-index bits chosen on the host so that the linear copy
 //     pattern and the group gather / scatter of BOTH blocks are free of bank
 //     conflicts (make_tile_params; replayed on the CPU in tests/test_plan_host.py).
-constexpr int kTileBits = 12;
+constexpr int kTileBits = 13;
 constexpr int kTileAmps = 1 << kTileBits;
 constexpr int kTileMaxBlocks = 2;
-constexpr int kTileGroups = 2;
-constexpr int kTileThreads = kTileGroups * kTcThreads;
+constexpr int kTileGroups = 2;              // UMMA M tiles per block = TMEM regions
+constexpr int kTileGroupThreads = 256;      // two threads per UMMA row: one per half of the members
+constexpr int kTileThreads = kTileGroups * kTileGroupThreads;
+constexpr int kTileGroupBits = kTileBits - 5;  // bits of the amplitude-group index
+constexpr int kTileRounds = kTileAmps / 2 / kTileThreads;  // 16-byte copies per thread and tile
 constexpr uint32_t kTileBufBytes = kTileAmps * sizeof(float2);
 constexpr size_t kTileBBytes = TcTraits<5>::kBBytes;  // per block: B_hi + B_lo
-constexpr size_t kTileSmemBytes =
-    kTileMaxBlocks * kTileBBytes + (size_t)kTileGroups * 2 * kTileBufBytes;
+constexpr size_t kTileSmemBytes = kTileMaxBlocks * kTileBBytes + 2ull * kTileBufBytes;
 
 struct TcTileParams {
   float2* state;
   uint64_t num_tiles;
   const float* bmat;  // num_blocks x (B_hi, B_lo), UMMA K-major layout
   int num_blocks;
-  int tbits[kTileBits];  // ascending index positions of the tile bits (tbits[0] = 0, tbits[1] = 1)
+  int tbits[kTileBits];  // ascending index positions of the tile bits (tbits[i] = i for i < 3)
   uint32_t xmask[3];     // slot bit d + 1 = parity(local index & xmask[d])
-  uint64_t rgoff[16];    // copy round r (local bits 8-11) -> element offset in the state
-  uint32_t rslot[16];    // copy round r -> slot offset
-  int vec[kTileMaxBlocks];              // 1: local bit 0 is a target (members 2i, 2i+1 adjacent)
-  int gbit[kTileMaxBlocks][7];          // local position behind thread bit i (lane 0-4, warp 5-6)
-  uint32_t mslot[kTileMaxBlocks][32];   // member j -> slot offset
+  uint64_t rgoff[kTileRounds];  // copy round r (local bits 10-12) -> element offset in the state
+  uint32_t rslot[kTileRounds];  // copy round r -> slot offset
+  int vec[kTileMaxBlocks];                        // 1: local bit 0 is a target (members 2i, 2i+1 adjacent)
+  int gbit[kTileMaxBlocks][kTileGroupBits];       // local position behind bit i of the group index
+  uint32_t mslot[kTileMaxBlocks][32];             // member j -> slot offset
 };
 
 B2Q_HD uint32_t tile_slot(uint32_t local, const uint32_t* xmask) {
@@ -870,24 +877,32 @@ B2Q_HD uint32_t tile_slot(uint32_t local, const uint32_t* xmask) {
 }
 
 __device__ __forceinline__ void group_barrier(int group) {
-  asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(kTcThreads) : "memory");
+  asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(kTileGroupThreads) : "memory");
 }
 
 __global__ void __launch_bounds__(kTileThreads, 1)
     sv_apply_tc_tile_kernel(const __grid_constant__ TcTileParams p) {
   constexpr int kTcDim = 32;
   constexpr int kTcN = 64;
+  constexpr int kHalf = kTcDim / 2;     // members per thread
   constexpr int kGroupCols = 4 * kTcN;  // A_hi | A_lo | D0 | D1
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* sB = reinterpret_cast<float*>(smem_raw);
   __shared__ __align__(8) uint64_t mbar[kTileGroups];
   __shared__ uint32_t tmem_base_s;
 
+  // 16 warps: warp = q | h << 2 | g << 3.  q = TMEM lane quarter (the hardware lets a
+  // warp touch lanes 32 * (warp % 4) ...), h = which half of a group's 32 members this
+  // thread moves, g = UMMA M tile.  Two warps share every lane quarter, so the per-thread
+  // gather / convert / epilogue chains are half as long and four warps per scheduler hide
+  // each other's latencies.
   const int tid = threadIdx.x;
-  const int group = tid >> 7;
-  const int gt = tid & (kTcThreads - 1);  // thread within the group = UMMA row
-  const int warp_g = gt >> 5;
   const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int q = warp & 3;
+  const int h = (warp >> 2) & 1;
+  const int group = warp >> 3;
+  const int gidx = lane | (q << 5) | (group << 7);  // amplitude group of this thread
 
   if (tid < 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -912,48 +927,59 @@ __global__ void __launch_bounds__(kTileThreads, 1)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_group = tmem_base_s + (uint32_t)(group * kGroupCols);
-  const uint32_t lane_base = tmem_group + ((uint32_t)(warp_g * 32) << 16);
+  const uint32_t lane_base = tmem_group + ((uint32_t)(q * 32) << 16);
   const uint32_t d_col = 2 * kTcN;
   constexpr uint32_t idesc =
       (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((128u >> 4) << 24);
   constexpr uint32_t kLbo = kTcN * 16;
   constexpr uint32_t kSbo = 128;
   const uint32_t mbar_s = smem_u32(&mbar[group]);
+  const bool issuer = (tid & (kTileGroupThreads - 1)) == 0;
 
-  // copy pattern: this thread moves local elements (2 * lane | warp << 6 | round << 8), +1
-  const uint32_t thr_local = ((uint32_t)lane << 1) | ((uint32_t)warp_g << 6);
+  // copy pattern: this thread moves local elements (2 * lane | warp << 6 | round << 10), +1
+  const uint32_t thr_local = ((uint32_t)lane << 1) | ((uint32_t)warp << 6);
   uint64_t thr_goff = 0;
 #pragma unroll
-  for (int i = 1; i < 8; ++i) thr_goff += (uint64_t)((thr_local >> i) & 1u) << p.tbits[i];
+  for (int i = 1; i < 10; ++i) thr_goff += (uint64_t)((thr_local >> i) & 1u) << p.tbits[i];
   const uint32_t thr_slot = tile_slot(thr_local, p.xmask);
-  // gather pattern: this thread's group, per block
+  // gather pattern: this thread's amplitude group, per block
   uint32_t sg[kTileMaxBlocks];
 #pragma unroll
   for (int b = 0; b < kTileMaxBlocks; ++b) {
     uint32_t gl = 0;
 #pragma unroll
-    for (int i = 0; i < 7; ++i) gl |= (uint32_t)((gt >> i) & 1) << p.gbit[b][i];
+    for (int i = 0; i < kTileGroupBits; ++i) gl |= (uint32_t)((gidx >> i) & 1) << p.gbit[b][i];
     sg[b] = tile_slot(gl, p.xmask);
   }
-  unsigned char* const tiles =
-      smem_raw + kTileMaxBlocks * kTileBBytes + (size_t)group * 2 * kTileBufBytes;
+  unsigned char* const tiles = smem_raw + kTileMaxBlocks * kTileBBytes;
   const uint32_t tiles_s = smem_u32(tiles);
 
   auto prefetch = [&](uint64_t base, uint32_t buf) {
     const float2* src = p.state + base + thr_goff;
     const uint32_t dst = tiles_s + buf * kTileBufBytes;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
+    for (int r = 0; r < kTileRounds; ++r) {
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + ((thr_slot ^ p.rslot[r]) << 3)),
                    "l"(src + p.rgoff[r])
                    : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  // tile -> HBM, 16-byte lanes, the copy pattern backwards
+  auto copy_out = [&](uint64_t tile_base, uint32_t from_buf) {
+    float2* const dstp = p.state + tile_base + thr_goff;
+    const unsigned char* const src = tiles + (size_t)from_buf * kTileBufBytes;
+    float4 v[kTileRounds];
+#pragma unroll
+    for (int r = 0; r < kTileRounds; ++r)
+      v[r] = *reinterpret_cast<const float4*>(src + ((thr_slot ^ p.rslot[r]) << 3));
+#pragma unroll
+    for (int r = 0; r < kTileRounds; ++r) *reinterpret_cast<float4*>(dstp + p.rgoff[r]) = v[r];
+  };
 
-  const uint64_t stride = (uint64_t)gridDim.x * kTileGroups;
-  uint64_t tile = (uint64_t)blockIdx.x * kTileGroups + (uint64_t)group;
-  uint64_t base = 0;
+  uint64_t tile = blockIdx.x;
+  uint64_t base = 0, prev_base = 0;
+  bool have_prev = false;
   uint32_t parity = 0, buf = 0;
   if (tile < p.num_tiles) {
     base = insert_zero_bits(tile, p.tbits, kTileBits);
@@ -961,48 +987,47 @@ __global__ void __launch_bounds__(kTileThreads, 1)
   }
   while (tile < p.num_tiles) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    group_barrier(group);  // the tile is complete and visible to the whole group
-    const uint64_t next = tile + stride;
+    __syncthreads();  // the tile is complete and visible to the whole CTA
+    const uint64_t next = tile + gridDim.x;
     uint64_t next_base = 0;
     if (next < p.num_tiles) next_base = insert_zero_bits(next, p.tbits, kTileBits);
     unsigned char* const sbuf = tiles + (size_t)buf * kTileBufBytes;
     for (int b = 0; b < p.num_blocks; ++b) {
       const uint32_t sgb = b == 0 ? sg[0] : sg[1];
-      const uint32_t* const mslot = p.mslot[b];
+      const uint32_t* const mslot = p.mslot[b] + h * kHalf;  // this thread's members
       const bool vec = p.vec[b] != 0;
-      float2 x[kTcDim];
+      float2 x[kHalf];
       if (vec) {
 #pragma unroll
-        for (int i = 0; i < kTcDim / 2; ++i) {
+        for (int i = 0; i < kHalf / 2; ++i) {
           const float4 v = *reinterpret_cast<const float4*>(sbuf + ((sgb ^ mslot[2 * i]) << 3));
           x[2 * i] = make_float2(v.x, v.y);
           x[2 * i + 1] = make_float2(v.z, v.w);
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < kTcDim; ++j)
+        for (int j = 0; j < kHalf; ++j)
           x[j] = *reinterpret_cast<const float2*>(sbuf + ((sgb ^ mslot[j]) << 3));
       }
+      // members [16h, 16h + 16) = real columns [32h, 32h + 32) of the A row
 #pragma unroll
-      for (int c16 = 0; c16 < kTcN / 16; ++c16) {
+      for (int c16 = 0; c16 < 2; ++c16) {
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const int col = c16 * 16 + e;
           const float a = (col & 1) ? x[col >> 1].y : x[col >> 1].x;
-          const uint32_t h = to_tf32(a);
-          hi[e] = h;
-          lo[e] = to_tf32(a - __uint_as_float(h));
+          const uint32_t hh = to_tf32(a);
+          hi[e] = hh;
+          lo[e] = to_tf32(a - __uint_as_float(hh));
         }
-        tmem_st16(lane_base + (uint32_t)(c16 * 16), hi);
-        tmem_st16(lane_base + (uint32_t)(kTcN + c16 * 16), lo);
+        tmem_st16(lane_base + (uint32_t)(h * 32 + c16 * 16), hi);
+        tmem_st16(lane_base + (uint32_t)(kTcN + h * 32 + c16 * 16), lo);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      // next tile -> the other buffer while the tensor core works on this one
-      if (b == 0 && next < p.num_tiles) prefetch(next_base, buf ^ 1u);
-      group_barrier(group);
-      if (gt == 0) {
+      group_barrier(group);  // this M tile's A operand is complete
+      if (issuer) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // same product order as sv_apply_tc_kernel (see the comment there)
         const uint32_t sb_hi = smem_u32(sB) + (uint32_t)b * (uint32_t)kTileBBytes;
@@ -1031,59 +1056,76 @@ __global__ void __launch_bounds__(kTileThreads, 1)
             "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar_s)
             : "memory");
       }
+      if (b == 0) {
+        // Under block A's MMAs: the PREVIOUS tile (finished, in the other buffer) goes
+        // back to HBM and that buffer is refilled with the next tile.  A thread refills
+        // exactly the slots it reads (same copy pattern both ways), so no barrier is
+        // needed in between: its slots are read into registers first, then the
+        // latency-critical loads of the next tile are issued, then the stores.
+        float4 v[kTileRounds];
+        if (have_prev) {
+          const unsigned char* const src = tiles + (size_t)(buf ^ 1u) * kTileBufBytes;
+#pragma unroll
+          for (int r = 0; r < kTileRounds; ++r)
+            v[r] = *reinterpret_cast<const float4*>(src + ((thr_slot ^ p.rslot[r]) << 3));
+        }
+        if (next < p.num_tiles) prefetch(next_base, buf ^ 1u);
+        if (have_prev) {
+          float2* const dstp = p.state + prev_base + thr_goff;
+#pragma unroll
+          for (int r = 0; r < kTileRounds; ++r) *reinterpret_cast<float4*>(dstp + p.rgoff[r]) = v[r];
+        }
+      }
       mbar_wait(mbar_s, parity);
       parity ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // D0 + D1 (this thread's 32 real columns) -> its 16 slots of the tile; all four
+      // TMEM loads are in flight before the one wait
+      {
+        uint32_t d[2][16], d1[2][16];
 #pragma unroll
-      for (int c16 = 0; c16 < kTcN / 16; ++c16) {
-        uint32_t d[16], d1[16];
-        tmem_ld16(lane_base + d_col + (uint32_t)(c16 * 16), d);
-        tmem_ld16(lane_base + d_col + (uint32_t)(kTcN + c16 * 16), d1);
+        for (int c16 = 0; c16 < 2; ++c16) {
+          tmem_ld16(lane_base + d_col + (uint32_t)(h * 32 + c16 * 16), d[c16]);
+          tmem_ld16(lane_base + d_col + (uint32_t)(kTcN + h * 32 + c16 * 16), d1[c16]);
+        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (vec) {
 #pragma unroll
-          for (int e = 0; e < 16; e += 4) {
-            const int r = (c16 * 16 + e) >> 1;
-            float4 o;
-            o.x = __uint_as_float(d[e]) + __uint_as_float(d1[e]);
-            o.y = __uint_as_float(d[e + 1]) + __uint_as_float(d1[e + 1]);
-            o.z = __uint_as_float(d[e + 2]) + __uint_as_float(d1[e + 2]);
-            o.w = __uint_as_float(d[e + 3]) + __uint_as_float(d1[e + 3]);
-            *reinterpret_cast<float4*>(sbuf + ((sgb ^ mslot[r]) << 3)) = o;
-          }
-        } else {
+        for (int c16 = 0; c16 < 2; ++c16) {
+          if (vec) {
 #pragma unroll
-          for (int e = 0; e < 16; e += 2) {
-            const int r = (c16 * 16 + e) >> 1;
-            float2 o;
-            o.x = __uint_as_float(d[e]) + __uint_as_float(d1[e]);
-            o.y = __uint_as_float(d[e + 1]) + __uint_as_float(d1[e + 1]);
-            *reinterpret_cast<float2*>(sbuf + ((sgb ^ mslot[r]) << 3)) = o;
+            for (int e = 0; e < 16; e += 4) {
+              const int r = (c16 * 16 + e) >> 1;
+              float4 o;
+              o.x = __uint_as_float(d[c16][e]) + __uint_as_float(d1[c16][e]);
+              o.y = __uint_as_float(d[c16][e + 1]) + __uint_as_float(d1[c16][e + 1]);
+              o.z = __uint_as_float(d[c16][e + 2]) + __uint_as_float(d1[c16][e + 2]);
+              o.w = __uint_as_float(d[c16][e + 3]) + __uint_as_float(d1[c16][e + 3]);
+              *reinterpret_cast<float4*>(sbuf + ((sgb ^ mslot[r]) << 3)) = o;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) {
+              const int r = (c16 * 16 + e) >> 1;
+              float2 o;
+              o.x = __uint_as_float(d[c16][e]) + __uint_as_float(d1[c16][e]);
+              o.y = __uint_as_float(d[c16][e + 1]) + __uint_as_float(d1[c16][e + 1]);
+              *reinterpret_cast<float2*>(sbuf + ((sgb ^ mslot[r]) << 3)) = o;
+            }
           }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      group_barrier(group);  // results visible before the next block regroups them
+      __syncthreads();  // both M tiles' results visible before the tile is regrouped
     }
-    // tile -> HBM
-    {
-      float2* const dstp = p.state + base + thr_goff;
-#pragma unroll
-      for (int r0 = 0; r0 < 16; r0 += 8) {
-        float4 v[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-          v[r] = *reinterpret_cast<const float4*>(sbuf + ((thr_slot ^ p.rslot[r0 + r]) << 3));
-#pragma unroll
-        for (int r = 0; r < 8; ++r) *reinterpret_cast<float4*>(dstp + p.rgoff[r0 + r]) = v[r];
-      }
-    }
-    // (this buffer is refilled by the prefetch issued in the NEXT iteration, after
-    // that iteration's first group barrier: every thread has read it by then)
+    // (the finished tile stays in its buffer; it is written back under the next
+    // tile's first MMAs, or after the loop)
+    have_prev = true;
+    prev_base = base;
     tile = next;
     base = next_base;
     buf ^= 1u;
   }
+  if (have_prev) copy_out(prev_base, buf ^ 1u);
   __syncthreads();
   if (tid < 32) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s),
@@ -1093,10 +1135,11 @@ __global__ void __launch_bounds__(kTileThreads, 1)
 }
 
 // Host side of the tile layout.  `sorted[b]` = the 5 ascending targets of block b
-// (already widened to 5), `tbits` = the 12 ascending tile bits (a superset of all
-// targets, containing index bits 0 and 1).  Returns false if no conflict-free
-// swizzle exists (not observed; the caller then applies the blocks one by one).
+// (already widened to 5), `tbits` = the 13 ascending tile bits (a superset of all
+// targets, containing index bits 0-2).  Returns false if no conflict-free swizzle
+// exists (not observed; the caller then applies the blocks one by one).
 static bool make_tile_params(int nb, const int (*sorted)[5], const int* tbits, TcTileParams* p) {
+  constexpr int G = kTileGroupBits;
   for (int i = 0; i < kTileBits; ++i) p->tbits[i] = tbits[i];
   p->num_blocks = nb;
   auto local_pos = [&](int bit) {
@@ -1104,8 +1147,8 @@ static bool make_tile_params(int nb, const int (*sorted)[5], const int* tbits, T
       if (tbits[i] == bit) return i;
     return -1;
   };
-  int tl[kTileMaxBlocks][5];            // local positions of the targets, ascending
-  int grp[kTileMaxBlocks][7];           // local positions of the group bits, ascending
+  int tl[kTileMaxBlocks][5];  // local positions of the targets, ascending
+  int grp[kTileMaxBlocks][G];  // local positions of the group bits, ascending
   for (int b = 0; b < nb; ++b) {
     bool is_t[kTileBits] = {false};
     for (int i = 0; i < 5; ++i) {
@@ -1129,11 +1172,10 @@ static bool make_tile_params(int nb, const int (*sorted)[5], const int* tbits, T
   for (int b = 0; b < nb; ++b)
     for (int d = 1; d <= 3; ++d) {
       bool have = false;
-      for (int i = 0; i < 7; ++i) have |= grp[b][i] == d;
+      for (int i = 0; i < G; ++i) have |= grp[b][i] == d;
       if (!have) needs[nn++] = Need{b, d};
     }
   int pick[3 * kTileMaxBlocks];
-  // iterative DFS
   int depth = 0;
   for (int i = 0; i < nn; ++i) pick[i] = -1;
   bool ok = nn == 0;
@@ -1150,7 +1192,7 @@ static bool make_tile_params(int nb, const int (*sorted)[5], const int* tbits, T
       pick[depth] = -1;
     }
     bool placed = false;
-    for (int i = start; i < 7; ++i) {
+    for (int i = start; i < G; ++i) {
       const int h = grp[nd.b][i];
       if (h < 4) continue;
       if (dir[h] == nd.d) { pick[depth] = i; placed = true; break; }
@@ -1173,17 +1215,17 @@ static bool make_tile_params(int nb, const int (*sorted)[5], const int* tbits, T
     if (!p->vec[b]) { p->gbit[b][out++] = 0; used[0] = true; }
     for (int d = 1; d <= 3; ++d) {
       int chosen = -1;
-      for (int i = 0; i < 7 && chosen < 0; ++i)
+      for (int i = 0; i < G && chosen < 0; ++i)
         if (grp[b][i] == d) chosen = d;
-      for (int i = 0; i < 7 && chosen < 0; ++i)
+      for (int i = 0; i < G && chosen < 0; ++i)
         if (grp[b][i] >= 4 && dir[grp[b][i]] == d && !used[grp[b][i]]) chosen = grp[b][i];
       if (chosen < 0) return false;
       p->gbit[b][out++] = chosen;
       used[chosen] = true;
     }
-    for (int i = 0; i < 7; ++i)
+    for (int i = 0; i < G; ++i)
       if (!used[grp[b][i]]) p->gbit[b][out++] = grp[b][i];
-    if (out != 7) return false;
+    if (out != G) return false;
     for (int j = 0; j < 32; ++j) {
       uint32_t loc = 0;
       for (int i = 0; i < 5; ++i)
@@ -1193,26 +1235,28 @@ static bool make_tile_params(int nb, const int (*sorted)[5], const int* tbits, T
   }
   for (int b = nb; b < kTileMaxBlocks; ++b) {
     p->vec[b] = 0;
-    for (int i = 0; i < 7; ++i) p->gbit[b][i] = i;
+    for (int i = 0; i < G; ++i) p->gbit[b][i] = i;
     for (int j = 0; j < 32; ++j) p->mslot[b][j] = 0;
   }
-  for (int r = 0; r < 16; ++r) {
+  for (int r = 0; r < kTileRounds; ++r) {
     uint64_t off = 0;
-    for (int i = 0; i < 4; ++i)
-      if ((r >> i) & 1) off += 1ull << tbits[8 + i];
+    for (int i = 0; i < 3; ++i)
+      if ((r >> i) & 1) off += 1ull << tbits[10 + i];
     p->rgoff[r] = off;
-    p->rslot[r] = tile_slot((uint32_t)r << 8, p->xmask);
+    p->rslot[r] = tile_slot((uint32_t)r << 10, p->xmask);
   }
   return true;
 }
 
-// Tile bits of a group of blocks: the union of their targets, index bits 0 and 1,
-// and the lowest other bits up to 12.  Returns false if the union is too wide.
+// Tile bits of a group of blocks: the union of their targets, index bits 0-2,
+// and the lowest other bits up to 13.  Returns false if the union is too wide.
 bool tile_bits_for(int n, int nb, const int* ks, const int* targets, int* tbits) {
   if (n < kTileBits || nb < 1 || nb > kTileMaxBlocks) return false;
   bool in[64] = {false};
-  in[0] = in[1] = true;
-  int count = 2;
+  // index bits 0-2 are always tile bits: the tile then moves in runs of >= 64
+  // bytes (with 32-byte runs a pass fell to 1.1 TB/s, profiles/README.md r2b)
+  in[0] = in[1] = in[2] = true;
+  int count = 3;
   size_t off = 0;
   for (int b = 0; b < nb; ++b) {
     if (ks[b] < 1 || ks[b] > 5) return false;
@@ -1292,8 +1336,7 @@ int launch_tc_tile(void* state, int n, int nb, const int (*sorted)[5], const int
       attr_set[dev] = true;
     }
   }
-  const uint64_t ctas = (p.num_tiles + kTileGroups - 1) / kTileGroups;
-  const uint64_t grid = std::min<uint64_t>(ctas, (uint64_t)sms);
+  const uint64_t grid = std::min<uint64_t>(p.num_tiles, (uint64_t)sms);
   sv_apply_tc_tile_kernel<<<(unsigned)grid, kTileThreads, kTileSmemBytes, stream>>>(p);
   B2Q_LAUNCH_CHECK("sv_apply_tc_tile_kernel");
   B2Q_CUDA_CHECK(cudaEventRecord(ring->done[slot], stream));
@@ -1436,8 +1479,8 @@ extern "C" int b2q_debug_tc_stage_plan(int n_qubits, const int* sorted_targets, 
 }
 
 // Host-only: the tile kernel's address tables for `num_blocks` blocks of 5 ascending
-// targets each.  out (int64): tbits[12] | xmask[3] | rgoff[16] | rslot[16] | then per
-// block: vec | gbit[7] | mslot[32].  Returns B2Q_ERR_UNSUPPORTED if the blocks do not
+// targets each.  out (int64): tbits[13] | xmask[3] | rgoff[8] | rslot[8] | then per
+// block: vec | gbit[8] | mslot[32].  Returns B2Q_ERR_UNSUPPORTED if the blocks do not
 // fit one tile.
 extern "C" int b2q_debug_tile_plan(int n_qubits, int num_blocks, const int* sorted_targets,
                                    int64_t* out) {
@@ -1456,13 +1499,13 @@ extern "C" int b2q_debug_tile_plan(int n_qubits, int num_blocks, const int* sort
   if (!b2q::make_tile_params(num_blocks, sorted, tbits, &p))
     return b2q::set_error(B2Q_ERR_UNSUPPORTED, "no conflict-free tile layout");
   int o = 0;
-  for (int i = 0; i < 12; ++i) out[o++] = p.tbits[i];
+  for (int i = 0; i < b2q::kTileBits; ++i) out[o++] = p.tbits[i];
   for (int i = 0; i < 3; ++i) out[o++] = p.xmask[i];
-  for (int i = 0; i < 16; ++i) out[o++] = (int64_t)p.rgoff[i];
-  for (int i = 0; i < 16; ++i) out[o++] = p.rslot[i];
+  for (int i = 0; i < b2q::kTileRounds; ++i) out[o++] = (int64_t)p.rgoff[i];
+  for (int i = 0; i < b2q::kTileRounds; ++i) out[o++] = p.rslot[i];
   for (int b = 0; b < num_blocks; ++b) {
     out[o++] = p.vec[b];
-    for (int i = 0; i < 7; ++i) out[o++] = p.gbit[b][i];
+    for (int i = 0; i < b2q::kTileGroupBits; ++i) out[o++] = p.gbit[b][i];
     for (int j = 0; j < 32; ++j) out[o++] = p.mslot[b][j];
   }
   return B2Q_OK;

@@ -11,6 +11,7 @@
 #include "b2q_common.cuh"
 
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 namespace b2q {
@@ -48,6 +49,78 @@ __global__ void __launch_bounds__(256)
     uint64_t i = 0;
     for (int k = 0; k < p.n; ++k) i |= ((o >> k) & 1ull) << p.src_bit[k];
     out[o] = in[i];
+  }
+}
+
+// ---- in-place bit permutation, one 64 KB tile per CTA --------------------------
+//
+// A permutation that only moves index bits inside a set T (|T| <= 13 for complex64,
+// 12 for complex128) maps every "tile" — the 2^|T| amplitudes that agree on all
+// other bits — onto itself, so it can run IN PLACE: a CTA reads its tile with
+// coalesced 16-byte accesses, drops every amplitude at its permuted position in
+// shared memory, and writes the tile back linearly.  T always contains the lowest
+// index bits, so HBM moves in runs of >= 128 bytes whatever is permuted.  Any
+// permutation is a short product of such passes (the host picks them: each pass
+// settles up to |T| - 4 more bits).  Replaces np.moveaxis / transpose of
+// linalg/transformations.py:743-754 without the second buffer, which is what lets
+// states above 30 qubits keep the reference's product-state form
+// (sim/simulation_product_state.py:68-81) and puts relabelled SWAPs back.
+constexpr int kPermMaxTileBits = 13;
+
+struct PermuteTileParams {
+  uint64_t num_tiles;
+  int tile_bits;
+  int tbits[kPermMaxTileBits];      // ascending index positions of the tile bits, tbits[0] = 0
+  int src_local[kPermMaxTileBits];  // output local bit k = input local bit src_local[k]
+  int dst_local[kPermMaxTileBits];  // input local bit j goes to output local bit dst_local[j]
+};
+
+// XOR of higher local bits into bits 1-3 (complex64: 8-byte slots) so that neither the
+// permuted writes nor the linear reads pile up on a few banks
+__device__ __forceinline__ uint32_t perm_slot(uint32_t o) {
+  return o ^ ((((o >> 4) ^ (o >> 7) ^ (o >> 10)) & 7u) << 1);
+}
+
+template <typename real>
+__global__ void __launch_bounds__(256, 2)
+    sv_permute_tile_kernel(typename Cplx<real>::type* __restrict__ state,
+                           const __grid_constant__ PermuteTileParams p) {
+  using C = typename Cplx<real>::type;
+  constexpr int kVec = 16 / sizeof(C);  // amplitudes per 16-byte access
+  extern __shared__ __align__(16) unsigned char perm_smem[];
+  C* tile = reinterpret_cast<C*>(perm_smem);
+  const uint32_t tile_elems = 1u << p.tile_bits;
+  for (uint64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    const uint64_t base = insert_zero_bits(t, p.tbits, p.tile_bits);
+    for (uint32_t l = threadIdx.x * kVec; l < tile_elems; l += 256 * kVec) {
+      uint64_t off = 0;
+      uint32_t o = 0;
+      for (int j = (kVec == 2 ? 1 : 0); j < p.tile_bits; ++j) {
+        const uint32_t bit = (l >> j) & 1u;
+        off += (uint64_t)bit << p.tbits[j];
+        o |= bit << p.dst_local[j];
+      }
+      if constexpr (kVec == 2) {
+        const float4 v = *reinterpret_cast<const float4*>(state + base + off);
+        tile[perm_slot(o)] = make_float2(v.x, v.y);
+        tile[perm_slot(o | (1u << p.dst_local[0]))] = make_float2(v.z, v.w);
+      } else {
+        tile[perm_slot(o)] = state[base + off];
+      }
+    }
+    __syncthreads();
+    for (uint32_t l = threadIdx.x * kVec; l < tile_elems; l += 256 * kVec) {
+      uint64_t off = 0;
+      for (int j = (kVec == 2 ? 1 : 0); j < p.tile_bits; ++j)
+        off += (uint64_t)((l >> j) & 1u) << p.tbits[j];
+      if constexpr (kVec == 2) {
+        const float4 v = *reinterpret_cast<const float4*>(&tile[perm_slot(l)]);
+        *reinterpret_cast<float4*>(state + base + off) = v;
+      } else {
+        state[base + off] = tile[perm_slot(l)];
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -219,6 +292,153 @@ extern "C" int b2q_sv_permute_bits(const void* in, void* out, int dtype, int n_q
     sv_permute_kernel<double><<<layout_grid(total), 256, 0, s>>>(
         reinterpret_cast<const double2*>(in), reinterpret_cast<double2*>(out), p);
   B2Q_LAUNCH_CHECK("sv_permute_kernel");
+  return B2Q_OK;
+}
+
+// Host planner of the in-place permutation: `want[k]` = the bit whose content must end
+// at position k.  Fills passes (tile bits + local source map) until done.
+struct PermutePass {
+  int count;
+  int tbits[kPermMaxTileBits];
+  int src_local[kPermMaxTileBits];
+};
+
+static int plan_permute_passes(int n, const int* want, int cap, std::vector<PermutePass>* passes) {
+  std::vector<int> cur(n);  // cur[pos] = original bit whose content sits at pos now
+  for (int i = 0; i < n; ++i) cur[i] = i;
+  const int forced = std::min(n, 4);  // index bits 0-3: runs of >= 128 bytes
+  for (int guard = 0; guard < 64; ++guard) {
+    bool done = true;
+    for (int k = 0; k < n; ++k) done &= cur[k] == want[k];
+    if (done) return B2Q_OK;
+    std::vector<char> in(n, 0);
+    std::vector<int> set;
+    auto add = [&](int b) {
+      if (!in[b]) {
+        in[b] = 1;
+        set.push_back(b);
+      }
+    };
+    for (int b = 0; b < forced; ++b) add(b);
+    std::vector<int> where(n);  // where[original bit] = current position
+    for (int pos = 0; pos < n; ++pos) where[cur[pos]] = pos;
+    // follow chains: an unsettled position, then the position holding what it wants, ...
+    for (int k = 0; k < n && (int)set.size() < cap; ++k) {
+      if (cur[k] == want[k] || in[k]) continue;
+      int pos = k;
+      while (true) {
+        if (!in[pos]) {
+          if ((int)set.size() >= cap) break;
+          add(pos);
+        }
+        const int next = where[want[pos]];
+        if (in[next]) break;  // the chain closes inside the set
+        pos = next;
+      }
+    }
+    std::sort(set.begin(), set.end());
+    const int T = (int)set.size();
+    // sigma on the set: position k takes the content it wants when that content is
+    // inside the set; leftovers are matched in order
+    std::vector<int> src_pos(n, -1);
+    std::vector<char> taken(n, 0);
+    for (int k : set) {
+      const int q = where[want[k]];
+      if (in[q]) {
+        src_pos[k] = q;
+        taken[q] = 1;
+      }
+    }
+    std::vector<int> free_src;
+    for (int q : set)
+      if (!taken[q]) free_src.push_back(q);
+    size_t fi = 0;
+    for (int k : set)
+      if (src_pos[k] < 0) src_pos[k] = free_src[fi++];
+    PermutePass pass;
+    pass.count = T;
+    bool moves = false;
+    for (int i = 0; i < T; ++i) {
+      pass.tbits[i] = set[i];
+      const int q = src_pos[set[i]];
+      pass.src_local[i] = (int)(std::lower_bound(set.begin(), set.end(), q) - set.begin());
+      moves |= q != set[i];
+    }
+    if (!moves) return set_error(B2Q_ERR_INVALID, "permutation planner made no progress");
+    std::vector<int> next_cur(cur);
+    for (int k : set) next_cur[k] = cur[src_pos[k]];
+    cur.swap(next_cur);
+    passes->push_back(pass);
+  }
+  return set_error(B2Q_ERR_INVALID, "permutation planner did not converge");
+}
+
+extern "C" int b2q_sv_permute_bits_inplace(void* state, int dtype, int n_qubits, const int* src_bit,
+                                           int* passes_out, void* stream) {
+  B2Q_REQUIRE(state != nullptr && src_bit != nullptr, "null argument");
+  B2Q_REQUIRE(dtype == B2Q_C64 || dtype == B2Q_C128, "bad dtype %d", dtype);
+  B2Q_REQUIRE(n_qubits >= 1 && n_qubits <= 40, "n_qubits out of range");
+  uint64_t seen = 0;
+  for (int k = 0; k < n_qubits; ++k) {
+    B2Q_REQUIRE(src_bit[k] >= 0 && src_bit[k] < n_qubits, "source bit out of range");
+    B2Q_REQUIRE(!((seen >> src_bit[k]) & 1ull), "src_bit is not a permutation");
+    seen |= 1ull << src_bit[k];
+  }
+  const int cap = std::min(n_qubits, dtype == B2Q_C64 ? kPermMaxTileBits : kPermMaxTileBits - 1);
+  std::vector<PermutePass> passes;
+  const int rc = plan_permute_passes(n_qubits, src_bit, cap, &passes);
+  if (rc != B2Q_OK) return rc;
+  if (passes_out != nullptr) *passes_out = (int)passes.size();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2Q_CUDA_CHECK(cudaFuncSetAttribute(sv_permute_tile_kernel<float>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    B2Q_CUDA_CHECK(cudaFuncSetAttribute(sv_permute_tile_kernel<double>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    attr_set = true;
+  }
+  for (const PermutePass& pass : passes) {
+    PermuteTileParams p;
+    memset(&p, 0, sizeof(p));
+    p.tile_bits = pass.count;
+    p.num_tiles = 1ull << (n_qubits - pass.count);
+    for (int i = 0; i < pass.count; ++i) {
+      p.tbits[i] = pass.tbits[i];
+      p.src_local[i] = pass.src_local[i];
+      p.dst_local[pass.src_local[i]] = i;
+    }
+    B2Q_REQUIRE(p.tbits[0] == 0, "tile must contain index bit 0");
+    const size_t smem = elem_bytes(dtype) << pass.count;
+    const unsigned grid = (unsigned)std::min<uint64_t>(p.num_tiles, 148ull * 2);
+    if (dtype == B2Q_C64)
+      sv_permute_tile_kernel<float><<<grid, 256, smem, s>>>(reinterpret_cast<float2*>(state), p);
+    else
+      sv_permute_tile_kernel<double><<<grid, 256, smem, s>>>(reinterpret_cast<double2*>(state), p);
+    B2Q_LAUNCH_CHECK("sv_permute_tile_kernel");
+  }
+  return B2Q_OK;
+}
+
+// Host-only: the passes b2q_sv_permute_bits_inplace would run.  out: per pass
+// count | tbits[13] | src_local[13] (27 ints), at most max_passes of them;
+// returns the number of passes in *passes_out.
+extern "C" int b2q_debug_permute_plan(int dtype, int n_qubits, const int* src_bit, int max_passes,
+                                      int* out, int* passes_out) {
+  B2Q_REQUIRE(src_bit != nullptr && out != nullptr && passes_out != nullptr, "null argument");
+  const int cap = std::min(n_qubits, dtype == B2Q_C64 ? kPermMaxTileBits : kPermMaxTileBits - 1);
+  std::vector<PermutePass> passes;
+  const int rc = plan_permute_passes(n_qubits, src_bit, cap, &passes);
+  if (rc != B2Q_OK) return rc;
+  *passes_out = (int)passes.size();
+  for (int i = 0; i < (int)passes.size() && i < max_passes; ++i) {
+    int* o = out + 27 * i;
+    o[0] = passes[i].count;
+    for (int j = 0; j < kPermMaxTileBits; ++j) {
+      o[1 + j] = j < passes[i].count ? passes[i].tbits[j] : -1;
+      o[14 + j] = j < passes[i].count ? passes[i].src_local[j] : -1;
+    }
+  }
   return B2Q_OK;
 }
 

@@ -144,14 +144,20 @@ class DeviceState:
     def plan_passes(self, gates: Sequence[tuple]) -> list[list[tuple]]:
         """Groups [(matrix, bits), ...] into kernel launches, in order: each inner
         list is ONE pass over the state — a single block, or two consecutive dense
-        blocks of <= 5 bits each, whose targets always fit one 12-bit tile."""
+        blocks of <= 5 bits each (their targets plus index bits 0-2 always fit one
+        13-bit tile)."""
         gates = list(gates)
         if not self.tile_pairing():
             return [[g] for g in gates]
+        # index bits that must be tile bits besides the targets: 0-2 (runs of >= 64 bytes)
+        # lets ANY two 5-bit blocks share a pass; asking for bits 0-3 (128-byte runs: 5.7
+        # instead of 8.3 ms for the worst pair) pairs fewer blocks and measured slower on
+        # the bench circuit (1881 against 1937 gates/s, profiles/README.md r2e)
+        low = set(range(int(os.environ.get('CIRQ_B200_TILE_RUN_BITS', '3'))))
         out, i = [], 0
         while i < len(gates):
             if (i + 1 < len(gates) and self._pairable(*gates[i]) and self._pairable(*gates[i + 1])
-                    and len(set(gates[i][1]) | set(gates[i + 1][1]) | {0, 1}) <= 12):
+                    and len(set(gates[i][1]) | set(gates[i + 1][1]) | low) <= 13):
                 out.append([gates[i], gates[i + 1]])
                 i += 2
             else:
@@ -548,6 +554,19 @@ class DeviceState:
             )
         )
         return out
+
+    def permute_bits_inplace(self, src_bit: Sequence[int]) -> int:
+        """self[o] <- self[i], bit k of o == bit src_bit[k] of i, without a second
+        buffer (tile passes in shared memory); returns the number of passes."""
+        torch = _torch()
+        passes = ctypes.c_int(0)
+        check(
+            self._lib.b2q_sv_permute_bits_inplace(
+                self.ptr, self.code, self.n_bits, _lib.int_array(src_bit), ctypes.byref(passes),
+                _stream_ptr(torch),
+            )
+        )
+        return int(passes.value)
 
     def argmax_abs(self) -> int:
         torch = _torch()

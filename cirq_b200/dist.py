@@ -269,6 +269,165 @@ class ShardBackend:
         self._bufs = []
 
 
+class ExchangePlanner:
+    """Plans the global<->local exchanges of a block list on the wires alone.
+
+    `metas[i]` = (wires, diagonal wires, fusable) of block i.  A block runs without
+    communication when every wire it is NOT diagonal in is local.  When the first
+    block in line needs global wires, they are exchanged with the local bits whose
+    next use lies furthest away; further global wires that later blocks need before
+    those evicted bits are used again may join the same exchange (m bits at once
+    move 1 - 2^-m of a shard, m single swaps m/2).  How many join is decided per
+    exchange by rolling the rest of the schedule out under both simple policies
+    (none / all that qualify) and keeping the cheapest total.
+
+    Cost unit: one shard volume over NVLink.  A single-bit swap that rides along
+    with the preceding local pass (fused kernel) hides that pass: FUSE_GAIN.
+    """
+
+    FUSE_GAIN = 0.2  # a hidden HBM pass, in units of a shard over NVLink (0.31 / 0.72 * 0.5)
+
+    def __init__(self, metas, n_local: int, lowest_victim: int, can_fuse: bool, max_bits: int):
+        self.metas = metas
+        self.n_local = n_local
+        self.lowest_victim = lowest_victim
+        self.can_fuse = can_fuse
+        self.max_bits = max_bits
+
+    def _needs(self, i: int, phys) -> list[int]:
+        ws, diag, _ = self.metas[i]
+        return [w for w in ws if phys[w] >= self.n_local and w not in diag]
+
+    def _drain_local(self, remaining, phys):
+        """(blocks runnable now, in order; blocks left): commuting blocks overtake."""
+        pending = []
+        progressed = True
+        while progressed and remaining:
+            progressed = False
+            blocked: set[int] = set()
+            keep = []
+            for i in remaining:
+                ws = self.metas[i][0]
+                if blocked.isdisjoint(ws) and not self._needs(i, phys):
+                    pending.append(i)
+                    progressed = True
+                    continue
+                keep.append(i)
+                blocked.update(ws)
+            remaining = keep
+        return pending, remaining
+
+    def _victim(self, remaining, phys, protected):
+        next_use = {}
+        for pos, i in enumerate(remaining):
+            for w in self.metas[i][0]:
+                p = phys[w]
+                if p < self.n_local and p not in next_use:
+                    next_use[p] = pos
+        best, best_pos = None, -1
+        for p in range(self.n_local - 1, self.lowest_victim - 1, -1):
+            if p in protected:
+                continue
+            pos = next_use.get(p, 1 << 60)
+            if pos > best_pos:
+                best, best_pos = p, pos
+        if best is None:
+            raise RuntimeError('no local bit available to swap with')
+        return best, best_pos
+
+    def _options(self, remaining, phys):
+        """(forced pairs, optional pairs in order of first use)."""
+        first = remaining[0]
+        needed = self._needs(first, phys)
+        protected = {phys[w] for w in self.metas[first][0]}
+        forced = []
+        for w in needed:
+            victim, _ = self._victim(remaining, phys, protected)
+            protected.add(victim)
+            forced.append((phys[w], victim))
+        optional = []
+        if self.max_bits > len(forced):
+            first_use = {}
+            for pos, i in enumerate(remaining):
+                for w in self._needs(i, phys):
+                    first_use.setdefault(w, pos)
+            cands = sorted((pos, w) for w, pos in first_use.items() if w not in needed)
+            for pos, w in cands:
+                if len(forced) + len(optional) >= self.max_bits:
+                    break
+                try:
+                    victim, victim_pos = self._victim(remaining, phys, protected)
+                except RuntimeError:
+                    break
+                if victim_pos <= pos:
+                    break  # the evicted bit would be needed first: no gain
+                protected.add(victim)
+                optional.append((phys[w], victim))
+        return forced, optional
+
+    def _cost(self, pairs, pending) -> tuple[float, bool]:
+        fuse = bool(self.can_fuse and pending and self.metas[pending[-1]][2] and pairs[0][1] >= 1)
+        if len(pairs) == 1 or self.max_bits == 1:
+            # single swaps (the first may ride along with the last local pass)
+            return 0.5 * len(pairs) - (self.FUSE_GAIN if fuse else 0.0), fuse
+        return 1.0 - 0.5 ** len(pairs), False
+
+    @staticmethod
+    def _swapped(phys, pairs):
+        phys = list(phys)
+        for g, l in pairs:
+            for w in range(len(phys)):
+                if phys[w] == g:
+                    phys[w] = l
+                elif phys[w] == l:
+                    phys[w] = g
+        return phys
+
+    def plan(self, phys, mode: str = 'search', remaining=None):
+        """(actions, cost).  actions: ('run', [block indices]) |
+        ('exchange', [(global phys bit, local phys bit), ...], fused block index | None).
+        mode: 'none' = only the wires a block needs, 'greedy' = every qualifying
+        wire joins, 'search' = per exchange, the count with the cheapest rollout."""
+        phys = list(phys)
+        remaining = list(range(len(self.metas))) if remaining is None else list(remaining)
+        actions = []
+        total = 0.0
+        while remaining:
+            pending, remaining = self._drain_local(remaining, phys)
+            if not remaining:
+                if pending:
+                    actions.append(('run', pending))
+                break
+            forced, optional = self._options(remaining, phys)
+            if mode == 'none' or not optional:
+                take = 0
+            elif mode == 'greedy':
+                take = len(optional)
+            else:
+                best = None
+                for j in range(len(optional) + 1):
+                    pairs = forced + optional[:j]
+                    now, _ = self._cost(pairs, pending)
+                    after = self._swapped(phys, pairs)
+                    rest = min(self.plan(after, 'none', remaining)[1], self.plan(after, 'greedy', remaining)[1])
+                    if best is None or now + rest < best[0] - 1e-9:
+                        best = (now + rest, j)
+                take = best[1]
+            pairs = forced + optional[:take]
+            cost, fuse = self._cost(pairs, pending)
+            total += cost
+            if fuse:
+                if pending[:-1]:
+                    actions.append(('run', pending[:-1]))
+                actions.append(('exchange', pairs, pending[-1]))
+            else:
+                if pending:
+                    actions.append(('run', pending))
+                actions.append(('exchange', pairs, None))
+            phys = self._swapped(phys, pairs)
+        return actions, total
+
+
 class ShardedStateVector:
     """n-qubit state sharded over the ranks of a process group.
 
@@ -443,75 +602,53 @@ class ShardedStateVector:
     def apply_blocks(self, blocks: Sequence[tuple[np.ndarray, Sequence[int]]]) -> None:
         """Applies fused blocks [(matrix, logical bits)], reordering commuting
         blocks so that everything executable without communication runs before
-        the next qubit swap."""
-        remaining = [(np.asarray(m), tuple(int(w) for w in ws)) for m, ws in blocks]
+        the next exchange.  The exchanges themselves are planned first, on the
+        wires alone (`ExchangePlanner`): which global bits to bring in together and
+        which local bits to evict."""
+        blocks = [(np.asarray(m), tuple(int(w) for w in ws)) for m, ws in blocks]
         self._diag_cache = {}
-        while remaining:
-            progressed = True
-            pending = []  # local passes scheduled since the last exchange, in order
-            while progressed and remaining:
-                progressed = False
-                blocked: set[int] = set()
-                keep = []
-                for m, ws in remaining:
-                    if blocked.isdisjoint(ws):
-                        local_form = self._local_form(m, ws)
-                        if local_form is not None:
-                            if local_form[1]:
-                                pending.append(local_form)
-                            progressed = True
-                            continue
-                    keep.append((m, ws))
-                    blocked.update(ws)
-                remaining = keep
-            if not remaining:
-                self._run_local(pending)
-                break
-            # The first remaining block has no unexecuted predecessor: bring its
-            # global wires in, evicting the local bits needed furthest away.
-            m, ws = remaining[0]
-            needed = [w for w in ws if self.phys[w] >= self.n_local]
-            protected = {self.phys[w] for w in ws}
-            pairs = []
-            for w in needed:
-                victim = self._choose_victim(remaining, protected)
-                protected.add(victim)
-                pairs.append((self.phys[w], victim))
-            # Look ahead: a global wire that a later block needs BEFORE the local bit
-            # it would evict is used again joins this exchange — a 3-bit exchange
-            # moves 7/8 of a shard once, three 1-bit swaps 3/2 of it.
-            if self.multi_bit_exchange and hasattr(self.backend, 'swap_bits'):
-                first_use = {}
-                for pos, (_, bws) in enumerate(remaining):
-                    for w in bws:
-                        first_use.setdefault(w, pos)
-                cands = sorted((pos, w) for w, pos in first_use.items()
-                               if self.phys[w] >= self.n_local and w not in needed)
-                for pos, w in cands:
-                    if len(pairs) >= 3:
-                        break
-                    try:
-                        victim, victim_pos = self._choose_victim(remaining, protected, with_pos=True)
-                    except RuntimeError:
-                        break
-                    if victim_pos <= pos:
-                        break  # the evicted bit would be needed first: no gain
-                    protected.add(victim)
-                    pairs.append((self.phys[w], victim))
-            if len(pairs) == 1 or not self.multi_bit_exchange or not hasattr(self.backend, 'swap_bits'):
-                for i, (gbit, victim) in enumerate(pairs):
-                    if i == 0:
-                        fused = self._fusable(pending, victim)
-                        if fused is not None:
-                            # the last local pass and the exchange travel as ONE kernel
-                            self._run_local(pending[:-1])
-                            self.swap_global_local(gbit, victim, fused_block=fused)
-                            continue
-                        self._run_local(pending)
+        metas = [(ws, self._diagonal_wires(m, ws), np.ndim(m) == 2 and len(ws) <= 5) for m, ws in blocks]
+        can_multi = self.multi_bit_exchange and hasattr(self.backend, 'swap_bits') and self.g > 1
+        planner = ExchangePlanner(
+            metas, self.n_local, lowest_victim=1 if self.dtype == np.dtype(np.complex64) else 0,
+            can_fuse=bool(getattr(self.backend, 'can_fuse_exchange', False)),
+            max_bits=min(3, self.g) if can_multi else 1)
+        actions, _ = planner.plan(self.phys, 'search' if can_multi else 'none')
+        for action in actions:
+            if action[0] == 'run':
+                forms = []
+                for i in action[1]:
+                    form = self._local_form(*blocks[i])
+                    assert form is not None, 'planner scheduled a block that needs an exchange'
+                    if form[1]:
+                        forms.append(form)
+                self._run_local(forms)
+                continue
+            _, pairs, fused_index = action
+            if fused_index is not None:
+                form = self._local_form(*blocks[fused_index])
+                fused = self._fusable([form], pairs[0][1]) if form is not None and form[1] else None
+                if fused is None:  # (became a pure phase on this rank: nothing to fuse)
+                    self.swap_global_local(*pairs[0])
+                else:
+                    self.swap_global_local(pairs[0][0], pairs[0][1], fused_block=fused)
+                for gbit, victim in pairs[1:]:
+                    self.swap_global_local(gbit, victim)
+            elif len(pairs) == 1 or not can_multi:
+                for gbit, victim in pairs:
                     self.swap_global_local(gbit, victim)
             else:
-                self._run_local(pending)
                 self.exchange_bits(pairs)
+
+    def _diagonal_wires(self, m: np.ndarray, ws: tuple[int, ...]) -> frozenset:
+        """Wires whose basis value the block never changes: with those global the
+        block still runs without communication (each rank applies the sub-matrix
+        selected by its rank bits)."""
+        if np.ndim(m) == 1:
+            return frozenset(ws)
+        if all(self.phys[w] < self.n_local for w in ws) and self.g == 0:
+            return frozenset()
+        return frozenset(w for w in ws if block_diagonal_in(m, list(ws), [w], atol=1e-24) is not None)
 
     def _run_local(self, batch) -> None:
         if batch:

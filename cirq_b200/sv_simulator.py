@@ -45,9 +45,21 @@ from cirq.sim.simulation_state import SimulationState, strat_act_on_from_apply_d
 # protocols/apply_unitary_protocol.py:375-399, one wider because a 5-qubit
 # matrix is still a single streaming pass here).
 _MAX_DIRECT_UNITARY_QUBITS = 5
-# Above this many qubits split_untangled_states is ignored (see
-# B200Simulator._create_simulation_state).
-_MAX_SPLIT_QUBITS = 30
+# Product-state form (split_untangled_states) at any size.  A join whose result would
+# exceed _DENSE_JOIN_BITS qubits merges EVERY sub-state into one dense state when the
+# whole register still fits a GPU (<= _MAX_DENSE_QUBITS: 137 GB complex64): the join
+# is out of place, so growing a 33-qubit state by one qubit would need 137 + 69 GB,
+# whereas (largest sub-state) x (everything else) needs 137 + 17 GB.  Larger
+# registers stay in product form for good (a join that does not fit raises
+# MemoryError, as the reference's numpy allocation would).  States above
+# _MAX_FACTOR_BITS are not factored back after a measurement (factoring transposes out
+# of place).
+# from this size on, three or more displaced bits are put back by the in-place
+# permutation kernel rather than by SWAP gates
+_PERMUTE_RESTORE_MIN_BITS = 20
+_DENSE_JOIN_BITS = 31
+_MAX_DENSE_QUBITS = 34
+_MAX_FACTOR_BITS = 30
 
 
 class B200StateVector(qis.QuantumStateRepresentation):
@@ -139,6 +151,15 @@ class B200StateVector(qis.QuantumStateRepresentation):
         with real swaps (`restore`, the default: every reader of the raw array
         expects the canonical bit order) or kept as a bit map (`restore=False`, for
         the readers that can translate bit positions: `mapped_device_state`)."""
+        if restore and self._n >= _PERMUTE_RESTORE_MIN_BITS and self._displaced_bits() >= 3:
+            # several relabelled SWAPs to put back: one or two in-place permutation
+            # passes (pure copies) instead of real SWAP gates fused into dense passes
+            self.flush(restore=False)
+            if self._where is not None:
+                self.passes += self._dev.permute_bits_inplace(self._where)
+                self._where = None
+                self._host = None
+            return
         if restore:
             if self._where is not None:
                 # fold the kept map into the fuser's, which then undoes both
@@ -159,6 +180,15 @@ class B200StateVector(qis.QuantumStateRepresentation):
             if moved:
                 where = self._where if self._where is not None else list(range(self._n))
                 self._where = [moved.get(w, w) for w in where]
+
+    def _displaced_bits(self) -> int:
+        """Index bits not holding their own logical bit once the queue is applied
+        (kept bit map composed with the fuser's pending SWAP relabelling)."""
+        pending = self._fuser._map
+        if not pending and self._where is None:
+            return 0
+        where = self._where if self._where is not None else range(self._n)
+        return sum(1 for b, w in enumerate(where) if pending.get(w, w) != b)
 
     @property
     def device_state(self) -> DeviceState:
@@ -233,7 +263,7 @@ class B200StateVector(qis.QuantumStateRepresentation):
 
     @property
     def supports_factor(self) -> bool:
-        return True
+        return self._n <= _MAX_FACTOR_BITS
 
     # ---- layout: Kronecker product, factoring, axis order (split_untangled_states) ----------
 
@@ -256,6 +286,22 @@ class B200StateVector(qis.QuantumStateRepresentation):
         out = B200StateVector(self.device_state.permute_bits(src_bit), n, self._max_fused)
         out.passes = self.passes
         return out
+
+    def reindex_inplace(self, axes: Sequence[int]) -> None:
+        """`reindex` without a second buffer: the in-place tile permutation
+        (b2q_sv_permute_bits_inplace).  For callers that drop the old order anyway
+        (``transpose_to_qubit_order(inplace=True)`` at the end of
+        ``create_merged_state``, sim/simulation_product_state.py:68-81)."""
+        axes = [int(a) for a in axes]
+        n = self._n
+        if axes == list(range(n)):
+            return
+        src_bit = [0] * n
+        for k, a in enumerate(axes):
+            src_bit[n - 1 - k] = n - 1 - a
+        dev = self.device_state  # (flushes; relabelled SWAPs restored)
+        self._host = None
+        self.passes += dev.permute_bits_inplace(src_bit)
 
     def factor(self, axes: Sequence[int], *, validate=True, atol=1e-07):
         """``factor_state_vector`` (linalg/transformations.py:647-691): pivot on the
@@ -348,18 +394,43 @@ class B200ProductState(SimulationProductState):
 
     def join_for(self, qubits):
         """The sub-state holding all of `qubits`, joining sub-states by Kronecker
-        products when they live apart (sim/simulation_product_state.py:110-123)."""
+        products when they live apart (sim/simulation_product_state.py:110-123).
+        A join that would pass _DENSE_JOIN_BITS merges the whole register at once,
+        largest sub-state x everything else (see the constants' comment)."""
         states = self._sim_states
         target = states[qubits[0]]
-        joined = False
+        parts = [target]
         for q in qubits[1:]:
-            if q not in target.qubits:
-                target.kronecker_product(states[q], inplace=True)
-                joined = True
-        if joined:
-            for q in target.qubits:
-                states[q] = target
+            if not any(states[q] is p for p in parts):
+                parts.append(states[q])
+        if len(parts) == 1:
+            return target
+        total = sum(len(p.qubits) for p in parts)
+        n_all = len(self.qubits)
+        if total > _DENSE_JOIN_BITS and n_all <= _MAX_DENSE_QUBITS:
+            everything = []
+            for q in self.qubits:
+                if not any(states[q] is p for p in everything):
+                    everything.append(states[q])
+            everything.sort(key=lambda p: -len(p.qubits))
+            target, rest = everything[0], everything[1:]
+            small = rest[-1]
+            for p in reversed(rest[:-1]):  # smallest first: the temporaries stay small
+                small.kronecker_product(p, inplace=True)
+            target.kronecker_product(small, inplace=True)
+        else:
+            for p in parts[1:]:
+                target.kronecker_product(p, inplace=True)
+        for q in target.qubits:
+            states[q] = target
         return target
+
+    def _act_on_fallback_(self, action, qubits, allow_decompose: bool = True):
+        gate = action if isinstance(action, ops.Gate) else getattr(action, 'gate', None)
+        swap = (isinstance(gate, ops.SwapPowGate) and gate.exponent % 2 == 1 and gate.global_shift == 0)
+        if len(qubits) > 1 and not swap and not isinstance(gate, ops.IdentityGate):
+            self.join_for(tuple(qubits))  # (the reference's joins, with the size policy above)
+        return super()._act_on_fallback_(action, qubits, allow_decompose)
 
     def sample(self, qubits, repetitions: int = 1, seed=None) -> np.ndarray:
         q_set = set(qubits)
@@ -435,6 +506,18 @@ class B200StateVectorSimulationState(SimulationState[B200StateVector]):
         super().__init__(state=state, prng=prng, qubits=qubits, classical_data=classical_data)
         self._dtype = np.dtype(dtype)
         self._max_fused_qubits = max_fused_qubits
+
+    def transpose_to_qubit_order(self, qubits, *, inplace=False):
+        """As SimulationState.transpose_to_qubit_order (sim/simulation_state.py:217-236);
+        with `inplace` the device array is permuted in place (no second buffer), which is
+        what the final merge of a product state asks for."""
+        if not inplace:
+            return super().transpose_to_qubit_order(qubits, inplace=False)
+        if len(self.qubits) != len(qubits) or set(qubits) != set(self.qubits):
+            raise ValueError(f'Qubits do not match. Existing: {self.qubits}, provided: {qubits}')
+        self._state.reindex_inplace(self.get_axes(qubits))
+        self._set_qubits(qubits)
+        return self
 
     def add_qubits(self, qubits):
         """Ancilla / late-joining qubits in |0> (state_vector_simulation_state.py:357-363)."""
@@ -1046,16 +1129,9 @@ class B200Simulator(
         )
 
     def _create_simulation_state(self, initial_state, qubits):
-        """As SimulatorBase (sim/simulator_base.py:322-352), except that states too
-        large to be transposed out of place at the end (the product state's final
-        merge needs a second buffer of the state's size) are kept as one dense
-        tensor from the start."""
-        if self._split_untangled_states and len(qubits) > _MAX_SPLIT_QUBITS:
-            self._split_untangled_states = False
-            try:
-                return create_product_state(self, initial_state, qubits)
-            finally:
-                self._split_untangled_states = True
+        """As SimulatorBase (sim/simulator_base.py:322-352): product-state form at any
+        size when split_untangled_states is on (B200ProductState.join_for bounds the
+        memory of the joins)."""
         return create_product_state(self, initial_state, qubits)
 
     def _create_step_result(self, sim_state):

@@ -92,12 +92,12 @@ int b2q_sv_apply_batch(void* state, int dtype, int n_qubits, int num_gates, cons
                        void* stream);
 
 /* Applies `num_blocks` (1 or 2) fused blocks IN ORDER with ONE pass over HBM
- * (complex64, each k <= 5): a CTA stages a tile of 2^12 amplitudes spanning the
+ * (complex64, each k <= 5): a CTA stages a tile of 2^13 amplitudes spanning the
  * union of the blocks' targets in shared memory, applies every block to it on
  * the tensor cores (3xTF32, fp32 accuracy) and writes it back once — half the
  * HBM traffic per block of b2q_sv_apply_batch.  ks / targets / matrices_c128 as
- * in b2q_sv_apply_batch.  The union of all targets together with index bits 0
- * and 1 must not exceed 12 bits and n_qubits >= 12: b2q_tile_blocks_feasible
+ * in b2q_sv_apply_batch.  The union of all targets together with index bits 0,
+ * 1 and 2 must not exceed 13 bits (always true for two blocks) and n_qubits >= 13: b2q_tile_blocks_feasible
  * (host-only, returns 1/0) tells; otherwise B2Q_ERR_INVALID.  Same reference
  * call sites as b2q_sv_apply_batch (sim/simulator_base.py:199-212 over
  * linalg/transformations.py:105-172). */
@@ -191,6 +191,14 @@ int b2q_sv_kron(const void* a, int na, const void* b, int nb, int dtype, void* o
  * (transpose_state_vector_to_axis_order) in bit-position form. */
 int b2q_sv_permute_bits(const void* in, void* out, int dtype, int n_qubits, const int* src_bit,
                         void* stream);
+/* The same permutation IN PLACE (no second buffer): state[o] <- state[i] with bit k
+ * of o == bit src_bit[k] of i, as a short sequence of passes that each permute at
+ * most 13 index bits (12 for complex128) inside 64 KB shared-memory tiles;
+ * *passes_out (may be NULL) receives their number.  What lets states above 30
+ * qubits keep the product-state form of sim/simulation_product_state.py:68-81
+ * (the final merge transposes) and puts relabelled SWAP gates back. */
+int b2q_sv_permute_bits_inplace(void* state, int dtype, int n_qubits, const int* src_bit,
+                                int* passes_out, void* stream);
 /* Index of the largest |amplitude| (first one on ties): the pivot of
  * factor_state_vector (linalg/transformations.py:677). */
 int b2q_sv_argmax_abs(const void* state, int dtype, int n_qubits, uint64_t* index_out,
@@ -366,6 +374,10 @@ int b2q_set_tc_stage_opts(int early, int l2_ahead);
  * permutation to sorted-target order; no GPU needed. */
 int b2q_debug_plan(int dtype, int n_qubits, const int* targets, int k, int* out);
 int b2q_debug_permute_matrix(const double* matrix_c128, const int* targets, int k, double* out);
+/* Host-only: the passes of b2q_sv_permute_bits_inplace (per pass 27 ints: count |
+ * tile bits[13] | local source bit of each local output bit[13]). */
+int b2q_debug_permute_plan(int dtype, int n_qubits, const int* src_bit, int max_passes, int* out,
+                           int* passes_out);
 /* Host-only: address tables of the tile kernel (b2q_sv_apply_tile_blocks) for
  * `num_blocks` blocks of 5 ascending targets each (layout of `out`: see
  * tests/test_plan_host.py). */

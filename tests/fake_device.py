@@ -181,6 +181,10 @@ class OracleDeviceState:
             i |= ((o >> k) & 1) << sb
         return OracleDeviceState(self.n_bits, self.dtype, self.array[i])
 
+    def permute_bits_inplace(self, src_bit):
+        self.array = self.permute_bits(src_bit).array
+        return 1
+
     def argmax_abs(self):
         return int(np.argmax(np.abs(self.array.astype(np.complex128)) ** 2))
 

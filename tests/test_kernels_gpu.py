@@ -153,7 +153,7 @@ def test_tile_kernel_two_blocks_per_pass_matches_oracle(DS):
     applying them one after the other.  Same error bound as the one-block
     tensor-core kernels, per block."""
     rng = np.random.RandomState(77)
-    for n in (12, 13, 16, 21):
+    for n in (13, 14, 16, 21):
         cases = [([0, 1, 2, 3, 4], [5, 6, 7, 8, 9]), (list(range(n - 5, n)), list(range(n - 10, n - 5))),
                  ([n - 1, 0, 5, 2, 9], [9, 2, n - 2, 3, 7]), ([2, 3, 4, 5, 6], [6, 5, 4, 3, 2]),
                  ([1, 3, 5, 7, 9], [0, 2, 4, 6, 8]), ([4, n - 1, 8, 6, 11], [n - 2, 5, 4, 10, 3]),
@@ -200,6 +200,28 @@ def test_tile_kernel_two_blocks_per_pass_matches_oracle(DS):
     diff = dev.to_numpy().astype(np.complex128) - want
     assert np.linalg.norm(diff) <= len(gates) * 6e-7, np.linalg.norm(diff)
     assert abs(dev.norm2() - 1.0) < 2e-5
+
+
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
+def test_inplace_bit_permutation_matches_out_of_place(DS, dtype):
+    """b2q_sv_permute_bits_inplace (tile passes in shared memory, no second buffer)
+    is bit-exact with the index definition out[o] = in[i], bit k of o = bit
+    src_bit[k] of i (np.moveaxis of linalg/transformations.py:743-754)."""
+    rng = np.random.RandomState(21)
+    for n in (1, 2, 5, 12, 13, 14, 18, 21):
+        perms = [list(range(n))[::-1], list(range(1, n)) + [0], list(range(n))]
+        perms += [rng.permutation(n).tolist() for _ in range(3)]
+        for src in perms:
+            state = rand_state(rng, n, dtype)
+            dev = DS.from_numpy(state)
+            passes = dev.permute_bits_inplace(src)
+            o = np.arange(1 << n, dtype=np.int64)
+            i = np.zeros_like(o)
+            for k, sb in enumerate(src):
+                i |= ((o >> k) & 1) << sb
+            np.testing.assert_array_equal(dev.to_numpy(), state[i])
+            assert passes <= 4 and (passes == 0) == (src == list(range(n)))
+            np.testing.assert_array_equal(DS.from_numpy(state).permute_bits(src).to_numpy(), state[i])
 
 
 def test_generic_kernel_large_k(DS):

@@ -431,30 +431,29 @@ def _tile_plan(lib, n, blocks_sorted):
 
     nb = len(blocks_sorted)
     flat = _lib.int_array([t for b in blocks_sorted for t in b])
-    out = (ctypes.c_int64 * (12 + 3 + 16 + 16 + nb * 40))()
+    out = (ctypes.c_int64 * (13 + 3 + 8 + 8 + nb * 41))()
     rc = lib.b2q_debug_tile_plan(n, nb, flat, out)
     if rc != 0:
         return None
     v = list(out)
-    plan = dict(tbits=v[0:12], xmask=v[12:15], rgoff=v[15:31], rslot=v[31:47], blocks=[])
-    o = 47
+    plan = dict(tbits=v[0:13], xmask=v[13:16], rgoff=v[16:24], rslot=v[24:32], blocks=[])
+    o = 32
     for _ in range(nb):
-        plan['blocks'].append(dict(vec=v[o], gbit=v[o + 1:o + 8], mslot=v[o + 8:o + 40]))
-        o += 40
+        plan['blocks'].append(dict(vec=v[o], gbit=v[o + 1:o + 9], mslot=v[o + 9:o + 41]))
+        o += 41
     return plan
 
 
 def _tile_emulate(lib, n, state, blocks):
-    """Replays sv_apply_tc_tile_kernel's data movement on the CPU: blocks =
-    [(matrix 32x32 in the caller's target order, targets[5])].  Returns the new
-    state; asserts bijections and bank-conflict freedom on the way."""
-    import ctypes
-
+    """Replays sv_apply_tc_tile_kernel's data movement on the CPU (512 threads: warp
+    = q | h << 2 | g << 3; thread (g, q, lane) = amplitude group, h = half of its
+    members): blocks = [(matrix 32x32 in the caller's target order, targets[5])].
+    Returns the new state; asserts bijections and bank-conflict freedom on the way."""
     sorted_blocks = [sorted(t) for _, t in blocks]
     plan = _tile_plan(lib, n, sorted_blocks)
     assert plan is not None
     tbits, xmask = plan['tbits'], plan['xmask']
-    assert tbits[0] == 0 and tbits[1] == 1 and tbits == sorted(tbits)
+    assert tbits[:3] == [0, 1, 2] and tbits == sorted(tbits)
     mats = []
     for m, t in blocks:
         out = np.empty((32, 32), dtype=np.complex128)
@@ -462,46 +461,54 @@ def _tile_emulate(lib, n, state, blocks):
         assert lib.b2q_debug_permute_matrix(src.ctypes.data, _lib.int_array(t), 5, out.ctypes.data) == 0
         mats.append(out)
     state = state.copy()
-    threads = np.arange(128)
+    size = 1 << 13
+    threads = np.arange(512)
     lane, warp = threads & 31, threads >> 5
     thr_local = (lane << 1) | (warp << 6)
-    thr_goff = np.zeros(128, dtype=np.int64)
-    for i in range(1, 8):
+    thr_goff = np.zeros(512, dtype=np.int64)
+    for i in range(1, 10):
         thr_goff += ((thr_local >> i) & 1).astype(np.int64) << tbits[i]
     thr_slot = np.array([_tile_slot(int(x), xmask) for x in thr_local])
-    # copy pattern: a bijection onto the 4096 slots, quarter-warps conflict free
+    # copy pattern: a bijection onto the slots, quarter-warps conflict free
     slots = (thr_slot[:, None] ^ np.array(plan['rslot'])[None, :])
-    assert sorted(np.concatenate([slots.reshape(-1), slots.reshape(-1) + 1]).tolist()) == list(range(4096))
-    for r in range(16):
-        for q0 in range(0, 128, 8):
+    assert sorted(np.concatenate([slots.reshape(-1), slots.reshape(-1) + 1]).tolist()) == list(range(size))
+    for r in range(8):
+        for q0 in range(0, 512, 8):
             assert len({(int(s) >> 1) & 7 for s in slots[q0:q0 + 8, r]}) == 8
     goffs = thr_goff[:, None] + np.array(plan['rgoff'], dtype=np.int64)[None, :]
-    for tile in range(1 << (n - 12)):
+    q, h, g = warp & 3, (warp >> 2) & 1, warp >> 3
+    gidx = lane | (q << 5) | (g << 7)
+    for tile in range(1 << (n - 13)):
         base = tile
         for pos in tbits:
             base = ((base >> pos) << (pos + 1)) | (base & ((1 << pos) - 1))
-        smem = np.zeros(4096, dtype=state.dtype)
+        smem = np.zeros(size, dtype=state.dtype)
         smem[slots] = state[base + goffs]
         smem[slots + 1] = state[base + goffs + 1]
         for blk, m in zip(plan['blocks'], mats):
-            gl = np.zeros(128, dtype=np.int64)
-            for i in range(7):
-                gl |= ((threads >> i) & 1) << blk['gbit'][i]
+            gl = np.zeros(512, dtype=np.int64)
+            for i in range(8):
+                gl |= ((gidx >> i) & 1) << blk['gbit'][i]
             sg = np.array([_tile_slot(int(x), xmask) for x in gl])
-            addr = sg[:, None] ^ np.array(blk['mslot'])[None, :]
+            mslot = np.array(blk['mslot'])
+            member = h[:, None] * 16 + np.arange(16)[None, :]  # [thread, 16]
+            addr = sg[:, None] ^ mslot[member]
             if tile == 0:
-                assert sorted(addr.reshape(-1).tolist()) == list(range(4096))
+                assert sorted(addr.reshape(-1).tolist()) == list(range(size))
                 if blk['vec']:
                     assert np.all(addr[:, 1::2] == addr[:, 0::2] + 1) and np.all(addr[:, 0::2] % 2 == 0)
-                    for j in range(0, 32, 2):
-                        for q0 in range(0, 128, 8):
+                    for j in range(0, 16, 2):
+                        for q0 in range(0, 512, 8):
                             assert len({(int(s) >> 1) & 7 for s in addr[q0:q0 + 8, j]}) == 8
                 else:
-                    for j in range(32):
-                        for h0 in range(0, 128, 16):
+                    for j in range(16):
+                        for h0 in range(0, 512, 16):
                             assert len({int(s) & 15 for s in addr[h0:h0 + 16, j]}) == 16
-            x = smem[addr]  # [thread, member]
-            smem[addr] = x @ m.T
+            # the two half-threads of a group together hold its 32 members
+            order = np.argsort(gidx * 2 + h, kind='stable')
+            full_addr = addr[order].reshape(256, 32)
+            x = smem[full_addr]
+            smem[full_addr] = x @ m.T
         state[base + goffs] = smem[slots]
         state[base + goffs + 1] = smem[slots + 1]
     return state
@@ -518,7 +525,7 @@ def test_tile_kernel_plan_replays_to_the_oracle():
         q, r = np.linalg.qr(rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d)))
         return q * (np.diag(r) / np.abs(np.diag(r)))
 
-    n = 14
+    n = 15
     cases = [([0, 1, 2, 3, 4], [5, 6, 7, 8, 9]), ([9, 10, 11, 12, 13], [4, 5, 6, 7, 8]),
              ([13, 0, 5, 2, 9], [9, 2, 11, 3, 7]), ([2, 3, 4, 5, 6], [2, 3, 4, 5, 6]),
              ([1, 3, 5, 7, 9], [0, 2, 4, 6, 8]), ([13, 12, 11, 10, 9], [8, 7, 6, 5, 4]),
@@ -530,9 +537,7 @@ def test_tile_kernel_plan_replays_to_the_oracle():
         cases.append((a, b))
     checked = 0
     for ta, tb in cases:
-        if len(set(ta) | set(tb) | {0, 1}) > 12:
-            assert _tile_plan(lib, n, [sorted(ta), sorted(tb)]) is None
-            continue
+        assert len(set(ta) | set(tb) | {0, 1, 2}) <= 13  # always: 10 targets + 3
         state = (rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)) / 2 ** (n / 2)
         ma, mb = unitary(5), unitary(5)
         got = _tile_emulate(lib, n, state, [(ma, ta), (mb, tb)])
@@ -549,16 +554,75 @@ def test_tile_kernel_plan_replays_to_the_oracle():
 
 def test_tile_blocks_feasibility():
     lib = _lib.load()
-    ok = lib.b2q_tile_blocks_feasible(_lib.C64, 30, 2, _lib.int_array([5, 5]),
-                                      _lib.int_array([29, 28, 27, 26, 25, 24, 23, 22, 21, 20]))
-    assert ok == 1
-    # 11 distinct high bits + bits 0, 1 = 13 > 12
+    ten_high = [29, 28, 27, 26, 25, 24, 23, 22, 21, 20]
+    # two 5-bit blocks always fit: 10 targets + index bits 0-2 = 13 tile bits
+    assert lib.b2q_tile_blocks_feasible(_lib.C64, 30, 2, _lib.int_array([5, 5]), _lib.int_array(ten_high)) == 1
     assert lib.b2q_tile_blocks_feasible(_lib.C64, 30, 2, _lib.int_array([5, 5]),
-                                        _lib.int_array([29, 28, 27, 26, 25, 24, 23, 22, 21, 20][:5] +
-                                                       [19, 18, 17, 16, 15])) == 1
+                                        _lib.int_array([0, 1, 2, 3, 4, 5, 6, 7, 8, 9])) == 1
     assert lib.b2q_tile_blocks_feasible(_lib.C128, 30, 2, _lib.int_array([5, 5]),
                                         _lib.int_array(list(range(2, 12)))) == 0
-    assert lib.b2q_tile_blocks_feasible(_lib.C64, 11, 2, _lib.int_array([5, 5]),
+    assert lib.b2q_tile_blocks_feasible(_lib.C64, 12, 2, _lib.int_array([5, 5]),
                                         _lib.int_array(list(range(0, 10)))) == 0
     assert lib.b2q_tile_blocks_feasible(_lib.C64, 30, 2, _lib.int_array([3, 2]),
                                         _lib.int_array([4, 9, 1, 0, 17])) == 1
+    assert lib.b2q_tile_blocks_feasible(_lib.C64, 30, 2, _lib.int_array([6, 2]),
+                                        _lib.int_array([4, 9, 1, 0, 17, 3, 5, 6])) == 0
+
+
+# ---- in-place bit permutation: the host planner's passes, replayed -----------------------
+
+def _permute_reference(state, src_bit):
+    n = len(src_bit)
+    o = np.arange(1 << n, dtype=np.int64)
+    i = np.zeros_like(o)
+    for k, sb in enumerate(src_bit):
+        i |= ((o >> k) & 1) << sb
+    return state[i]
+
+
+def test_inplace_permutation_planner_passes_compose_to_the_permutation():
+    """b2q_sv_permute_bits_inplace = a product of tile passes, each moving at most 13
+    (complex64) / 12 (complex128) index bits that include bits 0-3; replaying the
+    planned passes on the CPU must give the requested permutation."""
+    import ctypes
+
+    lib = _lib.load()
+    rng = np.random.RandomState(4)
+    cases = []
+    for n in (3, 9, 14, 16):
+        cases.append((n, list(range(n))[::-1]))                    # bit reversal (QFT order)
+        cases.append((n, list(range(1, n)) + [0]))                  # one long cycle
+        cases += [(n, rng.permutation(n).tolist()) for _ in range(3)]
+    worst = 0
+    for dtype_code, cap in ((_lib.C64, 13), (_lib.C128, 12)):
+        for n, src in cases:
+            out = (ctypes.c_int * (27 * 16))()
+            count = ctypes.c_int(0)
+            assert lib.b2q_debug_permute_plan(dtype_code, n, _lib.int_array(src), 16, out, ctypes.byref(count)) == 0
+            state = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+            want = _permute_reference(state, src)
+            got = state
+            assert count.value <= 16
+            if src == list(range(n)):
+                assert count.value == 0
+            for p in range(count.value):
+                row = list(out[27 * p: 27 * p + 27])
+                T = row[0]
+                tbits, src_local = row[1:1 + T], row[14:14 + T]
+                assert T <= min(cap, n) and tbits == sorted(tbits) and tbits[0] == 0
+                assert sorted(src_local) == list(range(T))
+                if n >= 4:
+                    assert tbits[:4] == [0, 1, 2, 3]  # runs of >= 128 bytes
+                full = list(range(n))
+                for k in range(T):
+                    full[tbits[k]] = tbits[src_local[k]]
+                got = _permute_reference(got, full)
+            np.testing.assert_array_equal(got, want)
+            worst = max(worst, count.value)
+    assert worst <= 4
+    # the 34-qubit bit reversal (the QFT's relabelled SWAPs): 17 transpositions, <= 5 passes
+    out = (ctypes.c_int * (27 * 16))()
+    count = ctypes.c_int(0)
+    assert lib.b2q_debug_permute_plan(_lib.C64, 34, _lib.int_array(list(range(34))[::-1]), 16, out,
+                                      ctypes.byref(count)) == 0
+    assert 1 <= count.value <= 5

@@ -1127,3 +1127,99 @@ def test_use_b200_is_reentrant_and_thread_safe(cirq, SV):
             t.join()
         assert not errors and sparse_simulator.Simulator is SV
     assert sparse_simulator.Simulator is original
+
+
+def test_forty_qubit_mostly_unentangled_circuit_like_reference(cirq, SV):
+    """split_untangled_states is honoured at any register size
+    (sim/simulation_product_state.py:68-139; the state-vector analogue of
+    density_matrix_simulator_test.py:1502-1520): 40 qubits whose entangled clusters
+    stay small never need more than a few amplitudes.  Seeded records equal the
+    reference's, mid-circuit measurement and reset included."""
+    q = cirq.LineQubit.range(40)
+    rng = np.random.RandomState(2)
+    ops_list = [cirq.H(x) for x in q[::3]] + [cirq.X(q[7]) ** 0.3, cirq.Y(q[22]) ** 0.7]
+    for start in (0, 9, 18, 30):  # four 4-qubit clusters
+        cluster = q[start:start + 4]
+        for _ in range(6):
+            a, b = rng.choice(4, 2, replace=False)
+            ops_list.append(cirq.FSimGate(rng.uniform(0, 2), rng.uniform(0, 2)).on(cluster[a], cluster[b]))
+            ops_list.append(cirq.rx(rng.uniform(0, 3)).on(cluster[a]))
+    ops_list += [cirq.SWAP(q[5], q[38]), cirq.CZ(q[13], q[14]) ** 0.4, cirq.measure(q[10], key='mid'),
+                 cirq.ResetChannel().on(q[11]), cirq.CNOT(q[10], q[12])]
+    # (per-qubit terminal measurements: with a mid-circuit measurement every repetition
+    # walks the circuit, and a JOINT measurement of 40 qubits would join them all — in
+    # the reference too)
+    circuit = cirq.Circuit(ops_list) + cirq.Circuit(cirq.measure(x, key=f'm{i}') for i, x in enumerate(q))
+    want = cirq.Simulator(seed=9).run(circuit, repetitions=6)
+    got = SV(seed=9).run(circuit, repetitions=6)
+    for key in ['mid'] + [f'm{i}' for i in range(40)]:
+        np.testing.assert_array_equal(got.measurements[key], want.measurements[key])
+    # all measurements terminal: one joint key, sampled sub-state by sub-state
+    terminal = cirq.Circuit(op for op in ops_list if not cirq.is_measurement(op)
+                            and not isinstance(op.gate, cirq.ResetChannel))
+    terminal += cirq.Circuit(cirq.measure(*q, key='m'))
+    want = cirq.Simulator(seed=3).run(terminal, repetitions=50)
+    got = SV(seed=3).run(terminal, repetitions=50)
+    np.testing.assert_array_equal(got.measurements['m'], want.measurements['m'])
+    # the final state stays a product of small sub-states (never 2^40 amplitudes)
+    sim = SV(seed=1)
+    final = sim.simulate(cirq.Circuit(ops_list))._final_simulator_state
+    comps = list({id(v): v for k, v in final.sim_states.items() if k is not None}.values())
+    assert max(len(v.qubits) for v in comps) <= 6 and len(comps) >= 10
+    ref = cirq.Simulator(seed=1).simulate(cirq.Circuit(ops_list))._final_simulator_state
+    for qubit in (q[0], q[9], q[19], q[33]):
+        a, b = final.sim_states[qubit], ref.sim_states[qubit]
+        assert a.qubits == b.qubits
+        np.testing.assert_allclose(a._state.to_numpy_tensor().reshape(-1), b.target_tensor.reshape(-1), atol=1e-6)
+
+
+def test_product_state_densifies_before_joins_outgrow_memory(cirq, SV, monkeypatch):
+    """Join policy of B200ProductState above _DENSE_JOIN_BITS (exercised here with the
+    thresholds lowered): the first join that would pass the limit merges the whole
+    register as (largest sub-state) x (everything else), later operations act on
+    the one dense state, large states are not factored back after measurements, and
+    the final merge transposes in place — results equal the reference's."""
+    import cirq_b200.sv_simulator as svm
+
+    monkeypatch.setattr(svm, '_DENSE_JOIN_BITS', 4)
+    monkeypatch.setattr(svm, '_MAX_DENSE_QUBITS', 9)
+    monkeypatch.setattr(svm, '_MAX_FACTOR_BITS', 4)
+    q = cirq.LineQubit.range(9)
+    circuit = cirq.testing.random_circuit(q, 14, 0.8, random_state=6)
+    for dtype, atol in ((np.complex64, 1e-5), (np.complex128, 1e-12)):
+        want = cirq.Simulator(dtype=dtype).simulate(circuit, qubit_order=q)
+        sim = SV(dtype=dtype)
+        got = sim.simulate(circuit, qubit_order=q)
+        np.testing.assert_allclose(got.final_state_vector, want.final_state_vector, atol=atol, rtol=0)
+        comps = {id(v) for k, v in got._final_simulator_state.sim_states.items() if k is not None}
+        assert len(comps) == 1  # densified
+    noisy = circuit + cirq.Circuit(cirq.measure(q[2], key='a'), cirq.H(q[2]), cirq.CNOT(q[2], q[5]),
+                                   cirq.measure(*q, key='m'))
+    want = cirq.Simulator(seed=4, split_untangled_states=False).run(noisy, repetitions=10)
+    got = SV(seed=4).run(noisy, repetitions=10)
+    for key in ('a', 'm'):
+        np.testing.assert_array_equal(got.measurements[key], want.measurements[key])
+
+
+def test_relabelled_swaps_put_back_by_inplace_permutation(cirq, SV, monkeypatch):
+    """With several SWAP gates relabelled by the scheduler, reading the raw state
+    restores the bit order with the in-place permutation kernel (here from 3 qubits
+    on) instead of real SWAP gates; same state as the reference."""
+    import cirq_b200.sv_simulator as svm
+
+    monkeypatch.setattr(svm, '_PERMUTE_RESTORE_MIN_BITS', 3)
+    q = cirq.LineQubit.range(7)
+    rng = np.random.RandomState(8)
+    ops_list = [cirq.H.on_each(*q)]
+    for i in range(12):
+        a, b = rng.choice(7, 2, replace=False)
+        ops_list.append(cirq.SWAP(q[a], q[b]))
+        ops_list.append(cirq.CZ(q[a], q[(a + 1) % 7]) ** rng.uniform(0, 1) if a != (a + 1) % 7 else cirq.T(q[a]))
+        ops_list.append(cirq.rx(rng.uniform(0, 3)).on(q[b]))
+    circuit = cirq.Circuit(ops_list)
+    for dtype, atol in ((np.complex64, 1e-5), (np.complex128, 1e-12)):
+        want = cirq.Simulator(dtype=dtype).simulate(circuit, qubit_order=q)
+        got = SV(dtype=dtype, split_untangled_states=False).simulate(circuit, qubit_order=q)
+        np.testing.assert_allclose(got.final_state_vector, want.final_state_vector, atol=atol, rtol=0)
+        steps = list(SV(dtype=dtype, split_untangled_states=False).simulate_moment_steps(circuit, qubit_order=q))
+        np.testing.assert_allclose(steps[-1].state_vector(), want.final_state_vector, atol=atol, rtol=0)
