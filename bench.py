@@ -68,19 +68,23 @@ WORKLOADS = {
     'qft24': ('qft', dict(n=24), 0),
     'qft22': ('qft', dict(n=22), 0),
     'rc20': ('rc', dict(n=20, depth=20, seed=1234), 0),
+    # the headline circuit in complex128 (17 GB state, register-tiled fp64 kernels: no
+    # tensor-core path for double precision)
+    'rqc30_c128': ('rqc', dict(rows=5, cols=6, depth=20, seed=1), 1_000_000),
     'qaoa16': ('qaoa', dict(n=16, p=2, graph_seed=0, noise=0.01, resolvers=256), 1000),
     'qaoa12': ('qaoa', dict(n=12, p=2, graph_seed=0, noise=0.01, resolvers=256), 1000),
     'qaoa10': ('qaoa', dict(n=10, p=2, graph_seed=0, noise=0.01, resolvers=256), 1000),
     'qaoa8': ('qaoa', dict(n=8, p=2, graph_seed=0, noise=0.01, resolvers=256), 1000),
 }
 # bounded CPU samples (same generator, fewer qubits): ~5-20 s of reference time in all
-CPU_SAMPLE = {'rqc30': 'rqc20', 'rqc24': 'rqc20', 'rqc20': 'rqc20', 'qft34': 'qft22', 'qft30': 'qft22',
+CPU_SAMPLE = {'rqc30': 'rqc20', 'rqc30_c128': 'rqc20', 'rqc24': 'rqc20', 'rqc20': 'rqc20', 'qft34': 'qft22', 'qft30': 'qft22',
               'qft24': 'qft22', 'qft22': 'qft22', 'rc20': 'rc20', 'qaoa16': 'qaoa10', 'qaoa12': 'qaoa10',
               'qaoa10': 'qaoa10', 'qaoa8': 'qaoa8'}
 # the reference arm (`--impl reference`) has minutes, not seconds: a larger sample
 REFERENCE_ARM_SAMPLE = dict(CPU_SAMPLE, rqc30='rqc24', qft34='qft24', qft30='qft24')
+WORKLOAD_DTYPE = {'rqc30_c128': np.complex128}
 # sub-entries of the N = 1 line
-SUB_CONFIGS = ('rc20', 'rqc24', 'qft34', 'qaoa16')
+SUB_CONFIGS = ('rc20', 'rqc24', 'qft34', 'qaoa16', 'rqc30_c128')
 
 
 def quiet_stdout():
@@ -142,10 +146,12 @@ def measured_traffic(n_bits, kernel):
     return int(got * 2.0 ** (n_bits - 30))
 
 
-def kernel_class(wires, n_bits=30):
-    """Name of the kernel a fused block on these index bits runs on (complex64,
-    default knobs: b2q_apply_tc.cu launch_tc_k / b2q_apply.cu apply_matrix_t)."""
+def kernel_class(wires, n_bits=30, real='float'):
+    """Name of the kernel a fused block on these index bits runs on (default
+    knobs: b2q_apply_tc.cu launch_tc_k / b2q_apply.cu apply_matrix_t)."""
     k = len(wires)
+    if real == 'double':
+        return f'sv_apply_fast_kernel<double,{k}>'
     tc4 = os.environ.get('CIRQ_B200_TC_MODE') == '2'  # opt-in: 4-qubit blocks on tcgen05 too
     if n_bits >= k + 7 and (k == 5 or (k == 4 and tc4)):
         return f'sv_apply_tc_staged_kernel<{k}>' if min(wires) < 2 else f'sv_apply_tc_kernel<{k}>'
@@ -154,19 +160,19 @@ def kernel_class(wires, n_bits=30):
     return f'sv_apply_fast_kernel<float,{k}>'
 
 
-def block_kernel_name(m, w, n_bits):
+def block_kernel_name(m, w, n_bits, real='float'):
     """(kernel name, blocks in the launch) of one scheduled block."""
     if np.ndim(m) == 1:
-        return 'sv_apply_diag_smem_kernel<float>', 1
-    return kernel_class(w, n_bits), 1
+        return f'sv_apply_diag_smem_kernel<{real}>', 1
+    return kernel_class(w, n_bits, real), 1
 
 
-def pass_kernel_name(group, n_bits):
+def pass_kernel_name(group, n_bits, real='float'):
     """Kernel of one pass from DeviceState.plan_passes: a single block, or two
     blocks in one tile pass."""
     if len(group) == 2:
         return 'sv_apply_tc_tile_kernel (2 blocks per pass)'
-    return block_kernel_name(group[0][0], group[0][1], n_bits)[0]
+    return block_kernel_name(group[0][0], group[0][1], n_bits, real)[0]
 
 
 def ref_unit_gates(cirq, circuit):
@@ -254,10 +260,10 @@ class ClockSampler:
 _REF_CACHE: dict = {}
 
 
-def time_reference(name, steps, warmup):
+def time_reference(name, steps, warmup, dtype=np.complex64):
     """Times the unmodified reference (cirq.Simulator / cirq.DensityMatrixSimulator,
     numpy) on the host; nothing of this repo's library is involved."""
-    key = (name, steps, warmup)
+    key = (name, steps, warmup, np.dtype(dtype).name)
     if key in _REF_CACHE:
         return _REF_CACHE[key]
     from cirq_b200._cirq_compat import import_cirq
@@ -270,7 +276,7 @@ def time_reference(name, steps, warmup):
         state = {'i': 0}
 
         def step():
-            sim = cirq.DensityMatrixSimulator(dtype=np.complex64, noise=cirq.depolarize(wl['noise_p']), seed=0)
+            sim = cirq.DensityMatrixSimulator(dtype=dtype, noise=cirq.depolarize(wl['noise_p']), seed=0)
             r = resolvers[state['i'] % len(resolvers)]
             state['i'] += 1
             sim.run_sweep(circuit, [r], repetitions=reps)
@@ -278,7 +284,7 @@ def time_reference(name, steps, warmup):
         run_circuit = circuit + cirq.Circuit(cirq.measure(*qubits, key='m')) if reps else circuit
 
         def step():
-            sim = cirq.Simulator(dtype=np.complex64, seed=0)
+            sim = cirq.Simulator(dtype=dtype, seed=0)
             if reps:
                 sim.run(run_circuit, repetitions=reps)
             else:
@@ -300,10 +306,11 @@ def cpu_baseline_for(workload, steps=3):
     """cpu_baseline object of `workload`: the reference on CPU_SAMPLE[workload]."""
     try:
         sample = CPU_SAMPLE[workload]
-        r = time_reference(sample, steps, 0)
+        dtype = WORKLOAD_DTYPE.get(workload, np.complex64)
+        r = time_reference(sample, steps, 0, dtype)
         eq, n = workload_equivalent(r['value'], r['bits'], workload)
         api = 'cirq.DensityMatrixSimulator(noise=depolarize).run_sweep, one resolver per step' \
-            if WORKLOADS[sample][0] == 'qaoa' else 'cirq.Simulator(complex64)'
+            if WORKLOADS[sample][0] == 'qaoa' else f'cirq.Simulator({np.dtype(dtype).name})'
         return {'value': eq, 'unit': 'gates/s', 'cores': 1, 'kind': 'reference',
                 'raw_value_on_sample': r['value'], 'same_config': sample == workload,
                 'sample': f"{api} on {sample}: {r['n']} qubits, {r['raw_ops']} ops = {r['unit_gates']} k<=2 "
@@ -365,19 +372,37 @@ def run_reference_arm(args):
 # ---- the B200 arm, one GPU -----------------------------------------------------------------
 
 
-def _roofline(per_kernel, record_steps, bytes_per_launch, n_bits, peak_gbs, peak_src):
+def _roofline(per_kernel, record_steps, bytes_per_pass, n_bits, peak_gbs, peak_src):
+    """`roofline` object of one measurement.  The unit of the metric is the fused gate
+    pass: 2 * sizeof(complex) * 2^bits algorithmic bytes each.  A launch
+    of the tile kernel processes TWO units while moving the state once, so its
+    `achieved` (algorithmic bytes per launch / launch time, the definition the
+    contract gives) is reported next to the rate of the bytes it really moves."""
     total_ms = sum(np.sum(v) for v in per_kernel.values())
     count = sum(len(v) for v in per_kernel.values())
+    units = {k: (2 if '2 blocks per pass' in k else 1) for k in per_kernel}
     breakdown = {k: {'launches_per_step': len(v) // record_steps, 'ms_per_launch': float(np.mean(v)),
+                     'fused_blocks_per_launch': units[k],
                      'share_of_gate_time': float(np.sum(v) / total_ms)} for k, v in per_kernel.items()}
     dominant = max(breakdown, key=lambda k: breakdown[k]['share_of_gate_time'])
     pass_ms = breakdown[dominant]['ms_per_launch']
-    achieved = bytes_per_launch / (pass_ms * 1e-3) / 1e9
+    u = units[dominant]
+    achieved = u * bytes_per_pass / (pass_ms * 1e-3) / 1e9
+    moved = bytes_per_pass / (pass_ms * 1e-3) / 1e9
+    total_units = sum(units[k] * len(v) for k, v in per_kernel.items())
     return {'bound': 'hbm', 'achieved': achieved, 'peak': peak_gbs, 'unit': 'GB/s',
             'frac': achieved / peak_gbs, 'traffic': measured_traffic(n_bits, dominant), 'kernel': dominant,
-            'peak_source': peak_src, 'bytes_per_launch': bytes_per_launch, 'ms_per_launch': pass_ms,
-            'mean_ms_over_all_passes': float(total_ms / max(1, count)),
-            'frac_over_all_passes': float(bytes_per_launch / (total_ms / max(1, count) * 1e-3) / 1e9 / peak_gbs),
+            'peak_source': peak_src, 'bytes_per_launch': u * bytes_per_pass,
+            'fused_blocks_per_launch': u, 'algorithmic_bytes_per_fused_block': bytes_per_pass,
+            'hbm_bytes_moved_per_launch': bytes_per_pass,
+            'frac_of_peak_by_bytes_moved': moved / peak_gbs,
+            'note': ('this kernel applies 2 fused blocks per pass over HBM: it moves half the algorithmic '
+                     'bytes, so `achieved` (algorithmic bytes / time) can exceed what the memory system '
+                     'carries; `frac_of_peak_by_bytes_moved` is the rate of the real traffic — the kernel is '
+                     'bound by its tensor-core / TMEM round trips, not by HBM') if u > 1 else None,
+            'ms_per_launch': pass_ms, 'mean_ms_over_all_passes': float(total_ms / max(1, count)),
+            'ms_per_fused_block_over_all_passes': float(total_ms / max(1, total_units)),
+            'frac_over_all_passes': float(total_units * bytes_per_pass / (total_ms * 1e-3) / 1e9 / peak_gbs),
             'kernels': breakdown}, count // record_steps
 
 
@@ -413,12 +438,13 @@ def measure_sv(name, steps, warmup, args, local_rank=0):
     n, reps = wl['n'], wl['reps']
     gates = W.circuit_to_gates(wl['circuit'], wl['qubits'])
     unit_gates = wl['unit_gates']
-    dtype = np.complex64
+    dtype = WORKLOAD_DTYPE.get(name, np.complex64)
+    amp_bytes = np.dtype(dtype).itemsize
     # Host scheduling happens ONCE, outside the timed region: fusion + lazy state
     # growth (sub-states joined by the kron kernel, as with split_untangled_states).
     plan = build_plan(n, gates, dtype, args.max_fused)
     blocks = [blk for op in plan['ops'] if op[0] == 'apply' for blk in op[2]]
-    state_bytes = (8 << n)
+    state_bytes = (amp_bytes << n)
     rng = np.random.RandomState(0)
     uniforms = rng.random_sample(max(reps, 1))
     u_dev = torch.from_numpy(uniforms).to('cuda')
@@ -438,7 +464,8 @@ def measure_sv(name, steps, warmup, args, local_rank=0):
             a.record()
             state.apply_batch(group)
             b.record()
-            pairs.append((state.n_bits, pass_kernel_name(group, state.n_bits), a, b))
+            pairs.append((state.n_bits, pass_kernel_name(group, state.n_bits,
+                                                         'double' if amp_bytes == 16 else 'float'), a, b))
 
     def step(record=False):
         dev = replay_plan(plan, on_apply=timed_apply if record else None)
@@ -512,7 +539,7 @@ def measure_sv(name, steps, warmup, args, local_rank=0):
     dense_widths = [len(w) for m, w in flat if np.ndim(m) == 2]
     return {
         'metric': 'fused_gates_per_s', 'value': value, 'unit': 'gates/s', 'steps': steps, 'warmup': warmup,
-        'ms_per_step': ms_per_step, 'dtype': 'c64',
+        'ms_per_step': ms_per_step, 'dtype': 'c128' if amp_bytes == 16 else 'c64',
         'config': {'workload': name, 'generator': wl['generator'], 'n_qubits': n,
                    'raw_ops': len(gates),
                    'gate_unit': 'k<=2 fused blocks (cirq.merge_k_qubit_unitaries(k=2) count)',

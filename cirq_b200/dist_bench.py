@@ -207,7 +207,8 @@ def measure(workload, args, world, rank, local_rank, steps, warmup, n_local=None
     bare = breakdown.get('dist_swap_bit_kernel (+ 2 stream barriers)')
     equiv = 2.0 ** (n - 30)
     value = unit_gates * equiv / (ms_per_step * 1e-3)
-    achieved = 2 * shard_bytes / (pass_ms * 1e-3) / 1e9
+    units = 2 if '2 blocks per pass' in dominant else 1  # fused blocks per launch of the tile kernel
+    achieved = units * 2 * shard_bytes / (pass_ms * 1e-3) / 1e9
 
     # e2e through the Cirq-facing sharded API (host scheduling + result gather inside)
     sv.close()
@@ -280,7 +281,9 @@ def measure(workload, args, world, rank, local_rank, steps, warmup, n_local=None
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak_gbs, 'unit': 'GB/s',
                      'frac': achieved / peak_gbs, 'traffic': B.measured_traffic(n - (world.bit_length() - 1), dominant),
                      'kernel': dominant + ' (per rank, in-step, max over ranks)',
-                     'peak_source': peak_src, 'bytes_per_launch': 2 * shard_bytes,
+                     'peak_source': peak_src, 'bytes_per_launch': units * 2 * shard_bytes,
+                     'fused_blocks_per_launch': units, 'hbm_bytes_moved_per_launch': 2 * shard_bytes,
+                     'frac_of_peak_by_bytes_moved': achieved / units / peak_gbs,
                      'ms_per_launch': pass_ms, 'kernels': breakdown},
         'cpu_baseline': cpu,
         'e2e': {'value': unit_gates * equiv / e2e_s, 'unit': 'gates/s', 'ms_per_step': e2e_s * 1e3,

@@ -392,6 +392,24 @@ class B200ProductState(SimulationProductState):
         target = self.join_for(op.qubits)
         target._state.queue_unitary(unitary, target.get_axes(op.qubits))
 
+    def create_merged_state(self):
+        """``SimulationProductState.create_merged_state``
+        (sim/simulation_product_state.py:68-81).  The reference copies: it joins the
+        empty [None] state with every sub-state out of place and transposes the result,
+        i.e. needs the final state twice.  Registers above _MAX_FACTOR_BITS qubits are
+        merged IN the product state instead — the sub-states are joined for good
+        (`join_for`) and the one remaining state is brought to the register's qubit
+        order by the in-place permutation — so a 34-qubit state is never duplicated."""
+        if not self.split_untangled_states or len(self.qubits) <= _MAX_FACTOR_BITS:
+            return super().create_merged_state()
+        merged = self.join_for(tuple(self.qubits))
+        phase = self._sim_states[None]
+        scalar = complex(phase._state.to_numpy_tensor().reshape(-1)[0]) if phase is not None else 1.0
+        if scalar != 1.0:  # zero-qubit operations (global phases) live in the [None] state
+            merged._state.scale(scalar)
+            phase._state.scale(1.0 / scalar)
+        return merged.transpose_to_qubit_order(self.qubits, inplace=True)
+
     def join_for(self, qubits):
         """The sub-state holding all of `qubits`, joining sub-states by Kronecker
         products when they live apart (sim/simulation_product_state.py:110-123).

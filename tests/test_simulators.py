@@ -1186,6 +1186,7 @@ def test_product_state_densifies_before_joins_outgrow_memory(cirq, SV, monkeypat
     monkeypatch.setattr(svm, '_MAX_FACTOR_BITS', 4)
     q = cirq.LineQubit.range(9)
     circuit = cirq.testing.random_circuit(q, 14, 0.8, random_state=6)
+    circuit.append(cirq.global_phase_operation(np.exp(0.7j)))  # lives in the empty [None] state
     for dtype, atol in ((np.complex64, 1e-5), (np.complex128, 1e-12)):
         want = cirq.Simulator(dtype=dtype).simulate(circuit, qubit_order=q)
         sim = SV(dtype=dtype)
