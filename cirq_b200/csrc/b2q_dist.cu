@@ -65,9 +65,9 @@ __global__ void __launch_bounds__(256)
 // with sub-rank rho (its values of the exchanged global bits) keeps sub-block rho
 // and swaps sub-block c with sub-block rho of the rank whose sub-rank is c: every
 // rank streams (1 - 2^-m) of its shard out and in once, instead of m times a half
-// (m = 3: 7/8 against 3/2).  blockIdx.y selects the partner; of each pair the
-// lower sub-rank serves the lower half of the index range, the higher one the
-// upper half, so both link directions carry equal traffic.  In place.
+// (m = 3: 7/8 against 3/2).  One launch per partner `c`; of each pair the lower
+// sub-rank serves the lower half of the index range, the higher one the upper
+// half, so both link directions carry equal traffic.  In place.
 struct SwapMultiParams {
   void* peers[8];    // by sub-rank value (entry [rho] unused)
   int lbits_v[3];    // exchanged local bits, ascending, in vector-index units
@@ -78,9 +78,8 @@ struct SwapMultiParams {
 
 template <typename V>
 __global__ void __launch_bounds__(256)
-    dist_swap_multi_kernel(V* __restrict__ mine, const __grid_constant__ SwapMultiParams p) {
+    dist_swap_multi_kernel(V* __restrict__ mine, const __grid_constant__ SwapMultiParams p, int c) {
   constexpr int U = 4;
-  const int c = (int)blockIdx.y < p.rho ? (int)blockIdx.y : (int)blockIdx.y + 1;
   V* __restrict__ peer = reinterpret_cast<V*>(p.peers[c]);
   uint64_t mine_or = 0, peer_or = 0;
   for (int i = 0; i < p.m; ++i) {
@@ -152,15 +151,21 @@ extern "C" int b2q_dist_swap_bits(void* mine, void* const* peers, int dtype, int
   p.rho = my_sub_rank;
   p.nvec_rest = 1ull << (n_local - elems_log2 - m);
   const uint64_t work = std::max<uint64_t>(1, p.nvec_rest / 2);
-  const uint64_t per_partner = std::max<uint64_t>(1, (148ull * 16) / ((1u << m) - 1));
-  const uint64_t blocks = std::max<uint64_t>(1, std::min<uint64_t>((work / 4 + 255) / 256, per_partner));
-  const dim3 grid((unsigned)blocks, (1u << m) - 1);
+  const uint64_t blocks = std::max<uint64_t>(1, std::min<uint64_t>((work / 4 + 255) / 256, 148ull * 16));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == B2Q_C64)
-    dist_swap_multi_kernel<float4><<<grid, 256, 0, s>>>(reinterpret_cast<float4*>(mine), p);
-  else
-    dist_swap_multi_kernel<double2><<<grid, 256, 0, s>>>(reinterpret_cast<double2*>(mine), p);
-  B2Q_LAUNCH_CHECK("dist_swap_multi_kernel");
+  // One launch per partner, in the order rho ^ 1, rho ^ 2, ...: at step s every rank
+  // talks to the rank whose sub-rank differs by s — a perfect matching, so no GPU
+  // serves more than one partner at a time (all partners at once measured 387 GB/s
+  // per direction for m = 2 and 293 for m = 3, against 680 for one pair).  The
+  // steps touch disjoint sub-blocks, so they need no barrier between them.
+  for (int step = 1; step < (1 << m); ++step) {
+    const int c = my_sub_rank ^ step;
+    if (dtype == B2Q_C64)
+      dist_swap_multi_kernel<float4><<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<float4*>(mine), p, c);
+    else
+      dist_swap_multi_kernel<double2><<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<double2*>(mine), p, c);
+    B2Q_LAUNCH_CHECK("dist_swap_multi_kernel");
+  }
   return B2Q_OK;
 }
 

@@ -154,13 +154,16 @@ def measure(workload, args, world, rank, local_rank, steps, warmup, n_local=None
     for _ in range(warmup):
         step()
     launches0 = int(lib.b2q_launch_count())
-    sv.swaps = sv.passes = sv.fused_exchanges = 0
+    sv.swaps = sv.passes = sv.fused_exchanges = sv.exchanges = 0
+    sv.exchange_volume = 0.0
     with B.ClockSampler(local_rank) as clocks:
         ms_per_step = _timed(torch, dist, step, steps)
         launches = (int(lib.b2q_launch_count()) - launches0) // max(steps, 1)
         swaps = sv.swaps // max(steps, 1)
         passes = sv.passes // max(steps, 1)
         fused_per_step = sv.fused_exchanges // max(steps, 1)
+        exchanges_per_step = sv.exchanges // max(steps, 1)
+        volume_per_step = sv.exchange_volume / max(steps, 1)
         norm2_big = sv.norm2()
 
         # two instrumented steps: CUDA events around every launch on the shard
@@ -173,6 +176,8 @@ def measure(workload, args, world, rank, local_rank, steps, warmup, n_local=None
             b.record()
             if kind == 'exchange':
                 kname = 'dist_swap_bit_kernel (+ 2 stream barriers)'
+            elif kind.startswith('exchange'):
+                kname = f'dist_swap_multi_kernel, {kind[8:]} bits (+ 2 stream barriers)'
             elif kind == 'pass+exchange':
                 kname = 'sv_apply_tc_staged_kernel + exchange (b2q_dist_apply_exchange)'
             else:
@@ -198,13 +203,18 @@ def measure(workload, args, world, rank, local_rank, steps, warmup, n_local=None
     breakdown = {k: {'launches_per_step': len(per_kernel[k]) // record_steps, 'ms_per_launch': float(means[i]),
                      'share_of_step_kernel_time': float(means[i] * len(per_kernel[k]) / total)}
                  for i, k in enumerate(keys)}
-    pass_keys = [k for k in keys if 'exchange' not in k and 'swap' not in k]
+    pass_keys = [k for k in keys if 'exchange' not in k and 'swap' not in k] or keys
     dominant = max(pass_keys, key=lambda k: breakdown[k]['share_of_step_kernel_time'])
     pass_ms = breakdown[dominant]['ms_per_launch']
     exch = [k for k in keys if k not in pass_keys]
     exchange_ms_per_step = sum(breakdown[k]['ms_per_launch'] * breakdown[k]['launches_per_step'] for k in exch)
     swap_bytes = shard_bytes // 2
     bare = breakdown.get('dist_swap_bit_kernel (+ 2 stream barriers)')
+    multi = {k: {'ms': breakdown[k]['ms_per_launch'],
+                 'bytes_out_per_gpu': int(shard_bytes * (1 - 0.5 ** int(k.split(',')[1].split()[0]))),
+                 'GBps_per_direction': shard_bytes * (1 - 0.5 ** int(k.split(',')[1].split()[0]))
+                 / (breakdown[k]['ms_per_launch'] * 1e-3) / 1e9}
+             for k in keys if k.startswith('dist_swap_multi_kernel')}
     equiv = 2.0 ** (n - 30)
     value = unit_gates * equiv / (ms_per_step * 1e-3)
     units = 2 if '2 blocks per pass' in dominant else 1  # fused blocks per launch of the tile kernel
@@ -274,6 +284,8 @@ def measure(workload, args, world, rank, local_rank, steps, warmup, n_local=None
                                 'bare_swap_ms': bare['ms_per_launch'] if bare else None,
                                 'bare_swap_GBps_per_direction':
                                     swap_bytes / (bare['ms_per_launch'] * 1e-3) / 1e9 if bare else None,
+                                'multi_bit_exchanges': multi, 'exchange_kernels_per_step': exchanges_per_step,
+                                'shard_volumes_sent_per_step': volume_per_step,
                                 'nvlink5_GBps_per_direction': 900.0,
                                 'how': 'one peer-memory kernel per rank (b2q_dist_swap_bit / '
                                        'b2q_dist_apply_exchange) between two stream-ordered barriers'},

@@ -910,8 +910,8 @@ class B200Simulator(
         noise, seed: as ``cirq.Simulator``.
         split_untangled_states: as ``cirq.Simulator`` (default True): unentangled
             qubit sets are kept as separate device states and joined by a
-            Kronecker-product kernel when a gate couples them; ignored above
-            30 qubits.
+            Kronecker-product kernel when a gate couples them, at any register
+            size (above 31 qubits a join merges the whole register at once).
         max_fused_qubits: widest fused block (one GPU pass each).
         sweep_batch: False (default) runs ``run_sweep`` resolver by resolver like
             the reference; True lays all resolvers out as one device array and

@@ -46,6 +46,12 @@ def main():
             ref.apply_batch(blocks)
             want = ref.to_numpy()
             err = float(np.max(np.abs(got - want)))
+            if n <= 16:
+                # ... and against the CPU oracle (the checker; gate by gate, unfused)
+                from oracle import sv_oracle as orc
+
+                want_oracle = orc.run_gate_list(n, gates, dtype=dtype, initial=5)
+                err = max(err, float(np.max(np.abs(got - want_oracle))))
             nrm = sv.norm2()
             samples = sv.sample(20000, seed=3)
             # chi-squared of the top 4 logical qubits against the single-GPU probabilities
@@ -57,8 +63,10 @@ def main():
             good = err <= atol and abs(nrm - 1) < 1e-4 and chi2 < 15 + 6 * np.sqrt(30) + 10
             ok &= good
             if rank == 0:
-                print(f'n={n} {np.dtype(dtype)} world={world}: max|diff|={err:.2e} norm={nrm:.6f} '
-                      f'swaps={sv.swaps} passes={sv.passes} chi2={chi2:.1f} {"OK" if good else "FAIL"}',
+                print(f'n={n} {np.dtype(dtype)} world={world}: max|diff| vs 1 GPU{" and oracle" if n <= 16 else ""}'
+                      f'={err:.2e} norm={nrm:.6f} swaps={sv.swaps} exchanges={sv.exchanges} '
+                      f'(volume {sv.exchange_volume:.3f} shards) passes={sv.passes} chi2={chi2:.1f} '
+                      f'{"OK" if good else "FAIL"}',
                       flush=True)
             sv.close()
     # lazy state growth from |0...0>: prefix on replicated sub-states, join into the shards
@@ -138,6 +146,26 @@ def main():
         if rank == 0:
             print(f'swap global<->local bit {lbit}: {ms:.2f} ms, {half / ms / 1e6:.0f} GB/s per direction '
                   f'(half shard {half / 1e9:.2f} GB)', flush=True)
+    if world >= 4:
+        g = world.bit_length() - 1
+        for m in range(2, g + 1):
+            pairs = [(n_local + i, n_local - 1 - 2 * i) for i in range(m)]
+            torch.cuda.synchronize()
+            dist.barrier()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            sv.exchange_bits(pairs)
+            s.record()
+            reps = 4
+            for _ in range(reps):
+                sv.exchange_bits([(n_local + i, n_local - 1 - 2 * i) for i in range(m)])
+            e.record()
+            torch.cuda.synchronize()
+            ms = s.elapsed_time(e) / reps
+            out = sv.local.nbytes * (1 - 0.5 ** m)
+            if rank == 0:
+                print(f'{m}-bit exchange: {ms:.2f} ms, {out / ms / 1e6:.0f} GB/s per direction '
+                      f'({out / 1e9:.2f} GB out per GPU = {1 - 0.5 ** m:.3f} shard; {m} single swaps move '
+                      f'{m * 0.5:.1f} shards)', flush=True)
     sv.close()
     if rank == 0:
         print('DIST CHECK', 'PASSED' if ok else 'FAILED', flush=True)
