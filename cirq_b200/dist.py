@@ -285,7 +285,7 @@ class ExchangePlanner:
     with the preceding local pass (fused kernel) hides that pass: FUSE_GAIN.
     """
 
-    FUSE_GAIN = 0.2  # a hidden HBM pass, in units of a shard over NVLink (0.31 / 0.72 * 0.5)
+    FUSE_GAIN = 0.13  # measured: a fused pass + swap costs 4.7 ms more than the pass, a bare swap 6.3 ms (30-bit shards)
 
     def __init__(self, metas, n_local: int, lowest_victim: int, can_fuse: bool, max_bits: int):
         self.metas = metas

@@ -288,20 +288,25 @@ class B200StateVector(qis.QuantumStateRepresentation):
         return out
 
     def reindex_inplace(self, axes: Sequence[int]) -> None:
-        """`reindex` without a second buffer: the in-place tile permutation
-        (b2q_sv_permute_bits_inplace).  For callers that drop the old order anyway
-        (``transpose_to_qubit_order(inplace=True)`` at the end of
+        """`reindex` without a second buffer and, at first, without moving anything: the
+        new axis order is folded into the bit map that relabelled SWAPs already use
+        (`_where`).  Readers that address the array by bit position (amplitude gathers,
+        Pauli expectations, reduced density matrices) never pay for it; a reader of the
+        raw array triggers ONE in-place permutation (b2q_sv_permute_bits_inplace) that
+        settles the SWAPs and the axis order together.  For callers that drop the old
+        order anyway (``transpose_to_qubit_order(inplace=True)`` at the end of
         ``create_merged_state``, sim/simulation_product_state.py:68-81)."""
         axes = [int(a) for a in axes]
         n = self._n
         if axes == list(range(n)):
             return
-        src_bit = [0] * n
-        for k, a in enumerate(axes):
-            src_bit[n - 1 - k] = n - 1 - a
-        dev = self.device_state  # (flushes; relabelled SWAPs restored)
+        self.flush(restore=False)
+        where = self._where if self._where is not None else list(range(n))
+        # new logical bit n-1-k is the old logical bit n-1-axes[k]
+        self._where = [where[n - 1 - axes[n - 1 - b]] for b in range(n)]
+        if self._where == list(range(n)):
+            self._where = None
         self._host = None
-        self.passes += dev.permute_bits_inplace(src_bit)
 
     def factor(self, axes: Sequence[int], *, validate=True, atol=1e-07):
         """``factor_state_vector`` (linalg/transformations.py:647-691): pivot on the

@@ -70,6 +70,13 @@ def calls(n, DS, torch):
     perm[0], perm[n - 1] = perm[n - 1], perm[0]
     perm[3], perm[12] = perm[12], perm[3]
     out.append(('permute bits out of place (sv_permute_bits_kernel)', 2 * amp, lambda: dev.permute_bits(perm)))
+    rev = list(range(n))[::-1]
+    out.append(('bit reversal IN PLACE, 3-4 tile passes (sv_permute_tile_kernel)', 2 * amp * 3,
+                lambda: dev.permute_bits_inplace(rev)))
+    u5a, u5b = np.linalg.qr(rng.standard_normal((32, 32)) + 1j * rng.standard_normal((32, 32)))[0], \
+        np.linalg.qr(rng.standard_normal((32, 32)) + 1j * rng.standard_normal((32, 32)))[0]
+    out.append(('two 5-qubit blocks in one pass (sv_apply_tc_tile_kernel)', 2 * amp,
+                lambda: dev.apply_tile_blocks([(u5a, [n - 1, 17, 9, 5, 12]), (u5b, [22, 9, n - 4, 14, 3])])))
     other = dev.copy()
     out.append(('allclose (sv_allclose_kernel)', 2 * amp, lambda: dev.allclose(other, 1e-6)))
     # density matrix view of the same array: n/2 qubits

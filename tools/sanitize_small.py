@@ -3,7 +3,8 @@
     compute-sanitizer --tool memcheck python tools/sanitize_small.py
 
 (register / tensor-core / diagonal gate passes, reductions, sampler, collapse,
-layout, batched-trajectory and reduced-density-matrix kernels at 12-14 qubits).
+layout, in-place permutation, two-block tile, batched-trajectory and
+reduced-density-matrix kernels at 12-15 qubits).
 """
 import os
 import sys
@@ -39,6 +40,16 @@ def main():
         dev.amplitudes([0, 5, 77])
         p = dev.marginal_probs([5])
         dev.collapse([5], [1], p[1] / p.sum())
+        # in-place bit permutation (shared-memory tiles) and, for complex64, two blocks in
+        # one tile pass (tcgen05 + TMEM, cp.async double buffering)
+        dev.permute_bits_inplace(list(range(n))[::-1])
+        dev.permute_bits_inplace(rng.permutation(n).tolist())
+        if dtype == np.complex64:
+            dev.apply_tile_blocks([(unitary(5), [12, 4, 9, 0, 6]), (unitary(3), [7, 1, 11])])
+            dev.apply_tile_blocks([(unitary(5), [8, 3, 10, 5, 2])])
+            big = DeviceState.basis(15, dtype, 1)
+            big.apply_tile_blocks([(unitary(5), [14, 13, 12, 11, 10]), (unitary(5), [9, 8, 7, 6, 5])])
+            assert abs(big.norm2() - 1) < 1e-3
         a = DeviceState.basis(4, dtype, 3)
         b = a.kron(DeviceState.basis(3, dtype, 1))
         b.permute_bits([6, 5, 4, 3, 2, 1, 0][::-1])
