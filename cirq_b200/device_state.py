@@ -136,7 +136,8 @@ class DeviceState:
 
     def tile_pairing(self) -> bool:
         return (self.code == _lib.C64 and self.n_bits >= self.TILE_MIN_BITS
-                and os.environ.get('CIRQ_B200_TILE_PAIRS', '1') != '0')
+                and os.environ.get('CIRQ_B200_TILE_PAIRS', '1') != '0'
+                and os.environ.get('CIRQ_B200_TC_MODE', '1') != '0')  # (the tile pass is a tensor-core kernel)
 
     def _pairable(self, m, b) -> bool:
         return np.ndim(m) == 2 and len(b) <= 5
