@@ -443,6 +443,7 @@ class ShardedStateVector:
 
     def __init__(self, n_qubits: int, dtype=np.complex64, *, backend=None, group=None,
                  initial_index: int | None = 0):
+        self._owns_backend = backend is None  # (a caller's backend outlives this state)
         if backend is None:
             import torch.distributed as dist
 
@@ -778,7 +779,9 @@ class ShardedStateVector:
         return phys_state[src]
 
     def close(self):
-        if hasattr(self.backend, 'close'):
+        """Releases the shard memory — unless it belongs to the caller (a
+        B200ShardedSimulator keeps one set of shards and IPC mappings across calls)."""
+        if self._owns_backend and hasattr(self.backend, 'close'):
             self.backend.close()
 
 
@@ -904,7 +907,9 @@ class B200ShardedSimulator:
         return gates, measured
 
     def simulate_sharded(self, circuit, qubit_order=None, initial_state: int = 0) -> ShardedStateVector:
-        """Evolves |initial_state> and returns the sharded final state."""
+        """Evolves |initial_state> and returns the sharded final state.  The state lives in
+        the simulator's cached shards: it is valid until the next call on this simulator
+        (or `close()`)."""
         from cirq_b200._cirq_compat import import_cirq
         from cirq_b200.fusion import fuse_gates
 
@@ -914,13 +919,15 @@ class B200ShardedSimulator:
         ).order_for(circuit.all_qubits())
         gates, _ = self._gates(circuit, qubits)
         if initial_state != 0:
-            sv = ShardedStateVector(len(qubits), self.dtype, group=self.group, initial_index=initial_state)
+            sv = ShardedStateVector(len(qubits), self.dtype, group=self.group,
+                                    backend=self._backend_for(len(qubits)), initial_index=initial_state)
             perm: dict = {}
             sv.apply_blocks(fuse_gates(gates, self.max_fused, self.dtype, sv.n_local, diagonal_blocks=True,
                                        permutation=perm))
             sv.rename_bits(perm)
             return sv
-        sv = ShardedStateVector(len(qubits), self.dtype, group=self.group, initial_index=None)
+        sv = ShardedStateVector(len(qubits), self.dtype, group=self.group,
+                                backend=self._backend_for(len(qubits)), initial_index=None)
         execute_sharded_plan(plan_sharded(sv.n, gates, self.dtype, self.max_fused, sv.n_local,
                                           live_cls=type(sv.local)), sv)
         return sv
