@@ -65,6 +65,8 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_int, c_int, c_uint64, c_uint64, POINTER(c_double), c_void_p],
     ),
+    'b2q_sv_pauli_expectation_multi': (
+        c_int, [c_void_p, c_int, c_int, c_uint64, c_void_p, c_int, c_void_p, c_void_p]),
     'b2q_sv_kron': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'b2q_sv_permute_bits': (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_int), c_void_p]),
     'b2q_sv_permute_bits_inplace': (c_int, [c_void_p, c_int, c_int, POINTER(c_int), POINTER(c_int), c_void_p]),

@@ -583,6 +583,82 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Several Pauli strings that flip the SAME bits (one x mask, T <= 16 z masks) in ONE
+// pass: conj(psi[i ^ x]) * psi[i] is formed once per amplitude, each string only adds
+// its own sign.  A PauliSum of Z-type terms (the cost Hamiltonian of a QAOA sweep:
+// x = 0 for every edge) costs one read of the state instead of one per term.
+// partial[b * 2T + 2t] (+1) = re (im) of block b's sum for string t.
+constexpr int kPauliMaxTerms = 16;
+struct PauliMultiParams {
+  uint64_t zmask[kPauliMaxTerms];
+  int count;
+};
+
+// DIAG: x mask 0 (Z-type strings): the pair product is |psi[i]|^2, real.
+template <typename real, bool DIAG>
+__global__ void __launch_bounds__(256)
+    sv_pauli_multi_partial_kernel(const typename Cplx<real>::type* __restrict__ state,
+                                  uint64_t total, uint64_t xmask,
+                                  const __grid_constant__ PauliMultiParams p,
+                                  double* __restrict__ partial) {
+  using C = typename Cplx<real>::type;
+  double ar[kPauliMaxTerms], ai[kPauliMaxTerms];
+#pragma unroll
+  for (int t = 0; t < kPauliMaxTerms; ++t) ar[t] = ai[t] = 0.0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const C a = state[i];
+    const C b = DIAG ? a : state[i ^ xmask];
+    const double re = (double)b.x * (double)a.x + (double)b.y * (double)a.y;
+    const double im = DIAG ? 0.0 : (double)b.x * (double)a.y - (double)b.y * (double)a.x;
+#pragma unroll
+    for (int t = 0; t < kPauliMaxTerms; ++t) {
+      if (t < p.count) {
+        const bool neg = __popcll(i & p.zmask[t]) & 1;
+        ar[t] += neg ? -re : re;
+        if constexpr (!DIAG) ai[t] += neg ? -im : im;
+      }
+    }
+  }
+  __shared__ double sm[8][2 * kPauliMaxTerms];
+#pragma unroll
+  for (int t = 0; t < kPauliMaxTerms; ++t) {
+    if (t < p.count) {
+      const double r = warp_sum(ar[t]);
+      const double m = warp_sum(ai[t]);
+      if ((threadIdx.x & 31) == 0) {
+        sm[threadIdx.x >> 5][2 * t] = r;
+        sm[threadIdx.x >> 5][2 * t + 1] = m;
+      }
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < 2 * p.count) {
+    double v = 0;
+    for (int w = 0; w < 8; ++w) v += sm[w][threadIdx.x];
+    partial[(size_t)blockIdx.x * 2 * p.count + threadIdx.x] = v;
+  }
+}
+
+// out[j] = sum_b partial[b * width + j]
+__global__ void __launch_bounds__(256)
+    column_sum_kernel(const double* __restrict__ partial, uint64_t blocks, int width,
+                      double* __restrict__ out) {
+  __shared__ double sm[256];
+  for (int j = 0; j < width; ++j) {
+    double v = 0;
+    for (uint64_t b = threadIdx.x; b < blocks; b += blockDim.x) v += partial[b * width + j];
+    sm[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if ((int)threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[j] = sm[0];
+    __syncthreads();
+  }
+}
+
 // ---- reduced density matrix ---------------------------------------------------
 
 // rho[a][b] = sum_rest psi[a, rest] conj(psi[b, rest]) over the M kept bits
@@ -1104,6 +1180,61 @@ extern "C" int b2q_sv_pauli_expectation(const void* state, int dtype, int n_qubi
   }
   out_re_im[0] = re;
   out_re_im[1] = im;
+  return B2Q_OK;
+}
+
+extern "C" int b2q_sv_pauli_expectation_multi(const void* state, int dtype, int n_qubits,
+                                              uint64_t x_mask, const uint64_t* z_masks, int count,
+                                              double* out_re_im, void* stream) {
+  B2Q_REQUIRE(state != nullptr && z_masks != nullptr && out_re_im != nullptr, "null argument");
+  B2Q_CHECK_DTYPE(dtype);
+  B2Q_REQUIRE(count >= 1, "no Pauli strings");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const uint64_t total = 1ull << n_qubits;
+  B2Q_REQUIRE(x_mask < total, "mask out of range");
+  const unsigned blocks = stride_grid(total, 256);
+  for (int t0 = 0; t0 < count; t0 += kPauliMaxTerms) {
+    PauliMultiParams p;
+    p.count = std::min(kPauliMaxTerms, count - t0);
+    for (int t = 0; t < kPauliMaxTerms; ++t) {
+      p.zmask[t] = t < p.count ? z_masks[t0 + t] : 0;
+      B2Q_REQUIRE(p.zmask[t] < total, "mask out of range");
+    }
+    const int width = 2 * p.count;
+    double* partial = reinterpret_cast<double*>(workspace(sizeof(double) * width * ((size_t)blocks + 1)));
+    if (partial == nullptr) return B2Q_ERR_CUDA;
+    if (dtype == B2Q_C64 && x_mask == 0)
+      sv_pauli_multi_partial_kernel<float, true><<<blocks, 256, 0, s>>>(
+          reinterpret_cast<const float2*>(state), total, x_mask, p, partial);
+    else if (dtype == B2Q_C64)
+      sv_pauli_multi_partial_kernel<float, false><<<blocks, 256, 0, s>>>(
+          reinterpret_cast<const float2*>(state), total, x_mask, p, partial);
+    else if (x_mask == 0)
+      sv_pauli_multi_partial_kernel<double, true><<<blocks, 256, 0, s>>>(
+          reinterpret_cast<const double2*>(state), total, x_mask, p, partial);
+    else
+      sv_pauli_multi_partial_kernel<double, false><<<blocks, 256, 0, s>>>(
+          reinterpret_cast<const double2*>(state), total, x_mask, p, partial);
+    B2Q_LAUNCH_CHECK("sv_pauli_multi_partial_kernel");
+    column_sum_kernel<<<1, 256, 0, s>>>(partial, blocks, width, partial + (size_t)blocks * width);
+    B2Q_LAUNCH_CHECK("column_sum_kernel");
+    double h[2 * kPauliMaxTerms];
+    B2Q_CUDA_CHECK(cudaMemcpyAsync(h, partial + (size_t)blocks * width, sizeof(double) * width,
+                                   cudaMemcpyDeviceToHost, s));
+    B2Q_CUDA_CHECK(cudaStreamSynchronize(s));
+    for (int t = 0; t < p.count; ++t) {
+      // P|i> = i^{nY} (-1)^{popcount(i & z)} |i ^ x>, nY = popcount(x & z)
+      const int ny = __builtin_popcountll(x_mask & p.zmask[t]) & 3;
+      double re = h[2 * t], im = h[2 * t + 1];
+      for (int k = 0; k < ny; ++k) {  // multiply by i
+        const double nr = -im, ni = re;
+        re = nr;
+        im = ni;
+      }
+      out_re_im[2 * (t0 + t)] = re;
+      out_re_im[2 * (t0 + t) + 1] = im;
+    }
+  }
   return B2Q_OK;
 }
 

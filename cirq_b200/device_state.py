@@ -406,6 +406,20 @@ class DeviceState:
         )
         return complex(out[0], out[1])
 
+    def pauli_expectations(self, x_mask: int, z_masks: Sequence[int]) -> np.ndarray:
+        """complex128[len(z_masks)]: <psi|P_t|psi> for Pauli strings sharing `x_mask`,
+        one pass over the state per 16 strings."""
+        torch = _torch()
+        z = np.ascontiguousarray(np.asarray([int(v) for v in z_masks], dtype=np.uint64))
+        out = np.empty(2 * z.size, dtype=np.float64)
+        check(
+            self._lib.b2q_sv_pauli_expectation_multi(
+                self.ptr, self.code, self.n_bits, ctypes.c_uint64(int(x_mask)), z.ctypes.data, int(z.size),
+                out.ctypes.data, _stream_ptr(torch),
+            )
+        )
+        return out[0::2] + 1j * out[1::2]
+
     def reduced_density_matrix(self, bits: Sequence[int]) -> np.ndarray:
         """complex128[2^m, 2^m]: the state with every bit not in `bits` traced out
         (bits[0] = most significant index bit of the result), m <= 5."""

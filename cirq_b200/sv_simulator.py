@@ -1248,9 +1248,13 @@ def pauli_masks(pauli_string, qubit_map, n_qubits: int, where: Sequence[int] | N
 
 
 def pauli_sum_expectation(dev: DeviceState, pauli_sum, qubit_map, where: Sequence[int] | None = None) -> complex:
-    """sum_k c_k <psi|P_k|psi>, each term one device reduction."""
+    """sum_k c_k <psi|P_k|psi>.  Terms that flip the same bits (equal X mask) share
+    ONE device reduction (b2q_sv_pauli_expectation_multi: the pair product
+    conj(psi[i ^ x]) psi[i] is formed once, each term adds its own sign), so a sum of
+    Z-type terms costs one read of the state, not one per term as in
+    sim/sparse_simulator.py:193-218."""
     n = dev.n_bits
-    total = 0.0 + 0.0j
+    groups: dict[int, list] = {}
     for ps in pauli_sum:
         if abs(complex(ps.coefficient).imag) > 0.0001:
             raise NotImplementedError(
@@ -1258,5 +1262,12 @@ def pauli_sum_expectation(dev: DeviceState, pauli_sum, qubit_map, where: Sequenc
                 f'PauliString <{ps}>. Coefficient must be real.'
             )
         x, z = pauli_masks(ps, qubit_map, n, where)
-        total += ps.coefficient * dev.pauli_expectation(x, z)
+        groups.setdefault(x, []).append((z, ps.coefficient))
+    total = 0.0 + 0.0j
+    for x, terms in groups.items():
+        if len(terms) == 1:
+            total += terms[0][1] * dev.pauli_expectation(x, terms[0][0])
+        else:
+            values = dev.pauli_expectations(x, [z for z, _ in terms])
+            total += sum(c * v for (_, c), v in zip(terms, values))
     return total

@@ -170,6 +170,15 @@ int b2q_sv_collapse(void* state, int dtype, int n_qubits, const int* bits, const
 int b2q_sv_pauli_expectation(const void* state, int dtype, int n_qubits, uint64_t x_mask,
                              uint64_t z_mask, double* out_re_im, void* stream);
 
+/* `count` Pauli strings that share one x_mask (they flip the same bits) in ONE pass
+ * over the state, 16 strings per launch: out_re_im[2t], [2t+1] = <psi| P_t |psi>.
+ * A PauliSum's terms grouped by x_mask (all Z-type terms of a cost Hamiltonian have
+ * x_mask = 0) cost one read of the state per group instead of one per term
+ * (sim/sparse_simulator.py:193-218 evaluates ops/pauli_string.py:625-655 per term). */
+int b2q_sv_pauli_expectation_multi(const void* state, int dtype, int n_qubits, uint64_t x_mask,
+                                   const uint64_t* z_masks, int count, double* out_re_im,
+                                   void* stream);
+
 /* Reduced density matrix of m <= 5 qubits, the rest traced out:
  * out[a * 2^m + b] = sum_rest psi[a, rest] conj(psi[b, rest]) as 4^m complex128
  * values on the host, bits[0] = most significant bit of a and b.  Replaces

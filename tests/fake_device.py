@@ -145,6 +145,10 @@ class OracleDeviceState:
     def pauli_expectation(self, x_mask, z_mask):
         return orc.pauli_expectation(self.array, self.n_bits, x_mask, z_mask)
 
+    def pauli_expectations(self, x_mask, z_masks):
+        return np.array([orc.pauli_expectation(self.array, self.n_bits, x_mask, int(z)) for z in z_masks],
+                        dtype=np.complex128)
+
     def kron(self, other):
         return OracleDeviceState(self.n_bits + other.n_bits, self.dtype, np.kron(self.array, other.array))
 

@@ -371,6 +371,38 @@ def test_golden_pauli_expectation(DS):
 
 
 @pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
+def test_pauli_expectations_sharing_an_x_mask(DS, dtype):
+    """b2q_sv_pauli_expectation_multi: strings with one X mask in one pass (16 per
+    launch) equal the one-string kernel, the oracle, and the golden cases."""
+    rng = np.random.RandomState(31)
+    tol = 2e-6 if dtype == np.complex64 else 1e-12
+    for n in (1, 4, 9, 14, 19):
+        state = rand_state(rng, n, dtype)
+        dev = DS.from_numpy(state)
+        for x in (0, int(rng.randint(0, 1 << n)), (1 << n) - 1):
+            for count in (1, 5, 16, 21):
+                zs = [int(v) for v in rng.randint(0, 1 << n, size=count)]
+                got = dev.pauli_expectations(x, zs)
+                assert got.shape == (count,)
+                for z, v in zip(zs, got):
+                    assert abs(v - orc.pauli_expectation(state, n, x, z)) < tol
+                    assert abs(v - dev.pauli_expectation(x, z)) < tol
+    g = load_golden('pauli_expectation.npz')
+    for c in range(int(g['num_cases'])):
+        n = int(g[f'c{c}_n'])
+        x = z = 0
+        for axis, code in enumerate(g[f'c{c}_codes']):
+            b = n - 1 - axis
+            if code in (1, 2):
+                x |= 1 << b
+            if code in (2, 3):
+                z |= 1 << b
+        if g[f'c{c}_state'].dtype == dtype:
+            vals = DS.from_numpy(g[f'c{c}_state']).pauli_expectations(x, [z, z])
+            assert abs(vals[0] - complex(g[f'c{c}_value'])) < 1e-6 and vals[0] == vals[1]
+
+
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
 def test_marginal_probs(DS, dtype):
     rng = np.random.RandomState(21)
     for n in (1, 3, 6, 7, 10, 15):
