@@ -73,51 +73,97 @@ struct PermuteTileParams {
   int tbits[kPermMaxTileBits];      // ascending index positions of the tile bits, tbits[0] = 0
   int src_local[kPermMaxTileBits];  // output local bit k = input local bit src_local[k]
   int dst_local[kPermMaxTileBits];  // input local bit j goes to output local bit dst_local[j]
+  uint32_t xmask[3];                // slot bit d + 1 = parity(position & xmask[d])
 };
 
-// XOR of higher local bits into bits 1-3 (complex64: 8-byte slots) so that neither the
-// permuted writes nor the linear reads pile up on a few banks
-__device__ __forceinline__ uint32_t perm_slot(uint32_t o) {
-  return o ^ ((((o >> 4) ^ (o >> 7) ^ (o >> 10)) & 7u) << 1);
+// Shared-memory slot of tile position o: bits 1-3 are parities chosen on the host
+// (`permute_swizzle`) so that the permuted writes of a half warp spread over 8 bank
+// pairs (lanes drive position bits dst_local[1..4]; bit 0 stays, for the 16-byte
+// linear reads) while the linear reads stay conflict free.
+__device__ __forceinline__ uint32_t perm_slot(uint32_t o, const uint32_t* xmask) {
+  uint32_t s = o & ~0xeu;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) s |= (uint32_t)(__popc(o & xmask[d]) & 1) << (d + 1);
+  return s;
 }
 
 template <typename real>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
     sv_permute_tile_kernel(typename Cplx<real>::type* __restrict__ state,
                            const __grid_constant__ PermuteTileParams p) {
   using C = typename Cplx<real>::type;
   constexpr int kVec = 16 / sizeof(C);  // amplitudes per 16-byte access
+  constexpr int kPerRound = 256 * kVec;  // local indices covered by one round of the CTA
   extern __shared__ __align__(16) unsigned char perm_smem[];
   C* tile = reinterpret_cast<C*>(perm_smem);
+  // A local index is (round << log2(kPerRound)) | (thread part): its state offset and its
+  // permuted position split the same way (sums / ORs of per-bit contributions), so the
+  // per-bit loops run once per thread and once per round, not once per element.
+  __shared__ uint64_t round_off[16];
+  __shared__ uint32_t round_o[16];
   const uint32_t tile_elems = 1u << p.tile_bits;
+  const uint32_t rounds = (tile_elems + kPerRound - 1) / kPerRound;
+  const uint32_t l_thread = threadIdx.x * kVec;
+  uint64_t off_thread = 0;
+  uint32_t o_thread = 0;
+  for (int j = 0; j < p.tile_bits; ++j) {
+    const uint32_t bit = (l_thread >> j) & 1u;
+    off_thread += (uint64_t)bit << p.tbits[j];
+    o_thread |= bit << p.dst_local[j];
+  }
+  if (threadIdx.x < rounds) {
+    const uint32_t l = threadIdx.x * kPerRound;
+    uint64_t off = 0;
+    uint32_t o = 0;
+    for (int j = 0; j < p.tile_bits; ++j) {
+      const uint32_t bit = (l >> j) & 1u;
+      off += (uint64_t)bit << p.tbits[j];
+      o |= bit << p.dst_local[j];
+    }
+    round_off[threadIdx.x] = off;
+    round_o[threadIdx.x] = o;
+  }
+  __syncthreads();
+  const bool active = l_thread < tile_elems;
+  const uint32_t second = 1u << p.dst_local[0];  // where the vector's second amplitude goes
+  constexpr int kBatch = 8;  // global loads in flight per thread
   for (uint64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-    const uint64_t base = insert_zero_bits(t, p.tbits, p.tile_bits);
-    for (uint32_t l = threadIdx.x * kVec; l < tile_elems; l += 256 * kVec) {
-      uint64_t off = 0;
-      uint32_t o = 0;
-      for (int j = (kVec == 2 ? 1 : 0); j < p.tile_bits; ++j) {
-        const uint32_t bit = (l >> j) & 1u;
-        off += (uint64_t)bit << p.tbits[j];
-        o |= bit << p.dst_local[j];
-      }
-      if constexpr (kVec == 2) {
-        const float4 v = *reinterpret_cast<const float4*>(state + base + off);
-        tile[perm_slot(o)] = make_float2(v.x, v.y);
-        tile[perm_slot(o | (1u << p.dst_local[0]))] = make_float2(v.z, v.w);
-      } else {
-        tile[perm_slot(o)] = state[base + off];
+    const uint64_t base = insert_zero_bits(t, p.tbits, p.tile_bits) + off_thread;
+    if (active) {
+      for (uint32_t r0 = 0; r0 < rounds; r0 += kBatch) {
+        if constexpr (kVec == 2) {
+          float4 v[kBatch];
+#pragma unroll
+          for (int k = 0; k < kBatch; ++k)
+            if (r0 + k < rounds) v[k] = *reinterpret_cast<const float4*>(state + base + round_off[r0 + k]);
+#pragma unroll
+          for (int k = 0; k < kBatch; ++k)
+            if (r0 + k < rounds) {
+              const uint32_t o = o_thread | round_o[r0 + k];
+              tile[perm_slot(o, p.xmask)] = make_float2(v[k].x, v[k].y);
+              tile[perm_slot(o | second, p.xmask)] = make_float2(v[k].z, v[k].w);
+            }
+        } else {
+          C v[kBatch];
+#pragma unroll
+          for (int k = 0; k < kBatch; ++k)
+            if (r0 + k < rounds) v[k] = state[base + round_off[r0 + k]];
+#pragma unroll
+          for (int k = 0; k < kBatch; ++k)
+            if (r0 + k < rounds) tile[perm_slot(o_thread | round_o[r0 + k], p.xmask)] = v[k];
+        }
       }
     }
     __syncthreads();
-    for (uint32_t l = threadIdx.x * kVec; l < tile_elems; l += 256 * kVec) {
-      uint64_t off = 0;
-      for (int j = (kVec == 2 ? 1 : 0); j < p.tile_bits; ++j)
-        off += (uint64_t)((l >> j) & 1u) << p.tbits[j];
-      if constexpr (kVec == 2) {
-        const float4 v = *reinterpret_cast<const float4*>(&tile[perm_slot(l)]);
-        *reinterpret_cast<float4*>(state + base + off) = v;
-      } else {
-        state[base + off] = tile[perm_slot(l)];
+    if (active) {
+      for (uint32_t r = 0; r < rounds; ++r) {
+        const uint32_t l = l_thread + r * kPerRound;
+        if constexpr (kVec == 2) {
+          const float4 v = *reinterpret_cast<const float4*>(&tile[perm_slot(l, p.xmask)]);
+          *reinterpret_cast<float4*>(state + base + round_off[r]) = v;
+        } else {
+          state[base + round_off[r]] = tile[perm_slot(l, p.xmask)];
+        }
       }
     }
     __syncthreads();
@@ -295,6 +341,33 @@ extern "C" int b2q_sv_permute_bits(const void* in, void* out, int dtype, int n_q
   return B2Q_OK;
 }
 
+// Swizzle of a pass: lanes 0-15 of a warp drive input local bits first..first+3
+// (first = 1 for complex64, whose lanes move 2 amplitudes; 0 for complex128), i.e. tile
+// position bits dst_local[first..first+3].  Each of the slot bits 1-3 must be driven by
+// a different one of them: bit d itself when it is among them, else one of the others
+// is XORed in.
+static void permute_swizzle(PermuteTileParams* p, int first) {
+  int lane_bits[4], nl = 0;
+  for (int j = first; j < first + 4 && j < p->tile_bits; ++j) lane_bits[nl++] = p->dst_local[j];
+  bool used[4] = {false, false, false, false};
+  for (int d = 1; d <= 3; ++d) {
+    p->xmask[d - 1] = 1u << d;
+    for (int i = 0; i < nl; ++i)
+      if (lane_bits[i] == d) used[i] = true;
+  }
+  for (int d = 1; d <= 3; ++d) {
+    bool direct = false;
+    for (int i = 0; i < nl; ++i) direct |= lane_bits[i] == d;
+    if (direct) continue;
+    for (int i = 0; i < nl; ++i)
+      if (!used[i] && lane_bits[i] >= 4) {
+        p->xmask[d - 1] |= 1u << lane_bits[i];
+        used[i] = true;
+        break;
+      }
+  }
+}
+
 // Host planner of the in-place permutation: `want[k]` = the bit whose content must end
 // at position k.  Fills passes (tile bits + local source map) until done.
 struct PermutePass {
@@ -336,6 +409,9 @@ static int plan_permute_passes(int n, const int* want, int cap, std::vector<Perm
         pos = next;
       }
     }
+    // pad with the lowest bits that stay where they are: a full tile keeps all 256
+    // threads busy and moves the state in the longest runs the permutation allows
+    for (int b = 0; b < n && (int)set.size() < cap; ++b) add(b);
     std::sort(set.begin(), set.end());
     const int T = (int)set.size();
     // sigma on the set: position k takes the content it wants when that content is
@@ -409,8 +485,9 @@ extern "C" int b2q_sv_permute_bits_inplace(void* state, int dtype, int n_qubits,
       p.dst_local[pass.src_local[i]] = i;
     }
     B2Q_REQUIRE(p.tbits[0] == 0, "tile must contain index bit 0");
+    permute_swizzle(&p, dtype == B2Q_C64 ? 1 : 0);
     const size_t smem = elem_bytes(dtype) << pass.count;
-    const unsigned grid = (unsigned)std::min<uint64_t>(p.num_tiles, 148ull * 2);
+    const unsigned grid = (unsigned)std::min<uint64_t>(p.num_tiles, 148ull * 3);
     if (dtype == B2Q_C64)
       sv_permute_tile_kernel<float><<<grid, 256, smem, s>>>(reinterpret_cast<float2*>(state), p);
     else
