@@ -977,20 +977,26 @@ __global__ void __launch_bounds__(kTileThreads, 1)
     for (int r = 0; r < kTileRounds; ++r) *reinterpret_cast<float4*>(dstp + p.rgoff[r]) = v[r];
   };
 
+  // The state offset of a tile (13 inserted zero bits: ~150 instructions) is the same for
+  // all 512 threads, so ONE lane computes it, two tiles ahead, in the shadow of block A's
+  // MMAs, and hands it over through shared memory (every thread computing it at the top
+  // of the tile cost ~850 cycles of the critical path, profiles/r2l_tile_trace_*).
+  __shared__ uint64_t s_next_base[2];
   uint64_t tile = blockIdx.x;
   uint64_t base = 0, prev_base = 0;
   bool have_prev = false;
-  uint32_t parity = 0, buf = 0;
+  uint32_t parity = 0, buf = 0, it = 0;
   if (tile < p.num_tiles) {
     base = insert_zero_bits(tile, p.tbits, kTileBits);
     prefetch(base, 0);
+    if (tid == 0 && tile + gridDim.x < p.num_tiles)
+      s_next_base[0] = insert_zero_bits(tile + gridDim.x, p.tbits, kTileBits);
   }
   while (tile < p.num_tiles) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();  // the tile is complete and visible to the whole CTA
     const uint64_t next = tile + gridDim.x;
-    uint64_t next_base = 0;
-    if (next < p.num_tiles) next_base = insert_zero_bits(next, p.tbits, kTileBits);
+    const uint64_t next_base = next < p.num_tiles ? s_next_base[it & 1u] : 0;
     unsigned char* const sbuf = tiles + (size_t)buf * kTileBufBytes;
     for (int b = 0; b < p.num_blocks; ++b) {
       const uint32_t sgb = b == 0 ? sg[0] : sg[1];
@@ -1056,6 +1062,8 @@ __global__ void __launch_bounds__(kTileThreads, 1)
             "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar_s)
             : "memory");
       }
+      if (b == 0 && tid == 32 && next + gridDim.x < p.num_tiles)  // (warp 1: not an MMA issuer)
+        s_next_base[(it + 1u) & 1u] = insert_zero_bits(next + gridDim.x, p.tbits, kTileBits);
       if (b == 0) {
         // Under block A's MMAs: the PREVIOUS tile (finished, in the other buffer) goes
         // back to HBM and that buffer is refilled with the next tile.  A thread refills
@@ -1124,6 +1132,7 @@ __global__ void __launch_bounds__(kTileThreads, 1)
     tile = next;
     base = next_base;
     buf ^= 1u;
+    ++it;
   }
   if (have_prev) copy_out(prev_base, buf ^ 1u);
   __syncthreads();
