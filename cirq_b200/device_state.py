@@ -573,6 +573,18 @@ class DeviceState:
     def permute_bits(self, src_bit: Sequence[int]) -> 'DeviceState':
         """New state with out[o] = self[i], bit k of o == bit src_bit[k] of i."""
         torch = _torch()
+        if self.n_bits >= 20:
+            # A copy followed by one or two in-place tile passes (each at the copy rate)
+            # beats the gather kernel (2.7 TB/s); the planner tells how many it takes.
+            plan = (ctypes.c_int * 27)()
+            count = ctypes.c_int(0)
+            check(self._lib.b2q_debug_permute_plan(self.code, self.n_bits, _lib.int_array(src_bit), 1, plan,
+                                                   ctypes.byref(count)))
+            if count.value <= 2:
+                out = self.copy()
+                if count.value:
+                    out.permute_bits_inplace(src_bit)
+                return out
         out = DeviceState(self.n_bits, self.dtype)
         check(
             self._lib.b2q_sv_permute_bits(

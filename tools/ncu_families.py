@@ -52,6 +52,11 @@ def calls(n, DS, torch):
     zm = (1 << 3) | (1 << 9)
     out.append(('pauli expectation X..Y..Z (sv_pauli_partial_kernel)', 2 * amp, lambda: dev.pauli_expectation(xm, zm)))
     out.append(('pauli expectation Z-only (sv_pauli_partial_kernel)', amp, lambda: dev.pauli_expectation(0, zm)))
+    zz = [(1 << int(a)) | (1 << int(b)) for a, b in rng.randint(0, n, size=(16, 2))]
+    out.append(('16 Z-type Pauli strings in one pass (sv_pauli_multi_partial_kernel<DIAG>)', amp,
+                lambda: dev.pauli_expectations(0, zz)))
+    out.append(('16 Pauli strings sharing an X mask in one pass (sv_pauli_multi_partial_kernel)', 2 * amp,
+                lambda: dev.pauli_expectations(xm, zz)))
     out.append(('reduced density matrix of 2 qubits (sv_reduced_dm_kernel)', amp,
                 lambda: dev.reduced_density_matrix([n - 3, 4])))
     out.append(('reduced density matrix of 5 qubits (sv_reduced_dm_kernel)', amp,
