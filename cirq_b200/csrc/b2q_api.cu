@@ -125,3 +125,32 @@ extern "C" int b2q_host_left_apply(double* block, int u, const double* matrix, c
   }
   return B2Q_OK;
 }
+
+// out <- M_{n-1} ... M_1 M_0 on a space of u wires: `out` (2^u x 2^u complex128, row-major)
+// starts as the identity and is left-multiplied by every member in order; member m is a
+// 2^k x 2^k matrix (ks[m] wires, consecutive in `matrices`) on the row-index bits
+// bitpos[...] (consecutive in `bitpos`, first wire = most significant index bit).  The
+// gate fuser keeps a block as the LIST of its member gates while it schedules and asks
+// for the product once, when the block is emitted (one call per block instead of two
+// to three per gate).
+extern "C" int b2q_host_compose(double* out, int u, int num_members, const int* ks,
+                                const int* bitpos, const double* matrices) {
+  B2Q_REQUIRE(out != nullptr && ks != nullptr && bitpos != nullptr && matrices != nullptr, "null argument");
+  B2Q_REQUIRE(u >= 1 && u <= 6 && num_members >= 1, "bad sizes u=%d members=%d", u, num_members);
+  const int dim = 1 << u;
+  for (int r = 0; r < dim; ++r)
+    for (int c = 0; c < dim; ++c) {
+      out[2 * ((size_t)r * dim + c)] = r == c ? 1.0 : 0.0;
+      out[2 * ((size_t)r * dim + c) + 1] = 0.0;
+    }
+  size_t boff = 0, moff = 0;
+  for (int m = 0; m < num_members; ++m) {
+    const int k = ks[m];
+    B2Q_REQUIRE(k >= 1 && k <= u, "member %d has %d wires", m, k);
+    const int rc = b2q_host_left_apply(out, u, matrices + moff, bitpos + boff, k);
+    if (rc != B2Q_OK) return rc;
+    boff += k;
+    moff += (size_t)2 << (2 * k);
+  }
+  return B2Q_OK;
+}

@@ -111,19 +111,64 @@ def apply_to_block(block: np.ndarray, union: Sequence[int], matrix: np.ndarray,
     return res.reshape(1 << u, 1 << u)
 
 
-class _Block:
-    __slots__ = ('wires', 'matrix', 'seq', 'alive', 'count', 'diag')
+def _materialize(members, union) -> np.ndarray:
+    """Product of `members` = [(matrix, wires), ...] (applied in order) on the wires
+    `union`: ONE native call (b2q_host_compose) for blocks of up to 6 wires."""
+    u = len(union)
+    if len(members) == 1 and tuple(members[0][1]) == tuple(union):
+        return np.asarray(members[0][0], dtype=np.complex128)
+    lib = _native()
+    if lib and u <= 6 and hasattr(lib, 'b2q_host_compose'):
+        top = u - 1
+        ks = (ctypes.c_int * len(members))(*[len(w) for _, w in members])
+        pos = [top - union.index(x) for _, w in members for x in w]
+        bitpos = (ctypes.c_int * len(pos))(*pos)
+        flat = np.concatenate([np.ascontiguousarray(m, dtype=np.complex128).reshape(-1) for m, _ in members])
+        out = np.empty((1 << u, 1 << u), dtype=np.complex128)
+        if lib.b2q_host_compose(out.ctypes.data, u, len(members), ks, bitpos, flat.ctypes.data) == 0:
+            return out
+    total = None
+    for m, w in members:
+        total = expand_matrix(m, w, union) if total is None else apply_to_block(total, union, m, w)
+    return total
 
-    def __init__(self, wires, matrix, seq, count=1, diag=False):
+
+class _Block:
+    """A fused block.  While the scheduler is still growing it, a dense block is
+    only the LIST of its member gates (`members`); the 2^k x 2^k product is formed
+    once, when somebody reads `matrix` (emission), instead of after every gate."""
+
+    __slots__ = ('wires', '_matrix', 'members', 'seq', 'alive', 'count', 'diag')
+
+    def __init__(self, wires, matrix, seq, count=1, diag=False, members=None):
         self.wires = tuple(wires)
-        self.matrix = matrix  # 2^k x 2^k, or the 2^k diagonal entries when `diag`
+        self._matrix = matrix  # 2^k x 2^k, or the 2^k diagonal entries when `diag`; None = lazy
+        self.members = members  # [(matrix, wires), ...] in application order, when lazy
         self.seq = seq
         self.alive = True
         self.count = count
         self.diag = diag
 
+    @property
+    def matrix(self):
+        if self._matrix is None:
+            self._matrix = _materialize(self.members, self.wires)
+            self.members = None
+        return self._matrix
+
+    @matrix.setter
+    def matrix(self, value):
+        self._matrix = value
+        self.members = None
+
     def dense(self) -> np.ndarray:
         return np.diag(self.matrix) if self.diag else self.matrix
+
+    def parts(self) -> list:
+        """[(matrix, wires), ...] whose ordered product is this block."""
+        if self._matrix is None:
+            return self.members
+        return [(self.dense(), self.wires)]
 
 
 _SWAP = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
@@ -131,7 +176,13 @@ _SWAP = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype
 
 def is_diagonal(matrix: np.ndarray) -> bool:
     m = np.asarray(matrix)
-    return m.ndim == 2 and not np.count_nonzero(m - np.diag(np.diagonal(m)))
+    # (every non-zero entry sits on the diagonal)
+    return m.ndim == 2 and np.count_nonzero(m) == np.count_nonzero(np.diagonal(m))
+
+
+def _is_swap(m: np.ndarray) -> bool:
+    """m == SWAP exactly (4 x 4); most gates fail the first comparison."""
+    return bool(m[1, 2] == 1 and m[2, 1] == 1 and m[0, 0] == 1 and m[3, 3] == 1 and np.count_nonzero(m) == 4)
 
 
 def expand_diagonal(diag: np.ndarray, wires: Sequence[int], out_wires: Sequence[int]) -> np.ndarray:
@@ -211,9 +262,10 @@ class GateFuser:
     def add(self, matrix: np.ndarray, wires: Sequence[int]) -> None:
         wires = tuple(int(w) for w in wires)
         k = len(wires)
-        matrix = np.asarray(matrix, dtype=np.complex128).reshape(1 << k, 1 << k)
+        if not (type(matrix) is np.ndarray and matrix.dtype == np.complex128 and matrix.shape == (1 << k, 1 << k)):
+            matrix = np.asarray(matrix, dtype=np.complex128).reshape(1 << k, 1 << k)
         if self.relabel_swaps:
-            if k == 2 and np.array_equal(matrix, _SWAP):
+            if k == 2 and _is_swap(matrix):
                 a, b = wires
                 self._map[a], self._map[b] = self._map.get(b, b), self._map.get(a, a)
                 return
@@ -308,33 +360,31 @@ class GateFuser:
             if last is None or last.seq < best.seq:
                 self._last[w] = best
 
-    def _compose(self, blocks: Sequence[_Block], matrix, wires, union) -> tuple[np.ndarray, int]:
-        """G . (product of the given blocks, seq order) on `union`."""
-        total = None
+    def _compose(self, blocks: Sequence[_Block], matrix, wires, union) -> tuple[list, int]:
+        """Members of G . (product of the given blocks, seq order): the product itself
+        is formed when the block is emitted (`_Block.matrix`)."""
+        members: list = []
         count = 1
         for b in sorted(blocks, key=lambda b: b.seq):
-            if total is None:
-                total = expand_matrix(b.dense(), b.wires, union)
-            else:
-                total = apply_to_block(total, union, b.dense(), b.wires)
+            members.extend(b.parts())
             count += b.count
-        if total is None:
-            return expand_matrix(matrix, wires, union), count
-        return apply_to_block(total, union, matrix, wires), count
+        members.append((matrix, tuple(wires)))
+        return members, count
 
     def _merge_at_end(self, blocks, matrix, wires, union) -> None:
-        m, count = self._compose(blocks, matrix, wires, union)
+        members, count = self._compose(blocks, matrix, wires, union)
         for b in blocks:
             b.alive = False
-        self._append(_Block(union, m, self._new_seq(), count))
+        self._append(_Block(union, None, self._new_seq(), count, members=members))
 
     def _merge_into(self, target: _Block, extra, matrix, wires, union) -> None:
-        m, count = self._compose([target] + list(extra), matrix, wires, union)
+        members, count = self._compose([target] + list(extra), matrix, wires, union)
         for b in extra:
             b.alive = False
         was_diag = target.diag
         target.wires = union
-        target.matrix = m
+        target._matrix = None
+        target.members = members
         target.count = count
         target.diag = False
         # Only the wires that gained an operation move their frontier here; the

@@ -355,6 +355,13 @@ int b2q_bsv_collapse(void* state, int dtype, int n_qubits, int batch_bits, uint6
  * obtains from protocols.unitary(CircuitOperation)); no GPU involved. */
 int b2q_host_left_apply(double* block, int u, const double* matrix, const int* bitpos, int k);
 
+/* out <- M_{n-1} ... M_1 M_0: the product of `num_members` small matrices, each embedded
+ * on its wires of a u-wire space (u <= 6; ks / bitpos / matrices_c128 consecutive per
+ * member, conventions of b2q_host_left_apply), starting from the identity.  One call per
+ * emitted block of the gate fuser; no GPU involved. */
+int b2q_host_compose(double* out, int u, int num_members, const int* ks, const int* bitpos,
+                     const double* matrices_c128);
+
 /* ---- tuning knobs and host-only test hooks (not needed by a binding) -------- */
 
 /* How target bits inside the 512-byte warp zone are handled by the register
