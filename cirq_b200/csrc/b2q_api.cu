@@ -154,3 +154,36 @@ extern "C" int b2q_host_compose(double* out, int u, int num_members, const int* 
   }
   return B2Q_OK;
 }
+
+// out[i] = prod_m diag_m[bits of i at member m's wires]: the table of a diagonal block
+// that the fuser kept as a list of diagonal gates (u <= 16 wires; member m has ks[m]
+// wires at index bits bitpos[...], first wire = most significant bit of its own index).
+extern "C" int b2q_host_compose_diag(double* out, int u, int num_members, const int* ks,
+                                     const int* bitpos, const double* diags) {
+  B2Q_REQUIRE(out != nullptr && ks != nullptr && bitpos != nullptr && diags != nullptr, "null argument");
+  B2Q_REQUIRE(u >= 1 && u <= 16 && num_members >= 1, "bad sizes u=%d members=%d", u, num_members);
+  const int dim = 1 << u;
+  for (int i = 0; i < dim; ++i) {
+    out[2 * i] = 1.0;
+    out[2 * i + 1] = 0.0;
+  }
+  size_t boff = 0, doff = 0;
+  for (int m = 0; m < num_members; ++m) {
+    const int k = ks[m];
+    B2Q_REQUIRE(k >= 1 && k <= u, "member %d has %d wires", m, k);
+    const int* pos = bitpos + boff;
+    for (int q = 0; q < k; ++q) B2Q_REQUIRE(pos[q] >= 0 && pos[q] < u, "bit position out of range");
+    const double* d = diags + doff;
+    for (int i = 0; i < dim; ++i) {
+      int sub = 0;
+      for (int q = 0; q < k; ++q) sub = (sub << 1) | ((i >> pos[q]) & 1);
+      const double dr = d[2 * sub], di = d[2 * sub + 1];
+      const double xr = out[2 * i], xi = out[2 * i + 1];
+      out[2 * i] = xr * dr - xi * di;
+      out[2 * i + 1] = xr * di + xi * dr;
+    }
+    boff += k;
+    doff += (size_t)2 << k;
+  }
+  return B2Q_OK;
+}

@@ -133,6 +133,26 @@ def _materialize(members, union) -> np.ndarray:
     return total
 
 
+def _materialize_diag(members, union) -> np.ndarray:
+    """Table of a diagonal block from its member gates [(diagonal entries, wires), ...]."""
+    u = len(union)
+    lib = _native()
+    if lib and u <= 16 and hasattr(lib, 'b2q_host_compose_diag'):
+        top = u - 1
+        ks = (ctypes.c_int * len(members))(*[len(w) for _, w in members])
+        pos = [top - union.index(x) for _, w in members for x in w]
+        bitpos = (ctypes.c_int * len(pos))(*pos)
+        flat = np.concatenate([np.ascontiguousarray(d, dtype=np.complex128).reshape(-1) for d, _ in members])
+        out = np.empty(1 << u, dtype=np.complex128)
+        if lib.b2q_host_compose_diag(out.ctypes.data, u, len(members), ks, bitpos, flat.ctypes.data) == 0:
+            return out
+    total = None
+    for d, w in members:
+        e = expand_diagonal(d, w, union)
+        total = e if total is None else total * e
+    return total
+
+
 class _Block:
     """A fused block.  While the scheduler is still growing it, a dense block is
     only the LIST of its member gates (`members`); the 2^k x 2^k product is formed
@@ -152,7 +172,7 @@ class _Block:
     @property
     def matrix(self):
         if self._matrix is None:
-            self._matrix = _materialize(self.members, self.wires)
+            self._matrix = (_materialize_diag if self.diag else _materialize)(self.members, self.wires)
             self.members = None
         return self._matrix
 
@@ -166,7 +186,7 @@ class _Block:
 
     def parts(self) -> list:
         """[(matrix, wires), ...] whose ordered product is this block."""
-        if self._matrix is None:
+        if self._matrix is None and not self.diag:
             return self.members
         return [(self.dense(), self.wires)]
 
@@ -347,13 +367,14 @@ class GateFuser:
             if overlap > best_overlap and len(set(b.wires) | set(wires)) <= self.diag_max:
                 best, best_overlap = b, overlap
         if best is None:
-            self._append(_Block(tuple(sorted(wires, reverse=True)),
-                                expand_diagonal(diag, wires, tuple(sorted(wires, reverse=True))),
-                                self._new_seq(), diag=True))
+            self._append(_Block(tuple(sorted(wires, reverse=True)), None, self._new_seq(), diag=True,
+                                members=[(diag, tuple(wires))]))
             return
-        union = self._union([best.wires, wires])
-        best.matrix = expand_diagonal(best.matrix, best.wires, union) * expand_diagonal(diag, wires, union)
-        best.wires = union
+        # (the table over the union is formed once, when the block is emitted)
+        members = best.members if best._matrix is None else [(best._matrix, best.wires)]
+        best.members = members + [(diag, tuple(wires))]
+        best._matrix = None
+        best.wires = self._union([best.wires, wires])
         best.count += 1
         for w in wires:
             last = self._last.get(w)

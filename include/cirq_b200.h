@@ -362,6 +362,11 @@ int b2q_host_left_apply(double* block, int u, const double* matrix, const int* b
 int b2q_host_compose(double* out, int u, int num_members, const int* ks, const int* bitpos,
                      const double* matrices_c128);
 
+/* out[i] = product over the members of diag_m[bits of i at member m's wires]: the table of
+ * a diagonal block (u <= 16 wires) from the list of its diagonal gates; host only. */
+int b2q_host_compose_diag(double* out, int u, int num_members, const int* ks, const int* bitpos,
+                          const double* diags_c128);
+
 /* ---- tuning knobs and host-only test hooks (not needed by a binding) -------- */
 
 /* How target bits inside the 512-byte warp zone are handled by the register

@@ -245,3 +245,24 @@ def test_plan_replay_equals_direct_execution():
     np.testing.assert_allclose(got[src], run(n, gates), atol=1e-10)
     # replaying twice gives the same state (plans are reusable)
     np.testing.assert_array_equal(replay_plan(plan, OracleDeviceState).to_numpy(), got)
+
+
+def test_native_block_composition_matches_numpy(monkeypatch):
+    """b2q_host_compose / b2q_host_compose_diag (one native call per emitted block)
+    against the numpy composition the fuser falls back to without the library."""
+    from cirq_b200 import fusion
+
+    if not fusion._native():
+        pytest.skip('C-ABI library not built')
+    rng = np.random.RandomState(11)
+    union = (9, 7, 4, 3, 1, 0)
+    dense = []
+    for wires in ((7, 0), (3,), (9, 4, 1), (0, 7), (4, 9)):
+        d = 1 << len(wires)
+        dense.append((rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d)), wires))
+    diags = [(np.exp(1j * rng.standard_normal(1 << len(w))), w) for w in ((1, 9), (0,), (7, 3, 4), (9, 1))]
+    native_dense = fusion._materialize(dense, union)
+    native_diag = fusion._materialize_diag(diags, union)
+    monkeypatch.setattr(fusion, '_NATIVE', False)
+    np.testing.assert_allclose(native_dense, fusion._materialize(dense, union), atol=1e-12)
+    np.testing.assert_allclose(native_diag, fusion._materialize_diag(diags, union), atol=1e-13)
