@@ -642,11 +642,39 @@ def cached_unitary(action: Any):
         except TypeError:  # unhashable gate
             key = None
     u = protocols.unitary(action, None)
+    if u is not None and gate is not None and u.shape[0] <= 8 and _only_applies_in_place(gate):
+        u = _unitary_by_columns(action, u.shape[0].bit_length() - 1, u)
     if key is not None and not protocols.is_parameterized(gate):
         if len(_UNITARY_CACHE) >= _UNITARY_CACHE_MAX:
             _UNITARY_CACHE.clear()
         _UNITARY_CACHE[key] = False if u is None else u
     return u
+
+
+def _only_applies_in_place(gate) -> bool:
+    """A gate whose only description is an ``_apply_unitary_`` method."""
+    cls = type(gate)
+    return getattr(cls, '_apply_unitary_', None) is not None and getattr(cls, '_unitary_', None) is None
+
+
+def _unitary_by_columns(action: Any, k: int, default: np.ndarray) -> np.ndarray:
+    """Matrix of a gate that only has ``_apply_unitary_``, one basis state at a time.
+    ``protocols.unitary`` hands such a gate the whole identity tensor
+    (protocols/unitary_protocol.py:161-179), which an ad-hoc method written for a
+    STATE (e.g. one that swaps ``target_tensor[0]`` and ``[1]`` and so needs them
+    to be scalars — sparse_simulator_test.py:745-754) may not survive; the
+    reference calls it on the state itself, so here it sees 2^k states."""
+    dim = 1 << k
+    cols = np.empty((dim, dim), dtype=np.complex128)
+    for j in range(dim):
+        basis = np.zeros((2,) * k, dtype=np.complex128)
+        basis.flat[j] = 1
+        out = protocols.apply_unitary(
+            action, protocols.ApplyUnitaryArgs(basis, np.empty_like(basis), range(k)), default=None)
+        if out is None:
+            return default
+        cols[:, j] = out.reshape(-1)
+    return cols
 
 
 _MIXTURE_CACHE: dict = {}
