@@ -26,7 +26,10 @@ e2e       the same metric through the public API a Cirq user calls
           (B200Simulator.run / compute_amplitudes, B200DensityMatrixSimulator
           .run_sweep) on the cirq.Circuit: host scheduling, uploads and the
           device->host copy of the result inside the timed region.  `first_call_ms`
-          is the cold call (per-gate unitary cache empty), `ms_per_step` the warm one.
+          is the cold call (per-gate unitary cache empty), `second_call_ms` the call
+          that records the circuit's schedule (cirq_b200/plan_cache.py), `ms_per_step`
+          the calls after it (schedule replayed; every gate pass still runs on the
+          GPU), `ms_per_step_without_schedule_cache` the same with plan_cache=False.
 roofline  dominant in-step kernel: algorithmic bytes per launch
           (2 * sizeof(complex) * 2^bits) / mean launch duration measured with CUDA
           events around the gate passes, vs the measured copy peak.
@@ -406,20 +409,26 @@ def _roofline(per_kernel, record_steps, bytes_per_pass, n_bits, peak_gbs, peak_s
             'kernels': breakdown}, count // record_steps
 
 
-def _time_e2e(fn, steps):
+def _time_e2e(fn, steps, settle=0):
+    """(seconds per call over `steps` calls, seconds of the first call, seconds of each
+    of the `settle` untimed calls in between)."""
     import torch
+
+    def once():
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
 
     torch.cuda.empty_cache()
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    fn()
-    torch.cuda.synchronize()
-    first = time.perf_counter() - t0
+    first = once()
+    settled = [once() for _ in range(settle)]
     t0 = time.perf_counter()
     for _ in range(steps):
         fn()
     torch.cuda.synchronize()
-    return (time.perf_counter() - t0) / steps, first
+    return (time.perf_counter() - t0) / steps, first, settled
 
 
 def measure_sv(name, steps, warmup, args, local_rank=0):
@@ -517,8 +526,8 @@ def measure_sv(name, steps, warmup, args, local_rank=0):
         circuit = circuit + cirq.Circuit(cirq.measure(*wl['qubits'], key='m'))
     e2e_steps = max(1, min(steps, 3))
 
-    def e2e_step():
-        sim = cirq_b200.B200Simulator(dtype=dtype, seed=0, max_fused_qubits=args.max_fused)
+    def e2e_step(plan_cache=True):
+        sim = cirq_b200.B200Simulator(dtype=dtype, seed=0, max_fused_qubits=args.max_fused, plan_cache=plan_cache)
         if reps:
             res = sim.run(circuit, repetitions=reps)
             return res.measurements['m'].shape
@@ -526,9 +535,20 @@ def measure_sv(name, steps, warmup, args, local_rank=0):
         # large to download (SimulatesAmplitudes, sim/simulator.py:120-182)
         return sim.compute_amplitudes(circuit, [0, 1], qubit_order=wl['qubits'])
 
-    dt, first = _time_e2e(e2e_step, e2e_steps)
+    # call 1 is cold (per-gate unitary cache empty), call 2 records the circuit's schedule
+    # (cirq_b200/plan_cache.py: the second sighting of a circuit), the timed calls replay
+    # it; the same calls with the schedule cache off are timed beside them
+    from cirq_b200 import plan_cache as _pc
+
+    _pc.CACHE.clear()
+    dt, first, settled = _time_e2e(e2e_step, e2e_steps, settle=1)
+    cache_hits = _pc.CACHE.hits
+    _pc.CACHE.clear()
+    dt_nocache, _, _ = _time_e2e(lambda: e2e_step(plan_cache=False), max(1, min(e2e_steps, 2)))
     mat_bytes = int(sum(16 * np.size(m) for m, _ in _flat_blocks(blocks)))
     e2e = {'value': unit_gates / dt, 'unit': 'gates/s', 'ms_per_step': dt * 1e3, 'first_call_ms': first * 1e3,
+           'second_call_ms': settled[0] * 1e3, 'schedule_cache_hits': cache_hits,
+           'ms_per_step_without_schedule_cache': dt_nocache * 1e3,
            'h2d_bytes_per_step': int(8 * reps + mat_bytes),
            'd2h_bytes_per_step': int(reps * n if reps else 32),
            'api': 'cirq_b200.B200Simulator(seed=0).run(circuit, repetitions)' if reps
@@ -663,7 +683,7 @@ def measure_dm(name, steps, warmup, args, local_rank=0):
         res = sim.run_sweep(circuit, resolvers[:e2e_res], repetitions=reps)
         return [r.measurements['m'].shape for r in res]
 
-    dt, first = _time_e2e(e2e_step, 1)
+    dt, first, _ = _time_e2e(e2e_step, 1)
     dt /= e2e_res
     mat_bytes = int(sum(16 * np.size(m) for m, _ in _flat_blocks(plans[0])))
     e2e = {'value': unit_gates / dt, 'unit': 'gates/s', 'ms_per_step': dt * 1e3,

@@ -181,6 +181,19 @@ class B200StateVector(qis.QuantumStateRepresentation):
                 where = self._where if self._where is not None else list(range(self._n))
                 self._where = [moved.get(w, w) for w in where]
 
+    def detach_pending(self) -> list:
+        """The blocks `flush(restore=False)` would launch, taken off the queue WITHOUT
+        launching them (the bit map is updated as if they had run).  For the plan
+        cache (cirq_b200/plan_cache.py), which hands them to the replayed state."""
+        blocks = self._held + self._fuser.blocks(restore=False)
+        self._fuser.clear()
+        self._held = []
+        moved = self._fuser.take_permutation()
+        if moved:
+            where = self._where if self._where is not None else list(range(self._n))
+            self._where = [moved.get(w, w) for w in where]
+        return blocks
+
     def _displaced_bits(self) -> int:
         """Index bits not holding their own logical bit once the queue is applied
         (kept bit map composed with the fuser's pending SWAP relabelling)."""
@@ -954,6 +967,10 @@ class B200Simulator(
             its seeded results.  N > 1 advances up to N repetitions together as
             one device array (``cirq_b200.trajectories``): same distribution of
             results, random numbers consumed in a different order.
+        plan_cache: True (default) keeps the device schedule of a circuit's unitary
+            prefix from the second time the same circuit object is executed on
+            (``cirq_b200.plan_cache``): later ``run`` / ``simulate`` calls skip the
+            per-operation Python of the driver loop and the gate fuser.
     """
 
     def __init__(
@@ -966,6 +983,7 @@ class B200Simulator(
         max_fused_qubits: int | None = None,
         trajectory_batch: int = 0,
         sweep_batch: bool = False,
+        plan_cache: bool = True,
     ):
         if np.dtype(dtype).kind != 'c':
             raise ValueError(f'dtype must be a complex type but was {dtype}')
@@ -978,6 +996,7 @@ class B200Simulator(
         self._max_fused = None if max_fused_qubits is None else int(max_fused_qubits)
         self._trajectory_batch = int(trajectory_batch)
         self._sweep_batch = bool(sweep_batch)
+        self._plan_cache = bool(plan_cache)
         self.last_run_info: dict = {}
 
     def _state_from_device(self, dev: DeviceState, qubits):
@@ -986,6 +1005,129 @@ class B200Simulator(
             qubits=qubits, prng=self._prng, dtype=self._dtype, max_fused_qubits=self._max_fused,
             initial_state=B200StateVector(dev, len(qubits), self._max_fused),
         )
+
+    # ---- per-circuit schedule cache (cirq_b200/plan_cache.py) ------------------------------
+
+    def _lookup_plan(self, circuit, qubit_order=ops.QubitOrder.DEFAULT):
+        """The cached schedule of `circuit`'s unitary prefix from |0...0>, built the
+        second time the circuit is seen; None when there is none (first sighting,
+        noise model, parameterized or qudit circuit, custom QubitOrder object)."""
+        from cirq import devices
+        from cirq_b200 import plan_cache
+
+        if not self._plan_cache or self.noise is not devices.NO_NOISE or not plan_cache.enabled():
+            return None
+        if qubit_order is ops.QubitOrder.DEFAULT:
+            order_key: Any = None
+        elif isinstance(qubit_order, (list, tuple)):
+            order_key = tuple(qubit_order)
+        else:
+            return None
+        moments = circuit.moments
+        if not moments:
+            return None
+        try:
+            key = (tuple(map(id, moments)), order_key, np.dtype(self._dtype).str, self._max_fused,
+                   self._split_untangled_states, DeviceState)
+            found, plan = plan_cache.CACHE.get(key)
+        except TypeError:  # unhashable entries in qubit_order
+            return None
+        if found:
+            return plan
+        if not plan_cache.CACHE.seen_before(key):
+            return None
+        plan = self._record_prefix(circuit, qubit_order)
+        plan_cache.CACHE.put(key, plan)
+        return plan
+
+    def _record_prefix(self, circuit, qubit_order):
+        """Dry run of the longest all-unitary prefix of `circuit` against a recording
+        device state: the product-state logic and the fuser run as in a live call, the
+        device operations are written down (no GPU work).  None if it cannot be cached."""
+        from cirq_b200 import plan_cache
+
+        tagged = ops.TaggedOperation
+        first = 0
+        for moment in circuit.moments:
+            ok = True
+            for op in moment.operations:
+                base = op.untagged if type(op) is tagged else op
+                # (wider operations end the prefix: asking a 40-qubit measurement for its
+                # unitary would build a 2^40 x 2^40 identity)
+                if (type(base) not in PLAIN_GATE_OPERATIONS or len(base.qubits) > 5
+                        or cached_unitary(base) is None):
+                    ok = False
+                    break
+            if not ok:
+                break
+            first += 1
+        if first == 0 or protocols.is_parameterized(circuit):
+            return None
+        qubits = ops.QubitOrder.as_qubit_order(qubit_order).order_for(circuit.all_qubits())
+        if not qubits or any(q.dimension != 2 for q in qubits):
+            return None
+        rec = plan_cache.recorder_for(DeviceState)
+        classical_data = value.ClassicalDataDictionaryStore()
+        prng = np.random.RandomState(0)  # (a unitary prefix draws nothing)
+
+        def fresh(qs):
+            return B200StateVectorSimulationState(
+                qubits=qs, prng=prng, classical_data=classical_data, dtype=self._dtype,
+                max_fused_qubits=self._max_fused,
+                initial_state=B200StateVector(rec.basis(len(qs), self._dtype, 0), len(qs), self._max_fused),
+            )
+
+        if self._split_untangled_states:
+            # as create_product_state for initial_state=0 (sim/simulator_base.py:322-352)
+            args_map: dict = {q: fresh([q]) for q in reversed(qubits)}
+            args_map[None] = fresh([])
+            state: Any = B200ProductState(args_map, qubits, True, classical_data=classical_data)
+        else:
+            state = fresh(list(qubits))
+        try:
+            for _ in self._core_iterator(circuit=circuit[:first], sim_state=state):
+                pass
+            subs = list(dict.fromkeys(state.sim_states.values())) if self._split_untangled_states else [state]
+            components = []
+            for sub in subs:
+                sv = sub._state
+                blocks = sv.detach_pending()
+                where = list(sv._where) if sv._where is not None else None
+                components.append((sv._dev.ident, tuple(sub.qubits), where, blocks))
+        except plan_cache.Untraceable:
+            return None
+        owner = None
+        if self._split_untangled_states:
+            index = {id(sub): i for i, sub in enumerate(subs)}
+            owner = [(q, index[id(sub)]) for q, sub in state.sim_states.items()]
+        rest = circuit.moments[first:]
+        plan = plan_cache.PrefixPlan(tuple(circuit.moments), first, tuple(qubits), rec.ops, components, owner)
+        # (for `run`: is what follows the prefix nothing but measurements?)
+        plan.measure_tail = bool(rest) and all(
+            isinstance(op.gate, ops.MeasurementGate) for m in rest for op in m.operations)
+        return plan
+
+    def _state_from_plan(self, plan):
+        """Replays a cached prefix on the GPU and rebuilds the simulation state the live
+        loop would have left behind."""
+        from cirq_b200 import plan_cache
+
+        live, passes = plan_cache.replay(plan, self._dtype, DeviceState)
+        classical_data = value.ClassicalDataDictionaryStore()
+        subs = []
+        for ident, qs, where, blocks in plan.components:
+            sv = B200StateVector(live[ident], len(qs), self._max_fused)
+            sv._where = list(where) if where is not None else None
+            sv._held = list(blocks)  # launched (paired) with whatever comes next, or by flush()
+            sv.passes = passes[ident]
+            subs.append(B200StateVectorSimulationState(
+                qubits=qs, prng=self._prng, classical_data=classical_data, dtype=self._dtype,
+                max_fused_qubits=self._max_fused, initial_state=sv,
+            ))
+        if plan.owner is None:
+            return subs[0]
+        return B200ProductState({q: subs[i] for q, i in plan.owner}, plan.qubits, True,
+                                classical_data=classical_data)
 
     def simulate_sweep_iter(self, program, params, qubit_order=ops.QubitOrder.DEFAULT, initial_state=None):
         """``SimulatorBase.simulate_sweep_iter`` (sim/simulator_base.py:277-320); with
@@ -1007,6 +1149,20 @@ class B200Simulator(
             # (sim/simulator_base.py:304-320: ~40 us of Python per operation before
             # the first gate reaches the GPU) is skipped — same result (with a noise
             # model the split decides where noise lands, so it is kept)
+            if (initial_state is None or (type(initial_state) is int and initial_state == 0)) and not resolvers[0]:
+                plan = self._lookup_plan(program, qubit_order)
+                if plan is not None:
+                    # the unitary prefix replayed from the schedule cache, the rest of
+                    # the circuit as in simulate_sweep_iter (sim/simulator.py:586-605)
+                    sim_state = self._state_from_plan(plan)
+                    measurements: dict = {}
+                    if plan.first < len(program):
+                        for step in self._core_iterator(circuit=program[plan.first:], sim_state=sim_state):
+                            for k, v in step.measurements.items():
+                                measurements[k] = np.array(v, dtype=np.uint8)
+                    yield self._create_simulator_trial_result(
+                        params=resolvers[0], measurements=measurements, final_simulator_state=sim_state)
+                    return
             yield from simulator.SimulatesIntermediateState.simulate_sweep_iter(
                 self, program, resolvers, qubit_order, initial_state)
             return
@@ -1137,6 +1293,20 @@ class B200Simulator(
             return None
         if param_resolver and protocols.is_parameterized(circuit):
             return None  # sweeps over symbols: the generic path resolves them
+        plan = self._lookup_plan(circuit)
+        if plan is not None and plan.measure_tail:
+            # seen before: the unitary prefix is replayed from the schedule cache
+            sim_state = self._state_from_plan(plan)
+            suffix = circuit[plan.first:]
+            step_result = None
+            for step_result in self._core_iterator(
+                circuit=suffix, sim_state=sim_state, all_measurements_are_terminal=True
+            ):
+                pass
+            self.last_run_info = {'path': 'unitary prefix + sampling', 'plan_cache': 'hit'}
+            return step_result.sample_measurement_ops(
+                list(suffix.all_operations()), repetitions, seed=self._prng, _allow_repeated=True
+            )
         first = None
         for i, moment in enumerate(circuit):
             measuring = [isinstance(op.gate, ops.MeasurementGate) for op in moment]
@@ -1249,8 +1419,8 @@ class B200Simulator(
             if batched is not None:
                 yield from batched
                 return
-        qubit_order = ops.QubitOrder.as_qubit_order(qubit_order)
-        qmap = {q: i for i, q in enumerate(qubit_order.order_for(program.all_qubits()))}
+        order = ops.QubitOrder.as_qubit_order(qubit_order)
+        qmap = {q: i for i, q in enumerate(order.order_for(program.all_qubits()))}
         for result in self.simulate_sweep_iter(
             program, params, qubit_order=qubit_order, initial_state=initial_state
         ):
