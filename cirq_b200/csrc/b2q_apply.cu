@@ -782,6 +782,7 @@ int apply_generic(void* state, int n, const int* sorted, int K, const real* mat,
                      "a %d-qubit gate needs the out-of-place kernel: pass a scratch buffer", K);
   const size_t dim = (size_t)1 << K;
   C* dmat = nullptr;
+  keep_async_pool_memory();
   B2Q_CUDA_CHECK(cudaMallocAsync((void**)&dmat, sizeof(C) * dim * dim, stream));
   B2Q_CUDA_CHECK(
       cudaMemcpyAsync(dmat, mat, sizeof(C) * dim * dim, cudaMemcpyHostToDevice, stream));
@@ -1037,6 +1038,7 @@ extern "C" int b2q_sv_apply_diagonal(void* state, int dtype, int n_qubits,
     }
   }
   void* ddiag = nullptr;
+  keep_async_pool_memory();
   if (dtype == B2Q_C64) {
     std::vector<float> h(2 * dim);
     for (size_t i = 0; i < 2 * dim; ++i) h[i] = (float)diag_c128[i];

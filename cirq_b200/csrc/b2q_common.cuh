@@ -42,6 +42,23 @@ inline int set_error(int code, const char* fmt, ...) {
     }                                                                                     \
   } while (0)
 
+// Small stream-ordered temporaries (gate tables uploaded next to the kernel that reads
+// them) come from the device's default memory pool.  By default the pool hands its memory
+// back to the driver at every synchronisation, so each later cudaMallocAsync maps fresh
+// pages — cheap on an empty GPU, but measured at up to 0.6 s per call next to a 128 GiB
+// state (profiles/README.md r2z).  Keep what the pool has.
+inline void keep_async_pool_memory() {
+  static bool done[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done[dev] = true;
+}
+
 #define B2Q_LAUNCH_CHECK(name)                                                            \
   do {                                                                                    \
     b2q::g_launch_count.fetch_add(1, std::memory_order_relaxed);                          \

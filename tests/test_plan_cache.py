@@ -221,3 +221,19 @@ def test_recorder_refuses_what_a_schedule_cannot_hold():
             getattr(c, reader)
     # a second recorder starts from an empty list
     assert plan_cache.recorder_for(OracleDeviceState).ops == []
+
+
+def test_differential_fuzz_with_every_circuit_cached(cirq, SV, monkeypatch):
+    """The simulator fuzz tests (random circuits, sizes, fusion widths, split settings,
+    channels, resets, mid-circuit measurements; final states, amplitude gathers and
+    seeded records against cirq.Simulator) with every circuit served from the schedule
+    cache from its first call on."""
+    import test_simulators as ts
+    from cirq_b200 import plan_cache
+
+    monkeypatch.setenv('CIRQ_B200_PLAN_CACHE_EAGER', '1')
+    ts.test_differential_fuzz_state_vector(cirq, SV, seed=7)
+    assert plan_cache.CACHE.builds >= 60 and plan_cache.CACHE.hits >= 60
+    builds = plan_cache.CACHE.builds
+    ts.test_differential_fuzz_noisy_state_vector_seeded(cirq, SV)
+    assert plan_cache.CACHE.builds > builds  # (the noise-free cases with a unitary prefix)
