@@ -187,3 +187,59 @@ extern "C" int b2q_host_compose_diag(double* out, int u, int num_members, const 
   }
   return B2Q_OK;
 }
+
+// ---- a recorded schedule executed by ONE library call ---------------------------------
+// (cirq_b200/program.py compiles the device operations of a cached schedule into this
+// form; replaying them from Python costs ~20 us of interpreter + ctypes per operation,
+// which is what a 20-qubit circuit's end-to-end time consists of.)
+
+extern "C" int b2q_schedule_op_bytes(void) { return (int)sizeof(b2q_schedule_op); }
+
+extern "C" int b2q_run_schedule(int dtype, int num_ops, const b2q_schedule_op* ops, const int* ints,
+                                const double* reals, int num_slots, void* const* slots, void* stream) {
+  B2Q_REQUIRE(dtype == B2Q_C64 || dtype == B2Q_C128, "bad dtype %d", dtype);
+  B2Q_REQUIRE(num_ops >= 0 && num_slots >= 0, "negative count");
+  B2Q_REQUIRE(num_ops == 0 || (ops != nullptr && slots != nullptr), "null argument");
+  for (int i = 0; i < num_ops; ++i) {
+    const b2q_schedule_op& op = ops[i];
+    B2Q_REQUIRE(op.slot >= 0 && op.slot < num_slots && slots[op.slot] != nullptr,
+                "operation %d: bad state slot %d", i, op.slot);
+    void* const st = slots[op.slot];
+    const int* const iv = ints + op.ints_offset;
+    const double* const rv = reals + op.reals_offset;
+    int rc = B2Q_OK;
+    switch (op.kind) {
+      case B2Q_OP_BASIS:
+        rc = b2q_sv_init_basis(st, dtype, op.n_bits, op.basis_index, stream);
+        break;
+      case B2Q_OP_KRON:
+        B2Q_REQUIRE(op.a >= 0 && op.a < num_slots && op.b >= 0 && op.b < num_slots &&
+                        slots[op.a] != nullptr && slots[op.b] != nullptr,
+                    "operation %d: bad input slots", i);
+        // ints: bits of a, bits of b
+        rc = b2q_sv_kron(slots[op.a], iv[0], slots[op.b], iv[1], dtype, st, stream);
+        break;
+      case B2Q_OP_DENSE:  // ints: ks[count], then all targets; reals: the matrices
+        rc = b2q_sv_apply_batch(st, dtype, op.n_bits, op.count, iv, iv + op.count, rv, nullptr, stream);
+        break;
+      case B2Q_OP_TILE:
+        rc = b2q_sv_apply_tile_blocks(st, dtype, op.n_bits, op.count, iv, iv + op.count, rv, stream);
+        break;
+      case B2Q_OP_DIAGONAL:  // ints: targets[count]; reals: the 2^count entries
+        rc = b2q_sv_apply_diagonal(st, dtype, op.n_bits, rv, iv, op.count, stream);
+        break;
+      case B2Q_OP_SCALE:
+        rc = b2q_sv_scale(st, dtype, op.n_bits, rv[0], rv[1], stream);
+        break;
+      case B2Q_OP_PERMUTE: {
+        int passes = 0;
+        rc = b2q_sv_permute_bits_inplace(st, dtype, op.n_bits, iv, &passes, stream);
+        break;
+      }
+      default:
+        return b2q::set_error(B2Q_ERR_INVALID, "operation %d: unknown kind %d", i, op.kind);
+    }
+    if (rc != B2Q_OK) return rc;
+  }
+  return B2Q_OK;
+}

@@ -190,42 +190,53 @@ class DeviceState:
             )
         )
 
-    def apply_batch(self, gates: Sequence[tuple]) -> None:
-        """Applies [(matrix, bits), ...] in order; consecutive dense blocks travel
-        two per pass where the tile kernel applies (`plan_passes`)."""
-        torch = _torch()
-        if not gates:
-            return
+    def lower_batch(self, gates: Sequence[tuple]) -> list[tuple]:
+        """The library calls `apply_batch` makes for [(matrix, bits), ...], in order:
+        ('tile', [two dense blocks]) = one tile pass, ('dense', [blocks]) = one
+        b2q_sv_apply_batch call (a pass per block), ('diag', (entries, bits)).  Needs
+        only n_bits / dtype of `self` (cirq_b200/program.py lowers recorded schedules
+        with it, so a compiled schedule launches exactly what a live call does)."""
+        out: list[tuple] = []
+
+        def singles(run):
+            dense: list = []
+            for m, b in run:
+                if np.ndim(m) == 1:
+                    if dense:
+                        out.append(('dense', dense))
+                        dense = []
+                    out.append(('diag', (m, b)))
+                else:
+                    dense.append((m, b))
+            if dense:
+                out.append(('dense', dense))
+
         if self.tile_pairing() and len(gates) > 1:
             run: list = []
             for group in self.plan_passes(gates):
                 if len(group) == 2:
-                    self._apply_singles(run)
+                    singles(run)
                     run = []
-                    self.apply_tile_blocks(group)
+                    out.append(('tile', group))
                 else:
                     run.append(group[0])
-            self._apply_singles(run)
-            return
-        self._apply_singles(gates)
+            singles(run)
+        else:
+            singles(gates)
+        return out
 
-    def _apply_singles(self, gates: Sequence[tuple]) -> None:
-        """One pass per block: diagonal blocks (1-D: the diagonal entries) between
-        runs of dense ones."""
+    def apply_batch(self, gates: Sequence[tuple]) -> None:
+        """Applies [(matrix, bits), ...] in order; consecutive dense blocks travel
+        two per pass where the tile kernel applies (`plan_passes`)."""
         if not gates:
             return
-        if any(np.ndim(m) == 1 for m, _ in gates):
-            run = []
-            for m, b in gates:
-                if np.ndim(m) == 1:
-                    self._apply_dense_run(run)
-                    run = []
-                    self.apply_diagonal(m, b)
-                else:
-                    run.append((m, b))
-            self._apply_dense_run(run)
-            return
-        self._apply_dense_run(gates)
+        for what, payload in self.lower_batch(gates):
+            if what == 'tile':
+                self.apply_tile_blocks(payload)
+            elif what == 'dense':
+                self._apply_dense_run(payload)
+            else:
+                self.apply_diagonal(*payload)
 
     def _apply_dense_run(self, gates: Sequence[tuple]) -> None:
         """Dense blocks, one pass each, with one library call."""

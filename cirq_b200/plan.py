@@ -261,5 +261,15 @@ def replay_ops(ops, dtype, device_state_cls=None, on_apply=None):
 def replay_plan(plan, device_state_cls=None, on_apply=None):
     """Executes a plan from `build_plan`; returns the final DeviceState.
     `on_apply(state, blocks)` replaces ``state.apply_batch(blocks)`` when given
-    (bench.py times individual launches through it)."""
+    (bench.py times individual launches through it).  Small registers on the real
+    device run as ONE library call (cirq_b200/program.py)."""
+    if on_apply is None:
+        from cirq_b200 import program
+        from cirq_b200.device_state import DeviceState
+
+        if (device_state_cls is None or device_state_cls is DeviceState) and program.enabled():
+            if '_native' not in plan:
+                plan['_native'] = program.compile_schedule(plan['ops'], plan['dtype'], DeviceState)
+            if plan['_native'] is not None:
+                return plan['_native'].run(DeviceState)[0][plan['final']]
     return replay_ops(plan['ops'], plan['dtype'], device_state_cls, on_apply)[plan['final']]

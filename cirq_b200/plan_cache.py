@@ -115,7 +115,8 @@ def recorder_for(device_cls):
 class PrefixPlan:
     """Recorded schedule of moments[:first] of one circuit from |0...0>."""
 
-    __slots__ = ('moments', 'first', 'qubits', 'ops', 'components', 'owner', 'nbytes', 'measure_tail')
+    __slots__ = ('moments', 'first', 'qubits', 'ops', 'components', 'owner', 'nbytes', 'measure_tail',
+                 '_native')
 
     def __init__(self, moments, first, qubits, ops, components, owner):
         self.moments = moments  # keeps the Moment objects (and so their ids) alive
@@ -126,6 +127,7 @@ class PrefixPlan:
         self.components = components
         self.owner = owner  # [(qubit or None, component index)] in product-state order
         self.measure_tail = False  # moments[first:] are measurements only (and exist)
+        self._native = {}  # dtype -> NativeSchedule, or None when it cannot be compiled
         self.nbytes = sum(m.nbytes for op in ops if op[0] == 'apply' for m, _ in op[2]) + sum(
             m.nbytes for c in components for m, _ in c[3])
 
@@ -189,9 +191,26 @@ class PlanCache:
 CACHE = PlanCache()
 
 
+def _native_schedule(plan: PrefixPlan, dtype, device_cls):
+    """The schedule compiled for b2q_run_schedule (cirq_b200/program.py): small
+    registers on the real device only; None otherwise."""
+    from cirq_b200 import program
+    from cirq_b200.device_state import DeviceState
+
+    if device_cls is not DeviceState or not program.enabled():
+        return None
+    key = np.dtype(dtype).str
+    if key not in plan._native:
+        plan._native[key] = program.compile_schedule(plan.ops, dtype, device_cls)
+    return plan._native[key]
+
+
 def replay(plan: PrefixPlan, dtype, device_cls):
     """Executes the recorded device operations; returns ({ident: device state},
     {ident: passes issued})."""
+    native = _native_schedule(plan, dtype, device_cls)
+    if native is not None:
+        return native.run(device_cls)
     live: dict = {}
     passes: dict = {}
     for op in plan.ops:

@@ -362,6 +362,37 @@ int b2q_host_left_apply(double* block, int u, const double* matrix, const int* b
 int b2q_host_compose(double* out, int u, int num_members, const int* ks, const int* bitpos,
                      const double* matrices_c128);
 
+/* ---- a recorded schedule executed by one call --------------------------------
+ * The device operations a circuit's unitary prefix issues from |0...0> (basis states,
+ * Kronecker joins, gate passes, in-place permutations, scalings: what
+ * SimulationProductState + the scheduler do to the sub-states,
+ * cirq-core/cirq/sim/simulation_product_state.py:83-139), recorded once per circuit
+ * (cirq_b200/plan_cache.py) and replayed without the interpreter in the loop.
+ * `slots[i]` = device buffer of state i (caller-allocated, 2^bits amplitudes each);
+ * `ints` / `reals` hold the operations' arguments at ints_offset / reals_offset. */
+enum {
+  B2Q_OP_BASIS = 0,    /* slot <- |basis_index> of n_bits */
+  B2Q_OP_KRON = 1,     /* slot <- slots[a] (x) slots[b]; ints: bits of a, bits of b */
+  B2Q_OP_DENSE = 2,    /* b2q_sv_apply_batch: ints = ks[count] then the targets; reals = matrices */
+  B2Q_OP_TILE = 3,     /* b2q_sv_apply_tile_blocks: same layout, count = 1 or 2 */
+  B2Q_OP_DIAGONAL = 4, /* b2q_sv_apply_diagonal: ints = targets[count]; reals = 2^count entries */
+  B2Q_OP_SCALE = 5,    /* reals = re, im */
+  B2Q_OP_PERMUTE = 6   /* b2q_sv_permute_bits_inplace: ints = src_bit[n_bits] */
+};
+typedef struct {
+  int32_t kind;
+  int32_t slot;
+  int32_t a, b;
+  int32_t n_bits; /* bits of slots[slot] */
+  int32_t count;
+  int64_t ints_offset;
+  int64_t reals_offset;
+  uint64_t basis_index;
+} b2q_schedule_op;
+int b2q_schedule_op_bytes(void);
+int b2q_run_schedule(int dtype, int num_ops, const b2q_schedule_op* ops, const int* ints,
+                     const double* reals, int num_slots, void* const* slots, void* stream);
+
 /* out[i] = product over the members of diag_m[bits of i at member m's wires]: the table of
  * a diagonal block (u <= 16 wires) from the list of its diagonal gates; host only. */
 int b2q_host_compose_diag(double* out, int u, int num_members, const int* ks, const int* bitpos,
