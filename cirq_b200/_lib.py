@@ -104,7 +104,8 @@ SIGNATURES = {
     'b2q_host_compose': (c_int, [c_void_p, c_int, c_int, POINTER(c_int), POINTER(c_int), c_void_p]),
     'b2q_host_compose_diag': (c_int, [c_void_p, c_int, c_int, POINTER(c_int), POINTER(c_int), c_void_p]),
     'b2q_schedule_op_bytes': (c_int, []),
-    'b2q_run_schedule': (c_int, [c_int, c_int, c_void_p, POINTER(c_int), c_void_p, c_int, c_void_p, c_void_p]),
+    'b2q_run_schedule': (c_int, [c_int, c_int, c_void_p, POINTER(c_int), c_void_p, c_int, c_void_p, POINTER(c_int),
+                                 c_void_p]),
     'b2q_sv_reduced_density_matrix': (c_int, [c_void_p, c_int, c_int, POINTER(c_int), c_int, c_void_p, c_void_p]),
     'b2q_bsv_apply_select_multi': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, POINTER(c_int), c_int,
                                            c_void_p, c_int, c_void_p]),

@@ -196,7 +196,8 @@ extern "C" int b2q_host_compose_diag(double* out, int u, int num_members, const 
 extern "C" int b2q_schedule_op_bytes(void) { return (int)sizeof(b2q_schedule_op); }
 
 extern "C" int b2q_run_schedule(int dtype, int num_ops, const b2q_schedule_op* ops, const int* ints,
-                                const double* reals, int num_slots, void* const* slots, void* stream) {
+                                const double* reals, int num_slots, void* const* slots,
+                                int* permute_passes, void* stream) {
   B2Q_REQUIRE(dtype == B2Q_C64 || dtype == B2Q_C128, "bad dtype %d", dtype);
   B2Q_REQUIRE(num_ops >= 0 && num_slots >= 0, "negative count");
   B2Q_REQUIRE(num_ops == 0 || (ops != nullptr && slots != nullptr), "null argument");
@@ -234,6 +235,7 @@ extern "C" int b2q_run_schedule(int dtype, int num_ops, const b2q_schedule_op* o
       case B2Q_OP_PERMUTE: {
         int passes = 0;
         rc = b2q_sv_permute_bits_inplace(st, dtype, op.n_bits, iv, &passes, stream);
+        if (permute_passes != nullptr) permute_passes[op.slot] += passes;
         break;
       }
       default:

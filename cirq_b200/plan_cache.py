@@ -217,7 +217,7 @@ def replay(plan: PrefixPlan, dtype, device_cls):
         kind = op[0]
         if kind == 'apply':
             live[op[1]].apply_batch(op[2])
-            passes[op[1]] += op[3]
+            passes[op[1]] += op[3] if len(op) > 3 else len(live[op[1]].plan_passes(op[2]))
         elif kind == 'basis':
             live[op[1]] = device_cls.basis(op[2], dtype, op[3])
             passes[op[1]] = 0

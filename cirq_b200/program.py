@@ -69,7 +69,7 @@ class _Shape:
 class NativeSchedule:
     """Compiled form of a list of recorded device operations (see `compile_schedule`)."""
 
-    def __init__(self, dtype, records, ints, reals, slot_bits, alive, passes):
+    def __init__(self, dtype, records, ints, reals, slot_bits, alive, passes, permutes=()):
         self.dtype = np.dtype(dtype)
         self.code = _lib.dtype_code(self.dtype)
         self.num_ops = len(records)
@@ -86,6 +86,7 @@ class NativeSchedule:
         self.amp_bytes = amp
         self.alive = dict(alive)  # ident -> slot of the states that exist at the end
         self.passes = dict(passes)  # ident -> gate passes issued on it (and its ancestors)
+        self.permutes = list(permutes)  # (surviving ident, slot) of the in-place permutations
 
     def run(self, device_cls):
         """Executes the schedule on the current stream; ({ident: device state}, {ident:
@@ -96,9 +97,10 @@ class NativeSchedule:
         arena = torch.empty(self.total_bytes, dtype=torch.uint8, device='cuda')
         base = arena.data_ptr()
         slots = (ctypes.c_void_p * max(1, len(self.offsets)))(*[base + off for off in self.offsets])
+        permute_passes = (ctypes.c_int * max(1, len(self.offsets)))() if self.permutes else None
         _lib.check(lib.b2q_run_schedule(
             self.code, self.num_ops, self.ops, self.ints.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
-            self.reals.ctypes.data, len(self.offsets), slots,
+            self.reals.ctypes.data, len(self.offsets), slots, permute_passes,
             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
         real = torch.float32 if self.code == _lib.C64 else torch.float64
         live = {}
@@ -106,7 +108,10 @@ class NativeSchedule:
             off, nbytes = self.offsets[slot], self.amp_bytes << self.slot_bits[slot]
             live[ident] = device_cls(self.slot_bits[slot], self.dtype,
                                      tensor=arena[off:off + nbytes].view(real).view(-1, 2))
-        return live, dict(self.passes)
+        passes = dict(self.passes)
+        for ident, slot in self.permutes:  # (how many tile passes a permutation took is the library's answer)
+            passes[ident] += int(permute_passes[slot])
+        return live, passes
 
 
 def compile_schedule(ops, dtype, device_cls):
@@ -118,6 +123,8 @@ def compile_schedule(ops, dtype, device_cls):
     max_fast = 5 if _lib.dtype_code(dtype) == _lib.C64 else 4
     records, ints, reals = [], [], []
     slot_of, bits_of, alive, passes = {}, [], {}, {}
+    permuted: list = []  # idents permuted in place (their pass counts come back from the library)
+    heir: dict = {}  # ident -> the state it was joined into
 
     def new_slot(ident, bits):
         slot_of[ident] = len(bits_of)
@@ -148,6 +155,7 @@ def compile_schedule(ops, dtype, device_cls):
             slot = new_slot(op[1], bits)
             passes[op[1]] = passes.pop(op[2]) + passes.pop(op[3])
             del alive[op[2]], alive[op[3]]
+            heir[op[2]] = heir[op[3]] = op[1]
             emit(OP_KRON, slot, bits, a=a, b=b, ivals=(bits_of[a], bits_of[b]))
         elif kind == 'apply':
             slot = slot_of[op[1]]
@@ -173,6 +181,14 @@ def compile_schedule(ops, dtype, device_cls):
         elif kind == 'permute':
             slot = slot_of[op[1]]
             emit(OP_PERMUTE, slot, bits_of[slot], count=len(op[2]), ivals=op[2])
+            permuted.append(op[1])
         else:
             return None
-    return NativeSchedule(dtype, records, ints, reals, bits_of, alive, passes)
+    permutes = []
+    for ident in permuted:
+        last = ident
+        while last in heir:
+            last = heir[last]
+        permutes.append((last, slot_of[ident]))
+    # (the library adds up the permutations of a slot itself: one entry per slot)
+    return NativeSchedule(dtype, records, ints, reals, bits_of, alive, passes, list(dict.fromkeys(permutes)))

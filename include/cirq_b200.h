@@ -369,7 +369,9 @@ int b2q_host_compose(double* out, int u, int num_members, const int* ks, const i
  * cirq-core/cirq/sim/simulation_product_state.py:83-139), recorded once per circuit
  * (cirq_b200/plan_cache.py) and replayed without the interpreter in the loop.
  * `slots[i]` = device buffer of state i (caller-allocated, 2^bits amplitudes each);
- * `ints` / `reals` hold the operations' arguments at ints_offset / reals_offset. */
+ * `ints` / `reals` hold the operations' arguments at ints_offset / reals_offset;
+ * `permute_passes` (num_slots counters, or NULL) receives the passes the in-place
+ * permutations took, per slot. */
 enum {
   B2Q_OP_BASIS = 0,    /* slot <- |basis_index> of n_bits */
   B2Q_OP_KRON = 1,     /* slot <- slots[a] (x) slots[b]; ints: bits of a, bits of b */
@@ -391,7 +393,8 @@ typedef struct {
 } b2q_schedule_op;
 int b2q_schedule_op_bytes(void);
 int b2q_run_schedule(int dtype, int num_ops, const b2q_schedule_op* ops, const int* ints,
-                     const double* reals, int num_slots, void* const* slots, void* stream);
+                     const double* reals, int num_slots, void* const* slots, int* permute_passes,
+                     void* stream);
 
 /* out[i] = product over the members of diag_m[bits of i at member m's wires]: the table of
  * a diagonal block (u <= 16 wires) from the list of its diagonal gates; host only. */
