@@ -16,19 +16,72 @@
 
 namespace b2q {
 
-// out[(i << nb) | j] = a[i] * b[j]
-template <typename real>
+template <typename real, int VEC>
+struct AmpVec;
+template <>
+struct AmpVec<float, 1> {
+  using type = float2;
+  static __device__ __forceinline__ float2 at(const float2& v, int) { return v; }
+  static __device__ __forceinline__ float2 pack(const float2* e) { return e[0]; }
+};
+template <>
+struct AmpVec<float, 2> {
+  using type = float4;
+  static __device__ __forceinline__ float2 at(const float4& v, int e) {
+    return e == 0 ? make_float2(v.x, v.y) : make_float2(v.z, v.w);
+  }
+  static __device__ __forceinline__ float4 pack(const float2* e) {
+    return make_float4(e[0].x, e[0].y, e[1].x, e[1].y);
+  }
+};
+template <>
+struct AmpVec<double, 1> {
+  using type = double2;
+  static __device__ __forceinline__ double2 at(const double2& v, int) { return v; }
+  static __device__ __forceinline__ double2 pack(const double2* e) { return e[0]; }
+};
+constexpr int kLayoutUnroll = 4;  // independent accesses in flight per thread and operand
+
+// 16-byte accesses of complex64 pairs need aligned operands (sub-states live at any
+// 8-byte offset of an arena).
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// out[(i << nb) | j] = a[i] * b[j]; VEC amplitudes of b and out per access (16-byte
+// stores: VEC = 2 for complex64 needs nb >= 1 and aligned operands)
+template <typename real, int VEC>
 __global__ void __launch_bounds__(256)
     sv_kron_kernel(const typename Cplx<real>::type* __restrict__ a,
                    const typename Cplx<real>::type* __restrict__ b, int nb,
                    typename Cplx<real>::type* __restrict__ out, uint64_t total) {
   using C = typename Cplx<real>::type;
+  using V = typename AmpVec<real, VEC>::type;
   const uint64_t mask = (1ull << nb) - 1ull;
-  for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total;
-       o += (uint64_t)gridDim.x * blockDim.x) {
-    const C x = a[o >> nb];
-    const C y = b[o & mask];
-    out[o] = make_c<real>(x.x * y.x - x.y * y.y, x.x * y.y + x.y * y.x);
+  const uint64_t nvec = total / VEC, stride = (uint64_t)gridDim.x * blockDim.x;
+  V* outv = reinterpret_cast<V*>(out);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += stride * kLayoutUnroll) {
+    V y[kLayoutUnroll];
+    C x[kLayoutUnroll];
+#pragma unroll
+    for (int u = 0; u < kLayoutUnroll; ++u) {
+      const uint64_t o = (i + u * stride) * VEC;
+      if (o < total) {
+        x[u] = a[o >> nb];
+        y[u] = *reinterpret_cast<const V*>(b + (o & mask));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kLayoutUnroll; ++u) {
+      if ((i + u * stride) * VEC < total) {
+        C r[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const C ye = AmpVec<real, VEC>::at(y[u], e);
+          r[e] = make_c<real>(x[u].x * ye.x - x[u].y * ye.y, x[u].x * ye.y + x[u].y * ye.x);
+        }
+        outv[i + u * stride] = AmpVec<real, VEC>::pack(r);
+      }
+    }
   }
 }
 
@@ -208,24 +261,62 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// flag[0] = 1 if some |a[i]*b[j] - t[(i<<nb)|j]| > atol + rtol*|t|  (np.allclose)
-template <typename real>
+// One element of np.allclose: |got - want| > atol + rtol * |want|.  Differences below
+// atol (every element of a matching pair of states) are settled without the two
+// float64 square roots that bound these kernels before (1.4 TB/s at 28 qubits).
+__device__ __forceinline__ bool allclose_violated(double got_re, double got_im, double want_re,
+                                                  double want_im, double atol, double atol2,
+                                                  double rtol) {
+  const double dr = got_re - want_re, di = got_im - want_im;
+  const double d2 = dr * dr + di * di;
+  if (d2 <= atol2) return false;
+  return sqrt(d2) > atol + rtol * sqrt(want_re * want_re + want_im * want_im);
+}
+
+
+// flag[0] = 1 if some |a[i]*b[j] - t[(i<<nb)|j]| > atol + rtol*|t|  (np.allclose);
+// VEC amplitudes of t and b per access (VEC = 2 needs nb >= 1 and 16-byte alignment).
+template <typename real, int VEC>
 __global__ void __launch_bounds__(256)
     sv_kron_mismatch_kernel(const typename Cplx<real>::type* __restrict__ a,
                             const typename Cplx<real>::type* __restrict__ b, int nb,
                             const typename Cplx<real>::type* __restrict__ t, uint64_t total,
-                            double atol, double rtol, int* __restrict__ flag) {
+                            double atol, double rtol, int* flag) {
+  using V = typename AmpVec<real, VEC>::type;
   const uint64_t mask = (1ull << nb) - 1ull;
+  const uint64_t nvec = total / VEC, stride = (uint64_t)gridDim.x * blockDim.x;
+  const V* tv = reinterpret_cast<const V*>(t);
+  const double atol2 = atol * atol;
   bool bad = false;
-  for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total;
-       o += (uint64_t)gridDim.x * blockDim.x) {
-    const auto x = a[o >> nb];
-    const auto y = b[o & mask];
-    const auto z = t[o];
-    const double dr = (double)(x.x * y.x - x.y * y.y) - (double)z.x;
-    const double di = (double)(x.x * y.y + x.y * y.x) - (double)z.y;
-    const double lim = atol + rtol * sqrt((double)z.x * z.x + (double)z.y * z.y);
-    if (sqrt(dr * dr + di * di) > lim) bad = true;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += stride * kLayoutUnroll) {
+    if (*reinterpret_cast<volatile const int*>(flag)) return;  // settled elsewhere
+    V z[kLayoutUnroll], y[kLayoutUnroll];
+    typename Cplx<real>::type x[kLayoutUnroll];
+#pragma unroll
+    for (int u = 0; u < kLayoutUnroll; ++u) {
+      const uint64_t o = (i + u * stride) * VEC;
+      if (o < total) {
+        z[u] = tv[i + u * stride];
+        y[u] = *reinterpret_cast<const V*>(b + (o & mask));
+        x[u] = a[o >> nb];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kLayoutUnroll; ++u) {
+      if ((i + u * stride) * VEC < total) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const auto ye = AmpVec<real, VEC>::at(y[u], e);
+          const auto ze = AmpVec<real, VEC>::at(z[u], e);
+          if (allclose_violated((double)(x[u].x * ye.x - x[u].y * ye.y),
+                                (double)(x[u].x * ye.y + x[u].y * ye.x), (double)ze.x,
+                                (double)ze.y, atol, atol2, rtol))
+            bad = true;
+        }
+      }
+    }
+    if (bad) break;
   }
   if (bad) atomicExch(flag, 1);
 }
@@ -271,19 +362,40 @@ __global__ void __launch_bounds__(256)
 }
 
 // flag[0] = 1 if some |a[i] - b[i]| > atol + rtol*|b[i]|  (np.allclose(a, b))
-template <typename real>
+template <typename real, int VEC>
 __global__ void __launch_bounds__(256)
     sv_mismatch_kernel(const typename Cplx<real>::type* __restrict__ a,
                        const typename Cplx<real>::type* __restrict__ b, uint64_t total,
-                       double atol, double rtol, int* __restrict__ flag) {
+                       double atol, double rtol, int* flag) {
+  using V = typename AmpVec<real, VEC>::type;
+  const uint64_t nvec = total / VEC, stride = (uint64_t)gridDim.x * blockDim.x;
+  const V* av = reinterpret_cast<const V*>(a);
+  const V* bv = reinterpret_cast<const V*>(b);
+  const double atol2 = atol * atol;
   bool bad = false;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (uint64_t)gridDim.x * blockDim.x) {
-    const auto x = a[i];
-    const auto y = b[i];
-    const double dr = (double)x.x - (double)y.x, di = (double)x.y - (double)y.y;
-    if (sqrt(dr * dr + di * di) > atol + rtol * sqrt((double)y.x * y.x + (double)y.y * y.y))
-      bad = true;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += stride * kLayoutUnroll) {
+    if (*reinterpret_cast<volatile const int*>(flag)) return;  // settled elsewhere
+    V x[kLayoutUnroll], y[kLayoutUnroll];
+#pragma unroll
+    for (int u = 0; u < kLayoutUnroll; ++u)
+      if (i + u * stride < nvec) {
+        x[u] = av[i + u * stride];
+        y[u] = bv[i + u * stride];
+      }
+#pragma unroll
+    for (int u = 0; u < kLayoutUnroll; ++u)
+      if (i + u * stride < nvec) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const auto xe = AmpVec<real, VEC>::at(x[u], e);
+          const auto ye = AmpVec<real, VEC>::at(y[u], e);
+          if (allclose_violated((double)xe.x, (double)xe.y, (double)ye.x, (double)ye.y, atol,
+                                atol2, rtol))
+            bad = true;
+        }
+      }
+    if (bad) break;
   }
   if (bad) atomicExch(flag, 1);
 }
@@ -303,12 +415,16 @@ extern "C" int b2q_sv_kron(const void* a, int na, const void* b, int nb, int dty
   B2Q_REQUIRE(na >= 0 && nb >= 0 && na + nb <= 40, "qubit counts out of range");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const uint64_t total = 1ull << (na + nb);
-  if (dtype == B2Q_C64)
-    sv_kron_kernel<float><<<layout_grid(total), 256, 0, s>>>(
+  if (dtype == B2Q_C64 && nb >= 1 && aligned16(b) && aligned16(out))
+    sv_kron_kernel<float, 2><<<layout_grid(total / 2 / kLayoutUnroll), 256, 0, s>>>(
+        reinterpret_cast<const float2*>(a), reinterpret_cast<const float2*>(b), nb,
+        reinterpret_cast<float2*>(out), total);
+  else if (dtype == B2Q_C64)
+    sv_kron_kernel<float, 1><<<layout_grid(total / kLayoutUnroll), 256, 0, s>>>(
         reinterpret_cast<const float2*>(a), reinterpret_cast<const float2*>(b), nb,
         reinterpret_cast<float2*>(out), total);
   else
-    sv_kron_kernel<double><<<layout_grid(total), 256, 0, s>>>(
+    sv_kron_kernel<double, 1><<<layout_grid(total / kLayoutUnroll), 256, 0, s>>>(
         reinterpret_cast<const double2*>(a), reinterpret_cast<const double2*>(b), nb,
         reinterpret_cast<double2*>(out), total);
   B2Q_LAUNCH_CHECK("sv_kron_kernel");
@@ -562,12 +678,16 @@ extern "C" int b2q_sv_kron_allclose(const void* a, int na, const void* b, int nb
   int* flag = reinterpret_cast<int*>(workspace(sizeof(int)));
   if (flag == nullptr) return B2Q_ERR_CUDA;
   B2Q_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), s));
-  if (dtype == B2Q_C64)
-    sv_kron_mismatch_kernel<float><<<layout_grid(total), 256, 0, s>>>(
+  if (dtype == B2Q_C64 && nb >= 1 && aligned16(b) && aligned16(t))
+    sv_kron_mismatch_kernel<float, 2><<<layout_grid(total / 2 / kLayoutUnroll), 256, 0, s>>>(
+        reinterpret_cast<const float2*>(a), reinterpret_cast<const float2*>(b), nb,
+        reinterpret_cast<const float2*>(t), total, atol, rtol, flag);
+  else if (dtype == B2Q_C64)
+    sv_kron_mismatch_kernel<float, 1><<<layout_grid(total / kLayoutUnroll), 256, 0, s>>>(
         reinterpret_cast<const float2*>(a), reinterpret_cast<const float2*>(b), nb,
         reinterpret_cast<const float2*>(t), total, atol, rtol, flag);
   else
-    sv_kron_mismatch_kernel<double><<<layout_grid(total), 256, 0, s>>>(
+    sv_kron_mismatch_kernel<double, 1><<<layout_grid(total / kLayoutUnroll), 256, 0, s>>>(
         reinterpret_cast<const double2*>(a), reinterpret_cast<const double2*>(b), nb,
         reinterpret_cast<const double2*>(t), total, atol, rtol, flag);
   B2Q_LAUNCH_CHECK("sv_kron_mismatch_kernel");
@@ -619,12 +739,16 @@ extern "C" int b2q_sv_allclose(const void* a, const void* b, int dtype, int n_qu
   int* flag = reinterpret_cast<int*>(workspace(sizeof(int)));
   if (flag == nullptr) return B2Q_ERR_CUDA;
   B2Q_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), s));
-  if (dtype == B2Q_C64)
-    sv_mismatch_kernel<float><<<layout_grid(total), 256, 0, s>>>(
+  if (dtype == B2Q_C64 && n_qubits >= 1 && aligned16(a) && aligned16(b))
+    sv_mismatch_kernel<float, 2><<<layout_grid(total / 2 / kLayoutUnroll), 256, 0, s>>>(
+        reinterpret_cast<const float2*>(a), reinterpret_cast<const float2*>(b), total, atol, rtol,
+        flag);
+  else if (dtype == B2Q_C64)
+    sv_mismatch_kernel<float, 1><<<layout_grid(total / kLayoutUnroll), 256, 0, s>>>(
         reinterpret_cast<const float2*>(a), reinterpret_cast<const float2*>(b), total, atol, rtol,
         flag);
   else
-    sv_mismatch_kernel<double><<<layout_grid(total), 256, 0, s>>>(
+    sv_mismatch_kernel<double, 1><<<layout_grid(total / kLayoutUnroll), 256, 0, s>>>(
         reinterpret_cast<const double2*>(a), reinterpret_cast<const double2*>(b), total, atol,
         rtol, flag);
   B2Q_LAUNCH_CHECK("sv_mismatch_kernel");

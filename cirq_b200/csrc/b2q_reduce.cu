@@ -16,6 +16,7 @@
 #include "b2q_common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 namespace b2q {
@@ -640,6 +641,137 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// The same sums with the sign work amortised.  A thread takes a run of 8 amplitudes
+// (index bits 0-2) per step: the 8 signed sums of the run over its low bits are the
+// Walsh-Hadamard transform W of its 8 pair products (24 additions for all 8), so a
+// string with Z bits z reads W[z & 7].  The rest of the sign splits by index bits:
+// run r = k * vt + g with vt (a power of two) "virtual threads" g — the part of z over
+// g's bits is constant while a thread walks k and is applied once per walk, the part
+// over k's bits is the same for every thread and comes from a table built once per
+// CTA (flip[k][t] = sign bit to XOR into the addend).  Per run and string that leaves
+// one shared-memory read of W (own column: no synchronisation), one XOR and one
+// float64 addition.  A CTA walks virtual CTAs and keeps running column sums, so
+// partial[] has gridDim.x rows.
+constexpr int kPauliMaxK = 128;
+template <typename real, bool DIAG>
+__global__ void __launch_bounds__(256)
+    sv_pauli_multi_run_kernel(const typename Cplx<real>::type* __restrict__ state, uint64_t vt,
+                              int k_count, uint64_t xmask,
+                              const __grid_constant__ PauliMultiParams p,
+                              double* __restrict__ partial) {
+  using C = typename Cplx<real>::type;
+  constexpr int T = kPauliMaxTerms;
+  __shared__ double w_re[8][256];
+  __shared__ double w_im[DIAG ? 1 : 8][DIAG ? 1 : 256];
+  __shared__ __align__(16) uint32_t flip[kPauliMaxK][T];
+  __shared__ double sm[8][2 * T];
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < k_count * T; idx += 256) {
+    const int k = idx / T, t = idx % T;
+    flip[k][t] = (uint32_t)(__popcll((((uint64_t)k * vt) << 3) & p.zmask[t]) & 1) << 31;
+  }
+  __syncthreads();
+  const uint64_t xhigh = xmask & ~7ull;
+  const int xlow = (int)(xmask & 7ull);
+  int w_at[T];  // this thread's element of W[z_t & 7]
+#pragma unroll
+  for (int t = 0; t < T; ++t) w_at[t] = (int)(p.zmask[t] & 7ull) * 256 + tid;
+  double column_total = 0.0;  // threads < 2 * count: this CTA's sum of one output column
+  for (uint64_t vb = blockIdx.x; vb < (vt >> 8); vb += gridDim.x) {
+    double ar[T], ai[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) ar[t] = ai[t] = 0.0;
+    const uint64_t g = (vb << 8) | (uint64_t)tid;
+    for (int k = 0; k < k_count; ++k) {
+      const uint64_t i0 = ((uint64_t)k * vt + g) << 3;
+      C a[8];
+      if constexpr (sizeof(real) == 4) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const float4 v = *reinterpret_cast<const float4*>(state + i0 + j);
+          a[j] = make_float2(v.x, v.y);
+          a[j + 1] = make_float2(v.z, v.w);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = state[i0 + j];
+      }
+      double wr[8], wi[8];
+      if constexpr (DIAG) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          wr[j] = (double)a[j].x * (double)a[j].x + (double)a[j].y * (double)a[j].y;
+          wi[j] = 0.0;
+        }
+      } else {
+        const C* other = state + (i0 ^ xhigh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const C b = other[j ^ xlow];
+          wr[j] = (double)b.x * (double)a[j].x + (double)b.y * (double)a[j].y;
+          wi[j] = (double)b.x * (double)a[j].y - (double)b.y * (double)a[j].x;
+        }
+      }
+#pragma unroll
+      for (int h = 1; h < 8; h <<= 1)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (!(j & h)) {
+            const double x = wr[j], y = wr[j | h];
+            wr[j] = x + y;
+            wr[j | h] = x - y;
+            if constexpr (!DIAG) {
+              const double u = wi[j], v = wi[j | h];
+              wi[j] = u + v;
+              wi[j | h] = u - v;
+            }
+          }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        w_re[j][tid] = wr[j];
+        if constexpr (!DIAG) w_im[j][tid] = wi[j];
+      }
+      uint32_t f[T];
+#pragma unroll
+      for (int q = 0; q < T; q += 4) {
+        const uint4 v = *reinterpret_cast<const uint4*>(&flip[k][q]);
+        f[q] = v.x, f[q + 1] = v.y, f[q + 2] = v.z, f[q + 3] = v.w;
+      }
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        if (t < p.count) {
+          const double re = (&w_re[0][0])[w_at[t]];
+          ar[t] += __hiloint2double(__double2hiint(re) ^ (int)f[t], __double2loint(re));
+          if constexpr (!DIAG) {
+            const double im = (&w_im[0][0])[w_at[t]];
+            ai[t] += __hiloint2double(__double2hiint(im) ^ (int)f[t], __double2loint(im));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      if (t < p.count) {
+        const bool neg = __popcll((g << 3) & p.zmask[t]) & 1;
+        const double r = warp_sum(neg ? -ar[t] : ar[t]);
+        const double m = DIAG ? 0.0 : warp_sum(neg ? -ai[t] : ai[t]);
+        if ((tid & 31) == 0) {
+          sm[tid >> 5][2 * t] = r;
+          sm[tid >> 5][2 * t + 1] = m;
+        }
+      }
+    }
+    __syncthreads();
+    if (tid < 2 * p.count) {
+      double v = 0;
+      for (int w = 0; w < 8; ++w) v += sm[w][tid];
+      column_total += v;
+    }
+    __syncthreads();
+  }
+  if (tid < 2 * p.count) partial[(size_t)blockIdx.x * 2 * p.count + tid] = column_total;
+}
+
 // out[j] = sum_b partial[b * width + j]
 __global__ void __launch_bounds__(256)
     column_sum_kernel(const double* __restrict__ partial, uint64_t blocks, int width,
@@ -754,6 +886,201 @@ static int reduced_dm_t(const void* state, int n, int m, const RdmParams& p, dou
     case 4: return reduced_dm_launch<real, 4, sizeof(real) == 4 ? 2 : 1>(state, n, p, out_dev, s);
     default: return reduced_dm_launch<real, 5, 1>(state, n, p, out_dev, s);
   }
+}
+
+// Gram form of the same sum for M = 3..5 kept bits and states of >= 2^11
+// amplitudes: ONE read of the state.  A CTA walks tiles of 2^11 amplitudes — the
+// kept bits plus the lowest free bits, so a tile is made of long contiguous runs —,
+// stages a tile in shared memory as X[rest][a] and accumulates rho += X^T conj(X)
+// with 4 x 4 register blocks (thread = one block of rho x one slice of the tile's
+// rest values; complex64: two packed FFMA2 per complex MAC, partial sums in the
+// state's precision over one tile, folded into float64 registers per tile).  The
+// next tile's loads are in flight while the current one is multiplied.  CTA sums
+// go to partial[cta][2 D D] and rdm_fold_kernel adds them in a fixed order: the
+// result does not depend on scheduling.
+constexpr int kRdmTileBits = 11;
+struct RdmGramParams {
+  int tile_pos[kRdmTileBits];  // ascending: the kept bits and the lowest free bits
+  int kept_rank[5];            // kept bit q (ascending position) = tile bit kept_rank[q]
+};
+
+template <typename real>
+__device__ __forceinline__ void rdm_mac(typename Cplx<real>::type& acc,
+                                        const typename Cplx<real>::type& xa,
+                                        const typename Cplx<real>::type& xb);
+template <>
+__device__ __forceinline__ void rdm_mac<float>(float2& acc, const float2& xa, const float2& xb) {
+  // acc += xa * conj(xb)
+  acc = __ffma2_rn(make_float2(xb.x, xb.x), xa, acc);
+  acc = __ffma2_rn(make_float2(xb.y, -xb.y), make_float2(xa.y, xa.x), acc);
+}
+template <>
+__device__ __forceinline__ void rdm_mac<double>(double2& acc, const double2& xa,
+                                                const double2& xb) {
+  acc.x = fma(xa.x, xb.x, fma(xa.y, xb.y, acc.x));
+  acc.y = fma(xa.y, xb.x, fma(-xa.x, xb.y, acc.y));
+}
+
+template <typename real, int M>
+__global__ void __launch_bounds__(256)
+    sv_reduced_dm_gram_kernel(const typename Cplx<real>::type* __restrict__ state,
+                              uint64_t num_tiles, const __grid_constant__ RdmGramParams p,
+                              double* __restrict__ partial) {
+  using C = typename Cplx<real>::type;
+  constexpr int D = 1 << M;
+  constexpr int E = 1 << kRdmTileBits;  // amplitudes per tile
+  constexpr int G = E / D;              // rest values per tile
+  constexpr int NBR = D / 4;            // 4 x 4 blocks per side of rho
+  constexpr int NB = NBR * NBR;
+  constexpr int S = 256 / NB;           // slices of the rest values
+  constexpr int kLoads = E / 256;
+  static_assert(M >= 3 && M <= 5 && G % S == 0, "tile shape");
+  static_assert(sizeof(C) * E >= sizeof(double) * 2 * D * D, "fold buffer aliases the tile");
+  __shared__ __align__(16) C tile[E];
+  __shared__ uint64_t k_off[kLoads];
+  __shared__ int k_slot[kLoads];
+
+  const int t = threadIdx.x;
+  // element e = t | (k << 8) of a tile: its offset in the state and its slot X[rest][a]
+  auto offset_of = [&](int e) {
+    uint64_t off = 0;
+    for (int j = 0; j < kRdmTileBits; ++j) off |= (uint64_t)((e >> j) & 1) << p.tile_pos[j];
+    return off;
+  };
+  auto slot_of = [&](int e) {
+    int a = 0, kept = 0;
+    for (int q = 0; q < M; ++q) {
+      a |= ((e >> p.kept_rank[q]) & 1) << q;
+      kept |= 1 << p.kept_rank[q];
+    }
+    int rest = 0, f = 0;
+    for (int j = 0; j < kRdmTileBits; ++j)
+      if (!((kept >> j) & 1)) rest |= ((e >> j) & 1) << f++;
+    return rest * D + a;
+  };
+  const uint64_t t_off = offset_of(t);
+  const int t_slot = slot_of(t);
+  if (t < kLoads) {
+    k_off[t] = offset_of(t << 8);
+    k_slot[t] = slot_of(t << 8);
+  }
+  __syncthreads();
+
+  const int blk = t % NB, slice = t / NB;
+  const int ra = 4 * (blk / NBR), rb = 4 * (blk % NBR);
+  double acc_re[4][4], acc_im[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc_re[r][c] = acc_im[r][c] = 0.0;
+
+  C v[kLoads];
+  uint64_t tl = blockIdx.x;
+  if (tl < num_tiles) {
+    const C* src = state + insert_zero_bits(tl, p.tile_pos, kRdmTileBits) + t_off;
+#pragma unroll
+    for (int k = 0; k < kLoads; ++k) v[k] = src[k_off[k]];
+  }
+  for (; tl < num_tiles; tl += gridDim.x) {
+    __syncthreads();  // the previous tile has been consumed
+#pragma unroll
+    for (int k = 0; k < kLoads; ++k) tile[t_slot | k_slot[k]] = v[k];
+    __syncthreads();
+    const uint64_t next = tl + gridDim.x;
+    if (next < num_tiles) {
+      const C* src = state + insert_zero_bits(next, p.tile_pos, kRdmTileBits) + t_off;
+#pragma unroll
+      for (int k = 0; k < kLoads; ++k) v[k] = src[k_off[k]];
+    }
+    C part[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) part[r][c] = make_c<real>(0, 0);
+#pragma unroll 4
+    for (int g = slice; g < G; g += S) {
+      const C* row = tile + g * D;
+      C xa[4], xb[4];
+      if constexpr (sizeof(real) == 4) {
+        const float4 a01 = *reinterpret_cast<const float4*>(row + ra);
+        const float4 a23 = *reinterpret_cast<const float4*>(row + ra + 2);
+        const float4 b01 = *reinterpret_cast<const float4*>(row + rb);
+        const float4 b23 = *reinterpret_cast<const float4*>(row + rb + 2);
+        xa[0] = make_float2(a01.x, a01.y), xa[1] = make_float2(a01.z, a01.w);
+        xa[2] = make_float2(a23.x, a23.y), xa[3] = make_float2(a23.z, a23.w);
+        xb[0] = make_float2(b01.x, b01.y), xb[1] = make_float2(b01.z, b01.w);
+        xb[2] = make_float2(b23.x, b23.y), xb[3] = make_float2(b23.z, b23.w);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) xa[r] = row[ra + r], xb[r] = row[rb + r];
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) rdm_mac<real>(part[r][c], xa[r], xb[c]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        acc_re[r][c] += (double)part[r][c].x;
+        acc_im[r][c] += (double)part[r][c].y;
+      }
+  }
+  // fold the slices in a fixed order (the tile's memory is free now)
+  __syncthreads();
+  double* red = reinterpret_cast<double*>(tile);
+  for (int i = t; i < 2 * D * D; i += 256) red[i] = 0.0;
+  __syncthreads();
+  for (int s = 0; s < S; ++s) {
+    if (slice == s) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          red[2 * ((ra + r) * D + rb + c)] += acc_re[r][c];
+          red[2 * ((ra + r) * D + rb + c) + 1] += acc_im[r][c];
+        }
+    }
+    __syncthreads();
+  }
+  for (int i = t; i < 2 * D * D; i += 256) partial[(size_t)blockIdx.x * 2 * D * D + i] = red[i];
+}
+
+// out[i] = sum over CTAs of partial[cta][i], in CTA order
+__global__ void __launch_bounds__(256)
+    rdm_fold_kernel(const double* __restrict__ partial, int ctas, int width,
+                    double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= width) return;
+  double v = 0.0;
+  for (int b = 0; b < ctas; ++b) v += partial[(size_t)b * width + i];
+  out[i] = v;
+}
+
+// Most CTAs of the Gram kernel that can be resident at once (its loop is persistent).
+template <typename real, int M>
+static int rdm_gram_grid(uint64_t num_tiles) {
+  int dev = 0, sms = 148, per_sm = 1;
+  if (cudaGetDevice(&dev) == cudaSuccess)
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sv_reduced_dm_gram_kernel<real, M>,
+                                                    256, 0) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  return (int)std::min<uint64_t>(num_tiles, (uint64_t)sms * std::min(per_sm, 2));
+}
+
+template <typename real, int M>
+static int reduced_dm_gram_launch(const void* state, int n, const RdmGramParams& p, int ctas,
+                                  double* partial, double* out_dev, cudaStream_t s) {
+  using C = typename Cplx<real>::type;
+  constexpr int width = 2 << (2 * M);
+  sv_reduced_dm_gram_kernel<real, M><<<ctas, 256, 0, s>>>(
+      reinterpret_cast<const C*>(state), 1ull << (n - kRdmTileBits), p, partial);
+  B2Q_LAUNCH_CHECK("sv_reduced_dm_gram_kernel");
+  rdm_fold_kernel<<<(width + 255) / 256, 256, 0, s>>>(partial, ctas, width, out_dev);
+  B2Q_LAUNCH_CHECK("rdm_fold_kernel");
+  return B2Q_OK;
 }
 
 // tr(rho P) = sum_i rho[i, i ^ x] * sign(i): only 2^n of rho's 4^n entries are read.
@@ -1192,7 +1519,19 @@ extern "C" int b2q_sv_pauli_expectation_multi(const void* state, int dtype, int 
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const uint64_t total = 1ull << n_qubits;
   B2Q_REQUIRE(x_mask < total, "mask out of range");
-  const unsigned blocks = stride_grid(total, 256);
+  // CIRQ_B200_PAULI_RUNS=0 keeps the amplitude-per-thread kernel (A/B measurements)
+  static const bool runs_enabled = [] {
+    const char* e = std::getenv("CIRQ_B200_PAULI_RUNS");
+    return e == nullptr || e[0] != '0';
+  }();
+  const bool by_runs = runs_enabled && n_qubits >= 12;
+  // runs of 8 amplitudes: run = k * vt + virtual thread, at most kPauliMaxK values of k
+  const uint64_t num_runs = total >> 3;
+  const uint64_t vt =
+      by_runs ? std::min<uint64_t>(num_runs, std::max<uint64_t>(1ull << 18, num_runs / kPauliMaxK)) : 1;
+  const int k_count = (int)(num_runs / vt);
+  const unsigned blocks = by_runs ? (unsigned)std::min<uint64_t>(vt >> 8, 148ull * 4)
+                                  : stride_grid(total, 256);
   for (int t0 = 0; t0 < count; t0 += kPauliMaxTerms) {
     PauliMultiParams p;
     p.count = std::min(kPauliMaxTerms, count - t0);
@@ -1203,7 +1542,19 @@ extern "C" int b2q_sv_pauli_expectation_multi(const void* state, int dtype, int 
     const int width = 2 * p.count;
     double* partial = reinterpret_cast<double*>(workspace(sizeof(double) * width * ((size_t)blocks + 1)));
     if (partial == nullptr) return B2Q_ERR_CUDA;
-    if (dtype == B2Q_C64 && x_mask == 0)
+    if (by_runs && dtype == B2Q_C64 && x_mask == 0)
+      sv_pauli_multi_run_kernel<float, true><<<blocks, 256, 0, s>>>(
+          reinterpret_cast<const float2*>(state), vt, k_count, x_mask, p, partial);
+    else if (by_runs && dtype == B2Q_C64)
+      sv_pauli_multi_run_kernel<float, false><<<blocks, 256, 0, s>>>(
+          reinterpret_cast<const float2*>(state), vt, k_count, x_mask, p, partial);
+    else if (by_runs && x_mask == 0)
+      sv_pauli_multi_run_kernel<double, true><<<blocks, 256, 0, s>>>(
+          reinterpret_cast<const double2*>(state), vt, k_count, x_mask, p, partial);
+    else if (by_runs)
+      sv_pauli_multi_run_kernel<double, false><<<blocks, 256, 0, s>>>(
+          reinterpret_cast<const double2*>(state), vt, k_count, x_mask, p, partial);
+    else if (dtype == B2Q_C64 && x_mask == 0)
       sv_pauli_multi_partial_kernel<float, true><<<blocks, 256, 0, s>>>(
           reinterpret_cast<const float2*>(state), total, x_mask, p, partial);
     else if (dtype == B2Q_C64)
@@ -1255,11 +1606,46 @@ extern "C" int b2q_sv_reduced_density_matrix(const void* state, int dtype, int n
   for (int q = 0; q < 6; ++q) p.pos[q] = q < m ? sorted[q] : 0;
   for (int q = 1; q < m; ++q) B2Q_REQUIRE(sorted[q] != sorted[q - 1], "duplicate bit %d", sorted[q]);
   const int d = 1 << m;
-  double* out_dev = reinterpret_cast<double*>(workspace(sizeof(double) * 2 * d * d));
-  if (out_dev == nullptr) return B2Q_ERR_CUDA;
-  B2Q_CUDA_CHECK(cudaMemsetAsync(out_dev, 0, sizeof(double) * 2 * d * d, s));
-  const int rc = dtype == B2Q_C64 ? reduced_dm_t<float>(state, n_qubits, m, p, out_dev, s)
-                                  : reduced_dm_t<double>(state, n_qubits, m, p, out_dev, s);
+  // CIRQ_B200_RDM_GRAM=0 keeps the row-tile kernel at every size (A/B measurements)
+  static const bool gram_enabled = [] {
+    const char* e = std::getenv("CIRQ_B200_RDM_GRAM");
+    return e == nullptr || e[0] != '0';
+  }();
+  int rc;
+  double* out_dev = nullptr;
+  if (gram_enabled && m >= 3 && n_qubits >= kRdmTileBits) {
+    RdmGramParams gp;
+    int count = 0;
+    for (int b = 0, kept = 0; count < kRdmTileBits; ++b) {  // kept bits + lowest free bits
+      const bool is_kept = std::find(sorted, sorted + m, b) != sorted + m;
+      if (is_kept) ++kept;
+      // a free bit is taken while there is room for the kept bits still to come
+      if (is_kept || count - kept < kRdmTileBits - m) gp.tile_pos[count++] = b;
+    }
+    for (int q = 0; q < 5; ++q)
+      gp.kept_rank[q] =
+          q < m ? (int)(std::find(gp.tile_pos, gp.tile_pos + kRdmTileBits, sorted[q]) - gp.tile_pos) : 0;
+    const uint64_t tiles = 1ull << (n_qubits - kRdmTileBits);
+    const bool f32 = dtype == B2Q_C64;
+    const int ctas = m == 3   ? (f32 ? rdm_gram_grid<float, 3>(tiles) : rdm_gram_grid<double, 3>(tiles))
+                     : m == 4 ? (f32 ? rdm_gram_grid<float, 4>(tiles) : rdm_gram_grid<double, 4>(tiles))
+                              : (f32 ? rdm_gram_grid<float, 5>(tiles) : rdm_gram_grid<double, 5>(tiles));
+    out_dev = reinterpret_cast<double*>(workspace(sizeof(double) * 2 * d * d * (1 + (size_t)ctas)));
+    if (out_dev == nullptr) return B2Q_ERR_CUDA;
+    double* partial = out_dev + 2 * d * d;
+    rc = m == 3   ? (f32 ? reduced_dm_gram_launch<float, 3>(state, n_qubits, gp, ctas, partial, out_dev, s)
+                         : reduced_dm_gram_launch<double, 3>(state, n_qubits, gp, ctas, partial, out_dev, s))
+         : m == 4 ? (f32 ? reduced_dm_gram_launch<float, 4>(state, n_qubits, gp, ctas, partial, out_dev, s)
+                         : reduced_dm_gram_launch<double, 4>(state, n_qubits, gp, ctas, partial, out_dev, s))
+                  : (f32 ? reduced_dm_gram_launch<float, 5>(state, n_qubits, gp, ctas, partial, out_dev, s)
+                         : reduced_dm_gram_launch<double, 5>(state, n_qubits, gp, ctas, partial, out_dev, s));
+  } else {
+    out_dev = reinterpret_cast<double*>(workspace(sizeof(double) * 2 * d * d));
+    if (out_dev == nullptr) return B2Q_ERR_CUDA;
+    B2Q_CUDA_CHECK(cudaMemsetAsync(out_dev, 0, sizeof(double) * 2 * d * d, s));
+    rc = dtype == B2Q_C64 ? reduced_dm_t<float>(state, n_qubits, m, p, out_dev, s)
+                          : reduced_dm_t<double>(state, n_qubits, m, p, out_dev, s);
+  }
   if (rc != B2Q_OK) return rc;
   std::vector<double> h((size_t)2 * d * d);
   B2Q_CUDA_CHECK(cudaMemcpyAsync(h.data(), out_dev, sizeof(double) * 2 * d * d,

@@ -537,6 +537,84 @@ def test_layout_ops_kron_permute_argmax(DS, dtype):
 
 
 @pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
+def test_allclose_and_kron_sizes_and_positions(DS, dtype):
+    """b2q_sv_allclose / b2q_sv_kron_allclose / b2q_sv_kron with 16-byte accesses and
+    four accesses in flight: every size class (scalar, one vector, unroll tails), a
+    violation at the first, an odd and the last index, and np.allclose's threshold
+    (|a - b| <= atol + rtol |b|; reference use: sim/simulation_product_state.py via
+    qis/states.py validate / linalg.allclose_up_to_global_phase call sites)."""
+    rng = np.random.RandomState(72)
+    for n in (1, 2, 3, 5, 10, 13, 17):
+        s = rand_state(rng, n, dtype)
+        dev = DS.from_numpy(s)
+        assert dev.allclose(DS.from_numpy(s.copy()), 1e-7)
+        for pos in sorted({0, (1 << n) // 2 | 1, (1 << n) - 1}):
+            bad = s.copy()
+            bad[pos] += 3e-3
+            assert not dev.allclose(DS.from_numpy(bad), 1e-3, rtol=0.0)
+            assert dev.allclose(DS.from_numpy(bad), 1e-2, rtol=0.0)
+            # the relative term: |bad[pos]| <= 1.1, so rtol = 1 admits nothing below 3e-3 only if
+            # |bad[pos]| < 3e-3; a huge rtol admits everything non-zero
+            assert dev.allclose(DS.from_numpy(bad), 1e-9, rtol=1e3) == bool(
+                np.all(np.abs(s.astype(np.complex128) - bad) <= 1e-9 + 1e3 * np.abs(bad.astype(np.complex128))))
+    for na, nb in ((1, 1), (3, 1), (1, 4), (4, 7), (9, 2), (2, 12), (8, 8)):
+        a = rand_state(rng, na, dtype)
+        b = rand_state(rng, nb, dtype)
+        k = DS.from_numpy(a).kron(DS.from_numpy(b))
+        want = np.kron(a, b)
+        np.testing.assert_allclose(k.to_numpy(), want, atol=ATOL[np.dtype(dtype)])
+        t = DS.from_numpy(want.astype(dtype))
+        assert t.kron_allclose(DS.from_numpy(a), DS.from_numpy(b), 1e-6)
+        for pos in sorted({0, (1 << (na + nb)) - 1, (1 << (na + nb)) // 3 | 1}):
+            wrong = want.astype(dtype).copy()
+            wrong[pos] += 5e-3
+            assert not DS.from_numpy(wrong).kron_allclose(DS.from_numpy(a), DS.from_numpy(b), 1e-3, rtol=0.0)
+            assert DS.from_numpy(wrong).kron_allclose(DS.from_numpy(a), DS.from_numpy(b), 1e-2, rtol=0.0)
+
+
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
+def test_reduced_density_matrix_gram_kernel_positions(DS, dtype):
+    """The one-read Gram kernel (3-5 kept bits, >= 11 qubits) for kept bits at the
+    bottom, at the top, straddling the tile, and in the caller's order; against
+    qis/states.py:676-693 restated, and against the row-tile kernel's size class."""
+    rng = np.random.default_rng(15)
+    tol = 2e-6 if dtype == np.complex64 else 1e-13
+    for n in (11, 12, 16, 22):
+        psi = rand_state(rng, n, dtype)
+        dev = DS.from_numpy(psi, dtype)
+        cases = [[0, 1, 2], [2, 1, 0, 3], [4, 3, 2, 1, 0], [n - 1, n - 2, n - 3], [n - 3, n - 1, n - 2, n - 5, n - 4],
+                 [0, n - 1, 5], [n - 1, 0, 6, 3], [9, 0, n - 1, 7, 3], [8, 9, 10, 7]]
+        for bits in cases:
+            got = dev.reduced_density_matrix(bits)
+            want = orc.reduced_density_matrix(psi, n, bits)
+            np.testing.assert_allclose(got, want, atol=tol, rtol=0)
+            np.testing.assert_allclose(got, got.conj().T, atol=tol, rtol=0)  # (a,b) and (b,a) are summed by different threads
+        again = dev.reduced_density_matrix(cases[-2])
+        np.testing.assert_array_equal(again, dev.reduced_density_matrix(cases[-2]))  # fixed summation order
+
+
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
+def test_pauli_expectations_on_states_that_walk_the_sign_table(DS, dtype):
+    """b2q_sv_pauli_expectation_multi above 2^21 amplitudes: a thread walks several runs
+    and the signs of the index bits above the virtual-thread bits come from the
+    per-CTA table (n = 22: two steps per thread).  The oracle (seconds per string at this
+    size) checks three strings per X mask, the one-string kernel all of them."""
+    rng = np.random.RandomState(33)
+    tol = 2e-6 if dtype == np.complex64 else 1e-12
+    for n in (12, 22):
+        state = rand_state(rng, n, dtype)
+        dev = DS.from_numpy(state)
+        top = (1 << (n - 1)) | (1 << (n - 2))
+        for x in (0, (1 << (n - 1)) | int(rng.randint(0, 1 << (n - 1))) | 5):
+            zs = [int(v) for v in rng.randint(0, 1 << n, size=15)] + [top, (1 << n) - 1, 0, 7, top | 7]
+            got = dev.pauli_expectations(x, zs)
+            for i in (0, 15, 19):
+                assert abs(got[i] - orc.pauli_expectation(state, n, x, zs[i])) < tol, (n, x, zs[i])
+            for z, v in zip(zs, got):
+                assert abs(v - dev.pauli_expectation(x, z)) < tol, (n, x, z)
+
+
+@pytest.mark.parametrize('dtype', [np.complex64, np.complex128])
 def test_dist_pack_unpack(DS, dtype):
     import torch
 

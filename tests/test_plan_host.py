@@ -417,6 +417,39 @@ def test_library_exports_every_symbol_the_header_declares():
     assert isinstance(lib.b2q_last_error(), bytes)
 
 
+def test_read_out_entry_points_plan_without_crashing_at_every_size():
+    """The host half of the read-out entry points (grid and table planning: virtual
+    threads of the multi-string Pauli kernel, the reduced-density-matrix tile bits,
+    vector widths of kron / allclose) runs before any launch.  On a machine without a
+    device the calls must come back with an error code at every register size — a
+    division by the zero runs of a 1-qubit state once took the process down."""
+    import ctypes
+
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip('the device tests cover these calls where a GPU exists')
+    lib = _lib.load()
+    buf = np.zeros(1 << 12, dtype=np.complex128)
+    ptr = ctypes.c_void_p(buf.ctypes.data)
+    out = (ctypes.c_double * 4096)()
+    zs = (ctypes.c_uint64 * 3)(1, 0, 1)
+    ok = ctypes.c_int()
+    for code in (_lib.C64, _lib.C128):
+        for n in list(range(1, 24)) + [28, 34]:
+            for x in (0, 1):
+                assert lib.b2q_sv_pauli_expectation_multi(ptr, code, n, x, zs, 3, out, None) != 0
+            for m in range(1, min(n, 5) + 1):
+                bits = (ctypes.c_int * 5)(*([n - 1, 0, 2, 1, 3][:m] + [0] * (5 - m)))
+                if len(set(bits[:m])) == m and max(bits[:m]) < n:
+                    assert lib.b2q_sv_reduced_density_matrix(ptr, code, n, bits, m, out, None) != 0
+            assert lib.b2q_sv_allclose(ptr, ptr, code, n, 1e-6, 1e-5, ctypes.byref(ok), None) != 0
+        for na, nb in ((0, 0), (0, 1), (1, 0), (3, 2), (12, 1)):
+            assert lib.b2q_sv_kron_allclose(ptr, na, ptr, nb, ptr, code, 1e-6, 1e-5, ctypes.byref(ok), None) != 0
+            assert lib.b2q_sv_kron(ptr, na, ptr, nb, code, ptr, None) != 0
+    assert lib.b2q_last_error()
+
+
 # ---- tile kernel (two blocks per HBM pass): replay of its address tables ----------------
 
 def _tile_slot(local, xmask):

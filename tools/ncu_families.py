@@ -84,6 +84,9 @@ def calls(n, DS, torch):
                 lambda: dev.apply_tile_blocks([(u5a, [n - 1, 17, 9, 5, 12]), (u5b, [22, 9, n - 4, 14, 3])])))
     other = dev.copy()
     out.append(('allclose (sv_allclose_kernel)', 2 * amp, lambda: dev.allclose(other, 1e-6)))
+    joined = a.kron(b10)
+    out.append(('kron allclose 2^(n-10) x 2^10 (sv_kron_mismatch_kernel)', amp + (8 << (n - 10)),
+                lambda: joined.kron_allclose(a, b10, 1e-6)))
     # density matrix view of the same array: n/2 qubits
     nq = n // 2
     rho = DS.basis(2 * nq, np.complex64, 0)
@@ -134,7 +137,10 @@ def run(args):
     from cirq_b200.device_state import DeviceState as DS
 
     rows = []
+    only = [w for w in args.only.split(',') if w]
     for label, nbytes, fn in calls(args.n, DS, torch):
+        if only and not any(w in label for w in only):
+            continue
         fn()  # warm (allocations, attribute setup)
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -209,5 +215,6 @@ if __name__ == '__main__':
     ap.add_argument('--n', type=int, default=28)
     ap.add_argument('--out', default='')
     ap.add_argument('--summarise', default='')
+    ap.add_argument('--only', default='', help='comma-separated substrings of the call labels to run')
     a = ap.parse_args()
     summarise(a) if a.summarise else run(a)
