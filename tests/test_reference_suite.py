@@ -89,10 +89,31 @@ USER_MODULES = [
     'contrib/quantum_volume/quantum_volume_test.py', 'experiments/n_qubit_tomography_test.py',
     'contrib/bayesian_network/bayesian_network_gate_test.py',
     'transformers/analytical_decompositions/single_to_two_qubit_isometry_test.py', 'study/result_test.py',
+    # samplers, calibration and characterisation experiments, readout mitigation, state-vector and
+    # density-matrix utilities (sampling / measurement helpers used with simulator output)
+    'contrib/ghz/fidelity_test.py', 'contrib/paulistring/pauli_string_measurement_with_readout_mitigation_test.py',
+    'contrib/shuffle_circuits/shuffle_circuits_with_readout_benchmarking_test.py',
+    'experiments/qubit_characterizations_test.py', 'experiments/single_qubit_readout_calibration_test.py',
+    'experiments/t1_decay_experiment_test.py', 'experiments/t2_decay_experiment_test.py',
+    'experiments/xeb_fitting_test.py', 'experiments/xeb_sampling_test.py',
+    'work/observable_readout_calibration_test.py', 'work/sampler_test.py', 'sim/state_vector_test.py',
+    'sim/density_matrix_utils_test.py',
 ]
 USER_EXPECTED_FAIL = {  # qudits: the kernels are qubit-only
     'test_sympy_qudits', 'test_xpow_dim_3', 'test_xpow_dim_4', 'test_zpow_dim_3', 'test_zpow_dim_4',
     'test_qudits', 'test_sympy_control_complex_qudit', 'test_confusion_map_qudits', 'test_drop_terminal_qudit',
+}
+
+
+# These fail identically with the STOCK cirq.Simulator in this image: matplotlib and duet are
+# inert stand-ins here (cirq_b200/_cirq_compat.py: plotting, async fan-out), and the deprecation
+# tests count log records that this runner's `-W ignore` suppresses.
+ENVIRONMENT_EXPECTED_FAIL = {
+    'test_deprecated_run_shuffled_with_readout_benchmarking', 'test_single_qubit_randomized_benchmarking',
+    'test_parallel_single_qubit_parallel_single_qubit_randomized_benchmarking',
+    'test_parallel_single_qubit_randomized_benchmarking_with_noise',
+    'test_estimate_parallel_readout_errors_with_noise', 'test_plot_does_not_raise_error',
+    'test_curve_fit_plot_works', 'test_run_sweep_impl', 'test_run_batch_async_calls_run_sweep_asynchronously',
 }
 
 
@@ -110,7 +131,7 @@ def test_reference_user_modules_host_logic(tmp_path):
     with open(out) as f:
         outcomes = json.load(f)
     failed = sorted(k for k, v in outcomes.items() if v not in ('passed', 'skipped'))
-    unexpected = [k for k in failed if k.split('[')[0] not in USER_EXPECTED_FAIL]
+    unexpected = [k for k in failed if k.split('[')[0] not in USER_EXPECTED_FAIL | ENVIRONMENT_EXPECTED_FAIL]
     passed = sum(1 for v in outcomes.values() if v == 'passed')
     assert not unexpected, f'unexpected reference-test failures: {unexpected}'
-    assert passed >= 690, f'only {passed} reference tests passed'  # (same-named tests of different modules count once)
+    assert passed >= 975, f'only {passed} reference tests passed'  # (same-named tests of different modules count once)
