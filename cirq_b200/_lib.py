@@ -132,6 +132,8 @@ DEBUG_SIGNATURES = {
     'b2q_debug_permute_plan': (c_int, [c_int, c_int, POINTER(c_int), c_int, POINTER(c_int), POINTER(c_int)]),
     'b2q_debug_tile_plan': (c_int, [c_int, c_int, POINTER(c_int), POINTER(ctypes.c_int64)]),
     'b2q_debug_permute_matrix': (c_int, [c_void_p, POINTER(c_int), c_int, c_void_p]),
+    'b2q_debug_rdm_plan': (c_int, [c_int, POINTER(c_int), c_int, POINTER(ctypes.c_int64)]),
+    'b2q_debug_pauli_plan': (c_int, [c_int, POINTER(ctypes.c_int64)]),
 }
 
 

@@ -772,6 +772,25 @@ __global__ void __launch_bounds__(256)
   if (tid < 2 * p.count) partial[(size_t)blockIdx.x * 2 * p.count + tid] = column_total;
 }
 
+// Launch shape of the run kernel: run = k * vt + virtual thread, at most kPauliMaxK values
+// of k, vt >= 2^18 virtual threads for big states (enough virtual CTAs for every SM).
+struct PauliRunPlan {
+  bool by_runs;
+  uint64_t vt;
+  int k_count;
+  unsigned blocks;
+};
+static PauliRunPlan pauli_run_plan(int n_qubits, bool runs_enabled) {
+  PauliRunPlan r;
+  const uint64_t total = 1ull << n_qubits;
+  r.by_runs = runs_enabled && n_qubits >= 12;
+  const uint64_t num_runs = total >> 3;
+  r.vt = r.by_runs ? std::min<uint64_t>(num_runs, std::max<uint64_t>(1ull << 18, num_runs / kPauliMaxK)) : 1;
+  r.k_count = (int)(num_runs / r.vt);
+  r.blocks = r.by_runs ? (unsigned)std::min<uint64_t>(r.vt >> 8, 148ull * 4) : 0;
+  return r;
+}
+
 // out[j] = sum_b partial[b * width + j]
 __global__ void __launch_bounds__(256)
     column_sum_kernel(const double* __restrict__ partial, uint64_t blocks, int width,
@@ -904,6 +923,41 @@ struct RdmGramParams {
   int kept_rank[5];            // kept bit q (ascending position) = tile bit kept_rank[q]
 };
 
+// Element e (11 bits, tile bits ascending) of a tile: offset of its amplitude from the
+// tile's base, and its slot in the staged tile X[rest][a] (a = the kept bits, LSB first).
+B2Q_HD uint64_t rdm_tile_offset(const RdmGramParams& p, int e) {
+  uint64_t off = 0;
+  for (int j = 0; j < kRdmTileBits; ++j) off |= (uint64_t)((e >> j) & 1) << p.tile_pos[j];
+  return off;
+}
+B2Q_HD int rdm_tile_slot(const RdmGramParams& p, int m, int e) {
+  int a = 0, kept = 0;
+  for (int q = 0; q < m; ++q) {
+    a |= ((e >> p.kept_rank[q]) & 1) << q;
+    kept |= 1 << p.kept_rank[q];
+  }
+  int rest = 0, f = 0;
+  for (int j = 0; j < kRdmTileBits; ++j)
+    if (!((kept >> j) & 1)) rest |= ((e >> j) & 1) << f++;
+  return (rest << m) | a;
+}
+
+// Tile bits of a reduction over the ascending kept bits `sorted`: the kept bits and the
+// lowest free bits (a free bit is taken while there is room for the kept bits to come).
+static RdmGramParams rdm_gram_plan(const int* sorted, int m) {
+  RdmGramParams gp;
+  int count = 0;
+  for (int b = 0, kept = 0; count < kRdmTileBits; ++b) {
+    const bool is_kept = std::find(sorted, sorted + m, b) != sorted + m;
+    if (is_kept) ++kept;
+    if (is_kept || count - kept < kRdmTileBits - m) gp.tile_pos[count++] = b;
+  }
+  for (int q = 0; q < 5; ++q)
+    gp.kept_rank[q] =
+        q < m ? (int)(std::find(gp.tile_pos, gp.tile_pos + kRdmTileBits, sorted[q]) - gp.tile_pos) : 0;
+  return gp;
+}
+
 template <typename real>
 __device__ __forceinline__ void rdm_mac(typename Cplx<real>::type& acc,
                                         const typename Cplx<real>::type& xa,
@@ -942,22 +996,8 @@ __global__ void __launch_bounds__(256)
 
   const int t = threadIdx.x;
   // element e = t | (k << 8) of a tile: its offset in the state and its slot X[rest][a]
-  auto offset_of = [&](int e) {
-    uint64_t off = 0;
-    for (int j = 0; j < kRdmTileBits; ++j) off |= (uint64_t)((e >> j) & 1) << p.tile_pos[j];
-    return off;
-  };
-  auto slot_of = [&](int e) {
-    int a = 0, kept = 0;
-    for (int q = 0; q < M; ++q) {
-      a |= ((e >> p.kept_rank[q]) & 1) << q;
-      kept |= 1 << p.kept_rank[q];
-    }
-    int rest = 0, f = 0;
-    for (int j = 0; j < kRdmTileBits; ++j)
-      if (!((kept >> j) & 1)) rest |= ((e >> j) & 1) << f++;
-    return rest * D + a;
-  };
+  auto offset_of = [&](int e) { return rdm_tile_offset(p, e); };
+  auto slot_of = [&](int e) { return rdm_tile_slot(p, M, e); };
   const uint64_t t_off = offset_of(t);
   const int t_slot = slot_of(t);
   if (t < kLoads) {
@@ -1524,14 +1564,11 @@ extern "C" int b2q_sv_pauli_expectation_multi(const void* state, int dtype, int 
     const char* e = std::getenv("CIRQ_B200_PAULI_RUNS");
     return e == nullptr || e[0] != '0';
   }();
-  const bool by_runs = runs_enabled && n_qubits >= 12;
-  // runs of 8 amplitudes: run = k * vt + virtual thread, at most kPauliMaxK values of k
-  const uint64_t num_runs = total >> 3;
-  const uint64_t vt =
-      by_runs ? std::min<uint64_t>(num_runs, std::max<uint64_t>(1ull << 18, num_runs / kPauliMaxK)) : 1;
-  const int k_count = (int)(num_runs / vt);
-  const unsigned blocks = by_runs ? (unsigned)std::min<uint64_t>(vt >> 8, 148ull * 4)
-                                  : stride_grid(total, 256);
+  const PauliRunPlan plan = pauli_run_plan(n_qubits, runs_enabled);
+  const bool by_runs = plan.by_runs;
+  const uint64_t vt = plan.vt;
+  const int k_count = plan.k_count;
+  const unsigned blocks = by_runs ? plan.blocks : stride_grid(total, 256);
   for (int t0 = 0; t0 < count; t0 += kPauliMaxTerms) {
     PauliMultiParams p;
     p.count = std::min(kPauliMaxTerms, count - t0);
@@ -1614,17 +1651,7 @@ extern "C" int b2q_sv_reduced_density_matrix(const void* state, int dtype, int n
   int rc;
   double* out_dev = nullptr;
   if (gram_enabled && m >= 3 && n_qubits >= kRdmTileBits) {
-    RdmGramParams gp;
-    int count = 0;
-    for (int b = 0, kept = 0; count < kRdmTileBits; ++b) {  // kept bits + lowest free bits
-      const bool is_kept = std::find(sorted, sorted + m, b) != sorted + m;
-      if (is_kept) ++kept;
-      // a free bit is taken while there is room for the kept bits still to come
-      if (is_kept || count - kept < kRdmTileBits - m) gp.tile_pos[count++] = b;
-    }
-    for (int q = 0; q < 5; ++q)
-      gp.kept_rank[q] =
-          q < m ? (int)(std::find(gp.tile_pos, gp.tile_pos + kRdmTileBits, sorted[q]) - gp.tile_pos) : 0;
+    const RdmGramParams gp = rdm_gram_plan(sorted, m);
     const uint64_t tiles = 1ull << (n_qubits - kRdmTileBits);
     const bool f32 = dtype == B2Q_C64;
     const int ctas = m == 3   ? (f32 ? rdm_gram_grid<float, 3>(tiles) : rdm_gram_grid<double, 3>(tiles))
@@ -1816,4 +1843,41 @@ extern "C" int b2q_dist_pack(const void* shard, int dtype, int n_local, const in
 extern "C" int b2q_dist_unpack(void* shard, int dtype, int n_local, const int* local_bits, int g,
                                const void* packed, void* stream) {
   return pack_common(shard, dtype, n_local, local_bits, g, const_cast<void*>(packed), 1, stream);
+}
+
+// Host-only (tests/test_plan_host.py): the Gram kernel's tile plan for kept bits `bits`
+// (any order) — out[0..10] tile bits, out[11..15] rank of kept bit q in the tile, then for
+// each of the 2^11 tile elements e: out[16 + 2e] = offset from the tile base,
+// out[17 + 2e] = slot in the staged tile X[rest][a].
+extern "C" int b2q_debug_rdm_plan(int n_qubits, const int* bits, int m, int64_t* out) {
+  B2Q_REQUIRE(bits != nullptr && out != nullptr, "null argument");
+  B2Q_REQUIRE(m >= 3 && m <= 5 && n_qubits >= kRdmTileBits && n_qubits <= 40, "not a Gram-kernel shape");
+  int sorted[5];
+  for (int q = 0; q < m; ++q) {
+    B2Q_REQUIRE(bits[q] >= 0 && bits[q] < n_qubits, "bit %d out of range", bits[q]);
+    sorted[q] = bits[q];
+  }
+  std::sort(sorted, sorted + m);
+  for (int q = 1; q < m; ++q) B2Q_REQUIRE(sorted[q] != sorted[q - 1], "duplicate bit %d", sorted[q]);
+  const RdmGramParams gp = rdm_gram_plan(sorted, m);
+  for (int j = 0; j < kRdmTileBits; ++j) out[j] = gp.tile_pos[j];
+  for (int q = 0; q < 5; ++q) out[kRdmTileBits + q] = gp.kept_rank[q];
+  for (int e = 0; e < (1 << kRdmTileBits); ++e) {
+    out[16 + 2 * e] = (int64_t)rdm_tile_offset(gp, e);
+    out[17 + 2 * e] = rdm_tile_slot(gp, m, e);
+  }
+  return B2Q_OK;
+}
+
+// Host-only: launch shape of b2q_sv_pauli_expectation_multi at this register size —
+// out[0] = 1 when the run kernel is used, out[1] = virtual threads, out[2] = runs per
+// virtual thread (steps of the sign table), out[3] = CTAs.
+extern "C" int b2q_debug_pauli_plan(int n_qubits, int64_t* out) {
+  B2Q_REQUIRE(out != nullptr && n_qubits >= 1 && n_qubits <= 40, "bad argument");
+  const PauliRunPlan plan = pauli_run_plan(n_qubits, true);
+  out[0] = plan.by_runs ? 1 : 0;
+  out[1] = (int64_t)plan.vt;
+  out[2] = plan.k_count;
+  out[3] = plan.blocks;
+  return B2Q_OK;
 }

@@ -440,6 +440,13 @@ int b2q_debug_tile_plan(int n_qubits, int num_blocks, const int* sorted_targets,
 /* Host-only: address tables of the staged tensor-core kernel for ascending
  * targets (layout of `out`, 86 int64: see tests/test_plan_host.py). */
 int b2q_debug_tc_stage_plan(int n_qubits, const int* sorted_targets, int k, int64_t* out);
+/* Host-only: tile plan of the one-read reduced-density-matrix kernel for 3-5 kept
+ * bits of a register of >= 11 qubits (layout of `out`, 16 + 2 * 2048 int64: tile bits,
+ * kept-bit ranks, then offset and shared-memory slot of every tile element). */
+int b2q_debug_rdm_plan(int n_qubits, const int* bits, int m, int64_t* out);
+/* Host-only: launch shape of b2q_sv_pauli_expectation_multi (out[4]: run kernel used,
+ * virtual threads, runs per virtual thread, CTAs). */
+int b2q_debug_pauli_plan(int n_qubits, int64_t* out);
 
 #ifdef __cplusplus
 }

@@ -450,6 +450,119 @@ def test_read_out_entry_points_plan_without_crashing_at_every_size():
     assert lib.b2q_last_error()
 
 
+# ---- read-out kernels: replay of their host plans ----------------------------------------
+
+def _insert_zero_bits(x, positions):
+    for pos in positions:
+        x = ((x >> pos) << (pos + 1)) | (x & ((1 << pos) - 1))
+    return x
+
+
+@pytest.mark.parametrize('m', [3, 4, 5])
+def test_reduced_density_matrix_tile_plan_replays_to_the_oracle(m):
+    """b2q_debug_rdm_plan = the tile plan sv_reduced_dm_gram_kernel runs on (the same
+    functions compute the offsets and slots on the device).  Replayed here: the tiles
+    cover every amplitude once, a tile's slots are a bijection onto X[rest][a], the
+    per-thread / per-load split of an element index is an OR of its parts, and the Gram
+    sums of the staged tiles are the reference's reduced density matrix
+    (qis/states.py:676-693 via the oracle)."""
+    import ctypes
+
+    lib = _lib.load()
+    rng = np.random.default_rng(40 + m)
+    for n in (11, 12, 14):
+        psi = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+        psi /= np.linalg.norm(psi)
+        cases = [rng.permutation(n)[:m].tolist() for _ in range(4)]
+        cases += [list(range(m)), list(range(n - 1, n - 1 - m, -1)), [n - 1, 0, 5, 9, 2][:m]]
+        for bits in cases:
+            out = (ctypes.c_int64 * (16 + 2 * 2048))()
+            assert lib.b2q_debug_rdm_plan(n, (ctypes.c_int * m)(*bits), m, out) == 0, lib.b2q_last_error()
+            plan = np.array(out[:], dtype=np.int64)
+            tile_pos, kept_rank = plan[:11].tolist(), plan[11:11 + m].tolist()
+            offs, slots = plan[16::2], plan[17::2]
+            assert tile_pos == sorted(set(tile_pos)) and max(tile_pos) < n
+            assert set(sorted(bits)) <= set(tile_pos)
+            free = [b for b in tile_pos if b not in bits]
+            assert free == [b for b in range(n) if b not in bits][:11 - m]  # the LOWEST free bits
+            assert [tile_pos[r] for r in kept_rank] == sorted(bits)
+            assert sorted(slots.tolist()) == list(range(2048))
+            for t in (0, 77, 255):
+                for k in range(8):  # thread part | load part
+                    assert offs[t | (k << 8)] == offs[t] | offs[k << 8]
+                    assert slots[t | (k << 8)] == slots[t] | slots[k << 8]
+            d = 1 << m
+            rho = np.zeros((d, d), dtype=np.complex128)
+            seen = np.zeros(1 << n, dtype=np.int64)
+            for tile in range(1 << (n - 11)):
+                base = _insert_zero_bits(tile, tile_pos)
+                staged = np.zeros(2048, dtype=np.complex128)
+                staged[slots] = psi[base + offs]
+                seen[base + offs] += 1
+                x = staged.reshape(2048 // d, d)
+                rho += x.T @ x.conj()
+            assert np.all(seen == 1)
+            srt = sorted(bits)
+            to_kernel = [sum(((idx >> (m - 1 - q)) & 1) << srt.index(bits[q]) for q in range(m)) for idx in range(d)]
+            got = rho[np.ix_(to_kernel, to_kernel)]
+            np.testing.assert_allclose(got, orc.reduced_density_matrix(psi, n, bits), atol=1e-13, rtol=0)
+    assert lib.b2q_debug_rdm_plan(10, (ctypes.c_int * 3)(0, 1, 2), 3, out) != 0
+    assert lib.b2q_debug_rdm_plan(12, (ctypes.c_int * 3)(0, 1, 1), 3, out) != 0
+
+
+def test_pauli_run_plan_sign_decomposition_matches_the_oracle():
+    """b2q_debug_pauli_plan = the launch shape of sv_pauli_multi_run_kernel.  Replayed with
+    numpy: run r = k * vt + g, Walsh-Hadamard transform of the run's 8 pair products,
+    W[z & 7], the sign of g's bits applied per walk and the sign of k's bits from the
+    table — equal to ops/pauli_string.py:625-655 restated (the oracle), at sizes with
+    one and with several steps per virtual thread."""
+    import ctypes
+
+    lib = _lib.load()
+    out = (ctypes.c_int64 * 4)()
+    shapes = {}
+    for n in range(1, 35):
+        assert lib.b2q_debug_pauli_plan(n, out) == 0
+        by_runs, vt, k_count, blocks = out[:]
+        shapes[n] = (by_runs, vt, k_count, blocks)
+        if n < 12:
+            assert not by_runs
+            continue
+        runs = (1 << n) >> 3
+        assert by_runs and vt * k_count == runs and vt & (vt - 1) == 0 and vt >= 256
+        assert 1 <= k_count <= 128 and 1 <= blocks <= min(vt >> 8, 148 * 4)
+    assert shapes[21][2] == 1 and shapes[22][2] == 2 and shapes[28][2] == 128 and shapes[34][2] == 128
+    had = np.array([[(-1) ** bin(j & w).count('1') for j in range(8)] for w in range(8)], dtype=np.float64)
+    parity = lambda v: np.array([bin(int(x)).count('1') & 1 for x in v])  # noqa: E731
+    rng = np.random.default_rng(9)
+    for n, (vt, k_count) in ((12, (shapes[12][1], shapes[12][2])), (13, (256, 4)), (22, (shapes[22][1], shapes[22][2]))):
+        psi = (rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)).astype(np.complex128)
+        psi /= np.linalg.norm(psi)
+        g = np.arange(vt, dtype=np.int64)
+        for x in (0, (1 << (n - 1)) | 6):
+            i = np.arange(1 << n, dtype=np.int64)
+            prod = (np.conj(psi[i ^ x]) * psi).reshape(-1, 8)  # pair products by run
+            w = prod @ had.T  # w[r, m] = sum_j (-1)^popcount(j & m) prod[r, j]
+            for z in [int(v) for v in rng.integers(0, 1 << n, size=3)] + [(1 << n) - 1, 7, 1 << (n - 1)]:
+                col = w[:, z & 7].reshape(k_count, vt)  # [k][g]
+                if n <= 13:
+                    flip = parity((np.arange(k_count, dtype=np.int64) * vt << 3) & z)
+                    fixed = parity((g << 3) & z)
+                else:  # (vectorised parity for the big case)
+                    kk = (np.arange(k_count, dtype=np.int64) * vt << 3) & z
+                    gg = (g << 3) & z
+                    flip = np.array([bin(int(v)).count('1') & 1 for v in kk])
+                    gb = gg.copy()
+                    fixed = np.zeros_like(gb)
+                    while gb.any():
+                        fixed ^= gb & 1
+                        gb >>= 1
+                walk = (np.where(flip[:, None] == 1, -col, col)).sum(axis=0)  # one virtual thread's walk
+                value = np.where(fixed == 1, -walk, walk).sum()
+                value *= 1j ** (bin(x & z).count('1') & 3)
+                assert abs(value - orc.pauli_expectation(psi, n, x, z)) < 1e-11, (n, x, z)
+
+
 # ---- tile kernel (two blocks per HBM pass): replay of its address tables ----------------
 
 def _tile_slot(local, xmask):
