@@ -44,7 +44,9 @@ cpu_baseline  the reference (cirq.Simulator / cirq.DensityMatrixSimulator) on th
 `--impl reference` runs ONLY the unmodified reference (no library of this repo is
 loaded): its top-level value is measured on a sample (`same_config: false`,
 `extrapolated: true` in `config`), and `configs.rqc24` is the like-for-like entry
-(`same_config: true`) that the repo arm also reports.
+(`same_config: true`) that the repo arm also reports.  With `--gpus N` > 1 it mirrors
+the sharded line instead: workload `rc_hbm` (cirq.testing.random_circuit, same seed) on a
+24-qubit sample, counted in 30-qubit-equivalent gates like `cirq_b200/dist_bench.py`.
 """
 from __future__ import annotations
 
@@ -71,6 +73,8 @@ WORKLOADS = {
     'qft24': ('qft', dict(n=24), 0),
     'qft22': ('qft', dict(n=22), 0),
     'rc20': ('rc', dict(n=20, depth=20, seed=1234), 0),
+    # sample of the sharded workload `rc_hbm` (same generator and seed, 24 qubits) for the reference arm
+    'rc24': ('rc', dict(n=24, depth=20, seed=1234), 0),
     # the headline circuit in complex128 (17 GB state, register-tiled fp64 kernels: no
     # tensor-core path for double precision)
     'rqc30_c128': ('rqc', dict(rows=5, cols=6, depth=20, seed=1), 1_000_000),
@@ -80,7 +84,7 @@ WORKLOADS = {
     'qaoa8': ('qaoa', dict(n=8, p=2, graph_seed=0, noise=0.01, resolvers=256), 1000),
 }
 # bounded CPU samples (same generator, fewer qubits): ~5-20 s of reference time in all
-CPU_SAMPLE = {'rqc30': 'rqc20', 'rqc30_c128': 'rqc20', 'rqc24': 'rqc20', 'rqc20': 'rqc20', 'qft34': 'qft22', 'qft30': 'qft22',
+CPU_SAMPLE = {'rc24': 'rc20', 'rqc30': 'rqc20', 'rqc30_c128': 'rqc20', 'rqc24': 'rqc20', 'rqc20': 'rqc20', 'qft34': 'qft22', 'qft30': 'qft22',
               'qft24': 'qft22', 'qft22': 'qft22', 'rc20': 'rc20', 'qaoa16': 'qaoa10', 'qaoa12': 'qaoa10',
               'qaoa10': 'qaoa10', 'qaoa8': 'qaoa8'}
 # the reference arm (`--impl reference`) has minutes, not seconds: a larger sample
@@ -117,11 +121,14 @@ def workload_bits(workload):
     return 2 * params['n'] if kind == 'qaoa' else params['n']
 
 
+SHARDED_EQUIVALENT_BITS = 30  # the N > 1 lines count 30-qubit-equivalent gates (cirq_b200/dist_bench.py)
+
+
 def workload_equivalent(value, bits_sample, workload):
     """gates/s measured on a sample with 2^bits_sample amplitudes -> gates/s in
     units of the workload's state size (a pass over 2^m amplitudes = 2^(m-n)
-    workload gates)."""
-    n = workload_bits(workload)
+    workload gates); the sharded workloads are counted in 30-qubit equivalents."""
+    n = SHARDED_EQUIVALENT_BITS if workload in ('rc_hbm', 'rqc_weak') else workload_bits(workload)
     return value * 2.0 ** (bits_sample - n), n
 
 
@@ -357,14 +364,22 @@ def run_reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    workload = 'rqc30' if args.workload in (None, 'rc_hbm', 'rqc_weak') else args.workload
-    sample = REFERENCE_ARM_SAMPLE[workload]
-    big = sample != CPU_SAMPLE[workload]  # ~55 s per step: keep the run within minutes
-    steps = max(1, min(args.steps, 2 if big else 3))
-    warmup = 0 if big else min(args.warmup, 1)
+    if args.workload == 'rc_hbm' or (args.workload is None and args.gpus > 1):
+        # the repo arm's N > 1 workload: cirq.testing.random_circuit at 34 + log2(N) qubits,
+        # counted in 30-qubit-equivalent gates; here the same generator and seed at 24 qubits
+        workload, sample = 'rc_hbm', 'rc24'
+        steps, warmup = max(1, min(args.steps, 3)), 0
+    else:
+        workload = 'rqc30' if args.workload in (None, 'rqc_weak') else args.workload
+        sample = REFERENCE_ARM_SAMPLE[workload]
+        big = sample != CPU_SAMPLE[workload]  # ~55 s per step: keep the run within minutes
+        steps = max(1, min(args.steps, 2 if big else 3))
+        warmup = 0 if big else min(args.warmup, 1)
     line = reference_entry(sample, workload, steps, warmup)
     line.update({'n_gpus': args.gpus, 'scaling': 'weak', 'vs_baseline': None, 'gpu_launches': 0})
-    if sample != workload:
+    if workload == 'rc_hbm':
+        line['config']['n_qubits_of_the_repo_arm'] = 34 + max(args.gpus, 1).bit_length() - 1
+    elif sample != workload:
         # the like-for-like entry: the repo arm reports configs[sample] on the SAME
         # circuit, repetitions and gate unit (no extrapolation)
         sub = reference_entry(sample, sample, steps, warmup)

@@ -29,6 +29,29 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert line['e2e']['h2d_bytes_per_step'] == 0 and line['e2e']['d2h_bytes_per_step'] == 0
 
 
+def test_reference_arm_of_the_sharded_line_uses_the_sharded_workload():
+    """`--impl reference --gpus N` (N > 1) mirrors the repo arm's N > 1 line: workload
+    `rc_hbm` (cirq.testing.random_circuit, same seed) on a 24-qubit sample, counted in
+    30-qubit-equivalent gates like cirq_b200/dist_bench.py; rank 0 alone prints."""
+    env = dict(os.environ, RANK='1', WORLD_SIZE='2', LOCAL_RANK='1')
+    idle = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2',
+                           '--steps', '1', '--warmup', '0'], capture_output=True, text=True, timeout=600,
+                          cwd=ROOT, env=env)
+    assert idle.returncode == 0 and idle.stdout.strip() == ''
+    proc = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2',
+                           '--steps', '1', '--warmup', '0'], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [ln for ln in proc.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, proc.stdout
+    line = json.loads(lines[0])
+    assert line['impl'] == 'reference' and line['n_gpus'] == 2 and line['scaling'] == 'weak'
+    cfg = line['config']
+    assert cfg['workload'] == 'rc_hbm' and cfg['reference_sample'] == 'rc24' and cfg['n_qubits'] == 24
+    assert cfg['extrapolated'] is True and cfg['n_qubits_of_the_repo_arm'] == 35
+    assert abs(line['value'] - cfg['gates_per_s_on_sample'] * 2.0 ** (24 - 30)) < 1e-12
+    assert line['e2e']['value'] == line['value'] and line['cpu_baseline']['value'] == line['value']
+
+
 def test_workload_equivalent_units():
     sys.path.insert(0, ROOT)
     import bench
@@ -38,6 +61,8 @@ def test_workload_equivalent_units():
     assert n == 30 and abs(value - 1.0) < 1e-12
     value, n = bench.workload_equivalent(5.0, 20, 'rc20')
     assert n == 20 and value == 5.0
+    value, n = bench.workload_equivalent(64.0, 24, 'rc_hbm')  # the sharded lines count 30-qubit equivalents
+    assert n == 30 and abs(value - 1.0) < 1e-12
 
 
 def test_density_matrix_bench_schedule_matches_reference(cirq):
