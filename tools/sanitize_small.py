@@ -36,7 +36,13 @@ def main():
         dev.marginal_probs([3, 11, 0])
         dev.sample_bits(list(range(n - 1, -1, -1)), rng.random_sample(500))
         dev.pauli_expectation(0b101, 0b110)
-        dev.reduced_density_matrix([5, 0, 9])
+        dev.reduced_density_matrix([5, 0, 9])  # 13 qubits, 3 kept bits: the one-read Gram kernel
+        dev.reduced_density_matrix([12, 1, 7, 3, 10])
+        dev.reduced_density_matrix([4, 11])  # the row-tile kernel
+        dev.pauli_expectations(0, [0b101, 1 << 12, (1 << 13) - 1])  # run kernel (>= 12 qubits), Z type
+        dev.pauli_expectations((1 << 12) | 3, list(range(1, 20)))  # ... with an X mask, two launches
+        other = dev.copy()
+        assert dev.allclose(other, 1e-6)
         dev.amplitudes([0, 5, 77])
         p = dev.marginal_probs([5])
         dev.collapse([5], [1], p[1] / p.sum())
@@ -52,6 +58,7 @@ def main():
             assert abs(big.norm2() - 1) < 1e-3
         a = DeviceState.basis(4, dtype, 3)
         b = a.kron(DeviceState.basis(3, dtype, 1))
+        assert b.kron_allclose(a, DeviceState.basis(3, dtype, 1), 1e-6)
         b.permute_bits([6, 5, 4, 3, 2, 1, 0][::-1])
         # batched trajectories: 2^4 states of 9 qubits
         t = DeviceState.from_numpy(np.ones(16, dtype=dtype), dtype).kron(DeviceState.basis(9, dtype, 0))
