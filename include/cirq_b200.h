@@ -174,7 +174,8 @@ int b2q_sv_pauli_expectation(const void* state, int dtype, int n_qubits, uint64_
  * over the state, 16 strings per launch: out_re_im[2t], [2t+1] = <psi| P_t |psi>.
  * A PauliSum's terms grouped by x_mask (all Z-type terms of a cost Hamiltonian have
  * x_mask = 0) cost one read of the state per group instead of one per term
- * (sim/sparse_simulator.py:193-218 evaluates ops/pauli_string.py:625-655 per term). */
+ * (sim/sparse_simulator.py:193-218 evaluates ops/pauli_string.py:625-655 per term).
+ * Sums are float64; synchronises the stream. */
 int b2q_sv_pauli_expectation_multi(const void* state, int dtype, int n_qubits, uint64_t x_mask,
                                    const uint64_t* z_masks, int count, double* out_re_im,
                                    void* stream);
@@ -185,7 +186,9 @@ int b2q_sv_pauli_expectation_multi(const void* state, int dtype, int n_qubits, u
  * qis/states.py:623-693 (density_matrix_from_state_vector) behind
  * StateVectorMixin.density_matrix_of / bloch_vector_of (sim/state_vector.py:109-167),
  * which the reference evaluates on a host copy of the state (and refuses above
- * 25 qubits).  Synchronises the stream. */
+ * 25 qubits).  One read of the state at any m (m >= 3 on >= 11 qubits: Gram
+ * products of shared-memory tiles, partial sums added in a fixed order, so two
+ * calls return identical bits).  Synchronises the stream. */
 int b2q_sv_reduced_density_matrix(const void* state, int dtype, int n_qubits, const int* bits,
                                   int m, double* out_c128, void* stream);
 
@@ -217,7 +220,9 @@ int b2q_sv_argmax_abs(const void* state, int dtype, int n_qubits, uint64_t* inde
 int b2q_sv_kron_allclose(const void* a, int na, const void* b, int nb, const void* t, int dtype,
                          double atol, double rtol, int* ok_out, void* stream);
 
-/* *ok_out = np.allclose(a, b, atol, rtol) for two states of n_qubits. */
+/* *ok_out = np.allclose(a, b, atol, rtol) for two states of n_qubits: true iff
+ * |a[i] - b[i]| <= atol + rtol * |b[i]| for every i (compared in float64; NaNs
+ * compare as close, unlike numpy).  Synchronises the stream. */
 int b2q_sv_allclose(const void* a, const void* b, int dtype, int n_qubits, double atol,
                     double rtol, int* ok_out, void* stream);
 
