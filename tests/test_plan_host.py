@@ -543,7 +543,8 @@ def test_pauli_run_plan_sign_decomposition_matches_the_oracle():
             i = np.arange(1 << n, dtype=np.int64)
             prod = (np.conj(psi[i ^ x]) * psi).reshape(-1, 8)  # pair products by run
             w = prod @ had.T  # w[r, m] = sum_j (-1)^popcount(j & m) prod[r, j]
-            for z in [int(v) for v in rng.integers(0, 1 << n, size=3)] + [(1 << n) - 1, 7, 1 << (n - 1)]:
+            zs = [int(v) for v in rng.integers(0, 1 << n, size=3)] + [(1 << n) - 1, 7, 1 << (n - 1)]
+            for z in zs if n <= 13 else zs[1:4:2]:  # (the 2^22 case costs a second per string)
                 col = w[:, z & 7].reshape(k_count, vt)  # [k][g]
                 if n <= 13:
                     flip = parity((np.arange(k_count, dtype=np.int64) * vt << 3) & z)
